@@ -1,0 +1,81 @@
+"""ctypes binding of libgwd_b200.so (the C ABI declared in include/gwd_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call
+fails, an exception is raised.  Build it with `python __graft_entry__.py build`
+(nvcc -gencode arch=compute_100a,code=sm_100a).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libgwd_b200.so")
+
+ACT_NONE, ACT_RELU, ACT_GELU, ACT_ELU, ACT_SIGMOID = 0, 1, 2, 3, 4
+RES_NONE, RES_BEFORE_NORM, RES_AFTER = 0, 1, 2
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int32
+c_i64 = ctypes.c_int64
+c_float = ctypes.c_float
+
+
+class GemmDesc(ctypes.Structure):
+    """struct gwd_gemm_desc (include/gwd_b200.h)"""
+    _fields_ = [
+        ("x", c_void_p), ("B", c_int), ("H", c_int), ("W", c_int),
+        ("x_cstride", c_int), ("x_coff", c_int), ("cin", c_int),
+        ("w", c_void_p), ("taps", c_int), ("n_pad", c_int), ("n", c_int),
+        ("bias", c_void_p), ("ln_g", c_void_p), ("ln_b", c_void_p), ("ln_eps", c_float),
+        ("pre_act", c_int), ("post_act", c_int), ("out_scale", c_float),
+        ("res", c_void_p), ("res_cstride", c_int), ("res_coff", c_int), ("res_mode", c_int),
+        ("y", c_void_p), ("y_cstride", c_int), ("y_coff", c_int), ("y_f32", c_int),
+        ("y_raw", c_void_p), ("yraw_cstride", c_int), ("yraw_coff", c_int),
+        ("store_n", c_int),
+    ]
+
+
+# name -> (restype, argtypes); must list every symbol of include/gwd_b200.h
+SIGNATURES = {
+    "gwd_last_error": (ctypes.c_char_p, []),
+    "gwd_version": (c_int, []),
+    "gwd_launch_count": (c_i64, []),
+    "gwd_reset_launch_count": (None, []),
+    "gwd_conv_gemm": (c_int, [ctypes.POINTER(GemmDesc), c_void_p]),
+}
+
+_lib = None
+
+
+class GwdError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load the shared library once; fail loudly when it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise GwdError(
+                "libgwd_b200.so is not built (%s). Run `python __graft_entry__.py build`; "
+                "there is no CPU or PyTorch fallback for the GW-Depth hot path." % LIB_PATH)
+        h = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(h, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = h
+    return _lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = lib().gwd_last_error()
+        raise GwdError("%s failed (%d): %s" % (what, status, msg.decode() if msg else ""))
+
+
+def launch_count():
+    return int(lib().gwd_launch_count())
+
+
+def reset_launch_count():
+    lib().gwd_reset_launch_count()

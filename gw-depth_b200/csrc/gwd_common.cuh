@@ -1,0 +1,84 @@
+// gwd_common.cuh -- shared host/device helpers for libgwd_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+#include "../../include/gwd_b200.h"
+
+// ----------------------------------------------------------------------------------------------
+// host side: error reporting + launch accounting
+// ----------------------------------------------------------------------------------------------
+void gwd_set_error(const char* fmt, ...);
+extern std::atomic<int64_t> g_gwd_launches;
+
+#define GWD_CHECK_ARG(cond, ...)            \
+  do {                                      \
+    if (!(cond)) {                          \
+      gwd_set_error(__VA_ARGS__);           \
+      return GWD_ERR_ARG;                   \
+    }                                       \
+  } while (0)
+
+#define GWD_CUDA(call)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      gwd_set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return GWD_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+#define GWD_LAUNCHED()                                                                   \
+  do {                                                                                   \
+    g_gwd_launches.fetch_add(1, std::memory_order_relaxed);                              \
+    cudaError_t e__ = cudaGetLastError();                                                \
+    if (e__ != cudaSuccess) {                                                            \
+      gwd_set_error("kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), __FILE__, __LINE__); \
+      return GWD_ERR_CUDA;                                                               \
+    }                                                                                    \
+  } while (0)
+
+int gwd_num_sms();
+
+static inline int64_t gwd_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ----------------------------------------------------------------------------------------------
+// device side: activations, packing, warp reductions
+// ----------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float gwd_apply_act(float v, int act) {
+  switch (act) {
+    case GWD_ACT_RELU: return fmaxf(v, 0.f);
+    case GWD_ACT_GELU: return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+    case GWD_ACT_ELU: return v > 0.f ? v : expm1f(v);
+    case GWD_ACT_SIGMOID: return 1.f / (1.f + __expf(-v));
+    default: return v;
+  }
+}
+
+__device__ __forceinline__ uint32_t gwd_pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+__device__ __forceinline__ float2 gwd_unpack_bf16x2(uint32_t u) {
+  __nv_bfloat162 t = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(t);
+}
+
+__device__ __forceinline__ float gwd_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ __forceinline__ float gwd_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+#endif  // __CUDACC__

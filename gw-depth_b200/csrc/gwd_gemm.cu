@@ -1,0 +1,622 @@
+// gwd_gemm.cu -- persistent, warp-specialised implicit-GEMM for sm_100a.
+//
+//   D[128 pixels, Nt] (fp32, TMEM) += A_tap[128, BK] (bf16, smem, K-major, swizzled) * W_tap[Nt, BK]^T
+//
+// One CTA per SM, looping over output tiles.  Roles:
+//   warp 0      : TMA producer  (cp.async.bulk.tensor 4D for activations, 3D for packed weights)
+//   warp 1      : MMA issuer    (tcgen05.mma.cta_group::1.kind::f16, one elected lane) + TMEM alloc
+//   warps 2..9  : epilogue      (tcgen05.ld -> bias / act / residual / LayerNorm / act -> global)
+// The fp32 accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main
+// loop of tile i+1.
+//
+// 3x3 convolutions (stride 1, zero pad 1) are tap-GEMMs: for each channel chunk and each dx the
+// producer loads ONE activation box of (TH+2) x TW pixels (TMA out-of-bounds zero fill provides
+// the padding) and the three dy taps are MMAs whose A descriptor start address is shifted by
+// dy*TW rows -- a multiple of 8 rows, so the shared-memory swizzle phase is preserved.  The
+// weights for (dx, dy=0..2) arrive as one 3D box.  Linear layers are the taps==1 special case
+// of the same kernel (W = rows, H = B = 1).
+//
+// Reference call sites replaced: see include/gwd_b200.h (gwd_conv_gemm).
+#include <cuda.h>
+#include "gwd_common.cuh"
+
+namespace {
+
+constexpr int kNumEpilogueWarps = 8;
+constexpr int kNumThreads = (2 + kNumEpilogueWarps) * 32;
+constexpr int kMaxStages = 8;
+constexpr int kTileM = 128;
+
+struct GemmParams {
+  int B, H, W;
+  int TW, TH, pad;
+  int tiles_x, tiles_y, m_tiles;
+  int n_tiles, Nt;
+  int kchunks, BK, nsub, ndx;
+  int x_coff;
+  int stages;
+  uint32_t a_stage_bytes, b_stage_bytes;  // 1024-aligned slot sizes
+  uint32_t a_tx_bytes, b_tx_bytes;        // bytes TMA actually delivers per stage
+  uint32_t a_dy_bytes, b_sub_bytes;
+  uint32_t layout_type;                   // UMMA smem descriptor layout: 2=SW128 4=SW64 6=SW32
+  uint32_t sbo_bytes;                     // 8 rows * row bytes
+  uint32_t idesc;
+  uint32_t acc_stride;                    // TMEM columns between the two accumulators
+  uint32_t tmem_cols;
+  int n, n_pad, store_n;
+  const float* bias;
+  const float* ln_g;
+  const float* ln_b;
+  float ln_eps;
+  int pre_act, post_act;
+  float out_scale;
+  const __nv_bfloat16* res;
+  int res_cstride, res_coff, res_mode;
+  void* y;
+  int y_cstride, y_coff, y_f32;
+  __nv_bfloat16* y_raw;
+  int yraw_cstride, yraw_coff;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  uint32_t done = 0;
+  uint32_t spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    // watchdog: a protocol bug must fault, never hang the box (try_wait itself sleeps in HW)
+    if (++spins > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
+                                            int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, swizzled UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor bit layout):
+// [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major, 1) | [32,46) SBO>>4 | [46,48) version=1 |
+// [61,64) layout type
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(layout_type & 7u) << 61;
+  return d;
+}
+
+struct TileCoord {
+  int b, y0, x0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) {
+  TileCoord t;
+  int nt = tile % p.n_tiles;
+  int mt = tile / p.n_tiles;
+  int per_img = p.tiles_x * p.tiles_y;
+  t.b = mt / per_img;
+  int r = mt - t.b * per_img;
+  int ty = r / p.tiles_x;
+  int tx = r - ty * p.tiles_x;
+  t.y0 = ty * p.TH;
+  t.x0 = tx * p.TW;
+  t.n0 = nt * p.Nt;
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// epilogue helpers: one thread owns one output pixel (one TMEM lane)
+// ---------------------------------------------------------------------------------------------
+struct RowCtx {
+  bool valid;
+  int64_t pix;  // linear pixel index (b*H + y)*W + x
+};
+
+// loads 16 accumulator columns starting at chunk c0 (relative to tile) and applies bias/pre_act/res(before)
+__device__ __forceinline__ void load_chunk(const GemmParams& p, uint32_t taddr, int n_base, const RowCtx& rc,
+                                           float (&v)[16]) {
+  uint32_t r[16];
+  tmem_ld16(taddr, r);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+  if (p.bias != nullptr) {
+    const float4* bp = reinterpret_cast<const float4*>(p.bias + n_base);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float4 b4 = __ldg(bp + i);
+      v[4 * i + 0] += b4.x;
+      v[4 * i + 1] += b4.y;
+      v[4 * i + 2] += b4.z;
+      v[4 * i + 3] += b4.w;
+    }
+  }
+  if (p.pre_act != GWD_ACT_NONE) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = gwd_apply_act(v[i], p.pre_act);
+  }
+  if (p.res_mode == GWD_RES_BEFORE_NORM && rc.valid) {
+    const uint4* rp = reinterpret_cast<const uint4*>(p.res + rc.pix * p.res_cstride + p.res_coff + n_base);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      uint4 u = __ldg(rp + h);
+      float2 f0 = gwd_unpack_bf16x2(u.x), f1 = gwd_unpack_bf16x2(u.y), f2 = gwd_unpack_bf16x2(u.z),
+             f3 = gwd_unpack_bf16x2(u.w);
+      v[8 * h + 0] += f0.x; v[8 * h + 1] += f0.y; v[8 * h + 2] += f1.x; v[8 * h + 3] += f1.y;
+      v[8 * h + 4] += f2.x; v[8 * h + 5] += f2.y; v[8 * h + 6] += f3.x; v[8 * h + 7] += f3.y;
+    }
+  }
+}
+
+__device__ __forceinline__ void store_bf16_16(__nv_bfloat16* dst, const float (&v)[16], int n_base, int store_n) {
+  // dst points at channel n_base of this pixel; channel counts are multiples of 8
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (n_base + 8 * h + 8 <= store_n) {
+      uint4 u;
+      u.x = gwd_pack_bf16x2(v[8 * h + 0], v[8 * h + 1]);
+      u.y = gwd_pack_bf16x2(v[8 * h + 2], v[8 * h + 3]);
+      u.z = gwd_pack_bf16x2(v[8 * h + 4], v[8 * h + 5]);
+      u.w = gwd_pack_bf16x2(v[8 * h + 6], v[8 * h + 7]);
+      *reinterpret_cast<uint4*>(dst + 8 * h) = u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kNumThreads, 1)
+gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                   const __grid_constant__ GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment is required by SWIZZLE_128B; do not trust the declared alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + static_cast<size_t>(p.stages) * p.a_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + static_cast<size_t>(p.stages) * p.b_stage_bytes);
+  uint64_t* full_bar = bars;                      // [stages]
+  uint64_t* empty_bar = bars + kMaxStages;        // [stages]
+  uint64_t* tmem_full = bars + 2 * kMaxStages;    // [2]
+  uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], kNumEpilogueWarps);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                 "r"(p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        TileCoord t = decode_tile(p, tile);
+        for (int kc = 0; kc < p.kchunks; ++kc) {
+          for (int dx = 0; dx < p.ndx; ++dx) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes + p.b_tx_bytes);
+            tma_load_4d(smem_a + static_cast<size_t>(stage) * p.a_stage_bytes, &map_a, &full_bar[stage],
+                        p.x_coff + kc * p.BK, t.x0 + dx - p.pad, t.y0 - p.pad, t.b);
+            tma_load_3d(smem_b + static_cast<size_t>(stage) * p.b_stage_bytes, &map_b, &full_bar[stage],
+                        kc * p.BK, t.n0, dx * p.nsub);
+            if (++stage == p.stages) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const int ksteps = p.BK / 16;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * p.acc_stride;
+        uint32_t accumulate = 0;
+        for (int it = 0; it < p.kchunks * p.ndx; ++it) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t a_base = smem_u32(smem_a + static_cast<size_t>(stage) * p.a_stage_bytes);
+          const uint32_t b_base = smem_u32(smem_b + static_cast<size_t>(stage) * p.b_stage_bytes);
+          for (int sub = 0; sub < p.nsub; ++sub) {
+            for (int k = 0; k < ksteps; ++k) {
+              uint64_t adesc = make_smem_desc(a_base + sub * p.a_dy_bytes + k * 32, p.sbo_bytes, p.layout_type);
+              uint64_t bdesc = make_smem_desc(b_base + sub * p.b_sub_bytes + k * 32, p.sbo_bytes, p.layout_type);
+              umma_bf16(d_tmem, adesc, bdesc, p.idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (++stage == p.stages) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int ew = warp - 2;
+    const int quad = warp & 3;   // TMEM lane quarter this warp may touch
+    const int half = ew >> 2;    // which half of the tile's columns this warp stores
+    const int row = quad * 32 + lane;
+    const int nchunks = p.Nt / 16;
+    const int c_begin = half == 0 ? 0 : (nchunks + 1) / 2;
+    const int c_end = half == 0 ? (nchunks + 1) / 2 : nchunks;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      TileCoord t = decode_tile(p, tile);
+      RowCtx rc;
+      {
+        int py = t.y0 + row / p.TW;
+        int px = t.x0 + row % p.TW;
+        rc.valid = (py < p.H) && (px < p.W);
+        rc.pix = (static_cast<int64_t>(t.b) * p.H + py) * p.W + px;
+      }
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc) * p.acc_stride +
+                             (static_cast<uint32_t>(quad * 32) << 16);
+
+      float mean = 0.f, rstd = 1.f;
+      if (p.ln_g != nullptr) {
+        // statistics over the n logical channels of this pixel (both halves read the whole row)
+        float s = 0.f, ss = 0.f;
+        for (int c = 0; c < nchunks; ++c) {
+          float v[16];
+          load_chunk(p, t_row + c * 16, t.n0 + c * 16, rc, v);
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (t.n0 + c * 16 + i < p.n) {
+              s += v[i];
+              ss += v[i] * v[i];
+            }
+          }
+        }
+        mean = s / static_cast<float>(p.n);
+        float var = fmaxf(ss / static_cast<float>(p.n) - mean * mean, 0.f);
+        rstd = rsqrtf(var + p.ln_eps);
+      }
+
+      for (int c = c_begin; c < c_end; ++c) {
+        const int n_base = t.n0 + c * 16;
+        float v[16];
+        load_chunk(p, t_row + c * 16, n_base, rc, v);
+        if (p.y_raw != nullptr && rc.valid) {
+          store_bf16_16(p.y_raw + rc.pix * p.yraw_cstride + p.yraw_coff + n_base, v, n_base, p.store_n);
+        }
+        if (p.ln_g != nullptr) {
+          const float4* gp = reinterpret_cast<const float4*>(p.ln_g + n_base);
+          const float4* bp = reinterpret_cast<const float4*>(p.ln_b + n_base);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float4 g4 = __ldg(gp + i), b4 = __ldg(bp + i);
+            v[4 * i + 0] = (v[4 * i + 0] - mean) * rstd * g4.x + b4.x;
+            v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * g4.y + b4.y;
+            v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * g4.z + b4.z;
+            v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * g4.w + b4.w;
+          }
+        }
+        if (p.post_act != GWD_ACT_NONE) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = gwd_apply_act(v[i], p.post_act);
+        }
+        if (p.out_scale != 1.f) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] *= p.out_scale;
+        }
+        if (p.res_mode == GWD_RES_AFTER && rc.valid) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + rc.pix * p.res_cstride + p.res_coff + n_base);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            if (n_base + 8 * h + 8 <= p.store_n) {
+              uint4 u = __ldg(rp + h);
+              float2 f0 = gwd_unpack_bf16x2(u.x), f1 = gwd_unpack_bf16x2(u.y), f2 = gwd_unpack_bf16x2(u.z),
+                     f3 = gwd_unpack_bf16x2(u.w);
+              v[8 * h + 0] += f0.x; v[8 * h + 1] += f0.y; v[8 * h + 2] += f1.x; v[8 * h + 3] += f1.y;
+              v[8 * h + 4] += f2.x; v[8 * h + 5] += f2.y; v[8 * h + 6] += f3.x; v[8 * h + 7] += f3.y;
+            }
+          }
+        }
+        // channels beyond the logical width are padding: keep them exactly zero
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (n_base + i >= p.n) v[i] = 0.f;
+        if (rc.valid) {
+          if (p.y_f32) {
+            float* dst = reinterpret_cast<float*>(p.y) + rc.pix * p.y_cstride + p.y_coff + n_base;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (n_base + i < p.store_n) dst[i] = v[i];
+          } else {
+            store_bf16_16(reinterpret_cast<__nv_bfloat16*>(p.y) + rc.pix * p.y_cstride + p.y_coff + n_base, v, n_base,
+                          p.store_n);
+          }
+        }
+      }
+      // release the accumulator
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1u;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) != cudaSuccess ||
+        qres != cudaDriverEntryPointSuccess)
+      return nullptr;
+    fn = reinterpret_cast<EncodeTiledFn>(sym);
+  }
+  return fn;
+}
+
+uint32_t pow2_at_least(uint32_t v, uint32_t lo) {
+  uint32_t r = lo;
+  while (r < v) r <<= 1;
+  return r;
+}
+
+}  // namespace
+
+extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GWD_CHECK_ARG(d != nullptr && d->x && d->w && d->y, "gwd_conv_gemm: null pointer");
+  GWD_CHECK_ARG(d->taps == 1 || d->taps == 9, "gwd_conv_gemm: taps must be 1 or 9 (got %d)", d->taps);
+  GWD_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0, "gwd_conv_gemm: empty input");
+  GWD_CHECK_ARG(d->cin > 0 && d->cin % 16 == 0, "gwd_conv_gemm: cin %% 16 != 0 (%d)", d->cin);
+  GWD_CHECK_ARG(d->n_pad > 0 && d->n_pad % 16 == 0 && d->n > 0 && d->n <= d->n_pad, "gwd_conv_gemm: bad n/n_pad");
+  GWD_CHECK_ARG(d->x_cstride % 8 == 0 && d->x_coff % 8 == 0 && d->x_coff + d->cin <= d->x_cstride,
+                "gwd_conv_gemm: bad x channel slice");
+  GWD_CHECK_ARG((reinterpret_cast<uintptr_t>(d->x) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->w) & 15) == 0,
+                "gwd_conv_gemm: x/w must be 16-byte aligned");
+  int store_n = d->store_n > 0 ? d->store_n : d->n;
+  GWD_CHECK_ARG(store_n <= d->n_pad, "gwd_conv_gemm: store_n > n_pad");
+  if (!d->y_f32)
+    GWD_CHECK_ARG(d->y_cstride % 8 == 0 && d->y_coff % 8 == 0 && store_n % 8 == 0 &&
+                      (reinterpret_cast<uintptr_t>(d->y) & 15) == 0,
+                  "gwd_conv_gemm: bf16 output needs 8-channel alignment");
+  if (d->res_mode != GWD_RES_NONE)
+    GWD_CHECK_ARG(d->res && d->res_cstride % 8 == 0 && d->res_coff % 8 == 0 &&
+                      (reinterpret_cast<uintptr_t>(d->res) & 15) == 0 && store_n % 8 == 0,
+                  "gwd_conv_gemm: bad residual");
+  if (d->y_raw)
+    GWD_CHECK_ARG(d->yraw_cstride % 8 == 0 && d->yraw_coff % 8 == 0 && store_n % 8 == 0, "gwd_conv_gemm: bad y_raw");
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.B = d->B; p.H = d->H; p.W = d->W;
+  const bool conv = d->taps == 9;
+  p.pad = conv ? 1 : 0;
+  p.nsub = conv ? 3 : 1;
+  p.ndx = conv ? 3 : 1;
+  // N tiling
+  int n_tiles = 1;
+  while (!(d->n_pad % n_tiles == 0 && (d->n_pad / n_tiles) % 16 == 0 && d->n_pad / n_tiles <= 256)) {
+    ++n_tiles;
+    GWD_CHECK_ARG(n_tiles <= d->n_pad, "gwd_conv_gemm: cannot tile n_pad=%d", d->n_pad);
+  }
+  p.n_tiles = n_tiles;
+  p.Nt = d->n_pad / n_tiles;
+  GWD_CHECK_ARG(d->ln_g == nullptr || n_tiles == 1, "gwd_conv_gemm: LayerNorm epilogue needs n_pad <= 256");
+  // M tiling: TW x TH = 128 pixels, TW a multiple of 8
+  if (!conv || d->H == 1) {
+    p.TW = 128; p.TH = 1;
+    GWD_CHECK_ARG(!conv, "gwd_conv_gemm: 3x3 conv needs H > 1");
+  } else {
+    const int cand[4][2] = {{16, 8}, {8, 16}, {32, 4}, {64, 2}};
+    int64_t best = -1;
+    for (int i = 0; i < 4; ++i) {
+      int64_t cover = gwd_ceil_div(d->W, cand[i][0]) * cand[i][0] * gwd_ceil_div(d->H, cand[i][1]) * cand[i][1];
+      if (best < 0 || cover < best) {
+        best = cover; p.TW = cand[i][0]; p.TH = cand[i][1];
+      }
+    }
+  }
+  p.tiles_x = static_cast<int>(gwd_ceil_div(d->W, p.TW));
+  p.tiles_y = static_cast<int>(gwd_ceil_div(d->H, p.TH));
+  p.m_tiles = p.tiles_x * p.tiles_y * d->B;
+  // K chunking
+  p.BK = (d->cin % 64 == 0) ? 64 : (d->cin % 32 == 0) ? 32 : 16;
+  const int a_rows = (p.TH + 2 * p.pad) * p.TW;
+  auto round1k = [](uint32_t v) { return (v + 1023u) & ~1023u; };
+  const uint32_t budget = 200 * 1024;
+  while (true) {
+    p.a_tx_bytes = static_cast<uint32_t>(a_rows) * p.BK * 2;
+    p.b_tx_bytes = static_cast<uint32_t>(p.nsub) * p.Nt * p.BK * 2;
+    p.a_stage_bytes = round1k(p.a_tx_bytes);
+    p.b_stage_bytes = round1k(p.b_tx_bytes);
+    if ((p.a_stage_bytes + p.b_stage_bytes) * 3 <= budget || p.BK == 16) break;
+    p.BK /= 2;  // keep at least 3 stages in flight
+  }
+  p.kchunks = d->cin / p.BK;
+  p.stages = static_cast<int>(budget / (p.a_stage_bytes + p.b_stage_bytes));
+  if (p.stages > kMaxStages) p.stages = kMaxStages;
+  GWD_CHECK_ARG(p.stages >= 2, "gwd_conv_gemm: tile does not fit shared memory");
+  const uint32_t row_bytes = p.BK * 2;
+  p.layout_type = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
+  p.sbo_bytes = 8 * row_bytes;
+  p.a_dy_bytes = static_cast<uint32_t>(p.TW) * row_bytes;
+  p.b_sub_bytes = static_cast<uint32_t>(p.Nt) * row_bytes;
+  // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 @17, M>>4 @24
+  p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.Nt >> 3) << 17) |
+            (static_cast<uint32_t>(kTileM >> 4) << 24);
+  p.acc_stride = (static_cast<uint32_t>(p.Nt) + 31u) & ~31u;
+  p.tmem_cols = pow2_at_least(2 * p.acc_stride, 32);
+  p.x_coff = d->x_coff;
+  p.n = d->n; p.n_pad = d->n_pad; p.store_n = store_n;
+  p.bias = d->bias; p.ln_g = d->ln_g; p.ln_b = d->ln_b; p.ln_eps = d->ln_eps;
+  p.pre_act = d->pre_act; p.post_act = d->post_act; p.out_scale = d->out_scale;
+  p.res = static_cast<const __nv_bfloat16*>(d->res);
+  p.res_cstride = d->res_cstride; p.res_coff = d->res_coff; p.res_mode = d->res_mode;
+  p.y = d->y; p.y_cstride = d->y_cstride; p.y_coff = d->y_coff; p.y_f32 = d->y_f32;
+  p.y_raw = static_cast<__nv_bfloat16*>(d->y_raw);
+  p.yraw_cstride = d->yraw_cstride; p.yraw_coff = d->yraw_coff;
+
+  EncodeTiledFn encode = get_encode_fn();
+  if (encode == nullptr) {
+    gwd_set_error("cuTensorMapEncodeTiled entry point not available");
+    return GWD_ERR_CUDA;
+  }
+  const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                 : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                   : CU_TENSOR_MAP_SWIZZLE_32B;
+  CUtensorMap map_a, map_b;
+  {
+    cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d->x_cstride), static_cast<cuuint64_t>(d->W),
+                          static_cast<cuuint64_t>(d->H), static_cast<cuuint64_t>(d->B)};
+    cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d->x_cstride) * 2, static_cast<cuuint64_t>(d->W) * d->x_cstride * 2,
+                          static_cast<cuuint64_t>(d->H) * d->W * d->x_cstride * 2};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(p.BK), static_cast<cuuint32_t>(p.TW),
+                         static_cast<cuuint32_t>(p.TH + 2 * p.pad), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      gwd_set_error("cuTensorMapEncodeTiled(activation) failed: %d", static_cast<int>(r));
+      return GWD_ERR_CUDA;
+    }
+  }
+  {
+    cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>(d->n_pad),
+                          static_cast<cuuint64_t>(d->taps)};
+    cuuint64_t gstr[2] = {static_cast<cuuint64_t>(d->cin) * 2, static_cast<cuuint64_t>(d->n_pad) * d->cin * 2};
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(p.BK), static_cast<cuuint32_t>(p.Nt),
+                         static_cast<cuuint32_t>(p.nsub)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->w), gdim, gstr, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      gwd_set_error("cuTensorMapEncodeTiled(weights) failed: %d", static_cast<int>(r));
+      return GWD_ERR_CUDA;
+    }
+  }
+
+  const size_t smem_bytes = 1024 + static_cast<size_t>(p.stages) * (p.a_stage_bytes + p.b_stage_bytes) +
+                            (2 * kMaxStages + 4) * sizeof(uint64_t) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GWD_CUDA(cudaFuncSetAttribute(gwd_tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  int grid = gwd_num_sms();
+  if (grid > total_tiles) grid = total_tiles;
+  gwd_tapgemm_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(map_a, map_b, p);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}

@@ -1,0 +1,130 @@
+"""GPU parity of gwd_conv_gemm (tcgen05/TMA implicit GEMM) against fp32 torch on bf16-rounded inputs."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import ops
+    return ops
+
+
+def _rand(shape, g, scale=1.0):
+    return (torch.randn(shape, generator=g) * scale)
+
+
+def _act(v, a):
+    return {0: lambda t: t, 1: F.relu, 2: F.gelu, 3: F.elu, 4: torch.sigmoid}[a](v)
+
+
+def _ref_epilogue(acc, bias, pre_act, res, res_mode, ln, post_act, scale, n):
+    v = acc + (bias if bias is not None else 0)
+    v = _act(v, pre_act)
+    if res_mode == 1:
+        v = v + res
+    if ln is not None:
+        v = F.layer_norm(v, (n,), ln[0], ln[1], 1e-5)
+    v = _act(v, post_act) * scale
+    if res_mode == 2:
+        v = v + res
+    return v
+
+
+LINEAR_CASES = [
+    # M, K, N, pre, post, res_mode, ln
+    (300, 256, 256, 0, 1, 0, False),
+    (1000, 256, 2048, 0, 1, 0, False),
+    (777, 2048, 256, 0, 0, 1, True),
+    (4800, 64, 192, 0, 2, 0, False),
+    (130, 512, 1536, 0, 0, 0, False),
+    (19200, 192, 64, 0, 0, 2, False),
+    (513, 80, 160, 0, 2, 0, True),
+    (100, 256, 6, 0, 4, 0, False),
+]
+
+
+@pytest.mark.parametrize("M,K,N,pre,post,res_mode,use_ln", LINEAR_CASES)
+def test_linear(M, K, N, pre, post, res_mode, use_ln):
+    ops = _ops()
+    g = torch.Generator().manual_seed(M * 7 + K + N)
+    x = _rand((M, K), g).bfloat16()
+    w = _rand((N, K), g, K ** -0.5).bfloat16()
+    b = _rand((N,), g, 0.5)
+    n8 = ops.round_up(N, 8)
+    res = _rand((M, n8), g).bfloat16() if res_mode else None
+    ln = (1 + 0.1 * _rand((N,), g), 0.1 * _rand((N,), g)) if use_ln else None
+    acc = x.float() @ w.float().t()
+    ref = _ref_epilogue(acc, b, pre, res.float()[:, :N] if res is not None else None, res_mode, ln, post, 1.0, N)
+
+    pw = ops.pack_linear(w.cuda(), b.cuda())
+    lnp = (ops.pad_vec(ln[0].cuda(), pw.n_pad), ops.pad_vec(ln[1].cuda(), pw.n_pad)) if use_ln else None
+    y = ops.conv_gemm(x.cuda(), pw, ln=lnp, pre_act=pre, post_act=post,
+                      res=res.cuda() if res is not None else None, res_mode=res_mode)
+    torch.cuda.synchronize()
+    got = y.float().cpu()[:, :N]
+    err = (got - ref).abs().max().item()
+    tol = 2e-2 * max(1.0, ref.abs().max().item())
+    assert err < tol, (err, tol)
+    if n8 > N:
+        assert (y.float().cpu()[:, N:] == 0).all()
+
+
+CONV_CASES = [
+    # B, H, W, C, N, pre, post, res_mode, ln
+    (2, 30, 40, 64, 64, 3, 0, 0, False),
+    (1, 24, 32, 160, 160, 0, 2, 0, True),
+    (2, 17, 23, 80, 80, 0, 2, 0, True),
+    (1, 16, 24, 160, 160, 0, 0, 2, True),
+    (1, 20, 28, 32, 32, 3, 0, 0, False),
+    (1, 12, 16, 320, 320, 0, 0, 0, False),
+    (1, 9, 13, 1024, 256, 0, 2, 0, False),
+    (3, 7, 10, 160, 160, 0, 2, 0, True),
+]
+
+
+@pytest.mark.parametrize("B,H,W,C,N,pre,post,res_mode,use_ln", CONV_CASES)
+def test_conv3x3(B, H, W, C, N, pre, post, res_mode, use_ln):
+    ops = _ops()
+    g = torch.Generator().manual_seed(B + H * 3 + W * 5 + C + N)
+    x = _rand((B, H, W, C), g).bfloat16()
+    w = _rand((N, C, 3, 3), g, (9 * C) ** -0.5).bfloat16()
+    b = _rand((N,), g, 0.5)
+    res = _rand((B, H, W, N), g).bfloat16() if res_mode else None
+    ln = (1 + 0.1 * _rand((N,), g), 0.1 * _rand((N,), g)) if use_ln else None
+    acc = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, 1, 1).permute(0, 2, 3, 1)
+    ref = _ref_epilogue(acc, b, pre, res.float() if res is not None else None, res_mode, ln, post, 1.0, N)
+
+    pw = ops.pack_conv3x3(w.cuda(), b.cuda())
+    lnp = (ops.pad_vec(ln[0].cuda(), pw.n_pad), ops.pad_vec(ln[1].cuda(), pw.n_pad)) if use_ln else None
+    y = ops.conv_gemm(x.cuda(), pw, ln=lnp, pre_act=pre, post_act=post,
+                      res=res.cuda() if res is not None else None, res_mode=res_mode)
+    torch.cuda.synchronize()
+    got = y.float().cpu()
+    err = (got - ref).abs().max().item()
+    tol = 2e-2 * max(1.0, ref.abs().max().item())
+    assert err < tol, (err, tol)
+
+
+def test_channel_slices_and_f32_out():
+    ops = _ops()
+    g = torch.Generator().manual_seed(5)
+    x = _rand((2, 10, 12, 96), g).bfloat16()
+    w = _rand((2, 32, 3, 3), g, 0.1).bfloat16()
+    acc = F.conv2d(x.float()[..., 32:64].permute(0, 3, 1, 2), w.float(), None, 1, 1).permute(0, 2, 3, 1)
+    pw = ops.pack_conv3x3(w.cuda())
+    y = ops.conv_gemm(x.cuda(), pw, x_coff=32, out_f32=True, bias=False)
+    torch.cuda.synchronize()
+    assert y.shape[-1] == 2
+    assert (y.cpu() - acc).abs().max().item() < 2e-2
+    # write into a channel slice of a wider bf16 buffer
+    w2 = _rand((16, 32, 3, 3), g, 0.1).bfloat16()
+    acc2 = F.conv2d(x.float()[..., 64:96].permute(0, 3, 1, 2), w2.float(), None, 1, 1).permute(0, 2, 3, 1)
+    buf = torch.zeros(2, 10, 12, 48, dtype=torch.bfloat16, device="cuda")
+    ops.conv_gemm(x.cuda(), ops.pack_conv3x3(w2.cuda()), x_coff=64, out=buf, y_coff=16, bias=False)
+    torch.cuda.synchronize()
+    got = buf.float().cpu()
+    assert (got[..., 16:32] - acc2).abs().max().item() < 3e-2
+    assert (got[..., :16] == 0).all() and (got[..., 32:] == 0).all()
