@@ -30,17 +30,51 @@ class GemmDesc(ctypes.Structure):
         ("res", c_void_p), ("res_cstride", c_int), ("res_coff", c_int), ("res_mode", c_int),
         ("y", c_void_p), ("y_cstride", c_int), ("y_coff", c_int), ("y_f32", c_int),
         ("y_raw", c_void_p), ("yraw_cstride", c_int), ("yraw_coff", c_int),
-        ("store_n", c_int),
+        ("store_n", c_int), ("w_per_image", c_int),
     ]
 
 
+class AttnDesc(ctypes.Structure):
+    """struct gwd_attn_desc (include/gwd_b200.h)"""
+    _fields_ = [
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("o", c_void_p),
+        ("items", c_int), ("heads", c_int), ("Lq", c_int), ("Lk", c_int), ("hd", c_int),
+        ("q_item_stride", c_i64), ("q_row_stride", c_i64), ("k_item_stride", c_i64), ("k_row_stride", c_i64),
+        ("v_item_stride", c_i64), ("v_row_stride", c_i64), ("o_item_stride", c_i64), ("o_row_stride", c_i64),
+        ("bias", c_void_p), ("mask", c_void_p), ("mask_windows", c_int), ("key_padding", c_void_p),
+        ("scale", c_float),
+    ]
+
+
+P, I, L, F_ = c_void_p, c_int, c_i64, c_float
 # name -> (restype, argtypes); must list every symbol of include/gwd_b200.h
 SIGNATURES = {
     "gwd_last_error": (ctypes.c_char_p, []),
     "gwd_version": (c_int, []),
     "gwd_launch_count": (c_i64, []),
     "gwd_reset_launch_count": (None, []),
-    "gwd_conv_gemm": (c_int, [ctypes.POINTER(GemmDesc), c_void_p]),
+    "gwd_conv_gemm": (c_int, [ctypes.POINTER(GemmDesc), P]),
+    "gwd_attention": (c_int, [ctypes.POINTER(AttnDesc), P]),
+    "gwd_token_attention": (c_int, [P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, F_, P]),
+    "gwd_ref_scores": (c_int, [P, L, P, L, P, I, I, I, I, I, I, F_, P]),
+    "gwd_ref_diffuse": (c_int, [P, P, P, P, I, I, I, I, P]),
+    "gwd_ref_requery": (c_int, [P, P, L, P, L, I, I, I, I, I, I, F_, P]),
+    "gwd_layernorm": (c_int, [P, L, P, L, P, P, F_, I, P, L, L, I, I, P]),
+    "gwd_add_rows": (c_int, [P, L, P, L, L, P, L, L, I, P]),
+    "gwd_window_gather": (c_int, [P, L, P, P, F_, P, L, I, I, I, I, I, I, I, P]),
+    "gwd_window_merge": (c_int, [P, L, P, L, P, L, P, P, F_, P, L, I, I, I, I, I, I, I, P]),
+    "gwd_upsample_nearest": (c_int, [P, L, I, I, I, P, L, I, I, I, P, L, P]),
+    "gwd_avgpool": (c_int, [P, L, I, I, I, I, P, L, I, P]),
+    "gwd_bilinear_up": (c_int, [P, L, I, I, I, P, L, I, I, I, P]),
+    "gwd_sample_bilinear": (c_int, [P, L, I, P, I, I, I, I, P, I, P, P]),
+    "gwd_sample_scalar": (c_int, [P, I, I, I, P, I, P, P]),
+    "gwd_line_ref_gather": (c_int, [P, L, P, P, I, P, L, I, I, I, I, I, I, P]),
+    "gwd_anchor_mix": (c_int, [P, L, P, I, L, I, P, P]),
+    "gwd_nchw_to_nhwc": (c_int, [P, I, I, L, P, I, P]),
+    "gwd_certain_sample": (c_int, [P, I, I, P, I, I, I, I, ctypes.POINTER(c_float), I, P, P, P]),
+    "gwd_match_cost": (c_int, [P, P, P, P, P, I, I, I, I, F_, F_, P, P, P]),
+    "gwd_depth_metrics": (c_int, [P, P, I, L, F_, F_, P, P, P]),
+    "gwd_silog_sums": (c_int, [P, I, I, I, P, I, I, F_, F_, I, P, P]),
 }
 
 _lib = None

@@ -1,0 +1,577 @@
+// gwd_elem.cu -- bandwidth-bound kernels of the GW-Depth forward: LayerNorm, row-broadcast add, the Swin
+// window gather / merge (LayerNorm + pad + cyclic shift + partition folded into one pass each way),
+// nearest / bilinear resampling, average pooling, point sampling and the anchor-mixture depth read-out.
+// All activations are channels-last bf16; statistics and small depth maps are fp32.
+// One warp owns one token (pixel) row: 16-byte vector loads, shuffle reductions, no shared memory.
+#include "gwd_common.cuh"
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+constexpr int kMaxVec = 8;  // a warp covers up to 32 lanes * 8 vectors * 8 channels = 2048 channels
+
+__device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = gwd_unpack_bf16x2(u.x), b = gwd_unpack_bf16x2(u.y), c = gwd_unpack_bf16x2(u.z), d = gwd_unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = gwd_pack_bf16x2(f[0], f[1]); u.y = gwd_pack_bf16x2(f[2], f[3]);
+  u.z = gwd_pack_bf16x2(f[4], f[5]); u.w = gwd_pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// row held by a warp: vector v of lane l covers channels (v*32 + l)*8 .. +8
+struct WarpRow {
+  float f[kMaxVec][8];
+};
+
+__device__ __forceinline__ void row_load(WarpRow& r, const bf16* src, int C, int lane, bool valid) {
+#pragma unroll
+  for (int v = 0; v < kMaxVec; ++v) {
+    int c = (v * 32 + lane) * 8;
+    if (c < C && valid) load8(src + c, r.f[v]);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r.f[v][i] = 0.f;
+    }
+  }
+}
+__device__ __forceinline__ void row_add(WarpRow& r, const bf16* src, int C, int lane) {
+#pragma unroll
+  for (int v = 0; v < kMaxVec; ++v) {
+    int c = (v * 32 + lane) * 8;
+    if (c < C) {
+      float t[8];
+      load8(src + c, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r.f[v][i] += t[i];
+    }
+  }
+}
+__device__ __forceinline__ void row_store(const WarpRow& r, bf16* dst, int C, int lane) {
+#pragma unroll
+  for (int v = 0; v < kMaxVec; ++v) {
+    int c = (v * 32 + lane) * 8;
+    if (c < C) store8(dst + c, r.f[v]);
+  }
+}
+// LayerNorm over the first n channels (channels >= n are padding and come out as 0)
+__device__ __forceinline__ void row_layernorm(WarpRow& r, int C, int n, int lane, const float* g, const float* b, float eps) {
+  float s = 0.f;
+#pragma unroll
+  for (int v = 0; v < kMaxVec; ++v) {
+    int c = (v * 32 + lane) * 8;
+    if (c < C) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (c + i < n) s += r.f[v][i];
+    }
+  }
+  float mean = gwd_warp_sum(s) / n;
+  float ss = 0.f;
+#pragma unroll
+  for (int v = 0; v < kMaxVec; ++v) {
+    int c = (v * 32 + lane) * 8;
+    if (c < C) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (c + i < n) { float dlt = r.f[v][i] - mean; ss += dlt * dlt; }
+    }
+  }
+  float rstd = rsqrtf(gwd_warp_sum(ss) / n + eps);
+#pragma unroll
+  for (int v = 0; v < kMaxVec; ++v) {
+    int c = (v * 32 + lane) * 8;
+    if (c < C) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r.f[v][i] = (c + i < n) ? (r.f[v][i] - mean) * rstd * g[c + i] + b[c + i] : 0.f;
+    }
+  }
+}
+__device__ __forceinline__ void row_act(WarpRow& r, int act) {
+  if (act == GWD_ACT_NONE) return;
+#pragma unroll
+  for (int v = 0; v < kMaxVec; ++v)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r.f[v][i] = gwd_apply_act(r.f[v][i], act);
+}
+
+// ------------------------------------------------------------------------------------------------
+// out[row] = act(LN(x[row] + res[row]))     (res, LN optional)
+// ------------------------------------------------------------------------------------------------
+__global__ void gwd_layernorm_kernel(const bf16* x, int64_t x_rs, const bf16* res, int64_t res_rs, const float* g,
+                                     const float* b, float eps, int act, bf16* out, int64_t out_rs, int64_t rows, int C,
+                                     int n) {
+  int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  WarpRow r;
+  row_load(r, x + row * x_rs, C, lane, true);
+  if (res) row_add(r, res + row * res_rs, C, lane);
+  if (g) row_layernorm(r, C, n, lane, g, b, eps);
+  row_act(r, act);
+  row_store(r, out + row * out_rs, C, lane);
+}
+
+// out[row] = x[row] + addend[row % period]
+__global__ void gwd_add_rows_kernel(const bf16* x, int64_t x_rs, const bf16* addend, int64_t a_rs, int64_t period,
+                                    bf16* out, int64_t out_rs, int64_t rows, int C) {
+  int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  WarpRow r;
+  row_load(r, x + row * x_rs, C, lane, true);
+  row_add(r, addend + (row % period) * a_rs, C, lane);
+  row_store(r, out + row * out_rs, C, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Swin window gather: out[(b*nW + w)*N + t] = LN(x[b, y, x]) (0 in the bottom/right padding), where the window
+// grid lives on the cyclically shifted, padded map (multiscale_transformerr.py:659-707)
+// ------------------------------------------------------------------------------------------------
+struct WinGeom {
+  int B, H, W, Hp, Wp, ws, shift;
+};
+__device__ __forceinline__ bool win_source(const WinGeom& gm, int64_t orow, int& b, int& y, int& x) {
+  int N = gm.ws * gm.ws;
+  int nWx = gm.Wp / gm.ws, nWy = gm.Hp / gm.ws;
+  int t = orow % N;
+  int64_t wi = orow / N;
+  int w = wi % (nWx * nWy);
+  b = wi / (nWx * nWy);
+  int ys = (w / nWx) * gm.ws + t / gm.ws;
+  int xs = (w % nWx) * gm.ws + t % gm.ws;
+  y = (ys + gm.shift) % gm.Hp;
+  x = (xs + gm.shift) % gm.Wp;
+  return y < gm.H && x < gm.W;
+}
+__global__ void gwd_window_gather_kernel(const bf16* x, int64_t x_rs, const float* g, const float* b, float eps, bf16* out,
+                                         int64_t out_rs, WinGeom gm, int C, int n) {
+  int64_t orow = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int64_t rows = static_cast<int64_t>(gm.B) * gm.Hp * gm.Wp;
+  if (orow >= rows) return;
+  int bb, y, xx;
+  bool valid = win_source(gm, orow, bb, y, xx);
+  WarpRow r;
+  row_load(r, x + ((static_cast<int64_t>(bb) * gm.H + y) * gm.W + xx) * x_rs, C, lane, valid);
+  if (valid && g) row_layernorm(r, C, n, lane, g, b, eps);
+  row_store(r, out + orow * out_rs, C, lane);
+}
+
+// Swin window merge: y[b,y,x] = shortcut[b,y,x] + win[row(b,y,x)]; optionally y_ln = LN(y)   (:731-755)
+__global__ void gwd_window_merge_kernel(const bf16* win, int64_t win_rs, const bf16* shortcut, int64_t sc_rs, bf16* out,
+                                        int64_t out_rs, const float* g, const float* b, float eps, bf16* out_ln,
+                                        int64_t ln_rs, WinGeom gm, int C, int n) {
+  int64_t pix = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  int64_t rows = static_cast<int64_t>(gm.B) * gm.H * gm.W;
+  if (pix >= rows) return;
+  int x = pix % gm.W;
+  int y = (pix / gm.W) % gm.H;
+  int bb = pix / (static_cast<int64_t>(gm.W) * gm.H);
+  int ys = (y - gm.shift + gm.Hp) % gm.Hp, xs = (x - gm.shift + gm.Wp) % gm.Wp;
+  int nWx = gm.Wp / gm.ws, nWy = gm.Hp / gm.ws;
+  int64_t wrow = ((static_cast<int64_t>(bb) * nWy + ys / gm.ws) * nWx + xs / gm.ws) * (gm.ws * gm.ws) +
+                 (ys % gm.ws) * gm.ws + xs % gm.ws;
+  WarpRow r;
+  row_load(r, win + wrow * win_rs, C, lane, true);
+  row_add(r, shortcut + pix * sc_rs, C, lane);
+  row_store(r, out + pix * out_rs, C, lane);
+  if (out_ln) {
+    row_layernorm(r, C, n, lane, g, b, eps);
+    row_store(r, out_ln + pix * ln_rs, C, lane);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// resampling (8-channel vectors, one thread per output vector)
+// ------------------------------------------------------------------------------------------------
+// nearest (legacy F.interpolate(mode='nearest'): src = floor(dst * in / out)); optional add of a second same-size map
+__global__ void gwd_upsample_nearest_kernel(const bf16* x, int64_t x_rs, int B, int h, int w, bf16* out, int64_t out_rs,
+                                            int H, int W, int C, const bf16* add, int64_t add_rs) {
+  int cv = C / 8;
+  int64_t total = static_cast<int64_t>(B) * H * W * cv;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int c = (idx % cv) * 8;
+    int64_t pix = idx / cv;
+    int X = pix % W;
+    int Y = (pix / W) % H;
+    int b = pix / (static_cast<int64_t>(W) * H);
+    int sy = min(static_cast<int>((static_cast<int64_t>(Y) * h) / H), h - 1);
+    int sx = min(static_cast<int>((static_cast<int64_t>(X) * w) / W), w - 1);
+    float f[8];
+    load8(x + ((static_cast<int64_t>(b) * h + sy) * w + sx) * x_rs + c, f);
+    if (add) {
+      float t[8];
+      load8(add + pix * add_rs + c, t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += t[i];
+    }
+    store8(out + pix * out_rs + c, f);
+  }
+}
+
+// nn.AvgPool2d(k, stride=k), floor mode
+__global__ void gwd_avgpool_kernel(const bf16* x, int64_t x_rs, int B, int H, int W, int k, bf16* out, int64_t out_rs,
+                                   int C) {
+  int cv = C / 8;
+  int oh = H / k, ow = W / k;
+  int64_t total = static_cast<int64_t>(B) * oh * ow * cv;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int c = (idx % cv) * 8;
+    int64_t pix = idx / cv;
+    int X = pix % ow;
+    int Y = (pix / ow) % oh;
+    int b = pix / (static_cast<int64_t>(ow) * oh);
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int dy = 0; dy < k; ++dy)
+      for (int dx = 0; dx < k; ++dx) {
+        float f[8];
+        load8(x + ((static_cast<int64_t>(b) * H + Y * k + dy) * W + X * k + dx) * x_rs + c, f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += f[i];
+      }
+    float inv = 1.f / (k * k);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= inv;
+    store8(out + pix * out_rs + c, acc);
+  }
+}
+
+// F.interpolate(mode='bilinear', align_corners=True)
+__global__ void gwd_bilinear_ac_kernel(const bf16* x, int64_t x_rs, int B, int h, int w, bf16* out, int64_t out_rs, int H,
+                                       int W, int C) {
+  int cv = C / 8;
+  int64_t total = static_cast<int64_t>(B) * H * W * cv;
+  float ry = (H > 1) ? static_cast<float>(h - 1) / (H - 1) : 0.f;
+  float rx = (W > 1) ? static_cast<float>(w - 1) / (W - 1) : 0.f;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int c = (idx % cv) * 8;
+    int64_t pix = idx / cv;
+    int X = pix % W;
+    int Y = (pix / W) % H;
+    int b = pix / (static_cast<int64_t>(W) * H);
+    float fy = ry * Y, fx = rx * X;
+    int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+    int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+    float ly = fy - y0, lx = fx - x0;
+    const bf16* base = x + static_cast<int64_t>(b) * h * w * x_rs + c;
+    float f00[8], f01[8], f10[8], f11[8], o[8];
+    load8(base + (static_cast<int64_t>(y0) * w + x0) * x_rs, f00);
+    load8(base + (static_cast<int64_t>(y0) * w + x1) * x_rs, f01);
+    load8(base + (static_cast<int64_t>(y1) * w + x0) * x_rs, f10);
+    load8(base + (static_cast<int64_t>(y1) * w + x1) * x_rs, f11);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      o[i] = (1.f - ly) * ((1.f - lx) * f00[i] + lx * f01[i]) + ly * ((1.f - lx) * f10[i] + lx * f11[i]);
+    store8(out + pix * out_rs + c, o);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// point sampling  (F.grid_sample, align_corners=False, zero padding)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float unnorm(float g, int size) { return ((g + 1.f) * size - 1.f) * 0.5f; }
+
+// bilinear sample of a bf16 map (+ an fp32 [H,W,C] table, e.g. the sine position code) at K points per image:
+// out fp32 [B,K,C]
+__global__ void gwd_sample_bilinear_kernel(const bf16* x, int64_t x_rs, int x_coff, const float* table, int B, int H, int W,
+                                           int C, const float* coords, int K, float* out) {
+  int64_t total = static_cast<int64_t>(B) * K * C;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int c = idx % C;
+    int k = (idx / C) % K;
+    int b = idx / (static_cast<int64_t>(C) * K);
+    float gx = coords[(static_cast<int64_t>(b) * K + k) * 2], gy = coords[(static_cast<int64_t>(b) * K + k) * 2 + 1];
+    float fx = unnorm(gx, W), fy = unnorm(gy, H);
+    int x0 = static_cast<int>(floorf(fx)), y0 = static_cast<int>(floorf(fy));
+    float lx = fx - x0, ly = fy - y0;
+    float acc = 0.f;
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        int xx = x0 + dx, yy = y0 + dy;
+        if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+        float wgt = (dx ? lx : 1.f - lx) * (dy ? ly : 1.f - ly);
+        float v = 0.f;
+        if (x) v += __bfloat162float(x[((static_cast<int64_t>(b) * H + yy) * W + xx) * x_rs + x_coff + c]);
+        if (table) v += table[(static_cast<int64_t>(yy) * W + xx) * C + c];
+        acc = fmaf(wgt, v, acc);
+      }
+    out[idx] = acc;
+  }
+}
+
+// bilinear sample of a single-channel fp32 map [B,H,W] at K points: out [B,K]
+__global__ void gwd_sample_scalar_kernel(const float* x, int B, int H, int W, const float* coords, int K, float* out) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * K) return;
+  int b = idx / K;
+  float fx = unnorm(coords[idx * 2], W), fy = unnorm(coords[idx * 2 + 1], H);
+  int x0 = static_cast<int>(floorf(fx)), y0 = static_cast<int>(floorf(fy));
+  float lx = fx - x0, ly = fy - y0, acc = 0.f;
+  for (int dy = 0; dy < 2; ++dy)
+    for (int dx = 0; dx < 2; ++dx) {
+      int xx = x0 + dx, yy = y0 + dy;
+      if (xx < 0 || xx >= W || yy < 0 || yy >= H) continue;
+      acc += (dx ? lx : 1.f - lx) * (dy ? ly : 1.f - ly) * x[(static_cast<int64_t>(b) * H + yy) * W + xx];
+    }
+  out[idx] = acc;
+}
+
+// reference tokens of the 1/32 line-window attention (multiscale_transformerr.py:676-701): nearest sample of the
+// windowed (LayerNorm'ed, padded, shifted) feature map + nearest sample of the shifted position table at R points.
+// win: [B*nW*N, C] (window layout produced by gwd_window_gather), pos: fp32 [H,W,C] (un-shifted), out bf16 [B,R,C]
+__global__ void gwd_line_ref_gather_kernel(const bf16* win, int64_t win_rs, const float* pos, const float* coords, int R,
+                                           bf16* out, int64_t out_rs, WinGeom gm, int C) {
+  int64_t wid = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  int lane = threadIdx.x & 31;
+  if (wid >= static_cast<int64_t>(gm.B) * R) return;
+  int b = wid / R;
+  float gx = coords[wid * 2], gy = coords[wid * 2 + 1];
+  if (gm.shift > 0) {  // roll the coordinates with the feature map, reflecting what crosses -1 (:680-684)
+    gx -= (static_cast<float>(gm.shift) / (gm.Wp - 1)) * 2.f;
+    gy -= (static_cast<float>(gm.shift) / (gm.Hp - 1)) * 2.f;
+    if (gx < -1.f) gx = -1.f - (1.f + gx);
+    if (gy < -1.f) gy = -1.f - (1.f + gy);
+  }
+  // feature sample on the padded, shifted map
+  int ix = static_cast<int>(nearbyintf(unnorm(gx, gm.Wp))), iy = static_cast<int>(nearbyintf(unnorm(gy, gm.Hp)));
+  bool fvalid = ix >= 0 && ix < gm.Wp && iy >= 0 && iy < gm.Hp;
+  int nWx = gm.Wp / gm.ws;
+  int64_t wrow = 0;
+  if (fvalid)
+    wrow = ((static_cast<int64_t>(b) * (gm.Hp / gm.ws) + iy / gm.ws) * nWx + ix / gm.ws) * (gm.ws * gm.ws) +
+           (iy % gm.ws) * gm.ws + ix % gm.ws;
+  // position sample on the un-padded, shifted table
+  int px = static_cast<int>(nearbyintf(unnorm(gx, gm.W))), py = static_cast<int>(nearbyintf(unnorm(gy, gm.H)));
+  bool pvalid = px >= 0 && px < gm.W && py >= 0 && py < gm.H;
+  int sy = pvalid ? (py + gm.shift) % gm.H : 0, sx = pvalid ? (px + gm.shift) % gm.W : 0;
+  for (int c = lane * 8; c < C; c += 256) {
+    float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (fvalid) load8(win + wrow * win_rs + c, f);
+    if (pvalid) {
+      const float* pp = pos + (static_cast<int64_t>(sy) * gm.W + sx) * C + c;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += pp[i];
+    }
+    store8(out + wid * out_rs + c, f);
+  }
+}
+
+// depth[p] = sum_k softmax_k(logits[p, :K]) * anchor[b, k]        (points_sample.py:277-279)
+__global__ void gwd_anchor_mix_kernel(const bf16* logits, int64_t l_rs, const float* anchor, int B, int64_t HW, int K,
+                                      float* out) {
+  int64_t pix = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  if (pix >= B * HW) return;
+  int b = pix / HW;
+  const bf16* row = logits + pix * l_rs;
+  const float* an = anchor + static_cast<int64_t>(b) * K;
+  float mx = -INFINITY;
+  for (int k = 0; k < K; k += 8) {
+    float f[8];
+    load8(row + k, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (k + i < K) mx = fmaxf(mx, f[i]);
+  }
+  float sum = 0.f, acc = 0.f;
+  for (int k = 0; k < K; k += 8) {
+    float f[8];
+    load8(row + k, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (k + i < K) {
+        float e = __expf(f[i] - mx);
+        sum += e;
+        acc = fmaf(e, an[k + i], acc);
+      }
+  }
+  out[pix] = acc / sum;
+}
+
+// image NCHW fp32 -> NHWC bf16 with channel padding (backbone stem input)  and  NHWC bf16 -> NCHW fp32 (outputs)
+__global__ void gwd_nchw_to_nhwc_kernel(const float* x, int B, int C, int64_t HW, bf16* out, int Cp) {
+  int64_t total = B * HW * Cp;
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int c = idx % Cp;
+    int64_t p = (idx / Cp) % HW;
+    int b = idx / (Cp * HW);
+    out[idx] = __float2bfloat16(c < C ? x[(static_cast<int64_t>(b) * C + c) * HW + p] : 0.f);
+  }
+}
+
+int grid_for(int64_t total, int threads) {
+  int64_t blocks = gwd_ceil_div(total, threads);
+  int64_t cap = static_cast<int64_t>(gwd_num_sms()) * 16;
+  return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
+}
+
+}  // namespace
+
+#define GWD_STREAM cudaStream_t stream = static_cast<cudaStream_t>(stream_)
+#define GWD_ALIGN8(v) ((v) % 8 == 0)
+
+extern "C" int gwd_layernorm(const void* x, int64_t x_rs, const void* res, int64_t res_rs, const float* gamma,
+                             const float* beta, float eps, int32_t act, void* out, int64_t out_rs, int64_t rows, int32_t C,
+                             int32_t n, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(x && out && rows > 0, "gwd_layernorm: null pointer / empty");
+  GWD_CHECK_ARG(GWD_ALIGN8(C) && C <= 2048 && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs) && GWD_ALIGN8(res_rs),
+                "gwd_layernorm: C and strides must be multiples of 8, C <= 2048");
+  gwd_layernorm_kernel<<<static_cast<unsigned>(gwd_ceil_div(rows * 32, 256)), 256, 0, stream>>>(
+      static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(res), res_rs, gamma, beta, eps, act,
+      static_cast<bf16*>(out), out_rs, rows, C, n);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_add_rows(const void* x, int64_t x_rs, const void* addend, int64_t a_rs, int64_t period, void* out,
+                            int64_t out_rs, int64_t rows, int32_t C, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(x && addend && out && rows > 0 && period > 0, "gwd_add_rows: bad argument");
+  GWD_CHECK_ARG(GWD_ALIGN8(C) && C <= 2048 && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs) && GWD_ALIGN8(a_rs),
+                "gwd_add_rows: alignment");
+  gwd_add_rows_kernel<<<static_cast<unsigned>(gwd_ceil_div(rows * 32, 256)), 256, 0, stream>>>(
+      static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(addend), a_rs, period, static_cast<bf16*>(out), out_rs,
+      rows, C);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+static int make_geom(WinGeom& gm, int B, int H, int W, int ws, int shift) {
+  gm.B = B; gm.H = H; gm.W = W; gm.ws = ws; gm.shift = shift;
+  gm.Hp = static_cast<int>(gwd_ceil_div(H, ws)) * ws;
+  gm.Wp = static_cast<int>(gwd_ceil_div(W, ws)) * ws;
+  return 0;
+}
+
+extern "C" int gwd_window_gather(const void* x, int64_t x_rs, const float* gamma, const float* beta, float eps, void* out,
+                                 int64_t out_rs, int32_t B, int32_t H, int32_t W, int32_t ws, int32_t shift, int32_t C,
+                                 int32_t n, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(x && out && ws > 0 && shift >= 0 && shift < ws, "gwd_window_gather: bad argument");
+  GWD_CHECK_ARG(GWD_ALIGN8(C) && C <= 2048 && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs), "gwd_window_gather: alignment");
+  WinGeom gm;
+  make_geom(gm, B, H, W, ws, shift);
+  int64_t rows = static_cast<int64_t>(B) * gm.Hp * gm.Wp;
+  gwd_window_gather_kernel<<<static_cast<unsigned>(gwd_ceil_div(rows * 32, 256)), 256, 0, stream>>>(
+      static_cast<const bf16*>(x), x_rs, gamma, beta, eps, static_cast<bf16*>(out), out_rs, gm, C, n);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_window_merge(const void* win, int64_t win_rs, const void* shortcut, int64_t sc_rs, void* out,
+                                int64_t out_rs, const float* gamma, const float* beta, float eps, void* out_ln,
+                                int64_t ln_rs, int32_t B, int32_t H, int32_t W, int32_t ws, int32_t shift, int32_t C,
+                                int32_t n, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(win && shortcut && out, "gwd_window_merge: null pointer");
+  GWD_CHECK_ARG(GWD_ALIGN8(C) && C <= 2048 && GWD_ALIGN8(win_rs) && GWD_ALIGN8(sc_rs) && GWD_ALIGN8(out_rs) &&
+                    GWD_ALIGN8(ln_rs),
+                "gwd_window_merge: alignment");
+  WinGeom gm;
+  make_geom(gm, B, H, W, ws, shift);
+  int64_t rows = static_cast<int64_t>(B) * H * W;
+  gwd_window_merge_kernel<<<static_cast<unsigned>(gwd_ceil_div(rows * 32, 256)), 256, 0, stream>>>(
+      static_cast<const bf16*>(win), win_rs, static_cast<const bf16*>(shortcut), sc_rs, static_cast<bf16*>(out), out_rs,
+      gamma, beta, eps, static_cast<bf16*>(out_ln), ln_rs, gm, C, n);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_upsample_nearest(const void* x, int64_t x_rs, int32_t B, int32_t h, int32_t w, void* out, int64_t out_rs,
+                                    int32_t H, int32_t W, int32_t C, const void* add, int64_t add_rs, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(x && out && GWD_ALIGN8(C) && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs) && GWD_ALIGN8(add_rs),
+                "gwd_upsample_nearest: bad argument");
+  int64_t total = static_cast<int64_t>(B) * H * W * (C / 8);
+  gwd_upsample_nearest_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, h, w,
+                                                                        static_cast<bf16*>(out), out_rs, H, W, C,
+                                                                        static_cast<const bf16*>(add), add_rs);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_avgpool(const void* x, int64_t x_rs, int32_t B, int32_t H, int32_t W, int32_t k, void* out,
+                           int64_t out_rs, int32_t C, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(x && out && k > 0 && H >= k && W >= k && GWD_ALIGN8(C) && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs),
+                "gwd_avgpool: bad argument");
+  int64_t total = static_cast<int64_t>(B) * (H / k) * (W / k) * (C / 8);
+  gwd_avgpool_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, H, W, k,
+                                                               static_cast<bf16*>(out), out_rs, C);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_bilinear_up(const void* x, int64_t x_rs, int32_t B, int32_t h, int32_t w, void* out, int64_t out_rs,
+                               int32_t H, int32_t W, int32_t C, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(x && out && GWD_ALIGN8(C) && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs), "gwd_bilinear_up: bad argument");
+  int64_t total = static_cast<int64_t>(B) * H * W * (C / 8);
+  gwd_bilinear_ac_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, h, w,
+                                                                   static_cast<bf16*>(out), out_rs, H, W, C);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_sample_bilinear(const void* x, int64_t x_rs, int32_t x_coff, const float* table, int32_t B, int32_t H,
+                                   int32_t W, int32_t C, const float* coords, int32_t K, float* out, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG((x || table) && coords && out, "gwd_sample_bilinear: null pointer");
+  int64_t total = static_cast<int64_t>(B) * K * C;
+  gwd_sample_bilinear_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, x_coff, table, B,
+                                                                       H, W, C, coords, K, out);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_sample_scalar(const float* x, int32_t B, int32_t H, int32_t W, const float* coords, int32_t K,
+                                 float* out, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(x && coords && out, "gwd_sample_scalar: null pointer");
+  gwd_sample_scalar_kernel<<<static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(B) * K, 128)), 128, 0, stream>>>(
+      x, B, H, W, coords, K, out);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_line_ref_gather(const void* win, int64_t win_rs, const float* pos, const float* coords, int32_t R,
+                                   void* out, int64_t out_rs, int32_t B, int32_t H, int32_t W, int32_t ws, int32_t shift,
+                                   int32_t C, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(win && pos && coords && out && GWD_ALIGN8(C) && GWD_ALIGN8(win_rs) && GWD_ALIGN8(out_rs),
+                "gwd_line_ref_gather: bad argument");
+  WinGeom gm;
+  make_geom(gm, B, H, W, ws, shift);
+  int64_t warps = static_cast<int64_t>(B) * R;
+  gwd_line_ref_gather_kernel<<<static_cast<unsigned>(gwd_ceil_div(warps * 32, 128)), 128, 0, stream>>>(
+      static_cast<const bf16*>(win), win_rs, pos, coords, R, static_cast<bf16*>(out), out_rs, gm, C);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_anchor_mix(const void* logits, int64_t l_rs, const float* anchor, int32_t B, int64_t HW, int32_t K,
+                              float* out, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(logits && anchor && out && GWD_ALIGN8(l_rs), "gwd_anchor_mix: bad argument");
+  gwd_anchor_mix_kernel<<<static_cast<unsigned>(gwd_ceil_div(B * HW, 256)), 256, 0, stream>>>(
+      static_cast<const bf16*>(logits), l_rs, anchor, B, HW, K, out);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_nchw_to_nhwc(const float* x, int32_t B, int32_t C, int64_t HW, void* out, int32_t Cp, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(x && out && Cp >= C, "gwd_nchw_to_nhwc: bad argument");
+  gwd_nchw_to_nhwc_kernel<<<grid_for(B * HW * Cp, 256), 256, 0, stream>>>(x, B, C, HW, static_cast<bf16*>(out), Cp);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}

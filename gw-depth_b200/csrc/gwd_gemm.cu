@@ -34,6 +34,7 @@ struct GemmParams {
   int n_tiles, Nt;
   int kchunks, BK, nsub, ndx;
   int x_coff;
+  int w_img_stride;  // taps when the weights are per image ([B][taps][n_pad][cin]), else 0
   int stages;
   uint32_t a_stage_bytes, b_stage_bytes;  // 1024-aligned slot sizes
   uint32_t a_tx_bytes, b_tx_bytes;        // bytes TMA actually delivers per stage
@@ -278,7 +279,7 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             tma_load_4d(smem_a + static_cast<size_t>(stage) * p.a_stage_bytes, &map_a, &full_bar[stage],
                         p.x_coff + kc * p.BK, t.x0 + dx - p.pad, t.y0 - p.pad, t.b);
             tma_load_3d(smem_b + static_cast<size_t>(stage) * p.b_stage_bytes, &map_b, &full_bar[stage],
-                        kc * p.BK, t.n0, dx * p.nsub);
+                        kc * p.BK, t.n0, dx * p.nsub + t.b * p.w_img_stride);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1u;
@@ -512,14 +513,14 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   p.Nt = d->n_pad / n_tiles;
   GWD_CHECK_ARG(d->ln_g == nullptr || n_tiles == 1, "gwd_conv_gemm: LayerNorm epilogue needs n_pad <= 256");
   // M tiling: TW x TH = 128 pixels, TW a multiple of 8
-  if (!conv || d->H == 1) {
+  if (!conv) {
     p.TW = 128; p.TH = 1;
-    GWD_CHECK_ARG(!conv, "gwd_conv_gemm: 3x3 conv needs H > 1");
   } else {
-    const int cand[4][2] = {{16, 8}, {8, 16}, {32, 4}, {64, 2}};
+    const int cand[5][2] = {{16, 8}, {8, 16}, {32, 4}, {64, 2}, {128, 1}};
     int64_t best = -1;
-    for (int i = 0; i < 4; ++i) {
-      int64_t cover = gwd_ceil_div(d->W, cand[i][0]) * cand[i][0] * gwd_ceil_div(d->H, cand[i][1]) * cand[i][1];
+    for (int i = 0; i < 5; ++i) {
+      // padded pixels covered by the tiling, plus the halo rows every tile re-reads
+      int64_t cover = gwd_ceil_div(d->W, cand[i][0]) * cand[i][0] * gwd_ceil_div(d->H, cand[i][1]) * (cand[i][1] + 2);
       if (best < 0 || cover < best) {
         best = cover; p.TW = cand[i][0]; p.TH = cand[i][1];
       }
@@ -556,6 +557,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   p.acc_stride = (static_cast<uint32_t>(p.Nt) + 31u) & ~31u;
   p.tmem_cols = pow2_at_least(2 * p.acc_stride, 32);
   p.x_coff = d->x_coff;
+  p.w_img_stride = d->w_per_image ? d->taps : 0;
   p.n = d->n; p.n_pad = d->n_pad; p.store_n = store_n;
   p.bias = d->bias; p.ln_g = d->ln_g; p.ln_b = d->ln_b; p.ln_eps = d->ln_eps;
   p.pre_act = d->pre_act; p.post_act = d->post_act; p.out_scale = d->out_scale;
@@ -592,7 +594,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   }
   {
     cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>(d->n_pad),
-                          static_cast<cuuint64_t>(d->taps)};
+                          static_cast<cuuint64_t>(d->taps) * (d->w_per_image ? d->B : 1)};
     cuuint64_t gstr[2] = {static_cast<cuuint64_t>(d->cin) * 2, static_cast<cuuint64_t>(d->n_pad) * d->cin * 2};
     cuuint32_t box[3] = {static_cast<cuuint32_t>(p.BK), static_cast<cuuint32_t>(p.Nt),
                          static_cast<cuuint32_t>(p.nsub)};

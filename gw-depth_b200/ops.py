@@ -92,7 +92,7 @@ def _as_bhwc(t):
 
 def conv_gemm(x, pw, *, x_coff=0, out=None, y_coff=0, out_channels=None, out_f32=False,
               bias=True, ln=None, ln_eps=1e-5, pre_act=ACT_NONE, post_act=ACT_NONE, out_scale=1.0,
-              res=None, res_coff=0, res_mode=RES_NONE, y_raw=None):
+              res=None, res_coff=0, res_mode=RES_NONE, y_raw=None, w_per_image=False):
     """y = epilogue(conv_or_linear(x[..., x_coff:x_coff+cin], pw)).  See include/gwd_b200.h.
 
     x      : bf16 channels-last [B,H,W,Cx] or [rows,Cx] / [B,L,Cx]
@@ -106,7 +106,9 @@ def conv_gemm(x, pw, *, x_coff=0, out=None, y_coff=0, out_channels=None, out_f32
     taps = pw.taps
     if taps == 9:
         assert x.dim() == 4
-    store_n = round_up(pw.n, 8) if not out_f32 else pw.n
+    # bf16 outputs carry all n_pad physical channels (pads are written as exact zeros) so that the next layer can
+    # consume a 16-aligned K; fp32 outputs (small heads) carry the logical channels only
+    store_n = pw.n if out_f32 else min(pw.n_pad, out_channels or pw.n_pad)
     if out is None:
         oc = out_channels or store_n
         out = torch.empty(tuple(x.shape[:-1]) + (oc,), dtype=torch.float32 if out_f32 else torch.bfloat16,
@@ -128,5 +130,227 @@ def conv_gemm(x, pw, *, x_coff=0, out=None, y_coff=0, out_channels=None, out_f32
     if y_raw is not None:
         d.y_raw = y_raw.data_ptr(); d.yraw_cstride = y_raw.shape[-1]; d.yraw_coff = 0
     d.store_n = store_n
+    d.w_per_image = 1 if w_per_image else 0
     capi.check(capi.lib().gwd_conv_gemm(ctypes.byref(d), _stream()), "gwd_conv_gemm")
     return out
+
+
+# ------------------------------------------------------------------------------------------
+# attention family
+# ------------------------------------------------------------------------------------------
+def _L():
+    return capi.lib()
+
+
+def attention(q, k, v, o, *, items, heads, Lq, Lk, hd, q_strides, k_strides, v_strides, o_strides,
+              bias=None, mask=None, key_padding=None, scale=1.0):
+    """q/k/v/o: bf16 tensors (possibly channel slices via .data_ptr() of a narrowed view); *_strides = (item, row)
+    in elements; head h is at +h*hd."""
+    d = capi.AttnDesc()
+    d.q, d.k, d.v, d.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), o.data_ptr()
+    d.items, d.heads, d.Lq, d.Lk, d.hd = items, heads, Lq, Lk, hd
+    d.q_item_stride, d.q_row_stride = q_strides
+    d.k_item_stride, d.k_row_stride = k_strides
+    d.v_item_stride, d.v_row_stride = v_strides
+    d.o_item_stride, d.o_row_stride = o_strides
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.is_contiguous()
+        d.bias = bias.data_ptr()
+    if mask is not None:
+        assert mask.dtype == torch.float32 and mask.is_contiguous()
+        d.mask = mask.data_ptr()
+        d.mask_windows = mask.shape[0]
+    if key_padding is not None:
+        assert key_padding.dtype == torch.uint8 and key_padding.is_contiguous()
+        d.key_padding = key_padding.data_ptr()
+    d.scale = scale
+    capi.check(_L().gwd_attention(ctypes.byref(d), _stream()), "gwd_attention")
+    return o
+
+
+def token_attention(dq, sq, tk, tv, dout, sout, *, items, N, heads, td, tc, q_rs, k_rs, v_rs, o_rs, scale):
+    capi.check(_L().gwd_token_attention(_ptr(dq), _ptr(sq), _ptr(tk), _ptr(tv), _ptr(dout), _ptr(sout), items, N, heads,
+                                        td, tc, q_rs, k_rs, v_rs, o_rs, scale, _stream()), "gwd_token_attention")
+
+
+def ref_scores(q, q_rs, ref_k, ref_rs, out, B, nW, N, heads, hd, R, scale=1.0):
+    capi.check(_L().gwd_ref_scores(_ptr(q), q_rs, _ptr(ref_k), ref_rs, _ptr(out), B, nW, N, heads, hd, R, scale,
+                                   _stream()), "gwd_ref_scores")
+
+
+def ref_diffuse(a_in, a_out, w, b, B, heads, P, R):
+    capi.check(_L().gwd_ref_diffuse(_ptr(a_in), _ptr(a_out), _ptr(w), _ptr(b), B, heads, P, R, _stream()),
+               "gwd_ref_diffuse")
+
+
+def ref_requery(a, ref_v, ref_rs, out, o_rs, B, nW, N, heads, hd, R, scale):
+    capi.check(_L().gwd_ref_requery(_ptr(a), _ptr(ref_v), ref_rs, _ptr(out), o_rs, B, nW, N, heads, hd, R, scale,
+                                    _stream()), "gwd_ref_requery")
+
+
+# ------------------------------------------------------------------------------------------
+# bandwidth kernels.  Tensors are bf16 channels-last; `rows` = product of the leading dims.
+# ------------------------------------------------------------------------------------------
+def _rows(t):
+    return t.numel() // t.shape[-1]
+
+
+def layernorm(x, gamma=None, beta=None, *, res=None, act=ACT_NONE, out=None, n=None, eps=1e-5, C=None, x_coff=0):
+    """rows of x[..., x_coff:x_coff+C] -> act(LN(x + res)) (contiguous [rows, C] unless `out` is given)"""
+    C = C or x.shape[-1]
+    rows = _rows(x)
+    if out is None:
+        out = torch.empty(tuple(x.shape[:-1]) + (C,), dtype=torch.bfloat16, device=x.device)
+    capi.check(_L().gwd_layernorm(_off(x, x_coff), x.shape[-1], _ptr(res), res.shape[-1] if res is not None else 0,
+                                  _ptr(gamma), _ptr(beta), eps, act, _ptr(out), out.shape[-1], rows, C, n or C, _stream()),
+               "gwd_layernorm")
+    return out
+
+
+def add_rows(x, addend, period, out=None):
+    C = x.shape[-1]
+    out = torch.empty_like(x) if out is None else out
+    capi.check(_L().gwd_add_rows(_ptr(x), C, _ptr(addend), addend.shape[-1], period, _ptr(out), out.shape[-1], _rows(x),
+                                 C, _stream()), "gwd_add_rows")
+    return out
+
+
+def _off(t, coff):
+    return ctypes.c_void_p(t.data_ptr() + coff * t.element_size())
+
+
+def window_gather(x, B, H, W, ws, shift, gamma=None, beta=None, n=None, eps=1e-5, C=None, x_coff=0, out=None, y_coff=0):
+    """x [B,H,W,Cx] (channels [x_coff, x_coff+C)) -> windows [B*nW*ws*ws, C] of the LayerNorm'ed, zero-padded,
+    cyclically shifted map; optionally written into channels [y_coff, y_coff+C) of a wider `out`."""
+    C = C or x.shape[-1]
+    Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
+    if out is None:
+        out = torch.empty(B * Hp * Wp, C, dtype=torch.bfloat16, device=x.device)
+    capi.check(_L().gwd_window_gather(_off(x, x_coff), x.shape[-1], _ptr(gamma), _ptr(beta), eps, _off(out, y_coff),
+                                      out.shape[-1], B, H, W, ws, shift, C, n or C, _stream()), "gwd_window_gather")
+    return out
+
+
+def window_merge(win, shortcut, B, H, W, ws, shift, gamma=None, beta=None, n=None, eps=1e-5, want_ln=False, C=None,
+                 sc_coff=0):
+    """-> (shortcut + unwindowed(win[:, :C]), LN(of that) or None), both [B*H*W, C] contiguous.  win may be wider than C
+    (row stride = win.shape[-1]); shortcut may be a channel slice [sc_coff, sc_coff+C) of a wider buffer."""
+    C = C or shortcut.shape[-1]
+    rows = B * H * W
+    out = torch.empty(rows, C, dtype=torch.bfloat16, device=win.device)
+    out_ln = torch.empty(rows, C, dtype=torch.bfloat16, device=win.device) if want_ln else None
+    capi.check(_L().gwd_window_merge(_ptr(win), win.shape[-1], _off(shortcut, sc_coff), shortcut.shape[-1], _ptr(out), C,
+                                     _ptr(gamma), _ptr(beta), eps, _ptr(out_ln), C, B, H, W, ws, shift, C, n or C,
+                                     _stream()), "gwd_window_merge")
+    return out, out_ln
+
+
+def upsample_nearest(x, H, W, add=None, out=None, y_coff=0, C=None, x_coff=0):
+    """nearest resize of x[..., x_coff:x_coff+C] ([B,h,w,Cx]) to HxW (+ optional same-size `add`), optionally into a
+    channel slice of a wider `out`"""
+    B, h, w, Cx = x.shape
+    C = C or Cx
+    out = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=x.device) if out is None else out
+    capi.check(_L().gwd_upsample_nearest(_off(x, x_coff), Cx, B, h, w, _off(out, y_coff), out.shape[-1], H, W, C, _ptr(add),
+                                         add.shape[-1] if add is not None else 0, _stream()), "gwd_upsample_nearest")
+    return out
+
+
+def avgpool(x, k, C=None):
+    """average-pool the first C channels of x [B,H,W,Cx]"""
+    B, H, W, Cx = x.shape
+    C = C or Cx
+    out = torch.empty(B, H // k, W // k, C, dtype=torch.bfloat16, device=x.device)
+    capi.check(_L().gwd_avgpool(_ptr(x), Cx, B, H, W, k, _ptr(out), C, C, _stream()), "gwd_avgpool")
+    return out
+
+
+def bilinear_up_into(x, out, y_coff, H, W):
+    """align_corners=True bilinear resize of x [B,h,w,C] into channels [y_coff, y_coff+C) of out [B,H,W,Ctot]"""
+    B, h, w, C = x.shape
+    dst = ctypes.c_void_p(out.data_ptr() + y_coff * 2)
+    capi.check(_L().gwd_bilinear_up(_ptr(x), C, B, h, w, dst, out.shape[-1], H, W, C, _stream()), "gwd_bilinear_up")
+    return out
+
+
+def sample_bilinear(x, x_coff, table, B, H, W, C, coords, K):
+    out = torch.empty(B, K, C, dtype=torch.float32, device=coords.device)
+    capi.check(_L().gwd_sample_bilinear(_ptr(x), x.shape[-1] if x is not None else 0, x_coff, _ptr(table), B, H, W, C,
+                                        _ptr(coords), K, _ptr(out), _stream()), "gwd_sample_bilinear")
+    return out
+
+
+def sample_scalar(x, coords, K):
+    B, H, W = x.shape
+    out = torch.empty(B, K, dtype=torch.float32, device=x.device)
+    capi.check(_L().gwd_sample_scalar(_ptr(x), B, H, W, _ptr(coords), K, _ptr(out), _stream()), "gwd_sample_scalar")
+    return out
+
+
+def line_ref_gather(win, pos, coords, R, B, H, W, ws, shift, C):
+    out = torch.empty(B, R, C, dtype=torch.bfloat16, device=win.device)
+    capi.check(_L().gwd_line_ref_gather(_ptr(win), win.shape[-1], _ptr(pos), _ptr(coords), R, _ptr(out), C, B, H, W, ws,
+                                        shift, C, _stream()), "gwd_line_ref_gather")
+    return out
+
+
+def anchor_mix(logits, anchor, B, HW, K):
+    out = torch.empty(B, HW, dtype=torch.float32, device=logits.device)
+    capi.check(_L().gwd_anchor_mix(_ptr(logits), logits.shape[-1], _ptr(anchor), B, HW, K, _ptr(out), _stream()),
+               "gwd_anchor_mix")
+    return out
+
+
+def nchw_to_nhwc(x, Cp):
+    B, C, H, W = x.shape
+    out = torch.empty(B, H, W, Cp, dtype=torch.bfloat16, device=x.device)
+    capi.check(_L().gwd_nchw_to_nhwc(_ptr(x), B, C, H * W, _ptr(out), Cp, _stream()), "gwd_nchw_to_nhwc")
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# selection / reduction kernels
+# ------------------------------------------------------------------------------------------
+def certain_sample(pred_small, pred_large, K, edges):
+    """pred_small [B,h,w], pred_large [B,H,W] fp32 -> (coords fp32 [B,K,1,2], index int32 [B,K])"""
+    B, h, w = pred_small.shape
+    _, H, W = pred_large.shape
+    coords = torch.empty(B, K, 1, 2, dtype=torch.float32, device=pred_large.device)
+    index = torch.empty(B, K, dtype=torch.int32, device=pred_large.device)
+    e = (ctypes.c_float * len(edges))(*edges)
+    capi.check(_L().gwd_certain_sample(_ptr(pred_small), h, w, _ptr(pred_large), H, W, B, K, e, len(edges) - 1,
+                                       _ptr(coords), _ptr(index), _stream()), "gwd_certain_sample")
+    return coords, index
+
+
+def match_cost(logits, lines, tgt_lines, tgt_labels, tgt_offsets, w_class, w_line):
+    """-> (flat block-diagonal cost fp32 [Q * sum T_b], row_min fp32 [B,Q])"""
+    B, Q, ncls = logits.shape
+    total_t = tgt_lines.shape[0]
+    cost = torch.empty(Q * total_t, dtype=torch.float32, device=logits.device)
+    row_min = torch.empty(B, Q, dtype=torch.float32, device=logits.device)
+    capi.check(_L().gwd_match_cost(_ptr(logits), _ptr(lines), _ptr(tgt_lines), _ptr(tgt_labels), _ptr(tgt_offsets), B, Q,
+                                   ncls, lines.shape[-1], w_class, w_line, _ptr(cost), _ptr(row_min), _stream()),
+               "gwd_match_cost")
+    return cost, row_min
+
+
+def depth_metrics(pred, gt, min_depth=1e-3, max_depth=10.0):
+    """pred, gt fp32 [B,H,W] -> fp64 [B,9] (silog, abs_rel, log10, rms, sq_rel, log_rms, d1, d2, d3)"""
+    B = pred.shape[0]
+    HW = pred[0].numel()
+    ws = torch.empty(B, 10, dtype=torch.float64, device=pred.device)
+    out = torch.empty(B, 9, dtype=torch.float64, device=pred.device)
+    capi.check(_L().gwd_depth_metrics(_ptr(pred), _ptr(gt), B, HW, min_depth, max_depth, _ptr(ws), _ptr(out), _stream()),
+               "gwd_depth_metrics")
+    return out
+
+
+def silog_sums(pred, gt, lo=0.2, hi=10.0, log_only=False):
+    """pred fp32 [B,1,h,w], gt fp32 [B,1,H,W] -> fp64 [3] = count, sum d, sum d^2"""
+    B, _, h, w = pred.shape
+    H, W = gt.shape[-2:]
+    sums = torch.empty(3, dtype=torch.float64, device=pred.device)
+    capi.check(_L().gwd_silog_sums(_ptr(pred), B, h, w, _ptr(gt), H, W, lo, hi, 1 if log_only else 0, _ptr(sums),
+                                   _stream()), "gwd_silog_sums")
+    return sums

@@ -86,9 +86,120 @@ typedef struct gwd_gemm_desc {
   void* y_raw;          /* optional bf16 copy of the pre-norm value, or NULL */
   int32_t yraw_cstride, yraw_coff;
   int32_t store_n;      /* channels stored (<= n_pad); pad channels written as 0 when store_n > n */
+  int32_t w_per_image;  /* 1: w is [B][taps][n_pad][cin], image b of x uses w[b] (PointBasedPred correlation,
+                           src/models/points/points_sample.py:272) */
 } gwd_gemm_desc;
 
 int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * gwd_attention: fused multi-head softmax attention  O = softmax(Q K^T * scale + bias + mask) V
+ * for one (item, head) at a time with K/V staged in shared memory (head_dim in {4,8,16,32}).
+ * Q/K/V/O are bf16 views: element (item, row, head h, d) lives at  base + item*item_stride +
+ * row*row_stride + h*head_dim + d.  bias is fp32 [heads, Lq, Lk] (relative position bias), mask is
+ * fp32 [mask_windows, Lq, Lk] selected by item % mask_windows (shifted-window mask, value -100),
+ * key_padding is uint8 [items, Lk] (1 = key ignored, scores -> -inf).
+ * Replaces src/models/multi_head_attention.py:317-372 (bmm, masked_fill, softmax, bmm, transposes; the
+ * head-averaged weights of :375-378 are dead and not produced) and the attention cores of
+ * src/models/multiscale_transformerr.py:311-328 and :539-556.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct gwd_attn_desc {
+  const void* q; const void* k; const void* v; void* o;
+  int32_t items, heads, Lq, Lk, hd;
+  int64_t q_item_stride, q_row_stride, k_item_stride, k_row_stride;
+  int64_t v_item_stride, v_row_stride, o_item_stride, o_row_stride;
+  const float* bias;
+  const float* mask;
+  int32_t mask_windows;
+  const uint8_t* key_padding;
+  float scale;
+} gwd_attn_desc;
+int gwd_attention(const gwd_attn_desc* d, void* stream);
+
+/* class-token CHANNEL attention of WindowClassAttention (multiscale_transformerr.py:561-578): for every window
+ * (item) and head, A = softmax_c(scale * tq^T tk) [td x tc], out = (A tv^T)^T; depth and seg tokens share tk/tv. */
+int gwd_token_attention(const void* depth_q, const void* seg_q, const void* tk, const void* tv, void* depth_out,
+                        void* seg_out, int32_t items, int32_t N, int32_t heads, int32_t td, int32_t tc, int64_t q_rs,
+                        int64_t k_rs, int64_t v_rs, int64_t o_rs, float scale, void* stream);
+
+/* line end-point re-query of WindowAttention (multiscale_transformerr.py:281-310):
+ *   gwd_ref_scores : a[b][h][w*N+n][r] = scale * q . ref_k                      (:295-298)
+ *   gwd_ref_diffuse: a_out = a_in + gelu(layer_norm_[P,R](conv3x3_{h->h}(a_in)))  one of the 3 steps of :299-302
+ *   gwd_ref_requery: q_new = scale * softmax_r(a) ref_v                          (:307-310), bf16 window layout */
+int gwd_ref_scores(const void* q, int64_t q_rs, const float* ref_k, int64_t ref_rs, float* a, int32_t B, int32_t nW,
+                   int32_t N, int32_t heads, int32_t hd, int32_t R, float scale, void* stream);
+int gwd_ref_diffuse(const float* a_in, float* a_out, const float* conv_w, const float* conv_b, int32_t B, int32_t heads,
+                    int32_t P, int32_t R, void* stream);
+int gwd_ref_requery(const float* a, const float* ref_v, int64_t ref_rs, void* q_new, int64_t o_rs, int32_t B, int32_t nW,
+                    int32_t N, int32_t heads, int32_t hd, int32_t R, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * bandwidth kernels (bf16 channels-last rows, strides in elements, C and strides multiples of 8)
+ * ------------------------------------------------------------------------------------------ */
+/* out = act(LayerNorm_n(x + res)); res / gamma may be NULL.  nn.LayerNorm + residual adds of
+ * src/models/transformer.py:113-120,157-161 and multiscale_transformerr.py:659,664-665 */
+int gwd_layernorm(const void* x, int64_t x_rs, const void* res, int64_t res_rs, const float* gamma, const float* beta,
+                  float eps, int32_t act, void* out, int64_t out_rs, int64_t rows, int32_t C, int32_t n, void* stream);
+/* out[r] = x[r] + addend[r % period]   (with_pos_embed, src/models/transformer.py:154,219,224-225) */
+int gwd_add_rows(const void* x, int64_t x_rs, const void* addend, int64_t a_rs, int64_t period, void* out, int64_t out_rs,
+                 int64_t rows, int32_t C, void* stream);
+/* LayerNorm + zero pad + cyclic shift + window partition in one pass (multiscale_transformerr.py:659-707) */
+int gwd_window_gather(const void* x, int64_t x_rs, const float* gamma, const float* beta, float eps, void* out,
+                      int64_t out_rs, int32_t B, int32_t H, int32_t W, int32_t ws, int32_t shift, int32_t C, int32_t n,
+                      void* stream);
+/* window reverse + un-shift + crop + residual add (+ LayerNorm of the sum into out_ln) (:731-755) */
+int gwd_window_merge(const void* win, int64_t win_rs, const void* shortcut, int64_t sc_rs, void* out, int64_t out_rs,
+                     const float* gamma, const float* beta, float eps, void* out_ln, int64_t ln_rs, int32_t B, int32_t H,
+                     int32_t W, int32_t ws, int32_t shift, int32_t C, int32_t n, void* stream);
+/* F.interpolate(mode='nearest') (+ optional add of a same-size map) */
+int gwd_upsample_nearest(const void* x, int64_t x_rs, int32_t B, int32_t h, int32_t w, void* out, int64_t out_rs, int32_t H,
+                         int32_t W, int32_t C, const void* add, int64_t add_rs, void* stream);
+/* nn.AvgPool2d(k, stride=k)  (points_sample.py:61-75) */
+int gwd_avgpool(const void* x, int64_t x_rs, int32_t B, int32_t H, int32_t W, int32_t k, void* out, int64_t out_rs,
+                int32_t C, void* stream);
+/* F.interpolate(mode='bilinear', align_corners=True)  (points_sample.py:115-121) */
+int gwd_bilinear_up(const void* x, int64_t x_rs, int32_t B, int32_t h, int32_t w, void* out, int64_t out_rs, int32_t H,
+                    int32_t W, int32_t C, void* stream);
+/* F.grid_sample(bilinear, align_corners=False, zeros) of a bf16 map (+ fp32 [H,W,C] table) at K points -> fp32 [B,K,C]
+ * (points_sample.py:264-267) */
+int gwd_sample_bilinear(const void* x, int64_t x_rs, int32_t x_coff, const float* table, int32_t B, int32_t H, int32_t W,
+                        int32_t C, const float* coords, int32_t K, float* out, void* stream);
+/* same for a 1-channel fp32 map -> fp32 [B,K]  (points_sample.py:268) */
+int gwd_sample_scalar(const float* x, int32_t B, int32_t H, int32_t W, const float* coords, int32_t K, float* out,
+                      void* stream);
+/* nearest sample of the windowed feature map + shifted position table at R line end points
+ * (multiscale_transformerr.py:676-701) -> bf16 [B,R,C] */
+int gwd_line_ref_gather(const void* win, int64_t win_rs, const float* pos, const float* coords, int32_t R, void* out,
+                        int64_t out_rs, int32_t B, int32_t H, int32_t W, int32_t ws, int32_t shift, int32_t C, void* stream);
+/* depth[p] = sum_k softmax_k(logits[p,:K]) anchor[b,k]  (points_sample.py:277-279) -> fp32 [B,HW] */
+int gwd_anchor_mix(const void* logits, int64_t l_rs, const float* anchor, int32_t B, int64_t HW, int32_t K, float* out,
+                   void* stream);
+/* fp32 NCHW image -> bf16 NHWC with Cp >= C channels (zero padded) */
+int gwd_nchw_to_nhwc(const float* x, int32_t B, int32_t C, int64_t HW, void* out, int32_t Cp, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * selection / reduction kernels (fp32 inputs)
+ * ------------------------------------------------------------------------------------------ */
+/* CertainSample.forward (src/models/points/points_sample.py:291-364): K most uncertain pixels per image with the
+ * reference's per-depth-bin quota / repeat / trim rules.  edges_host: HOST array of nbins+1 bin edges.
+ * coords fp32 [B,K,2] = (x/W*2-1, y/H*2-1); index int32 [B,K] = y*W+x. */
+int gwd_certain_sample(const float* pred_small, int32_t h, int32_t w, const float* pred_large, int32_t H, int32_t W,
+                       int32_t B, int32_t K, const float* edges_host, int32_t nbins, float* coords, int32_t* index,
+                       void* stream);
+/* HungarianMatcher_Line cost, block diagonal only (src/models/matcher.py:52-71):
+ * cost[tgt_offsets[b]*Q + q*T_b + t] = w_line*L1(lines[b,q], tgt[t]) - w_class*softmax(logits[b,q])[label[t]]
+ * row_min (optional) fp32 [B,Q]. tgt_offsets int32 [B+1] (device). */
+int gwd_match_cost(const float* logits, const float* lines, const float* tgt_lines, const int64_t* tgt_labels,
+                   const int32_t* tgt_offsets, int32_t B, int32_t Q, int32_t num_classes, int32_t line_dim, float w_class,
+                   float w_line, float* cost, float* row_min, void* stream);
+/* compute_depth_errors per image (src/util/metrics.py:197-218 after the scrub of src/engine_glassrgbd.py:249-253):
+ * metrics fp64 [B,9] = silog, abs_rel, log10, rms, sq_rel, log_rms, d1, d2, d3; workspace fp64 [B,10]. */
+int gwd_depth_metrics(const float* pred, const float* gt, int32_t B, int64_t HW, float min_depth, float max_depth,
+                      double* workspace, double* metrics, void* stream);
+/* SilogLoss sums over valid pixels with gt nearest-resized to the prediction (src/models/glassrgbd.py:366-374,
+ * src/engine_glassrgbd.py:74-80): sums3 fp64 = {count, sum d, sum d^2}. */
+int gwd_silog_sums(const float* pred, int32_t B, int32_t h, int32_t w, const float* gt, int32_t H, int32_t W, float lo,
+                   float hi, int32_t log_only, double* sums3, void* stream);
 
 #ifdef __cplusplus
 }

@@ -53,7 +53,7 @@ def test_linear(M, K, N, pre, post, res_mode, use_ln):
     x = _rand((M, K), g).bfloat16()
     w = _rand((N, K), g, K ** -0.5).bfloat16()
     b = _rand((N,), g, 0.5)
-    n8 = ops.round_up(N, 8)
+    n8 = ops.round_up(N, 16)
     res = _rand((M, n8), g).bfloat16() if res_mode else None
     ln = (1 + 0.1 * _rand((N,), g), 0.1 * _rand((N,), g)) if use_ln else None
     acc = x.float() @ w.float().t()
