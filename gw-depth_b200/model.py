@@ -1,0 +1,347 @@
+"""Host-side mirror of the reference's model interface (src/models/__init__.py:5-6, src/models/glassrgbd.py:44-123,
+133-358,360-383,452-506,509-579, src/models/matcher.py:10-87, src/util/misc.py:291-367): same names, argument
+meaning and error behaviour, so that src/main_glassrgbd.py and src/engine_glassrgbd.py can import this module in
+place of `models`.
+
+    model, [criterion, criterion_depth, criterion_seg, criterion_plane], postprocessors = build_model(args)
+    out = model(samples)      # {'pred_logits','pred_lines','aux_outputs','pred_depth': [4 maps],'pred_seg'}
+
+`GlassRGBD` holds the reference's parameters under the reference's state_dict names (see spec.py) and runs its
+forward through the sm_100a kernel plan in engine.py.  There is no PyTorch fallback: without libgwd_b200.so or
+without a CUDA device the forward raises.
+"""
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import engine as _engine
+from . import ops
+from .spec import model_spec
+
+
+class NestedTensor(object):
+    """(tensors, padding mask) pair, src/util/misc.py:347-367"""
+
+    def __init__(self, tensors, mask):
+        self.tensors, self.mask = tensors, mask
+
+    def to(self, device):
+        return NestedTensor(self.tensors.to(device), self.mask.to(device) if self.mask is not None else None)
+
+    def decompose(self):
+        return self.tensors, self.mask
+
+    def __repr__(self):
+        return str(self.tensors)
+
+
+def nested_tensor_from_tensor_list(tensor_list):
+    """pad a list of [C,H,W] images to a common size; mask is True on padding (src/util/misc.py:291-313)"""
+    if isinstance(tensor_list, torch.Tensor) and tensor_list.dim() == 4:
+        tensor_list = list(tensor_list)
+    if tensor_list[0].dim() != 3:
+        raise ValueError("not supported")
+    c = tensor_list[0].shape[0]
+    hmax = max(t.shape[1] for t in tensor_list)
+    wmax = max(t.shape[2] for t in tensor_list)
+    batch = tensor_list[0].new_zeros((len(tensor_list), c, hmax, wmax))
+    mask = torch.ones((len(tensor_list), hmax, wmax), dtype=torch.bool, device=batch.device)
+    for i, t in enumerate(tensor_list):
+        batch[i, :, : t.shape[1], : t.shape[2]].copy_(t)
+        mask[i, : t.shape[1], : t.shape[2]] = False
+    return NestedTensor(batch, mask)
+
+
+class _Node(nn.Module):
+    """anonymous container: gives parameters the reference's dotted names"""
+
+
+def _build_tree(root, entries):
+    for name, shape, dtype, kind, trainable in entries:
+        *path, leaf = name.split(".")
+        node = root
+        for part in path:
+            if part not in node._modules:
+                node.add_module(part, _Node())
+            node = node._modules[part]
+        if kind == "param":
+            node.register_parameter(leaf, nn.Parameter(torch.zeros(shape), requires_grad=trainable))
+        else:
+            dt = torch.int64 if dtype == "int64" else torch.float32
+            node.register_buffer(leaf, torch.zeros(shape, dtype=dt))
+
+
+def _init_parameters(module):
+    """Random initialisation in the spirit of the reference (xavier for the DETR part, transformer.py:42-45;
+    truncated normal 0.02 for the dense encoder, multiscale_transformerr.py:1140-1149): training from scratch is
+    possible, but the usual entry is load_state_dict() of a reference checkpoint."""
+    from .engine import rel_pos_bias  # noqa: F401  (structural buffer helper lives with the tables)
+    for name, p in module.named_parameters():
+        leaf = name.rsplit(".", 1)[-1]
+        if "norm" in name and leaf == "weight":
+            nn.init.ones_(p)
+        elif leaf in ("bias", "in_proj_bias", "diff_logsigma", "border_logsigma"):
+            nn.init.zeros_(p)
+        elif p.dim() > 1 and (name.startswith("transformer") or p.dim() == 4):
+            nn.init.xavier_uniform_(p)
+        elif p.dim() > 1:
+            nn.init.trunc_normal_(p, std=0.02)
+        else:
+            nn.init.normal_(p, std=0.02)
+    for name, b in module.named_buffers():
+        leaf = name.rsplit(".", 1)[-1]
+        if leaf == "relative_position_index":
+            ws = int(round(b.shape[0] ** 0.5))
+            c = torch.stack(torch.meshgrid(torch.arange(ws), torch.arange(ws), indexing="ij")).flatten(1)
+            rel = c[:, :, None] - c[:, None, :]
+            b.copy_((rel[0] + ws - 1) * (2 * ws - 1) + rel[1] + ws - 1)
+        elif leaf in ("weight", "running_var"):
+            b.fill_(1.0)
+
+
+class GlassRGBD(_Node):
+    """Drop-in for src/models/glassrgbd.py:44-123 (flag set --with_line --with_center --with_dense)."""
+
+    def __init__(self, args):
+        super().__init__()
+        if not (getattr(args, "with_line", True) and getattr(args, "with_dense", True)):
+            raise NotImplementedError("only the --with_line --with_dense configuration of the reference is a working "
+                                      "model (SURVEY.md section 9-F); it is the one built here")
+        if getattr(args, "with_line_depth", False):
+            raise NotImplementedError("--with_line_depth raises AttributeError in the reference itself (SURVEY.md 9-F)")
+        self.args = args
+        self.num_queries = args.num_queries
+        self.aux_loss = getattr(args, "aux_loss", True)
+        self.cfg = dict(
+            hidden_dim=args.hidden_dim, nheads=args.nheads, enc_layers=args.enc_layers, dec_layers=args.dec_layers,
+            num_queries=args.num_queries, dense_trans_dim=args.dense_trans_dim, dense_trans_heads=args.dense_trans_heads,
+            dense_trans_layers=tuple(args.dense_trans_layers), class_trans_layers=tuple(args.class_trans_layers),
+            class_token_dim=args.class_token_dim, num_ref=args.num_ref, with_dense_center=bool(args.with_dense_center),
+            window=7, interval_sample_num=tuple(args.interval_sample_num)[:2], depth_interval=tuple(args.depth_interval),
+            min_depth_eval=args.min_depth_eval, max_depth_eval=args.max_depth_eval, max_depth=float(args.max_depth),
+            aux_loss=self.aux_loss)
+        hp = dict(hidden_dim=args.hidden_dim, dim_feedforward=args.dim_feedforward, enc_layers=args.enc_layers,
+                  dec_layers=args.dec_layers, num_queries=args.num_queries, with_center=bool(args.with_center),
+                  dense_trans_dim=args.dense_trans_dim, dense_trans_heads=args.dense_trans_heads,
+                  dense_trans_layers=tuple(args.dense_trans_layers), class_trans_layers=tuple(args.class_trans_layers),
+                  class_token_dim=args.class_token_dim, window=7, interval_sample_num=tuple(args.interval_sample_num))
+        _build_tree(self, model_spec(hp))
+        _init_parameters(self)
+        self._plan = None
+        self._plan_key = None
+
+    # the kernel plan caches re-laid-out weights; rebuild it whenever a parameter changed or moved
+    def _current_key(self):
+        vers = tuple(t._version for t in self.state_dict(keep_vars=True).values())
+        dev = next(self.parameters()).device
+        return (vers, str(dev))
+
+    def plan(self):
+        key = self._current_key()
+        if self._plan is None or key != self._plan_key:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("GlassRGBD runs on sm_100a CUDA kernels only; move the model to a CUDA device "
+                                   "(there is no CPU path)")
+            self._plan = _engine.Engine(self.state_dict(), self.cfg, device=dev)
+            self._plan_key = key
+        return self._plan
+
+    def forward(self, samples, reflc_points=None, reflc_mat=None, img_name=None, _pinned=None, _trace=None):
+        if isinstance(samples, (list, torch.Tensor)):
+            samples = nested_tensor_from_tensor_list(samples)
+        images, mask = samples.decompose()
+        assert mask is not None
+        if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("backward kernels are not built yet: run the forward under torch.no_grad() / "
+                                      "model.eval() (DESIGN.md, 'what comes next')")
+        if bool(mask.any()):
+            raise NotImplementedError("padded (ragged) batches are not built yet on the CUDA path; batch equal-size images")
+        plan = self.plan()      # raises off-GPU: there is no CPU path
+        with torch.cuda.device(images.device):
+            return plan.forward(images.float(), pinned=_pinned, trace=_trace)
+
+
+# --------------------------------------------------------------------------------------------------
+# criteria
+# --------------------------------------------------------------------------------------------------
+class HungarianMatcher_Line(nn.Module):
+    """src/models/matcher.py:10-82.  The block-diagonal cost matrix comes from the gwd_match_cost kernel; the
+    assignment itself is solved by scipy.optimize.linear_sum_assignment exactly like the reference (:74)."""
+
+    def __init__(self, cost_class=1, cost_line=1):
+        super().__init__()
+        assert cost_class != 0 or cost_line != 0, "all costs cant be 0"
+        self.cost_class, self.cost_line = cost_class, cost_line
+
+    @torch.no_grad()
+    def cost_matrices(self, outputs, targets):
+        logits = outputs["pred_logits"].float().contiguous()
+        lines = outputs["pred_lines"].float().contiguous()
+        B, Q = logits.shape[:2]
+        sizes = [len(v["lines"]) for v in targets]
+        tgt_lines = torch.cat([v["lines"] for v in targets]).float().contiguous()
+        tgt_ids = torch.cat([v["labels"] for v in targets]).to(torch.int64).contiguous()
+        offs = [0]
+        for s in sizes:
+            offs.append(offs[-1] + s)
+        offsets = torch.tensor(offs, dtype=torch.int32, device=logits.device)
+        cost, _ = ops.match_cost(logits, lines, tgt_lines, tgt_ids, offsets, float(self.cost_class), float(self.cost_line))
+        flat = cost.cpu()
+        return [flat[offs[b] * Q: offs[b + 1] * Q].view(Q, sizes[b]) for b in range(B)]
+
+    @torch.no_grad()
+    def forward(self, outputs, targets):
+        from scipy.optimize import linear_sum_assignment
+        result = []
+        for c in self.cost_matrices(outputs, targets):
+            i, j = linear_sum_assignment(c.numpy())
+            result.append((torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)))
+        return result
+
+
+def build_matcher(args, type=None):
+    return HungarianMatcher_Line(cost_class=args.set_cost_class, cost_line=args.set_cost_line)
+
+
+def _world_size():
+    import torch.distributed as dist
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+class SetCriterion(nn.Module):
+    """line set loss, src/models/glassrgbd.py:133-358 (losses 'lines_labels' and 'lines', repeated on the aux outputs)"""
+
+    def __init__(self, num_classes, weight_dict, eos_coef, losses, args, matcher=None):
+        super().__init__()
+        self.num_classes, self.matcher, self.weight_dict = num_classes, matcher, weight_dict
+        self.eos_coef, self.losses, self.args = eos_coef, losses, args
+        w = torch.ones(num_classes + 1)
+        w[-1] = eos_coef
+        self.register_buffer("empty_weight", w)
+        if getattr(args, "label_loss_func", "cross_entropy") != "cross_entropy":
+            raise NotImplementedError("only label_loss_func='cross_entropy' (the default) is built")
+
+    def _pairs(self, indices):
+        batch_idx = torch.cat([torch.full_like(src, i) for i, (src, _) in enumerate(indices)])
+        return batch_idx, torch.cat([src for src, _ in indices])
+
+    def loss_lines_labels(self, outputs, targets, num_items, origin_indices):
+        logits = outputs["pred_logits"]
+        idx = self._pairs(origin_indices)
+        matched = torch.cat([t["labels"][j.to(t["labels"].device)] for t, (_, j) in zip(targets, origin_indices)])
+        classes = torch.full(logits.shape[:2], self.num_classes, dtype=torch.int64, device=logits.device)
+        classes[idx[0].to(logits.device), idx[1].to(logits.device)] = matched.to(logits.device)
+        return {"loss_ce": F.cross_entropy(logits.transpose(1, 2), classes, self.empty_weight.to(logits.device))}
+
+    def loss_lines(self, outputs, targets, num_items, origin_indices):
+        idx = self._pairs(origin_indices)
+        dev = outputs["pred_lines"].device
+        src = outputs["pred_lines"][idx[0].to(dev), idx[1].to(dev)]
+        tgt = torch.cat([t["lines"][j.to(t["lines"].device)] for t, (_, j) in zip(targets, origin_indices)], dim=0).to(dev)
+        return {"loss_line": F.l1_loss(src, tgt, reduction="none").sum() / num_items}
+
+    def get_loss(self, loss, outputs, targets, num_items, **kw):
+        table = {"lines_labels": self.loss_lines_labels, "lines": self.loss_lines,
+                 "POST_lines_labels": self.loss_lines_labels, "POST_lines": self.loss_lines}
+        assert loss in table, f"do you really want to compute {loss} loss?"
+        return table[loss](outputs, targets, num_items, **kw)
+
+    def forward(self, outputs, targets, origin_indices=None, depth_gt=None):
+        plain = {k: v for k, v in outputs.items() if k != "aux_outputs"}
+        origin_indices = self.matcher(plain, targets)
+        n = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float,
+                            device=next(iter(outputs.values())).device)
+        if _world_size() > 1:
+            torch.distributed.all_reduce(n)
+        num_items = torch.clamp(n / _world_size(), min=1).item()
+        losses = {}
+        for loss in self.losses:
+            losses.update(self.get_loss(loss, outputs, targets, num_items, origin_indices=origin_indices))
+        for i, aux in enumerate(outputs.get("aux_outputs", [])):
+            idx = self.matcher(aux, targets)
+            for loss in self.losses:
+                d = self.get_loss(loss, aux, targets, num_items, origin_indices=idx)
+                losses.update({k + f"_{i}": v for k, v in d.items()})
+        return losses
+
+
+class SilogLoss(nn.Module):
+    """src/models/glassrgbd.py:360-374, without the boolean-index compaction (masked sums instead: no host sync)"""
+
+    def __init__(self, variance_focus=0.85, log_depth_error=True):
+        super().__init__()
+        self.variance_focus, self.log_depth_error = variance_focus, log_depth_error
+
+    def forward(self, depth_est, depth_gt, mask):
+        m = mask.to(depth_est.dtype)
+        n = m.sum()
+        est = torch.where(mask, depth_est, torch.ones_like(depth_est))
+        gt = torch.where(mask, depth_gt, torch.ones_like(depth_gt))
+        d = (torch.log(est) - torch.log(gt)) if self.log_depth_error else ((est + torch.log(est)) - (gt + torch.log(gt)))
+        d = d * m
+        return torch.sqrt((d ** 2).sum() / n - self.variance_focus * (d.sum() / n) ** 2) * 10.0
+
+
+class SegLoss(nn.Module):
+    """src/models/glassrgbd.py:376-383"""
+
+    def forward(self, seg_pred, seg_gt):
+        return F.cross_entropy(seg_pred, seg_gt)
+
+
+class PostProcess_Line(nn.Module):
+    """src/models/glassrgbd.py:452-506"""
+
+    @torch.no_grad()
+    def forward(self, outputs, target_sizes, output_type):
+        if output_type in ("prediction", "prediction_POST"):
+            logits = outputs["pred_logits"]
+            lines = outputs["pred_lines" if output_type == "prediction" else "POST_pred_lines"]
+            assert len(logits) == len(target_sizes) and target_sizes.shape[1] == 2
+            scores, labels = F.softmax(logits, -1)[..., :-1].max(-1)
+            h, w = target_sizes.unbind(1)
+            scale = torch.stack([w, h, w, h], dim=1)[:, None, :]
+            return [{"scores": s, "labels": l, "lines": b} for s, l, b in zip(scores, labels, lines * scale)]
+        if output_type == "ground_truth":
+            h, w = target_sizes.unbind(1)
+            scale = torch.stack([w, h, w, h], dim=1)
+            return [{"labels": d["labels"], "lines": d["lines"] * scale, "image_id": d["image_id"]} for d in outputs]
+        raise AssertionError(output_type)
+
+
+def build(args):
+    """src/models/glassrgbd.py:509-579 -> (model, [criterion, criterion_depth, criterion_seg, criterion_plane], postprocessors)"""
+    model = GlassRGBD(args)
+    weight_dict = {"loss_ce": 1, "loss_line": args.line_loss_coef}
+    if args.aux_loss:
+        for i in range(args.dec_layers - 1):
+            weight_dict.update({k + f"_{i}": v for k, v in list(weight_dict.items())[:2]})
+    device = torch.device(args.device)
+    criterion = SetCriterion(1, weight_dict=weight_dict, eos_coef=args.eos_coef, losses=["lines_labels", "lines"], args=args,
+                             matcher=build_matcher(args, type="origin_line")).to(device)
+    criterion_depth = SilogLoss(variance_focus=args.variance_focus, log_depth_error=args.log_depth_error).to(device)
+    criterion_seg = SegLoss().to(device)
+    if getattr(args, "with_plane_norm_loss", False):
+        raise NotImplementedError("--with_plane_norm_loss needs matplotlib polygons and B == 1 in the reference; not built")
+    return model, [criterion, criterion_depth, criterion_seg, None], {"line": PostProcess_Line()}
+
+
+def build_model(args):
+    return build(args)
+
+
+def default_args(**overrides):
+    """the reference's argparse defaults for the flags that shape the model (src/args.py), with the working flag set
+    --with_line --with_center --with_dense --num_queries 100"""
+    import argparse
+    d = dict(device="cuda", hidden_dim=256, nheads=8, enc_layers=6, dec_layers=6, dim_feedforward=2048, dropout=0.1,
+             num_queries=100, aux_loss=True, with_line=True, with_dense=True, with_center=True, with_dense_center=False,
+             with_line_depth=False, with_plane_norm_loss=False, set_cost_class=1.0, set_cost_line=5.0, line_loss_coef=5.0,
+             eos_coef=0.1, label_loss_func="cross_entropy", variance_focus=0.85, log_depth_error=False, max_depth=10,
+             min_depth_eval=1e-3, max_depth_eval=10.0, dense_trans_dim=512, dense_trans_heads=16, dense_trans_layers=[4],
+             class_trans_layers=[2, 2, 1], class_token_dim=64, num_ref=20, interval_sample_num=[30, 80, 160],
+             depth_interval=[0.1, 0.3, 0.5, 0.7, 0.9], depth_loss_weights=[0.25, 0.25, 0.25, 1], seg_loss_weight=2.0,
+             lr_backbone=1e-5, backbone="resnet50", layer1_num=3)
+    d.update(overrides)
+    return argparse.Namespace(**d)

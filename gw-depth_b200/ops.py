@@ -25,6 +25,11 @@ def round_up(v, m):
     return (v + m - 1) // m * m
 
 
+# bench.py sets this to a list to time every gwd_conv_gemm launch with CUDA events on the launching stream:
+# entries are (start_event, end_event, algorithmic_flops, description)
+PROFILE = None
+
+
 # ------------------------------------------------------------------------------------------
 # weight packing (done once at model-load time; not part of the hot path)
 # ------------------------------------------------------------------------------------------
@@ -131,6 +136,14 @@ def conv_gemm(x, pw, *, x_coff=0, out=None, y_coff=0, out_channels=None, out_f32
         d.y_raw = y_raw.data_ptr(); d.yraw_cstride = y_raw.shape[-1]; d.yraw_coff = 0
     d.store_n = store_n
     d.w_per_image = 1 if w_per_image else 0
+    if PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        capi.check(capi.lib().gwd_conv_gemm(ctypes.byref(d), _stream()), "gwd_conv_gemm")
+        e1.record()
+        PROFILE.append((e0, e1, 2.0 * B * H * W * pw.n * pw.cin * taps,
+                        "%dx%dx%d pixels, %d->%d ch, %d taps" % (B, H, W, pw.cin, pw.n, taps)))
+        return out
     capi.check(capi.lib().gwd_conv_gemm(ctypes.byref(d), _stream()), "gwd_conv_gemm")
     return out
 
