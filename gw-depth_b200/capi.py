@@ -57,7 +57,7 @@ SIGNATURES = {
     "gwd_attention": (c_int, [ctypes.POINTER(AttnDesc), P]),
     "gwd_token_attention": (c_int, [P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, F_, P]),
     "gwd_ref_scores": (c_int, [P, L, P, L, P, I, I, I, I, I, I, F_, P]),
-    "gwd_ref_diffuse": (c_int, [P, P, P, P, I, I, I, I, P]),
+    "gwd_ref_diffuse": (c_int, [P, P, P, P, P, P, I, I, I, I, P]),
     "gwd_ref_requery": (c_int, [P, P, L, P, L, I, I, I, I, I, I, F_, P]),
     "gwd_layernorm": (c_int, [P, L, P, L, P, P, F_, I, P, L, L, I, I, P]),
     "gwd_add_rows": (c_int, [P, L, P, L, L, P, L, L, I, P]),

@@ -103,6 +103,93 @@ __global__ void __launch_bounds__(kAttnWarps * 32) gwd_attention_kernel(const At
   }
 }
 
+
+// -------------------------------------------------------------------------------------------------
+// window attention: one CTA per window, one warp per head.  The window's K and V rows ([N, C], all heads) are
+// staged in shared memory with coalesced 16-byte loads; K rows are padded per head to kill bank conflicts.
+// -------------------------------------------------------------------------------------------------
+struct WinAttnParams {
+  const bf16* q; const bf16* k; const bf16* v; bf16* o;
+  int windows, heads, N, hd;
+  int64_t q_rs, k_rs, v_rs, o_rs;      // row strides; window stride = N * row stride
+  const float* bias;                   // [heads, N, N]
+  const float* mask;                   // [nW, N, N] or null
+  int nW;
+};
+
+__global__ void gwd_window_attention_kernel(const WinAttnParams p) {
+  extern __shared__ __align__(16) uint8_t smem[];
+  const int N = p.N, hd = p.hd, heads = p.heads, C = heads * hd;
+  const int kst = hd + 2;                                 // padded per-head K row (bf16 elements)
+  bf16* Ks = reinterpret_cast<bf16*>(smem);               // [heads][N][kst]
+  bf16* Vs = Ks + static_cast<size_t>(heads) * N * kst;   // [N][C]
+  float* Ps = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(Vs + static_cast<size_t>(N) * C) + 15) & ~uintptr_t(15));
+  float* Qs = Ps + static_cast<size_t>(heads) * 64;       // [heads][64] probabilities, then [heads][32] query
+  const int win = blockIdx.x;
+  const bf16* kb = p.k + static_cast<int64_t>(win) * N * p.k_rs;
+  const bf16* vb = p.v + static_cast<int64_t>(win) * N * p.v_rs;
+  const int cw = C >> 1;                                  // 32-bit words per row
+  for (int idx = threadIdx.x; idx < N * cw; idx += blockDim.x) {
+    int j = idx / cw, w = idx - j * cw;
+    uint32_t kk = reinterpret_cast<const uint32_t*>(kb + j * p.k_rs)[w];
+    uint32_t vv = reinterpret_cast<const uint32_t*>(vb + j * p.v_rs)[w];
+    int h = (2 * w) / hd, dd = 2 * w - h * hd;
+    *reinterpret_cast<uint32_t*>(Ks + (static_cast<size_t>(h) * N + j) * kst + dd) = kk;
+    reinterpret_cast<uint32_t*>(Vs + static_cast<size_t>(j) * C)[w] = vv;
+  }
+  __syncthreads();
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (h >= heads) return;
+  float* ps = Ps + h * 64;
+  float* qs = Qs + h * 32;
+  const bf16* Kh = Ks + static_cast<size_t>(h) * N * kst;
+  const int hw = hd >> 1;
+  const int G = 32 / hd, d = lane % hd, g = lane / hd;
+  const float* mbase = p.mask ? p.mask + static_cast<int64_t>(win % p.nW) * N * N : nullptr;
+  for (int qi = 0; qi < N; ++qi) {
+    const bf16* qrow = p.q + (static_cast<int64_t>(win) * N + qi) * p.q_rs + h * hd;
+    if (lane < hd) qs[lane] = __bfloat162float(qrow[lane]);
+    __syncwarp();
+    const float* brow = p.bias + (static_cast<int64_t>(h) * N + qi) * N;
+    float sc[2];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      int j = lane + 32 * r;
+      float s = -INFINITY;
+      if (j < N) {
+        const uint32_t* kr = reinterpret_cast<const uint32_t*>(Kh + static_cast<size_t>(j) * kst);
+        s = 0.f;
+        for (int w = 0; w < hw; ++w) {
+          float2 kk = gwd_unpack_bf16x2(kr[w]);
+          s = fmaf(qs[2 * w], kk.x, s);
+          s = fmaf(qs[2 * w + 1], kk.y, s);
+        }
+        s += brow[j];
+        if (mbase) s += mbase[qi * N + j];
+      }
+      sc[r] = s;
+      mx = fmaxf(mx, s);
+    }
+    mx = gwd_warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      int j = lane + 32 * r;
+      float e = j < N ? __expf(sc[r] - mx) : 0.f;
+      ps[j] = e;
+      sum += e;
+    }
+    sum = gwd_warp_sum(sum);
+    __syncwarp();
+    float acc = 0.f;
+    for (int j = g; j < N; j += G) acc = fmaf(ps[j], __bfloat162float(Vs[static_cast<size_t>(j) * C + h * hd + d]), acc);
+    for (int o = hd; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane < hd) p.o[(static_cast<int64_t>(win) * N + qi) * p.o_rs + h * hd + lane] = __float2bfloat16(acc / sum);
+    __syncwarp();
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // class-token channel attention (one CTA per window, one warp per head)
 //   tq  [items, N, tdim]        projected (cls_dth_q / cls_seg_q) class tokens, two of them (depth, seg)
@@ -119,29 +206,49 @@ struct TokAttnParams {
 
 __global__ void gwd_token_attention_kernel(const TokAttnParams p) {
   extern __shared__ __align__(16) uint8_t smem[];
-  // per warp: attn[2][td][tc] floats
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int N = p.N, td = p.td, tc = p.tc, heads = p.heads;
+  const int TQ = heads * td, TC = heads * tc;          // row widths of the query / key-value tensors
+  bf16* sk = reinterpret_cast<bf16*>(smem);            // [N][TC]
+  bf16* sv = sk + static_cast<size_t>(N) * TC;         // [N][TC]
+  bf16* sdq = sv + static_cast<size_t>(N) * TC;        // [N][TQ]
+  bf16* ssq = sdq + static_cast<size_t>(N) * TQ;       // [N][TQ]
+  float* Aall = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ssq + static_cast<size_t>(N) * TQ) + 15) & ~uintptr_t(15));
   const int item = blockIdx.x;
-  const int h = warp;
-  if (h >= p.heads) return;
-  float* A = reinterpret_cast<float*>(smem) + static_cast<size_t>(warp) * 2 * p.td * p.tc;
-  const int N = p.N, td = p.td, tc = p.tc;
-  const bf16* tk = p.tk + static_cast<int64_t>(item) * N * p.k_rs + h * tc;
-  const bf16* tv = p.tv + static_cast<int64_t>(item) * N * p.v_rs + h * tc;
-  // scores: (which, i, c) pairs distributed over lanes
+  {  // coalesced staging of the window's rows (32-bit words)
+    const int kw = TC >> 1, qw = TQ >> 1;
+    const bf16* gk = p.tk + static_cast<int64_t>(item) * N * p.k_rs;
+    const bf16* gv = p.tv + static_cast<int64_t>(item) * N * p.v_rs;
+    for (int i = threadIdx.x; i < N * kw; i += blockDim.x) {
+      int n = i / kw, w = i - n * kw;
+      reinterpret_cast<uint32_t*>(sk)[i] = reinterpret_cast<const uint32_t*>(gk + n * p.k_rs)[w];
+      reinterpret_cast<uint32_t*>(sv)[i] = reinterpret_cast<const uint32_t*>(gv + n * p.v_rs)[w];
+    }
+    const bf16* gd = p.dq + static_cast<int64_t>(item) * N * p.q_rs;
+    const bf16* gs = p.sq + static_cast<int64_t>(item) * N * p.q_rs;
+    for (int i = threadIdx.x; i < N * qw; i += blockDim.x) {
+      int n = i / qw, w = i - n * qw;
+      reinterpret_cast<uint32_t*>(sdq)[i] = reinterpret_cast<const uint32_t*>(gd + n * p.q_rs)[w];
+      reinterpret_cast<uint32_t*>(ssq)[i] = reinterpret_cast<const uint32_t*>(gs + n * p.q_rs)[w];
+    }
+  }
+  __syncthreads();
+  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (h >= heads) return;
+  float* A = Aall + static_cast<size_t>(h) * 2 * td * tc;
+  // scores A[which][i][c] = scale * sum_n tq[n][h*td+i] * tk[n][h*tc+c]
   const int npairs = 2 * td * tc;
   for (int e = lane; e < npairs; e += 32) {
     int which = e / (td * tc);
     int r = e - which * td * tc;
     int i = r / tc, c = r - i * tc;
-    const bf16* tq = (which == 0 ? p.dq : p.sq) + static_cast<int64_t>(item) * N * p.q_rs + h * td + i;
+    const bf16* tq = (which == 0 ? sdq : ssq) + h * td + i;
+    const bf16* tk = sk + h * tc + c;
     float s = 0.f;
-    for (int n = 0; n < N; ++n) s = fmaf(__bfloat162float(tq[n * p.q_rs]), __bfloat162float(tk[n * p.k_rs + c]), s);
+    for (int n = 0; n < N; ++n) s = fmaf(__bfloat162float(tq[n * TQ]), __bfloat162float(tk[n * TC]), s);
     A[e] = s * p.scale;
   }
   __syncwarp();
-  // softmax over c for each (which, i)
-  for (int r = lane; r < 2 * td; r += 32) {
+  for (int r = lane; r < 2 * td; r += 32) {   // softmax over c
     float* a = A + r * tc;
     float mx = -INFINITY;
     for (int c = 0; c < tc; ++c) mx = fmaxf(mx, a[c]);
@@ -151,14 +258,15 @@ __global__ void gwd_token_attention_kernel(const TokAttnParams p) {
     for (int c = 0; c < tc; ++c) a[c] *= inv;
   }
   __syncwarp();
-  // out[which][n][h*td+i] = sum_c A[which][i][c] * tv[n][c]
+  // out[which][n][h*td+i] = sum_c A[which][i][c] * tv[n][h*tc+c]
   for (int e = lane; e < 2 * N * td; e += 32) {
     int which = e / (N * td);
     int r = e - which * N * td;
     int n = r / td, i = r - n * td;
     const float* a = A + (which * td + i) * tc;
+    const bf16* tv = sv + static_cast<size_t>(n) * TC + h * tc;
     float s = 0.f;
-    for (int c = 0; c < tc; ++c) s = fmaf(a[c], __bfloat162float(tv[n * p.v_rs + c]), s);
+    for (int c = 0; c < tc; ++c) s = fmaf(a[c], __bfloat162float(tv[c]), s);
     bf16* o = (which == 0 ? p.dout : p.sout) + (static_cast<int64_t>(item) * N + n) * p.o_rs + h * td + i;
     *o = __float2bfloat16(s);
   }
@@ -167,111 +275,139 @@ __global__ void gwd_token_attention_kernel(const TokAttnParams p) {
 // -------------------------------------------------------------------------------------------------
 // line end-point re-query (1/32 scale)
 // -------------------------------------------------------------------------------------------------
-// scores[b][h][w*N+n][r] = scale * q[(b*nW+w)*N+n][h*hd:] . refk[b*R+r][h*hd:]     (fp32 out)
-__global__ void gwd_ref_scores_kernel(const bf16* __restrict__ q, int64_t q_rs, const float* __restrict__ refk,
-                                      int64_t ref_rs, float* __restrict__ out, int B, int nW, int N, int heads, int hd,
-                                      int R, float scale) {
-  int64_t total = static_cast<int64_t>(B) * heads * nW * N * R;
-  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    int r = idx % R;
-    int64_t t = idx / R;
-    int tok = t % (nW * N);
-    t /= (nW * N);
-    int h = t % heads;
-    int b = t / heads;
-    const bf16* qr = q + (static_cast<int64_t>(b) * nW * N + tok) * q_rs + h * hd;
-    const float* kr = refk + (static_cast<int64_t>(b) * R + r) * ref_rs + h * hd;
-    float s = 0.f;
-    for (int d = 0; d < hd; ++d) s = fmaf(__bfloat162float(qr[d]) * scale, kr[d], s);
-    out[idx] = s;
+// scores[b][h][tok][r] = scale * q[b*T+tok][h*hd:] . refk[b*R+r][h*hd:]     (fp32 out, T = nW*N tokens per image)
+// grid (token tiles, heads, B): ref_k of one (image, head) sits in shared memory, one thread per token
+__global__ void __launch_bounds__(128) gwd_ref_scores_kernel(const bf16* __restrict__ q, int64_t q_rs,
+                                                            const float* __restrict__ refk, int64_t ref_rs,
+                                                            float* __restrict__ out, int T, int heads, int hd, int R,
+                                                            float scale) {
+  extern __shared__ float rk[];  // [R][hd]
+  const int b = blockIdx.z, h = blockIdx.y;
+  for (int i = threadIdx.x; i < R * hd; i += blockDim.x) {
+    int r = i / hd, dd = i - r * hd;
+    rk[i] = refk[(static_cast<int64_t>(b) * R + r) * ref_rs + h * hd + dd] * scale;
+  }
+  __syncthreads();
+  int tok = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tok >= T) return;
+  float qv[32];
+  const bf16* qr = q + (static_cast<int64_t>(b) * T + tok) * q_rs + h * hd;
+#pragma unroll
+  for (int dd = 0; dd < 32; ++dd) qv[dd] = dd < hd ? __bfloat162float(qr[dd]) : 0.f;
+  float* o = out + ((static_cast<int64_t>(b) * heads + h) * T + tok) * R;
+  for (int r = 0; r < R; ++r) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int dd = 0; dd < 32; ++dd)
+      if (dd < hd) sacc = fmaf(qv[dd], rk[r * hd + dd], sacc);
+    o[r] = sacc;
   }
 }
 
-// one diffusion step: a += gelu(layer_norm_over_image(conv3x3(a)))   a: [B][heads][P][R] fp32
-// grid (heads_out, B); the conv output of one (b, oc) image is kept in shared memory (P*R floats)
-__global__ void __launch_bounds__(256) gwd_ref_diffuse_kernel(const float* __restrict__ a_in, float* __restrict__ a_out,
-                                                              const float* __restrict__ w, const float* __restrict__ bias,
-                                                              int heads, int P, int R) {
-  extern __shared__ float img[];
-  __shared__ float red[64];
-  const int oc = blockIdx.x, b = blockIdx.y;
-  const float* in_b = a_in + static_cast<int64_t>(b) * heads * P * R;
-  const int n = P * R;
-  float s = 0.f, ss = 0.f;
-  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-    int y = idx / R, x = idx - y * R;
-    float acc = bias[oc];
-    for (int ic = 0; ic < heads; ++ic) {
-      const float* src = in_b + static_cast<int64_t>(ic) * n;
-      const float* wk = w + (static_cast<int64_t>(oc) * heads + ic) * 9;
+// diffusion step, phase 1: raw = conv3x3_{heads->heads}(a) for a band of rows of one image, all output channels;
+// per-(image, channel) sum / sum of squares accumulated in fp64 for the whole-image LayerNorm of phase 2.
+// a: [B][heads][P][R] fp32.  grid (row bands, B), block 256.
+constexpr int kDiffBand = 21;
+__global__ void __launch_bounds__(256) gwd_ref_diffuse_conv_kernel(const float* __restrict__ a, float* __restrict__ raw,
+                                                                   const float* __restrict__ w, const float* __restrict__ bias,
+                                                                   double* __restrict__ stats, int heads, int P, int R) {
+  extern __shared__ float sm[];
+  float* tile = sm;                                       // [heads][band+2][R+2] zero padded
+  const int y0 = blockIdx.x * kDiffBand, b = blockIdx.y;
+  const int rows = min(kDiffBand, P - y0);
+  const int TR = kDiffBand + 2, TC = R + 2;
+  float* wsm = tile + static_cast<size_t>(heads) * TR * TC;  // [heads*heads*9]
+  for (int i = threadIdx.x; i < heads * heads * 9; i += blockDim.x) wsm[i] = w[i];
+  for (int i = threadIdx.x; i < heads * TR * TC; i += blockDim.x) {
+    int ic = i / (TR * TC);
+    int rem = i - ic * TR * TC;
+    int ty = rem / TC, tx = rem - ty * TC;
+    int y = y0 + ty - 1, x = tx - 1;
+    float v = 0.f;
+    if (y >= 0 && y < P && x >= 0 && x < R && ty < rows + 2) v = a[((static_cast<int64_t>(b) * heads + ic) * P + y) * R + x];
+    tile[i] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // each warp owns output channels oc = warp, warp + 8, ...; lanes stride over the band's pixels
+  for (int oc = warp; oc < heads; oc += 8) {
+    float s = 0.f, ss = 0.f;
+    for (int pix = lane; pix < rows * R; pix += 32) {
+      int ty = pix / R, tx = pix - ty * R;
+      float acc = bias[oc];
+      for (int ic = 0; ic < heads; ++ic) {
+        const float* t = tile + (static_cast<size_t>(ic) * TR + ty) * TC + tx;
+        const float* wk = wsm + (oc * heads + ic) * 9;
 #pragma unroll
-      for (int dy = -1; dy <= 1; ++dy) {
-        int yy = y + dy;
-        if (yy < 0 || yy >= P) continue;
+        for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          int xx = x + dx;
-          if (xx < 0 || xx >= R) continue;
-          acc = fmaf(wk[(dy + 1) * 3 + dx + 1], src[yy * R + xx], acc);
-        }
+          for (int dx = 0; dx < 3; ++dx) acc = fmaf(wk[dy * 3 + dx], t[dy * TC + dx], acc);
       }
+      raw[((static_cast<int64_t>(b) * heads + oc) * P + y0 + ty) * R + tx] = acc;
+      s += acc;
+      ss += acc * acc;
     }
-    img[idx] = acc;
-    s += acc;
-    ss += acc * acc;
-  }
-  s = gwd_warp_sum(s);
-  ss = gwd_warp_sum(ss);
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane == 0) { red[warp] = s; red[32 + warp] = ss; }
-  __syncthreads();
-  if (warp == 0) {
-    float a = lane < (blockDim.x >> 5) ? red[lane] : 0.f;
-    float c = lane < (blockDim.x >> 5) ? red[32 + lane] : 0.f;
-    a = gwd_warp_sum(a);
-    c = gwd_warp_sum(c);
-    if (lane == 0) { red[0] = a; red[32] = c; }
-  }
-  __syncthreads();
-  float mean = red[0] / n;
-  float var = fmaxf(red[32] / n - mean * mean, 0.f);
-  float rstd = rsqrtf(var + 1e-5f);
-  const float* res = in_b + static_cast<int64_t>(oc) * n;
-  float* dst = a_out + (static_cast<int64_t>(b) * heads + oc) * n;
-  for (int idx = threadIdx.x; idx < n; idx += blockDim.x) {
-    float v = (img[idx] - mean) * rstd;
-    dst[idx] = res[idx] + gwd_apply_act(v, GWD_ACT_GELU);
+    double ds = s, dss = ss;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      ds += __shfl_xor_sync(0xffffffffu, ds, o);
+      dss += __shfl_xor_sync(0xffffffffu, dss, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&stats[(static_cast<int64_t>(b) * heads + oc) * 2], ds);
+      atomicAdd(&stats[(static_cast<int64_t>(b) * heads + oc) * 2 + 1], dss);
+    }
   }
 }
 
-// q_new[(b*nW+w)*N+n][h*hd+d] = scale * sum_r softmax_r(a[b][h][w*N+n][:])[r] * refv[b*R+r][h*hd+d]   (bf16 out)
-// one warp per (b, h, token)
-__global__ void gwd_ref_requery_kernel(const float* __restrict__ a, const float* __restrict__ refv, int64_t ref_rs,
-                                       bf16* __restrict__ out, int64_t o_rs, int B, int nW, int N, int heads, int hd, int R,
-                                       float scale) {
-  int64_t wid = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  int64_t total = static_cast<int64_t>(B) * heads * nW * N;
-  if (wid >= total) return;
-  int tok = wid % (nW * N);
-  int64_t t = wid / (nW * N);
-  int h = t % heads;
-  int b = t / heads;
-  const float* row = a + wid * R;
-  float mx = -INFINITY;
-  for (int r = lane; r < R; r += 32) mx = fmaxf(mx, row[r]);
-  mx = gwd_warp_max(mx);
-  float sum = 0.f;
-  for (int r = lane; r < R; r += 32) sum += __expf(row[r] - mx);
-  sum = gwd_warp_sum(sum);
-  // lane <-> d (hd <= 32)
-  if (lane < hd) {
-    float acc = 0.f;
-    for (int r = 0; r < R; ++r)
-      acc = fmaf(__expf(row[r] - mx), refv[(static_cast<int64_t>(b) * R + r) * ref_rs + h * hd + lane], acc);
-    out[(static_cast<int64_t>(b) * nW * N + tok) * o_rs + h * hd + lane] = __float2bfloat16(acc / sum * scale);
+// phase 2: a_out = a_in + gelu((raw - mean) * rstd)   with mean / var over the whole [P,R] image of (b, channel)
+__global__ void gwd_ref_diffuse_norm_kernel(const float* __restrict__ a_in, const float* __restrict__ raw,
+                                            const double* __restrict__ stats, float* __restrict__ a_out, int64_t per_img,
+                                            int64_t total) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    int64_t img = i / per_img;
+    double mean = stats[img * 2] / per_img;
+    double var = stats[img * 2 + 1] / per_img - mean * mean;
+    float rstd = rsqrtf(static_cast<float>(var > 0 ? var : 0) + 1e-5f);
+    float v = (raw[i] - static_cast<float>(mean)) * rstd;
+    a_out[i] = a_in[i] + gwd_apply_act(v, GWD_ACT_GELU);
   }
+}
+
+// q_new[b*T+tok][h*hd+d] = scale * sum_r softmax_r(a[b][h][tok][:])[r] * refv[b*R+r][h*hd+d]   (bf16 out)
+// grid (token tiles, heads, B), one thread per token, ref_v of the (image, head) in shared memory
+__global__ void __launch_bounds__(128) gwd_ref_requery_kernel(const float* __restrict__ a, const float* __restrict__ refv,
+                                                             int64_t ref_rs, bf16* __restrict__ out, int64_t o_rs, int T,
+                                                             int heads, int hd, int R, float scale) {
+  extern __shared__ float rv[];  // [R][hd]
+  const int b = blockIdx.z, h = blockIdx.y;
+  for (int i = threadIdx.x; i < R * hd; i += blockDim.x) {
+    int r = i / hd, dd = i - r * hd;
+    rv[i] = refv[(static_cast<int64_t>(b) * R + r) * ref_rs + h * hd + dd];
+  }
+  __syncthreads();
+  int tok = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tok >= T) return;
+  const float* row = a + ((static_cast<int64_t>(b) * heads + h) * T + tok) * R;
+  float mx = -INFINITY;
+  for (int r = 0; r < R; ++r) mx = fmaxf(mx, row[r]);
+  float acc[32];
+#pragma unroll
+  for (int dd = 0; dd < 32; ++dd) acc[dd] = 0.f;
+  float sum = 0.f;
+  for (int r = 0; r < R; ++r) {
+    float e = __expf(row[r] - mx);
+    sum += e;
+#pragma unroll
+    for (int dd = 0; dd < 32; ++dd)
+      if (dd < hd) acc[dd] = fmaf(e, rv[r * hd + dd], acc[dd]);
+  }
+  float inv = scale / sum;
+  bf16* o = out + (static_cast<int64_t>(b) * T + tok) * o_rs + h * hd;
+#pragma unroll
+  for (int dd = 0; dd < 32; dd += 2)
+    if (dd < hd) *reinterpret_cast<uint32_t*>(o + dd) = gwd_pack_bf16x2(acc[dd] * inv, acc[dd + 1] * inv);
 }
 
 }  // namespace
@@ -287,6 +423,29 @@ extern "C" int gwd_attention(const gwd_attn_desc* d, void* stream_) {
   GWD_CHECK_ARG(d->k_row_stride % 2 == 0 && d->v_row_stride % 2 == 0 && d->k_item_stride % 2 == 0 && d->v_item_stride % 2 == 0 &&
                     (reinterpret_cast<uintptr_t>(d->k) & 3) == 0 && (reinterpret_cast<uintptr_t>(d->v) & 3) == 0,
                 "gwd_attention: K/V must be 4-byte aligned with even strides");
+  if (d->Lq == d->Lk && d->Lk <= 64 && d->bias != nullptr && d->key_padding == nullptr && d->scale == 1.0f &&
+      d->heads <= 32 && d->q_item_stride == d->Lq * d->q_row_stride && d->k_item_stride == d->Lk * d->k_row_stride &&
+      d->v_item_stride == d->Lk * d->v_row_stride && d->o_item_stride == d->Lq * d->o_row_stride) {
+    WinAttnParams w;
+    w.q = static_cast<const bf16*>(d->q); w.k = static_cast<const bf16*>(d->k); w.v = static_cast<const bf16*>(d->v);
+    w.o = static_cast<bf16*>(d->o);
+    w.windows = d->items; w.heads = d->heads; w.N = d->Lq; w.hd = d->hd;
+    w.q_rs = d->q_row_stride; w.k_rs = d->k_row_stride; w.v_rs = d->v_row_stride; w.o_rs = d->o_row_stride;
+    w.bias = d->bias; w.mask = d->mask; w.nW = d->mask_windows > 0 ? d->mask_windows : 1;
+    const int C = d->heads * d->hd;
+    size_t smem = static_cast<size_t>(d->heads) * d->Lk * (d->hd + 2) * 2 + static_cast<size_t>(d->Lk) * C * 2 + 16 +
+                  static_cast<size_t>(d->heads) * (64 + 32) * 4;
+    if (smem > 48 * 1024) {
+      static bool configured = false;
+      if (!configured) {
+        GWD_CUDA(cudaFuncSetAttribute(gwd_window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = true;
+      }
+    }
+    gwd_window_attention_kernel<<<d->items, d->heads * 32, smem, stream>>>(w);
+    GWD_LAUNCHED();
+    return GWD_OK;
+  }
   AttnParams p;
   p.q = static_cast<const bf16*>(d->q); p.k = static_cast<const bf16*>(d->k); p.v = static_cast<const bf16*>(d->v);
   p.o = static_cast<bf16*>(d->o);
@@ -324,7 +483,18 @@ extern "C" int gwd_token_attention(const void* dq, const void* sq, const void* t
   p.dout = static_cast<bf16*>(dout); p.sout = static_cast<bf16*>(sout);
   p.items = items; p.N = N; p.heads = heads; p.td = td; p.tc = tc;
   p.q_rs = q_rs; p.k_rs = k_rs; p.v_rs = v_rs; p.o_rs = o_rs; p.scale = scale;
-  size_t smem = static_cast<size_t>(heads) * 2 * td * tc * sizeof(float);
+  GWD_CHECK_ARG((heads * td) % 2 == 0 && (heads * tc) % 2 == 0 && q_rs % 2 == 0 && k_rs % 2 == 0 && v_rs % 2 == 0,
+                "gwd_token_attention: widths / strides must be even");
+  size_t smem = (static_cast<size_t>(N) * heads * tc * 2 + static_cast<size_t>(N) * heads * td * 2) * 2 + 16 +
+                static_cast<size_t>(heads) * 2 * td * tc * sizeof(float);
+  GWD_CHECK_ARG(smem <= 200 * 1024, "gwd_token_attention: window does not fit shared memory");
+  if (smem > 48 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      GWD_CUDA(cudaFuncSetAttribute(gwd_token_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+  }
   gwd_token_attention_kernel<<<items, heads * 32, smem, stream>>>(p);
   GWD_LAUNCHED();
   return GWD_OK;
@@ -333,29 +503,36 @@ extern "C" int gwd_token_attention(const void* dq, const void* sq, const void* t
 extern "C" int gwd_ref_scores(const void* q, int64_t q_rs, const float* refk, int64_t ref_rs, float* out, int32_t B,
                               int32_t nW, int32_t N, int32_t heads, int32_t hd, int32_t R, float scale, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  GWD_CHECK_ARG(q && refk && out, "gwd_ref_scores: null pointer");
-  int64_t total = static_cast<int64_t>(B) * heads * nW * N * R;
-  int blocks = static_cast<int>(std::min<int64_t>(gwd_ceil_div(total, 256), gwd_num_sms() * 8));
-  gwd_ref_scores_kernel<<<blocks, 256, 0, stream>>>(static_cast<const bf16*>(q), q_rs, refk, ref_rs, out, B, nW, N, heads,
-                                                    hd, R, scale);
+  GWD_CHECK_ARG(q && refk && out && hd <= 32 && hd % 2 == 0, "gwd_ref_scores: bad argument");
+  const int T = nW * N;
+  dim3 grid(static_cast<unsigned>(gwd_ceil_div(T, 128)), heads, B);
+  gwd_ref_scores_kernel<<<grid, 128, static_cast<size_t>(R) * hd * sizeof(float), stream>>>(
+      static_cast<const bf16*>(q), q_rs, refk, ref_rs, out, T, heads, hd, R, scale);
   GWD_LAUNCHED();
   return GWD_OK;
 }
 
-extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w, const float* bias, int32_t B, int32_t heads,
-                               int32_t P, int32_t R, void* stream_) {
+extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w, const float* bias, float* raw_ws,
+                               double* stats_ws, int32_t B, int32_t heads, int32_t P, int32_t R, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  GWD_CHECK_ARG(a_in && a_out && w && bias && a_in != a_out, "gwd_ref_diffuse: null / aliased pointer");
-  size_t smem = static_cast<size_t>(P) * R * sizeof(float);
-  GWD_CHECK_ARG(smem <= 200 * 1024, "gwd_ref_diffuse: image %dx%d too large", P, R);
+  GWD_CHECK_ARG(a_in && a_out && w && bias && raw_ws && stats_ws && a_in != a_out, "gwd_ref_diffuse: null / aliased pointer");
+  GWD_CHECK_ARG(heads <= 16, "gwd_ref_diffuse: at most 16 heads");
+  GWD_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * B * heads, stream));
+  size_t smem = (static_cast<size_t>(heads) * (kDiffBand + 2) * (R + 2) + static_cast<size_t>(heads) * heads * 9) * sizeof(float);
+  GWD_CHECK_ARG(smem <= 200 * 1024, "gwd_ref_diffuse: %d reference points do not fit shared memory", R);
   if (smem > 48 * 1024) {
     static bool configured = false;
     if (!configured) {
-      GWD_CUDA(cudaFuncSetAttribute(gwd_ref_diffuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GWD_CUDA(cudaFuncSetAttribute(gwd_ref_diffuse_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
     }
   }
-  gwd_ref_diffuse_kernel<<<dim3(heads, B), 256, smem, stream>>>(a_in, a_out, w, bias, heads, P, R);
+  dim3 grid(static_cast<unsigned>(gwd_ceil_div(P, kDiffBand)), B);
+  gwd_ref_diffuse_conv_kernel<<<grid, 256, smem, stream>>>(a_in, raw_ws, w, bias, stats_ws, heads, P, R);
+  GWD_LAUNCHED();
+  int64_t per_img = static_cast<int64_t>(P) * R, total = per_img * B * heads;
+  int blocks = static_cast<int>(std::min<int64_t>(gwd_ceil_div(total, 256), gwd_num_sms() * 8));
+  gwd_ref_diffuse_norm_kernel<<<blocks, 256, 0, stream>>>(a_in, raw_ws, stats_ws, a_out, per_img, total);
   GWD_LAUNCHED();
   return GWD_OK;
 }
@@ -363,11 +540,11 @@ extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w, 
 extern "C" int gwd_ref_requery(const float* a, const float* refv, int64_t ref_rs, void* out, int64_t o_rs, int32_t B,
                                int32_t nW, int32_t N, int32_t heads, int32_t hd, int32_t R, float scale, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  GWD_CHECK_ARG(a && refv && out && hd <= 32, "gwd_ref_requery: bad argument");
-  int64_t warps = static_cast<int64_t>(B) * heads * nW * N;
-  int blocks = static_cast<int>(gwd_ceil_div(warps * 32, 256));
-  gwd_ref_requery_kernel<<<blocks, 256, 0, stream>>>(a, refv, ref_rs, static_cast<bf16*>(out), o_rs, B, nW, N, heads, hd, R,
-                                                     scale);
+  GWD_CHECK_ARG(a && refv && out && hd <= 32 && hd % 2 == 0 && o_rs % 2 == 0, "gwd_ref_requery: bad argument");
+  const int T = nW * N;
+  dim3 grid(static_cast<unsigned>(gwd_ceil_div(T, 128)), heads, B);
+  gwd_ref_requery_kernel<<<grid, 128, static_cast<size_t>(R) * hd * sizeof(float), stream>>>(
+      a, refv, ref_rs, static_cast<bf16*>(out), o_rs, T, heads, hd, R, scale);
   GWD_LAUNCHED();
   return GWD_OK;
 }

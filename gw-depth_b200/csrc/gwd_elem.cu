@@ -22,15 +22,40 @@ __device__ __forceinline__ void store8(bf16* p, const float (&f)[8]) {
   *reinterpret_cast<uint4*>(p) = u;
 }
 
-// row held by a warp: vector v of lane l covers channels (v*32 + l)*8 .. +8
+// A token row is held by a GROUP of G lanes (G = 8, 16 or 32, a power of two >= C/8 capped at 32), so narrow rows
+// (C = 64 at the 1/4 scale) keep all 32 lanes of a warp busy: a warp owns 32/G rows.  Vector v of sub-lane s covers
+// channels (v*G + s)*8 .. +8.
+struct RowGroup {
+  int G, sub;        // group width, lane index inside the group
+  int64_t row;       // row owned by this lane's group
+};
+__device__ __forceinline__ RowGroup row_group(int C) {
+  RowGroup rg;
+  int need = C >> 3;
+  rg.G = need <= 8 ? 8 : (need <= 16 ? 16 : 32);
+  int lane = threadIdx.x & 31;
+  rg.sub = lane & (rg.G - 1);
+  int64_t warp = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
+  rg.row = warp * (32 / rg.G) + lane / rg.G;
+  return rg;
+}
+__host__ __device__ inline int rows_per_warp(int C) {
+  int need = C >> 3;
+  return need <= 8 ? 4 : (need <= 16 ? 2 : 1);
+}
+__device__ __forceinline__ float group_sum(float v, int G) {
+  for (int o = G >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
 struct WarpRow {
   float f[kMaxVec][8];
 };
 
-__device__ __forceinline__ void row_load(WarpRow& r, const bf16* src, int C, int lane, bool valid) {
+__device__ __forceinline__ void row_load(WarpRow& r, const bf16* src, int C, const RowGroup& g, bool valid) {
 #pragma unroll
   for (int v = 0; v < kMaxVec; ++v) {
-    int c = (v * 32 + lane) * 8;
+    int c = (v * g.G + g.sub) * 8;
     if (c < C && valid) load8(src + c, r.f[v]);
     else {
 #pragma unroll
@@ -38,10 +63,10 @@ __device__ __forceinline__ void row_load(WarpRow& r, const bf16* src, int C, int
     }
   }
 }
-__device__ __forceinline__ void row_add(WarpRow& r, const bf16* src, int C, int lane) {
+__device__ __forceinline__ void row_add(WarpRow& r, const bf16* src, int C, const RowGroup& g) {
 #pragma unroll
   for (int v = 0; v < kMaxVec; ++v) {
-    int c = (v * 32 + lane) * 8;
+    int c = (v * g.G + g.sub) * 8;
     if (c < C) {
       float t[8];
       load8(src + c, t);
@@ -50,41 +75,42 @@ __device__ __forceinline__ void row_add(WarpRow& r, const bf16* src, int C, int 
     }
   }
 }
-__device__ __forceinline__ void row_store(const WarpRow& r, bf16* dst, int C, int lane) {
+__device__ __forceinline__ void row_store(const WarpRow& r, bf16* dst, int C, const RowGroup& g) {
 #pragma unroll
   for (int v = 0; v < kMaxVec; ++v) {
-    int c = (v * 32 + lane) * 8;
+    int c = (v * g.G + g.sub) * 8;
     if (c < C) store8(dst + c, r.f[v]);
   }
 }
-// LayerNorm over the first n channels (channels >= n are padding and come out as 0)
-__device__ __forceinline__ void row_layernorm(WarpRow& r, int C, int n, int lane, const float* g, const float* b, float eps) {
+// LayerNorm over the first n channels (channels >= n are padding and come out as 0).  Every lane of the warp must call.
+__device__ __forceinline__ void row_layernorm(WarpRow& r, int C, int n, const RowGroup& g, const float* gam, const float* bet,
+                                              float eps) {
   float s = 0.f;
 #pragma unroll
   for (int v = 0; v < kMaxVec; ++v) {
-    int c = (v * 32 + lane) * 8;
+    int c = (v * g.G + g.sub) * 8;
     if (c < C) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) if (c + i < n) s += r.f[v][i];
     }
   }
-  float mean = gwd_warp_sum(s) / n;
+  float mean = group_sum(s, g.G) / n;
   float ss = 0.f;
 #pragma unroll
   for (int v = 0; v < kMaxVec; ++v) {
-    int c = (v * 32 + lane) * 8;
+    int c = (v * g.G + g.sub) * 8;
     if (c < C) {
 #pragma unroll
       for (int i = 0; i < 8; ++i) if (c + i < n) { float dlt = r.f[v][i] - mean; ss += dlt * dlt; }
     }
   }
-  float rstd = rsqrtf(gwd_warp_sum(ss) / n + eps);
+  float rstd = rsqrtf(group_sum(ss, g.G) / n + eps);
 #pragma unroll
   for (int v = 0; v < kMaxVec; ++v) {
-    int c = (v * 32 + lane) * 8;
+    int c = (v * g.G + g.sub) * 8;
     if (c < C) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r.f[v][i] = (c + i < n) ? (r.f[v][i] - mean) * rstd * g[c + i] + b[c + i] : 0.f;
+      for (int i = 0; i < 8; ++i) r.f[v][i] = (c + i < n) ? (r.f[v][i] - mean) * rstd * gam[c + i] + bet[c + i] : 0.f;
     }
   }
 }
@@ -102,27 +128,26 @@ __device__ __forceinline__ void row_act(WarpRow& r, int act) {
 __global__ void gwd_layernorm_kernel(const bf16* x, int64_t x_rs, const bf16* res, int64_t res_rs, const float* g,
                                      const float* b, float eps, int act, bf16* out, int64_t out_rs, int64_t rows, int C,
                                      int n) {
-  int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  RowGroup rg = row_group(C);
+  bool live = rg.row < rows;
+  int64_t row = live ? rg.row : 0;
   WarpRow r;
-  row_load(r, x + row * x_rs, C, lane, true);
-  if (res) row_add(r, res + row * res_rs, C, lane);
-  if (g) row_layernorm(r, C, n, lane, g, b, eps);
+  row_load(r, x + row * x_rs, C, rg, live);
+  if (res && live) row_add(r, res + row * res_rs, C, rg);
+  if (g) row_layernorm(r, C, n, rg, g, b, eps);
   row_act(r, act);
-  row_store(r, out + row * out_rs, C, lane);
+  if (live) row_store(r, out + row * out_rs, C, rg);
 }
 
 // out[row] = x[row] + addend[row % period]
 __global__ void gwd_add_rows_kernel(const bf16* x, int64_t x_rs, const bf16* addend, int64_t a_rs, int64_t period,
                                     bf16* out, int64_t out_rs, int64_t rows, int C) {
-  int64_t row = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  RowGroup rg = row_group(C);
+  if (rg.row >= rows) return;
   WarpRow r;
-  row_load(r, x + row * x_rs, C, lane, true);
-  row_add(r, addend + (row % period) * a_rs, C, lane);
-  row_store(r, out + row * out_rs, C, lane);
+  row_load(r, x + rg.row * x_rs, C, rg, true);
+  row_add(r, addend + (rg.row % period) * a_rs, C, rg);
+  row_store(r, out + rg.row * out_rs, C, rg);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -147,26 +172,32 @@ __device__ __forceinline__ bool win_source(const WinGeom& gm, int64_t orow, int&
 }
 __global__ void gwd_window_gather_kernel(const bf16* x, int64_t x_rs, const float* g, const float* b, float eps, bf16* out,
                                          int64_t out_rs, WinGeom gm, int C, int n) {
-  int64_t orow = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
+  RowGroup rg = row_group(C);
   int64_t rows = static_cast<int64_t>(gm.B) * gm.Hp * gm.Wp;
-  if (orow >= rows) return;
+  bool live = rg.row < rows;
+  int64_t orow = live ? rg.row : 0;
   int bb, y, xx;
-  bool valid = win_source(gm, orow, bb, y, xx);
+  bool valid = win_source(gm, orow, bb, y, xx) && live;
   WarpRow r;
-  row_load(r, x + ((static_cast<int64_t>(bb) * gm.H + y) * gm.W + xx) * x_rs, C, lane, valid);
-  if (valid && g) row_layernorm(r, C, n, lane, g, b, eps);
-  row_store(r, out + orow * out_rs, C, lane);
+  row_load(r, x + ((static_cast<int64_t>(bb) * gm.H + (valid ? y : 0)) * gm.W + (valid ? xx : 0)) * x_rs, C, rg, valid);
+  if (g) row_layernorm(r, C, n, rg, g, b, eps);
+  if (!valid) {   // padding tokens are exact zeros, not LN(0)  (zero padding happens after norm1, :659-671)
+#pragma unroll
+    for (int v = 0; v < kMaxVec; ++v)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r.f[v][i] = 0.f;
+  }
+  if (live) row_store(r, out + orow * out_rs, C, rg);
 }
 
 // Swin window merge: y[b,y,x] = shortcut[b,y,x] + win[row(b,y,x)]; optionally y_ln = LN(y)   (:731-755)
 __global__ void gwd_window_merge_kernel(const bf16* win, int64_t win_rs, const bf16* shortcut, int64_t sc_rs, bf16* out,
                                         int64_t out_rs, const float* g, const float* b, float eps, bf16* out_ln,
                                         int64_t ln_rs, WinGeom gm, int C, int n) {
-  int64_t pix = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
-  int lane = threadIdx.x & 31;
+  RowGroup rg = row_group(C);
   int64_t rows = static_cast<int64_t>(gm.B) * gm.H * gm.W;
-  if (pix >= rows) return;
+  bool live = rg.row < rows;
+  int64_t pix = live ? rg.row : 0;
   int x = pix % gm.W;
   int y = (pix / gm.W) % gm.H;
   int bb = pix / (static_cast<int64_t>(gm.W) * gm.H);
@@ -175,12 +206,14 @@ __global__ void gwd_window_merge_kernel(const bf16* win, int64_t win_rs, const b
   int64_t wrow = ((static_cast<int64_t>(bb) * nWy + ys / gm.ws) * nWx + xs / gm.ws) * (gm.ws * gm.ws) +
                  (ys % gm.ws) * gm.ws + xs % gm.ws;
   WarpRow r;
-  row_load(r, win + wrow * win_rs, C, lane, true);
-  row_add(r, shortcut + pix * sc_rs, C, lane);
-  row_store(r, out + pix * out_rs, C, lane);
+  row_load(r, win + wrow * win_rs, C, rg, live);
+  if (live) {
+    row_add(r, shortcut + pix * sc_rs, C, rg);
+    row_store(r, out + pix * out_rs, C, rg);
+  }
   if (out_ln) {
-    row_layernorm(r, C, n, lane, g, b, eps);
-    row_store(r, out_ln + pix * ln_rs, C, lane);
+    row_layernorm(r, C, n, rg, g, b, eps);
+    if (live) row_store(r, out_ln + pix * ln_rs, C, rg);
   }
 }
 
@@ -425,7 +458,7 @@ extern "C" int gwd_layernorm(const void* x, int64_t x_rs, const void* res, int64
   GWD_CHECK_ARG(x && out && rows > 0, "gwd_layernorm: null pointer / empty");
   GWD_CHECK_ARG(GWD_ALIGN8(C) && C <= 2048 && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs) && GWD_ALIGN8(res_rs),
                 "gwd_layernorm: C and strides must be multiples of 8, C <= 2048");
-  gwd_layernorm_kernel<<<static_cast<unsigned>(gwd_ceil_div(rows * 32, 256)), 256, 0, stream>>>(
+  gwd_layernorm_kernel<<<static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), 256, 0, stream>>>(
       static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(res), res_rs, gamma, beta, eps, act,
       static_cast<bf16*>(out), out_rs, rows, C, n);
   GWD_LAUNCHED();
@@ -438,7 +471,7 @@ extern "C" int gwd_add_rows(const void* x, int64_t x_rs, const void* addend, int
   GWD_CHECK_ARG(x && addend && out && rows > 0 && period > 0, "gwd_add_rows: bad argument");
   GWD_CHECK_ARG(GWD_ALIGN8(C) && C <= 2048 && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs) && GWD_ALIGN8(a_rs),
                 "gwd_add_rows: alignment");
-  gwd_add_rows_kernel<<<static_cast<unsigned>(gwd_ceil_div(rows * 32, 256)), 256, 0, stream>>>(
+  gwd_add_rows_kernel<<<static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), 256, 0, stream>>>(
       static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(addend), a_rs, period, static_cast<bf16*>(out), out_rs,
       rows, C);
   GWD_LAUNCHED();
@@ -461,7 +494,7 @@ extern "C" int gwd_window_gather(const void* x, int64_t x_rs, const float* gamma
   WinGeom gm;
   make_geom(gm, B, H, W, ws, shift);
   int64_t rows = static_cast<int64_t>(B) * gm.Hp * gm.Wp;
-  gwd_window_gather_kernel<<<static_cast<unsigned>(gwd_ceil_div(rows * 32, 256)), 256, 0, stream>>>(
+  gwd_window_gather_kernel<<<static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), 256, 0, stream>>>(
       static_cast<const bf16*>(x), x_rs, gamma, beta, eps, static_cast<bf16*>(out), out_rs, gm, C, n);
   GWD_LAUNCHED();
   return GWD_OK;
@@ -479,7 +512,7 @@ extern "C" int gwd_window_merge(const void* win, int64_t win_rs, const void* sho
   WinGeom gm;
   make_geom(gm, B, H, W, ws, shift);
   int64_t rows = static_cast<int64_t>(B) * H * W;
-  gwd_window_merge_kernel<<<static_cast<unsigned>(gwd_ceil_div(rows * 32, 256)), 256, 0, stream>>>(
+  gwd_window_merge_kernel<<<static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), 256, 0, stream>>>(
       static_cast<const bf16*>(win), win_rs, static_cast<const bf16*>(shortcut), sc_rs, static_cast<bf16*>(out), out_rs,
       gamma, beta, eps, static_cast<bf16*>(out_ln), ln_rs, gm, C, n);
   GWD_LAUNCHED();

@@ -169,7 +169,17 @@ struct RowCtx {
   int64_t pix;  // linear pixel index (b*H + y)*W + x
 };
 
+template <int ACT>
+__device__ __forceinline__ float act_fn(float v) {
+  if (ACT == GWD_ACT_RELU) return fmaxf(v, 0.f);
+  if (ACT == GWD_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  if (ACT == GWD_ACT_ELU) return v > 0.f ? v : expm1f(v);
+  if (ACT == GWD_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+
 // loads 16 accumulator columns starting at chunk c0 (relative to tile) and applies bias/pre_act/res(before)
+template <int PRE_ACT>
 __device__ __forceinline__ void load_chunk(const GemmParams& p, uint32_t taddr, int n_base, const RowCtx& rc,
                                            float (&v)[16]) {
   uint32_t r[16];
@@ -187,9 +197,9 @@ __device__ __forceinline__ void load_chunk(const GemmParams& p, uint32_t taddr, 
       v[4 * i + 3] += b4.w;
     }
   }
-  if (p.pre_act != GWD_ACT_NONE) {
+  if (PRE_ACT != GWD_ACT_NONE) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = gwd_apply_act(v[i], p.pre_act);
+    for (int i = 0; i < 16; ++i) v[i] = act_fn<PRE_ACT>(v[i]);
   }
   if (p.res_mode == GWD_RES_BEFORE_NORM && rc.valid) {
     const uint4* rp = reinterpret_cast<const uint4*>(p.res + rc.pix * p.res_cstride + p.res_coff + n_base);
@@ -222,6 +232,9 @@ __device__ __forceinline__ void store_bf16_16(__nv_bfloat16* dst, const float (&
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
+// PRE_ACT / POST_ACT / HAS_LN are compile-time so that each instantiation carries one activation body instead of a
+// 5-way switch unrolled 16x at three sites (that version was instruction-fetch bound: ~100 KB of SASS per kernel)
+template <int PRE_ACT, int POST_ACT, bool HAS_LN>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ GemmParams p) {
@@ -351,12 +364,12 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                              (static_cast<uint32_t>(quad * 32) << 16);
 
       float mean = 0.f, rstd = 1.f;
-      if (p.ln_g != nullptr) {
+      if (HAS_LN) {
         // statistics over the n logical channels of this pixel (both halves read the whole row)
         float s = 0.f, ss = 0.f;
         for (int c = 0; c < nchunks; ++c) {
           float v[16];
-          load_chunk(p, t_row + c * 16, t.n0 + c * 16, rc, v);
+          load_chunk<PRE_ACT>(p, t_row + c * 16, t.n0 + c * 16, rc, v);
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             if (t.n0 + c * 16 + i < p.n) {
@@ -373,11 +386,11 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       for (int c = c_begin; c < c_end; ++c) {
         const int n_base = t.n0 + c * 16;
         float v[16];
-        load_chunk(p, t_row + c * 16, n_base, rc, v);
+        load_chunk<PRE_ACT>(p, t_row + c * 16, n_base, rc, v);
         if (p.y_raw != nullptr && rc.valid) {
           store_bf16_16(p.y_raw + rc.pix * p.yraw_cstride + p.yraw_coff + n_base, v, n_base, p.store_n);
         }
-        if (p.ln_g != nullptr) {
+        if (HAS_LN) {
           const float4* gp = reinterpret_cast<const float4*>(p.ln_g + n_base);
           const float4* bp = reinterpret_cast<const float4*>(p.ln_b + n_base);
 #pragma unroll
@@ -389,9 +402,9 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * g4.w + b4.w;
           }
         }
-        if (p.post_act != GWD_ACT_NONE) {
+        if (POST_ACT != GWD_ACT_NONE) {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = gwd_apply_act(v[i], p.post_act);
+          for (int i = 0; i < 16; ++i) v[i] = act_fn<POST_ACT>(v[i]);
         }
         if (p.out_scale != 1.f) {
 #pragma unroll
@@ -610,15 +623,37 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
 
   const size_t smem_bytes = 1024 + static_cast<size_t>(p.stages) * (p.a_stage_bytes + p.b_stage_bytes) +
                             (2 * kMaxStages + 4) * sizeof(uint64_t) + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    GWD_CUDA(cudaFuncSetAttribute(gwd_tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const int total_tiles = p.m_tiles * p.n_tiles;
   int grid = gwd_num_sms();
   if (grid > total_tiles) grid = total_tiles;
-  gwd_tapgemm_kernel<<<grid, kNumThreads, smem_bytes, stream>>>(map_a, map_b, p);
+  const bool has_ln = d->ln_g != nullptr;
+#define GWD_GEMM_CASE(PRE, POST, LN)                                                                          \
+  if (d->pre_act == PRE && d->post_act == POST && has_ln == LN) {                                             \
+    static bool attr_set = false;                                                                             \
+    if (!attr_set) {                                                                                          \
+      GWD_CUDA(cudaFuncSetAttribute(gwd_tapgemm_kernel<PRE, POST, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                    227 * 1024));                                                             \
+      attr_set = true;                                                                                        \
+    }                                                                                                         \
+    gwd_tapgemm_kernel<PRE, POST, LN><<<grid, kNumThreads, smem_bytes, stream>>>(map_a, map_b, p);            \
+    launched = true;                                                                                          \
+  }
+  bool launched = false;
+  GWD_GEMM_CASE(GWD_ACT_NONE, GWD_ACT_NONE, false)
+  else GWD_GEMM_CASE(GWD_ACT_NONE, GWD_ACT_RELU, false)
+  else GWD_GEMM_CASE(GWD_ACT_NONE, GWD_ACT_GELU, false)
+  else GWD_GEMM_CASE(GWD_ACT_NONE, GWD_ACT_ELU, false)
+  else GWD_GEMM_CASE(GWD_ACT_NONE, GWD_ACT_SIGMOID, false)
+  else GWD_GEMM_CASE(GWD_ACT_NONE, GWD_ACT_NONE, true)
+  else GWD_GEMM_CASE(GWD_ACT_NONE, GWD_ACT_GELU, true)
+  else GWD_GEMM_CASE(GWD_ACT_NONE, GWD_ACT_RELU, true)
+  else GWD_GEMM_CASE(GWD_ACT_ELU, GWD_ACT_NONE, true)
+#undef GWD_GEMM_CASE
+  if (!launched) {
+    gwd_set_error("gwd_conv_gemm: epilogue combination pre_act=%d post_act=%d ln=%d is not instantiated", d->pre_act,
+                  d->post_act, static_cast<int>(has_ln));
+    return GWD_ERR_ARG;
+  }
   GWD_LAUNCHED();
   return GWD_OK;
 }

@@ -382,6 +382,8 @@ class Engine:
         mask = self.table(("mask", H, W), lambda: shift_mask(H, W, ws, ws // 2, self.dev))
         a0 = torch.empty(B, nh, P, R, dtype=torch.float32, device=self.dev)
         a1 = torch.empty_like(a0)
+        raw_ws = torch.empty_like(a0)
+        stats_ws = torch.empty(B * nh * 2, dtype=torch.float64, device=self.dev)
         for i, blk in enumerate(self.line_blocks):
             shift = 0 if i % 2 == 0 else ws // 2
             xw = ops.window_gather(x, B, H, W, ws, shift, blk["n1"].g, blk["n1"].b)
@@ -389,9 +391,9 @@ class Engine:
             qkv = conv_gemm(xw, blk["qkv"])
             refkv = conv_gemm(xref.view(B * R, D), blk["ref"], out_f32=True)
             ops.ref_scores(qkv, 3 * D, refkv, 2 * D, a0, B, nW, N, nh, hd, R)
-            ops.ref_diffuse(a0, a1, blk["diff_w"], blk["diff_b"], B, nh, P, R)
-            ops.ref_diffuse(a1, a0, blk["diff_w"], blk["diff_b"], B, nh, P, R)
-            ops.ref_diffuse(a0, a1, blk["diff_w"], blk["diff_b"], B, nh, P, R)
+            ops.ref_diffuse(a0, a1, blk["diff_w"], blk["diff_b"], raw_ws, stats_ws, B, nh, P, R)
+            ops.ref_diffuse(a1, a0, blk["diff_w"], blk["diff_b"], raw_ws, stats_ws, B, nh, P, R)
+            ops.ref_diffuse(a0, a1, blk["diff_w"], blk["diff_b"], raw_ws, stats_ws, B, nh, P, R)
             qnew = torch.empty(B * P, D, dtype=torch.bfloat16, device=self.dev)
             ops.ref_requery(a1, refkv[:, D:], 2 * D, qnew, D, B, nW, N, nh, hd, R, hd ** -0.5)
             o = torch.empty(B * P, D, dtype=torch.bfloat16, device=self.dev)

@@ -191,9 +191,9 @@ def ref_scores(q, q_rs, ref_k, ref_rs, out, B, nW, N, heads, hd, R, scale=1.0):
                                    _stream()), "gwd_ref_scores")
 
 
-def ref_diffuse(a_in, a_out, w, b, B, heads, P, R):
-    capi.check(_L().gwd_ref_diffuse(_ptr(a_in), _ptr(a_out), _ptr(w), _ptr(b), B, heads, P, R, _stream()),
-               "gwd_ref_diffuse")
+def ref_diffuse(a_in, a_out, w, b, raw_ws, stats_ws, B, heads, P, R):
+    capi.check(_L().gwd_ref_diffuse(_ptr(a_in), _ptr(a_out), _ptr(w), _ptr(b), _ptr(raw_ws), _ptr(stats_ws), B, heads, P, R,
+                                    _stream()), "gwd_ref_diffuse")
 
 
 def ref_requery(a, ref_v, ref_rs, out, o_rs, B, nW, N, heads, hd, R, scale):
