@@ -7,6 +7,7 @@
 //   gwd_token_attention  per-window class-token CHANNEL attention, multiscale_transformerr.py:561-578
 //   gwd_ref_scores / gwd_ref_diffuse / gwd_ref_requery
 //                        the line end-point ("glass structure") re-query of WindowAttention, :281-310
+#include <string.h>
 #include <algorithm>
 #include "gwd_common.cuh"
 
@@ -26,168 +27,93 @@ struct AttnParams {
   int q_tile;
 };
 
-constexpr int kAttnWarps = 4;
 
-__global__ void __launch_bounds__(kAttnWarps * 32) gwd_attention_kernel(const AttnParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const int hd = p.hd, Lk = p.Lk;
-  const int kstride = hd + 2;  // bf16 elements per padded K row (odd number of 32-bit words -> no bank conflicts)
-  bf16* Ks = reinterpret_cast<bf16*>(smem);
-  bf16* Vs = Ks + static_cast<size_t>(Lk) * kstride;
-  float* Ps = reinterpret_cast<float*>(Vs + static_cast<size_t>(Lk) * hd + 8);
-  Ps = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(Ps) + 15) & ~uintptr_t(15));
-  float* Qs = Ps + static_cast<size_t>(kAttnWarps) * Lk;
-
+// -------------------------------------------------------------------------------------------------
+// thread-per-query attention: one CTA per (item, head, query tile); K and V of the (item, head) are staged in shared
+// memory as fp32 and every lane owns ONE query: it walks the keys with an online softmax, reading K/V rows as
+// warp-wide broadcasts (no shuffles, no per-query synchronisation).  HD is a template parameter so q / acc stay in
+// registers.
+// -------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void __launch_bounds__(128) gwd_attention_tq_kernel(const AttnParams p) {
+  extern __shared__ __align__(16) float smf[];
+  const int Lk = p.Lk;
+  float* Ks = smf;                                  // [Lk][HD]
+  float* Vs = smf + static_cast<size_t>(Lk) * HD;   // [Lk][HD]
   const int item = blockIdx.z, head = blockIdx.y;
-  const int q0 = blockIdx.x * p.q_tile;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // stage K and V of this (item, head): bf16x2 granularity (hd is even)
-  const bf16* kbase = p.k + item * p.k_is + head * hd;
-  const bf16* vbase = p.v + item * p.v_is + head * hd;
-  const int hw = hd >> 1;
-  for (int idx = threadIdx.x; idx < Lk * hw; idx += blockDim.x) {
-    int j = idx / hw, w = idx - j * hw;
-    reinterpret_cast<uint32_t*>(Ks + static_cast<size_t>(j) * kstride)[w] =
-        reinterpret_cast<const uint32_t*>(kbase + j * p.k_rs)[w];
-    reinterpret_cast<uint32_t*>(Vs + static_cast<size_t>(j) * hd)[w] =
-        reinterpret_cast<const uint32_t*>(vbase + j * p.v_rs)[w];
+  const bf16* kbase = p.k + item * p.k_is + head * HD;
+  const bf16* vbase = p.v + item * p.v_is + head * HD;
+  constexpr int HW = HD / 2;
+  for (int idx = threadIdx.x; idx < Lk * HW; idx += blockDim.x) {
+    int j = idx / HW, w = idx - j * HW;
+    float2 kk = gwd_unpack_bf16x2(reinterpret_cast<const uint32_t*>(kbase + j * p.k_rs)[w]);
+    float2 vv = gwd_unpack_bf16x2(reinterpret_cast<const uint32_t*>(vbase + j * p.v_rs)[w]);
+    Ks[j * HD + 2 * w] = kk.x; Ks[j * HD + 2 * w + 1] = kk.y;
+    Vs[j * HD + 2 * w] = vv.x; Vs[j * HD + 2 * w + 1] = vv.y;
   }
   __syncthreads();
-
-  float* ps = Ps + static_cast<size_t>(warp) * Lk;
-  float* qs = Qs + warp * 32;
-  const int G = 32 / hd;           // key groups in the PV pass
-  const int d = lane % hd, g = lane / hd;
-  const int q_end = min(q0 + p.q_tile, p.Lq);
-  for (int qi = q0 + warp; qi < q_end; qi += kAttnWarps) {
-    const bf16* qrow = p.q + item * p.q_is + static_cast<int64_t>(qi) * p.q_rs + head * hd;
-    if (lane < hd) qs[lane] = __bfloat162float(qrow[lane]) * p.scale;
-    __syncwarp();
-    const float* brow = p.bias ? p.bias + (static_cast<int64_t>(head) * p.Lq + qi) * Lk : nullptr;
-    const float* mrow = p.mask ? p.mask + (static_cast<int64_t>(item % p.nW) * p.Lq + qi) * Lk : nullptr;
-    const uint8_t* kp = p.kpm ? p.kpm + static_cast<int64_t>(item) * Lk : nullptr;
-    float mx = -INFINITY;
-    for (int j = lane; j < Lk; j += 32) {
-      const uint32_t* kr = reinterpret_cast<const uint32_t*>(Ks + static_cast<size_t>(j) * kstride);
-      float s = 0.f;
-#pragma unroll 4
-      for (int w = 0; w < hw; ++w) {
-        float2 kk = gwd_unpack_bf16x2(kr[w]);
-        s = fmaf(qs[2 * w], kk.x, s);
-        s = fmaf(qs[2 * w + 1], kk.y, s);
-      }
-      if (brow) s += brow[j];
-      if (mrow) s += mrow[j];
-      if (kp && kp[j]) s = -INFINITY;
-      ps[j] = s;
-      mx = fmaxf(mx, s);
-    }
-    mx = gwd_warp_max(mx);
-    float sum = 0.f;
-    for (int j = lane; j < Lk; j += 32) {
-      float e = __expf(ps[j] - mx);
-      ps[j] = e;
-      sum += e;
-    }
-    sum = gwd_warp_sum(sum);
-    __syncwarp();
-    float acc = 0.f;
-    for (int j = g; j < Lk; j += G) acc = fmaf(ps[j], __bfloat162float(Vs[static_cast<size_t>(j) * hd + d]), acc);
-    for (int o = hd; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane < hd) {
-      bf16* orow = p.o + item * p.o_is + static_cast<int64_t>(qi) * p.o_rs + head * hd;
-      orow[lane] = __float2bfloat16(acc / sum);
-    }
-    __syncwarp();
+  const int qi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (qi >= p.Lq) return;
+  float q[HD], acc[HD];
+  const bf16* qrow = p.q + item * p.q_is + static_cast<int64_t>(qi) * p.q_rs + head * HD;
+#pragma unroll
+  for (int w = 0; w < HW; ++w) {
+    float2 t = gwd_unpack_bf16x2(reinterpret_cast<const uint32_t*>(qrow)[w]);
+    q[2 * w] = t.x * p.scale; q[2 * w + 1] = t.y * p.scale;
   }
+#pragma unroll
+  for (int d = 0; d < HD; ++d) acc[d] = 0.f;
+  const float* brow = p.bias ? p.bias + (static_cast<int64_t>(head) * p.Lq + qi) * Lk : nullptr;
+  const float* mrow = p.mask ? p.mask + (static_cast<int64_t>(item % p.nW) * p.Lq + qi) * Lk : nullptr;
+  const uint8_t* kp = p.kpm ? p.kpm + static_cast<int64_t>(item) * Lk : nullptr;
+  float m = -INFINITY, l = 0.f;
+  for (int j = 0; j < Lk; ++j) {
+    const float4* kr = reinterpret_cast<const float4*>(Ks + j * HD);
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < HD / 4; ++w) {
+      float4 k4 = kr[w];
+      s = fmaf(q[4 * w], k4.x, s); s = fmaf(q[4 * w + 1], k4.y, s);
+      s = fmaf(q[4 * w + 2], k4.z, s); s = fmaf(q[4 * w + 3], k4.w, s);
+    }
+    if (brow) s += __ldg(brow + j);
+    if (mrow) s += __ldg(mrow + j);
+    if (kp && kp[j]) continue;
+    float mn = fmaxf(m, s);
+    float corr = __expf(m - mn), pj = __expf(s - mn);
+    m = mn;
+    l = l * corr + pj;
+    const float4* vr = reinterpret_cast<const float4*>(Vs + j * HD);
+#pragma unroll
+    for (int w = 0; w < HD / 4; ++w) {
+      float4 v4 = vr[w];
+      acc[4 * w] = fmaf(acc[4 * w], corr, pj * v4.x); acc[4 * w + 1] = fmaf(acc[4 * w + 1], corr, pj * v4.y);
+      acc[4 * w + 2] = fmaf(acc[4 * w + 2], corr, pj * v4.z); acc[4 * w + 3] = fmaf(acc[4 * w + 3], corr, pj * v4.w);
+    }
+  }
+  float inv = 1.f / l;
+  bf16* orow = p.o + item * p.o_is + static_cast<int64_t>(qi) * p.o_rs + head * HD;
+#pragma unroll
+  for (int w = 0; w < HW; ++w)
+    reinterpret_cast<uint32_t*>(orow)[w] = gwd_pack_bf16x2(acc[2 * w] * inv, acc[2 * w + 1] * inv);
 }
 
-
-// -------------------------------------------------------------------------------------------------
-// window attention: one CTA per window, one warp per head.  The window's K and V rows ([N, C], all heads) are
-// staged in shared memory with coalesced 16-byte loads; K rows are padded per head to kill bank conflicts.
-// -------------------------------------------------------------------------------------------------
-struct WinAttnParams {
-  const bf16* q; const bf16* k; const bf16* v; bf16* o;
-  int windows, heads, N, hd;
-  int64_t q_rs, k_rs, v_rs, o_rs;      // row strides; window stride = N * row stride
-  const float* bias;                   // [heads, N, N]
-  const float* mask;                   // [nW, N, N] or null
-  int nW;
-};
-
-__global__ void gwd_window_attention_kernel(const WinAttnParams p) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  const int N = p.N, hd = p.hd, heads = p.heads, C = heads * hd;
-  const int kst = hd + 2;                                 // padded per-head K row (bf16 elements)
-  bf16* Ks = reinterpret_cast<bf16*>(smem);               // [heads][N][kst]
-  bf16* Vs = Ks + static_cast<size_t>(heads) * N * kst;   // [N][C]
-  float* Ps = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(Vs + static_cast<size_t>(N) * C) + 15) & ~uintptr_t(15));
-  float* Qs = Ps + static_cast<size_t>(heads) * 64;       // [heads][64] probabilities, then [heads][32] query
-  const int win = blockIdx.x;
-  const bf16* kb = p.k + static_cast<int64_t>(win) * N * p.k_rs;
-  const bf16* vb = p.v + static_cast<int64_t>(win) * N * p.v_rs;
-  const int cw = C >> 1;                                  // 32-bit words per row
-  for (int idx = threadIdx.x; idx < N * cw; idx += blockDim.x) {
-    int j = idx / cw, w = idx - j * cw;
-    uint32_t kk = reinterpret_cast<const uint32_t*>(kb + j * p.k_rs)[w];
-    uint32_t vv = reinterpret_cast<const uint32_t*>(vb + j * p.v_rs)[w];
-    int h = (2 * w) / hd, dd = 2 * w - h * hd;
-    *reinterpret_cast<uint32_t*>(Ks + (static_cast<size_t>(h) * N + j) * kst + dd) = kk;
-    reinterpret_cast<uint32_t*>(Vs + static_cast<size_t>(j) * C)[w] = vv;
-  }
-  __syncthreads();
-  const int h = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (h >= heads) return;
-  float* ps = Ps + h * 64;
-  float* qs = Qs + h * 32;
-  const bf16* Kh = Ks + static_cast<size_t>(h) * N * kst;
-  const int hw = hd >> 1;
-  const int G = 32 / hd, d = lane % hd, g = lane / hd;
-  const float* mbase = p.mask ? p.mask + static_cast<int64_t>(win % p.nW) * N * N : nullptr;
-  for (int qi = 0; qi < N; ++qi) {
-    const bf16* qrow = p.q + (static_cast<int64_t>(win) * N + qi) * p.q_rs + h * hd;
-    if (lane < hd) qs[lane] = __bfloat162float(qrow[lane]);
-    __syncwarp();
-    const float* brow = p.bias + (static_cast<int64_t>(h) * N + qi) * N;
-    float sc[2];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      int j = lane + 32 * r;
-      float s = -INFINITY;
-      if (j < N) {
-        const uint32_t* kr = reinterpret_cast<const uint32_t*>(Kh + static_cast<size_t>(j) * kst);
-        s = 0.f;
-        for (int w = 0; w < hw; ++w) {
-          float2 kk = gwd_unpack_bf16x2(kr[w]);
-          s = fmaf(qs[2 * w], kk.x, s);
-          s = fmaf(qs[2 * w + 1], kk.y, s);
-        }
-        s += brow[j];
-        if (mbase) s += mbase[qi * N + j];
-      }
-      sc[r] = s;
-      mx = fmaxf(mx, s);
+template <int HD>
+static int launch_attention_tq(const AttnParams& p, cudaStream_t stream) {
+  size_t smem = static_cast<size_t>(p.Lk) * HD * 2 * sizeof(float);
+  GWD_CHECK_ARG(smem <= 200 * 1024, "gwd_attention: Lk=%d does not fit shared memory", p.Lk);
+  if (smem > 48 * 1024) {
+    static bool configured = false;
+    if (!configured) {
+      GWD_CUDA(cudaFuncSetAttribute(gwd_attention_tq_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
     }
-    mx = gwd_warp_max(mx);
-    float sum = 0.f;
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      int j = lane + 32 * r;
-      float e = j < N ? __expf(sc[r] - mx) : 0.f;
-      ps[j] = e;
-      sum += e;
-    }
-    sum = gwd_warp_sum(sum);
-    __syncwarp();
-    float acc = 0.f;
-    for (int j = g; j < N; j += G) acc = fmaf(ps[j], __bfloat162float(Vs[static_cast<size_t>(j) * C + h * hd + d]), acc);
-    for (int o = hd; o < 32; o <<= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane < hd) p.o[(static_cast<int64_t>(win) * N + qi) * p.o_rs + h * hd + lane] = __float2bfloat16(acc / sum);
-    __syncwarp();
   }
+  int threads = p.Lq <= 64 ? 64 : 128;
+  dim3 grid(static_cast<unsigned>(gwd_ceil_div(p.Lq, threads)), p.heads, p.items);
+  gwd_attention_tq_kernel<HD><<<grid, threads, smem, stream>>>(p);
+  GWD_LAUNCHED();
+  return GWD_OK;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -306,18 +232,22 @@ __global__ void __launch_bounds__(128) gwd_ref_scores_kernel(const bf16* __restr
 
 // diffusion step, phase 1: raw = conv3x3_{heads->heads}(a) for a band of rows of one image, all output channels;
 // per-(image, channel) sum / sum of squares accumulated in fp64 for the whole-image LayerNorm of phase 2.
-// a: [B][heads][P][R] fp32.  grid (row bands, B), block 256.
+// a: [B][heads][P][R] fp32.  grid (row bands, B), block 128: warp w produces output channels 4w..4w+3 (register tile),
+// lanes stride over the band's pixels.  The 16x16x9 filter travels as a kernel parameter (constant bank operands).
 constexpr int kDiffBand = 21;
-__global__ void __launch_bounds__(256) gwd_ref_diffuse_conv_kernel(const float* __restrict__ a, float* __restrict__ raw,
-                                                                   const float* __restrict__ w, const float* __restrict__ bias,
-                                                                   double* __restrict__ stats, int heads, int P, int R) {
-  extern __shared__ float sm[];
-  float* tile = sm;                                       // [heads][band+2][R+2] zero padded
+constexpr int kDiffHeads = 16;
+struct DiffuseFilter {
+  float w[kDiffHeads * kDiffHeads * 9];
+  float b[kDiffHeads];
+};
+__global__ void __launch_bounds__(128) gwd_ref_diffuse_conv_kernel(const float* __restrict__ a, float* __restrict__ raw,
+                                                                   const __grid_constant__ DiffuseFilter flt,
+                                                                   double* __restrict__ stats, int P, int R) {
+  extern __shared__ float tile[];                         // [heads][band+2][R+2] zero padded
+  const int heads = kDiffHeads;
   const int y0 = blockIdx.x * kDiffBand, b = blockIdx.y;
   const int rows = min(kDiffBand, P - y0);
   const int TR = kDiffBand + 2, TC = R + 2;
-  float* wsm = tile + static_cast<size_t>(heads) * TR * TC;  // [heads*heads*9]
-  for (int i = threadIdx.x; i < heads * heads * 9; i += blockDim.x) wsm[i] = w[i];
   for (int i = threadIdx.x; i < heads * TR * TC; i += blockDim.x) {
     int ic = i / (TR * TC);
     int rem = i - ic * TR * TC;
@@ -329,33 +259,46 @@ __global__ void __launch_bounds__(256) gwd_ref_diffuse_conv_kernel(const float* 
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // each warp owns output channels oc = warp, warp + 8, ...; lanes stride over the band's pixels
-  for (int oc = warp; oc < heads; oc += 8) {
-    float s = 0.f, ss = 0.f;
-    for (int pix = lane; pix < rows * R; pix += 32) {
-      int ty = pix / R, tx = pix - ty * R;
-      float acc = bias[oc];
-      for (int ic = 0; ic < heads; ++ic) {
-        const float* t = tile + (static_cast<size_t>(ic) * TR + ty) * TC + tx;
-        const float* wk = wsm + (oc * heads + ic) * 9;
+  const int oc0 = warp * 4;
+  float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  for (int pix = lane; pix < rows * R; pix += 32) {
+    int ty = pix / R, tx = pix - ty * R;
+    float acc[4];
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
+    for (int o = 0; o < 4; ++o) acc[o] = flt.b[oc0 + o];
+#pragma unroll 4
+    for (int ic = 0; ic < kDiffHeads; ++ic) {
+      const float* t = tile + (static_cast<size_t>(ic) * TR + ty) * TC + tx;
+      float in[9];
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) acc = fmaf(wk[dy * 3 + dx], t[dy * TC + dx], acc);
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) in[dy * 3 + dx] = t[dy * TC + dx];
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        const float* wk = flt.w + ((oc0 + o) * kDiffHeads + ic) * 9;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) acc[o] = fmaf(wk[k], in[k], acc[o]);
       }
-      raw[((static_cast<int64_t>(b) * heads + oc) * P + y0 + ty) * R + tx] = acc;
-      s += acc;
-      ss += acc * acc;
     }
-    double ds = s, dss = ss;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      ds += __shfl_xor_sync(0xffffffffu, ds, o);
-      dss += __shfl_xor_sync(0xffffffffu, dss, o);
+    for (int o = 0; o < 4; ++o) {
+      raw[((static_cast<int64_t>(b) * heads + oc0 + o) * P + y0 + ty) * R + tx] = acc[o];
+      s[o] += acc[o];
+      ss[o] += acc[o] * acc[o];
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    double ds = s[o], dss = ss[o];
+#pragma unroll
+    for (int sh = 16; sh > 0; sh >>= 1) {
+      ds += __shfl_xor_sync(0xffffffffu, ds, sh);
+      dss += __shfl_xor_sync(0xffffffffu, dss, sh);
     }
     if (lane == 0) {
-      atomicAdd(&stats[(static_cast<int64_t>(b) * heads + oc) * 2], ds);
-      atomicAdd(&stats[(static_cast<int64_t>(b) * heads + oc) * 2 + 1], dss);
+      atomicAdd(&stats[(static_cast<int64_t>(b) * heads + oc0 + o) * 2], ds);
+      atomicAdd(&stats[(static_cast<int64_t>(b) * heads + oc0 + o) * 2 + 1], dss);
     }
   }
 }
@@ -423,29 +366,6 @@ extern "C" int gwd_attention(const gwd_attn_desc* d, void* stream_) {
   GWD_CHECK_ARG(d->k_row_stride % 2 == 0 && d->v_row_stride % 2 == 0 && d->k_item_stride % 2 == 0 && d->v_item_stride % 2 == 0 &&
                     (reinterpret_cast<uintptr_t>(d->k) & 3) == 0 && (reinterpret_cast<uintptr_t>(d->v) & 3) == 0,
                 "gwd_attention: K/V must be 4-byte aligned with even strides");
-  if (d->Lq == d->Lk && d->Lk <= 64 && d->bias != nullptr && d->key_padding == nullptr && d->scale == 1.0f &&
-      d->heads <= 32 && d->q_item_stride == d->Lq * d->q_row_stride && d->k_item_stride == d->Lk * d->k_row_stride &&
-      d->v_item_stride == d->Lk * d->v_row_stride && d->o_item_stride == d->Lq * d->o_row_stride) {
-    WinAttnParams w;
-    w.q = static_cast<const bf16*>(d->q); w.k = static_cast<const bf16*>(d->k); w.v = static_cast<const bf16*>(d->v);
-    w.o = static_cast<bf16*>(d->o);
-    w.windows = d->items; w.heads = d->heads; w.N = d->Lq; w.hd = d->hd;
-    w.q_rs = d->q_row_stride; w.k_rs = d->k_row_stride; w.v_rs = d->v_row_stride; w.o_rs = d->o_row_stride;
-    w.bias = d->bias; w.mask = d->mask; w.nW = d->mask_windows > 0 ? d->mask_windows : 1;
-    const int C = d->heads * d->hd;
-    size_t smem = static_cast<size_t>(d->heads) * d->Lk * (d->hd + 2) * 2 + static_cast<size_t>(d->Lk) * C * 2 + 16 +
-                  static_cast<size_t>(d->heads) * (64 + 32) * 4;
-    if (smem > 48 * 1024) {
-      static bool configured = false;
-      if (!configured) {
-        GWD_CUDA(cudaFuncSetAttribute(gwd_window_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-        configured = true;
-      }
-    }
-    gwd_window_attention_kernel<<<d->items, d->heads * 32, smem, stream>>>(w);
-    GWD_LAUNCHED();
-    return GWD_OK;
-  }
   AttnParams p;
   p.q = static_cast<const bf16*>(d->q); p.k = static_cast<const bf16*>(d->k); p.v = static_cast<const bf16*>(d->v);
   p.o = static_cast<bf16*>(d->o);
@@ -454,21 +374,17 @@ extern "C" int gwd_attention(const gwd_attn_desc* d, void* stream_) {
   p.v_is = d->v_item_stride; p.v_rs = d->v_row_stride; p.o_is = d->o_item_stride; p.o_rs = d->o_row_stride;
   p.bias = d->bias; p.mask = d->mask; p.nW = d->mask_windows > 0 ? d->mask_windows : 1;
   p.kpm = d->key_padding; p.scale = d->scale;
-  p.q_tile = d->Lq <= 64 ? d->Lq : 32;
-  size_t smem = static_cast<size_t>(d->Lk) * (d->hd + 2) * 2 + static_cast<size_t>(d->Lk) * d->hd * 2 + 16 + 16 +
-                static_cast<size_t>(kAttnWarps) * d->Lk * 4 + kAttnWarps * 32 * 4;
-  GWD_CHECK_ARG(smem <= 220 * 1024, "gwd_attention: Lk=%d does not fit shared memory", d->Lk);
-  if (smem > 48 * 1024) {
-    static size_t configured = 0;
-    if (smem > configured) {
-      GWD_CUDA(cudaFuncSetAttribute(gwd_attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      configured = 227 * 1024;
-    }
+  p.q_tile = 0;
+  GWD_CHECK_ARG(d->q_row_stride % 2 == 0 && d->q_item_stride % 2 == 0 && d->o_row_stride % 2 == 0 &&
+                    d->o_item_stride % 2 == 0 && (reinterpret_cast<uintptr_t>(d->q) & 3) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d->o) & 3) == 0,
+                "gwd_attention: Q/O must be 4-byte aligned with even strides");
+  switch (d->hd) {
+    case 4: return launch_attention_tq<4>(p, stream);
+    case 8: return launch_attention_tq<8>(p, stream);
+    case 16: return launch_attention_tq<16>(p, stream);
+    default: return launch_attention_tq<32>(p, stream);
   }
-  dim3 grid(static_cast<unsigned>(gwd_ceil_div(d->Lq, p.q_tile)), d->heads, d->items);
-  gwd_attention_kernel<<<grid, kAttnWarps * 32, smem, stream>>>(p);
-  GWD_LAUNCHED();
-  return GWD_OK;
 }
 
 extern "C" int gwd_token_attention(const void* dq, const void* sq, const void* tk, const void* tv, void* dout, void* sout,
@@ -512,13 +428,17 @@ extern "C" int gwd_ref_scores(const void* q, int64_t q_rs, const float* refk, in
   return GWD_OK;
 }
 
-extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w, const float* bias, float* raw_ws,
+extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w_host, const float* bias_host, float* raw_ws,
                                double* stats_ws, int32_t B, int32_t heads, int32_t P, int32_t R, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  GWD_CHECK_ARG(a_in && a_out && w && bias && raw_ws && stats_ws && a_in != a_out, "gwd_ref_diffuse: null / aliased pointer");
-  GWD_CHECK_ARG(heads <= 16, "gwd_ref_diffuse: at most 16 heads");
+  GWD_CHECK_ARG(a_in && a_out && w_host && bias_host && raw_ws && stats_ws && a_in != a_out,
+                "gwd_ref_diffuse: null / aliased pointer");
+  GWD_CHECK_ARG(heads == kDiffHeads, "gwd_ref_diffuse: built for %d heads (got %d)", kDiffHeads, heads);
+  DiffuseFilter flt;
+  memcpy(flt.w, w_host, sizeof(flt.w));
+  memcpy(flt.b, bias_host, sizeof(flt.b));
   GWD_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * B * heads, stream));
-  size_t smem = (static_cast<size_t>(heads) * (kDiffBand + 2) * (R + 2) + static_cast<size_t>(heads) * heads * 9) * sizeof(float);
+  size_t smem = static_cast<size_t>(heads) * (kDiffBand + 2) * (R + 2) * sizeof(float);
   GWD_CHECK_ARG(smem <= 200 * 1024, "gwd_ref_diffuse: %d reference points do not fit shared memory", R);
   if (smem > 48 * 1024) {
     static bool configured = false;
@@ -528,7 +448,7 @@ extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w, 
     }
   }
   dim3 grid(static_cast<unsigned>(gwd_ceil_div(P, kDiffBand)), B);
-  gwd_ref_diffuse_conv_kernel<<<grid, 256, smem, stream>>>(a_in, raw_ws, w, bias, stats_ws, heads, P, R);
+  gwd_ref_diffuse_conv_kernel<<<grid, 128, smem, stream>>>(a_in, raw_ws, flt, stats_ws, P, R);
   GWD_LAUNCHED();
   int64_t per_img = static_cast<int64_t>(P) * R, total = per_img * B * heads;
   int blocks = static_cast<int>(std::min<int64_t>(gwd_ceil_div(total, 256), gwd_num_sms() * 8));

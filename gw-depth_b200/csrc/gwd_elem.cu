@@ -114,12 +114,15 @@ __device__ __forceinline__ void row_layernorm(WarpRow& r, int C, int n, const Ro
     }
   }
 }
-__device__ __forceinline__ void row_act(WarpRow& r, int act) {
+__device__ __forceinline__ void row_act(WarpRow& r, int act, int C, const RowGroup& g) {
   if (act == GWD_ACT_NONE) return;
 #pragma unroll
-  for (int v = 0; v < kMaxVec; ++v)
+  for (int v = 0; v < kMaxVec; ++v) {
+    if ((v * g.G + g.sub) * 8 < C) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) r.f[v][i] = gwd_apply_act(r.f[v][i], act);
+      for (int i = 0; i < 8; ++i) r.f[v][i] = gwd_apply_act(r.f[v][i], act);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -135,7 +138,7 @@ __global__ void gwd_layernorm_kernel(const bf16* x, int64_t x_rs, const bf16* re
   row_load(r, x + row * x_rs, C, rg, live);
   if (res && live) row_add(r, res + row * res_rs, C, rg);
   if (g) row_layernorm(r, C, n, rg, g, b, eps);
-  row_act(r, act);
+  row_act(r, act, C, rg);
   if (live) row_store(r, out + row * out_rs, C, rg);
 }
 

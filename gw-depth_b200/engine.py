@@ -229,8 +229,9 @@ class Engine:
             self.line_blocks.append({
                 "n1": _LN(sd, q + "norm1"), "n2": _LN(sd, q + "norm2"), "qkv": pack_linear(wqkv, bqkv),
                 "ref": pack_linear(wr, br), "proj": pack_linear(sd[q + "attn.proj.weight"], sd[q + "attn.proj.bias"]),
-                "diff_w": sd[q + "attn.ref_attn_diffusion.weight"].contiguous(),
-                "diff_b": sd[q + "attn.ref_attn_diffusion.bias"].contiguous(),
+                # the 16x16x3x3 diffusion filter travels as a kernel parameter: keep it on the host
+                "diff_w": sd[q + "attn.ref_attn_diffusion.weight"].float().cpu().contiguous(),
+                "diff_b": sd[q + "attn.ref_attn_diffusion.bias"].float().cpu().contiguous(),
                 "bias": rel_pos_bias(sd[q + "attn.relative_position_bias_table"], ws, nh), "mlp": self._pack_mlp(q + "mlp.")})
         self.depth32 = self._pack_composed(p + "depth_pred32.0", p + "depth_pred32.1")
         self.class_stages = []

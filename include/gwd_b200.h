@@ -128,9 +128,10 @@ int gwd_token_attention(const void* depth_q, const void* seg_q, const void* tk, 
  *   gwd_ref_requery: q_new = scale * softmax_r(a) ref_v                          (:307-310), bf16 window layout */
 int gwd_ref_scores(const void* q, int64_t q_rs, const float* ref_k, int64_t ref_rs, float* a, int32_t B, int32_t nW,
                    int32_t N, int32_t heads, int32_t hd, int32_t R, float scale, void* stream);
-int gwd_ref_diffuse(const float* a_in, float* a_out, const float* conv_w, const float* conv_b, float* raw_workspace,
+int gwd_ref_diffuse(const float* a_in, float* a_out, const float* conv_w_host, const float* conv_b_host, float* raw_workspace,
                     double* stats_workspace, int32_t B, int32_t heads, int32_t P, int32_t R, void* stream);
-/* raw_workspace: fp32 [B*heads*P*R]; stats_workspace: fp64 [B*heads*2] */
+/* conv_w_host / conv_b_host: HOST arrays [16*16*9] / [16] (they travel as kernel parameters);
+ * raw_workspace: device fp32 [B*heads*P*R]; stats_workspace: device fp64 [B*heads*2] */
 int gwd_ref_requery(const float* a, const float* ref_v, int64_t ref_rs, void* q_new, int64_t o_rs, int32_t B, int32_t nW,
                     int32_t N, int32_t heads, int32_t hd, int32_t R, float scale, void* stream);
 

@@ -74,11 +74,12 @@ def test_linear(M, K, N, pre, post, res_mode, use_ln):
 
 CONV_CASES = [
     # B, H, W, C, N, pre, post, res_mode, ln
-    (2, 30, 40, 64, 64, 3, 0, 0, False),
+    (2, 30, 40, 64, 64, 0, 3, 0, False),
+    (2, 18, 22, 64, 64, 3, 0, 0, True),
     (1, 24, 32, 160, 160, 0, 2, 0, True),
     (2, 17, 23, 80, 80, 0, 2, 0, True),
     (1, 16, 24, 160, 160, 0, 0, 2, True),
-    (1, 20, 28, 32, 32, 3, 0, 0, False),
+    (1, 20, 28, 32, 32, 0, 3, 0, False),
     (1, 12, 16, 320, 320, 0, 0, 0, False),
     (1, 9, 13, 1024, 256, 0, 2, 0, False),
     (3, 7, 10, 160, 160, 0, 2, 0, True),

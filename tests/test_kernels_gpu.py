@@ -1,0 +1,299 @@
+"""GPU parity of every non-GEMM C-ABI kernel against the CPU oracle / plain torch fp32 on the same seeded inputs.
+Index and selection kernels must be bit-exact; floating-point kernels carry their tolerance next to the assert."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import golden, oracle
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import ops
+    return ops
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def _bf(t):
+    return t.bfloat16()
+
+
+def close(got, ref, tol, what=""):
+    got, ref = got.float().cpu(), ref.float().cpu()
+    err = (got - ref).abs().max().item()
+    scale = max(1.0, ref.abs().max().item())
+    assert err <= tol * scale, "%s: max err %.4g > %.4g" % (what, err, tol * scale)
+
+
+# ------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,Lq,Lk,heads,hd,pad", [(2, 300, 300, 8, 32, False), (3, 100, 300, 8, 32, True), (2, 100, 100, 8, 32, False),
+                                                 (1, 37, 53, 4, 16, True)])
+def test_attention_detr(B, Lq, Lk, heads, hd, pad):
+    ops = _ops()
+    g = _g(Lq + Lk + hd)
+    E = heads * hd
+    q, k, v = (_bf(torch.randn(B, L, E, generator=g)) for L in (Lq, Lk, Lk))
+    kpm = None
+    if pad:
+        kpm = torch.zeros(B, Lk, dtype=torch.bool)
+        kpm[:, Lk - 7:] = True
+        kpm[0, 3] = True
+    qh = q.float().view(B, Lq, heads, hd).permute(0, 2, 1, 3)
+    kh = k.float().view(B, Lk, heads, hd).permute(0, 2, 1, 3)
+    vh = v.float().view(B, Lk, heads, hd).permute(0, 2, 1, 3)
+    s = qh @ kh.transpose(-1, -2)
+    if pad:
+        s = s.masked_fill(kpm[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ vh).permute(0, 2, 1, 3).reshape(B, Lq, E)
+    o = torch.empty(B * Lq, E, dtype=torch.bfloat16, device="cuda")
+    ops.attention(q.cuda().view(-1, E), k.cuda().view(-1, E), v.cuda().view(-1, E), o, items=B, heads=heads, Lq=Lq, Lk=Lk,
+                  hd=hd, q_strides=(Lq * E, E), k_strides=(Lk * E, E), v_strides=(Lk * E, E), o_strides=(Lq * E, E),
+                  key_padding=kpm.to(torch.uint8).cuda() if pad else None)
+    close(o.view(B, Lq, E), ref, 1e-2, "attention")     # bf16 output rounding
+
+
+@pytest.mark.parametrize("hd,heads,shifted", [(32, 16, True), (16, 16, False), (8, 16, True), (4, 16, True)])
+def test_attention_window(hd, heads, shifted):
+    ops = _ops()
+    g = _g(hd)
+    N, nW, B = 49, 6, 2
+    C = heads * hd
+    qkv = _bf(torch.randn(B * nW * N, 3 * C, generator=g))
+    bias = torch.randn(heads, N, N, generator=g)
+    mask = torch.where(torch.rand(nW, N, N, generator=g) > 0.7, torch.tensor(-100.0), torch.tensor(0.0)) if shifted else None
+    x = qkv.float().view(B * nW, N, 3, heads, hd).permute(2, 0, 3, 1, 4)
+    ref = oracle.softmax_attention(x[0], x[1], x[2], bias, mask, nW).transpose(1, 2).reshape(B * nW * N, C)
+    d = qkv.cuda()
+    o = torch.empty(B * nW * N, C, dtype=torch.bfloat16, device="cuda")
+    ops.attention(d, d[:, C:], d[:, 2 * C:], o, items=B * nW, heads=heads, Lq=N, Lk=N, hd=hd, q_strides=(N * 3 * C, 3 * C),
+                  k_strides=(N * 3 * C, 3 * C), v_strides=(N * 3 * C, 3 * C), o_strides=(N * C, C), bias=bias.cuda(),
+                  mask=mask.cuda() if shifted else None)
+    close(o, ref, 1e-2, "window attention")
+
+
+def test_token_attention():
+    """class-token channel attention vs the oracle's formulation (multiscale_transformerr.py:561-578)"""
+    ops = _ops()
+    g = _g(11)
+    items, N, heads, td_all, C = 5, 49, 16, 64, 128
+    tC = C + 2 * td_all
+    dq, sq = _bf(torch.randn(items * N, td_all, generator=g)), _bf(torch.randn(items * N, td_all, generator=g))
+    kv = _bf(torch.randn(items * N, 2 * tC, generator=g))
+    scale = (C // heads) ** -0.5
+
+    def ref_one(tq):
+        q = tq.float().view(items, N, heads, td_all // heads).permute(0, 2, 1, 3) * scale
+        tk = kv.float()[:, :tC].reshape(items, N, heads, tC // heads).permute(0, 2, 1, 3)
+        tv = kv.float()[:, tC:].reshape(items, N, heads, tC // heads).permute(0, 2, 1, 3)
+        a = torch.softmax(q.transpose(-2, -1) @ tk, dim=-1)
+        return (a @ tv.transpose(-2, -1)).reshape(items, -1, N).permute(0, 2, 1).reshape(items * N, td_all)
+
+    dout = torch.empty(items * N, td_all, dtype=torch.bfloat16, device="cuda")
+    sout = torch.empty_like(dout)
+    kvd = kv.cuda()
+    ops.token_attention(dq.cuda(), sq.cuda(), kvd, kvd[:, tC:], dout, sout, items=items, N=N, heads=heads, td=td_all // heads,
+                        tc=tC // heads, q_rs=td_all, k_rs=2 * tC, v_rs=2 * tC, o_rs=td_all, scale=scale)
+    close(dout, ref_one(dq), 1e-2, "depth token")
+    close(sout, ref_one(sq), 1e-2, "seg token")
+
+
+def test_line_requery_chain():
+    """ref_scores -> 3 x ref_diffuse -> ref_requery vs the oracle's WindowAttention re-query (mst.py:295-310)"""
+    ops = _ops()
+    g = _g(5)
+    B, nW, N, heads, hd, R = 2, 9, 49, 16, 32, 40
+    C = heads * hd
+    P = nW * N
+    q = _bf(torch.randn(B * P, C, generator=g) * 0.3)
+    refkv = torch.randn(B * R, 2 * C, generator=g) * 0.5
+    w = torch.randn(heads, heads, 3, 3, generator=g) * 0.1
+    b = torch.randn(heads, generator=g) * 0.1
+    scale = hd ** -0.5
+    qh = q.float().view(B, nW, N, heads, hd).permute(0, 3, 1, 2, 4).reshape(B, heads, P, hd)
+    rk = refkv[:, :C].reshape(B, R, heads, hd).permute(0, 2, 1, 3)
+    rv = refkv[:, C:].reshape(B, R, heads, hd).permute(0, 2, 1, 3)
+    a = qh @ rk.transpose(-1, -2)
+    for _ in range(3):
+        a = a + F.gelu(F.layer_norm(F.conv2d(a, w, b, padding=1), [P, R]))
+    ref = ((torch.softmax(a, -1) @ rv) * scale).permute(0, 2, 1, 3).reshape(B * P, C)
+
+    a0 = torch.empty(B, heads, P, R, device="cuda")
+    a1, raw = torch.empty_like(a0), torch.empty_like(a0)
+    st = torch.empty(B * heads * 2, dtype=torch.float64, device="cuda")
+    rd = refkv.cuda()
+    ops.ref_scores(q.cuda(), C, rd, 2 * C, a0, B, nW, N, heads, hd, R)
+    ops.ref_diffuse(a0, a1, w.contiguous(), b.contiguous(), raw, st, B, heads, P, R)
+    ops.ref_diffuse(a1, a0, w.contiguous(), b.contiguous(), raw, st, B, heads, P, R)
+    ops.ref_diffuse(a0, a1, w.contiguous(), b.contiguous(), raw, st, B, heads, P, R)
+    close(a1, a, 2e-4, "diffused reference scores")      # fp32 path
+    out = torch.empty(B * P, C, dtype=torch.bfloat16, device="cuda")
+    ops.ref_requery(a1, rd[:, C:], 2 * C, out, C, B, nW, N, heads, hd, R, scale)
+    close(out, ref, 1e-2, "re-queried q")
+
+
+# ------------------------------------------------------------------------------------------ bandwidth kernels
+@pytest.mark.parametrize("rows,C,n", [(1000, 256, 256), (777, 64, 64), (513, 320, 320), (300, 128, 120), (64, 512, 512), (99, 80, 80)])
+def test_layernorm_and_add(rows, C, n):
+    ops = _ops()
+    g = _g(rows + C)
+    x, r = _bf(torch.randn(rows, C, generator=g)), _bf(torch.randn(rows, C, generator=g))
+    gam, bet = 1 + 0.1 * torch.randn(n, generator=g), 0.1 * torch.randn(n, generator=g)
+    ref = F.gelu(F.layer_norm((x.float() + r.float())[:, :n], (n,), gam, bet, 1e-5))
+    out = ops.layernorm(x.cuda(), ops.pad_vec(gam.cuda(), C), ops.pad_vec(bet.cuda(), C), res=r.cuda(), act=ops.ACT_GELU, n=n)
+    close(out[:, :n], ref, 1e-2, "layernorm")
+    assert (out[:, n:] == 0).all()
+    period = 50
+    add = _bf(torch.randn(period, C, generator=g))
+    out2 = ops.add_rows(x.cuda(), add.cuda(), period)
+    idx = torch.arange(rows) % period
+    close(out2, x.float() + add.float()[idx], 1e-2, "add_rows")
+
+
+@pytest.mark.parametrize("H,W,C,shift", [(15, 20, 512, 0), (15, 20, 512, 3), (30, 40, 256, 3), (17, 23, 64, 3), (14, 21, 128, 0)])
+def test_window_gather_merge(H, W, C, shift):
+    ops = _ops()
+    g = _g(H * W + C + shift)
+    B, ws = 2, 7
+    x = _bf(torch.randn(B, H * W, C, generator=g))
+    gam, bet = 1 + 0.1 * torch.randn(C, generator=g), 0.1 * torch.randn(C, generator=g)
+    ln = F.layer_norm(x.float(), (C,), gam, bet, 1e-5)
+    ref_w = oracle.to_windows(oracle.pad_and_shift(ln, H, W, ws, shift), ws).reshape(-1, C)
+    got_w = ops.window_gather(x.cuda().view(B, H, W, C), B, H, W, ws, shift, gam.cuda(), bet.cuda())
+    close(got_w, ref_w, 1e-2, "window gather")
+    Hp, Wp = math.ceil(H / ws) * ws, math.ceil(W / ws) * ws
+    win = _bf(torch.randn(B * Hp * Wp, C, generator=g))
+    merged = x.float() + oracle.unshift_and_crop(oracle.from_windows(win.float().view(-1, ws * ws, C), ws, B, Hp, Wp), H, W, shift).reshape(B, H * W, C)
+    out, out_ln = ops.window_merge(win.cuda(), x.cuda().view(B * H * W, C), B, H, W, ws, shift, gam.cuda(), bet.cuda(), want_ln=True)
+    close(out, merged.view(-1, C), 1e-2, "window merge")
+    close(out_ln, F.layer_norm(merged, (C,), gam, bet, 1e-5).view(-1, C), 2e-2, "window merge LN")
+
+
+def test_resampling():
+    ops = _ops()
+    g = _g(3)
+    B, h, w, C = 2, 15, 20, 64
+    x = _bf(torch.randn(B, h, w, C, generator=g))
+    nchw = x.float().permute(0, 3, 1, 2)
+    add = _bf(torch.randn(B, 30, 40, C, generator=g))
+    up = ops.upsample_nearest(x.cuda(), 30, 40, add=add.cuda())
+    close(up, F.interpolate(nchw, size=(30, 40), mode="nearest").permute(0, 2, 3, 1) + add.float(), 1e-2, "nearest")
+    up2 = ops.upsample_nearest(x.cuda(), 37, 41)    # non-integer ratio: legacy floor(dst*in/out) rule
+    close(up2, F.interpolate(nchw, size=(37, 41), mode="nearest").permute(0, 2, 3, 1), 1e-2, "nearest ragged")
+    big = _bf(torch.randn(B, 33, 47, C, generator=g))
+    for k in (16, 8, 4, 2):
+        close(ops.avgpool(big.cuda(), k), F.avg_pool2d(big.float().permute(0, 3, 1, 2), k, k).permute(0, 2, 3, 1), 1e-2, "avgpool")
+    out = torch.zeros(B, 33, 47, 3 * C, dtype=torch.bfloat16, device="cuda")
+    ops.bilinear_up_into(x.cuda(), out, C, 33, 47)
+    ref = F.interpolate(nchw, size=(33, 47), mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    close(out[..., C:2 * C], ref, 1e-2, "bilinear")
+    assert (out[..., :C] == 0).all() and (out[..., 2 * C:] == 0).all()
+
+
+def test_point_sampling_and_mixture():
+    ops = _ops()
+    g = _g(4)
+    B, H, W, C, K = 2, 12, 17, 48, 30
+    feat = _bf(torch.randn(B, H, W, 2 * C, generator=g))
+    table = torch.randn(H * W, C, generator=g)
+    coords = torch.rand(B, K, 1, 2, generator=g) * 2.2 - 1.1          # some points fall outside
+    f = feat.float()[..., C:].permute(0, 3, 1, 2)
+    t = table.view(1, H, W, C).permute(0, 3, 1, 2).expand(B, -1, -1, -1)
+    ref = (F.grid_sample(f, coords, align_corners=False) + F.grid_sample(t, coords, align_corners=False)).flatten(2).permute(0, 2, 1)
+    got = ops.sample_bilinear(feat.cuda(), C, table.cuda(), B, H, W, C, coords.cuda().contiguous(), K)
+    close(got, ref, 1e-5, "bilinear point sample")
+    depth = torch.rand(B, 9, 11, generator=g)
+    ref_a = F.grid_sample(depth[:, None], coords, align_corners=False).flatten(1)
+    close(ops.sample_scalar(depth.cuda(), coords.cuda().contiguous(), K), ref_a, 1e-6, "anchor depth")
+    logits = _bf(torch.randn(B, H * W, 32, generator=g))
+    ref_m = (torch.softmax(logits.float()[..., :K], -1) * ref_a[:, None, :]).sum(-1)
+    close(ops.anchor_mix(logits.cuda(), ref_a.cuda().contiguous(), B, H * W, K), ref_m, 1e-5, "anchor mixture")
+
+
+@pytest.mark.parametrize("shift", [0, 3])
+def test_line_reference_gather(shift):
+    """nearest sampling of the shifted, padded, normalised map + shifted position table (mst.py:676-701)"""
+    ops = _ops()
+    g = _g(6 + shift)
+    B, H, W, C, ws, R = 2, 15, 20, 64, 7, 40
+    x = _bf(torch.randn(B, H * W, C, generator=g))
+    pos = torch.randn(H * W, C, generator=g)
+    ref_pts = torch.rand(B, R // 2, 2, 2, generator=g) * 2 - 1
+    xs = oracle.pad_and_shift(x.float(), H, W, ws, shift)
+    Hp, Wp = xs.shape[1:3]
+    pos_nchw = pos.view(1, H, W, C).permute(0, 3, 1, 2).expand(B, -1, -1, -1)
+    if shift:
+        rr = torch.zeros_like(ref_pts)
+        rr[..., 0] = ref_pts[..., 0] - (shift / (Wp - 1)) * 2
+        rr[..., 1] = ref_pts[..., 1] - (shift / (Hp - 1)) * 2
+        rr = torch.where(rr < -1, -1 - (1 + rr), rr)
+        rpos = torch.roll(pos_nchw, shifts=(-shift, -shift), dims=(2, 3))
+    else:
+        rr, rpos = ref_pts, pos_nchw
+    ref = (oracle.nearest_points(xs.permute(0, 3, 1, 2), rr) + oracle.nearest_points(rpos, rr)).reshape(B, C, -1).permute(0, 2, 1)
+    xw = ops.window_gather(x.cuda().view(B, H, W, C), B, H, W, ws, shift)
+    got = ops.line_ref_gather(xw, pos.cuda(), ref_pts.reshape(B, R, 2).cuda().contiguous(), R, B, H, W, ws, shift, C)
+    close(got, ref, 1e-2, "line reference tokens")
+
+
+# ------------------------------------------------------------------------------------------ selection / reduction kernels
+@pytest.mark.parametrize("h,w,K,seed", [(15, 20, 30, 0), (30, 40, 80, 1), (7, 10, 30, 2), (14, 20, 30, 3)])
+def test_certain_sample_bit_exact(h, w, K, seed):
+    ops = _ops()
+    g = _g(100 + seed)
+    B = 3
+    small = torch.rand(B, 1, h, w, generator=g)
+    large = torch.rand(B, 1, 2 * h, 2 * w, generator=g)
+    if seed == 2:
+        large = large * 0.08            # almost everything in the first bin: exercises the repeat / complement rules
+    if seed == 3:
+        large[1] = 2.0                  # no pixel in any bin for image 1: global top-K fallback
+    interval = [0.1, 0.3, 0.5, 0.7, 0.9]
+    ref_xy, ref_idx = oracle.certain_sample(small, large, K, interval, 1e-4)
+    xy, idx = ops.certain_sample(small[:, 0].cuda().contiguous(), large[:, 0].cuda().contiguous(), K, [1e-4] + interval + [1.0])
+    assert torch.equal(idx.cpu().long(), ref_idx), "sample indices differ"
+    assert torch.equal(xy.cpu(), ref_xy), "sample coordinates differ"
+
+
+def test_match_cost_and_assignment():
+    ops = _ops()
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import model as M
+    g = _g(9)
+    B, Q = 4, 100
+    logits = torch.randn(B, Q, 2, generator=g) * 2
+    lines = torch.rand(B, Q, 6, generator=g)
+    targets = [{"lines": torch.rand(12 + 5 * b, 6, generator=g), "labels": torch.zeros(12 + 5 * b, dtype=torch.int64)} for b in range(B)]
+    ref = oracle.matcher_cost(logits, lines, [t["lines"] for t in targets], 1.0, 5.0)
+    matcher = M.HungarianMatcher_Line(cost_class=1.0, cost_line=5.0)
+    out = {"pred_logits": logits.cuda(), "pred_lines": lines.cuda()}
+    tg = [{k: v.cuda() for k, v in t.items()} for t in targets]
+    got = matcher.cost_matrices(out, tg)
+    for a, b_ in zip(got, ref):
+        assert (a - b_).abs().max().item() <= 2e-6          # fp32, same operation order up to exp rounding
+    mine = matcher(out, tg)
+    theirs = oracle.hungarian(ref)
+    for (i, j), (ri, rj), c in zip(mine, theirs, ref):
+        assert torch.equal(i, ri) and torch.equal(j, rj), "assignment differs"        # random uniform lines: no exact L1 ties
+
+
+def test_depth_metrics_and_silog():
+    ops = _ops()
+    gld = golden("depth_metrics.npz")
+    pred, gt = torch.from_numpy(gld["pred"]), torch.from_numpy(gld["gt"])
+    got = ops.depth_metrics(pred.cuda(), gt.cuda()).cpu().numpy()
+    assert np.allclose(got, gld["metrics"], rtol=2e-5, atol=1e-7), (got, gld["metrics"])   # reference sums in fp32 (numpy)
+    g = _g(12)
+    p = torch.rand(2, 1, 30, 40, generator=g) * 0.9 + 0.05
+    d = torch.rand(2, 1, 120, 160, generator=g) * 11.0
+    s = ops.silog_sums(p.cuda(), d.cuda(), 0.2, 10.0, False).cpu()
+    loss = math.sqrt(s[2] / s[0] - 0.85 * (s[1] / s[0]) ** 2) * 10.0
+    ref = float(oracle.depth_losses([p], d, weights=(1.0,))[0])
+    assert abs(loss - ref) <= 1e-4 * abs(ref), (loss, ref)
