@@ -1,0 +1,173 @@
+"""GPU parity of the whole forward through the public API (build_model / model(samples)) against the CPU oracle and the
+fixtures the reference produced, plus size-independent properties at the benchmark size.
+
+Tolerances: activations are bf16 (8-bit mantissa) through ~150 layers, so the comparison against the fp32 oracle is
+bounded by bf16 round-off, not by kernel bugs; `test_error_is_bf16_roundoff` shows the same error level when the ORACLE
+itself is run with bf16-rounded weights/activations.  Discrete selections (top-20 lines, uncertainty samples) are
+pinned to the oracle's for the tight comparison and reported un-pinned separately."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import golden, oracle, synth, synth_weights
+
+pytestmark = pytest.mark.gpu
+
+# mean / max relative error bounds vs the fp32 oracle (bf16 path, selections pinned)
+TOL = {"depth_mean": 3e-2, "depth_max": 0.2, "logits_max": 8e-2, "lines_max": 0.15, "seg_mean": 0.2}
+
+
+def _model():
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import model as M
+    net, criterions, post = M.build_model(M.default_args(device="cuda"))
+    net.load_state_dict(synth_weights())
+    return net.cuda().eval(), criterions, M
+
+
+_cache = {}
+
+
+def model():
+    if "m" not in _cache:
+        _cache["m"] = _model()
+    return _cache["m"]
+
+
+def rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    d = (a - b).abs()
+    return float(d.mean() / b.abs().mean().clamp_min(1e-9)), float(d.max() / b.abs().max().clamp_min(1e-9))
+
+
+def pinned_from(trace):
+    return {"line_ids": trace["line_ids"].cuda(), "sample1": trace["sample1"].cuda(), "sample2": trace["sample2"].cuda()}
+
+
+@pytest.mark.parametrize("B,H,W,fixture", [(2, 224, 320, "fwd_224x320_b2.npz"), (1, 480, 640, "fwd_480x640_b1.npz")])
+def test_forward_matches_oracle_and_reference_fixture(B, H, W, fixture):
+    net, _, _ = model()
+    images, _, _, _ = synth.synth_batch(B, H, W, seed=0)
+    trace = {}
+    ref = oracle.forward(synth_weights(), images, trace=trace)
+    with torch.no_grad():
+        out = net(images.cuda(), _pinned=pinned_from(trace))
+    assert set(out) == {"pred_logits", "pred_lines", "aux_outputs", "pred_depth", "pred_seg"}
+    assert len(out["aux_outputs"]) == 5 and len(out["pred_depth"]) == 4
+    for a, b in zip(out["pred_depth"], ref["pred_depth"]):
+        assert a.shape == b.shape
+    assert out["pred_seg"].shape == ref["pred_seg"].shape
+    assert rel(out["pred_logits"], ref["pred_logits"])[1] < TOL["logits_max"]
+    assert rel(out["pred_lines"], ref["pred_lines"])[1] < TOL["lines_max"]
+    for i in range(4):
+        m, x = rel(out["pred_depth"][i], ref["pred_depth"][i])
+        assert m < (TOL["depth_mean"] if i == 3 else 6e-2) and x < 0.3, (i, m, x)
+    m, x = rel(out["pred_depth"][3], ref["pred_depth"][3])
+    assert m < TOL["depth_mean"] and x < TOL["depth_max"], (m, x)
+    assert rel(out["pred_seg"], ref["pred_seg"])[0] < TOL["seg_mean"]
+    # the same against what the UNMODIFIED reference produced (committed fixture)
+    g = golden(fixture)
+    s = int(g["dense_stride"])
+    m, x = rel(out["pred_depth"][3][..., ::s, ::s], torch.from_numpy(g["pred_depth_3"]))
+    assert m < TOL["depth_mean"] and x < TOL["depth_max"], (m, x)
+    assert rel(out["pred_logits"], torch.from_numpy(g["pred_logits"]))[1] < TOL["logits_max"]
+
+
+def test_unpinned_selections_agree_with_oracle():
+    """without pinning, the fp32-kept selection inputs must reproduce most of the oracle's choices"""
+    net, _, _ = model()
+    B, H, W = 2, 224, 320
+    images, _, _, _ = synth.synth_batch(B, H, W, seed=0)
+    trace, mine = {}, {}
+    ref = oracle.forward(synth_weights(), images, trace=trace)
+    with torch.no_grad():
+        out = net(images.cuda(), _trace=mine)
+    same = 0
+    for b in range(B):
+        same += len(set(mine["line_ids"][b].tolist()) & set(trace["line_ids"][b].tolist()))
+    assert same >= 0.85 * B * 20, "top-20 line sets diverge: %d of %d" % (same, B * 20)
+    m, x = rel(out["pred_depth"][3], ref["pred_depth"][3])
+    assert m < 5e-2, (m, x)          # un-pinned: a flipped sample point moves the anchor mixture
+
+
+def test_error_is_bf16_roundoff():
+    """the CUDA path's distance to the fp32 oracle is the distance of a bf16-rounded run of the oracle itself"""
+    net, _, _ = model()
+    B, H, W = 1, 224, 320
+    images, _, _, _ = synth.synth_batch(B, H, W, seed=0)
+    sd = synth_weights()
+    trace = {}
+    ref = oracle.forward(sd, images, trace=trace)
+    rnd = lambda t: t.bfloat16().float()  # noqa: E731
+    sdb = {k: (rnd(v) if v.is_floating_point() and v.dim() > 1 else v) for k, v in sd.items()}
+    names = ["linear", "conv2d", "layer_norm", "gelu", "relu", "elu"]
+    orig = {n: getattr(F, n) for n in names}
+    try:
+        for n in names:
+            setattr(F, n, (lambda f: (lambda *a, **k: rnd(f(*a, **k))))(orig[n]))
+        pin = {"line_ids": trace["line_ids"], "sample1": (trace["sample1"], trace["sample1_idx"]),
+               "sample2": (trace["sample2"], trace["sample2_idx"])}
+        emu = oracle.forward(sdb, images, pinned=pin)
+    finally:
+        for n in names:
+            setattr(F, n, orig[n])
+    with torch.no_grad():
+        out = net(images.cuda(), _pinned=pinned_from(trace))
+    e_emu = rel(emu["pred_depth"][3], ref["pred_depth"][3])[0]
+    e_cuda = rel(out["pred_depth"][3], ref["pred_depth"][3])[0]
+    assert e_cuda < 2.0 * e_emu + 5e-3, (e_cuda, e_emu)
+
+
+def test_criterion_on_device_outputs():
+    """SetCriterion with the CUDA cost-matrix kernel vs the oracle criterion on the SAME predictions"""
+    net, criterions, _ = model()
+    B, H, W = 2, 224, 320
+    images, targets, depth_gt, seg_gt = synth.synth_batch(B, H, W, seed=0)
+    with torch.no_grad():
+        out = net(images.cuda())
+    tg = [{k: v.cuda() for k, v in t.items()} for t in targets]
+    losses = criterions[0](out, tg)
+    cpu_out = {"pred_logits": out["pred_logits"].cpu(), "pred_lines": out["pred_lines"].cpu(),
+               "aux_outputs": [{k: v.cpu() for k, v in a.items()} for a in out["aux_outputs"]]}
+    ref_losses, _ = oracle.set_criterion(cpu_out, [t["lines"] for t in targets])
+    assert set(losses) == set(ref_losses)
+    for k in ref_losses:
+        assert abs(float(losses[k]) - float(ref_losses[k])) <= 2e-4 * max(1.0, abs(float(ref_losses[k]))), k
+    # dense losses through the reference-shaped criteria (engine_glassrgbd.py:65-90)
+    mask = (depth_gt >= 0.2) & (depth_gt < 10.0)
+    ref_d = oracle.depth_losses([d.cpu() for d in out["pred_depth"]], depth_gt)
+    for i, pd in enumerate(out["pred_depth"]):
+        size = pd.shape[-2:]
+        g = F.interpolate(depth_gt, size=size, mode="nearest").cuda()
+        m = F.interpolate(mask.to(torch.uint8), size=size, mode="nearest").to(torch.bool).cuda()
+        w = (0.25, 0.25, 0.25, 1.0)[i]
+        got = float(criterions[1](pd, g, m)) * w
+        assert abs(got - float(ref_d[i])) <= 1e-3 * max(1.0, abs(float(ref_d[i]))), (i, got, float(ref_d[i]))
+    got_s = float(criterions[2](out["pred_seg"], seg_gt.squeeze(1).cuda())) * 2.0
+    assert abs(got_s - float(oracle.seg_loss(out["pred_seg"].cpu(), seg_gt))) < 1e-3
+
+
+def test_benchmark_size_properties():
+    """BASELINE configs[1] size (16 x 480 x 640): finite, in range, and every image's result is independent of its
+    batch neighbours (the property that makes batch sharding across GPUs exact)."""
+    net, _, _ = model()
+    B, H, W = 16, 480, 640
+    images, _, _, _ = synth.synth_batch(B, H, W, seed=3)
+    x = images.cuda()
+    tr = {}
+    with torch.no_grad():
+        full = net(x, _trace=tr)
+        # same discrete selections for the solo run: a 1-ulp difference in a near-tied line logit would otherwise
+        # legitimately pick another reference line
+        pin = {"line_ids": tr["line_ids"][5:6], "sample1": tr["sample1"][5:6], "sample2": tr["sample2"][5:6]}
+        solo = net(x[5:6], _pinned=pin)
+    d = full["pred_depth"][3]
+    assert d.shape == (B, 1, H, W) and torch.isfinite(d).all() and float(d.min()) > 0 and float(d.max()) < 10.0
+    assert full["pred_seg"].shape == (B, 2, H, W) and torch.isfinite(full["pred_seg"]).all()
+    assert full["pred_logits"].shape == (B, 100, 2) and full["pred_lines"].shape == (B, 100, 6)
+    assert float(full["pred_lines"].min()) >= 0 and float(full["pred_lines"].max()) <= 1
+    # cuDNN chooses other algorithms for the backbone at batch 1 (different bf16 rounding of C2..C5) and the network
+    # amplifies a 1-ulp feature difference ~3x, so the two runs agree to bf16 round-off, not bit-for-bit
+    m, xm = rel(full["pred_depth"][3][5:6], solo["pred_depth"][3])
+    assert m < TOL["depth_mean"], (m, xm)
+    assert rel(full["pred_logits"][5:6], solo["pred_logits"])[1] < TOL["logits_max"]
