@@ -38,9 +38,11 @@ struct GemmParams {
   int stages;
   uint32_t a_stage_bytes, b_stage_bytes;  // 1024-aligned slot sizes
   uint32_t a_tx_bytes, b_tx_bytes;        // bytes TMA actually delivers per stage
-  uint32_t a_dy_bytes, b_sub_bytes;
+  uint32_t a_off[9], b_off[9];            // byte offsets of the A / B operand of every MMA sub-step inside a stage
+  int resident;                           // 1: all weights live in shared memory for the whole kernel
+  uint32_t w_kc_bytes, w_total_bytes;     // resident weights: bytes per channel chunk / in total
   uint32_t layout_type;                   // UMMA smem descriptor layout: 2=SW128 4=SW64 6=SW32
-  uint32_t sbo_bytes;                     // 8 rows * row bytes
+  uint32_t sbo_a, sbo_b;                  // byte stride between 8-row groups of the A / B operand
   uint32_t idesc;
   uint32_t acc_stride;                    // TMEM columns between the two accumulators
   uint32_t tmem_cols;
@@ -173,7 +175,9 @@ template <int ACT>
 __device__ __forceinline__ float act_fn(float v) {
   if (ACT == GWD_ACT_RELU) return fmaxf(v, 0.f);
   if (ACT == GWD_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
-  if (ACT == GWD_ACT_ELU) return v > 0.f ? v : expm1f(v);
+  // branch-free ELU: exp(min(v,0)) - 1 with the fast exponential (abs error < 1e-7, far below bf16 output rounding);
+  // libm expm1f made the epilogue of the dense-head convs the bottleneck (profiles/README.md)
+  if (ACT == GWD_ACT_ELU) return fmaxf(v, 0.f) + (__expf(fminf(v, 0.f)) - 1.f);
   if (ACT == GWD_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
   return v;
 }
@@ -243,12 +247,15 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + static_cast<size_t>(p.stages) * p.a_stage_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_b + static_cast<size_t>(p.stages) * p.b_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(
+      smem_b + (p.resident ? ((p.w_total_bytes + 1023u) & ~1023u) : static_cast<size_t>(p.stages) * p.b_stage_bytes));
   uint64_t* full_bar = bars;                      // [stages]
   uint64_t* empty_bar = bars + kMaxStages;        // [stages]
   uint64_t* tmem_full = bars + 2 * kMaxStages;    // [2]
   uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint64_t* w_bar = bars + 2 * kMaxStages + 4;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+  uint32_t* mma_tab = tmem_ptr + 4;   // [2][36] descriptor start-address increments (16-byte units) per MMA sub-step
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -263,11 +270,17 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kNumEpilogueWarps);
     }
+    mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
   if (warp == 1) {
+    const int ks = p.BK / 16;
+    for (int i = lane; i < p.nsub * ks; i += 32) {
+      mma_tab[i] = (p.a_off[i / ks] + (i % ks) * 32) >> 4;
+      mma_tab[36 + i] = (p.b_off[i / ks] + (i % ks) * 32) >> 4;
+    }
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
                  "r"(p.tmem_cols)
                  : "memory");
@@ -283,6 +296,11 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      if (p.resident) {  // small filters: fetch every weight once, they stay in shared memory for all tiles of this CTA
+        mbar_arrive_expect_tx(w_bar, p.w_total_bytes);
+        for (int kc = 0; kc < p.kchunks; ++kc)
+          tma_load_3d(smem_b + static_cast<size_t>(kc) * p.w_kc_bytes, &map_b, w_bar, kc * p.BK, 0, 0);
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         TileCoord t = decode_tile(p, tile);
         for (int kc = 0; kc < p.kchunks; ++kc) {
@@ -291,8 +309,9 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes + p.b_tx_bytes);
             tma_load_4d(smem_a + static_cast<size_t>(stage) * p.a_stage_bytes, &map_a, &full_bar[stage],
                         p.x_coff + kc * p.BK, t.x0 + dx - p.pad, t.y0 - p.pad, t.b);
-            tma_load_3d(smem_b + static_cast<size_t>(stage) * p.b_stage_bytes, &map_b, &full_bar[stage],
-                        kc * p.BK, t.n0, dx * p.nsub + t.b * p.w_img_stride);
+            if (!p.resident)
+              tma_load_3d(smem_b + static_cast<size_t>(stage) * p.b_stage_bytes, &map_b, &full_bar[stage],
+                          kc * p.BK, t.n0, dx * p.nsub + t.b * p.w_img_stride);
             if (++stage == p.stages) {
               stage = 0;
               phase ^= 1u;
@@ -308,7 +327,11 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      const int ksteps = p.BK / 16;
+      const int nmma = p.nsub * (p.BK / 16);
+      if (p.resident) {
+        mbar_wait(w_bar, 0);
+        tcgen05_fence_after();
+      }
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tcgen05_fence_after();
@@ -318,14 +341,15 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t a_base = smem_u32(smem_a + static_cast<size_t>(stage) * p.a_stage_bytes);
-          const uint32_t b_base = smem_u32(smem_b + static_cast<size_t>(stage) * p.b_stage_bytes);
-          for (int sub = 0; sub < p.nsub; ++sub) {
-            for (int k = 0; k < ksteps; ++k) {
-              uint64_t adesc = make_smem_desc(a_base + sub * p.a_dy_bytes + k * 32, p.sbo_bytes, p.layout_type);
-              uint64_t bdesc = make_smem_desc(b_base + sub * p.b_sub_bytes + k * 32, p.sbo_bytes, p.layout_type);
-              umma_bf16(d_tmem, adesc, bdesc, p.idesc, accumulate);
-              accumulate = 1;
-            }
+          const uint32_t b_base = p.resident ? smem_u32(smem_b + static_cast<size_t>(it / p.ndx) * p.w_kc_bytes)
+                                             : smem_u32(smem_b + static_cast<size_t>(stage) * p.b_stage_bytes);
+          // the single issuing thread is the critical path of small tiles: descriptors are one add per operand
+          const uint64_t adesc0 = make_smem_desc(a_base, p.sbo_a, p.layout_type);
+          const uint64_t bdesc0 = make_smem_desc(b_base, p.sbo_b, p.layout_type);
+#pragma unroll 4
+          for (int i = 0; i < nmma; ++i) {
+            umma_bf16(d_tmem, adesc0 + mma_tab[i], bdesc0 + mma_tab[36 + i], p.idesc, accumulate);
+            accumulate = 1;
           }
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == p.stages) {
@@ -525,9 +549,23 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   p.n_tiles = n_tiles;
   p.Nt = d->n_pad / n_tiles;
   GWD_CHECK_ARG(d->ln_g == nullptr || n_tiles == 1, "gwd_conv_gemm: LayerNorm epilogue needs n_pad <= 256");
+  // Resident-weight mode: when the whole packed filter fits in ~96 KB of shared memory it is fetched once per CTA
+  // and only activations stream through the TMA ring.  For 3x3 convs this mode also loads ONE (TH+2)x(TW+2) halo box
+  // per channel chunk and forms all nine taps from it: tap (dy,dx) is the same box read at a start address shifted
+  // by (dy*(TW+2)+dx) pixel rows, with TW = 8 so that each 8-row MMA group is one image row and the group stride
+  // (SBO) is uniform.  (The 128/64/32-byte swizzle is a function of the absolute shared-memory address, as the
+  // K-advance of +32 B inside a row already relies on, so a start address that is not 1024-byte aligned is fine.)
+  const uint64_t w_bytes = static_cast<uint64_t>(d->taps) * p.Nt * d->cin * 2;
+  p.resident = (!d->w_per_image && n_tiles == 1 && w_bytes <= 96 * 1024 && (!conv || d->H >= 12)) ? 1 : 0;
+  int box_w, box_h;
   // M tiling: TW x TH = 128 pixels, TW a multiple of 8
   if (!conv) {
     p.TW = 128; p.TH = 1;
+    box_w = 128; box_h = 1;
+  } else if (p.resident) {
+    p.TW = 8; p.TH = 16;
+    box_w = p.TW + 2; box_h = p.TH + 2;
+    p.nsub = 9; p.ndx = 1;
   } else {
     const int cand[5][2] = {{16, 8}, {8, 16}, {32, 4}, {64, 2}, {128, 1}};
     int64_t best = -1;
@@ -538,32 +576,54 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
         best = cover; p.TW = cand[i][0]; p.TH = cand[i][1];
       }
     }
+    box_w = p.TW; box_h = p.TH + 2;
   }
   p.tiles_x = static_cast<int>(gwd_ceil_div(d->W, p.TW));
   p.tiles_y = static_cast<int>(gwd_ceil_div(d->H, p.TH));
   p.m_tiles = p.tiles_x * p.tiles_y * d->B;
   // K chunking
   p.BK = (d->cin % 64 == 0) ? 64 : (d->cin % 32 == 0) ? 32 : 16;
-  const int a_rows = (p.TH + 2 * p.pad) * p.TW;
+  const int a_rows = box_w * box_h;
   auto round1k = [](uint32_t v) { return (v + 1023u) & ~1023u; };
   const uint32_t budget = 200 * 1024;
-  while (true) {
+  uint32_t w_region = 0;
+  if (p.resident) {
     p.a_tx_bytes = static_cast<uint32_t>(a_rows) * p.BK * 2;
-    p.b_tx_bytes = static_cast<uint32_t>(p.nsub) * p.Nt * p.BK * 2;
+    p.b_tx_bytes = 0;
     p.a_stage_bytes = round1k(p.a_tx_bytes);
-    p.b_stage_bytes = round1k(p.b_tx_bytes);
-    if ((p.a_stage_bytes + p.b_stage_bytes) * 3 <= budget || p.BK == 16) break;
-    p.BK /= 2;  // keep at least 3 stages in flight
+    p.b_stage_bytes = 0;
+    p.w_kc_bytes = static_cast<uint32_t>(d->taps) * p.Nt * p.BK * 2;
+    p.w_total_bytes = static_cast<uint32_t>(w_bytes);
+    w_region = round1k(p.w_total_bytes);
+    p.kchunks = d->cin / p.BK;
+    p.stages = static_cast<int>((budget - w_region) / p.a_stage_bytes);
+  } else {
+    while (true) {
+      p.a_tx_bytes = static_cast<uint32_t>(a_rows) * p.BK * 2;
+      p.b_tx_bytes = static_cast<uint32_t>(p.nsub) * p.Nt * p.BK * 2;
+      p.a_stage_bytes = round1k(p.a_tx_bytes);
+      p.b_stage_bytes = round1k(p.b_tx_bytes);
+      if ((p.a_stage_bytes + p.b_stage_bytes) * 3 <= budget || p.BK == 16) break;
+      p.BK /= 2;  // keep at least 3 stages in flight
+    }
+    p.kchunks = d->cin / p.BK;
+    p.stages = static_cast<int>(budget / (p.a_stage_bytes + p.b_stage_bytes));
   }
-  p.kchunks = d->cin / p.BK;
-  p.stages = static_cast<int>(budget / (p.a_stage_bytes + p.b_stage_bytes));
   if (p.stages > kMaxStages) p.stages = kMaxStages;
   GWD_CHECK_ARG(p.stages >= 2, "gwd_conv_gemm: tile does not fit shared memory");
   const uint32_t row_bytes = p.BK * 2;
   p.layout_type = row_bytes == 128 ? 2u : row_bytes == 64 ? 4u : 6u;
-  p.sbo_bytes = 8 * row_bytes;
-  p.a_dy_bytes = static_cast<uint32_t>(p.TW) * row_bytes;
-  p.b_sub_bytes = static_cast<uint32_t>(p.Nt) * row_bytes;
+  p.sbo_b = 8 * row_bytes;
+  p.sbo_a = (conv && p.resident) ? static_cast<uint32_t>(box_w) * row_bytes : 8 * row_bytes;
+  for (int sub = 0; sub < p.nsub; ++sub) {
+    if (conv && p.resident) {   // sub = dx*3 + dy (the packed tap order)
+      int dx = sub / 3, dy = sub % 3;
+      p.a_off[sub] = static_cast<uint32_t>(dy * box_w + dx) * row_bytes;
+    } else {
+      p.a_off[sub] = static_cast<uint32_t>(sub) * p.TW * row_bytes;   // dy shift of TW rows
+    }
+    p.b_off[sub] = static_cast<uint32_t>(sub) * p.Nt * row_bytes;
+  }
   // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 @17, M>>4 @24
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.Nt >> 3) << 17) |
             (static_cast<uint32_t>(kTileM >> 4) << 24);
@@ -594,8 +654,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
                           static_cast<cuuint64_t>(d->H), static_cast<cuuint64_t>(d->B)};
     cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d->x_cstride) * 2, static_cast<cuuint64_t>(d->W) * d->x_cstride * 2,
                           static_cast<cuuint64_t>(d->H) * d->W * d->x_cstride * 2};
-    cuuint32_t box[4] = {static_cast<cuuint32_t>(p.BK), static_cast<cuuint32_t>(p.TW),
-                         static_cast<cuuint32_t>(p.TH + 2 * p.pad), 1};
+    cuuint32_t box[4] = {static_cast<cuuint32_t>(p.BK), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -610,7 +669,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
                           static_cast<cuuint64_t>(d->taps) * (d->w_per_image ? d->B : 1)};
     cuuint64_t gstr[2] = {static_cast<cuuint64_t>(d->cin) * 2, static_cast<cuuint64_t>(d->n_pad) * d->cin * 2};
     cuuint32_t box[3] = {static_cast<cuuint32_t>(p.BK), static_cast<cuuint32_t>(p.Nt),
-                         static_cast<cuuint32_t>(p.nsub)};
+                         static_cast<cuuint32_t>(p.resident ? d->taps : p.nsub)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->w), gdim, gstr, box, estr,
                         CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -621,8 +680,8 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
     }
   }
 
-  const size_t smem_bytes = 1024 + static_cast<size_t>(p.stages) * (p.a_stage_bytes + p.b_stage_bytes) +
-                            (2 * kMaxStages + 4) * sizeof(uint64_t) + 16;
+  const size_t smem_bytes = 1024 + static_cast<size_t>(p.stages) * (p.a_stage_bytes + p.b_stage_bytes) + w_region +
+                            (2 * kMaxStages + 5) * sizeof(uint64_t) + 16 + 72 * sizeof(uint32_t);
   const int total_tiles = p.m_tiles * p.n_tiles;
   int grid = gwd_num_sms();
   if (grid > total_tiles) grid = total_tiles;
