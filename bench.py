@@ -162,8 +162,9 @@ def main():
 
     # ------------------------------------------------------------ device-resident throughput
     with torch.no_grad():
+        step = plan.forward_graphed if net.use_cuda_graph else plan.forward
         for i in range(max(args.warmup, 3)):
-            plan.forward(resident[i % NB])
+            step(resident[i % NB])
         barrier()
         sampler = ClockSampler(local_rank)
         sampler.start()
@@ -172,10 +173,15 @@ def main():
         barrier()
         e0.record()
         for i in range(args.steps):
-            plan.forward(resident[i % NB])
+            step(resident[i % NB])
         e1.record()
         barrier()
         launches = capi.launch_count()
+        if net.use_cuda_graph:   # replayed launches are not re-issued through the C ABI: count one eager step instead
+            capi.reset_launch_count()
+            plan.forward(resident[0])
+            torch.cuda.synchronize()
+            launches = capi.launch_count() * args.steps
         sampler.stop_flag = True
         ms = reduce_max_ms(e0.elapsed_time(e1))
         value = world * B * args.steps / (ms / 1000.0)
@@ -236,7 +242,8 @@ def main():
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": world * B, "image": [H, W], "parallelism": "dp%d (replicas, no data-path collective)" % world,
-                       "l2": "4 rotating input batches (236 MB > L2); per-step activations are several GB"},
+                       "l2": "4 rotating input batches (236 MB > L2); per-step activations are several GB",
+                       "cuda_graph": bool(net.use_cuda_graph)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
     print(json.dumps(line), flush=True)

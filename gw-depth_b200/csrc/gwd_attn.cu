@@ -240,50 +240,36 @@ struct DiffuseFilter {
   float w[kDiffHeads * kDiffHeads * 9];
   float b[kDiffHeads];
 };
-__global__ void __launch_bounds__(128) gwd_ref_diffuse_conv_kernel(const float* __restrict__ a, float* __restrict__ raw,
-                                                                   const __grid_constant__ DiffuseFilter flt,
-                                                                   double* __restrict__ stats, int P, int R) {
-  extern __shared__ float tile[];                         // [heads][band+2][R+2] zero padded
-  const int heads = kDiffHeads;
-  const int y0 = blockIdx.x * kDiffBand, b = blockIdx.y;
-  const int rows = min(kDiffBand, P - y0);
+// body for one group of 4 output channels: OC0 is a compile-time constant so every filter tap is an FFMA with an
+// immediate constant-bank operand (no filter loads at all)
+template <int OC0>
+__device__ __forceinline__ void diffuse_conv_body(const float* tile, const DiffuseFilter& flt, float* __restrict__ raw,
+                                                  double* __restrict__ stats, int b, int y0, int rows, int P, int R) {
+  constexpr int heads = kDiffHeads;
   const int TR = kDiffBand + 2, TC = R + 2;
-  for (int i = threadIdx.x; i < heads * TR * TC; i += blockDim.x) {
-    int ic = i / (TR * TC);
-    int rem = i - ic * TR * TC;
-    int ty = rem / TC, tx = rem - ty * TC;
-    int y = y0 + ty - 1, x = tx - 1;
-    float v = 0.f;
-    if (y >= 0 && y < P && x >= 0 && x < R && ty < rows + 2) v = a[((static_cast<int64_t>(b) * heads + ic) * P + y) * R + x];
-    tile[i] = v;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int oc0 = warp * 4;
+  const int lane = threadIdx.x & 31;
   float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-  for (int pix = lane; pix < rows * R; pix += 32) {
+  for (int pix = threadIdx.x; pix < rows * R; pix += blockDim.x) {
     int ty = pix / R, tx = pix - ty * R;
     float acc[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) acc[o] = flt.b[oc0 + o];
-#pragma unroll 4
-    for (int ic = 0; ic < kDiffHeads; ++ic) {
-      const float* t = tile + (static_cast<size_t>(ic) * TR + ty) * TC + tx;
+    for (int o = 0; o < 4; ++o) acc[o] = flt.b[OC0 + o];
+#pragma unroll
+    for (int ic = 0; ic < heads; ++ic) {
+      const float* t = tile + (ic * TR + ty) * TC + tx;
       float in[9];
 #pragma unroll
       for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) in[dy * 3 + dx] = t[dy * TC + dx];
 #pragma unroll
-      for (int o = 0; o < 4; ++o) {
-        const float* wk = flt.w + ((oc0 + o) * kDiffHeads + ic) * 9;
+      for (int o = 0; o < 4; ++o)
 #pragma unroll
-        for (int k = 0; k < 9; ++k) acc[o] = fmaf(wk[k], in[k], acc[o]);
-      }
+        for (int k = 0; k < 9; ++k) acc[o] = fmaf(flt.w[((OC0 + o) * heads + ic) * 9 + k], in[k], acc[o]);
     }
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
-      raw[((static_cast<int64_t>(b) * heads + oc0 + o) * P + y0 + ty) * R + tx] = acc[o];
+      raw[((static_cast<int64_t>(b) * heads + OC0 + o) * P + y0 + ty) * R + tx] = acc[o];
       s[o] += acc[o];
       ss[o] += acc[o] * acc[o];
     }
@@ -297,9 +283,38 @@ __global__ void __launch_bounds__(128) gwd_ref_diffuse_conv_kernel(const float* 
       dss += __shfl_xor_sync(0xffffffffu, dss, sh);
     }
     if (lane == 0) {
-      atomicAdd(&stats[(static_cast<int64_t>(b) * heads + oc0 + o) * 2], ds);
-      atomicAdd(&stats[(static_cast<int64_t>(b) * heads + oc0 + o) * 2 + 1], dss);
+      atomicAdd(&stats[(static_cast<int64_t>(b) * heads + OC0 + o) * 2], ds);
+      atomicAdd(&stats[(static_cast<int64_t>(b) * heads + OC0 + o) * 2 + 1], dss);
     }
+  }
+}
+
+// grid (row bands, B, 4 output-channel groups), block 128: all threads stride over the band's pixels
+__global__ void __launch_bounds__(128) gwd_ref_diffuse_conv_kernel(const float* __restrict__ a, float* __restrict__ raw,
+                                                                   const __grid_constant__ DiffuseFilter flt,
+                                                                   double* __restrict__ stats, int P, int R) {
+  extern __shared__ float tile[];                         // [heads][band+2][R+2] zero padded
+  constexpr int heads = kDiffHeads;
+  const int y0 = blockIdx.x * kDiffBand, b = blockIdx.y;
+  const int rows = min(kDiffBand, P - y0);
+  const int TR = kDiffBand + 2, TC = R + 2;
+  // one (channel, tile row) per warp iteration, lanes over the columns: no per-element div / mod
+  for (int rowid = threadIdx.x >> 5; rowid < heads * TR; rowid += blockDim.x >> 5) {
+    int ic = rowid / TR, ty = rowid - ic * TR;
+    int y = y0 + ty - 1;
+    bool yok = y >= 0 && y < P && ty < rows + 2;
+    const float* src = a + ((static_cast<int64_t>(b) * heads + ic) * P + (yok ? y : 0)) * R;
+    for (int tx = threadIdx.x & 31; tx < TC; tx += 32) {
+      int x = tx - 1;
+      tile[rowid * TC + tx] = (yok && x >= 0 && x < R) ? src[x] : 0.f;
+    }
+  }
+  __syncthreads();
+  switch (blockIdx.z) {
+    case 0: diffuse_conv_body<0>(tile, flt, raw, stats, b, y0, rows, P, R); break;
+    case 1: diffuse_conv_body<4>(tile, flt, raw, stats, b, y0, rows, P, R); break;
+    case 2: diffuse_conv_body<8>(tile, flt, raw, stats, b, y0, rows, P, R); break;
+    default: diffuse_conv_body<12>(tile, flt, raw, stats, b, y0, rows, P, R); break;
   }
 }
 
@@ -447,7 +462,7 @@ extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w_h
       configured = true;
     }
   }
-  dim3 grid(static_cast<unsigned>(gwd_ceil_div(P, kDiffBand)), B);
+  dim3 grid(static_cast<unsigned>(gwd_ceil_div(P, kDiffBand)), B, kDiffHeads / 4);
   gwd_ref_diffuse_conv_kernel<<<grid, 128, smem, stream>>>(a_in, raw_ws, flt, stats_ws, P, R);
   GWD_LAUNCHED();
   int64_t per_img = static_cast<int64_t>(P) * R, total = per_img * B * heads;

@@ -84,14 +84,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity)
+        : "r"(addr), "r"(parity), "r"(0x989680u)   // suspend-time hint (ns): sleep in hardware instead of spinning
         : "memory");
     if (done) break;
     // watchdog: a protocol bug must fault, never hang the box (try_wait itself sleeps in HW)
-    if (++spins > (1u << 24)) __trap();
+    if (++spins > (1u << 20)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,

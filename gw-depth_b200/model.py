@@ -129,6 +129,9 @@ class GlassRGBD(_Node):
         _init_parameters(self)
         self._plan = None
         self._plan_key = None
+        # replay the forward as one CUDA graph per input shape (GWD_CUDA_GRAPH=0 launches kernel by kernel)
+        import os
+        self.use_cuda_graph = os.environ.get("GWD_CUDA_GRAPH", "1") != "0"
 
     # the kernel plan caches re-laid-out weights; rebuild it whenever a parameter changed or moved
     def _current_key(self):
@@ -159,7 +162,10 @@ class GlassRGBD(_Node):
             raise NotImplementedError("padded (ragged) batches are not built yet on the CUDA path; batch equal-size images")
         plan = self.plan()      # raises off-GPU: there is no CPU path
         with torch.cuda.device(images.device):
-            return plan.forward(images.float(), pinned=_pinned, trace=_trace)
+            x = images.float().contiguous()
+            if self.use_cuda_graph and _pinned is None and _trace is None:
+                return plan.forward_graphed(x)
+            return plan.forward(x, pinned=_pinned, trace=_trace)
 
 
 # --------------------------------------------------------------------------------------------------
