@@ -234,71 +234,32 @@ __global__ void __launch_bounds__(128) gwd_ref_scores_kernel(const bf16* __restr
 // per-(image, channel) sum / sum of squares accumulated in fp64 for the whole-image LayerNorm of phase 2.
 // a: [B][heads][P][R] fp32.  grid (row bands, B), block 128: warp w produces output channels 4w..4w+3 (register tile),
 // lanes stride over the band's pixels.  The 16x16x9 filter travels as a kernel parameter (constant bank operands).
-constexpr int kDiffBand = 21;
+constexpr int kDiffBand = 7;
 constexpr int kDiffHeads = 16;
 struct DiffuseFilter {
   float w[kDiffHeads * kDiffHeads * 9];
   float b[kDiffHeads];
 };
-// body for one group of 4 output channels: OC0 is a compile-time constant so every filter tap is an FFMA with an
-// immediate constant-bank operand (no filter loads at all)
-template <int OC0>
-__device__ __forceinline__ void diffuse_conv_body(const float* tile, const DiffuseFilter& flt, float* __restrict__ raw,
-                                                  double* __restrict__ stats, int b, int y0, int rows, int P, int R) {
-  constexpr int heads = kDiffHeads;
-  const int TR = kDiffBand + 2, TC = R + 2;
-  const int lane = threadIdx.x & 31;
-  float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
-  for (int pix = threadIdx.x; pix < rows * R; pix += blockDim.x) {
-    int ty = pix / R, tx = pix - ty * R;
-    float acc[4];
-#pragma unroll
-    for (int o = 0; o < 4; ++o) acc[o] = flt.b[OC0 + o];
-#pragma unroll
-    for (int ic = 0; ic < heads; ++ic) {
-      const float* t = tile + (ic * TR + ty) * TC + tx;
-      float in[9];
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) in[dy * 3 + dx] = t[dy * TC + dx];
-#pragma unroll
-      for (int o = 0; o < 4; ++o)
-#pragma unroll
-        for (int k = 0; k < 9; ++k) acc[o] = fmaf(flt.w[((OC0 + o) * heads + ic) * 9 + k], in[k], acc[o]);
-    }
-#pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      raw[((static_cast<int64_t>(b) * heads + OC0 + o) * P + y0 + ty) * R + tx] = acc[o];
-      s[o] += acc[o];
-      ss[o] += acc[o] * acc[o];
-    }
-  }
-#pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    double ds = s[o], dss = ss[o];
-#pragma unroll
-    for (int sh = 16; sh > 0; sh >>= 1) {
-      ds += __shfl_xor_sync(0xffffffffu, ds, sh);
-      dss += __shfl_xor_sync(0xffffffffu, dss, sh);
-    }
-    if (lane == 0) {
-      atomicAdd(&stats[(static_cast<int64_t>(b) * heads + OC0 + o) * 2], ds);
-      atomicAdd(&stats[(static_cast<int64_t>(b) * heads + OC0 + o) * 2 + 1], dss);
-    }
-  }
-}
-
-// grid (row bands, B, 4 output-channel groups), block 128: all threads stride over the band's pixels
-__global__ void __launch_bounds__(128) gwd_ref_diffuse_conv_kernel(const float* __restrict__ a, float* __restrict__ raw,
+// Direct convolution, one pixel x 4 output channels per thread: lanes map to consecutive pixels (stride-1, conflict-free
+// shared-memory reads of the input window), the 9 taps of the thread's 4 output channels come as float4 broadcasts
+// from a [ic][tap][oc] copy of the filter.  8 warps: warp w -> channel group w%4, pixel half w/4.
+// grid (row bands of kDiffBand rows, B), block 256.
+__global__ void __launch_bounds__(256) gwd_ref_diffuse_conv_kernel(const float* __restrict__ a, float* __restrict__ raw,
                                                                    const __grid_constant__ DiffuseFilter flt,
                                                                    double* __restrict__ stats, int P, int R) {
-  extern __shared__ float tile[];                         // [heads][band+2][R+2] zero padded
+  extern __shared__ __align__(16) float dsm[];
   constexpr int heads = kDiffHeads;
   const int y0 = blockIdx.x * kDiffBand, b = blockIdx.y;
   const int rows = min(kDiffBand, P - y0);
   const int TR = kDiffBand + 2, TC = R + 2;
-  // one (channel, tile row) per warp iteration, lanes over the columns: no per-element div / mod
+  float* wsm = dsm;                                       // [heads ic][9][heads oc]
+  float* tile = dsm + heads * 9 * heads;                  // [heads][TR][TC] zero padded
+  __shared__ float red[8][8];
+  for (int i = threadIdx.x; i < heads * heads * 9; i += blockDim.x) {
+    int oc = i / (heads * 9), rem = i - oc * heads * 9;
+    int ic = rem / 9, k = rem - ic * 9;
+    wsm[(ic * 9 + k) * heads + oc] = flt.w[i];
+  }
   for (int rowid = threadIdx.x >> 5; rowid < heads * TR; rowid += blockDim.x >> 5) {
     int ic = rowid / TR, ty = rowid - ic * TR;
     int y = y0 + ty - 1;
@@ -310,11 +271,50 @@ __global__ void __launch_bounds__(128) gwd_ref_diffuse_conv_kernel(const float* 
     }
   }
   __syncthreads();
-  switch (blockIdx.z) {
-    case 0: diffuse_conv_body<0>(tile, flt, raw, stats, b, y0, rows, P, R); break;
-    case 1: diffuse_conv_body<4>(tile, flt, raw, stats, b, y0, rows, P, R); break;
-    case 2: diffuse_conv_body<8>(tile, flt, raw, stats, b, y0, rows, P, R); break;
-    default: diffuse_conv_body<12>(tile, flt, raw, stats, b, y0, rows, P, R); break;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ocg = warp & 3, half = warp >> 2;
+  float s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+  for (int pix = half * 32 + lane; pix < rows * R; pix += 64) {
+    int ty = pix / R, tx = pix - ty * R;
+    float acc[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) acc[o] = flt.b[ocg * 4 + o];
+#pragma unroll 2
+    for (int ic = 0; ic < heads; ++ic) {
+      const float* t = tile + (ic * TR + ty) * TC + tx;
+      const float* wk = wsm + ic * 9 * heads + ocg * 4;
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        float v = t[(k / 3) * TC + (k % 3)];
+        float4 w4 = *reinterpret_cast<const float4*>(wk + k * heads);
+        acc[0] = fmaf(w4.x, v, acc[0]);
+        acc[1] = fmaf(w4.y, v, acc[1]);
+        acc[2] = fmaf(w4.z, v, acc[2]);
+        acc[3] = fmaf(w4.w, v, acc[3]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      raw[((static_cast<int64_t>(b) * heads + ocg * 4 + o) * P + y0 + ty) * R + tx] = acc[o];
+      s[o] += acc[o];
+      ss[o] += acc[o] * acc[o];
+    }
+  }
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    s[o] = gwd_warp_sum(s[o]);
+    ss[o] = gwd_warp_sum(ss[o]);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) { red[warp][o] = s[o]; red[warp][4 + o] = ss[o]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {   // 16 channels x {sum, sumsq}: one fp64 atomic per CTA each
+    int oc = threadIdx.x >> 1, which = threadIdx.x & 1;
+    int g = oc >> 2, o = oc & 3;
+    double v = static_cast<double>(red[g][which * 4 + o]) + static_cast<double>(red[4 + g][which * 4 + o]);
+    atomicAdd(&stats[(static_cast<int64_t>(b) * heads + oc) * 2 + which], v);
   }
 }
 
@@ -453,7 +453,7 @@ extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w_h
   memcpy(flt.w, w_host, sizeof(flt.w));
   memcpy(flt.b, bias_host, sizeof(flt.b));
   GWD_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * B * heads, stream));
-  size_t smem = static_cast<size_t>(heads) * (kDiffBand + 2) * (R + 2) * sizeof(float);
+  size_t smem = (static_cast<size_t>(heads) * (kDiffBand + 2) * (R + 2) + static_cast<size_t>(heads) * heads * 9) * sizeof(float);
   GWD_CHECK_ARG(smem <= 200 * 1024, "gwd_ref_diffuse: %d reference points do not fit shared memory", R);
   if (smem > 48 * 1024) {
     static bool configured = false;
@@ -462,8 +462,8 @@ extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w_h
       configured = true;
     }
   }
-  dim3 grid(static_cast<unsigned>(gwd_ceil_div(P, kDiffBand)), B, kDiffHeads / 4);
-  gwd_ref_diffuse_conv_kernel<<<grid, 128, smem, stream>>>(a_in, raw_ws, flt, stats_ws, P, R);
+  dim3 grid(static_cast<unsigned>(gwd_ceil_div(P, kDiffBand)), B);
+  gwd_ref_diffuse_conv_kernel<<<grid, 256, smem, stream>>>(a_in, raw_ws, flt, stats_ws, P, R);
   GWD_LAUNCHED();
   int64_t per_img = static_cast<int64_t>(P) * R, total = per_img * B * heads;
   int blocks = static_cast<int>(std::min<int64_t>(gwd_ceil_div(total, 256), gwd_num_sms() * 8));

@@ -8,7 +8,6 @@
 namespace {
 
 typedef __nv_bfloat16 bf16;
-constexpr int kMaxVec = 8;  // a warp covers up to 32 lanes * 8 vectors * 8 channels = 2048 channels
 
 __device__ __forceinline__ void load8(const bf16* p, float (&f)[8]) {
   uint4 u = *reinterpret_cast<const uint4*>(p);
@@ -48,13 +47,15 @@ __device__ __forceinline__ float group_sum(float v, int G) {
   return v;
 }
 
+template <int NV>
 struct WarpRow {
-  float f[kMaxVec][8];
+  float f[NV][8];
 };
 
-__device__ __forceinline__ void row_load(WarpRow& r, const bf16* src, int C, const RowGroup& g, bool valid) {
+template <int NV>
+__device__ __forceinline__ void row_load(WarpRow<NV>& r, const bf16* src, int C, const RowGroup& g, bool valid) {
 #pragma unroll
-  for (int v = 0; v < kMaxVec; ++v) {
+  for (int v = 0; v < NV; ++v) {
     int c = (v * g.G + g.sub) * 8;
     if (c < C && valid) load8(src + c, r.f[v]);
     else {
@@ -63,9 +64,10 @@ __device__ __forceinline__ void row_load(WarpRow& r, const bf16* src, int C, con
     }
   }
 }
-__device__ __forceinline__ void row_add(WarpRow& r, const bf16* src, int C, const RowGroup& g) {
+template <int NV>
+__device__ __forceinline__ void row_add(WarpRow<NV>& r, const bf16* src, int C, const RowGroup& g) {
 #pragma unroll
-  for (int v = 0; v < kMaxVec; ++v) {
+  for (int v = 0; v < NV; ++v) {
     int c = (v * g.G + g.sub) * 8;
     if (c < C) {
       float t[8];
@@ -75,19 +77,21 @@ __device__ __forceinline__ void row_add(WarpRow& r, const bf16* src, int C, cons
     }
   }
 }
-__device__ __forceinline__ void row_store(const WarpRow& r, bf16* dst, int C, const RowGroup& g) {
+template <int NV>
+__device__ __forceinline__ void row_store(const WarpRow<NV>& r, bf16* dst, int C, const RowGroup& g) {
 #pragma unroll
-  for (int v = 0; v < kMaxVec; ++v) {
+  for (int v = 0; v < NV; ++v) {
     int c = (v * g.G + g.sub) * 8;
     if (c < C) store8(dst + c, r.f[v]);
   }
 }
 // LayerNorm over the first n channels (channels >= n are padding and come out as 0).  Every lane of the warp must call.
-__device__ __forceinline__ void row_layernorm(WarpRow& r, int C, int n, const RowGroup& g, const float* gam, const float* bet,
+template <int NV>
+__device__ __forceinline__ void row_layernorm(WarpRow<NV>& r, int C, int n, const RowGroup& g, const float* gam, const float* bet,
                                               float eps) {
   float s = 0.f;
 #pragma unroll
-  for (int v = 0; v < kMaxVec; ++v) {
+  for (int v = 0; v < NV; ++v) {
     int c = (v * g.G + g.sub) * 8;
     if (c < C) {
 #pragma unroll
@@ -97,7 +101,7 @@ __device__ __forceinline__ void row_layernorm(WarpRow& r, int C, int n, const Ro
   float mean = group_sum(s, g.G) / n;
   float ss = 0.f;
 #pragma unroll
-  for (int v = 0; v < kMaxVec; ++v) {
+  for (int v = 0; v < NV; ++v) {
     int c = (v * g.G + g.sub) * 8;
     if (c < C) {
 #pragma unroll
@@ -106,7 +110,7 @@ __device__ __forceinline__ void row_layernorm(WarpRow& r, int C, int n, const Ro
   }
   float rstd = rsqrtf(group_sum(ss, g.G) / n + eps);
 #pragma unroll
-  for (int v = 0; v < kMaxVec; ++v) {
+  for (int v = 0; v < NV; ++v) {
     int c = (v * g.G + g.sub) * 8;
     if (c < C) {
 #pragma unroll
@@ -114,13 +118,19 @@ __device__ __forceinline__ void row_layernorm(WarpRow& r, int C, int n, const Ro
     }
   }
 }
-__device__ __forceinline__ void row_act(WarpRow& r, int act, int C, const RowGroup& g) {
+template <int NV>
+__device__ __forceinline__ void row_act(WarpRow<NV>& r, int act, int C, const RowGroup& g) {
   if (act == GWD_ACT_NONE) return;
 #pragma unroll
-  for (int v = 0; v < kMaxVec; ++v) {
+  for (int v = 0; v < NV; ++v) {
     if ((v * g.G + g.sub) * 8 < C) {
+      if (act == GWD_ACT_GELU) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r.f[v][i] = gwd_apply_act(r.f[v][i], act);
+        for (int i = 0; i < 8; ++i) r.f[v][i] = gwd_gelu(r.f[v][i]);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) r.f[v][i] = gwd_apply_act(r.f[v][i], act);
+      }
     }
   }
 }
@@ -128,13 +138,14 @@ __device__ __forceinline__ void row_act(WarpRow& r, int act, int C, const RowGro
 // ------------------------------------------------------------------------------------------------
 // out[row] = act(LN(x[row] + res[row]))     (res, LN optional)
 // ------------------------------------------------------------------------------------------------
+template <int NV>
 __global__ void gwd_layernorm_kernel(const bf16* x, int64_t x_rs, const bf16* res, int64_t res_rs, const float* g,
                                      const float* b, float eps, int act, bf16* out, int64_t out_rs, int64_t rows, int C,
                                      int n) {
   RowGroup rg = row_group(C);
   bool live = rg.row < rows;
   int64_t row = live ? rg.row : 0;
-  WarpRow r;
+  WarpRow<NV> r;
   row_load(r, x + row * x_rs, C, rg, live);
   if (res && live) row_add(r, res + row * res_rs, C, rg);
   if (g) row_layernorm(r, C, n, rg, g, b, eps);
@@ -143,11 +154,12 @@ __global__ void gwd_layernorm_kernel(const bf16* x, int64_t x_rs, const bf16* re
 }
 
 // out[row] = x[row] + addend[row % period]
+template <int NV>
 __global__ void gwd_add_rows_kernel(const bf16* x, int64_t x_rs, const bf16* addend, int64_t a_rs, int64_t period,
                                     bf16* out, int64_t out_rs, int64_t rows, int C) {
   RowGroup rg = row_group(C);
   if (rg.row >= rows) return;
-  WarpRow r;
+  WarpRow<NV> r;
   row_load(r, x + rg.row * x_rs, C, rg, true);
   row_add(r, addend + (rg.row % period) * a_rs, C, rg);
   row_store(r, out + rg.row * out_rs, C, rg);
@@ -173,6 +185,7 @@ __device__ __forceinline__ bool win_source(const WinGeom& gm, int64_t orow, int&
   x = (xs + gm.shift) % gm.Wp;
   return y < gm.H && x < gm.W;
 }
+template <int NV>
 __global__ void gwd_window_gather_kernel(const bf16* x, int64_t x_rs, const float* g, const float* b, float eps, bf16* out,
                                          int64_t out_rs, WinGeom gm, int C, int n) {
   RowGroup rg = row_group(C);
@@ -181,12 +194,12 @@ __global__ void gwd_window_gather_kernel(const bf16* x, int64_t x_rs, const floa
   int64_t orow = live ? rg.row : 0;
   int bb, y, xx;
   bool valid = win_source(gm, orow, bb, y, xx) && live;
-  WarpRow r;
+  WarpRow<NV> r;
   row_load(r, x + ((static_cast<int64_t>(bb) * gm.H + (valid ? y : 0)) * gm.W + (valid ? xx : 0)) * x_rs, C, rg, valid);
   if (g) row_layernorm(r, C, n, rg, g, b, eps);
   if (!valid) {   // padding tokens are exact zeros, not LN(0)  (zero padding happens after norm1, :659-671)
 #pragma unroll
-    for (int v = 0; v < kMaxVec; ++v)
+    for (int v = 0; v < NV; ++v)
 #pragma unroll
       for (int i = 0; i < 8; ++i) r.f[v][i] = 0.f;
   }
@@ -194,6 +207,7 @@ __global__ void gwd_window_gather_kernel(const bf16* x, int64_t x_rs, const floa
 }
 
 // Swin window merge: y[b,y,x] = shortcut[b,y,x] + win[row(b,y,x)]; optionally y_ln = LN(y)   (:731-755)
+template <int NV>
 __global__ void gwd_window_merge_kernel(const bf16* win, int64_t win_rs, const bf16* shortcut, int64_t sc_rs, bf16* out,
                                         int64_t out_rs, const float* g, const float* b, float eps, bf16* out_ln,
                                         int64_t ln_rs, WinGeom gm, int C, int n) {
@@ -208,7 +222,7 @@ __global__ void gwd_window_merge_kernel(const bf16* win, int64_t win_rs, const b
   int nWx = gm.Wp / gm.ws, nWy = gm.Hp / gm.ws;
   int64_t wrow = ((static_cast<int64_t>(bb) * nWy + ys / gm.ws) * nWx + xs / gm.ws) * (gm.ws * gm.ws) +
                  (ys % gm.ws) * gm.ws + xs % gm.ws;
-  WarpRow r;
+  WarpRow<NV> r;
   row_load(r, win + wrow * win_rs, C, rg, live);
   if (live) {
     row_add(r, shortcut + pix * sc_rs, C, rg);
@@ -443,6 +457,21 @@ __global__ void gwd_nchw_to_nhwc_kernel(const float* x, int B, int C, int64_t HW
   }
 }
 
+// number of 8-channel vector slots a lane holds for a C-channel row
+inline int slots_for(int C) {
+  int need = C >> 3;
+  int G = need <= 8 ? 8 : (need <= 16 ? 16 : 32);
+  return (need + G - 1) / G;
+}
+#define GWD_ROW_DISPATCH(KERNEL, C, GRID, STREAM, ...)                                   \
+  do {                                                                                  \
+    int nv__ = slots_for(C);                                                            \
+    if (nv__ <= 1) KERNEL<1><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__);                    \
+    else if (nv__ <= 2) KERNEL<2><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__);               \
+    else if (nv__ <= 4) KERNEL<4><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__);               \
+    else KERNEL<8><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__);                              \
+  } while (0)
+
 int grid_for(int64_t total, int threads) {
   int64_t blocks = gwd_ceil_div(total, threads);
   int64_t cap = static_cast<int64_t>(gwd_num_sms()) * 16;
@@ -461,8 +490,8 @@ extern "C" int gwd_layernorm(const void* x, int64_t x_rs, const void* res, int64
   GWD_CHECK_ARG(x && out && rows > 0, "gwd_layernorm: null pointer / empty");
   GWD_CHECK_ARG(GWD_ALIGN8(C) && C <= 2048 && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs) && GWD_ALIGN8(res_rs),
                 "gwd_layernorm: C and strides must be multiples of 8, C <= 2048");
-  gwd_layernorm_kernel<<<static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), 256, 0, stream>>>(
-      static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(res), res_rs, gamma, beta, eps, act,
+  GWD_ROW_DISPATCH(gwd_layernorm_kernel, C, static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), stream,
+                   static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(res), res_rs, gamma, beta, eps, act,
       static_cast<bf16*>(out), out_rs, rows, C, n);
   GWD_LAUNCHED();
   return GWD_OK;
@@ -474,8 +503,8 @@ extern "C" int gwd_add_rows(const void* x, int64_t x_rs, const void* addend, int
   GWD_CHECK_ARG(x && addend && out && rows > 0 && period > 0, "gwd_add_rows: bad argument");
   GWD_CHECK_ARG(GWD_ALIGN8(C) && C <= 2048 && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs) && GWD_ALIGN8(a_rs),
                 "gwd_add_rows: alignment");
-  gwd_add_rows_kernel<<<static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), 256, 0, stream>>>(
-      static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(addend), a_rs, period, static_cast<bf16*>(out), out_rs,
+  GWD_ROW_DISPATCH(gwd_add_rows_kernel, C, static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), stream,
+                   static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(addend), a_rs, period, static_cast<bf16*>(out), out_rs,
       rows, C);
   GWD_LAUNCHED();
   return GWD_OK;
@@ -497,8 +526,8 @@ extern "C" int gwd_window_gather(const void* x, int64_t x_rs, const float* gamma
   WinGeom gm;
   make_geom(gm, B, H, W, ws, shift);
   int64_t rows = static_cast<int64_t>(B) * gm.Hp * gm.Wp;
-  gwd_window_gather_kernel<<<static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), 256, 0, stream>>>(
-      static_cast<const bf16*>(x), x_rs, gamma, beta, eps, static_cast<bf16*>(out), out_rs, gm, C, n);
+  GWD_ROW_DISPATCH(gwd_window_gather_kernel, C, static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), stream,
+                   static_cast<const bf16*>(x), x_rs, gamma, beta, eps, static_cast<bf16*>(out), out_rs, gm, C, n);
   GWD_LAUNCHED();
   return GWD_OK;
 }
@@ -515,8 +544,8 @@ extern "C" int gwd_window_merge(const void* win, int64_t win_rs, const void* sho
   WinGeom gm;
   make_geom(gm, B, H, W, ws, shift);
   int64_t rows = static_cast<int64_t>(B) * H * W;
-  gwd_window_merge_kernel<<<static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), 256, 0, stream>>>(
-      static_cast<const bf16*>(win), win_rs, static_cast<const bf16*>(shortcut), sc_rs, static_cast<bf16*>(out), out_rs,
+  GWD_ROW_DISPATCH(gwd_window_merge_kernel, C, static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), stream,
+                   static_cast<const bf16*>(win), win_rs, static_cast<const bf16*>(shortcut), sc_rs, static_cast<bf16*>(out), out_rs,
       gamma, beta, eps, static_cast<bf16*>(out_ln), ln_rs, gm, C, n);
   GWD_LAUNCHED();
   return GWD_OK;

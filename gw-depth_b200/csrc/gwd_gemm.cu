@@ -84,14 +84,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(addr), "r"(parity), "r"(0x989680u)   // suspend-time hint (ns): sleep in hardware instead of spinning
+        : "r"(addr), "r"(parity)
         : "memory");
     if (done) break;
     // watchdog: a protocol bug must fault, never hang the box (try_wait itself sleeps in HW)
-    if (++spins > (1u << 20)) __trap();
+    if (++spins > (1u << 24)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
@@ -174,7 +174,7 @@ struct RowCtx {
 template <int ACT>
 __device__ __forceinline__ float act_fn(float v) {
   if (ACT == GWD_ACT_RELU) return fmaxf(v, 0.f);
-  if (ACT == GWD_ACT_GELU) return 0.5f * v * (1.f + erff(v * 0.70710678118654752f));
+  if (ACT == GWD_ACT_GELU) return gwd_gelu(v);
   // branch-free ELU: exp(min(v,0)) - 1 with the fast exponential (abs error < 1e-7, far below bf16 output rounding);
   // libm expm1f made the epilogue of the dense-head convs the bottleneck (profiles/README.md)
   if (ACT == GWD_ACT_ELU) return fmaxf(v, 0.f) + (__expf(fminf(v, 0.f)) - 1.f);
