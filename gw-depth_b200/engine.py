@@ -110,7 +110,18 @@ class Engine:
         w = (sd[conv + ".weight"] * scale.view(-1, 1, 1, 1)).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         return w, shift.to(torch.bfloat16)
 
+    def _fold_packed(self, conv, bn, taps):
+        """same folding, packed for gwd_conv_gemm (1x1 -> taps=1, 3x3 stride 1 -> taps=9); the BN shift is the bias"""
+        sd = self.sd
+        scale = sd[bn + ".weight"] * (sd[bn + ".running_var"] + 1e-5).rsqrt()
+        shift = sd[bn + ".bias"] - sd[bn + ".running_mean"] * scale
+        w = sd[conv + ".weight"] * scale.view(-1, 1, 1, 1)
+        return pack_linear(w.flatten(1), shift) if taps == 1 else pack_conv3x3(w, shift)
+
     def _pack_backbone(self):
+        """stem, max-pool and the six stride-2 convolutions stay on cuDNN; every 1x1 and stride-1 3x3 convolution of the
+        bottlenecks (46 of the 53 convolutions, ~90% of the backbone FLOPs) runs on gwd_conv_gemm with the folded
+        FrozenBN shift, the ReLU and the residual add fused in its epilogue."""
         p = "backbone.0.body."
         self.stem = self._fold(p + "conv1", p + "bn1")
         self.blocks = []
@@ -118,29 +129,34 @@ class Engine:
             stage = []
             for bi in range(nb):
                 q = "%slayer%d.%d." % (p, li, bi)
-                blk = {"c1": self._fold(q + "conv1", q + "bn1"), "c2": self._fold(q + "conv2", q + "bn2"),
-                       "c3": self._fold(q + "conv3", q + "bn3"), "stride": 2 if (li > 1 and bi == 0) else 1}
+                stride = 2 if (li > 1 and bi == 0) else 1
+                blk = {"c1": self._fold_packed(q + "conv1", q + "bn1", 1), "c3": self._fold_packed(q + "conv3", q + "bn3", 1),
+                       "stride": stride}
+                blk["c2"] = self._fold(q + "conv2", q + "bn2") if stride == 2 else self._fold_packed(q + "conv2", q + "bn2", 9)
                 if (q + "downsample.0.weight") in self.sd:
-                    blk["down"] = self._fold(q + "downsample.0", q + "downsample.1")
+                    blk["down"] = (self._fold(q + "downsample.0", q + "downsample.1") if stride == 2
+                                   else self._fold_packed(q + "downsample.0", q + "downsample.1", 1))
                 stage.append(blk)
             self.blocks.append(stage)
 
     def backbone(self, images):
-        """torchvision-style ResNet-50 C2..C5 (src/models/backbone.py:58-92) on cuDNN, bf16 channels-last.
-        Returns channels-last [B,h,w,C] bf16 views."""
+        """torchvision-style ResNet-50 C2..C5 with frozen batch-norm (src/models/backbone.py:19-92), bf16 channels-last.
+        Returns [B,h,w,C] bf16 maps."""
         x = images.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         x = F.relu_(F.conv2d(x, self.stem[0], self.stem[1], stride=2, padding=3))
-        x = F.max_pool2d(x, 3, 2, 1)
+        x = F.max_pool2d(x, 3, 2, 1).permute(0, 2, 3, 1).contiguous()        # -> [B,h,w,64] channels-last buffer
         feats = []
         for stage in self.blocks:
             for blk in stage:
-                y = F.relu_(F.conv2d(x, *blk["c1"]))
-                y = F.relu_(F.conv2d(y, *blk["c2"], stride=blk["stride"], padding=1))
-                y = F.conv2d(y, *blk["c3"])
-                if "down" in blk:
-                    x = F.conv2d(x, *blk["down"], stride=blk["stride"])
-                x = F.relu_(y.add_(x))
-            feats.append(x.permute(0, 2, 3, 1))
+                y = conv_gemm(x, blk["c1"], post_act=ACT_RELU)
+                if blk["stride"] == 2:      # stride-2 3x3 and 1x1 projections: cuDNN on NCHW views of the same memory
+                    y = F.relu_(F.conv2d(y.permute(0, 3, 1, 2), *blk["c2"], stride=2, padding=1)).permute(0, 2, 3, 1)
+                    idt = F.conv2d(x.permute(0, 3, 1, 2), *blk["down"], stride=2).permute(0, 2, 3, 1)
+                else:
+                    y = conv_gemm(y, blk["c2"], post_act=ACT_RELU)
+                    idt = conv_gemm(x, blk["down"]) if "down" in blk else x
+                x = conv_gemm(y.contiguous(), blk["c3"], res=idt.contiguous(), res_mode=RES_BEFORE_NORM, post_act=ACT_RELU)
+            feats.append(x)
         return feats
 
     # ------------------------------------------------------------------ setup: DETR transformer
