@@ -83,9 +83,17 @@ def measured_peak():
     return 1590.0, "fallback (B200_PROFILING.md, 1.59 PFLOP/s)"
 
 
+def use_all_host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1; the CPU arm is entitled to every core of the box"""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    torch.set_num_threads(max(n, 1))
+    return torch.get_num_threads()
+
+
 def cpu_oracle_rate(max_seconds=20.0, min_iters=2):
     """images/s of the CPU oracle at B=1, 480x640 (a bounded sample of the batch-16 workload)"""
     from helpers import oracle, synth, synth_weights
+    use_all_host_threads()
     sd = synth_weights()
     images, _, _, _ = synth.synth_batch(1, H, W, seed=0)
     oracle.forward(sd, images)  # warm
@@ -102,6 +110,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     from helpers import oracle, synth, synth_weights
+    use_all_host_threads()
     sd = synth_weights()
     images, _, _, _ = synth.synth_batch(1, H, W, seed=0)
     for _ in range(min(args.warmup, 2)):

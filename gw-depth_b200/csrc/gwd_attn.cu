@@ -7,6 +7,7 @@
 //   gwd_token_attention  per-window class-token CHANNEL attention, multiscale_transformerr.py:561-578
 //   gwd_ref_scores / gwd_ref_diffuse / gwd_ref_requery
 //                        the line end-point ("glass structure") re-query of WindowAttention, :281-310
+#include <stdlib.h>
 #include <string.h>
 #include <algorithm>
 #include "gwd_common.cuh"
@@ -373,6 +374,8 @@ __global__ void __launch_bounds__(128) gwd_ref_requery_kernel(const float* __res
 // ---------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------
+int gwd_attention_tc_try(const gwd_attn_desc* d, cudaStream_t stream);   // gwd_attn_tc.cu (tcgen05 path)
+
 extern "C" int gwd_attention(const gwd_attn_desc* d, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GWD_CHECK_ARG(d && d->q && d->k && d->v && d->o, "gwd_attention: null pointer");
@@ -381,6 +384,13 @@ extern "C" int gwd_attention(const gwd_attn_desc* d, void* stream_) {
   GWD_CHECK_ARG(d->k_row_stride % 2 == 0 && d->v_row_stride % 2 == 0 && d->k_item_stride % 2 == 0 && d->v_item_stride % 2 == 0 &&
                     (reinterpret_cast<uintptr_t>(d->k) & 3) == 0 && (reinterpret_cast<uintptr_t>(d->v) & 3) == 0,
                 "gwd_attention: K/V must be 4-byte aligned with even strides");
+  {  // DETR-shaped problems (head_dim 32, no bias / window mask, Lk <= 480) run on the tensor cores
+    static const bool tc_enabled = []() { const char* e = getenv("GWD_ATTN_TC"); return !(e && e[0] == '0'); }();
+    if (tc_enabled) {
+      int rc = gwd_attention_tc_try(d, stream);
+      if (rc <= 0) return rc;   // 0 = launched, < 0 = error, 1 = not eligible
+    }
+  }
   AttnParams p;
   p.q = static_cast<const bf16*>(d->q); p.k = static_cast<const bf16*>(d->k); p.v = static_cast<const bf16*>(d->v);
   p.o = static_cast<bf16*>(d->o);
