@@ -243,7 +243,25 @@ def main():
             dist.destroy_process_group()
         return
     cpu = None
+    eager = None
     if world == 1 and not args.no_cpu_baseline:
+        # context only (not the reference arm): the same oracle restatement run as eager fp32 PyTorch ON THE GPU, i.e.
+        # what the reference's op-by-op structure (library kernels, per-image Python loops, host syncs) costs on a B200
+        try:
+            from helpers import oracle
+            sd_gpu = {k: v.to(dev) for k, v in synth_weights().items()}
+            with torch.no_grad():
+                oracle.forward(sd_gpu, resident[0])
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                for i in range(3):
+                    oracle.forward(sd_gpu, resident[i % NB])
+                torch.cuda.synchronize()
+            eager = {"value": 3 * B / (time.perf_counter() - t0), "unit": UNIT,
+                     "what": "oracle/gwdepth_oracle.py (port of the reference forward) as eager fp32 PyTorch on the same GPU, batch 16"}
+            del sd_gpu
+        except Exception as e:  # noqa: BLE001
+            eager = {"value": None, "error": repr(e)[:200]}
         rate, n = cpu_oracle_rate()
         cpu = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                "sample": "%d forwards of 1x3x480x640 (1/16 of a step) through oracle/gwdepth_oracle.py" % n}
@@ -254,7 +272,8 @@ def main():
                        "l2": "4 rotating input batches (236 MB > L2); per-step activations are several GB",
                        "cuda_graph": bool(net.use_cuda_graph)},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu}
+            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
+            "gpu_eager_port": eager}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

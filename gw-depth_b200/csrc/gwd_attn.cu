@@ -35,12 +35,30 @@ struct AttnParams {
 // warp-wide broadcasts (no shuffles, no per-query synchronisation).  HD is a template parameter so q / acc stay in
 // registers.
 // -------------------------------------------------------------------------------------------------
-template <int HD>
+// smem element type: fp32 (fast path) or bf16 (long key axes, e.g. L = 1200 at 960x1280, that would not fit as fp32)
+template <typename T> struct KvRow;
+template <> struct KvRow<float> {
+  static __device__ __forceinline__ float4 load4(const float* row, int w) { return reinterpret_cast<const float4*>(row)[w]; }
+  static __device__ __forceinline__ void store2(float* row, int w, float2 v) { row[2 * w] = v.x; row[2 * w + 1] = v.y; }
+};
+template <> struct KvRow<bf16> {
+  static __device__ __forceinline__ float4 load4(const bf16* row, int w) {
+    uint2 u = reinterpret_cast<const uint2*>(row)[w];
+    float2 a = gwd_unpack_bf16x2(u.x), b = gwd_unpack_bf16x2(u.y);
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ void store2(bf16* row, int w, float2 v) {
+    reinterpret_cast<uint32_t*>(row)[w] = gwd_pack_bf16x2(v.x, v.y);
+  }
+};
+
+template <int HD, typename T>
 __global__ void __launch_bounds__(128) gwd_attention_tq_kernel(const AttnParams p) {
-  extern __shared__ __align__(16) float smf[];
+  extern __shared__ __align__(16) uint8_t smraw[];
+  T* smf = reinterpret_cast<T*>(smraw);
   const int Lk = p.Lk;
-  float* Ks = smf;                                  // [Lk][HD]
-  float* Vs = smf + static_cast<size_t>(Lk) * HD;   // [Lk][HD]
+  T* Ks = smf;                                  // [Lk][HD]
+  T* Vs = smf + static_cast<size_t>(Lk) * HD;   // [Lk][HD]
   const int item = blockIdx.z, head = blockIdx.y;
   const bf16* kbase = p.k + item * p.k_is + head * HD;
   const bf16* vbase = p.v + item * p.v_is + head * HD;
@@ -49,8 +67,8 @@ __global__ void __launch_bounds__(128) gwd_attention_tq_kernel(const AttnParams 
     int j = idx / HW, w = idx - j * HW;
     float2 kk = gwd_unpack_bf16x2(reinterpret_cast<const uint32_t*>(kbase + j * p.k_rs)[w]);
     float2 vv = gwd_unpack_bf16x2(reinterpret_cast<const uint32_t*>(vbase + j * p.v_rs)[w]);
-    Ks[j * HD + 2 * w] = kk.x; Ks[j * HD + 2 * w + 1] = kk.y;
-    Vs[j * HD + 2 * w] = vv.x; Vs[j * HD + 2 * w + 1] = vv.y;
+    KvRow<T>::store2(Ks + j * HD, w, kk);
+    KvRow<T>::store2(Vs + j * HD, w, vv);
   }
   __syncthreads();
   const int qi = blockIdx.x * blockDim.x + threadIdx.x;
@@ -69,11 +87,11 @@ __global__ void __launch_bounds__(128) gwd_attention_tq_kernel(const AttnParams 
   const uint8_t* kp = p.kpm ? p.kpm + static_cast<int64_t>(item) * Lk : nullptr;
   float m = -INFINITY, l = 0.f;
   for (int j = 0; j < Lk; ++j) {
-    const float4* kr = reinterpret_cast<const float4*>(Ks + j * HD);
+    const T* kr = Ks + j * HD;
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < HD / 4; ++w) {
-      float4 k4 = kr[w];
+      float4 k4 = KvRow<T>::load4(kr, w);
       s = fmaf(q[4 * w], k4.x, s); s = fmaf(q[4 * w + 1], k4.y, s);
       s = fmaf(q[4 * w + 2], k4.z, s); s = fmaf(q[4 * w + 3], k4.w, s);
     }
@@ -84,10 +102,10 @@ __global__ void __launch_bounds__(128) gwd_attention_tq_kernel(const AttnParams 
     float corr = __expf(m - mn), pj = __expf(s - mn);
     m = mn;
     l = l * corr + pj;
-    const float4* vr = reinterpret_cast<const float4*>(Vs + j * HD);
+    const T* vr = Vs + j * HD;
 #pragma unroll
     for (int w = 0; w < HD / 4; ++w) {
-      float4 v4 = vr[w];
+      float4 v4 = KvRow<T>::load4(vr, w);
       acc[4 * w] = fmaf(acc[4 * w], corr, pj * v4.x); acc[4 * w + 1] = fmaf(acc[4 * w + 1], corr, pj * v4.y);
       acc[4 * w + 2] = fmaf(acc[4 * w + 2], corr, pj * v4.z); acc[4 * w + 3] = fmaf(acc[4 * w + 3], corr, pj * v4.w);
     }
@@ -99,22 +117,27 @@ __global__ void __launch_bounds__(128) gwd_attention_tq_kernel(const AttnParams 
     reinterpret_cast<uint32_t*>(orow)[w] = gwd_pack_bf16x2(acc[2 * w] * inv, acc[2 * w + 1] * inv);
 }
 
-template <int HD>
-static int launch_attention_tq(const AttnParams& p, cudaStream_t stream) {
-  size_t smem = static_cast<size_t>(p.Lk) * HD * 2 * sizeof(float);
+template <int HD, typename T>
+static int launch_attention_tq_as(const AttnParams& p, cudaStream_t stream) {
+  size_t smem = static_cast<size_t>(p.Lk) * HD * 2 * sizeof(T);
   GWD_CHECK_ARG(smem <= 200 * 1024, "gwd_attention: Lk=%d does not fit shared memory", p.Lk);
   if (smem > 48 * 1024) {
     static bool configured = false;
     if (!configured) {
-      GWD_CUDA(cudaFuncSetAttribute(gwd_attention_tq_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      GWD_CUDA(cudaFuncSetAttribute(gwd_attention_tq_kernel<HD, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       configured = true;
     }
   }
   int threads = p.Lq <= 64 ? 64 : 128;
   dim3 grid(static_cast<unsigned>(gwd_ceil_div(p.Lq, threads)), p.heads, p.items);
-  gwd_attention_tq_kernel<HD><<<grid, threads, smem, stream>>>(p);
+  gwd_attention_tq_kernel<HD, T><<<grid, threads, smem, stream>>>(p);
   GWD_LAUNCHED();
   return GWD_OK;
+}
+template <int HD>
+static int launch_attention_tq(const AttnParams& p, cudaStream_t stream) {
+  if (static_cast<size_t>(p.Lk) * HD * 2 * sizeof(float) <= 160 * 1024) return launch_attention_tq_as<HD, float>(p, stream);
+  return launch_attention_tq_as<HD, bf16>(p, stream);
 }
 
 // -------------------------------------------------------------------------------------------------

@@ -92,7 +92,7 @@ def sine_position(mask, num_pos_feats, normalize):
     if normalize:
         y_embed = y_embed / (y_embed[:, -1:, :] + 1e-6) * (2 * math.pi)
         x_embed = x_embed / (x_embed[:, :, -1:] + 1e-6) * (2 * math.pi)
-    dim_t = torch.arange(num_pos_feats, dtype=torch.float32)
+    dim_t = torch.arange(num_pos_feats, dtype=torch.float32, device=mask.device)
     dim_t = 10000 ** (2 * (dim_t // 2) / num_pos_feats)
     px = x_embed[:, :, :, None] / dim_t
     py = y_embed[:, :, :, None] / dim_t
@@ -172,8 +172,8 @@ def from_windows(win, ws, B, H, W):  # inverse of to_windows
     return x.reshape(B, H, W, C)
 
 
-def shift_window_mask(Hp, Wp, ws, shift):  # multiscale_transformerr.py:937-955 (fill value -100)
-    img = torch.zeros(1, Hp, Wp, 1)
+def shift_window_mask(Hp, Wp, ws, shift, device=None):  # multiscale_transformerr.py:937-955 (fill value -100)
+    img = torch.zeros(1, Hp, Wp, 1, device=device)
     cnt = 0
     for hs in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
         for wsl in (slice(0, -ws), slice(-ws, -shift), slice(-shift, None)):
@@ -319,7 +319,7 @@ def class_swin_block(x, dtok, stok, H, W, p, nheads, ws, shift, mask):
 def swin_stage(x, H, W, p, depth, nheads, ws, ref=None, ref_pos=None, dtok=None, stok=None):
     """BasicLayer.forward, mst.py:926-979: blocks alternate shift 0 / ws//2"""
     Hp, Wp = math.ceil(H / ws) * ws, math.ceil(W / ws) * ws
-    mask = shift_window_mask(Hp, Wp, ws, ws // 2)
+    mask = shift_window_mask(Hp, Wp, ws, ws // 2, x.device)
     for i in range(depth):
         shift = 0 if i % 2 == 0 else ws // 2
         bp = p.sub("blocks.%d" % i)
@@ -404,7 +404,7 @@ def certain_sample(pred_small, pred_large, sample_num, interval, min_depth):
         if remain > 0:                                                                   # :348-350
             idx = torch.cat([idx, idx[-remain:]])
         if remain < 0:                                                                   # :351-355
-            m = int(torch.argmax(torch.tensor(counts)))
+            m = int(torch.argmax(torch.tensor(counts)))  # noqa: host list, as in the reference
             picks[m] = picks[m][:remain]
             idx = torch.cat(picks)
         all_idx.append(idx)
@@ -540,7 +540,7 @@ def forward(sd, images, mask=None, cfg=None, pinned=None, trace=None):
     p = P(sd)
     B, _, H, W = images.shape
     if mask is None:
-        mask = torch.zeros(B, H, W, dtype=torch.bool)
+        mask = torch.zeros(B, H, W, dtype=torch.bool, device=images.device)
     with torch.no_grad():
         feats = resnet50_features(images, p.sub("backbone.0.body"))
         masks = [downsample_mask(mask, f.shape[-2:]) for f in feats]
