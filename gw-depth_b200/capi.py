@@ -30,7 +30,7 @@ class GemmDesc(ctypes.Structure):
         ("res", c_void_p), ("res_cstride", c_int), ("res_coff", c_int), ("res_mode", c_int),
         ("y", c_void_p), ("y_cstride", c_int), ("y_coff", c_int), ("y_f32", c_int),
         ("y_raw", c_void_p), ("yraw_cstride", c_int), ("yraw_coff", c_int),
-        ("store_n", c_int), ("w_per_image", c_int),
+        ("store_n", c_int), ("w_per_image", c_int), ("upsample2", c_int),
     ]
 
 

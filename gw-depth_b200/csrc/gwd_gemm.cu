@@ -59,6 +59,8 @@ struct GemmParams {
   int y_cstride, y_coff, y_f32;
   __nv_bfloat16* y_raw;
   int yraw_cstride, yraw_coff;
+  int phase_n;      // > 0: fused nearest x2 up-sampling, output channels are 4 phase groups of phase_n channels
+  int ln_groups;    // LayerNorm is applied per group of n / ln_groups channels (1 = whole row)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -169,6 +171,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmParams& p, int tile) 
 struct RowCtx {
   bool valid;
   int64_t pix;  // linear pixel index (b*H + y)*W + x
+  int b, py, px;
 };
 
 template <int ACT>
@@ -381,85 +384,108 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         int px = t.x0 + row % p.TW;
         rc.valid = (py < p.H) && (px < p.W);
         rc.pix = (static_cast<int64_t>(t.b) * p.H + py) * p.W + px;
+        rc.b = t.b; rc.py = py; rc.px = px;
       }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc) * p.acc_stride +
                              (static_cast<uint32_t>(quad * 32) << 16);
 
-      float mean = 0.f, rstd = 1.f;
-      if (HAS_LN) {
-        // statistics over the n logical channels of this pixel (both halves read the whole row)
-        float s = 0.f, ss = 0.f;
-        for (int c = 0; c < nchunks; ++c) {
-          float v[16];
-          load_chunk<PRE_ACT>(p, t_row + c * 16, t.n0 + c * 16, rc, v);
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            if (t.n0 + c * 16 + i < p.n) {
-              s += v[i];
-              ss += v[i] * v[i];
-            }
-          }
-        }
-        mean = s / static_cast<float>(p.n);
-        float var = fmaxf(ss / static_cast<float>(p.n) - mean * mean, 0.f);
-        rstd = rsqrtf(var + p.ln_eps);
-      }
-
-      for (int c = c_begin; c < c_end; ++c) {
-        const int n_base = t.n0 + c * 16;
-        float v[16];
-        load_chunk<PRE_ACT>(p, t_row + c * 16, n_base, rc, v);
-        if (p.y_raw != nullptr && rc.valid) {
-          store_bf16_16(p.y_raw + rc.pix * p.yraw_cstride + p.yraw_coff + n_base, v, n_base, p.store_n);
-        }
+      // A "segment" is a chunk range whose LayerNorm statistics are taken together.  Whole-row LayerNorm: both column
+      // halves read the full row for the statistics and store their own half.  Grouped LayerNorm (fused up-sampling:
+      // one group per output phase): each half owns whole groups.
+      const int groups = HAS_LN ? p.ln_groups : 1;
+      const int cpg = nchunks / groups;
+      const int seg_first = groups > 1 ? half * (groups / 2) : 0;
+      const int seg_last = groups > 1 ? (half + 1) * (groups / 2) : 1;
+      const int n_group = p.n / groups;
+      for (int seg = seg_first; seg < seg_last; ++seg) {
+        const int st_begin = groups > 1 ? seg * cpg : 0;
+        const int st_end = groups > 1 ? (seg + 1) * cpg : nchunks;
+        const int my_begin = groups > 1 ? st_begin : c_begin;
+        const int my_end = groups > 1 ? st_end : c_end;
+        float mean = 0.f, rstd = 1.f;
         if (HAS_LN) {
-          const float4* gp = reinterpret_cast<const float4*>(p.ln_g + n_base);
-          const float4* bp = reinterpret_cast<const float4*>(p.ln_b + n_base);
+          float s = 0.f, ss = 0.f;
+          for (int c = st_begin; c < st_end; ++c) {
+            float v[16];
+            load_chunk<PRE_ACT>(p, t_row + c * 16, t.n0 + c * 16, rc, v);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float4 g4 = __ldg(gp + i), b4 = __ldg(bp + i);
-            v[4 * i + 0] = (v[4 * i + 0] - mean) * rstd * g4.x + b4.x;
-            v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * g4.y + b4.y;
-            v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * g4.z + b4.z;
-            v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * g4.w + b4.w;
-          }
-        }
-        if (POST_ACT != GWD_ACT_NONE) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = act_fn<POST_ACT>(v[i]);
-        }
-        if (p.out_scale != 1.f) {
-#pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] *= p.out_scale;
-        }
-        if (p.res_mode == GWD_RES_AFTER && rc.valid) {
-          const uint4* rp = reinterpret_cast<const uint4*>(p.res + rc.pix * p.res_cstride + p.res_coff + n_base);
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            if (n_base + 8 * h + 8 <= p.store_n) {
-              uint4 u = __ldg(rp + h);
-              float2 f0 = gwd_unpack_bf16x2(u.x), f1 = gwd_unpack_bf16x2(u.y), f2 = gwd_unpack_bf16x2(u.z),
-                     f3 = gwd_unpack_bf16x2(u.w);
-              v[8 * h + 0] += f0.x; v[8 * h + 1] += f0.y; v[8 * h + 2] += f1.x; v[8 * h + 3] += f1.y;
-              v[8 * h + 4] += f2.x; v[8 * h + 5] += f2.y; v[8 * h + 6] += f3.x; v[8 * h + 7] += f3.y;
+            for (int i = 0; i < 16; ++i) {
+              if (groups > 1 || t.n0 + c * 16 + i < p.n) {
+                s += v[i];
+                ss += v[i] * v[i];
+              }
             }
           }
+          mean = s / static_cast<float>(n_group);
+          float var = fmaxf(ss / static_cast<float>(n_group) - mean * mean, 0.f);
+          rstd = rsqrtf(var + p.ln_eps);
         }
-        // channels beyond the logical width are padding: keep them exactly zero
+        for (int c = my_begin; c < my_end; ++c) {
+          const int n_base = t.n0 + c * 16;
+          float v[16];
+          load_chunk<PRE_ACT>(p, t_row + c * 16, n_base, rc, v);
+          if (p.y_raw != nullptr && rc.valid) {
+            store_bf16_16(p.y_raw + rc.pix * p.yraw_cstride + p.yraw_coff + n_base, v, n_base, p.store_n);
+          }
+          // output location: plain, or one of the four x2 up-sampling phases (channel group -> (oy, ox))
+          int64_t opix = rc.pix;
+          int och = n_base, olimit = p.store_n;
+          if (p.phase_n > 0) {
+            const int phase = n_base / p.phase_n;
+            och = n_base - phase * p.phase_n;
+            olimit = p.phase_n;
+            opix = (static_cast<int64_t>(rc.b) * (2 * p.H) + 2 * rc.py + (phase >> 1)) * (2 * p.W) + 2 * rc.px + (phase & 1);
+          }
+          if (HAS_LN) {
+            const float4* gp = reinterpret_cast<const float4*>(p.ln_g + och);
+            const float4* bp = reinterpret_cast<const float4*>(p.ln_b + och);
 #pragma unroll
-        for (int i = 0; i < 16; ++i)
-          if (n_base + i >= p.n) v[i] = 0.f;
-        if (rc.valid) {
-          if (p.y_f32) {
-            float* dst = reinterpret_cast<float*>(p.y) + rc.pix * p.y_cstride + p.y_coff + n_base;
+            for (int i = 0; i < 4; ++i) {
+              float4 g4 = __ldg(gp + i), b4 = __ldg(bp + i);
+              v[4 * i + 0] = (v[4 * i + 0] - mean) * rstd * g4.x + b4.x;
+              v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * g4.y + b4.y;
+              v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * g4.z + b4.z;
+              v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * g4.w + b4.w;
+            }
+          }
+          if (POST_ACT != GWD_ACT_NONE) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = act_fn<POST_ACT>(v[i]);
+          }
+          if (p.out_scale != 1.f) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] *= p.out_scale;
+          }
+          if (p.res_mode == GWD_RES_AFTER && rc.valid) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + rc.pix * p.res_cstride + p.res_coff + n_base);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (n_base + 8 * h + 8 <= p.store_n) {
+                uint4 u = __ldg(rp + h);
+                float2 f0 = gwd_unpack_bf16x2(u.x), f1 = gwd_unpack_bf16x2(u.y), f2 = gwd_unpack_bf16x2(u.z),
+                       f3 = gwd_unpack_bf16x2(u.w);
+                v[8 * h + 0] += f0.x; v[8 * h + 1] += f0.y; v[8 * h + 2] += f1.x; v[8 * h + 3] += f1.y;
+                v[8 * h + 4] += f2.x; v[8 * h + 5] += f2.y; v[8 * h + 6] += f3.x; v[8 * h + 7] += f3.y;
+              }
+            }
+          }
+          // channels beyond the logical width are padding: keep them exactly zero
+          if (n_base + 16 > p.n) {
 #pragma unroll
             for (int i = 0; i < 16; ++i)
-              if (n_base + i < p.store_n) dst[i] = v[i];
-          } else {
-            store_bf16_16(reinterpret_cast<__nv_bfloat16*>(p.y) + rc.pix * p.y_cstride + p.y_coff + n_base, v, n_base,
-                          p.store_n);
+              if (n_base + i >= p.n) v[i] = 0.f;
+          }
+          if (rc.valid) {
+            if (p.y_f32) {
+              float* dst = reinterpret_cast<float*>(p.y) + opix * p.y_cstride + p.y_coff + och;
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (och + i < olimit) dst[i] = v[i];
+            } else {
+              store_bf16_16(reinterpret_cast<__nv_bfloat16*>(p.y) + opix * p.y_cstride + p.y_coff + och, v, och, olimit);
+            }
           }
         }
       }
@@ -549,6 +575,10 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   p.n_tiles = n_tiles;
   p.Nt = d->n_pad / n_tiles;
   GWD_CHECK_ARG(d->ln_g == nullptr || n_tiles == 1, "gwd_conv_gemm: LayerNorm epilogue needs n_pad <= 256");
+  if (d->upsample2)
+    GWD_CHECK_ARG(d->taps == 9 && n_tiles == 1 && d->n == d->n_pad && (d->n_pad / 4) % 16 == 0 && d->res_mode == GWD_RES_NONE &&
+                      d->y_raw == nullptr && (p.Nt / 16) % 4 == 0,
+                  "gwd_conv_gemm: fused up-sampling needs a 3x3 filter with 4 x (multiple of 16) unpadded channels, no residual");
   // Resident-weight mode: when the whole packed filter fits in ~96 KB of shared memory it is fetched once per CTA
   // and only activations stream through the TMA ring.  For 3x3 convs this mode also loads ONE (TH+2)x(TW+2) halo box
   // per channel chunk and forms all nine taps from it: tap (dy,dx) is the same box read at a start address shifted
@@ -639,6 +669,8 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   p.y = d->y; p.y_cstride = d->y_cstride; p.y_coff = d->y_coff; p.y_f32 = d->y_f32;
   p.y_raw = static_cast<__nv_bfloat16*>(d->y_raw);
   p.yraw_cstride = d->yraw_cstride; p.yraw_coff = d->yraw_coff;
+  p.phase_n = d->upsample2 ? d->n_pad / 4 : 0;
+  p.ln_groups = d->upsample2 ? 4 : 1;
 
   EncodeTiledFn encode = get_encode_fn();
   if (encode == nullptr) {

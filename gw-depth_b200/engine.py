@@ -311,10 +311,10 @@ class Engine:
                                            cin_pad=width, col_map=torch.cat([feat, stok]))
         self.head["seg_fc2"] = pack_linear(sd[p + "seg_token_fuse.fc2.weight"], sd[p + "seg_token_fuse.fc2.bias"], cin_pad=hid_s)
         for kind in ("depth", "seg"):
-            self.head["up1_" + kind] = pack_conv3x3(sd[p + "upconv1_%s.conv.weight" % kind])
+            self.head["up1_" + kind] = ops.pack_upconv3x3(sd[p + "upconv1_%s.conv.weight" % kind])
             self.head["norm_" + kind] = _LN(sd, p + "norm_" + kind)
             self.head["conv1_" + kind] = pack_conv3x3(sd[p + "conv1_%s.0.weight" % kind])
-            self.head["up2_" + kind] = pack_conv3x3(sd[p + "upconv2_%s.conv.weight" % kind])
+            self.head["up2_" + kind] = ops.pack_upconv3x3(sd[p + "upconv2_%s.conv.weight" % kind])
             self.head["conv2_" + kind] = pack_conv3x3(sd[p + "conv2_%s.0.weight" % kind])
         self.head["get_depth"] = pack_conv3x3(sd[p + "get_depth.0.weight"])
         self.head["get_seg"] = pack_conv3x3(sd[p + "get_seg.weight"])
@@ -578,10 +578,11 @@ class Engine:
         for kind in ("depth", "seg"):
             t = conv_gemm(buf4, hd_[kind + "_fc1"], post_act=ACT_GELU, out_channels=hd_[kind + "_fc2"].cin_pad)
             f = conv_gemm(t, hd_[kind + "_fc2"]).view(B, H4, W4, td)
-            u = ops.upsample_nearest(f, 2 * H4, 2 * W4)
-            u = conv_gemm(u, hd_["up1_" + kind], bias=False, pre_act=ACT_ELU, ln=hd_["norm_" + kind].pair)
+            if (2 * H4, 2 * W4) != (H // 2, W // 2) or (H % 4 or W % 4):
+                raise NotImplementedError("the fused up-sampling convolutions need input sizes that are multiples of 4")
+            # upconv = nearest x2 + 3x3 conv + ELU (dense_upsample.py:82-90), the up-sampling folded into 4 phase filters
+            u = conv_gemm(f, hd_["up1_" + kind], bias=False, pre_act=ACT_ELU, ln=hd_["norm_" + kind].pair)
             u = conv_gemm(u, hd_["conv1_" + kind], bias=False, post_act=ACT_ELU)
-            u = ops.upsample_nearest(u, H, W)
             u = conv_gemm(u, hd_["up2_" + kind], bias=False, post_act=ACT_ELU)
             u = conv_gemm(u, hd_["conv2_" + kind], bias=False, post_act=ACT_ELU)
             outs[kind] = u

@@ -77,6 +77,30 @@ def pack_conv3x3(weight, bias=None, cin_pad=None, col_map=None):
     return PackedWeight(w.to(torch.bfloat16).contiguous(), b, 9, n, cin_pad)
 
 
+def pack_upconv3x3(weight):
+    """`upconv` (nearest x2 up-sampling followed by a bias-free 3x3 conv, src/models/dense_upsample.py:74-90) as ONE 3x3
+    conv on the low-resolution input with 4*Cout outputs: output pixel (2y+oy, 2x+ox) only sees low-res rows
+    {y-1, y} (oy = 0) or {y, y+1} (oy = 1), so the taps that land on the same low-res pixel are summed (in fp32).
+    Phase p = 2*oy + ox owns output channels [p*Cout, (p+1)*Cout)."""
+    n, c = weight.shape[:2]
+    assert n % 16 == 0 and c % 16 == 0
+    wf = weight.float()
+    # rows of the 3x3 filter (a = 0,1,2 <-> up-sampled rows 2y+oy-1 .. 2y+oy+1) -> low-res tap dy in {0,1,2} (= y-1,y,y+1)
+    taps = {0: {0: [0], 1: [1, 2], 2: []}, 1: {0: [], 1: [0, 1], 2: [2]}}
+    full = torch.zeros(4 * n, c, 3, 3, dtype=torch.float32, device=weight.device)
+    for oy in (0, 1):
+        for ox in (0, 1):
+            ph = 2 * oy + ox
+            for dy in range(3):
+                for dx in range(3):
+                    for a in taps[oy][dy]:
+                        for b in taps[ox][dx]:
+                            full[ph * n:(ph + 1) * n, :, dy, dx] += wf[:, :, a, b]
+    pw = pack_conv3x3(full)
+    pw.upsample2 = True
+    return pw
+
+
 def pad_vec(v, n_pad, fill=0.0):
     out = torch.full((n_pad,), fill, dtype=torch.float32, device=v.device)
     out[: v.numel()] = v.float()
@@ -114,10 +138,13 @@ def conv_gemm(x, pw, *, x_coff=0, out=None, y_coff=0, out_channels=None, out_f32
     # bf16 outputs carry all n_pad physical channels (pads are written as exact zeros) so that the next layer can
     # consume a 16-aligned K; fp32 outputs (small heads) carry the logical channels only
     store_n = pw.n if out_f32 else min(pw.n_pad, out_channels or pw.n_pad)
+    up2 = bool(getattr(pw, "upsample2", False))
     if out is None:
         oc = out_channels or store_n
-        out = torch.empty(tuple(x.shape[:-1]) + (oc,), dtype=torch.float32 if out_f32 else torch.bfloat16,
-                          device=x.device)
+        shape = tuple(x.shape[:-1]) + (oc,)
+        if up2:     # fused nearest x2 up-sampling: [B,H,W,C] -> [B,2H,2W,Cout]
+            shape = (B, 2 * H, 2 * W, pw.n // 4)
+        out = torch.empty(shape, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
     assert out.is_contiguous()
     d = capi.GemmDesc()
     d.x = x.data_ptr(); d.B, d.H, d.W = B, H, W
@@ -136,6 +163,7 @@ def conv_gemm(x, pw, *, x_coff=0, out=None, y_coff=0, out_channels=None, out_f32
         d.y_raw = y_raw.data_ptr(); d.yraw_cstride = y_raw.shape[-1]; d.yraw_coff = 0
     d.store_n = store_n
     d.w_per_image = 1 if w_per_image else 0
+    d.upsample2 = 1 if up2 else 0
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

@@ -88,6 +88,10 @@ typedef struct gwd_gemm_desc {
   int32_t store_n;      /* channels stored (<= n_pad); pad channels written as 0 when store_n > n */
   int32_t w_per_image;  /* 1: w is [B][taps][n_pad][cin], image b of x uses w[b] (PointBasedPred correlation,
                            src/models/points/points_sample.py:272) */
+  int32_t upsample2;    /* 1: `upconv` (src/models/dense_upsample.py:82-90): the 3x3 conv acts on the nearest x2 up-sampled
+                           input WITHOUT materialising it.  w holds 4 phase filters stacked along N (n = 4*Cout, phase
+                           2*oy+ox): output pixel (2y+oy, 2x+ox) of the [B,2H,2W,y_cstride] output takes channels
+                           [phase*Cout, (phase+1)*Cout).  A LayerNorm epilogue then normalises each phase group. */
 } gwd_gemm_desc;
 
 int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream);

@@ -129,3 +129,25 @@ def test_channel_slices_and_f32_out():
     got = buf.float().cpu()
     assert (got[..., 16:32] - acc2).abs().max().item() < 3e-2
     assert (got[..., :16] == 0).all() and (got[..., 32:] == 0).all()
+
+
+@pytest.mark.parametrize("C,N,use_ln", [(64, 64, True), (64, 32, False), (32, 16, False)])
+def test_fused_upsample_conv(C, N, use_ln):
+    """`upconv`: nearest x2 + 3x3 conv (+ELU, + per-pixel LayerNorm) computed on the low-resolution input"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(C + N)
+    B, H, W = 2, 13, 18
+    x = _rand((B, H, W, C), g).bfloat16()
+    w = _rand((N, C, 3, 3), g, (9 * C) ** -0.5).bfloat16()
+    ln = (1 + 0.1 * _rand((N,), g), 0.1 * _rand((N,), g)) if use_ln else None
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    ref = F.elu(F.conv2d(up, w.float(), None, 1, 1)).permute(0, 2, 3, 1)
+    if use_ln:
+        ref = F.layer_norm(ref, (N,), ln[0], ln[1], 1e-5)
+    pw = ops.pack_upconv3x3(w.cuda())
+    lnp = (ln[0].cuda().contiguous(), ln[1].cuda().contiguous()) if use_ln else None
+    y = ops.conv_gemm(x.cuda(), pw, bias=False, ln=lnp, pre_act=3 if use_ln else 0, post_act=0 if use_ln else 3)
+    torch.cuda.synchronize()
+    assert y.shape == (B, 2 * H, 2 * W, N)
+    err = (y.float().cpu() - ref).abs().max().item()
+    assert err < 3e-2 * max(1.0, ref.abs().max().item()), err     # phase filters are sums of bf16 taps, re-rounded to bf16

@@ -20,6 +20,9 @@ CASES = {
     "head32_32_elu": (16, 480, 640, 32, 32, 9, False, 3),
     "ffn_256_2048": (1, 1, 4800, 256, 2048, 1, False, 1),
     "ffn_2048_256_ln": (1, 1, 4800, 2048, 256, 1, True, 0),
+    "bb_64_256_relu": (1, 1, 307200, 64, 256, 1, False, 1),
+    "bb_256_64_relu": (1, 1, 307200, 256, 64, 1, False, 1),
+    "bb_512_128": (1, 1, 76800, 512, 128, 1, False, 1),
     "lin64_192": (1, 1, 16 * 414 * 49, 64, 192, 1, False, 0),
     "lin192_384": (1, 1, 16 * 414 * 49, 192, 384, 1, False, 0),
 }
