@@ -35,6 +35,11 @@ struct TcAttnParams {
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
@@ -136,7 +141,7 @@ gwd_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   const uint32_t tmem_o = tmem_base + Lk_pad;   // O accumulator after the S columns
 
   if (warp == 4) {
-    if (lane == 0) {
+    if (elect_one()) {
       // ---- loads
       const uint32_t bytes = kQTile * 64 + 2u * Lk_pad * 64;
       mbar_expect_tx(ld_bar, bytes);

@@ -18,6 +18,7 @@
 //
 // Reference call sites replaced: see include/gwd_b200.h (gwd_conv_gemm).
 #include <cuda.h>
+#include <stdlib.h>
 #include "gwd_common.cuh"
 
 namespace {
@@ -68,6 +69,11 @@ struct GemmParams {
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -296,7 +302,7 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       if (p.resident) {  // small filters: fetch every weight once, they stay in shared memory for all tiles of this CTA
@@ -325,7 +331,9 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    // elect.sync (not `lane == 0`): ptxas then knows exactly one thread runs this region and keeps the descriptors on
+    // the uniform datapath; with a lane test every tcgen05.mma was wrapped in an R2UR waterfall loop (~100 clk each)
+    if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
