@@ -23,8 +23,8 @@
 
 namespace {
 
-constexpr int kNumEpilogueWarps = 8;
-constexpr int kNumThreads = (2 + kNumEpilogueWarps) * 32;
+constexpr int kMaxEpilogueWarps = 16;   // 8 (two column groups) or 16 (four column groups) epilogue warps per CTA
+constexpr int kNumThreads = (2 + kMaxEpilogueWarps) * 32;
 constexpr int kMaxStages = 8;
 constexpr int kTileM = 128;
 
@@ -277,7 +277,7 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], kNumEpilogueWarps);
+      mbar_init(&tmem_empty[a], (blockDim.x >> 5) - 2);
     }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -377,11 +377,12 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // ===================================== epilogue =========================================
     const int ew = warp - 2;
     const int quad = warp & 3;   // TMEM lane quarter this warp may touch
-    const int half = ew >> 2;    // which half of the tile's columns this warp stores
+    const int ngrp = ((blockDim.x >> 5) - 2) >> 2;   // column groups: 4 warps (one per TMEM lane quarter) each
+    const int half = ew >> 2;    // which column group of the tile this warp stores
     const int row = quad * 32 + lane;
     const int nchunks = p.Nt / 16;
-    const int c_begin = half == 0 ? 0 : (nchunks + 1) / 2;
-    const int c_end = half == 0 ? (nchunks + 1) / 2 : nchunks;
+    const int c_begin = (nchunks * half + ngrp - 1) / ngrp;
+    const int c_end = (nchunks * (half + 1) + ngrp - 1) / ngrp;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -404,8 +405,8 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // one group per output phase): each half owns whole groups.
       const int groups = HAS_LN ? p.ln_groups : 1;
       const int cpg = nchunks / groups;
-      const int seg_first = groups > 1 ? half * (groups / 2) : 0;
-      const int seg_last = groups > 1 ? (half + 1) * (groups / 2) : 1;
+      const int seg_first = groups > 1 ? half * (groups / ngrp) : 0;
+      const int seg_last = groups > 1 ? (half + 1) * (groups / ngrp) : 1;
       const int n_group = p.n / groups;
       for (int seg = seg_first; seg < seg_last; ++seg) {
         const int st_begin = groups > 1 ? seg * cpg : 0;
@@ -497,7 +498,7 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           }
         }
       }
-      // release the accumulator
+      // release the accumulator (all TMEM reads of this tile are done)
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -623,6 +624,15 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   p.BK = (d->cin % 64 == 0) ? 64 : (d->cin % 32 == 0) ? 32 : 16;
   const int a_rows = box_w * box_h;
   auto round1k = [](uint32_t v) { return (v + 1023u) & ~1023u; };
+  // epilogue width: LayerNorm epilogues read the whole row per column group (keep 2 groups); plain epilogues are
+  // latency bound per warp, so wide tiles get 4 column groups (16 warps)
+  static const int forced_warps = []() { const char* e = getenv("GWD_GEMM_EPI_WARPS"); return e ? atoi(e) : 0; }();
+  const bool has_ln = d->ln_g != nullptr;
+  int epi_warps = (!has_ln && p.Nt >= 64) ? 16 : 8;
+  if (forced_warps == 8 || (forced_warps == 16 && !has_ln && p.Nt >= 64)) epi_warps = forced_warps;
+  const int threads = (2 + epi_warps) * 32;
+  // (staging the bf16 tile in shared memory for row-contiguous stores was measured: -13% on 192-column Linears, but
+  // +20..40% on narrow / LayerNorm tiles and -2% on the whole step, so stores stay thread-per-row)
   const uint32_t budget = 200 * 1024;
   uint32_t w_region = 0;
   if (p.resident) {
@@ -720,12 +730,12 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
     }
   }
 
-  const size_t smem_bytes = 1024 + static_cast<size_t>(p.stages) * (p.a_stage_bytes + p.b_stage_bytes) + w_region +
-                            (2 * kMaxStages + 5) * sizeof(uint64_t) + 16 + 72 * sizeof(uint32_t);
+  const size_t ring_bytes = static_cast<size_t>(p.stages) * (p.a_stage_bytes + p.b_stage_bytes) + w_region;
+  const size_t bar_bytes = ((2 * kMaxStages + 5) * sizeof(uint64_t) + 16 + 72 * sizeof(uint32_t) + 127) & ~size_t(127);
+  const size_t smem_bytes = 1024 + ring_bytes + bar_bytes;
   const int total_tiles = p.m_tiles * p.n_tiles;
   int grid = gwd_num_sms();
   if (grid > total_tiles) grid = total_tiles;
-  const bool has_ln = d->ln_g != nullptr;
 #define GWD_GEMM_CASE(PRE, POST, LN)                                                                          \
   if (d->pre_act == PRE && d->post_act == POST && has_ln == LN) {                                             \
     static bool attr_set = false;                                                                             \
@@ -734,7 +744,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
                                     227 * 1024));                                                             \
       attr_set = true;                                                                                        \
     }                                                                                                         \
-    gwd_tapgemm_kernel<PRE, POST, LN><<<grid, kNumThreads, smem_bytes, stream>>>(map_a, map_b, p);            \
+    gwd_tapgemm_kernel<PRE, POST, LN><<<grid, threads, smem_bytes, stream>>>(map_a, map_b, p);                \
     launched = true;                                                                                          \
   }
   bool launched = false;
