@@ -26,6 +26,7 @@ namespace {
 constexpr int kMaxEpilogueWarps = 16;   // 8 (two column groups) or 16 (four column groups) epilogue warps per CTA
 constexpr int kNumThreads = (2 + kMaxEpilogueWarps) * 32;
 constexpr int kMaxStages = 8;
+constexpr int kMaxAcc = 8;
 constexpr int kTileM = 128;
 
 struct GemmParams {
@@ -40,13 +41,16 @@ struct GemmParams {
   uint32_t a_stage_bytes, b_stage_bytes;  // 1024-aligned slot sizes
   uint32_t a_tx_bytes, b_tx_bytes;        // bytes TMA actually delivers per stage
   uint32_t a_off[9], b_off[9];            // byte offsets of the A / B operand of every MMA sub-step inside a stage
+  uint32_t a_tab[36], b_tab[36];          // descriptor start-address increments (16-byte units) of every MMA of a stage
   int resident;                           // 1: all weights live in shared memory for the whole kernel
   uint32_t w_kc_bytes, w_total_bytes;     // resident weights: bytes per channel chunk / in total
   uint32_t layout_type;                   // UMMA smem descriptor layout: 2=SW128 4=SW64 6=SW32
   uint32_t sbo_a, sbo_b;                  // byte stride between 8-row groups of the A / B operand
   uint32_t idesc;
-  uint32_t acc_stride;                    // TMEM columns between the two accumulators
+  uint32_t acc_stride;                    // TMEM columns between consecutive accumulators
   uint32_t tmem_cols;
+  int nacc;                               // TMEM accumulators in flight (2, 4 or 8; power of two)
+  int tile_split;   // 1: each 4-warp epilogue group drains whole tiles (tile j -> group j % groups); 0: groups split columns
   int n, n_pad, store_n;
   const float* bias;
   const float* ln_g;
@@ -130,6 +134,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+template <int N, typename P>
+__device__ __forceinline__ void issue_mmas(const P& p, uint32_t d_tmem, uint64_t adesc0, uint64_t bdesc0,
+                                           uint32_t accumulate) {
+#pragma unroll
+  for (int i = 0; i < N; ++i) umma_bf16(d_tmem, adesc0 + p.a_tab[i], bdesc0 + p.b_tab[i], p.idesc, i > 0 ? 1u : accumulate);
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -260,11 +270,10 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       smem_b + (p.resident ? ((p.w_total_bytes + 1023u) & ~1023u) : static_cast<size_t>(p.stages) * p.b_stage_bytes));
   uint64_t* full_bar = bars;                      // [stages]
   uint64_t* empty_bar = bars + kMaxStages;        // [stages]
-  uint64_t* tmem_full = bars + 2 * kMaxStages;    // [2]
-  uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;  // [2]
-  uint64_t* w_bar = bars + 2 * kMaxStages + 4;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
-  uint32_t* mma_tab = tmem_ptr + 4;   // [2][36] descriptor start-address increments (16-byte units) per MMA sub-step
+  uint64_t* tmem_full = bars + 2 * kMaxStages;              // [nacc]
+  uint64_t* tmem_empty = bars + 2 * kMaxStages + kMaxAcc;   // [nacc]
+  uint64_t* w_bar = bars + 2 * kMaxStages + 2 * kMaxAcc;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAcc + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -275,9 +284,9 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < p.nacc; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], (blockDim.x >> 5) - 2);
+      mbar_init(&tmem_empty[a], p.tile_split ? 4 : (blockDim.x >> 5) - 2);
     }
     mbar_init(w_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -285,11 +294,6 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
   if (warp == 1) {
-    const int ks = p.BK / 16;
-    for (int i = lane; i < p.nsub * ks; i += 32) {
-      mma_tab[i] = (p.a_off[i / ks] + (i % ks) * 32) >> 4;
-      mma_tab[36 + i] = (p.b_off[i / ks] + (i % ks) * 32) >> 4;
-    }
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
                  "r"(p.tmem_cols)
                  : "memory");
@@ -348,20 +352,36 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * p.acc_stride;
         uint32_t accumulate = 0;
+        int kc = 0, dx = 0;
         for (int it = 0; it < p.kchunks * p.ndx; ++it) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
           const uint32_t a_base = smem_u32(smem_a + static_cast<size_t>(stage) * p.a_stage_bytes);
-          const uint32_t b_base = p.resident ? smem_u32(smem_b + static_cast<size_t>(it / p.ndx) * p.w_kc_bytes)
-                                             : smem_u32(smem_b + static_cast<size_t>(stage) * p.b_stage_bytes);
+          const uint32_t b_base = p.resident ? smem_u32(smem_b) + static_cast<uint32_t>(kc) * p.w_kc_bytes
+                                             : smem_u32(smem_b) + static_cast<uint32_t>(stage) * p.b_stage_bytes;
+          if (++dx == p.ndx) {
+            dx = 0;
+            ++kc;
+          }
           // the single issuing thread is the critical path of small tiles: descriptors are one add per operand
           const uint64_t adesc0 = make_smem_desc(a_base, p.sbo_a, p.layout_type);
           const uint64_t bdesc0 = make_smem_desc(b_base, p.sbo_b, p.layout_type);
-#pragma unroll 4
-          for (int i = 0; i < nmma; ++i) {
-            umma_bf16(d_tmem, adesc0 + mma_tab[i], bdesc0 + mma_tab[36 + i], p.idesc, accumulate);
-            accumulate = 1;
+          // fully unrolled with constant indices: every table entry is a constant-bank operand that goes straight to
+          // the uniform datapath (a table in shared memory cost a generic load + R2UR pair per MMA on this one thread,
+          // which is the critical path of small-K tiles)
+          // and branch-free: a branch between two MMAs makes ptxas re-materialise every uniform register
+          switch (nmma) {
+            case 1: issue_mmas<1>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 2: issue_mmas<2>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 3: issue_mmas<3>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 4: issue_mmas<4>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 6: issue_mmas<6>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 9: issue_mmas<9>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 12: issue_mmas<12>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 18: issue_mmas<18>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            default: issue_mmas<36>(p, d_tmem, adesc0, bdesc0, accumulate); break;
           }
+          accumulate = 1;
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == p.stages) {
             stage = 0;
@@ -369,23 +389,32 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           }
         }
         umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1u;
+        if (++acc == p.nacc) {
+          acc = 0;
+          acc_phase ^= 1u;
+        }
       }
     }
   } else {
     // ===================================== epilogue =========================================
     const int ew = warp - 2;
     const int quad = warp & 3;   // TMEM lane quarter this warp may touch
-    const int ngrp = ((blockDim.x >> 5) - 2) >> 2;   // column groups: 4 warps (one per TMEM lane quarter) each
-    const int half = ew >> 2;    // which column group of the tile this warp stores
+    // 4 warps (one per TMEM lane quarter) form a group.  Column split: the groups share every tile, each storing its
+    // own column range.  Tile split: group g drains tiles g, g + groups, ... of this CTA on its own accumulators, so
+    // several tiles' epilogues (TMEM load -> math -> store latency chains) are in flight at once.
+    const int wgroups = ((blockDim.x >> 5) - 2) >> 2;
+    const int ngrp = p.tile_split ? 1 : wgroups;       // column groups
+    const int half = p.tile_split ? 0 : ew >> 2;       // which column group of the tile this warp stores
+    const int j_step = p.tile_split ? wgroups : 1;     // CTA-local tile counter stride
+    const int acc_mask = p.nacc - 1, acc_shift = 31 - __clz(p.nacc);
     const int row = quad * 32 + lane;
     const int nchunks = p.Nt / 16;
     const int c_begin = (nchunks * half + ngrp - 1) / ngrp;
     const int c_end = (nchunks * (half + 1) + ngrp - 1) / ngrp;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int j = p.tile_split ? ew >> 2 : 0;
+    for (int tile = blockIdx.x + j * gridDim.x; tile < total_tiles; tile += j_step * gridDim.x, j += j_step) {
+      const int acc = j & acc_mask;
+      const uint32_t acc_phase = (j >> acc_shift) & 1;
       TileCoord t = decode_tile(p, tile);
       RowCtx rc;
       {
@@ -502,8 +531,6 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1u;
     }
   }
 
@@ -624,16 +651,23 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   p.BK = (d->cin % 64 == 0) ? 64 : (d->cin % 32 == 0) ? 32 : 16;
   const int a_rows = box_w * box_h;
   auto round1k = [](uint32_t v) { return (v + 1023u) & ~1023u; };
-  // epilogue width: LayerNorm epilogues read the whole row per column group (keep 2 groups); plain epilogues are
-  // latency bound per warp, so wide tiles get 4 column groups (16 warps)
-  static const int forced_warps = []() { const char* e = getenv("GWD_GEMM_EPI_WARPS"); return e ? atoi(e) : 0; }();
-  const bool has_ln = d->ln_g != nullptr;
-  int epi_warps = (!has_ln && p.Nt >= 64) ? 16 : 8;
-  if (forced_warps == 8 || (forced_warps == 16 && !has_ln && p.Nt >= 64)) epi_warps = forced_warps;
-  const int threads = (2 + epi_warps) * 32;
-  // (staging the bf16 tile in shared memory for row-contiguous stores was measured: -13% on 192-column Linears, but
-  // +20..40% on narrow / LayerNorm tiles and -2% on the whole step, so stores stay thread-per-row)
-  const uint32_t budget = 200 * 1024;
+  // Two co-resident CTAs per SM for small filters: the producer thread, the MMA-issuing thread and each epilogue warp
+  // are serial latency chains (about 0.4-0.9 us per tile each), so a second independent CTA on the SM nearly doubles
+  // the tile rate of the small-K convolutions whose tiles carry little tensor work.  Needs: resident weights, half the
+  // shared memory, at most 256 TMEM columns, 8 epilogue warps (96 registers x 320 threads x 2 fits the register file).
+  static const int forced_ctas = []() { const char* e = getenv("GWD_GEMM_CTAS"); return e ? atoi(e) : 0; }();
+  int ctas = 1;
+  if (p.resident && forced_ctas != 1 && pow2_at_least(static_cast<uint32_t>(p.Nt), 32) <= 128 &&
+      p.m_tiles >= 4 * gwd_num_sms()) {
+    // at least three ring slots per CTA; a 64-channel chunk may be halved to get there
+    for (int bk = p.BK; bk >= 32 && ctas == 1; bk >>= 1) {
+      if (round1k(static_cast<uint32_t>(w_bytes)) + 3 * round1k(static_cast<uint32_t>(a_rows) * bk * 2) <= 104 * 1024) {
+        ctas = 2;
+        p.BK = bk;
+      }
+    }
+  }
+  const uint32_t budget = ctas == 2 ? 104 * 1024 : 200 * 1024;
   uint32_t w_region = 0;
   if (p.resident) {
     p.a_tx_bytes = static_cast<uint32_t>(a_rows) * p.BK * 2;
@@ -672,11 +706,47 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
     }
     p.b_off[sub] = static_cast<uint32_t>(sub) * p.Nt * row_bytes;
   }
+  {
+    const int ks = p.BK / 16;
+    for (int i = 0; i < p.nsub * ks; ++i) {
+      p.a_tab[i] = (p.a_off[i / ks] + (i % ks) * 32) >> 4;
+      p.b_tab[i] = (p.b_off[i / ks] + (i % ks) * 32) >> 4;
+    }
+  }
   // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 @17, M>>4 @24
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.Nt >> 3) << 17) |
             (static_cast<uint32_t>(kTileM >> 4) << 24);
-  p.acc_stride = (static_cast<uint32_t>(p.Nt) + 31u) & ~31u;
-  p.tmem_cols = pow2_at_least(2 * p.acc_stride, 32);
+  // Epilogue organisation.  Column split (the 4-warp groups share each tile): lowest latency for one tile, right for
+  // wide plain tiles and for launches with about one tile per CTA.  Tile split (each group drains whole tiles on its
+  // own TMEM accumulators): narrow tiles (no columns to share) and LayerNorm epilogues (whose statistics pass would be
+  // repeated by every column group) when the CTA has a queue of tiles to overlap.
+  // (staging the bf16 tile in shared memory for row-contiguous stores was measured: -13% on 192-column Linears, but
+  // +20..40% on narrow / LayerNorm tiles and -2% on the whole step, so stores stay thread-per-row)
+  static const int forced_warps = []() { const char* e = getenv("GWD_GEMM_EPI_WARPS"); return e ? atoi(e) : 0; }();
+  static const int forced_split = []() { const char* e = getenv("GWD_GEMM_TILE_SPLIT"); return e ? atoi(e) : -1; }();
+  const bool has_ln = d->ln_g != nullptr;
+  const int64_t tiles_all = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
+  p.acc_stride = pow2_at_least(static_cast<uint32_t>(p.Nt), 32);
+  const int acc_fit = static_cast<int>(512u / p.acc_stride);   // accumulators that fit the 512 TMEM columns
+  p.tile_split = (has_ln || p.Nt < 64) && tiles_all >= 3 * static_cast<int64_t>(gwd_num_sms()) ? 1 : 0;
+  if (forced_split >= 0) p.tile_split = forced_split;
+  int epi_warps;
+  if (ctas == 2) {
+    const int fit = static_cast<int>(256u / p.acc_stride);
+    p.nacc = fit >= 4 ? 4 : 2;
+    epi_warps = 8;
+    p.tile_split = forced_split >= 0 ? forced_split : ((has_ln || p.Nt < 64) ? 1 : 0);
+  } else if (p.tile_split) {
+    p.nacc = acc_fit >= 8 ? 8 : acc_fit >= 4 ? 4 : 2;
+    epi_warps = p.nacc >= 4 ? 16 : 8;
+    if (forced_warps == 8) epi_warps = 8;
+  } else {
+    p.nacc = 2;
+    epi_warps = (!has_ln && p.Nt >= 64) ? 16 : 8;
+    if (forced_warps == 8 || (forced_warps == 16 && !has_ln && p.Nt >= 64)) epi_warps = forced_warps;
+  }
+  p.tmem_cols = pow2_at_least(static_cast<uint32_t>(p.nacc) * p.acc_stride, 32);
+  const int threads = (2 + epi_warps) * 32;
   p.x_coff = d->x_coff;
   p.w_img_stride = d->w_per_image ? d->taps : 0;
   p.n = d->n; p.n_pad = d->n_pad; p.store_n = store_n;
@@ -731,10 +801,11 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   }
 
   const size_t ring_bytes = static_cast<size_t>(p.stages) * (p.a_stage_bytes + p.b_stage_bytes) + w_region;
-  const size_t bar_bytes = ((2 * kMaxStages + 5) * sizeof(uint64_t) + 16 + 72 * sizeof(uint32_t) + 127) & ~size_t(127);
+  const size_t bar_bytes =
+      ((2 * kMaxStages + 2 * kMaxAcc + 1) * sizeof(uint64_t) + 16 + 127) & ~size_t(127);
   const size_t smem_bytes = 1024 + ring_bytes + bar_bytes;
   const int total_tiles = p.m_tiles * p.n_tiles;
-  int grid = gwd_num_sms();
+  int grid = ctas * gwd_num_sms();
   if (grid > total_tiles) grid = total_tiles;
 #define GWD_GEMM_CASE(PRE, POST, LN)                                                                          \
   if (d->pre_act == PRE && d->post_act == POST && has_ln == LN) {                                             \

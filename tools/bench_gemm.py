@@ -18,6 +18,8 @@ CASES = {
     "head64_64_elu": (16, 240, 320, 64, 64, 9, False, 3),
     "head64_32_elu": (16, 480, 640, 64, 32, 9, False, 3),
     "head32_32_elu": (16, 480, 640, 32, 32, 9, False, 3),
+    "head32_1_sigmoid": (16, 480, 640, 32, 1, 9, False, 4),
+    "head64_64_ln": (16, 240, 320, 64, 64, 9, True, 0),
     "ffn_256_2048": (1, 1, 4800, 256, 2048, 1, False, 1),
     "ffn_2048_256_ln": (1, 1, 4800, 2048, 256, 1, True, 0),
     "bb_64_256_relu": (1, 1, 307200, 64, 256, 1, False, 1),
@@ -50,7 +52,7 @@ def run(name):
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     flop = 2.0 * B * H * W * C * N * taps
-    print("%-18s %8.1f us  %7.1f TFLOP/s" % (name, ms * 1000, flop / ms / 1e9))
+    print("%-18s %8.1f us  %7.1f TFLOP/s" % (name, ms * 1000, flop / ms / 1e9), "%6.0f GB/s" % ((xs[0].numel() + out.numel()) * 2 / ms / 1e6))
 
 
 if __name__ == "__main__":
