@@ -275,6 +275,8 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* w_bar = bars + 2 * kMaxStages + 2 * kMaxAcc;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAcc + 1);
 
+  float2* ln_stats = reinterpret_cast<float2*>(tmem_ptr + 4);   // [2][4 column groups][128 rows] partial (sum, sum of squares)
+
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
@@ -444,8 +446,11 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         const int my_end = groups > 1 ? st_end : c_end;
         float mean = 0.f, rstd = 1.f;
         if (HAS_LN) {
+          // whole-row LayerNorm under column split: every group sums its own columns, the partial sums of a row meet
+          // in shared memory (one named barrier per TMEM lane quarter), so no group re-reads the whole row
+          const bool exchange = groups == 1 && ngrp > 1;
           float s = 0.f, ss = 0.f;
-          for (int c = st_begin; c < st_end; ++c) {
+          for (int c = exchange ? my_begin : st_begin; c < (exchange ? my_end : st_end); ++c) {
             float v[16];
             load_chunk<PRE_ACT>(p, t_row + c * 16, t.n0 + c * 16, rc, v);
 #pragma unroll
@@ -454,6 +459,18 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
                 s += v[i];
                 ss += v[i] * v[i];
               }
+            }
+          }
+          if (exchange) {
+            float2* slot = ln_stats + (j & 1) * 512 + row;   // double buffered by tile parity
+            slot[half * 128] = make_float2(s, ss);
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + quad), "r"(ngrp * 32) : "memory");
+            s = 0.f;
+            ss = 0.f;
+            for (int g = 0; g < ngrp; ++g) {
+              const float2 part = slot[g * 128];
+              s += part.x;
+              ss += part.y;
             }
           }
           mean = s / static_cast<float>(n_group);
@@ -728,7 +745,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   const int64_t tiles_all = static_cast<int64_t>(p.m_tiles) * p.n_tiles;
   p.acc_stride = pow2_at_least(static_cast<uint32_t>(p.Nt), 32);
   const int acc_fit = static_cast<int>(512u / p.acc_stride);   // accumulators that fit the 512 TMEM columns
-  p.tile_split = (has_ln || p.Nt < 64) && tiles_all >= 3 * static_cast<int64_t>(gwd_num_sms()) ? 1 : 0;
+  p.tile_split = ((has_ln && p.Nt <= 128) || p.Nt < 64) && tiles_all >= 3 * static_cast<int64_t>(gwd_num_sms()) ? 1 : 0;
   if (forced_split >= 0) p.tile_split = forced_split;
   int epi_warps;
   if (ctas == 2) {
@@ -742,8 +759,8 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
     if (forced_warps == 8) epi_warps = 8;
   } else {
     p.nacc = 2;
-    epi_warps = (!has_ln && p.Nt >= 64) ? 16 : 8;
-    if (forced_warps == 8 || (forced_warps == 16 && !has_ln && p.Nt >= 64)) epi_warps = forced_warps;
+    epi_warps = p.Nt >= 64 ? 16 : 8;
+    if (forced_warps == 8 || (forced_warps == 16 && epi_warps == 16)) epi_warps = forced_warps;
   }
   p.tmem_cols = pow2_at_least(static_cast<uint32_t>(p.nacc) * p.acc_stride, 32);
   const int threads = (2 + epi_warps) * 32;
@@ -802,7 +819,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
 
   const size_t ring_bytes = static_cast<size_t>(p.stages) * (p.a_stage_bytes + p.b_stage_bytes) + w_region;
   const size_t bar_bytes =
-      ((2 * kMaxStages + 2 * kMaxAcc + 1) * sizeof(uint64_t) + 16 + 127) & ~size_t(127);
+      ((2 * kMaxStages + 2 * kMaxAcc + 1) * sizeof(uint64_t) + 16 + (has_ln ? 2 * 4 * 128 * sizeof(float2) : 0) + 127) & ~size_t(127);
   const size_t smem_bytes = 1024 + ring_bytes + bar_bytes;
   const int total_tiles = p.m_tiles * p.n_tiles;
   int grid = ctas * gwd_num_sms();
