@@ -397,7 +397,8 @@ __global__ void __launch_bounds__(128) gwd_ref_requery_kernel(const float* __res
 // ---------------------------------------------------------------------------------------------------
 // C ABI
 // ---------------------------------------------------------------------------------------------------
-int gwd_attention_tc_try(const gwd_attn_desc* d, cudaStream_t stream);   // gwd_attn_tc.cu (tcgen05 path)
+int gwd_attention_tc_try(const gwd_attn_desc* d, cudaStream_t stream);       // gwd_attn_tc.cu (tcgen05 path)
+int gwd_attention_window_try(const gwd_attn_desc* d, cudaStream_t stream);   // gwd_attn_win.cu (biased windows)
 
 extern "C" int gwd_attention(const gwd_attn_desc* d, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -412,6 +413,13 @@ extern "C" int gwd_attention(const gwd_attn_desc* d, void* stream_) {
     if (tc_enabled) {
       int rc = gwd_attention_tc_try(d, stream);
       if (rc <= 0) return rc;   // 0 = launched, < 0 = error, 1 = not eligible
+    }
+  }
+  {  // biased (shifted-)window attention, N <= 64 tokens: persistent-CTA kernel with the bias table in shared memory
+    static const bool win_enabled = []() { const char* e = getenv("GWD_ATTN_WINDOW"); return !(e && e[0] == '0'); }();
+    if (win_enabled) {
+      int rc = gwd_attention_window_try(d, stream);
+      if (rc <= 0) return rc;
     }
   }
   AttnParams p;
