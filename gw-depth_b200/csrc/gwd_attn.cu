@@ -399,6 +399,9 @@ __global__ void __launch_bounds__(128) gwd_ref_requery_kernel(const float* __res
 // ---------------------------------------------------------------------------------------------------
 int gwd_attention_tc_try(const gwd_attn_desc* d, cudaStream_t stream);       // gwd_attn_tc.cu (tcgen05 path)
 int gwd_attention_window_try(const gwd_attn_desc* d, cudaStream_t stream);   // gwd_attn_win.cu (biased windows)
+int gwd_token_attention_mma_try(const void* dq, const void* sq, const void* tk, const void* tv, void* dout, void* sout,
+                                int items, int N, int heads, int td, int tc, int64_t q_rs, int64_t k_rs, int64_t v_rs,
+                                int64_t o_rs, float scale, cudaStream_t stream);   // gwd_attn_win.cu (mma.sync path)
 
 extern "C" int gwd_attention(const gwd_attn_desc* d, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -449,6 +452,14 @@ extern "C" int gwd_token_attention(const void* dq, const void* sq, const void* t
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GWD_CHECK_ARG(dq && sq && tk && tv && dout && sout, "gwd_token_attention: null pointer");
   GWD_CHECK_ARG(heads > 0 && heads <= 32 && td > 0 && tc > 0 && items > 0, "gwd_token_attention: bad shape");
+  {
+    static const bool mma_enabled = []() { const char* e = getenv("GWD_TOKEN_MMA"); return !(e && e[0] == '0'); }();
+    if (mma_enabled) {
+      int rc = gwd_token_attention_mma_try(dq, sq, tk, tv, dout, sout, items, N, heads, td, tc, q_rs, k_rs, v_rs, o_rs, scale,
+                                           stream);
+      if (rc <= 0) return rc;
+    }
+  }
   TokAttnParams p;
   p.dq = static_cast<const bf16*>(dq); p.sq = static_cast<const bf16*>(sq);
   p.tk = static_cast<const bf16*>(tk); p.tv = static_cast<const bf16*>(tv);

@@ -300,3 +300,197 @@ int gwd_attention_window_try(const gwd_attn_desc* d, cudaStream_t stream) {
     default: return 1;
   }
 }
+
+// =====================================================================================================================
+// class-token CHANNEL attention of WindowClassAttention (multiscale_transformerr.py:561-578) on mma.sync
+// =====================================================================================================================
+// Per window and head: A[r][c] = softmax_c(scale * sum_n tq[n][r] tk[n][c]) with r = (depth | seg) x 4 token channels and
+// c = tc key channels, then out[n][r] = sum_c A[r][c] tv[n][c].  Both products contract over an axis that is the ROW
+// axis of the row-major operands in shared memory, which is exactly what ldmatrix.trans delivers, so the window is
+// staged once (8-byte copies, each head's tc channels padded to a multiple of 8 so that every 8x8 block is 16-byte
+// aligned) and each warp runs two heads: 4 k-steps of m16n8k16 for the scores, a 12..24-wide soft-max on the
+// accumulator fragments, and one MMA per 16 tokens for the output, whose B operand is the soft-max result still in
+// registers.  The thread-per-output kernel in gwd_attn.cu (730 us on 6624 windows) stays as the generic fallback.
+namespace {
+
+struct TokMmaParams {
+  const bf16* dq; const bf16* sq; const bf16* tk; const bf16* tv;
+  bf16* dout; bf16* sout;
+  int items, N, heads, tc;
+  int64_t q_rs, k_rs, v_rs, o_rs;
+  float scale;
+};
+
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t& r0, uint32_t& r1, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0,%1}, [%2];" : "=r"(r0), "=r"(r1) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
+// NTC = 8-wide key-channel tiles per head (tc padded to 8 * NTC)
+template <int NTC>
+__global__ void __launch_bounds__(256, 2) gwd_token_attention_mma_kernel(const TokMmaParams p) {
+  extern __shared__ __align__(16) uint8_t smraw[];
+  constexpr int TCP = 8 * NTC;
+  const int N = p.N, heads = p.heads, tc = p.tc;
+  const int SQ = heads * 16 + 16;             // bytes per staged query row: [head][depth x4 | seg x4] + 16 pad
+  const int SK = heads * TCP * 2 + 16;        // bytes per staged key / value row: [head][TCP] + 16 pad
+  const int SO = 256 + 8;                     // bytes per staged output row: depth 64 | seg 64 (+ pad)
+  uint8_t* TQ = smraw;                        // [64][SQ]   rows >= N stay zero (they are the k padding of the scores)
+  uint8_t* TK = TQ + 64 * SQ;                 // [64][SK]
+  uint8_t* TV = TK + 64 * SK;                 // [64][SK] (+ 64 bytes slack)
+  uint8_t* OS = TV + 64 * SK + 64;            // [64][SO]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  {
+    const int words = (64 * SQ + 128 * SK + 64 + 64 * SO) >> 2;
+    for (int i = tid; i < words; i += 256) reinterpret_cast<uint32_t*>(smraw)[i] = 0u;
+  }
+  __syncthreads();
+  const int kp = tc >> 2;                     // 8-byte pieces per head in a key / value row
+  const int m_tiles = (N + 15) >> 4;
+  const float sc = p.scale * kLog2e;
+
+  for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    // ---- stage the window ----
+    const int64_t row0 = static_cast<int64_t>(item) * N;
+    for (int idx = tid; idx < N * heads; idx += 256) {          // queries: one 8-byte piece per (token, head, tensor)
+      const int n = idx / heads, h = idx - n * heads;
+      const uint2 d = __ldg(reinterpret_cast<const uint2*>(p.dq + (row0 + n) * p.q_rs) + h);
+      const uint2 s = __ldg(reinterpret_cast<const uint2*>(p.sq + (row0 + n) * p.q_rs) + h);
+      *reinterpret_cast<uint4*>(TQ + n * SQ + h * 16) = make_uint4(d.x, d.y, s.x, s.y);
+    }
+    const int kv_pieces = heads * kp;
+    for (int idx = tid; idx < N * kv_pieces; idx += 256) {
+      const int n = idx / kv_pieces, r = idx - n * kv_pieces;
+      const int h = r / kp, w = r - h * kp;
+      const uint2 k = __ldg(reinterpret_cast<const uint2*>(p.tk + (row0 + n) * p.k_rs) + r);
+      const uint2 v = __ldg(reinterpret_cast<const uint2*>(p.tv + (row0 + n) * p.v_rs) + r);
+      *reinterpret_cast<uint2*>(TK + n * SK + h * TCP * 2 + w * 8) = k;
+      *reinterpret_cast<uint2*>(TV + n * SK + h * TCP * 2 + w * 8) = v;
+    }
+    __syncthreads();
+
+    for (int h = warp; h < heads; h += 8) {
+      // ---- scores[r][c] = sum_n tq[n][r] tk[n][c]  (M = 8 real rows, N = TCP, K = 64 zero-padded tokens) ----
+      float s[NTC][4];
+      const uint32_t q_addr = smem_addr(TQ + (lane & 15) * SQ + h * 16);
+      const uint32_t k_addr = smem_addr(TK + (lane & 15) * SK + h * TCP * 2);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t a[4];
+        ldsm_x2_trans(a[0], a[2], q_addr + kk * 16 * SQ);
+        a[1] = 0u;
+        a[3] = 0u;
+#pragma unroll
+        for (int nt = 0; nt < NTC; ++nt) {
+          uint32_t b0, b1;
+          ldsm_x2_trans(b0, b1, k_addr + kk * 16 * SK + nt * 16);
+          if (kk == 0) mma_16816_first(s[nt], a, b0, b1);
+          else mma_16816(s[nt], a, b0, b1);
+        }
+      }
+      // ---- soft-max over the tc key channels of every row g (accumulator rows g + 8 are padding) ----
+      float mx = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < NTC; ++nt) {
+        const int c0 = 8 * nt + 2 * t;
+        s[nt][0] = c0 < tc ? s[nt][0] * sc : -INFINITY;
+        s[nt][1] = c0 + 1 < tc ? s[nt][1] * sc : -INFINITY;
+        mx = fmaxf(mx, fmaxf(s[nt][0], s[nt][1]));
+      }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      float l = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < NTC; ++nt) {
+        s[nt][0] = ex2_approx(s[nt][0] - mx);
+        s[nt][1] = ex2_approx(s[nt][1] - mx);
+        l += s[nt][0] + s[nt][1];
+      }
+      l += __shfl_xor_sync(0xffffffffu, l, 1);
+      l += __shfl_xor_sync(0xffffffffu, l, 2);
+      const float inv = rcp_approx(l);
+      uint32_t pb[4] = {0u, 0u, 0u, 0u};      // B fragments of the output product: B[k = c][col = r] = A[r][c]
+#pragma unroll
+      for (int nt = 0; nt < NTC; ++nt) pb[nt] = gwd_pack_bf16x2(s[nt][0] * inv, s[nt][1] * inv);
+      // ---- out[n][r] = sum_c tv[n][c] A[r][c]  (M = tokens, N = 8, K = TCP padded to 16 / 32) ----
+      const uint32_t v_addr = smem_addr(TV + (lane & 15) * SK + h * TCP * 2 + (lane >> 4) * 16);
+      for (int mt = 0; mt < m_tiles; ++mt) {
+        float o[4];
+        uint32_t a[4];
+        ldsm_x4(a, v_addr + mt * 16 * SK);
+        mma_16816_first(o, a, pb[0], pb[1]);
+        if (NTC > 2) {
+          ldsm_x4(a, v_addr + mt * 16 * SK + 32);
+          mma_16816(o, a, pb[2], pb[3]);
+        }
+        uint8_t* orow = OS + (16 * mt + g) * SO + (t >> 1) * 128 + h * 8 + (t & 1) * 4;
+        *reinterpret_cast<uint32_t*>(orow) = gwd_pack_bf16x2(o[0], o[1]);
+        *reinterpret_cast<uint32_t*>(orow + 8 * SO) = gwd_pack_bf16x2(o[2], o[3]);
+      }
+    }
+    __syncthreads();
+
+    // ---- rows leave as 16-byte pieces: depth 64 channels | seg 64 channels ----
+    const int ppr = heads >> 1;                // 16-byte pieces per tensor row (heads * 4 channels * 2 bytes / 16)
+    for (int idx = tid; idx < N * 2 * ppr; idx += 256) {
+      const int n = idx / (2 * ppr), r = idx - n * 2 * ppr;
+      const int which = r / ppr, w = r - which * ppr;
+      const uint2 lo = *reinterpret_cast<const uint2*>(OS + n * SO + which * 128 + w * 16);
+      const uint2 hi = *reinterpret_cast<const uint2*>(OS + n * SO + which * 128 + w * 16 + 8);
+      bf16* dst = (which == 0 ? p.dout : p.sout) + (row0 + n) * p.o_rs + w * 8;
+      *reinterpret_cast<uint4*>(dst) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+    }
+  }
+}
+
+template <int NTC>
+int launch_token_mma(const TokMmaParams& p, cudaStream_t stream) {
+  const size_t SQ = p.heads * 16 + 16, SK = static_cast<size_t>(p.heads) * 8 * NTC * 2 + 16, SO = 264;
+  const size_t smem = 64 * SQ + 128 * SK + 64 + 64 * SO;
+  static int occ = 0;
+  static size_t occ_smem = 0;
+  if (occ == 0 || occ_smem != smem) {
+    GWD_CUDA(cudaFuncSetAttribute(gwd_token_attention_mma_kernel<NTC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int nb = 0;
+    GWD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gwd_token_attention_mma_kernel<NTC>, 256, smem));
+    GWD_CHECK_ARG(nb > 0, "gwd_token_attention: window does not fit shared memory");
+    occ = nb; occ_smem = smem;
+  }
+  int grid = occ * gwd_num_sms();
+  if (grid > p.items) grid = p.items;
+  gwd_token_attention_mma_kernel<NTC><<<grid, 256, smem, stream>>>(p);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+}  // namespace
+
+// returns 0 = launched, < 0 = error, 1 = shape not covered (caller uses the generic kernel)
+int gwd_token_attention_mma_try(const void* dq, const void* sq, const void* tk, const void* tv, void* dout, void* sout,
+                                int items, int N, int heads, int td, int tc, int64_t q_rs, int64_t k_rs, int64_t v_rs,
+                                int64_t o_rs, float scale, cudaStream_t stream) {
+  if (td != 4 || N > 64 || N < 1 || heads < 2 || heads > 16 || heads % 2 != 0 || tc % 4 != 0 || tc < 4 || tc > 32) return 1;
+  if (q_rs % 4 != 0 || k_rs % 4 != 0 || v_rs % 4 != 0 || o_rs % 8 != 0) return 1;
+  const uintptr_t align8 = reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(sq) | reinterpret_cast<uintptr_t>(tk) |
+                           reinterpret_cast<uintptr_t>(tv);
+  if ((align8 & 7) != 0 || ((reinterpret_cast<uintptr_t>(dout) | reinterpret_cast<uintptr_t>(sout)) & 15) != 0) return 1;
+  TokMmaParams p;
+  p.dq = static_cast<const bf16*>(dq); p.sq = static_cast<const bf16*>(sq);
+  p.tk = static_cast<const bf16*>(tk); p.tv = static_cast<const bf16*>(tv);
+  p.dout = static_cast<bf16*>(dout); p.sout = static_cast<bf16*>(sout);
+  p.items = items; p.N = N; p.heads = heads; p.tc = tc;
+  p.q_rs = q_rs; p.k_rs = k_rs; p.v_rs = v_rs; p.o_rs = o_rs; p.scale = scale;
+  const int ntc = (tc + 7) / 8;
+  switch (ntc) {
+    case 1: case 2: return launch_token_mma<2>(p, stream);
+    case 3: return launch_token_mma<3>(p, stream);
+    default: return launch_token_mma<4>(p, stream);
+  }
+}
