@@ -151,14 +151,17 @@ class GlassRGBD(_Node):
         return self._plan
 
     def forward(self, samples, reflc_points=None, reflc_mat=None, img_name=None, _pinned=None, _trace=None):
-        if isinstance(samples, (list, torch.Tensor)):
-            samples = nested_tensor_from_tensor_list(samples)
-        images, mask = samples.decompose()
-        assert mask is not None
+        if isinstance(samples, torch.Tensor) and samples.dim() == 4:
+            images, mask = samples, None      # one equal-size batch: no padding mask to build (or to synchronise on)
+        else:
+            if isinstance(samples, (list, torch.Tensor)):
+                samples = nested_tensor_from_tensor_list(samples)
+            images, mask = samples.decompose()
+            assert mask is not None
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError("backward kernels are not built yet: run the forward under torch.no_grad() / "
                                       "model.eval() (DESIGN.md, 'what comes next')")
-        if bool(mask.any()):
+        if mask is not None and bool(mask.any()):
             raise NotImplementedError("padded (ragged) batches are not built yet on the CUDA path; batch equal-size images")
         plan = self.plan()      # raises off-GPU: there is no CPU path
         with torch.cuda.device(images.device):
@@ -166,6 +169,65 @@ class GlassRGBD(_Node):
             if self.use_cuda_graph and _pinned is None and _trace is None:
                 return plan.forward_graphed(x)
             return plan.forward(x, pinned=_pinned, trace=_trace)
+
+
+    @torch.no_grad()
+    def infer_stream(self, host_batches, keys=("pred_logits", "pred_lines", "pred_depth", "pred_seg")):
+        """Serving loop over an iterable of PINNED host batches [B,3,H,W]: yields, per batch, a dict of pinned host
+        tensors (`pred_depth` = the full-resolution map).  Uploads, the forward and downloads run on three streams with
+        two buffers each, so the copy of batch i+1 and the read-back of batch i-1 overlap the forward of batch i.  A
+        yielded dict is valid until the next one is requested."""
+        plan = self.plan()
+        dev = plan.dev
+        comp = torch.cuda.current_stream(dev)
+        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        x_dev, out_dev, out_host = [None, None], [None, None], [None, None]
+        ev_in = [torch.cuda.Event() for _ in range(2)]
+        ev_used = [torch.cuda.Event() for _ in range(2)]
+        ev_out = [torch.cuda.Event() for _ in range(2)]
+        ev_done = [torch.cuda.Event() for _ in range(2)]
+        pending = []
+
+        def pick(out):
+            res = {}
+            for k in keys:
+                v = out[k]
+                res[k] = (v[-1] if k == "pred_depth" else v).contiguous()
+            return res
+
+        for i, hb in enumerate(host_batches):
+            b = i & 1
+            with torch.cuda.stream(s_in):
+                if x_dev[b] is None or x_dev[b].shape != hb.shape:
+                    x_dev[b] = torch.empty(hb.shape, dtype=torch.float32, device=dev)
+                elif i >= 2:
+                    s_in.wait_event(ev_used[b])          # the forward of batch i-2 has consumed this buffer
+                x_dev[b].copy_(hb, non_blocking=True)
+                ev_in[b].record(s_in)
+            comp.wait_event(ev_in[b])
+            out = pick(self.forward(x_dev[b]))
+            ev_used[b].record(comp)
+            if out_dev[b] is None:
+                out_dev[b] = {k: torch.empty_like(v) for k, v in out.items()}
+                out_host[b] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+            elif i >= 2:
+                comp.wait_event(ev_done[b])              # read-back of batch i-2 has left this buffer
+            for k, v in out.items():
+                out_dev[b][k].copy_(v, non_blocking=True)    # the graph's static outputs are reused by the next replay
+            ev_out[b].record(comp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_out[b])
+                for k, v in out_dev[b].items():
+                    out_host[b][k].copy_(v, non_blocking=True)
+                ev_done[b].record(s_out)
+            pending.append(b)
+            if len(pending) == 2:
+                pb = pending.pop(0)
+                ev_done[pb].synchronize()
+                yield out_host[pb]
+        for pb in pending:
+            ev_done[pb].synchronize()
+            yield out_host[pb]
 
 
 # --------------------------------------------------------------------------------------------------

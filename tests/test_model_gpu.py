@@ -171,3 +171,20 @@ def test_benchmark_size_properties():
     m, xm = rel(full["pred_depth"][3][5:6], solo["pred_depth"][3])
     assert m < TOL["depth_mean"], (m, xm)
     assert rel(full["pred_logits"][5:6], solo["pred_logits"])[1] < TOL["logits_max"]
+
+
+def test_infer_stream_matches_forward():
+    """the pipelined serving loop (three streams, double buffers) returns exactly what model(x) returns, batch by batch"""
+    net, _, _ = model()
+    batches = [synth.synth_batch(2, 224, 320, seed=300 + i)[0].pin_memory() for i in range(5)]
+    want = []
+    with torch.no_grad():
+        for hb in batches:
+            out = net(hb.cuda())
+            want.append({"pred_logits": out["pred_logits"].clone().cpu(), "pred_lines": out["pred_lines"].clone().cpu(),
+                         "pred_depth": out["pred_depth"][-1].clone().cpu(), "pred_seg": out["pred_seg"].clone().cpu()})
+    got = [{k: v.clone() for k, v in res.items()} for res in net.infer_stream(iter(batches))]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        for k in w:
+            assert torch.equal(g[k], w[k]), k

@@ -25,5 +25,10 @@ with torch.no_grad():
 recs, ops.PROFILE = ops.PROFILE, None
 rows = [(a.elapsed_time(b) * 1000, f, d) for a, b, f, d in recs]
 print("total %.1f us, %.1f TFLOP/s" % (sum(r[0] for r in rows), sum(r[1] for r in rows) / sum(r[0] for r in rows) / 1e6))
-for us, f, d in sorted(rows, key=lambda r: -r[0])[:45]:
-    print("%8.1f us %7.1f TFLOP/s  %s" % (us, f / us / 1e6, d))
+agg = {}
+for us, f, d in rows:
+    a = agg.setdefault(d, [0, 0.0, 0.0])
+    a[0] += 1; a[1] += us; a[2] += f
+print("grouped by shape:")
+for d, (n, us, f) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:60]:
+    print("%8.1f us x%-3d %7.1f us each %7.1f TFLOP/s  %s" % (us, n, us / n, f / us / 1e6, d))
