@@ -119,11 +119,14 @@ class Engine:
         return pack_linear(w.flatten(1), shift) if taps == 1 else pack_conv3x3(w, shift)
 
     def _pack_backbone(self):
-        """stem, max-pool and the six stride-2 convolutions stay on cuDNN; every 1x1 and stride-1 3x3 convolution of the
-        bottlenecks (46 of the 53 convolutions, ~90% of the backbone FLOPs) runs on gwd_conv_gemm with the folded
-        FrozenBN shift, the ReLU and the residual add fused in its epilogue."""
+        """The stem (7x7/2 conv + BN + ReLU + max-pool) is one gwd_stem_conv_pool launch; every 1x1 and stride-1 3x3
+        convolution of the bottlenecks (46 of the 53 convolutions, ~90% of the backbone FLOPs) runs on gwd_conv_gemm with
+        the folded FrozenBN shift, the ReLU and the residual add fused in its epilogue; the six stride-2 convolutions stay
+        on cuDNN."""
         p = "backbone.0.body."
-        self.stem = self._fold(p + "conv1", p + "bn1")
+        sd = self.sd
+        scale = sd[p + "bn1.weight"] * (sd[p + "bn1.running_var"] + 1e-5).rsqrt()
+        self.stem = ops.pack_stem(sd[p + "conv1.weight"] * scale.view(-1, 1, 1, 1), sd[p + "bn1.bias"] - sd[p + "bn1.running_mean"] * scale)
         self.blocks = []
         for li, nb in enumerate((3, 4, 6, 3), start=1):
             stage = []
@@ -142,9 +145,7 @@ class Engine:
     def backbone(self, images):
         """torchvision-style ResNet-50 C2..C5 with frozen batch-norm (src/models/backbone.py:19-92), bf16 channels-last.
         Returns [B,h,w,C] bf16 maps."""
-        x = images.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
-        x = F.relu_(F.conv2d(x, self.stem[0], self.stem[1], stride=2, padding=3))
-        x = F.max_pool2d(x, 3, 2, 1).permute(0, 2, 3, 1).contiguous()        # -> [B,h,w,64] channels-last buffer
+        x = ops.stem_conv_pool(images, *self.stem)                           # -> [B,h,w,64] channels-last buffer
         feats = []
         for stage in self.blocks:
             for blk in stage:

@@ -349,6 +349,27 @@ def nchw_to_nhwc(x, Cp):
     return out
 
 
+def pack_stem(w, shift):
+    """[64,3,7,7] BN-scaled stem filter -> bf16 [64,160] with column ky*22 + kx*3 + c (gwd_stem_conv_pool), fp32 shift"""
+    assert tuple(w.shape) == (64, 3, 7, 7)
+    packed = torch.zeros(64, 160, dtype=torch.float32, device=w.device)
+    wk = w.float().permute(0, 2, 3, 1).reshape(64, 7, 21)        # [n][ky][kx*3 + c]
+    packed[:, :154].view(64, 7, 22)[:, :, :21] = wk
+    return packed.to(torch.bfloat16).contiguous(), shift.float().contiguous()
+
+
+def stem_conv_pool(images, w_packed, bias):
+    """fp32 [B,3,H,W] -> bf16 [B,PH,PW,64]: conv 7x7/2 + BN shift + ReLU + max-pool 3x3/2 in one launch"""
+    assert images.dtype == torch.float32 and images.is_contiguous() and images.shape[1] == 3
+    B, _, H, W = images.shape
+    ch, cw = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    ph, pw = (ch - 1) // 2 + 1, (cw - 1) // 2 + 1
+    out = torch.empty(B, ph, pw, 64, dtype=torch.bfloat16, device=images.device)
+    capi.check(_L().gwd_stem_conv_pool(_ptr(images), _ptr(w_packed), _ptr(bias), _ptr(out), B, H, W, _stream()),
+               "gwd_stem_conv_pool")
+    return out
+
+
 # ------------------------------------------------------------------------------------------
 # selection / reduction kernels
 # ------------------------------------------------------------------------------------------

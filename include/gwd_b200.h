@@ -180,6 +180,13 @@ int gwd_line_ref_gather(const void* win, int64_t win_rs, const float* pos, const
 /* depth[p] = sum_k softmax_k(logits[p,:K]) anchor[b,k]  (points_sample.py:277-279) -> fp32 [B,HW] */
 int gwd_anchor_mix(const void* logits, int64_t l_rs, const float* anchor, int32_t B, int64_t HW, int32_t K, float* out,
                    void* stream);
+/* ResNet stem in one launch: 7x7/2 convolution (3 -> 64, padding 3) + folded FrozenBatchNorm shift + ReLU + 3x3/2
+ * max-pool (padding 1); replaces conv1/bn1/relu/maxpool of the torchvision body wrapped by src/models/backbone.py:58-92
+ * (FrozenBatchNorm2d :19-55).  images: fp32 [B,3,H,W]; w_packed: bf16 [64][160], column ky*22 + kx*3 + c holds the
+ * BN-scaled weight w[n][c][ky][kx] (other columns zero); bias: fp32 [64]; out: bf16 [B, PH, PW, 64] channels-last with
+ * PH = floor((floor((H-1)/2)+1 - 1)/2)+1 (the usual conv / pool output sizes). */
+int gwd_stem_conv_pool(const float* images, const void* w_packed, const float* bias, void* out, int32_t B, int32_t H,
+                       int32_t W, void* stream);
 /* fp32 NCHW image -> bf16 NHWC with Cp >= C channels (zero padded) */
 int gwd_nchw_to_nhwc(const float* x, int32_t B, int32_t C, int64_t HW, void* out, int32_t Cp, void* stream);
 

@@ -297,3 +297,22 @@ def test_depth_metrics_and_silog():
     loss = math.sqrt(s[2] / s[0] - 0.85 * (s[1] / s[0]) ** 2) * 10.0
     ref = float(oracle.depth_losses([p], d, weights=(1.0,))[0])
     assert abs(loss - ref) <= 1e-4 * abs(ref), (loss, ref)
+
+
+# ------------------------------------------------------------------------------------------ ResNet stem
+@pytest.mark.parametrize("B,H,W", [(2, 64, 96), (1, 480, 640), (2, 50, 70), (1, 33, 47)])
+def test_stem_conv_pool(B, H, W):
+    """7x7/2 conv + folded BN shift + ReLU + 3x3/2 max-pool in one launch vs torch (bf16-rounded operands, fp32 math);
+    sizes include tiles cut by the right / bottom border and odd extents"""
+    import torch.nn.functional as F
+    ops = _ops()
+    g = _g(H + W)
+    x = torch.randn(B, 3, H, W, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * 0.1
+    shift = torch.randn(64, generator=g) * 0.2
+    wp, bp = ops.pack_stem(w.cuda(), shift.cuda())
+    got = ops.stem_conv_pool(x.cuda().contiguous(), wp, bp)
+    conv = F.conv2d(_bf(x).float(), _bf(w).float(), shift, stride=2, padding=3)
+    ref = F.max_pool2d(_bf(F.relu(conv)).float(), 3, 2, 1).permute(0, 2, 3, 1)
+    assert tuple(got.shape) == tuple(ref.shape)
+    close(got, ref, 1e-2, "stem")
