@@ -453,11 +453,19 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           for (int c = exchange ? my_begin : st_begin; c < (exchange ? my_end : st_end); ++c) {
             float v[16];
             load_chunk<PRE_ACT>(p, t_row + c * 16, t.n0 + c * 16, rc, v);
+            if (groups > 1 || t.n0 + c * 16 + 16 <= p.n) {   // only the last chunk of a padded row needs the column test
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              if (groups > 1 || t.n0 + c * 16 + i < p.n) {
+              for (int i = 0; i < 16; ++i) {
                 s += v[i];
-                ss += v[i] * v[i];
+                ss = fmaf(v[i], v[i], ss);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                if (t.n0 + c * 16 + i < p.n) {
+                  s += v[i];
+                  ss = fmaf(v[i], v[i], ss);
+                }
               }
             }
           }
@@ -496,13 +504,14 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           if (HAS_LN) {
             const float4* gp = reinterpret_cast<const float4*>(p.ln_g + och);
             const float4* bp = reinterpret_cast<const float4*>(p.ln_b + och);
+            const float shift = -mean * rstd;   // (v - mean) * rstd * g + b as two FMAs
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               float4 g4 = __ldg(gp + i), b4 = __ldg(bp + i);
-              v[4 * i + 0] = (v[4 * i + 0] - mean) * rstd * g4.x + b4.x;
-              v[4 * i + 1] = (v[4 * i + 1] - mean) * rstd * g4.y + b4.y;
-              v[4 * i + 2] = (v[4 * i + 2] - mean) * rstd * g4.z + b4.z;
-              v[4 * i + 3] = (v[4 * i + 3] - mean) * rstd * g4.w + b4.w;
+              v[4 * i + 0] = fmaf(fmaf(v[4 * i + 0], rstd, shift), g4.x, b4.x);
+              v[4 * i + 1] = fmaf(fmaf(v[4 * i + 1], rstd, shift), g4.y, b4.y);
+              v[4 * i + 2] = fmaf(fmaf(v[4 * i + 2], rstd, shift), g4.z, b4.z);
+              v[4 * i + 3] = fmaf(fmaf(v[4 * i + 3], rstd, shift), g4.w, b4.w);
             }
           }
           if (POST_ACT != GWD_ACT_NONE) {

@@ -43,6 +43,15 @@ LINEAR_CASES = [
     (19200, 192, 64, 0, 0, 2, False),
     (513, 80, 160, 0, 2, 0, True),
     (100, 256, 6, 0, 4, 0, False),
+    # staged epilogue (residual tile fetched / result stored through per-warp shared-memory tiles)
+    (5000, 64, 256, 0, 1, 1, False),      # ResNet conv3: relu(x W + res), ragged last tile
+    (2500, 256, 1024, 0, 1, 1, False),    # four N tiles
+    (1111, 512, 128, 0, 0, 2, False),     # MLP fc2 + residual after
+    (3000, 128, 64, 0, 2, 2, False),      # 16-column staging rows
+    (700, 64, 120, 0, 1, 1, False),       # logical width below the padded width
+    # >= 4 x 148 M tiles with streamed weights: thread-block clusters of 2 CTAs, weight tiles by TMA multicast
+    (76057, 256, 512, 0, 1, 0, False),
+    (75800, 512, 320, 0, 0, 2, False),    # odd number of M tiles: one CTA of the last cluster runs a dummy tile
 ]
 
 
@@ -83,6 +92,9 @@ CONV_CASES = [
     (1, 12, 16, 320, 320, 0, 0, 0, False),
     (1, 9, 13, 1024, 256, 0, 2, 0, False),
     (3, 7, 10, 160, 160, 0, 2, 0, True),
+    # cluster / multicast path (>= 592 M tiles, filter too large to stay resident)
+    (4, 120, 160, 160, 160, 0, 2, 0, True),
+    (7, 97, 100, 80, 160, 0, 0, 0, False),    # 637 M tiles (odd), ragged borders
 ]
 
 

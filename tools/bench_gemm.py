@@ -23,6 +23,8 @@ CASES = {
     "ffn_256_2048": (1, 1, 4800, 256, 2048, 1, False, 1),
     "ffn_2048_256_ln": (1, 1, 4800, 2048, 256, 1, True, 0),
     "bb_64_256_relu": (1, 1, 307200, 64, 256, 1, False, 1),
+    "bb_64_256_res": (1, 1, 307200, 64, 256, 1, "res", 1),
+    "bb_256_1024_res": (1, 1, 19200, 256, 1024, 1, "res", 1),
     "bb_256_64_relu": (1, 1, 307200, 256, 64, 1, False, 1),
     "bb_512_128": (1, 1, 76800, 512, 128, 1, False, 1),
     "lin64_192": (1, 1, 16 * 414 * 49, 64, 192, 1, False, 0),
@@ -38,16 +40,20 @@ def run(name):
         pw = ops.pack_conv3x3(torch.randn(N, C, 3, 3, device="cuda", generator=g) * (9 * C) ** -0.5, torch.zeros(N, device="cuda"))
     else:
         pw = ops.pack_linear(torch.randn(N, C, device="cuda", generator=g) * C ** -0.5, torch.zeros(N, device="cuda"))
+    res = None
+    if ln == "res":
+        ln = False
+        res = torch.randn(B, H, W, pw.n_pad, device="cuda", generator=g).bfloat16()
     lnp = (torch.ones(pw.n_pad, device="cuda"), torch.zeros(pw.n_pad, device="cuda")) if ln else None
     out = torch.empty(B, H, W, pw.n_pad, device="cuda", dtype=torch.bfloat16)
     for i in range(3):
-        ops.conv_gemm(xs[i % 3], pw, ln=lnp, post_act=act, out=out)
+        ops.conv_gemm(xs[i % 3], pw, ln=lnp, post_act=act, out=out, res=res, res_mode=1 if res is not None else 0)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     iters = 10
     e0.record()
     for i in range(iters):
-        ops.conv_gemm(xs[i % 3], pw, ln=lnp, post_act=act, out=out)
+        ops.conv_gemm(xs[i % 3], pw, ln=lnp, post_act=act, out=out, res=res, res_mode=1 if res is not None else 0)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
