@@ -202,7 +202,14 @@ __device__ __forceinline__ float act_fn(float v) {
 }
 
 // loads 16 accumulator columns starting at chunk c0 (relative to tile) and applies bias/pre_act/res(before)
-template <int PRE_ACT>
+__device__ __forceinline__ void add_bf16x8(float* v, const uint4& u) {
+  float2 f0 = gwd_unpack_bf16x2(u.x), f1 = gwd_unpack_bf16x2(u.y), f2 = gwd_unpack_bf16x2(u.z), f3 = gwd_unpack_bf16x2(u.w);
+  v[0] += f0.x; v[1] += f0.y; v[2] += f1.x; v[3] += f1.y;
+  v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
+}
+
+// RES_BY_CALLER: the caller adds the (software-pipelined) residual itself
+template <int PRE_ACT, bool RES_BY_CALLER = false>
 __device__ __forceinline__ void load_chunk(const GemmParams& p, uint32_t taddr, int n_base, const RowCtx& rc,
                                            float (&v)[16]) {
   uint32_t r[16];
@@ -224,7 +231,7 @@ __device__ __forceinline__ void load_chunk(const GemmParams& p, uint32_t taddr, 
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = act_fn<PRE_ACT>(v[i]);
   }
-  if (p.res_mode == GWD_RES_BEFORE_NORM && rc.valid) {
+  if (!RES_BY_CALLER && p.res_mode == GWD_RES_BEFORE_NORM && rc.valid) {
     const uint4* rp = reinterpret_cast<const uint4*>(p.res + rc.pix * p.res_cstride + p.res_coff + n_base);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -426,6 +433,18 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         rc.pix = (static_cast<int64_t>(t.b) * p.H + py) * p.W + px;
         rc.b = t.b; rc.py = py; rc.px = px;
       }
+      // Plain epilogues: the residual of the first chunk is requested before the accumulator is waited for and the
+      // residual of chunk c+1 while chunk c is processed (the profile showed the epilogue warps parked on one
+      // dependent DRAM-latency load per 16-column chunk).
+      uint4 rpre0 = make_uint4(0u, 0u, 0u, 0u), rpre1 = rpre0;
+      const bool res_pf = !HAS_LN && p.res_mode != GWD_RES_NONE && rc.valid;
+      const __nv_bfloat16* res_row = p.res + rc.pix * p.res_cstride + p.res_coff + t.n0;
+      if (res_pf && c_begin < c_end) {
+        const bool after = p.res_mode == GWD_RES_AFTER;
+        const int nb = t.n0 + c_begin * 16;
+        if (!after || nb + 8 <= p.store_n) rpre0 = __ldg(reinterpret_cast<const uint4*>(res_row + c_begin * 16));
+        if (!after || nb + 16 <= p.store_n) rpre1 = __ldg(reinterpret_cast<const uint4*>(res_row + c_begin * 16) + 1);
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc) * p.acc_stride +
@@ -488,7 +507,18 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int c = my_begin; c < my_end; ++c) {
           const int n_base = t.n0 + c * 16;
           float v[16];
-          load_chunk<PRE_ACT>(p, t_row + c * 16, n_base, rc, v);
+          load_chunk<PRE_ACT, !HAS_LN>(p, t_row + c * 16, n_base, rc, v);
+          const uint4 rcur0 = rpre0, rcur1 = rpre1;
+          if (!HAS_LN && res_pf && c + 1 < my_end) {
+            const bool after = p.res_mode == GWD_RES_AFTER;
+            rpre0 = rpre1 = make_uint4(0u, 0u, 0u, 0u);
+            if (!after || n_base + 24 <= p.store_n) rpre0 = __ldg(reinterpret_cast<const uint4*>(res_row + (c + 1) * 16));
+            if (!after || n_base + 32 <= p.store_n) rpre1 = __ldg(reinterpret_cast<const uint4*>(res_row + (c + 1) * 16) + 1);
+          }
+          if (!HAS_LN && res_pf && p.res_mode == GWD_RES_BEFORE_NORM) {
+            add_bf16x8(v, rcur0);
+            add_bf16x8(v + 8, rcur1);
+          }
           if (p.y_raw != nullptr && rc.valid) {
             store_bf16_16(p.y_raw + rc.pix * p.yraw_cstride + p.yraw_coff + n_base, v, n_base, p.store_n);
           }
@@ -522,7 +552,12 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] *= p.out_scale;
           }
-          if (p.res_mode == GWD_RES_AFTER && rc.valid) {
+          if (!HAS_LN) {
+            if (res_pf && p.res_mode == GWD_RES_AFTER) {
+              add_bf16x8(v, rcur0);
+              add_bf16x8(v + 8, rcur1);
+            }
+          } else if (p.res_mode == GWD_RES_AFTER && rc.valid) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.res + rc.pix * p.res_cstride + p.res_coff + n_base);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
