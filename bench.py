@@ -228,8 +228,17 @@ def main():
             big = max(recs, key=lambda r: r[2])
             peak, peak_src = measured_peak()
             ach = tot_flop / (tot_ms / 1000.0) / 1e12
+            traffic, traffic_src = None, None
+            try:      # DRAM bytes of the same launches from the committed ncu pass (profiles/README.md); bench.py cannot run ncu
+                with open(os.path.join(ROOT, "profiles", "r1_tapgemm_dram.json")) as f:
+                    tj = json.load(f)
+                traffic = tj["dram_bytes_per_launch"]
+                traffic_src = "profiles/r1_tapgemm_dram.json: mean dram__bytes_read+write per launch over the %d launches of a step" % tj["launches"]
+            except (OSError, KeyError, ValueError):
+                pass
             roof = {"bound": "tensor", "kernel": "gwd_tapgemm_kernel (tcgen05 implicit GEMM, all %d launches of a step)" % len(recs),
-                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
+                    "traffic_source": traffic_src, "algorithmic_flop_per_launch": tot_flop / len(recs), "peak_source": peak_src,
                     "flop_per_step": tot_flop, "kernel_ms_per_step": tot_ms, "kernel_share_of_step": tot_ms / (ms / args.steps),
                     "largest_launch": {"desc": big[3], "tflops": big[2] / (big[0].elapsed_time(big[1]) / 1000.0) / 1e12}}
 

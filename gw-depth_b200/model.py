@@ -180,12 +180,17 @@ class GlassRGBD(_Node):
         plan = self.plan()
         dev = plan.dev
         comp = torch.cuda.current_stream(dev)
-        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        x_dev, out_dev, out_host = [None, None], [None, None], [None, None]
-        ev_in = [torch.cuda.Event() for _ in range(2)]
-        ev_used = [torch.cuda.Event() for _ in range(2)]
-        ev_out = [torch.cuda.Event() for _ in range(2)]
-        ev_done = [torch.cuda.Event() for _ in range(2)]
+        # streams, events and the device / pinned-host buffers live on the module: pinned allocations cost milliseconds
+        st = self.__dict__.setdefault("_serve_state", {})
+        if st.get("dev") != dev:
+            st.clear()
+            st.update(dev=dev, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev), x_dev=[None, None],
+                      out_dev=[None, None], out_host=[None, None],
+                      ev=[[torch.cuda.Event() for _ in range(2)] for _ in range(4)])
+        s_in, s_out = st["s_in"], st["s_out"]
+        x_dev, out_dev, out_host = st["x_dev"], st["out_dev"], st["out_host"]
+        ev_in, ev_used, ev_out, ev_done = st["ev"]
+        torch.cuda.synchronize(dev)      # a previous, abandoned iteration may still own the buffers
         pending = []
 
         def pick(out):
@@ -207,7 +212,7 @@ class GlassRGBD(_Node):
             comp.wait_event(ev_in[b])
             out = pick(self.forward(x_dev[b]))
             ev_used[b].record(comp)
-            if out_dev[b] is None:
+            if out_dev[b] is None or set(out_dev[b]) != set(out) or any(out_dev[b][k].shape != v.shape for k, v in out.items()):
                 out_dev[b] = {k: torch.empty_like(v) for k, v in out.items()}
                 out_host[b] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
             elif i >= 2:
