@@ -7,8 +7,8 @@ depth maps).  There are no host synchronisations and no data-dependent Python co
 it can be captured in a CUDA graph.
 
 What still runs through PyTorch library calls (cuDNN / ATen) and is therefore NOT claimed as a hand-written
-kernel: the ResNet-50 backbone convolutions (SURVEY.md section 8a row A2 keeps them on cuDNN) and three tiny
-index ops (top-k over 100 line logits, a gather of 20 lines, parameter broadcasts).
+kernel: the six stride-2 convolutions of the ResNet-50 backbone (with their ReLU) and three tiny index ops (top-k
+over 100 line logits, a gather of 20 lines, parameter broadcasts).
 
 Reference call sites are cited per method (paths relative to the reference root).
 """

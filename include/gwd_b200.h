@@ -106,6 +106,11 @@ int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream);
  * Replaces src/models/multi_head_attention.py:317-372 (bmm, masked_fill, softmax, bmm, transposes; the
  * head-averaged weights of :375-378 are dead and not produced) and the attention cores of
  * src/models/multiscale_transformerr.py:311-328 and :539-556.
+ * Three implementations behind this one entry point (the call never falls back to the host):
+ *   - head_dim 32, no bias / mask, Lk <= 480 (DETR self / cross attention): tcgen05 + TMEM (gwd_attn_tc.cu);
+ *   - bias given, Lq == Lk == 49 (7x7 windows): persistent mma.sync kernel with the bias table in shared memory
+ *     (gwd_attn_win.cu); the window mask must be two-valued (0 / one negative constant), as the reference builds it;
+ *   - anything else: thread-per-query kernel with K/V in shared memory (gwd_attn.cu).
  * ------------------------------------------------------------------------------------------ */
 typedef struct gwd_attn_desc {
   const void* q; const void* k; const void* v; void* o;
