@@ -342,18 +342,187 @@ __global__ void __launch_bounds__(256) gwd_ref_diffuse_conv_kernel(const float* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// The same convolution as an implicit GEMM on warp-level tensor-core MMAs (m16n8k8, TF32 operands, fp32 accumulate):
+// M = the band's pixels, N = 16 output channels, K = 9 taps x 16 input channels.  The scores feed a soft-max over the
+// reference axis after three diffusion rounds, so fp32-level accuracy is kept with the 3xTF32 split
+// (a_hi b_hi + a_lo b_hi + a_hi b_lo); the MMA count is irrelevant here (1.3 GFLOP per launch), the win is that one
+// A fragment of 4 shared-memory loads feeds 6 MMAs instead of 2 loads per 4 FMAs.  (direct kernel: 103 us, LSU bound.)
+// The weight fragments are laid out once per CTA as [k-step][n-tile][lane] float4 = {b0_hi, b1_hi, b0_lo, b1_lo}.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+constexpr int kDiffWarps = 9;
+__global__ void __launch_bounds__(kDiffWarps * 32) gwd_ref_diffuse_mma_kernel(const float* __restrict__ a, float* __restrict__ raw,
+                                                                           const __grid_constant__ DiffuseFilter flt,
+                                                                           double* __restrict__ stats, int P, int R,
+                                                                           int plane, int terms) {
+  extern __shared__ __align__(16) float dsm[];
+  constexpr int heads = kDiffHeads;
+  const int y0 = blockIdx.x * kDiffBand, b = blockIdx.y;
+  const int rows = min(kDiffBand, P - y0);
+  const int TR = kDiffBand + 2, TC = R + 2;
+  float4* wfrag = reinterpret_cast<float4*>(dsm);             // [18 k-steps][2 n-tiles][32 lanes]
+  float* tile = dsm + 18 * 2 * 32 * 4;                         // [heads][plane]  (plane >= TR*TC, == 8 mod 32: no bank conflicts)
+  __shared__ float red[kDiffWarps][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  // the filter leaves the parameter bank with consecutive lanes on consecutive words (a per-lane gather out of the
+  // constant bank is serialised address by address), parked in the tile area, then re-laid-out as fragments
+  for (int i = tid; i < heads * heads * 9; i += blockDim.x) tile[i] = flt.w[i];
+  __syncthreads();
+  // weight fragments: k-step ks = tap * 2 + kb covers input channels 8 kb .. 8 kb + 7 of tap `tap`
+  for (int i = tid; i < 18 * 2 * 32; i += blockDim.x) {
+    const int l = i & 31, nt = (i >> 5) & 1, ks = i >> 6;
+    const int tap = ks >> 1, kb = ks & 1;
+    const int oc = 8 * nt + (l >> 2), ic = 8 * kb + (l & 3);
+    const float w0 = tile[(oc * heads + ic) * 9 + tap], w1 = tile[(oc * heads + ic + 4) * 9 + tap];
+    const float h0 = __uint_as_float(__float_as_uint(w0) & 0xffffe000u), h1 = __uint_as_float(__float_as_uint(w1) & 0xffffe000u);
+    wfrag[i] = make_float4(h0, h1, w0 - h0, w1 - h1);
+  }
+  __syncthreads();
+  // input band with its halo, zero padded (cp.async with a zero source size): every request of the thread is in
+  // flight before the first one is waited for
+  {
+    const int per_ic = TR * TC, total = heads * per_ic;
+    const float* img = a + static_cast<int64_t>(b) * heads * P * R;
+    for (int i = tid; i < total; i += blockDim.x) {
+      const int ic = i / per_ic, r = i - ic * per_ic;
+      const int ty = r / TC, tx = r - ty * TC;
+      const int y = y0 + ty - 1, x = tx - 1;
+      const bool ok = y >= 0 && y < P && ty < rows + 2 && x >= 0 && x < R;
+      const float* src = ok ? img + (static_cast<int64_t>(ic) * P + y) * R + x : img;
+      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(tile + ic * plane + r));
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
+  __syncthreads();
+  const int npix = rows * R;
+  float s[4] = {0.f, 0.f, 0.f, 0.f}, ss[4] = {0.f, 0.f, 0.f, 0.f};   // this lane's channels: 2t, 2t+1, 8+2t, 8+2t+1
+  for (int mt = warp; mt * 16 < npix; mt += kDiffWarps) {
+    int p0 = mt * 16 + g, p1 = p0 + 8;
+    const bool ok0 = p0 < npix, ok1 = p1 < npix;
+    if (!ok0) p0 = npix - 1;
+    if (!ok1) p1 = npix - 1;
+    const int ty0 = p0 / R, tx0 = p0 - ty0 * R, ty1 = p1 / R, tx1 = p1 - ty1 * R;
+    const float* base0 = tile + t * plane + ty0 * TC + tx0;
+    const float* base1 = tile + t * plane + ty1 * TC + tx1;
+    float acc[2][4];
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+      acc[nt][0] = flt.b[8 * nt + 2 * t];
+      acc[nt][1] = flt.b[8 * nt + 2 * t + 1];
+      acc[nt][2] = acc[nt][0];
+      acc[nt][3] = acc[nt][1];
+    }
+    // operand split without conversions: the tensor core reads only the TF32 part (sign, exponent, 10 mantissa bits)
+    // of a 32-bit operand, so hi = v as is and lo = v - trunc_tf32(v) (exact in fp32) give the 3xTF32 terms with one
+    // LOP3 + one FADD per element (cvt.rna.tf32 expands to ~5 instructions here)
+    const int p4 = 4 * plane;
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy) {
+      const float* r0 = base0 + dy * TC;
+      const float* r1 = base1 + dy * TC;
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb) {
+          const float v[4] = {r0[2 * kb * p4 + dx], r1[2 * kb * p4 + dx], r0[(2 * kb + 1) * p4 + dx], r1[(2 * kb + 1) * p4 + dx]};
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            hi[i] = __float_as_uint(v[i]);
+            lo[i] = __float_as_uint(v[i] - __uint_as_float(hi[i] & 0xffffe000u));
+          }
+          const int ks = (dy * 3 + dx) * 2 + kb;
+#pragma unroll
+          for (int nt = 0; nt < 2; ++nt) {
+            const float4 w = wfrag[(ks * 2 + nt) * 32 + lane];
+            if (terms > 1) mma_tf32(acc[nt], lo, __float_as_uint(w.x), __float_as_uint(w.y));
+            if (terms > 2) mma_tf32(acc[nt], hi, __float_as_uint(w.z), __float_as_uint(w.w));
+            mma_tf32(acc[nt], hi, __float_as_uint(w.x), __float_as_uint(w.y));
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 2; ++nt) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int oc = 8 * nt + 2 * t + j;
+        float* dst = raw + ((static_cast<int64_t>(b) * heads + oc) * P + y0) * R;
+        if (ok0) {
+          dst[ty0 * R + tx0] = acc[nt][j];
+          s[2 * nt + j] += acc[nt][j];
+          ss[2 * nt + j] = fmaf(acc[nt][j], acc[nt][j], ss[2 * nt + j]);
+        }
+        if (ok1) {
+          dst[ty1 * R + tx1] = acc[nt][2 + j];
+          s[2 * nt + j] += acc[nt][2 + j];
+          ss[2 * nt + j] = fmaf(acc[nt][2 + j], acc[nt][2 + j], ss[2 * nt + j]);
+        }
+      }
+    }
+  }
+  // per-channel sums: over the 8 pixel lanes (xor 4, 8, 16), then over the warps, then one fp64 atomic per CTA
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+#pragma unroll
+    for (int o = 4; o < 32; o <<= 1) {
+      s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+      ss[i] += __shfl_xor_sync(0xffffffffu, ss[i], o);
+    }
+  }
+  if (g == 0) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int oc = 8 * (i >> 1) + 2 * t + (i & 1);
+      red[warp][oc * 2] = s[i];
+      red[warp][oc * 2 + 1] = ss[i];
+    }
+  }
+  __syncthreads();
+  if (tid < 32) {
+    double v = 0.0;
+    for (int w = 0; w < kDiffWarps; ++w) v += static_cast<double>(red[w][tid]);
+    atomicAdd(&stats[(static_cast<int64_t>(b) * heads) * 2 + tid], v);
+  }
+}
+
 // phase 2: a_out = a_in + gelu((raw - mean) * rstd)   with mean / var over the whole [P,R] image of (b, channel)
-__global__ void gwd_ref_diffuse_norm_kernel(const float* __restrict__ a_in, const float* __restrict__ raw,
-                                            const double* __restrict__ stats, float* __restrict__ a_out, int64_t per_img,
-                                            int64_t total) {
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
-       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    int64_t img = i / per_img;
-    double mean = stats[img * 2] / per_img;
-    double var = stats[img * 2 + 1] / per_img - mean * mean;
-    float rstd = rsqrtf(static_cast<float>(var > 0 ? var : 0) + 1e-5f);
-    float v = (raw[i] - static_cast<float>(mean)) * rstd;
-    a_out[i] = a_in[i] + gwd_apply_act(v, GWD_ACT_GELU);
+// grid (chunks, B * channels): the statistics are read once per thread, the plane is walked with 16-byte vectors
+__global__ void __launch_bounds__(256) gwd_ref_diffuse_norm_kernel(const float* __restrict__ a_in, const float* __restrict__ raw,
+                                                                   const double* __restrict__ stats, float* __restrict__ a_out,
+                                                                   int per_img) {
+  const int img = blockIdx.y;
+  const double mean_d = stats[img * 2] / per_img;
+  const double var = stats[img * 2 + 1] / per_img - mean_d * mean_d;
+  const float mean = static_cast<float>(mean_d);
+  const float rstd = rsqrtf(static_cast<float>(var > 0 ? var : 0) + 1e-5f);
+  const int64_t off = static_cast<int64_t>(img) * per_img;
+  const int stride = gridDim.x * blockDim.x, i0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((per_img & 3) == 0) {
+    const float4* ai = reinterpret_cast<const float4*>(a_in + off);
+    const float4* ri = reinterpret_cast<const float4*>(raw + off);
+    float4* ao = reinterpret_cast<float4*>(a_out + off);
+    for (int i = i0; i < (per_img >> 2); i += stride) {
+      const float4 x = ai[i], r = ri[i];
+      float4 y;
+      y.x = x.x + gwd_gelu((r.x - mean) * rstd);
+      y.y = x.y + gwd_gelu((r.y - mean) * rstd);
+      y.z = x.z + gwd_gelu((r.z - mean) * rstd);
+      y.w = x.w + gwd_gelu((r.w - mean) * rstd);
+      ao[i] = y;
+    }
+  } else {
+    for (int i = i0; i < per_img; i += stride) a_out[off + i] = a_in[off + i] + gwd_gelu((raw[off + i] - mean) * rstd);
   }
 }
 
@@ -505,21 +674,40 @@ extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w_h
   memcpy(flt.w, w_host, sizeof(flt.w));
   memcpy(flt.b, bias_host, sizeof(flt.b));
   GWD_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * B * heads, stream));
-  size_t smem = (static_cast<size_t>(heads) * (kDiffBand + 2) * (R + 2) + static_cast<size_t>(heads) * heads * 9) * sizeof(float);
-  GWD_CHECK_ARG(smem <= 200 * 1024, "gwd_ref_diffuse: %d reference points do not fit shared memory", R);
-  if (smem > 48 * 1024) {
-    static bool configured = false;
-    if (!configured) {
-      GWD_CUDA(cudaFuncSetAttribute(gwd_ref_diffuse_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
-    }
-  }
+  static const bool use_mma = []() { const char* e = getenv("GWD_DIFFUSE_MMA"); return !(e && e[0] == '0'); }();
   dim3 grid(static_cast<unsigned>(gwd_ceil_div(P, kDiffBand)), B);
-  gwd_ref_diffuse_conv_kernel<<<grid, 256, smem, stream>>>(a_in, raw_ws, flt, stats_ws, P, R);
+  if (use_mma) {
+    int plane = (kDiffBand + 2) * (R + 2);
+    plane += ((8 - plane % 32) + 32) % 32;     // plane stride == 8 (mod 32): the 4 channels x 8 pixels of a fragment load hit 32 banks
+    size_t smem = (static_cast<size_t>(heads) * plane + 18 * 2 * 32 * 4) * sizeof(float);
+    GWD_CHECK_ARG(smem <= 200 * 1024, "gwd_ref_diffuse: %d reference points do not fit shared memory", R);
+    if (smem > 48 * 1024) {
+      static bool configured = false;
+      if (!configured) {
+        GWD_CUDA(cudaFuncSetAttribute(gwd_ref_diffuse_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+      }
+    }
+    static const int terms = []() { const char* e = getenv("GWD_DIFFUSE_TERMS"); return e ? atoi(e) : 3; }();
+    gwd_ref_diffuse_mma_kernel<<<grid, kDiffWarps * 32, smem, stream>>>(a_in, raw_ws, flt, stats_ws, P, R, plane, terms);
+  } else {
+    size_t smem = (static_cast<size_t>(heads) * (kDiffBand + 2) * (R + 2) + static_cast<size_t>(heads) * heads * 9) * sizeof(float);
+    GWD_CHECK_ARG(smem <= 200 * 1024, "gwd_ref_diffuse: %d reference points do not fit shared memory", R);
+    if (smem > 48 * 1024) {
+      static bool configured = false;
+      if (!configured) {
+        GWD_CUDA(cudaFuncSetAttribute(gwd_ref_diffuse_conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        configured = true;
+      }
+    }
+    gwd_ref_diffuse_conv_kernel<<<grid, 256, smem, stream>>>(a_in, raw_ws, flt, stats_ws, P, R);
+  }
   GWD_LAUNCHED();
-  int64_t per_img = static_cast<int64_t>(P) * R, total = per_img * B * heads;
-  int blocks = static_cast<int>(std::min<int64_t>(gwd_ceil_div(total, 256), gwd_num_sms() * 8));
-  gwd_ref_diffuse_norm_kernel<<<blocks, 256, 0, stream>>>(a_in, raw_ws, stats_ws, a_out, per_img, total);
+  const int per_img = P * R;
+  int chunks = static_cast<int>(gwd_ceil_div(per_img, 256 * 4 * 4));
+  if (chunks < 1) chunks = 1;
+  gwd_ref_diffuse_norm_kernel<<<dim3(static_cast<unsigned>(chunks), static_cast<unsigned>(B * heads)), 256, 0, stream>>>(
+      a_in, raw_ws, stats_ws, a_out, per_img);
   GWD_LAUNCHED();
   return GWD_OK;
 }
