@@ -361,12 +361,11 @@ constexpr int kDiffWarps = 9;
 __global__ void __launch_bounds__(kDiffWarps * 32) gwd_ref_diffuse_mma_kernel(const float* __restrict__ a, float* __restrict__ raw,
                                                                            const __grid_constant__ DiffuseFilter flt,
                                                                            double* __restrict__ stats, int P, int R,
-                                                                           int plane, int terms) {
+                                                                           int plane, int terms, int nimg) {
   extern __shared__ __align__(16) float dsm[];
   constexpr int heads = kDiffHeads;
-  const int y0 = blockIdx.x * kDiffBand, b = blockIdx.y;
-  const int rows = min(kDiffBand, P - y0);
-  const int TR = kDiffBand + 2, TC = R + 2;
+  constexpr int TR = kDiffBand + 2;
+  const int TC = R + 2;
   float4* wfrag = reinterpret_cast<float4*>(dsm);             // [18 k-steps][2 n-tiles][32 lanes]
   float* tile = dsm + 18 * 2 * 32 * 4;                         // [heads][plane]  (plane >= TR*TC, == 8 mod 32: no bank conflicts)
   __shared__ float red[kDiffWarps][32];
@@ -386,19 +385,27 @@ __global__ void __launch_bounds__(kDiffWarps * 32) gwd_ref_diffuse_mma_kernel(co
     wfrag[i] = make_float4(h0, h1, w0 - h0, w1 - h1);
   }
   __syncthreads();
-  // input band with its halo, zero padded (cp.async with a zero source size): every request of the thread is in
-  // flight before the first one is waited for
+  // persistent CTAs: the fragments above are built once, then the CTA walks (band, image) items
+  const int bands = (P + kDiffBand - 1) / kDiffBand;
+  for (int item = blockIdx.x; item < bands * nimg; item += gridDim.x) {
+  const int b = item / bands, y0 = (item - b * bands) * kDiffBand;
+  const int rows = min(kDiffBand, P - y0);
+  // input band with its halo, zero padded (cp.async with a zero source size): a warp per (channel, row), every request
+  // of the thread in flight before the first one is waited for
   {
-    const int per_ic = TR * TC, total = heads * per_ic;
     const float* img = a + static_cast<int64_t>(b) * heads * P * R;
-    for (int i = tid; i < total; i += blockDim.x) {
-      const int ic = i / per_ic, r = i - ic * per_ic;
-      const int ty = r / TC, tx = r - ty * TC;
-      const int y = y0 + ty - 1, x = tx - 1;
-      const bool ok = y >= 0 && y < P && ty < rows + 2 && x >= 0 && x < R;
-      const float* src = ok ? img + (static_cast<int64_t>(ic) * P + y) * R + x : img;
-      const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(tile + ic * plane + r));
-      asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(ok ? 4 : 0) : "memory");
+    for (int rowid = warp; rowid < heads * TR; rowid += kDiffWarps) {
+      const int ic = rowid / TR, ty = rowid - ic * TR;
+      const int y = y0 + ty - 1;
+      const bool yok = y >= 0 && y < P && ty < rows + 2;
+      const float* srow = img + (static_cast<int64_t>(ic) * P + (yok ? y : 0)) * R;
+      float* drow = tile + ic * plane + ty * TC;
+      for (int tx = lane; tx < TC; tx += 32) {
+        const int x = tx - 1;
+        const bool ok = yok && x >= 0 && x < R;
+        const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(drow + tx));
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(ok ? srow + x : img), "r"(ok ? 4 : 0) : "memory");
+      }
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -493,6 +500,8 @@ __global__ void __launch_bounds__(kDiffWarps * 32) gwd_ref_diffuse_mma_kernel(co
     double v = 0.0;
     for (int w = 0; w < kDiffWarps; ++w) v += static_cast<double>(red[w][tid]);
     atomicAdd(&stats[(static_cast<int64_t>(b) * heads) * 2 + tid], v);
+  }
+  __syncthreads();   // `red` and the tile are reused by the next item
   }
 }
 
@@ -689,7 +698,12 @@ extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w_h
       }
     }
     static const int terms = []() { const char* e = getenv("GWD_DIFFUSE_TERMS"); return e ? atoi(e) : 3; }();
-    gwd_ref_diffuse_mma_kernel<<<grid, kDiffWarps * 32, smem, stream>>>(a_in, raw_ws, flt, stats_ws, P, R, plane, terms);
+    int per_sm = static_cast<int>((200 * 1024) / (smem + 1024));
+    if (per_sm > 3) per_sm = 3;
+    if (per_sm < 1) per_sm = 1;
+    unsigned ctas = static_cast<unsigned>(per_sm * gwd_num_sms());
+    if (ctas > grid.x * grid.y) ctas = grid.x * grid.y;
+    gwd_ref_diffuse_mma_kernel<<<ctas, kDiffWarps * 32, smem, stream>>>(a_in, raw_ws, flt, stats_ws, P, R, plane, terms, B);
   } else {
     size_t smem = (static_cast<size_t>(heads) * (kDiffBand + 2) * (R + 2) + static_cast<size_t>(heads) * heads * 9) * sizeof(float);
     GWD_CHECK_ARG(smem <= 200 * 1024, "gwd_ref_diffuse: %d reference points do not fit shared memory", R);
