@@ -31,6 +31,7 @@ class GemmDesc(ctypes.Structure):
         ("y", c_void_p), ("y_cstride", c_int), ("y_coff", c_int), ("y_f32", c_int),
         ("y_raw", c_void_p), ("yraw_cstride", c_int), ("yraw_coff", c_int),
         ("store_n", c_int), ("w_per_image", c_int), ("upsample2", c_int),
+        ("x_wstride", ctypes.c_int64), ("x_hstride", ctypes.c_int64), ("x_bstride", ctypes.c_int64),
     ]
 
 

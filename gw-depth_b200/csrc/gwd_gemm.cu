@@ -636,6 +636,9 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   GWD_CHECK_ARG(d != nullptr && d->x && d->w && d->y, "gwd_conv_gemm: null pointer");
   GWD_CHECK_ARG(d->taps == 1 || d->taps == 9, "gwd_conv_gemm: taps must be 1 or 9 (got %d)", d->taps);
+  GWD_CHECK_ARG((d->x_wstride == 0 && d->x_hstride == 0 && d->x_bstride == 0) ||
+                    (d->taps == 1 && d->x_wstride > 0 && d->x_hstride > 0 && d->x_bstride > 0),
+                "gwd_conv_gemm: strided pixel views need taps == 1 and three positive strides");
   GWD_CHECK_ARG(d->B > 0 && d->H > 0 && d->W > 0, "gwd_conv_gemm: empty input");
   GWD_CHECK_ARG(d->cin > 0 && d->cin % 16 == 0, "gwd_conv_gemm: cin %% 16 != 0 (%d)", d->cin);
   GWD_CHECK_ARG(d->n_pad > 0 && d->n_pad % 16 == 0 && d->n > 0 && d->n <= d->n_pad, "gwd_conv_gemm: bad n/n_pad");
@@ -833,8 +836,10 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   {
     cuuint64_t gdim[4] = {static_cast<cuuint64_t>(d->x_cstride), static_cast<cuuint64_t>(d->W),
                           static_cast<cuuint64_t>(d->H), static_cast<cuuint64_t>(d->B)};
-    cuuint64_t gstr[3] = {static_cast<cuuint64_t>(d->x_cstride) * 2, static_cast<cuuint64_t>(d->W) * d->x_cstride * 2,
-                          static_cast<cuuint64_t>(d->H) * d->W * d->x_cstride * 2};
+    const bool strided = d->x_wstride != 0 || d->x_hstride != 0 || d->x_bstride != 0;
+    const cuuint64_t ws = strided ? d->x_wstride : 1, hs = strided ? d->x_hstride : d->W,
+                     bs = strided ? d->x_bstride : static_cast<cuuint64_t>(d->H) * d->W;
+    cuuint64_t gstr[3] = {ws * d->x_cstride * 2, hs * d->x_cstride * 2, bs * d->x_cstride * 2};
     cuuint32_t box[4] = {static_cast<cuuint32_t>(p.BK), static_cast<cuuint32_t>(box_w), static_cast<cuuint32_t>(box_h), 1};
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = encode(&map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(d->x), gdim, gstr, box, estr,

@@ -136,9 +136,8 @@ class Engine:
                 blk = {"c1": self._fold_packed(q + "conv1", q + "bn1", 1), "c3": self._fold_packed(q + "conv3", q + "bn3", 1),
                        "stride": stride}
                 blk["c2"] = self._fold(q + "conv2", q + "bn2") if stride == 2 else self._fold_packed(q + "conv2", q + "bn2", 9)
-                if (q + "downsample.0.weight") in self.sd:
-                    blk["down"] = (self._fold(q + "downsample.0", q + "downsample.1") if stride == 2
-                                   else self._fold_packed(q + "downsample.0", q + "downsample.1", 1))
+                if (q + "downsample.0.weight") in self.sd:     # 1x1 projection; stride 2 = the same Linear on every other pixel
+                    blk["down"] = self._fold_packed(q + "downsample.0", q + "downsample.1", 1)
                 stage.append(blk)
             self.blocks.append(stage)
 
@@ -150,9 +149,12 @@ class Engine:
         for stage in self.blocks:
             for blk in stage:
                 y = conv_gemm(x, blk["c1"], post_act=ACT_RELU)
-                if blk["stride"] == 2:      # stride-2 3x3 and 1x1 projections: cuDNN on NCHW views of the same memory
-                    y = F.relu_(F.conv2d(y.permute(0, 3, 1, 2), *blk["c2"], stride=2, padding=1)).permute(0, 2, 3, 1)
-                    idt = F.conv2d(x.permute(0, 3, 1, 2), *blk["down"], stride=2).permute(0, 2, 3, 1)
+                if blk["stride"] == 2:
+                    # stride-2 3x3: cuDNN's fused conv + bias + ReLU on an NCHW view of the same memory (library call);
+                    # stride-2 1x1 projection: every other pixel, then the tcgen05 Linear with the BN shift fused
+                    y = torch.cudnn_convolution_relu(y.permute(0, 3, 1, 2), blk["c2"][0], blk["c2"][1], (2, 2), (1, 1), (1, 1),
+                                                     1).permute(0, 2, 3, 1)
+                    idt = conv_gemm(x, blk["down"], subsample2=True)
                 else:
                     y = conv_gemm(y, blk["c2"], post_act=ACT_RELU)
                     idt = conv_gemm(x, blk["down"]) if "down" in blk else x

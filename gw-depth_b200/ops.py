@@ -121,7 +121,7 @@ def _as_bhwc(t):
 
 def conv_gemm(x, pw, *, x_coff=0, out=None, y_coff=0, out_channels=None, out_f32=False,
               bias=True, ln=None, ln_eps=1e-5, pre_act=ACT_NONE, post_act=ACT_NONE, out_scale=1.0,
-              res=None, res_coff=0, res_mode=RES_NONE, y_raw=None, w_per_image=False):
+              res=None, res_coff=0, res_mode=RES_NONE, y_raw=None, w_per_image=False, subsample2=False):
     """y = epilogue(conv_or_linear(x[..., x_coff:x_coff+cin], pw)).  See include/gwd_b200.h.
 
     x      : bf16 channels-last [B,H,W,Cx] or [rows,Cx] / [B,L,Cx]
@@ -133,6 +133,11 @@ def conv_gemm(x, pw, *, x_coff=0, out=None, y_coff=0, out_channels=None, out_f32
     assert x.is_cuda and x.dtype == torch.bfloat16 and x.is_contiguous()
     B, H, W, Cx = _as_bhwc(x)
     taps = pw.taps
+    strides = None
+    if subsample2:      # Linear over x[:, ::2, ::2, :] without materialising the view (TMA walks the strided pixels)
+        assert taps == 1 and x.dim() == 4 and out is None
+        strides = (2, 2 * W, H * W)
+        H, W = (H + 1) // 2, (W + 1) // 2
     if taps == 9:
         assert x.dim() == 4
     # bf16 outputs carry all n_pad physical channels (pads are written as exact zeros) so that the next layer can
@@ -141,7 +146,7 @@ def conv_gemm(x, pw, *, x_coff=0, out=None, y_coff=0, out_channels=None, out_f32
     up2 = bool(getattr(pw, "upsample2", False))
     if out is None:
         oc = out_channels or store_n
-        shape = tuple(x.shape[:-1]) + (oc,)
+        shape = ((B, H, W) if subsample2 else tuple(x.shape[:-1])) + (oc,)
         if up2:     # fused nearest x2 up-sampling: [B,H,W,C] -> [B,2H,2W,Cout]
             shape = (B, 2 * H, 2 * W, pw.n // 4)
         out = torch.empty(shape, dtype=torch.float32 if out_f32 else torch.bfloat16, device=x.device)
@@ -164,6 +169,8 @@ def conv_gemm(x, pw, *, x_coff=0, out=None, y_coff=0, out_channels=None, out_f32
     d.store_n = store_n
     d.w_per_image = 1 if w_per_image else 0
     d.upsample2 = 1 if up2 else 0
+    if strides is not None:
+        d.x_wstride, d.x_hstride, d.x_bstride = strides
     if PROFILE is not None:
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()

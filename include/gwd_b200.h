@@ -92,6 +92,9 @@ typedef struct gwd_gemm_desc {
                            input WITHOUT materialising it.  w holds 4 phase filters stacked along N (n = 4*Cout, phase
                            2*oy+ox): output pixel (2y+oy, 2x+ox) of the [B,2H,2W,y_cstride] output takes channels
                            [phase*Cout, (phase+1)*Cout).  A LayerNorm epilogue then normalises each phase group. */
+  int64_t x_wstride, x_hstride, x_bstride;   /* pixel strides of x along W / H / B in PIXELS (0, 0, 0 = dense [B,H,W]); a
+                           stride-2 1x1 projection (ResNet downsample, torchvision Bottleneck) is a Linear over the
+                           view x[:, ::2, ::2, :]: H, W = the view's extents, strides = (2, 2*W0, H0*W0).  taps == 1 only. */
 } gwd_gemm_desc;
 
 int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream);

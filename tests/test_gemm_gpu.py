@@ -49,9 +49,9 @@ LINEAR_CASES = [
     (1111, 512, 128, 0, 0, 2, False),     # MLP fc2 + residual after
     (3000, 128, 64, 0, 2, 2, False),      # 16-column staging rows
     (700, 64, 120, 0, 1, 1, False),       # logical width below the padded width
-    # >= 4 x 148 M tiles with streamed weights: thread-block clusters of 2 CTAs, weight tiles by TMA multicast
+    # large M with streamed weights
     (76057, 256, 512, 0, 1, 0, False),
-    (75800, 512, 320, 0, 0, 2, False),    # odd number of M tiles: one CTA of the last cluster runs a dummy tile
+    (75800, 512, 320, 0, 0, 2, False),
 ]
 
 
@@ -92,7 +92,7 @@ CONV_CASES = [
     (1, 12, 16, 320, 320, 0, 0, 0, False),
     (1, 9, 13, 1024, 256, 0, 2, 0, False),
     (3, 7, 10, 160, 160, 0, 2, 0, True),
-    # cluster / multicast path (>= 592 M tiles, filter too large to stay resident)
+    # >= 592 M tiles, filter too large to stay resident
     (4, 120, 160, 160, 160, 0, 2, 0, True),
     (7, 97, 100, 80, 160, 0, 0, 0, False),    # 637 M tiles (odd), ragged borders
 ]
@@ -163,3 +163,20 @@ def test_fused_upsample_conv(C, N, use_ln):
     assert y.shape == (B, 2 * H, 2 * W, N)
     err = (y.float().cpu() - ref).abs().max().item()
     assert err < 3e-2 * max(1.0, ref.abs().max().item()), err     # phase filters are sums of bf16 taps, re-rounded to bf16
+
+
+@pytest.mark.parametrize("B,H,W,K,N", [(2, 30, 40, 256, 512), (1, 15, 21, 64, 128), (3, 7, 9, 512, 1024)])
+def test_linear_on_strided_pixels(B, H, W, K, N):
+    """stride-2 1x1 projection (ResNet downsample): a Linear over x[:, ::2, ::2, :] read through a strided tensor map;
+    odd extents included"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(B + H + W + K)
+    x = _rand((B, H, W, K), g).bfloat16()
+    w = _rand((N, K), g, K ** -0.5).bfloat16()
+    b = _rand((N,), g, 0.5)
+    ref = x.float()[:, ::2, ::2, :] @ w.float().t() + b
+    pw = ops.pack_linear(w.cuda(), b.cuda())
+    out = ops.conv_gemm(x.cuda(), pw, subsample2=True)
+    assert tuple(out.shape) == tuple(ref.shape)
+    err = (out.float().cpu() - ref).abs().max().item()
+    assert err <= 2e-2 * max(1.0, ref.abs().max().item()), err      # bf16 output rounding
