@@ -49,6 +49,7 @@ struct GemmParams {
   uint32_t idesc;
   uint32_t acc_stride;                    // TMEM columns between consecutive accumulators
   uint32_t tmem_cols;
+  uint32_t stage_off;                     // TMAEP kernels: byte offset of the per-warp epilogue staging tiles
   int nacc;                               // TMEM accumulators in flight (2, 4 or 8; power of two)
   int tile_split;   // 1: each 4-warp epilogue group drains whole tiles (tile j -> group j % groups); 0: groups split columns
   int n, n_pad, store_n;
@@ -119,6 +120,17 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
 }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -264,10 +276,17 @@ __device__ __forceinline__ void store_bf16_16(__nv_bfloat16* dst, const float (&
 // ---------------------------------------------------------------------------------------------
 // PRE_ACT / POST_ACT / HAS_LN are compile-time so that each instantiation carries one activation body instead of a
 // 5-way switch unrolled 16x at three sites (that version was instruction-fetch bound: ~100 KB of SASS per kernel)
-template <int PRE_ACT, int POST_ACT, bool HAS_LN>
+// TMAEP (plain [rows, N] Linears with 64 output columns per epilogue warp, bf16 out): the epilogue never touches global
+// memory with the LSU.  Each epilogue warp owns a 32-row x 128-byte staging tile (SWIZZLE_128B): the residual tile
+// arrives in it by TMA (requested before the accumulator is waited for), the thread-per-row math reads / overwrites it
+// in place (conflict-free: chunk ^ (row & 7)), and the result leaves by TMA store.  Ragged row / column tails are
+// clipped by the tensor maps.  A separate instantiation: the other epilogues do not carry this code (the kernel is
+// sensitive to its instruction footprint).
+template <int PRE_ACT, int POST_ACT, bool HAS_LN, bool TMAEP = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                   const __grid_constant__ GemmParams p) {
+                   const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap map_res,
+                   const __grid_constant__ CUtensorMap map_y) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment is required by SWIZZLE_128B; do not trust the declared alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -282,7 +301,9 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint64_t* w_bar = bars + 2 * kMaxStages + 2 * kMaxAcc;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAcc + 1);
 
-  float2* ln_stats = reinterpret_cast<float2*>(tmem_ptr + 4);   // [2][4 column groups][128 rows] partial (sum, sum of squares)
+  float2* ln_stats = reinterpret_cast<float2*>(tmem_ptr + 4);
+  uint64_t* ep_bar = reinterpret_cast<uint64_t*>(smem + p.stage_off);   // TMAEP: [16] one barrier per epilogue warp
+  uint8_t* ep_stage = smem + p.stage_off + 1024;                        // TMAEP: [16][32 rows][128 B]   // [2][4 column groups][128 rows] partial (sum, sum of squares)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -298,6 +319,8 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       mbar_init(&tmem_empty[a], p.tile_split ? 4 : (blockDim.x >> 5) - 2);
     }
     mbar_init(w_bar, 1);
+    if (TMAEP)
+      for (int w = 0; w < kMaxEpilogueWarps; ++w) mbar_init(&ep_bar[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
@@ -436,8 +459,22 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // Plain epilogues: the residual of the first chunk is requested before the accumulator is waited for and the
       // residual of chunk c+1 while chunk c is processed (the profile showed the epilogue warps parked on one
       // dependent DRAM-latency load per 16-column chunk).
+      uint8_t* my_stage = ep_stage + ew * 4096;
+      uint8_t* my_row = my_stage + lane * 128;
+      const int ep_col0 = t.n0 + c_begin * 16, ep_row0 = t.x0 + quad * 32;
+      if (TMAEP) {
+        if (lane == 0) {
+          // the previous tile's store must have finished reading the staging tile before it is overwritten
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (p.res_mode != GWD_RES_NONE) {
+            mbar_arrive_expect_tx(&ep_bar[ew], 4096);
+            tma_load_2d(my_stage, &map_res, &ep_bar[ew], ep_col0, ep_row0);
+          }
+        }
+        __syncwarp();
+      }
       uint4 rpre0 = make_uint4(0u, 0u, 0u, 0u), rpre1 = rpre0;
-      const bool res_pf = !HAS_LN && p.res_mode != GWD_RES_NONE && rc.valid;
+      const bool res_pf = !TMAEP && !HAS_LN && p.res_mode != GWD_RES_NONE && rc.valid;
       const __nv_bfloat16* res_row = p.res + rc.pix * p.res_cstride + p.res_coff + t.n0;
       if (res_pf && c_begin < c_end) {
         const bool after = p.res_mode == GWD_RES_AFTER;
@@ -449,6 +486,7 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       tcgen05_fence_after();
       const uint32_t t_row = tmem_base + static_cast<uint32_t>(acc) * p.acc_stride +
                              (static_cast<uint32_t>(quad * 32) << 16);
+      if (TMAEP && p.res_mode != GWD_RES_NONE) mbar_wait(&ep_bar[ew], static_cast<uint32_t>(j) & 1u);   // one phase per tile
 
       // A "segment" is a chunk range whose LayerNorm statistics are taken together.  Whole-row LayerNorm: both column
       // halves read the full row for the statistics and store their own half.  Grouped LayerNorm (fused up-sampling:
@@ -519,6 +557,12 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             add_bf16x8(v, rcur0);
             add_bf16x8(v + 8, rcur1);
           }
+          uint4* ep_p0 = reinterpret_cast<uint4*>(my_row + ((((c - c_begin) * 2) ^ (lane & 7)) << 4));
+          uint4* ep_p1 = reinterpret_cast<uint4*>(my_row + ((((c - c_begin) * 2 + 1) ^ (lane & 7)) << 4));
+          if (TMAEP && p.res_mode == GWD_RES_BEFORE_NORM) {
+            add_bf16x8(v, *ep_p0);
+            add_bf16x8(v + 8, *ep_p1);
+          }
           if (p.y_raw != nullptr && rc.valid) {
             store_bf16_16(p.y_raw + rc.pix * p.yraw_cstride + p.yraw_coff + n_base, v, n_base, p.store_n);
           }
@@ -557,6 +601,10 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               add_bf16x8(v, rcur0);
               add_bf16x8(v + 8, rcur1);
             }
+            if (TMAEP && p.res_mode == GWD_RES_AFTER) {
+              add_bf16x8(v, *ep_p0);
+              add_bf16x8(v + 8, *ep_p1);
+            }
           } else if (p.res_mode == GWD_RES_AFTER && rc.valid) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.res + rc.pix * p.res_cstride + p.res_coff + n_base);
 #pragma unroll
@@ -576,7 +624,15 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int i = 0; i < 16; ++i)
               if (n_base + i >= p.n) v[i] = 0.f;
           }
-          if (rc.valid) {
+          if (TMAEP) {   // the result overwrites the residual pieces in place
+            uint4 u0, u1;
+            u0.x = gwd_pack_bf16x2(v[0], v[1]); u0.y = gwd_pack_bf16x2(v[2], v[3]);
+            u0.z = gwd_pack_bf16x2(v[4], v[5]); u0.w = gwd_pack_bf16x2(v[6], v[7]);
+            u1.x = gwd_pack_bf16x2(v[8], v[9]); u1.y = gwd_pack_bf16x2(v[10], v[11]);
+            u1.z = gwd_pack_bf16x2(v[12], v[13]); u1.w = gwd_pack_bf16x2(v[14], v[15]);
+            *ep_p0 = u0;
+            *ep_p1 = u1;
+          } else if (rc.valid) {
             if (p.y_f32) {
               float* dst = reinterpret_cast<float*>(p.y) + opix * p.y_cstride + p.y_coff + och;
 #pragma unroll
@@ -592,7 +648,16 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (TMAEP) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&map_y, my_stage, ep_col0, ep_row0);
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
     }
+    if (TMAEP && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores complete before exit
   }
 
   tcgen05_fence_before();
@@ -810,7 +875,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
     if (forced_warps == 8 || (forced_warps == 16 && epi_warps == 16)) epi_warps = forced_warps;
   }
   p.tmem_cols = pow2_at_least(static_cast<uint32_t>(p.nacc) * p.acc_stride, 32);
-  const int threads = (2 + epi_warps) * 32;
+  int threads = (2 + epi_warps) * 32;
   p.x_coff = d->x_coff;
   p.w_img_stride = d->w_per_image ? d->taps : 0;
   p.n = d->n; p.n_pad = d->n_pad; p.store_n = store_n;
@@ -866,13 +931,84 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
     }
   }
 
-  const size_t ring_bytes = static_cast<size_t>(p.stages) * (p.a_stage_bytes + p.b_stage_bytes) + w_region;
   const size_t bar_bytes =
       ((2 * kMaxStages + 2 * kMaxAcc + 1) * sizeof(uint64_t) + 16 + (has_ln ? 2 * 4 * 128 * sizeof(float2) : 0) + 127) & ~size_t(127);
-  const size_t smem_bytes = 1024 + ring_bytes + bar_bytes;
+  // TMA epilogue (see the kernel): plain dense [rows, N] Linears whose epilogue warps own 64 columns each
+  CUtensorMap map_res, map_y;
+  memset(&map_res, 0, sizeof(map_res));
+  memset(&map_y, 0, sizeof(map_y));
+  bool tma_ep = false;
+  {
+    static const bool enabled = []() { const char* e = getenv("GWD_GEMM_TMAEP"); return !(e && e[0] == '0'); }();
+    const bool strided_x = d->x_wstride != 0;
+    const size_t ep_bytes = 1024 + static_cast<size_t>(kMaxEpilogueWarps) * 4096;
+    // one 4-warp group per 64 output columns: N tiles of 128 / 192 / 256 columns -> 8 / 12 / 16 epilogue warps
+    if (enabled && d->taps == 1 && d->B == 1 && d->H == 1 && !strided_x && ctas == 1 && !p.tile_split && !has_ln && !d->y_f32 &&
+        d->y_raw == nullptr && !d->upsample2 && !d->w_per_image && d->pre_act == GWD_ACT_NONE &&
+        (d->post_act == GWD_ACT_NONE || d->post_act == GWD_ACT_RELU || d->post_act == GWD_ACT_GELU) &&
+        (p.Nt == 128 || p.Nt == 192 || p.Nt == 256) &&
+        store_n % 8 == 0 && d->y_cstride % 8 == 0 && d->y_coff % 8 == 0 &&
+        (d->res == nullptr || (d->res_cstride % 8 == 0 && d->res_coff % 8 == 0)) &&
+        static_cast<int64_t>(p.m_tiles) * p.n_tiles >= gwd_num_sms()) {
+      int stages = p.stages;
+      const size_t slot = p.a_stage_bytes + p.b_stage_bytes;
+      auto total = [&](int st) { return 1024 + st * slot + w_region + ((bar_bytes + 1023) & ~size_t(1023)) + ep_bytes; };
+      while (stages > 3 && total(stages) > 226 * 1024) --stages;
+      if (total(stages) <= 226 * 1024) {
+        p.stages = stages;
+        tma_ep = true;
+        epi_warps = p.Nt / 16;
+        threads = (2 + epi_warps) * 32;
+      }
+    }
+  }
+  const size_t ring_bytes = static_cast<size_t>(p.stages) * (p.a_stage_bytes + p.b_stage_bytes) + w_region;
+  size_t smem_bytes = 1024 + ring_bytes + bar_bytes;
+  if (tma_ep) {
+    p.stage_off = static_cast<uint32_t>((ring_bytes + bar_bytes + 1023) & ~size_t(1023));   // staging tiles 1024-aligned (SW128)
+    smem_bytes = 1024 + p.stage_off + 1024 + static_cast<size_t>(kMaxEpilogueWarps) * 4096;
+    const cuuint64_t rows = static_cast<cuuint64_t>(d->W);
+    cuuint32_t box[2] = {64, 32};
+    cuuint32_t estr[2] = {1, 1};
+    {
+      cuuint64_t gdim[2] = {static_cast<cuuint64_t>(store_n), rows};
+      cuuint64_t gstr[1] = {static_cast<cuuint64_t>(d->y_cstride) * 2};
+      void* base = static_cast<__nv_bfloat16*>(d->y) + d->y_coff;
+      CUresult r = encode(&map_y, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        gwd_set_error("cuTensorMapEncodeTiled(output) failed: %d", static_cast<int>(r));
+        return GWD_ERR_CUDA;
+      }
+    }
+    if (d->res != nullptr) {
+      cuuint64_t gdim[2] = {static_cast<cuuint64_t>(store_n), rows};
+      cuuint64_t gstr[1] = {static_cast<cuuint64_t>(d->res_cstride) * 2};
+      void* base = const_cast<__nv_bfloat16*>(static_cast<const __nv_bfloat16*>(d->res)) + d->res_coff;
+      CUresult r = encode(&map_res, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, gdim, gstr, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) {
+        gwd_set_error("cuTensorMapEncodeTiled(residual) failed: %d", static_cast<int>(r));
+        return GWD_ERR_CUDA;
+      }
+    }
+  }
   const int total_tiles = p.m_tiles * p.n_tiles;
   int grid = ctas * gwd_num_sms();
   if (grid > total_tiles) grid = total_tiles;
+#define GWD_GEMM_CASE_TMAEP(POST)                                                                             \
+  if (tma_ep && d->post_act == POST) {                                                                        \
+    static bool attr_set = false;                                                                             \
+    if (!attr_set) {                                                                                          \
+      GWD_CUDA(cudaFuncSetAttribute(gwd_tapgemm_kernel<GWD_ACT_NONE, POST, false, true>,                       \
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));                \
+      attr_set = true;                                                                                        \
+    }                                                                                                         \
+    gwd_tapgemm_kernel<GWD_ACT_NONE, POST, false, true><<<grid, threads, smem_bytes, stream>>>(map_a, map_b, p, map_res, map_y); \
+    launched = true;                                                                                          \
+  }
 #define GWD_GEMM_CASE(PRE, POST, LN)                                                                          \
   if (d->pre_act == PRE && d->post_act == POST && has_ln == LN) {                                             \
     static bool attr_set = false;                                                                             \
@@ -881,11 +1017,14 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
                                     227 * 1024));                                                             \
       attr_set = true;                                                                                        \
     }                                                                                                         \
-    gwd_tapgemm_kernel<PRE, POST, LN><<<grid, threads, smem_bytes, stream>>>(map_a, map_b, p);                \
+    gwd_tapgemm_kernel<PRE, POST, LN><<<grid, threads, smem_bytes, stream>>>(map_a, map_b, p, map_res, map_y); \
     launched = true;                                                                                          \
   }
   bool launched = false;
-  GWD_GEMM_CASE(GWD_ACT_NONE, GWD_ACT_NONE, false)
+  GWD_GEMM_CASE_TMAEP(GWD_ACT_NONE)
+  else GWD_GEMM_CASE_TMAEP(GWD_ACT_RELU)
+  else GWD_GEMM_CASE_TMAEP(GWD_ACT_GELU)
+  else GWD_GEMM_CASE(GWD_ACT_NONE, GWD_ACT_NONE, false)
   else GWD_GEMM_CASE(GWD_ACT_NONE, GWD_ACT_RELU, false)
   else GWD_GEMM_CASE(GWD_ACT_NONE, GWD_ACT_GELU, false)
   else GWD_GEMM_CASE(GWD_ACT_NONE, GWD_ACT_ELU, false)
@@ -895,6 +1034,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   else GWD_GEMM_CASE(GWD_ACT_NONE, GWD_ACT_RELU, true)
   else GWD_GEMM_CASE(GWD_ACT_ELU, GWD_ACT_NONE, true)
 #undef GWD_GEMM_CASE
+#undef GWD_GEMM_CASE_TMAEP
   if (!launched) {
     gwd_set_error("gwd_conv_gemm: epilogue combination pre_act=%d post_act=%d ln=%d is not instantiated", d->pre_act,
                   d->post_act, static_cast<int>(has_ln));

@@ -153,6 +153,8 @@ def conv_gemm(x, pw, *, x_coff=0, out=None, y_coff=0, out_channels=None, out_f32
     assert out.is_contiguous()
     d = capi.GemmDesc()
     d.x = x.data_ptr(); d.B, d.H, d.W = B, H, W
+    if taps == 1 and not subsample2 and not w_per_image:
+        d.B, d.H, d.W = 1, 1, B * H * W      # a dense Linear is one row axis (lets the kernel use its TMA epilogue)
     d.x_cstride, d.x_coff, d.cin = Cx, x_coff, pw.cin_pad
     d.w = pw.w.data_ptr(); d.taps = taps; d.n_pad = pw.n_pad; d.n = pw.n
     d.bias = pw.bias.data_ptr() if (bias and pw.bias is not None) else None

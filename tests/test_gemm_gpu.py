@@ -49,6 +49,13 @@ LINEAR_CASES = [
     (1111, 512, 128, 0, 0, 2, False),     # MLP fc2 + residual after
     (3000, 128, 64, 0, 2, 2, False),      # 16-column staging rows
     (700, 64, 120, 0, 1, 1, False),       # logical width below the padded width
+    # TMA epilogue (>= 296 M tiles, 64 columns per epilogue warp): residual tile in / result out through shared memory
+    (40001, 64, 256, 0, 1, 1, False),     # ResNet conv3 shape, ragged last tile
+    (38013, 256, 1024, 0, 0, 2, False),   # four N tiles, residual after
+    (39000, 128, 250, 0, 1, 0, False),    # logical width below the padded width, no residual
+    (20011, 64, 192, 0, 2, 0, False),     # 12 epilogue warps (3 groups of 64 columns), GELU
+    (19999, 192, 384, 0, 0, 1, False),    # two N tiles of 192
+    (21000, 64, 128, 0, 2, 2, False),     # 8 epilogue warps
     # large M with streamed weights
     (76057, 256, 512, 0, 1, 0, False),
     (75800, 512, 320, 0, 0, 2, False),
