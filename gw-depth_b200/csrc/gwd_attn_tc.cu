@@ -101,6 +101,12 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes,
   return d;
 }
 
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __global__ void __launch_bounds__(160, 1)
 gwd_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                         const __grid_constant__ CUtensorMap map_v, const __grid_constant__ TcAttnParams p) {
@@ -179,14 +185,21 @@ gwd_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     const uint8_t* kp = p.kpm ? p.kpm + static_cast<int64_t>(item) * p.Lk : nullptr;
     mbar_wait(s_bar, 0);
     fence_after();
+    // full 16-key chunks without key padding take the check-free path: 1 FMNMX per score in the first pass and
+    // FFMA + MUFU.EX2 + FADD in the second (the per-element validity tests made this 4-warp soft-max the critical path)
     float mx = -INFINITY;
     for (int c = 0; c < Lk_pad; c += 16) {
       uint32_t r[16];
       tmem_ld16(t_row + c, r);
+      if (kp == nullptr && c + 16 <= p.Lk) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        bool ok = (c + i < p.Lk) && !(kp && kp[c + i]);
-        if (ok) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          bool ok = (c + i < p.Lk) && !(kp && kp[c + i]);
+          if (ok) mx = fmaxf(mx, __uint_as_float(r[i]));
+        }
       }
     }
     float sum = 0.f;
@@ -196,11 +209,19 @@ gwd_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
       uint32_t r[16];
       tmem_ld16(t_row + c, r);
       float e[16];
+      if (kp == nullptr && c + 16 <= p.Lk) {
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        bool ok = (c + i < p.Lk) && !(kp && kp[c + i]);
-        e[i] = ok ? exp2f(fmaf(__uint_as_float(r[i]), l2e, -mxs)) : 0.f;
-        sum += e[i];
+        for (int i = 0; i < 16; ++i) {
+          e[i] = ex2_fast(fmaf(__uint_as_float(r[i]), l2e, -mxs));
+          sum += e[i];
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          bool ok = (c + i < p.Lk) && !(kp && kp[c + i]);
+          e[i] = ok ? ex2_fast(fmaf(__uint_as_float(r[i]), l2e, -mxs)) : 0.f;
+          sum += e[i];
+        }
       }
       // 16 keys = two 16-byte units of the 64-key chunk (c / 64), row `row`, 128-byte swizzle
       uint8_t* chunk = sP + static_cast<size_t>(c >> 6) * (kQTile * 128) + row * 128;
