@@ -231,33 +231,50 @@ __global__ void __launch_bounds__(128) gwd_ref_scores_kernel(const bf16* __restr
                                                             const float* __restrict__ refk, int64_t ref_rs,
                                                             float* __restrict__ out, int T, int heads, int hd, int R,
                                                             float scale) {
-  extern __shared__ float rk[];  // [R][hd]
+  extern __shared__ __align__(16) float rk[];  // [R][hd] reference keys, then [128][R + 1] staged scores
+  float* stile = rk + R * hd;
   const int b = blockIdx.z, h = blockIdx.y;
   for (int i = threadIdx.x; i < R * hd; i += blockDim.x) {
     int r = i / hd, dd = i - r * hd;
     rk[i] = refk[(static_cast<int64_t>(b) * R + r) * ref_rs + h * hd + dd] * scale;
   }
   __syncthreads();
-  int tok = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tok >= T) return;
-  float qv[32];
-  const bf16* qr = q + (static_cast<int64_t>(b) * T + tok) * q_rs + h * hd;
+  const int tok0 = blockIdx.x * blockDim.x, tok = tok0 + threadIdx.x;
+  if (tok < T) {
+    float qv[32];
+    const bf16* qr = q + (static_cast<int64_t>(b) * T + tok) * q_rs + h * hd;
+    if ((hd & 7) == 0 && (reinterpret_cast<uintptr_t>(qr) & 15) == 0) {   // 16-byte pieces of the query row
 #pragma unroll
-  for (int dd = 0; dd < 32; ++dd) qv[dd] = dd < hd ? __bfloat162float(qr[dd]) : 0.f;
-  float* o = out + ((static_cast<int64_t>(b) * heads + h) * T + tok) * R;
-  for (int r = 0; r < R; ++r) {
-    float sacc = 0.f;
+      for (int w = 0; w < 4; ++w) {
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (8 * w < hd) u = __ldg(reinterpret_cast<const uint4*>(qr) + w);
+        float2 f0 = gwd_unpack_bf16x2(u.x), f1 = gwd_unpack_bf16x2(u.y), f2 = gwd_unpack_bf16x2(u.z), f3 = gwd_unpack_bf16x2(u.w);
+        qv[8 * w + 0] = f0.x; qv[8 * w + 1] = f0.y; qv[8 * w + 2] = f1.x; qv[8 * w + 3] = f1.y;
+        qv[8 * w + 4] = f2.x; qv[8 * w + 5] = f2.y; qv[8 * w + 6] = f3.x; qv[8 * w + 7] = f3.y;
+      }
+    } else {
 #pragma unroll
-    for (int dd = 0; dd < 32; ++dd)
-      if (dd < hd) sacc = fmaf(qv[dd], rk[r * hd + dd], sacc);
-    o[r] = sacc;
+      for (int dd = 0; dd < 32; ++dd) qv[dd] = dd < hd ? __bfloat162float(qr[dd]) : 0.f;
+    }
+    float* srow = stile + threadIdx.x * (R + 1);
+    for (int r = 0; r < R; ++r) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int dd = 0; dd < 32; ++dd)
+        if (dd < hd) sacc = fmaf(qv[dd], rk[r * hd + dd], sacc);
+      srow[r] = sacc;
+    }
+  }
+  __syncthreads();
+  // the tile's scores are one contiguous block of the output: consecutive threads write consecutive floats
+  const int ntok = min(static_cast<int>(blockDim.x), T - tok0);
+  float* o = out + ((static_cast<int64_t>(b) * heads + h) * T + tok0) * R;
+  for (int i = threadIdx.x; i < ntok * R; i += blockDim.x) {
+    const int tl = i / R, r = i - tl * R;
+    o[i] = stile[tl * (R + 1) + r];
   }
 }
 
-// diffusion step, phase 1: raw = conv3x3_{heads->heads}(a) for a band of rows of one image, all output channels;
-// per-(image, channel) sum / sum of squares accumulated in fp64 for the whole-image LayerNorm of phase 2.
-// a: [B][heads][P][R] fp32.  grid (row bands, B), block 128: warp w produces output channels 4w..4w+3 (register tile),
-// lanes stride over the band's pixels.  The 16x16x9 filter travels as a kernel parameter (constant bank operands).
 constexpr int kDiffBand = 7;
 constexpr int kDiffHeads = 16;
 struct DiffuseFilter {
@@ -540,16 +557,25 @@ __global__ void __launch_bounds__(256) gwd_ref_diffuse_norm_kernel(const float* 
 __global__ void __launch_bounds__(128) gwd_ref_requery_kernel(const float* __restrict__ a, const float* __restrict__ refv,
                                                              int64_t ref_rs, bf16* __restrict__ out, int64_t o_rs, int T,
                                                              int heads, int hd, int R, float scale) {
-  extern __shared__ float rv[];  // [R][hd]
+  extern __shared__ __align__(16) float rv[];  // [R][hd] reference values, then [128][R + 1] staged score rows
+  float* stile = rv + R * hd;
   const int b = blockIdx.z, h = blockIdx.y;
+  const int tok0 = blockIdx.x * blockDim.x, tok = tok0 + threadIdx.x;
   for (int i = threadIdx.x; i < R * hd; i += blockDim.x) {
     int r = i / hd, dd = i - r * hd;
     rv[i] = refv[(static_cast<int64_t>(b) * R + r) * ref_rs + h * hd + dd];
   }
+  {  // the tile's score rows are one contiguous block: coalesced read, one padded row per thread afterwards
+    const int ntok = min(static_cast<int>(blockDim.x), T - tok0);
+    const float* src = a + ((static_cast<int64_t>(b) * heads + h) * T + tok0) * R;
+    for (int i = threadIdx.x; i < ntok * R; i += blockDim.x) {
+      const int tl = i / R, r = i - tl * R;
+      stile[tl * (R + 1) + r] = __ldg(src + i);
+    }
+  }
   __syncthreads();
-  int tok = blockIdx.x * blockDim.x + threadIdx.x;
   if (tok >= T) return;
-  const float* row = a + ((static_cast<int64_t>(b) * heads + h) * T + tok) * R;
+  const float* row = stile + threadIdx.x * (R + 1);
   float mx = -INFINITY;
   for (int r = 0; r < R; ++r) mx = fmaxf(mx, row[r]);
   float acc[32];
@@ -565,9 +591,23 @@ __global__ void __launch_bounds__(128) gwd_ref_requery_kernel(const float* __res
   }
   float inv = scale / sum;
   bf16* o = out + (static_cast<int64_t>(b) * T + tok) * o_rs + h * hd;
+  if ((hd & 7) == 0 && (reinterpret_cast<uintptr_t>(o) & 15) == 0) {
 #pragma unroll
-  for (int dd = 0; dd < 32; dd += 2)
-    if (dd < hd) *reinterpret_cast<uint32_t*>(o + dd) = gwd_pack_bf16x2(acc[dd] * inv, acc[dd + 1] * inv);
+    for (int w = 0; w < 4; ++w) {
+      if (8 * w < hd) {
+        uint4 u;
+        u.x = gwd_pack_bf16x2(acc[8 * w + 0] * inv, acc[8 * w + 1] * inv);
+        u.y = gwd_pack_bf16x2(acc[8 * w + 2] * inv, acc[8 * w + 3] * inv);
+        u.z = gwd_pack_bf16x2(acc[8 * w + 4] * inv, acc[8 * w + 5] * inv);
+        u.w = gwd_pack_bf16x2(acc[8 * w + 6] * inv, acc[8 * w + 7] * inv);
+        reinterpret_cast<uint4*>(o)[w] = u;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int dd = 0; dd < 32; dd += 2)
+      if (dd < hd) *reinterpret_cast<uint32_t*>(o + dd) = gwd_pack_bf16x2(acc[dd] * inv, acc[dd + 1] * inv);
+  }
 }
 
 }  // namespace
@@ -667,7 +707,7 @@ extern "C" int gwd_ref_scores(const void* q, int64_t q_rs, const float* refk, in
   GWD_CHECK_ARG(q && refk && out && hd <= 32 && hd % 2 == 0, "gwd_ref_scores: bad argument");
   const int T = nW * N;
   dim3 grid(static_cast<unsigned>(gwd_ceil_div(T, 128)), heads, B);
-  gwd_ref_scores_kernel<<<grid, 128, static_cast<size_t>(R) * hd * sizeof(float), stream>>>(
+  gwd_ref_scores_kernel<<<grid, 128, (static_cast<size_t>(R) * hd + 128 * (R + 1)) * sizeof(float), stream>>>(
       static_cast<const bf16*>(q), q_rs, refk, ref_rs, out, T, heads, hd, R, scale);
   GWD_LAUNCHED();
   return GWD_OK;
@@ -732,7 +772,7 @@ extern "C" int gwd_ref_requery(const float* a, const float* refv, int64_t ref_rs
   GWD_CHECK_ARG(a && refv && out && hd <= 32 && hd % 2 == 0 && o_rs % 2 == 0, "gwd_ref_requery: bad argument");
   const int T = nW * N;
   dim3 grid(static_cast<unsigned>(gwd_ceil_div(T, 128)), heads, B);
-  gwd_ref_requery_kernel<<<grid, 128, static_cast<size_t>(R) * hd * sizeof(float), stream>>>(
+  gwd_ref_requery_kernel<<<grid, 128, (static_cast<size_t>(R) * hd + 128 * (R + 1)) * sizeof(float), stream>>>(
       a, refv, ref_rs, static_cast<bf16*>(out), o_rs, T, heads, hd, R, scale);
   GWD_LAUNCHED();
   return GWD_OK;
