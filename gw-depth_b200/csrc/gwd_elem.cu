@@ -113,8 +113,14 @@ __device__ __forceinline__ void row_layernorm(WarpRow<NV>& r, int C, int n, cons
   for (int v = 0; v < NV; ++v) {
     int c = (v * g.G + g.sub) * 8;
     if (c < C) {
+      // gamma / beta as 16-byte loads (padded to the physical width by the callers), (x - mean) * rstd * g + b as 2 FMAs
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gam + c)), g1 = __ldg(reinterpret_cast<const float4*>(gam + c) + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(bet + c)), b1 = __ldg(reinterpret_cast<const float4*>(bet + c) + 1);
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const float shift = -mean * rstd;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) r.f[v][i] = (c + i < n) ? (r.f[v][i] - mean) * rstd * gam[c + i] + bet[c + i] : 0.f;
+      for (int i = 0; i < 8; ++i) r.f[v][i] = (c + i < n) ? fmaf(fmaf(r.f[v][i], rstd, shift), gg[i], bb[i]) : 0.f;
     }
   }
 }
@@ -242,13 +248,15 @@ __global__ void gwd_upsample_nearest_kernel(const bf16* x, int64_t x_rs, int B, 
                                             int H, int W, int C, const bf16* add, int64_t add_rs) {
   int cv = C / 8;
   int64_t total = static_cast<int64_t>(B) * H * W * cv;
-  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  // 32-bit index arithmetic (the host checks total < 2^31): 64-bit div / mod are ~100-instruction software routines
+  const int total32 = static_cast<int>(total), step = gridDim.x * blockDim.x;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total32; idx += step) {
     int c = (idx % cv) * 8;
-    int64_t pix = idx / cv;
-    int X = pix % W;
-    int Y = (pix / W) % H;
-    int b = pix / (static_cast<int64_t>(W) * H);
+    int pix32 = idx / cv;
+    int64_t pix = pix32;
+    int X = pix32 % W;
+    int Y = (pix32 / W) % H;
+    int b = pix32 / (W * H);
     int sy = min(static_cast<int>((static_cast<int64_t>(Y) * h) / H), h - 1);
     int sx = min(static_cast<int>((static_cast<int64_t>(X) * w) / W), w - 1);
     float f[8];
@@ -269,13 +277,15 @@ __global__ void gwd_avgpool_kernel(const bf16* x, int64_t x_rs, int B, int H, in
   int cv = C / 8;
   int oh = H / k, ow = W / k;
   int64_t total = static_cast<int64_t>(B) * oh * ow * cv;
-  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  // 32-bit index arithmetic (the host checks total < 2^31): 64-bit div / mod are ~100-instruction software routines
+  const int total32 = static_cast<int>(total), step = gridDim.x * blockDim.x;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total32; idx += step) {
     int c = (idx % cv) * 8;
-    int64_t pix = idx / cv;
-    int X = pix % ow;
-    int Y = (pix / ow) % oh;
-    int b = pix / (static_cast<int64_t>(ow) * oh);
+    int pix32 = idx / cv;
+    int64_t pix = pix32;
+    int X = pix32 % ow;
+    int Y = (pix32 / ow) % oh;
+    int b = pix32 / (ow * oh);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     for (int dy = 0; dy < k; ++dy)
       for (int dx = 0; dx < k; ++dx) {
@@ -298,13 +308,15 @@ __global__ void gwd_bilinear_ac_kernel(const bf16* x, int64_t x_rs, int B, int h
   int64_t total = static_cast<int64_t>(B) * H * W * cv;
   float ry = (H > 1) ? static_cast<float>(h - 1) / (H - 1) : 0.f;
   float rx = (W > 1) ? static_cast<float>(w - 1) / (W - 1) : 0.f;
-  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+  // 32-bit index arithmetic (the host checks total < 2^31): 64-bit div / mod are ~100-instruction software routines
+  const int total32 = static_cast<int>(total), step = gridDim.x * blockDim.x;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total32; idx += step) {
     int c = (idx % cv) * 8;
-    int64_t pix = idx / cv;
-    int X = pix % W;
-    int Y = (pix / W) % H;
-    int b = pix / (static_cast<int64_t>(W) * H);
+    int pix32 = idx / cv;
+    int64_t pix = pix32;
+    int X = pix32 % W;
+    int Y = (pix32 / W) % H;
+    int b = pix32 / (W * H);
     float fy = ry * Y, fx = rx * X;
     int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
     int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
@@ -557,6 +569,7 @@ extern "C" int gwd_upsample_nearest(const void* x, int64_t x_rs, int32_t B, int3
   GWD_CHECK_ARG(x && out && GWD_ALIGN8(C) && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs) && GWD_ALIGN8(add_rs),
                 "gwd_upsample_nearest: bad argument");
   int64_t total = static_cast<int64_t>(B) * H * W * (C / 8);
+  GWD_CHECK_ARG(total < (int64_t(1) << 31) - (int64_t(1) << 24), "gwd_upsample_nearest: more than 2^31 output vectors");
   gwd_upsample_nearest_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, h, w,
                                                                         static_cast<bf16*>(out), out_rs, H, W, C,
                                                                         static_cast<const bf16*>(add), add_rs);
@@ -570,6 +583,7 @@ extern "C" int gwd_avgpool(const void* x, int64_t x_rs, int32_t B, int32_t H, in
   GWD_CHECK_ARG(x && out && k > 0 && H >= k && W >= k && GWD_ALIGN8(C) && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs),
                 "gwd_avgpool: bad argument");
   int64_t total = static_cast<int64_t>(B) * (H / k) * (W / k) * (C / 8);
+  GWD_CHECK_ARG(total < (int64_t(1) << 31) - (int64_t(1) << 24), "gwd_avgpool: more than 2^31 output vectors");
   gwd_avgpool_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, H, W, k,
                                                                static_cast<bf16*>(out), out_rs, C);
   GWD_LAUNCHED();
@@ -581,6 +595,7 @@ extern "C" int gwd_bilinear_up(const void* x, int64_t x_rs, int32_t B, int32_t h
   GWD_STREAM;
   GWD_CHECK_ARG(x && out && GWD_ALIGN8(C) && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs), "gwd_bilinear_up: bad argument");
   int64_t total = static_cast<int64_t>(B) * H * W * (C / 8);
+  GWD_CHECK_ARG(total < (int64_t(1) << 31) - (int64_t(1) << 24), "gwd_bilinear_up: more than 2^31 output vectors");
   gwd_bilinear_ac_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, h, w,
                                                                    static_cast<bf16*>(out), out_rs, H, W, C);
   GWD_LAUNCHED();

@@ -245,9 +245,17 @@ def _rows(t):
     return t.numel() // t.shape[-1]
 
 
+def _padded_affine(gamma, beta, C):
+    """the row kernels read gamma / beta as 16-byte vectors over the physical width C (a multiple of 8)"""
+    if gamma is not None and gamma.numel() < C:
+        gamma, beta = pad_vec(gamma, C), pad_vec(beta, C)
+    return gamma, beta
+
+
 def layernorm(x, gamma=None, beta=None, *, res=None, act=ACT_NONE, out=None, n=None, eps=1e-5, C=None, x_coff=0):
     """rows of x[..., x_coff:x_coff+C] -> act(LN(x + res)) (contiguous [rows, C] unless `out` is given)"""
     C = C or x.shape[-1]
+    gamma, beta = _padded_affine(gamma, beta, C)
     rows = _rows(x)
     if out is None:
         out = torch.empty(tuple(x.shape[:-1]) + (C,), dtype=torch.bfloat16, device=x.device)
@@ -273,6 +281,7 @@ def window_gather(x, B, H, W, ws, shift, gamma=None, beta=None, n=None, eps=1e-5
     """x [B,H,W,Cx] (channels [x_coff, x_coff+C)) -> windows [B*nW*ws*ws, C] of the LayerNorm'ed, zero-padded,
     cyclically shifted map; optionally written into channels [y_coff, y_coff+C) of a wider `out`."""
     C = C or x.shape[-1]
+    gamma, beta = _padded_affine(gamma, beta, C)
     Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
     if out is None:
         out = torch.empty(B * Hp * Wp, C, dtype=torch.bfloat16, device=x.device)
@@ -286,6 +295,7 @@ def window_merge(win, shortcut, B, H, W, ws, shift, gamma=None, beta=None, n=Non
     """-> (shortcut + unwindowed(win[:, :C]), LN(of that) or None), both [B*H*W, C] contiguous.  win may be wider than C
     (row stride = win.shape[-1]); shortcut may be a channel slice [sc_coff, sc_coff+C) of a wider buffer."""
     C = C or shortcut.shape[-1]
+    gamma, beta = _padded_affine(gamma, beta, C)
     rows = B * H * W
     out = torch.empty(rows, C, dtype=torch.bfloat16, device=win.device)
     out_ln = torch.empty(rows, C, dtype=torch.bfloat16, device=win.device) if want_ln else None
