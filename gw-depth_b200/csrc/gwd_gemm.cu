@@ -737,6 +737,16 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
     ++n_tiles;
     GWD_CHECK_ARG(n_tiles <= d->n_pad, "gwd_conv_gemm: cannot tile n_pad=%d", d->n_pad);
   }
+  // Small problems (a few M tiles, e.g. the 1 600- and 4 800-row Linears of the DETR transformer): every CTA streams its
+  // whole [Nt x K] weight slab through one SM (~100 GB/s), so narrower N tiles on more SMs cut the time almost
+  // linearly.  Split until about half the SMs have a tile (LayerNorm / fused up-sampling epilogues need the whole row).
+  if (d->ln_g == nullptr && !d->upsample2 && !d->w_per_image && d->taps == 1) {
+    const int64_t m_tiles_est = gwd_ceil_div(static_cast<int64_t>(d->B) * d->H * d->W, kTileM);
+    static const bool split_enabled = []() { const char* e = getenv("GWD_GEMM_NSPLIT"); return !(e && e[0] == '0'); }();
+    while (split_enabled && m_tiles_est * n_tiles * 2 <= gwd_num_sms() && (d->n_pad / n_tiles) % 2 == 0 &&
+           ((d->n_pad / n_tiles) / 2) % 16 == 0 && (d->n_pad / n_tiles) / 2 >= 64)
+      n_tiles *= 2;
+  }
   p.n_tiles = n_tiles;
   p.Nt = d->n_pad / n_tiles;
   GWD_CHECK_ARG(d->ln_g == nullptr || n_tiles == 1, "gwd_conv_gemm: LayerNorm epilogue needs n_pad <= 256");
