@@ -246,92 +246,76 @@ __global__ void gwd_window_merge_kernel(const bf16* win, int64_t win_rs, const b
 // nearest (legacy F.interpolate(mode='nearest'): src = floor(dst * in / out)); optional add of a second same-size map
 __global__ void gwd_upsample_nearest_kernel(const bf16* x, int64_t x_rs, int B, int h, int w, bf16* out, int64_t out_rs,
                                             int H, int W, int C, const bf16* add, int64_t add_rs) {
-  int cv = C / 8;
-  int64_t total = static_cast<int64_t>(B) * H * W * cv;
-  // 32-bit index arithmetic (the host checks total < 2^31): 64-bit div / mod are ~100-instruction software routines
-  const int total32 = static_cast<int>(total), step = gridDim.x * blockDim.x;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total32; idx += step) {
-    int c = (idx % cv) * 8;
-    int pix32 = idx / cv;
-    int64_t pix = pix32;
-    int X = pix32 % W;
-    int Y = (pix32 / W) % H;
-    int b = pix32 / (W * H);
-    int sy = min(static_cast<int>((static_cast<int64_t>(Y) * h) / H), h - 1);
-    int sx = min(static_cast<int>((static_cast<int64_t>(X) * w) / W), w - 1);
-    float f[8];
-    load8(x + ((static_cast<int64_t>(b) * h + sy) * w + sx) * x_rs + c, f);
-    if (add) {
-      float t[8];
-      load8(add + pix * add_rs + c, t);
+  // grid (vectors of one output row, rows, images): one division per thread (64-bit div / mod chains made these
+  // resampling kernels instruction bound)
+  const int cv = C / 8;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= W * cv) return;
+  const int X = t / cv, c = (t - X * cv) * 8;
+  const int Y = blockIdx.y, b = blockIdx.z;
+  const int64_t pix = (static_cast<int64_t>(b) * H + Y) * W + X;
+  int sy = min(static_cast<int>((static_cast<int64_t>(Y) * h) / H), h - 1);
+  int sx = min(static_cast<int>((static_cast<int64_t>(X) * w) / W), w - 1);
+  float f[8];
+  load8(x + ((static_cast<int64_t>(b) * h + sy) * w + sx) * x_rs + c, f);
+  if (add) {
+    float u[8];
+    load8(add + pix * add_rs + c, u);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) f[i] += t[i];
-    }
-    store8(out + pix * out_rs + c, f);
+    for (int i = 0; i < 8; ++i) f[i] += u[i];
   }
+  store8(out + pix * out_rs + c, f);
 }
 
 // nn.AvgPool2d(k, stride=k), floor mode
 __global__ void gwd_avgpool_kernel(const bf16* x, int64_t x_rs, int B, int H, int W, int k, bf16* out, int64_t out_rs,
                                    int C) {
-  int cv = C / 8;
-  int oh = H / k, ow = W / k;
-  int64_t total = static_cast<int64_t>(B) * oh * ow * cv;
-  // 32-bit index arithmetic (the host checks total < 2^31): 64-bit div / mod are ~100-instruction software routines
-  const int total32 = static_cast<int>(total), step = gridDim.x * blockDim.x;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total32; idx += step) {
-    int c = (idx % cv) * 8;
-    int pix32 = idx / cv;
-    int64_t pix = pix32;
-    int X = pix32 % ow;
-    int Y = (pix32 / ow) % oh;
-    int b = pix32 / (ow * oh);
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int dy = 0; dy < k; ++dy)
-      for (int dx = 0; dx < k; ++dx) {
-        float f[8];
-        load8(x + ((static_cast<int64_t>(b) * H + Y * k + dy) * W + X * k + dx) * x_rs + c, f);
+  const int cv = C / 8;
+  const int oh = H / k, ow = W / k;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ow * cv) return;
+  const int X = t / cv, c = (t - X * cv) * 8;
+  const int Y = blockIdx.y, b = blockIdx.z;
+  const int64_t pix = (static_cast<int64_t>(b) * oh + Y) * ow + X;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int dy = 0; dy < k; ++dy)
+    for (int dx = 0; dx < k; ++dx) {
+      float f[8];
+      load8(x + ((static_cast<int64_t>(b) * H + Y * k + dy) * W + X * k + dx) * x_rs + c, f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) acc[i] += f[i];
-      }
-    float inv = 1.f / (k * k);
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+  float inv = 1.f / (k * k);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] *= inv;
-    store8(out + pix * out_rs + c, acc);
-  }
+  for (int i = 0; i < 8; ++i) acc[i] *= inv;
+  store8(out + pix * out_rs + c, acc);
 }
 
 // F.interpolate(mode='bilinear', align_corners=True)
 __global__ void gwd_bilinear_ac_kernel(const bf16* x, int64_t x_rs, int B, int h, int w, bf16* out, int64_t out_rs, int H,
                                        int W, int C) {
-  int cv = C / 8;
-  int64_t total = static_cast<int64_t>(B) * H * W * cv;
+  const int cv = C / 8;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= W * cv) return;
+  const int X = t / cv, c = (t - X * cv) * 8;
+  const int Y = blockIdx.y, b = blockIdx.z;
+  const int64_t pix = (static_cast<int64_t>(b) * H + Y) * W + X;
   float ry = (H > 1) ? static_cast<float>(h - 1) / (H - 1) : 0.f;
   float rx = (W > 1) ? static_cast<float>(w - 1) / (W - 1) : 0.f;
-  // 32-bit index arithmetic (the host checks total < 2^31): 64-bit div / mod are ~100-instruction software routines
-  const int total32 = static_cast<int>(total), step = gridDim.x * blockDim.x;
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total32; idx += step) {
-    int c = (idx % cv) * 8;
-    int pix32 = idx / cv;
-    int64_t pix = pix32;
-    int X = pix32 % W;
-    int Y = (pix32 / W) % H;
-    int b = pix32 / (W * H);
-    float fy = ry * Y, fx = rx * X;
-    int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
-    int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
-    float ly = fy - y0, lx = fx - x0;
-    const bf16* base = x + static_cast<int64_t>(b) * h * w * x_rs + c;
-    float f00[8], f01[8], f10[8], f11[8], o[8];
-    load8(base + (static_cast<int64_t>(y0) * w + x0) * x_rs, f00);
-    load8(base + (static_cast<int64_t>(y0) * w + x1) * x_rs, f01);
-    load8(base + (static_cast<int64_t>(y1) * w + x0) * x_rs, f10);
-    load8(base + (static_cast<int64_t>(y1) * w + x1) * x_rs, f11);
+  float fy = ry * Y, fx = rx * X;
+  int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  float ly = fy - y0, lx = fx - x0;
+  const bf16* base = x + static_cast<int64_t>(b) * h * w * x_rs + c;
+  float f00[8], f01[8], f10[8], f11[8], o[8];
+  load8(base + (static_cast<int64_t>(y0) * w + x0) * x_rs, f00);
+  load8(base + (static_cast<int64_t>(y0) * w + x1) * x_rs, f01);
+  load8(base + (static_cast<int64_t>(y1) * w + x0) * x_rs, f10);
+  load8(base + (static_cast<int64_t>(y1) * w + x1) * x_rs, f11);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
-      o[i] = (1.f - ly) * ((1.f - lx) * f00[i] + lx * f01[i]) + ly * ((1.f - lx) * f10[i] + lx * f11[i]);
-    store8(out + pix * out_rs + c, o);
-  }
+  for (int i = 0; i < 8; ++i)
+    o[i] = (1.f - ly) * ((1.f - lx) * f00[i] + lx * f01[i]) + ly * ((1.f - lx) * f10[i] + lx * f11[i]);
+  store8(out + pix * out_rs + c, o);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -569,8 +553,8 @@ extern "C" int gwd_upsample_nearest(const void* x, int64_t x_rs, int32_t B, int3
   GWD_CHECK_ARG(x && out && GWD_ALIGN8(C) && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs) && GWD_ALIGN8(add_rs),
                 "gwd_upsample_nearest: bad argument");
   int64_t total = static_cast<int64_t>(B) * H * W * (C / 8);
-  GWD_CHECK_ARG(total < (int64_t(1) << 31) - (int64_t(1) << 24), "gwd_upsample_nearest: more than 2^31 output vectors");
-  gwd_upsample_nearest_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, h, w,
+  GWD_CHECK_ARG(total > 0 && H <= 65535 && B <= 65535, "gwd_upsample_nearest: bad extents");
+  gwd_upsample_nearest_kernel<<<dim3(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(W) * (C / 8), 256)), H, B), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, h, w,
                                                                         static_cast<bf16*>(out), out_rs, H, W, C,
                                                                         static_cast<const bf16*>(add), add_rs);
   GWD_LAUNCHED();
@@ -583,8 +567,8 @@ extern "C" int gwd_avgpool(const void* x, int64_t x_rs, int32_t B, int32_t H, in
   GWD_CHECK_ARG(x && out && k > 0 && H >= k && W >= k && GWD_ALIGN8(C) && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs),
                 "gwd_avgpool: bad argument");
   int64_t total = static_cast<int64_t>(B) * (H / k) * (W / k) * (C / 8);
-  GWD_CHECK_ARG(total < (int64_t(1) << 31) - (int64_t(1) << 24), "gwd_avgpool: more than 2^31 output vectors");
-  gwd_avgpool_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, H, W, k,
+  GWD_CHECK_ARG(total > 0 && H / k <= 65535 && B <= 65535, "gwd_avgpool: bad extents");
+  gwd_avgpool_kernel<<<dim3(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(W / k) * (C / 8), 256)), H / k, B), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, H, W, k,
                                                                static_cast<bf16*>(out), out_rs, C);
   GWD_LAUNCHED();
   return GWD_OK;
@@ -595,8 +579,8 @@ extern "C" int gwd_bilinear_up(const void* x, int64_t x_rs, int32_t B, int32_t h
   GWD_STREAM;
   GWD_CHECK_ARG(x && out && GWD_ALIGN8(C) && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs), "gwd_bilinear_up: bad argument");
   int64_t total = static_cast<int64_t>(B) * H * W * (C / 8);
-  GWD_CHECK_ARG(total < (int64_t(1) << 31) - (int64_t(1) << 24), "gwd_bilinear_up: more than 2^31 output vectors");
-  gwd_bilinear_ac_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, h, w,
+  GWD_CHECK_ARG(total > 0 && H <= 65535 && B <= 65535, "gwd_bilinear_up: bad extents");
+  gwd_bilinear_ac_kernel<<<dim3(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(W) * (C / 8), 256)), H, B), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, h, w,
                                                                    static_cast<bf16*>(out), out_rs, H, W, C);
   GWD_LAUNCHED();
   return GWD_OK;
