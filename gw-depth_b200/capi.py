@@ -47,6 +47,20 @@ class AttnDesc(ctypes.Structure):
     ]
 
 
+class AttnBwdDesc(ctypes.Structure):
+    """struct gwd_attn_bwd_desc (include/gwd_b200.h)"""
+    _fields_ = [
+        ("q", c_void_p), ("k", c_void_p), ("v", c_void_p), ("d_o", c_void_p),
+        ("dq", c_void_p), ("dk", c_void_p), ("dv", c_void_p),
+        ("items", c_int), ("heads", c_int), ("Lq", c_int), ("Lk", c_int), ("hd", c_int),
+        ("q_item_stride", c_i64), ("q_row_stride", c_i64), ("k_item_stride", c_i64), ("k_row_stride", c_i64),
+        ("v_item_stride", c_i64), ("v_row_stride", c_i64), ("do_item_stride", c_i64), ("do_row_stride", c_i64),
+        ("dq_item_stride", c_i64), ("dq_row_stride", c_i64), ("dk_item_stride", c_i64), ("dk_row_stride", c_i64),
+        ("dv_item_stride", c_i64), ("dv_row_stride", c_i64),
+        ("scale", c_float),
+    ]
+
+
 P, I, L, F_ = c_void_p, c_int, c_i64, c_float
 # name -> (restype, argtypes); must list every symbol of include/gwd_b200.h
 SIGNATURES = {
@@ -77,6 +91,12 @@ SIGNATURES = {
     "gwd_match_cost": (c_int, [P, P, P, P, P, I, I, I, I, F_, F_, P, P, P]),
     "gwd_depth_metrics": (c_int, [P, P, I, L, F_, F_, P, P, P]),
     "gwd_silog_sums": (c_int, [P, I, I, I, P, I, I, F_, F_, I, P, P]),
+    "gwd_layernorm_bwd": (c_int, [P, L, P, L, P, F_, P, L, P, L, P, P, L, I, P]),
+    "gwd_act_bwd": (c_int, [P, I, L, P, I, L, I, P, L, L, I, I, P]),
+    "gwd_transpose": (c_int, [P, L, P, L, L, L, I, P, P]),
+    "gwd_attention_bwd": (c_int, [ctypes.POINTER(AttnBwdDesc), P]),
+    "gwd_sumsq": (c_int, [P, L, P, P]),
+    "gwd_adamw_step": (c_int, [P, P, P, P, P, L, F_, F_, F_, F_, F_, I, F_, F_, P, P]),
 }
 
 _lib = None

@@ -1,0 +1,526 @@
+// gwd_train.cu -- backward and optimizer kernels of the line branch (DETR encoder / decoder, line heads):
+//   gwd_layernorm_bwd   : dz, dgamma, dbeta of y = LN(z)                         (HBM bound, warp per row)
+//   gwd_act_bwd         : dy * act'(y) for ReLU / sigmoid from the OUTPUT, with dtype conversion + channel padding
+//   gwd_transpose       : bf16 [rows, C] -> [C, rows_pad] (+ fp32 column sums = bias gradients); the weight-gradient
+//                         GEMMs dW = dY^T X then run on gwd_conv_gemm with dY^T as the row operand and X^T as the filter
+//   gwd_attention_bwd   : dQ, dK, dV of O = softmax(scale Q K^T) V, soft-max recomputed (two passes, no atomics)
+//   gwd_sumsq / gwd_adamw_step : global gradient norm and fused clip + AdamW over a flat parameter segment, writing
+//                         the bf16 mirror the forward kernels read
+// Data-gradient GEMMs dX = dY W run on gwd_conv_gemm with the transposed weight mirror.
+#include <algorithm>
+#include <math.h>
+#include "gwd_common.cuh"
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+__device__ __forceinline__ void ld8(const bf16* p, float (&f)[8]) {
+  uint4 u = *reinterpret_cast<const uint4*>(p);
+  float2 a = gwd_unpack_bf16x2(u.x), b = gwd_unpack_bf16x2(u.y), c = gwd_unpack_bf16x2(u.z), d = gwd_unpack_bf16x2(u.w);
+  f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+}
+__device__ __forceinline__ void st8(bf16* p, const float (&f)[8]) {
+  uint4 u;
+  u.x = gwd_pack_bf16x2(f[0], f[1]); u.y = gwd_pack_bf16x2(f[2], f[3]);
+  u.z = gwd_pack_bf16x2(f[4], f[5]); u.w = gwd_pack_bf16x2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = u;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm backward.  y = (z - mean) * rstd * gamma + beta over C channels (biased variance), so with
+// xh = (z - mean) * rstd and g = dy * gamma:   dz = rstd * (g - mean(g) - xh * mean(g * xh)),
+// dgamma = sum_rows dy * xh, dbeta = sum_rows dy.  A warp owns a row (lane l holds the 16-byte vectors l, l+32, ...),
+// keeps the column partial sums of all its rows in registers, the 8 warps of a CTA combine them in shared memory and
+// one atomicAdd per column and CTA reaches HBM.
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnWarps = 8;
+
+template <int NV>
+__global__ void __launch_bounds__(kLnWarps * 32)
+gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16* __restrict__ z, int64_t z_rs,
+                         const float* __restrict__ gamma, float eps, const bf16* __restrict__ add, int64_t add_rs,
+                         bf16* __restrict__ dz, int64_t dz_rs, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                         int64_t rows, int C) {
+  __shared__ float part[kLnWarps][NV * 256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t gwarp = static_cast<int64_t>(blockIdx.x) * kLnWarps + warp;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kLnWarps;
+  float ag[NV][8], ab[NV][8], gm[NV][8];
+  bool on[NV];
+#pragma unroll
+  for (int v = 0; v < NV; ++v) {
+    on[v] = (lane + 32 * v) * 8 < C;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      ag[v][e] = 0.f; ab[v][e] = 0.f;
+      gm[v][e] = on[v] ? gamma[(lane + 32 * v) * 8 + e] : 0.f;
+    }
+  }
+  const float invC = 1.f / static_cast<float>(C);
+  for (int64_t row = gwarp; row < rows; row += nwarps) {
+    float zv[NV][8], dv[NV][8];
+    float s = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (on[v]) {
+        ld8(z + row * z_rs + (lane + 32 * v) * 8, zv[v]);
+        ld8(dy + row * dy_rs + (lane + 32 * v) * 8, dv[v]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { zv[v][e] = 0.f; dv[v][e] = 0.f; }
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s += zv[v][e];
+    }
+    const float mean = gwd_warp_sum(s) * invC;
+    float q = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        zv[v][e] = on[v] ? zv[v][e] - mean : 0.f;
+        q += zv[v][e] * zv[v][e];
+      }
+    const float rstd = rsqrtf(gwd_warp_sum(q) * invC + eps);
+    float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        zv[v][e] *= rstd;                                  // xh
+        ag[v][e] += dv[v][e] * zv[v][e];
+        ab[v][e] += dv[v][e];
+        dv[v][e] *= gm[v][e];                              // g
+        m1 += dv[v][e];
+        m2 += dv[v][e] * zv[v][e];
+      }
+    m1 = gwd_warp_sum(m1) * invC;
+    m2 = gwd_warp_sum(m2) * invC;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      if (!on[v]) continue;
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = rstd * (dv[v][e] - m1 - zv[v][e] * m2);
+      if (add != nullptr) {
+        float a[8];
+        ld8(add + row * add_rs + (lane + 32 * v) * 8, a);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] += a[e];
+      }
+      st8(dz + row * dz_rs + (lane + 32 * v) * 8, o);
+    }
+  }
+  // column sums: warps -> shared memory -> one atomic per column and CTA
+#pragma unroll
+  for (int pass = 0; pass < 2; ++pass) {
+    float* dst = pass == 0 ? dgamma : dbeta;
+    if (dst == nullptr) continue;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) part[warp][(lane + 32 * v) * 8 + e] = pass == 0 ? ag[v][e] : ab[v][e];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += kLnWarps * 32) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < kLnWarps; ++w) t += part[w][c];
+      atomicAdd(dst + c, t);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// activation backward from the OUTPUT value: ReLU: dy * (y > 0); sigmoid: dy * y * (1 - y); none: dy.
+// Converts fp32 / bf16 inputs to a bf16 [rows, out_cols] matrix whose columns n..out_cols are zero.
+// ------------------------------------------------------------------------------------------------
+template <typename TD, typename TY>
+__global__ void gwd_act_bwd_kernel(const TD* __restrict__ dy, int64_t dy_rs, const TY* __restrict__ y, int64_t y_rs, int act,
+                                   bf16* __restrict__ out, int64_t out_rs, int64_t rows, int n, int out_cols) {
+  const int64_t total = rows * out_cols;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t r = i / out_cols;
+    const int c = static_cast<int>(i - r * out_cols);
+    float v = 0.f;
+    if (c < n) {
+      v = static_cast<float>(dy[r * dy_rs + c]);
+      if (act != GWD_ACT_NONE) {
+        const float yy = static_cast<float>(y[r * y_rs + c]);
+        v = act == GWD_ACT_RELU ? (yy > 0.f ? v : 0.f) : v * yy * (1.f - yy);
+      }
+    }
+    out[r * out_rs + c] = __float2bfloat16(v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// transpose (+ column sums).  64 x 64 tiles through shared memory, 4-byte accesses on both sides.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gwd_transpose_kernel(const bf16* __restrict__ x, int64_t x_rs, bf16* __restrict__ out, int64_t out_rs, int64_t rows,
+                     int64_t rows_pad, int C, float* __restrict__ colsum) {
+  __shared__ float tile[64][65];
+  const int64_t r0 = static_cast<int64_t>(blockIdx.x) * 64;
+  const int c0 = blockIdx.y * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 32 x 8
+  for (int rr = ty; rr < 64; rr += 8) {
+    const int64_t r = r0 + rr;
+    const int c = c0 + 2 * tx;
+    float2 v = make_float2(0.f, 0.f);
+    if (r < rows && c < C)     // C is even
+      v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + r * x_rs + c));
+    tile[rr][2 * tx] = v.x;
+    tile[rr][2 * tx + 1] = v.y;
+  }
+  __syncthreads();
+  if (colsum != nullptr && threadIdx.x < 64 && c0 + threadIdx.x < C) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int rr = 0; rr < 64; ++rr) s += tile[rr][threadIdx.x];
+    atomicAdd(colsum + c0 + threadIdx.x, s);
+  }
+  for (int cc = ty; cc < 64; cc += 8) {
+    const int c = c0 + cc;
+    const int64_t r = r0 + 2 * tx;
+    if (c < C && r < rows_pad)     // rows_pad is even
+      *reinterpret_cast<__nv_bfloat162*>(out + c * out_rs + r) = __floats2bfloat162_rn(tile[2 * tx][cc], tile[2 * tx + 1][cc]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// attention backward, head_dim 32.  One CTA per (head, item): Q, K, V, dO of the head sit in shared memory as bf16
+// rows of 17 words (conflict-free when lanes walk rows).  Pass A: a warp owns a query row, lanes own keys;
+// recomputes the soft-max row, stores its log-sum-exp and D = sum_j P_ij dP_ij, and forms dQ_i.  Pass B: a warp owns
+// a key row, lanes own queries; recomputes P and dS columns and forms dK_j, dV_j.  Cross-lane sums of the 32-wide
+// rows use a 31-shuffle reduce-scatter (lane l ends up with channel l).  No atomics: results are deterministic.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHD = 32, kRowW = 17, kBwdWarps = 8;
+
+struct AttnBwdParams {
+  const bf16 *q, *k, *v, *d_o;
+  bf16 *dq, *dk, *dv;
+  int Lq, Lk;
+  int64_t q_is, q_rs, k_is, k_rs, v_is, v_rs, do_is, do_rs, dq_is, dq_rs, dk_is, dk_rs, dv_is, dv_rs;
+  float scale;
+};
+
+__device__ __forceinline__ float reduce_scatter32(float (&acc)[32], int lane) {
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    const bool hi = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < o; ++i) {
+      const float send = hi ? acc[i] : acc[i + o];
+      const float keep = hi ? acc[i + o] : acc[i];
+      acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+  }
+  return acc[0];
+}
+
+__device__ __forceinline__ void load_row_bcast(const uint32_t* row, float (&f)[32]) {
+#pragma unroll
+  for (int w = 0; w < 16; ++w) {
+    float2 t = gwd_unpack_bf16x2(row[w]);
+    f[2 * w] = t.x; f[2 * w + 1] = t.y;
+  }
+}
+
+__device__ __forceinline__ void stage_rows(uint32_t* dst, const bf16* src, int64_t rs, int L) {
+  // each row: 32 bf16 = 16 words; 16 threads per row, 4-byte loads (row starts are only 4-byte aligned in general)
+  for (int i = threadIdx.x; i < L * 16; i += blockDim.x) {
+    const int r = i >> 4, w = i & 15;
+    dst[r * kRowW + w] = *reinterpret_cast<const uint32_t*>(src + r * rs + 2 * w);
+  }
+}
+
+template <int NJ>
+__global__ void __launch_bounds__(kBwdWarps * 32)
+gwd_attention_bwd_kernel(AttnBwdParams p) {
+  extern __shared__ uint32_t smem[];
+  const int head = blockIdx.x, item = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t* sQ = smem;
+  uint32_t* sK = sQ + p.Lq * kRowW;
+  uint32_t* sV = sK + p.Lk * kRowW;
+  uint32_t* sO = sV + p.Lk * kRowW;
+  float* sLse = reinterpret_cast<float*>(sO + p.Lq * kRowW);
+  float* sD = sLse + p.Lq;
+  const int64_t hoff = static_cast<int64_t>(head) * kHD;
+  stage_rows(sQ, p.q + item * p.q_is + hoff, p.q_rs, p.Lq);
+  stage_rows(sK, p.k + item * p.k_is + hoff, p.k_rs, p.Lk);
+  stage_rows(sV, p.v + item * p.v_is + hoff, p.v_rs, p.Lk);
+  stage_rows(sO, p.d_o + item * p.do_is + hoff, p.do_rs, p.Lq);
+  __syncthreads();
+
+  // ---- pass A: soft-max statistics and dQ
+  for (int i = warp; i < p.Lq; i += kBwdWarps) {
+    float qf[32], of[32];
+    load_row_bcast(sQ + i * kRowW, qf);
+    load_row_bcast(sO + i * kRowW, of);
+    float s[NJ], dp[NJ];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int j = jj * 32 + lane;
+      s[jj] = -INFINITY; dp[jj] = 0.f;
+      if (j < p.Lk) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+          const float2 kk = gwd_unpack_bf16x2(sK[j * kRowW + w]);
+          const float2 vv = gwd_unpack_bf16x2(sV[j * kRowW + w]);
+          a = fmaf(qf[2 * w], kk.x, a); a = fmaf(qf[2 * w + 1], kk.y, a);
+          b = fmaf(of[2 * w], vv.x, b); b = fmaf(of[2 * w + 1], vv.y, b);
+        }
+        s[jj] = a * p.scale; dp[jj] = b;
+        mx = fmaxf(mx, s[jj]);
+      }
+    }
+    mx = gwd_warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) sum += (jj * 32 + lane < p.Lk) ? __expf(s[jj] - mx) : 0.f;
+    sum = gwd_warp_sum(sum);
+    const float lse = mx + __logf(sum);
+    float D = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      s[jj] = (jj * 32 + lane < p.Lk) ? __expf(s[jj] - lse) : 0.f;     // P_ij
+      D = fmaf(s[jj], dp[jj], D);
+    }
+    D = gwd_warp_sum(D);
+    if (lane == 0) { sLse[i] = lse; sD[i] = D; }
+    float acc[32];
+#pragma unroll
+    for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+      const int j = jj * 32 + lane;
+      if (j < p.Lk) {
+        const float ds = s[jj] * (dp[jj] - D);
+#pragma unroll
+        for (int w = 0; w < 16; ++w) {
+          const float2 kk = gwd_unpack_bf16x2(sK[j * kRowW + w]);
+          acc[2 * w] = fmaf(ds, kk.x, acc[2 * w]);
+          acc[2 * w + 1] = fmaf(ds, kk.y, acc[2 * w + 1]);
+        }
+      }
+    }
+    const float r = reduce_scatter32(acc, lane) * p.scale;
+    p.dq[item * p.dq_is + i * p.dq_rs + hoff + lane] = __float2bfloat16(r);
+  }
+  __syncthreads();
+
+  // ---- pass B: dK and dV
+  for (int j = warp; j < p.Lk; j += kBwdWarps) {
+    float kf[32], vf[32], ak[32], av[32];
+    load_row_bcast(sK + j * kRowW, kf);
+    load_row_bcast(sV + j * kRowW, vf);
+#pragma unroll
+    for (int d = 0; d < 32; ++d) { ak[d] = 0.f; av[d] = 0.f; }
+    for (int i = lane; i < p.Lq; i += 32) {
+      float qr[32];
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < 16; ++w) {
+        const float2 qq = gwd_unpack_bf16x2(sQ[i * kRowW + w]);
+        qr[2 * w] = qq.x; qr[2 * w + 1] = qq.y;
+        a = fmaf(qq.x, kf[2 * w], a); a = fmaf(qq.y, kf[2 * w + 1], a);
+      }
+      const float pij = __expf(a * p.scale - sLse[i]);
+      float b = 0.f;
+#pragma unroll
+      for (int w = 0; w < 16; ++w) {
+        const float2 oo = gwd_unpack_bf16x2(sO[i * kRowW + w]);
+        b = fmaf(oo.x, vf[2 * w], b); b = fmaf(oo.y, vf[2 * w + 1], b);
+        av[2 * w] = fmaf(pij, oo.x, av[2 * w]);
+        av[2 * w + 1] = fmaf(pij, oo.y, av[2 * w + 1]);
+      }
+      const float ds = pij * (b - sD[i]);
+#pragma unroll
+      for (int d = 0; d < 32; ++d) ak[d] = fmaf(ds, qr[d], ak[d]);
+    }
+    const float rk = reduce_scatter32(ak, lane) * p.scale;
+    const float rv = reduce_scatter32(av, lane);
+    p.dk[item * p.dk_is + j * p.dk_rs + hoff + lane] = __float2bfloat16(rk);
+    p.dv[item * p.dv_is + j * p.dv_rs + hoff + lane] = __float2bfloat16(rv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// optimizer
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gwd_sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+  double acc = 0.0;
+  const int64_t n4 = n >> 2;
+  const float4* g4 = reinterpret_cast<const float4*>(g);
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 v = g4[i];
+    acc += static_cast<double>(v.x * v.x + v.y * v.y) + static_cast<double>(v.z * v.z + v.w * v.w);
+  }
+  for (int64_t i = (n4 << 2) + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride)
+    acc += static_cast<double>(g[i]) * g[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  __shared__ double part[8];
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += part[w];
+    atomicAdd(out, t);
+  }
+}
+
+struct AdamParams {
+  float lr, beta1, beta2, eps, wd, bc1, bc2_sqrt, max_norm, grad_scale;
+};
+
+// torch.optim.AdamW (decoupled weight decay, no amsgrad) after torch.nn.utils.clip_grad_norm_:
+//   g <- g * grad_scale * min(1, max_norm / (||g * grad_scale|| + 1e-6));  p <- p (1 - lr wd);
+//   m <- b1 m + (1-b1) g;  v <- b2 v + (1-b2) g^2;  p <- p - (lr / bc1) m / (sqrt(v) / sqrt(bc2) + eps)
+__global__ void __launch_bounds__(256)
+gwd_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 bf16* __restrict__ mirror, int64_t n, AdamParams a, const double* __restrict__ sumsq) {
+  float gs = a.grad_scale;
+  if (a.max_norm > 0.f && sumsq != nullptr) {
+    const float total = static_cast<float>(sqrt(*sumsq)) * a.grad_scale;
+    gs *= fminf(1.f, a.max_norm / (total + 1e-6f));
+  }
+  const float step = a.lr / a.bc1;
+  const float decay = 1.f - a.lr * a.wd;
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    const float gi = g[i] * gs;
+    const float mi = a.beta1 * m[i] + (1.f - a.beta1) * gi;
+    const float vi = a.beta2 * v[i] + (1.f - a.beta2) * gi * gi;
+    const float pi = p[i] * decay - step * (mi / (sqrtf(vi) / a.bc2_sqrt + a.eps));
+    m[i] = mi; v[i] = vi; p[i] = pi;
+    if (mirror != nullptr) mirror[i] = __float2bfloat16(pi);
+  }
+}
+
+}  // namespace
+
+#define GWD_STREAM cudaStream_t stream = static_cast<cudaStream_t>(stream_)
+
+extern "C" int gwd_layernorm_bwd(const void* dy, int64_t dy_rs, const void* z, int64_t z_rs, const float* gamma, float eps,
+                                 const void* add, int64_t add_rs, void* dz, int64_t dz_rs, float* dgamma, float* dbeta,
+                                 int64_t rows, int32_t C, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(dy && z && gamma && dz && rows > 0, "gwd_layernorm_bwd: null pointer / empty");
+  GWD_CHECK_ARG(C % 8 == 0 && C > 0 && C <= 512 && dy_rs % 8 == 0 && z_rs % 8 == 0 && dz_rs % 8 == 0 && add_rs % 8 == 0,
+                "gwd_layernorm_bwd: C and strides must be multiples of 8, C <= 512");
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(rows, kLnWarps * 2), 4 * gwd_num_sms()));
+  auto launch = [&](auto kern) {
+    kern<<<grid, kLnWarps * 32, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, static_cast<const bf16*>(z), z_rs, gamma, eps,
+                                             static_cast<const bf16*>(add), add_rs, static_cast<bf16*>(dz), dz_rs, dgamma,
+                                             dbeta, rows, C);
+  };
+  if (C <= 256) launch(gwd_layernorm_bwd_kernel<1>);
+  else launch(gwd_layernorm_bwd_kernel<2>);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_act_bwd(const void* dy, int32_t dy_f32, int64_t dy_rs, const void* y, int32_t y_f32, int64_t y_rs,
+                           int32_t act, void* out, int64_t out_rs, int64_t rows, int32_t n, int32_t out_cols, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(dy && out && rows > 0 && n > 0 && out_cols >= n && out_rs >= out_cols, "gwd_act_bwd: bad argument");
+  GWD_CHECK_ARG(act == GWD_ACT_NONE || act == GWD_ACT_RELU || act == GWD_ACT_SIGMOID, "gwd_act_bwd: activation %d unsupported", act);
+  GWD_CHECK_ARG(act == GWD_ACT_NONE || y != nullptr, "gwd_act_bwd: y needed");
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(rows * out_cols, 256), 8 * gwd_num_sms()));
+  bf16* o = static_cast<bf16*>(out);
+  if (dy_f32 && y_f32)
+    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(dy), dy_rs, static_cast<const float*>(y), y_rs, act, o, out_rs, rows, n, out_cols);
+  else if (dy_f32)
+    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(dy), dy_rs, static_cast<const bf16*>(y), y_rs, act, o, out_rs, rows, n, out_cols);
+  else if (y_f32)
+    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, static_cast<const float*>(y), y_rs, act, o, out_rs, rows, n, out_cols);
+  else
+    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, static_cast<const bf16*>(y), y_rs, act, o, out_rs, rows, n, out_cols);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_transpose(const void* x, int64_t x_rs, void* out, int64_t out_rs, int64_t rows, int64_t rows_pad, int32_t C,
+                             float* colsum, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(x && out && rows > 0 && C > 0 && rows_pad >= rows && out_rs >= rows_pad, "gwd_transpose: bad argument");
+  GWD_CHECK_ARG(C % 2 == 0 && x_rs % 2 == 0 && rows_pad % 2 == 0 && out_rs % 2 == 0 &&
+                    (reinterpret_cast<uintptr_t>(x) & 3) == 0 && (reinterpret_cast<uintptr_t>(out) & 3) == 0,
+                "gwd_transpose: even sizes / 4-byte alignment needed");
+  dim3 grid(static_cast<unsigned>(gwd_ceil_div(rows_pad, 64)), static_cast<unsigned>(gwd_ceil_div(C, 64)));
+  gwd_transpose_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, static_cast<bf16*>(out), out_rs, rows,
+                                                 rows_pad, C, colsum);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_attention_bwd(const gwd_attn_bwd_desc* d, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(d && d->q && d->k && d->v && d->d_o && d->dq && d->dk && d->dv, "gwd_attention_bwd: null pointer");
+  GWD_CHECK_ARG(d->hd == kHD, "gwd_attention_bwd: head dim must be 32 (got %d)", d->hd);
+  GWD_CHECK_ARG(d->items > 0 && d->heads > 0 && d->Lq > 0 && d->Lk > 0 && d->Lk <= 512 && d->Lq <= 512,
+                "gwd_attention_bwd: 1 <= Lq, Lk <= 512");
+  const int64_t strides[14] = {d->q_item_stride, d->q_row_stride, d->k_item_stride, d->k_row_stride, d->v_item_stride,
+                               d->v_row_stride, d->do_item_stride, d->do_row_stride, d->dq_item_stride, d->dq_row_stride,
+                               d->dk_item_stride, d->dk_row_stride, d->dv_item_stride, d->dv_row_stride};
+  for (int i = 0; i < 14; ++i) GWD_CHECK_ARG(strides[i] % 2 == 0, "gwd_attention_bwd: strides must be even");
+  GWD_CHECK_ARG(((reinterpret_cast<uintptr_t>(d->q) | reinterpret_cast<uintptr_t>(d->k) | reinterpret_cast<uintptr_t>(d->v) |
+                  reinterpret_cast<uintptr_t>(d->d_o)) & 3) == 0, "gwd_attention_bwd: inputs must be 4-byte aligned");
+  AttnBwdParams p;
+  p.q = static_cast<const bf16*>(d->q); p.k = static_cast<const bf16*>(d->k); p.v = static_cast<const bf16*>(d->v);
+  p.d_o = static_cast<const bf16*>(d->d_o);
+  p.dq = static_cast<bf16*>(d->dq); p.dk = static_cast<bf16*>(d->dk); p.dv = static_cast<bf16*>(d->dv);
+  p.Lq = d->Lq; p.Lk = d->Lk;
+  p.q_is = strides[0]; p.q_rs = strides[1]; p.k_is = strides[2]; p.k_rs = strides[3]; p.v_is = strides[4]; p.v_rs = strides[5];
+  p.do_is = strides[6]; p.do_rs = strides[7]; p.dq_is = strides[8]; p.dq_rs = strides[9]; p.dk_is = strides[10];
+  p.dk_rs = strides[11]; p.dv_is = strides[12]; p.dv_rs = strides[13];
+  p.scale = d->scale;
+  const size_t smem = static_cast<size_t>(2 * d->Lq + 2 * d->Lk) * kRowW * 4 + static_cast<size_t>(2 * d->Lq) * 4;
+  dim3 grid(d->heads, d->items);
+  auto launch = [&](auto kern) -> int {
+    GWD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, kBwdWarps * 32, smem, stream>>>(p);
+    return GWD_OK;
+  };
+  int rc;
+  if (d->Lk <= 128) rc = launch(gwd_attention_bwd_kernel<4>);
+  else if (d->Lk <= 320) rc = launch(gwd_attention_bwd_kernel<10>);
+  else rc = launch(gwd_attention_bwd_kernel<16>);
+  if (rc != GWD_OK) return rc;
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_sumsq(const float* g, int64_t n, double* out_accum, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(g && out_accum && n > 0 && (reinterpret_cast<uintptr_t>(g) & 15) == 0, "gwd_sumsq: bad argument");
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(n, 256 * 16), 4 * gwd_num_sms()));
+  gwd_sumsq_kernel<<<grid, 256, 0, stream>>>(g, n, out_accum);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_adamw_step(float* p, const float* g, float* m, float* v, void* mirror_bf16, int64_t n, float lr, float beta1,
+                              float beta2, float eps, float weight_decay, int32_t step, float max_norm, float grad_scale,
+                              const double* sumsq, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "gwd_adamw_step: bad argument");
+  AdamParams a;
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
+  a.bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), step));
+  a.bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
+  a.max_norm = max_norm; a.grad_scale = grad_scale;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(n, 256 * 4), 8 * gwd_num_sms()));
+  gwd_adamw_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, static_cast<bf16*>(mirror_bf16), n, a, sumsq);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}

@@ -272,6 +272,37 @@ class HungarianMatcher_Line(nn.Module):
             result.append((torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)))
         return result
 
+    @torch.no_grad()
+    def forward_stacked(self, logits, lines, targets):
+        """All S decoder stages at once (the reference calls the matcher once per stage, src/models/glassrgbd.py:318,344):
+        logits [S,B,Q,C], lines [S,B,Q,D] -> list over stages of the per-image (idx_pred, idx_tgt) lists.  ONE
+        gwd_match_cost launch over S*B (stage, image) pairs, ONE device-to-host copy, then the S*B assignments."""
+        from scipy.optimize import linear_sum_assignment
+        S, B, Q = logits.shape[:3]
+        sizes = [len(v["lines"]) for v in targets]
+        tgt_lines = torch.cat([v["lines"] for v in targets]).float()
+        tgt_ids = torch.cat([v["labels"] for v in targets]).to(torch.int64)
+        total = sum(sizes)
+        offs = [0]
+        for _ in range(S):
+            for n in sizes:
+                offs.append(offs[-1] + n)
+        offsets = torch.tensor(offs, dtype=torch.int32).to(logits.device, non_blocking=True)
+        cost, _ = ops.match_cost(logits.float().reshape(S * B, Q, -1).contiguous(), lines.float().reshape(S * B, Q, -1).contiguous(),
+                                 tgt_lines.repeat(S, 1).contiguous(), tgt_ids.repeat(S).contiguous(), offsets,
+                                 float(self.cost_class), float(self.cost_line))
+        flat = cost.cpu().numpy()
+        result = []
+        for s in range(S):
+            stage = []
+            for b in range(B):
+                o = offs[s * B + b]
+                i, j = linear_sum_assignment(flat[o * Q:(o + sizes[b]) * Q].reshape(Q, sizes[b]))
+                stage.append((torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)))
+            result.append(stage)
+        assert offs[-1] == S * total
+        return result
+
 
 def build_matcher(args, type=None):
     return HungarianMatcher_Line(cost_class=args.set_cost_class, cost_line=args.set_cost_line)
@@ -319,6 +350,46 @@ class SetCriterion(nn.Module):
                  "POST_lines_labels": self.loss_lines_labels, "POST_lines": self.loss_lines}
         assert loss in table, f"do you really want to compute {loss} loss?"
         return table[loss](outputs, targets, num_items, **kw)
+
+    def forward_stacked(self, logits, lines, targets):
+        """SetCriterion.forward for all decoder stages at once: logits [S,B,Q,2], lines [S,B,Q,D] with the FINAL stage
+        last (the layout the line heads produce).  Same losses and key names as `forward` (stage S-1 -> "loss_ce",
+        "loss_line"; stage i < S-1 -> "_i"), computed with one stacked matching (HungarianMatcher_Line.forward_stacked),
+        one host-to-device copy of the assignment indices and a dozen batched torch ops instead of ~60 per stage."""
+        S, B, Q = logits.shape[:3]
+        dev = logits.device
+        indices = self.matcher.forward_stacked(logits, lines, targets)
+        n = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float, device=dev)
+        if _world_size() > 1:
+            torch.distributed.all_reduce(n)
+        num_items = torch.clamp(n / _world_size(), min=1)
+        sizes = [len(t["labels"]) for t in targets]
+        starts = [0]
+        for m in sizes:
+            starts.append(starts[-1] + m)
+        s_idx = torch.cat([torch.full_like(i, s) for s, stage in enumerate(indices) for i, _ in stage])
+        b_idx = torch.cat([torch.full_like(i, b) for stage in indices for b, (i, _) in enumerate(stage)])
+        q_idx = torch.cat([i for stage in indices for i, _ in stage])
+        t_idx = torch.cat([j + starts[b] for stage in indices for b, (_, j) in enumerate(stage)])
+        idx = torch.stack([s_idx, b_idx, q_idx, t_idx]).to(dev, non_blocking=True)
+        labels = torch.cat([t["labels"] for t in targets]).to(dev)
+        tgt_lines = torch.cat([t["lines"] for t in targets]).to(dev)
+        classes = torch.full((S, B, Q), self.num_classes, dtype=torch.int64, device=dev)
+        classes[idx[0], idx[1], idx[2]] = labels[idx[3]]
+        w = self.empty_weight.to(dev)[classes]
+        nll = -torch.log_softmax(logits, dim=-1).gather(-1, classes.unsqueeze(-1)).squeeze(-1)
+        loss_ce = (w * nll).sum((1, 2)) / w.sum((1, 2))
+        l1 = (lines[idx[0], idx[1], idx[2]] - tgt_lines[idx[3]]).abs().sum(-1)
+        loss_line = torch.zeros(S, dtype=l1.dtype, device=dev).index_add_(0, idx[0], l1) / num_items
+        losses = {}
+        for s in range(S):
+            suffix = "" if s == S - 1 else "_%d" % s
+            if "lines_labels" in self.losses:
+                losses["loss_ce" + suffix] = loss_ce[s]
+            if "lines" in self.losses:
+                losses["loss_line" + suffix] = loss_line[s]
+        self.last_indices = indices
+        return losses
 
     def forward(self, outputs, targets, origin_indices=None, depth_gt=None):
         plain = {k: v for k, v in outputs.items() if k != "aux_outputs"}

@@ -435,3 +435,71 @@ def silog_sums(pred, gt, lo=0.2, hi=10.0, log_only=False):
     capi.check(_L().gwd_silog_sums(_ptr(pred), B, h, w, _ptr(gt), H, W, lo, hi, 1 if log_only else 0, _ptr(sums),
                                    _stream()), "gwd_silog_sums")
     return sums
+
+
+# ------------------------------------------------------------------------------------------
+# training side of the line branch: backward + optimizer kernels (gwd_train.cu)
+# ------------------------------------------------------------------------------------------
+def layernorm_bwd(dy, z, gamma, dgamma, dbeta, add=None, eps=1e-5):
+    """dz (+ add) of y = LN(z); dgamma / dbeta (fp32 views, may be None) are accumulated"""
+    C = z.shape[-1]
+    rows = _rows(z)
+    dz = torch.empty(rows, C, dtype=torch.bfloat16, device=z.device)
+    capi.check(_L().gwd_layernorm_bwd(_ptr(dy), dy.shape[-1], _ptr(z), C, _ptr(gamma), eps, _ptr(add),
+                                      add.shape[-1] if add is not None else 0, _ptr(dz), C, _ptr(dgamma), _ptr(dbeta), rows, C,
+                                      _stream()), "gwd_layernorm_bwd")
+    return dz
+
+
+def act_bwd(dy, y, act, out_cols=None):
+    """bf16 [rows, out_cols] = dy * act'(y) evaluated from the output y (zeros in the padding columns)"""
+    n = dy.shape[-1]
+    rows = _rows(dy)
+    out_cols = out_cols or round_up(n, 8)
+    out = torch.empty(rows, out_cols, dtype=torch.bfloat16, device=dy.device)
+    capi.check(_L().gwd_act_bwd(_ptr(dy), int(dy.dtype == torch.float32), n, _ptr(y),
+                                int(y is not None and y.dtype == torch.float32), y.shape[-1] if y is not None else 0, act,
+                                _ptr(out), out_cols, rows, n, out_cols, _stream()), "gwd_act_bwd")
+    return out
+
+
+def transpose(x, colsum=None, C=None, x_coff=0, pad_to=64, out=None):
+    """bf16 [rows, Cx] (columns [x_coff, x_coff+C)) -> [C, round_up(rows, pad_to)] with zero padding columns;
+    colsum (fp32 [C] view) accumulates the column sums of x"""
+    rows, Cx = _rows(x), x.shape[-1]
+    C = C or Cx
+    rp = round_up(rows, pad_to)
+    if out is None:
+        out = torch.empty(C, rp, dtype=torch.bfloat16, device=x.device)
+    assert out.shape == (C, rp) and out.is_contiguous()
+    capi.check(_L().gwd_transpose(_off(x, x_coff), Cx, _ptr(out), rp, rows, rp, C, _ptr(colsum), _stream()), "gwd_transpose")
+    return out
+
+
+def attention_bwd(q, k, v, d_o, dq, dk, dv, *, items, heads, Lq, Lk, hd, q_strides, k_strides, v_strides, do_strides,
+                  dq_strides, dk_strides, dv_strides, scale=1.0):
+    d = capi.AttnBwdDesc()
+    d.q, d.k, d.v, d.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), d_o.data_ptr()
+    d.dq, d.dk, d.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    d.items, d.heads, d.Lq, d.Lk, d.hd = items, heads, Lq, Lk, hd
+    d.q_item_stride, d.q_row_stride = q_strides
+    d.k_item_stride, d.k_row_stride = k_strides
+    d.v_item_stride, d.v_row_stride = v_strides
+    d.do_item_stride, d.do_row_stride = do_strides
+    d.dq_item_stride, d.dq_row_stride = dq_strides
+    d.dk_item_stride, d.dk_row_stride = dk_strides
+    d.dv_item_stride, d.dv_row_stride = dv_strides
+    d.scale = scale
+    capi.check(_L().gwd_attention_bwd(ctypes.byref(d), _stream()), "gwd_attention_bwd")
+
+
+def sumsq(g, out):
+    """out (fp64 [1], zeroed by the caller) += sum g^2"""
+    capi.check(_L().gwd_sumsq(_ptr(g), g.numel(), _ptr(out), _stream()), "gwd_sumsq")
+
+
+def adamw_step(p, g, m, v, mirror, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, step=1, max_norm=0.0,
+               grad_scale=1.0, sumsq_buf=None):
+    assert p.dtype == g.dtype == m.dtype == v.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous()
+    capi.check(_L().gwd_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(mirror), p.numel(), lr, betas[0], betas[1], eps,
+                                   weight_decay, step, max_norm, grad_scale, _ptr(sumsq_buf), _stream()), "gwd_adamw_step")

@@ -222,6 +222,48 @@ int gwd_depth_metrics(const float* pred, const float* gt, int32_t B, int64_t HW,
 int gwd_silog_sums(const float* pred, int32_t B, int32_t h, int32_t w, const float* gt, int32_t H, int32_t W, float lo,
                    float hi, int32_t log_only, double* sums3, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training side of the line branch (DETR encoder / decoder + line heads): backward and optimizer kernels.
+ * The reference gets all of this from torch.autograd over the modules of src/models/transformer.py:149-162,212-233,
+ * src/models/multi_head_attention.py:317-373 and src/models/glassrgbd.py:87-90, and from torch.optim.AdamW +
+ * clip_grad_norm_ (src/main_glassrgbd.py:59-67, src/engine_glassrgbd.py:155-159).
+ * Data gradients dX = dY W and weight gradients dW = dY^T X are gwd_conv_gemm calls on transposed operands.
+ * ------------------------------------------------------------------------------------------ */
+/* y = LayerNorm_C(z) * gamma + beta:  dz[rows,C] (bf16) = LN backward of dy (+ `add`, an optional bf16 gradient that
+ * joins at the same tensor, e.g. the residual branch); dgamma / dbeta fp32 [C] are ACCUMULATED (atomicAdd; NULL = skip). */
+int gwd_layernorm_bwd(const void* dy, int64_t dy_rs, const void* z, int64_t z_rs, const float* gamma, float eps,
+                      const void* add, int64_t add_rs, void* dz, int64_t dz_rs, float* dgamma, float* dbeta, int64_t rows,
+                      int32_t C, void* stream);
+/* out[r, c] (bf16, c < out_cols) = c < n ? dy[r,c] * act'(y[r,c]) : 0 with act' evaluated from the OUTPUT y
+ * (GWD_ACT_RELU, GWD_ACT_SIGMOID, or GWD_ACT_NONE = dtype conversion + padding).  dy / y are fp32 or bf16. */
+int gwd_act_bwd(const void* dy, int32_t dy_f32, int64_t dy_rs, const void* y, int32_t y_f32, int64_t y_rs, int32_t act,
+                void* out, int64_t out_rs, int64_t rows, int32_t n, int32_t out_cols, void* stream);
+/* out[c, r] = x[r, c] (bf16; r < rows, c < C), columns rows..rows_pad of out written as zeros; colsum (optional, fp32
+ * [C]) is ACCUMULATED with the column sums of x = the bias gradient when x is dY. */
+int gwd_transpose(const void* x, int64_t x_rs, void* out, int64_t out_rs, int64_t rows, int64_t rows_pad, int32_t C,
+                  float* colsum, void* stream);
+/* backward of O = softmax(scale Q K^T) V for head_dim 32, Lq, Lk <= 512 (no bias / mask): the soft-max is recomputed
+ * from Q, K; dQ, dK, dV are bf16 views addressed like gwd_attn_desc. */
+typedef struct gwd_attn_bwd_desc {
+  const void* q; const void* k; const void* v; const void* d_o;
+  void* dq; void* dk; void* dv;
+  int32_t items, heads, Lq, Lk, hd;
+  int64_t q_item_stride, q_row_stride, k_item_stride, k_row_stride, v_item_stride, v_row_stride;
+  int64_t do_item_stride, do_row_stride, dq_item_stride, dq_row_stride, dk_item_stride, dk_row_stride;
+  int64_t dv_item_stride, dv_row_stride;
+  float scale;
+} gwd_attn_bwd_desc;
+int gwd_attention_bwd(const gwd_attn_bwd_desc* d, void* stream);
+/* *out_accum += sum g[i]^2 (fp64 accumulate; the caller zeroes it).  Input of the gradient clip below. */
+int gwd_sumsq(const float* g, int64_t n, double* out_accum, void* stream);
+/* torch.nn.utils.clip_grad_norm_(max_norm) + torch.optim.AdamW step `step` (1-based) over a flat fp32 segment:
+ * g is first scaled by grad_scale (1 / world size after a sum all-reduce) and by the clip coefficient
+ * min(1, max_norm / (sqrt(*sumsq) * grad_scale + 1e-6)) read on the DEVICE (no host sync; max_norm <= 0 or sumsq NULL =
+ * no clipping); mirror_bf16 (optional) receives the bf16 copy of the new parameters that the forward kernels read. */
+int gwd_adamw_step(float* p, const float* g, float* m, float* v, void* mirror_bf16, int64_t n, float lr, float beta1,
+                   float beta2, float eps, float weight_decay, int32_t step, float max_norm, float grad_scale,
+                   const double* sumsq, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
