@@ -9,6 +9,7 @@
 // Data-gradient GEMMs dX = dY W run on gwd_conv_gemm with the transposed weight mirror.
 #include <algorithm>
 #include <math.h>
+#include <stdlib.h>
 #include "gwd_common.cuh"
 
 namespace {
@@ -200,10 +201,10 @@ gwd_transpose_kernel(const bf16* __restrict__ x, int64_t x_rs, bf16* __restrict_
 constexpr int kHD = 32, kRowW = 17, kBwdWarps = 8;
 
 struct AttnBwdParams {
-  const bf16 *q, *k, *v, *d_o;
+  const bf16 *q, *k, *v, *d_o, *o;
   bf16 *dq, *dk, *dv;
-  int Lq, Lk;
-  int64_t q_is, q_rs, k_is, k_rs, v_is, v_rs, do_is, do_rs, dq_is, dq_rs, dk_is, dk_rs, dv_is, dv_rs;
+  int Lq, Lk, Lq_pad, Lk_pad;
+  int64_t q_is, q_rs, k_is, k_rs, v_is, v_rs, do_is, do_rs, dq_is, dq_rs, dk_is, dk_rs, dv_is, dv_rs, o_is, o_rs;
   float scale;
 };
 
@@ -351,6 +352,226 @@ gwd_attention_bwd_kernel(AttnBwdParams p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// attention backward on the tensor cores (mma.sync m16n8k16, bf16 in, fp32 accumulate), head_dim 32, used when the
+// forward output O is available (D_i = sum_j P_ij dP_ij = dO_i . O_i, so no separate reduction sweep is needed).
+// One CTA per (head, item); Q, K, V, dO rows in shared memory with an 80-byte row stride (ldmatrix conflict-free), rows
+// beyond L zero-filled up to a multiple of 64.  Two products do everything:
+//   xyT : X_tile [16 x 32] . Y_chunk^T [32 x 64]   A by ldmatrix, B by ldmatrix            (S, dP, S^T, dP^T)
+//   fy  : F [16 x 64] (accumulators re-packed as A fragments) . Y_chunk [64 x 32], B by ldmatrix.trans   (dQ, dK, dV)
+// Pass A (a warp owns 16 queries): sweep 1 = online row max / sum of S -> log-sum-exp; sweep 2 = P, dP, dS -> dQ.
+// Pass B (a warp owns 16 keys): S^T, dP^T per 64-query chunk with the per-query lse / D read from shared memory
+// -> dV += P^T dO, dK += dS^T Q.  Deterministic (no atomics).
+// ------------------------------------------------------------------------------------------------
+constexpr int kMW = 20;      // shared-memory row stride in 32-bit words (32 bf16 + 8 padding)
+constexpr float kLog2eT = 1.4426950408889634f;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void ldsm4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm4t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// A fragments (both k-steps: dims 0-15, 16-31) of the 16 rows starting at row0
+__device__ __forceinline__ void load_a_tile(uint32_t (&a)[2][4], uint32_t base, int row0, int lane) {
+  const uint32_t addr = base + static_cast<uint32_t>((row0 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kMW * 4 + (lane >> 4) * 16);
+  ldsm4(a[0], addr);
+  ldsm4(a[1], addr + 32);
+}
+// acc[nt] = X_tile . Y[c0 + 8 nt .. +8]^T   (8 column tiles = 64 rows of Y)
+__device__ __forceinline__ void xyT(float (&acc)[8][4], const uint32_t (&a)[2][4], uint32_t ybase, int c0, int lane) {
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt) {
+    uint32_t b[4];
+    ldsm4(b, ybase + static_cast<uint32_t>((c0 + nt * 8 + (lane & 7)) * kMW * 4 + (lane >> 3) * 16));
+    acc[nt][0] = 0.f; acc[nt][1] = 0.f; acc[nt][2] = 0.f; acc[nt][3] = 0.f;
+    mma16816(acc[nt], a[0], b[0], b[1]);
+    mma16816(acc[nt], a[1], b[2], b[3]);
+  }
+}
+// out[4 dim tiles] += F [16 x 64] . Y[c0 .. c0+64][32]   with F given as fp32 accumulator tiles f[8][4]
+__device__ __forceinline__ void fy(float (&out)[4][4], const float (&f)[8][4], uint32_t ybase, int c0, int lane) {
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks) {
+    uint32_t a[4];
+    a[0] = gwd_pack_bf16x2(f[2 * ks][0], f[2 * ks][1]);
+    a[1] = gwd_pack_bf16x2(f[2 * ks][2], f[2 * ks][3]);
+    a[2] = gwd_pack_bf16x2(f[2 * ks + 1][0], f[2 * ks + 1][1]);
+    a[3] = gwd_pack_bf16x2(f[2 * ks + 1][2], f[2 * ks + 1][3]);
+    const uint32_t addr = ybase + static_cast<uint32_t>((c0 + ks * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kMW * 4 + (lane >> 4) * 16);
+    uint32_t b[4];
+    ldsm4t(b, addr);             // dims 0-15
+    mma16816(out[0], a, b[0], b[1]);
+    mma16816(out[1], a, b[2], b[3]);
+    ldsm4t(b, addr + 32);        // dims 16-31
+    mma16816(out[2], a, b[0], b[1]);
+    mma16816(out[3], a, b[2], b[3]);
+  }
+}
+__device__ __forceinline__ void store_tile(bf16* base, int64_t rs, int row0, int L, const float (&t)[4][4], float mul, int lane) {
+  const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    if (row0 + g < L)
+      *reinterpret_cast<uint32_t*>(base + (row0 + g) * rs + nt * 8 + 2 * tq) = gwd_pack_bf16x2(t[nt][0] * mul, t[nt][1] * mul);
+    if (row0 + g + 8 < L)
+      *reinterpret_cast<uint32_t*>(base + (row0 + g + 8) * rs + nt * 8 + 2 * tq) = gwd_pack_bf16x2(t[nt][2] * mul, t[nt][3] * mul);
+  }
+}
+
+__global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParams p) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int head = blockIdx.x, item = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  uint32_t* sQ = smem;
+  uint32_t* sK = sQ + p.Lq_pad * kMW;
+  uint32_t* sV = sK + p.Lk_pad * kMW;
+  uint32_t* sO = sV + p.Lk_pad * kMW;                 // dO
+  float* sLse = reinterpret_cast<float*>(sO + p.Lq_pad * kMW);
+  float* sD = sLse + p.Lq_pad;
+  const int64_t hoff = static_cast<int64_t>(head) * kHD;
+  {
+    const bf16* gq = p.q + item * p.q_is + hoff;
+    const bf16* gk = p.k + item * p.k_is + hoff;
+    const bf16* gv = p.v + item * p.v_is + hoff;
+    const bf16* gdo = p.d_o + item * p.do_is + hoff;
+    const bf16* go = p.o + item * p.o_is + hoff;
+    for (int i = threadIdx.x; i < p.Lk_pad * 16; i += 256) {
+      const int r = i >> 4, w = i & 15;
+      const bool in = r < p.Lk;
+      sK[r * kMW + w] = in ? *reinterpret_cast<const uint32_t*>(gk + r * p.k_rs + 2 * w) : 0u;
+      sV[r * kMW + w] = in ? *reinterpret_cast<const uint32_t*>(gv + r * p.v_rs + 2 * w) : 0u;
+    }
+    for (int i = threadIdx.x; i < p.Lq_pad * 16; i += 256) {      // 16 consecutive lanes hold one row
+      const int r = i >> 4, w = i & 15;
+      const bool in = r < p.Lq;
+      const uint32_t dov = in ? *reinterpret_cast<const uint32_t*>(gdo + r * p.do_rs + 2 * w) : 0u;
+      const uint32_t ov = in ? *reinterpret_cast<const uint32_t*>(go + r * p.o_rs + 2 * w) : 0u;
+      sQ[r * kMW + w] = in ? *reinterpret_cast<const uint32_t*>(gq + r * p.q_rs + 2 * w) : 0u;
+      sO[r * kMW + w] = dov;
+      const float2 a = gwd_unpack_bf16x2(dov), b = gwd_unpack_bf16x2(ov);
+      float d = a.x * b.x + a.y * b.y;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (w == 0) { sD[r] = d; sLse[r] = INFINITY; }     // lse of real rows is written by pass A; +inf = "no such query"
+    }
+  }
+  __syncthreads();
+  const uint32_t bQ = smem_u32(sQ), bK = smem_u32(sK), bV = smem_u32(sV), bO = smem_u32(sO);
+  const float sc = p.scale * kLog2eT;
+
+  // ---------------- pass A
+  for (int m0 = warp * 16; m0 < p.Lq; m0 += 8 * 16) {
+    uint32_t qa[2][4], oa[2][4];
+    load_a_tile(qa, bQ, m0, lane);
+    load_a_tile(oa, bO, m0, lane);
+    float mx[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+    for (int c0 = 0; c0 < p.Lk_pad; c0 += 64) {
+      float s[8][4];
+      xyT(s, qa, bK, c0, lane);
+      float cm[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = c0 + nt * 8 + 2 * tq + (e & 1);
+          if (col >= p.Lk) s[nt][e] = -INFINITY;
+          cm[e >> 1] = fmaxf(cm[e >> 1], s[nt][e]);
+        }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float mn = fmaxf(mx[h], cm[h]);
+        if (mn > -INFINITY) {
+          float add = 0.f;
+#pragma unroll
+          for (int nt = 0; nt < 8; ++nt) add += ex2f((s[nt][2 * h] - mn) * sc) + ex2f((s[nt][2 * h + 1] - mn) * sc);
+          l[h] = l[h] * ex2f((mx[h] - mn) * sc) + add;
+          mx[h] = mn;
+        }
+      }
+    }
+    float lse[2], D[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float ma = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+      ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+      float lh = l[h] * ex2f((mx[h] - ma) * sc);           // a lane that saw no valid column has mx = -inf -> factor 0
+      lh += __shfl_xor_sync(0xffffffffu, lh, 1);
+      lh += __shfl_xor_sync(0xffffffffu, lh, 2);
+      lse[h] = ma * sc + __log2f(lh);
+      const int row = m0 + g + 8 * h;
+      D[h] = sD[row];
+      if (tq == 0 && row < p.Lq) sLse[row] = lse[h];
+    }
+    float dq[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { dq[nt][0] = 0.f; dq[nt][1] = 0.f; dq[nt][2] = 0.f; dq[nt][3] = 0.f; }
+    for (int c0 = 0; c0 < p.Lk_pad; c0 += 64) {
+      float s[8][4], dp[8][4];
+      xyT(s, qa, bK, c0, lane);
+      xyT(dp, oa, bV, c0, lane);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int col = c0 + nt * 8 + 2 * tq + (e & 1);
+          const float pr = col < p.Lk ? ex2f(s[nt][e] * sc - lse[e >> 1]) : 0.f;
+          s[nt][e] = pr * (dp[nt][e] - D[e >> 1]);           // dS
+        }
+      fy(dq, s, bK, c0, lane);
+    }
+    store_tile(p.dq + item * p.dq_is + hoff, p.dq_rs, m0, p.Lq, dq, p.scale, lane);
+  }
+  __syncthreads();
+
+  // ---------------- pass B
+  for (int n0 = warp * 16; n0 < p.Lk; n0 += 8 * 16) {
+    uint32_t ka[2][4], va[2][4];
+    load_a_tile(ka, bK, n0, lane);
+    load_a_tile(va, bV, n0, lane);
+    float dk[4][4], dv[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { dk[nt][e] = 0.f; dv[nt][e] = 0.f; }
+    for (int c0 = 0; c0 < p.Lq_pad; c0 += 64) {
+      float st[8][4], dpt[8][4];
+      xyT(st, ka, bQ, c0, lane);
+      xyT(dpt, va, bO, c0, lane);
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        const float2 ls = *reinterpret_cast<const float2*>(sLse + c0 + nt * 8 + 2 * tq);
+        const float2 dd = *reinterpret_cast<const float2*>(sD + c0 + nt * 8 + 2 * tq);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float pr = ex2f(st[nt][e] * sc - ((e & 1) ? ls.y : ls.x));        // lse = +inf beyond Lq -> 0
+          st[nt][e] = pr;                                                         // P^T
+          dpt[nt][e] = pr * (dpt[nt][e] - ((e & 1) ? dd.y : dd.x));               // dS^T
+        }
+      }
+      fy(dv, st, bO, c0, lane);
+      fy(dk, dpt, bQ, c0, lane);
+    }
+    store_tile(p.dk + item * p.dk_is + hoff, p.dk_rs, n0, p.Lk, dk, p.scale, lane);
+    store_tile(p.dv + item * p.dv_is + hoff, p.dv_rs, n0, p.Lk, dv, 1.f, lane);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // optimizer
 // ------------------------------------------------------------------------------------------------
@@ -484,8 +705,22 @@ extern "C" int gwd_attention_bwd(const gwd_attn_bwd_desc* d, void* stream_) {
   p.do_is = strides[6]; p.do_rs = strides[7]; p.dq_is = strides[8]; p.dq_rs = strides[9]; p.dk_is = strides[10];
   p.dk_rs = strides[11]; p.dv_is = strides[12]; p.dv_rs = strides[13];
   p.scale = d->scale;
-  const size_t smem = static_cast<size_t>(2 * d->Lq + 2 * d->Lk) * kRowW * 4 + static_cast<size_t>(2 * d->Lq) * 4;
   dim3 grid(d->heads, d->items);
+  static const bool mma_enabled = []() { const char* e = getenv("GWD_ATTN_BWD_MMA"); return !(e && e[0] == '0'); }();
+  if (d->o != nullptr && mma_enabled) {
+    GWD_CHECK_ARG(d->o_item_stride % 2 == 0 && d->o_row_stride % 2 == 0 && (reinterpret_cast<uintptr_t>(d->o) & 3) == 0 &&
+                      ((reinterpret_cast<uintptr_t>(d->dq) | reinterpret_cast<uintptr_t>(d->dk) | reinterpret_cast<uintptr_t>(d->dv)) & 3) == 0,
+                  "gwd_attention_bwd: o / dq / dk / dv must be 4-byte aligned with even strides");
+    p.o = static_cast<const bf16*>(d->o); p.o_is = d->o_item_stride; p.o_rs = d->o_row_stride;
+    p.Lq_pad = static_cast<int>(gwd_ceil_div(d->Lq, 64)) * 64;
+    p.Lk_pad = static_cast<int>(gwd_ceil_div(d->Lk, 64)) * 64;
+    const size_t sm = static_cast<size_t>(2 * p.Lq_pad + 2 * p.Lk_pad) * kMW * 4 + static_cast<size_t>(2 * p.Lq_pad) * 4;
+    GWD_CUDA(cudaFuncSetAttribute(gwd_attention_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)));
+    gwd_attention_bwd_mma_kernel<<<grid, 256, sm, stream>>>(p);
+    GWD_LAUNCHED();
+    return GWD_OK;
+  }
+  const size_t smem = static_cast<size_t>(2 * d->Lq + 2 * d->Lk) * kRowW * 4 + static_cast<size_t>(2 * d->Lq) * 4;
   auto launch = [&](auto kern) -> int {
     GWD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<grid, kBwdWarps * 32, smem, stream>>>(p);

@@ -477,7 +477,8 @@ def transpose(x, colsum=None, C=None, x_coff=0, pad_to=64, out=None):
 
 
 def attention_bwd(q, k, v, d_o, dq, dk, dv, *, items, heads, Lq, Lk, hd, q_strides, k_strides, v_strides, do_strides,
-                  dq_strides, dk_strides, dv_strides, scale=1.0):
+                  dq_strides, dk_strides, dv_strides, scale=1.0, o=None, o_strides=None):
+    """o: the forward output (bf16) -> tensor-core kernel; None -> CUDA-core kernel that recomputes D = rowsum(P dP)"""
     d = capi.AttnBwdDesc()
     d.q, d.k, d.v, d.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), d_o.data_ptr()
     d.dq, d.dk, d.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
@@ -490,6 +491,9 @@ def attention_bwd(q, k, v, d_o, dq, dk, dv, *, items, heads, Lq, Lk, hd, q_strid
     d.dk_item_stride, d.dk_row_stride = dk_strides
     d.dv_item_stride, d.dv_row_stride = dv_strides
     d.scale = scale
+    if o is not None:
+        d.o = o.data_ptr()
+        d.o_item_stride, d.o_row_stride = o_strides or do_strides
     capi.check(_L().gwd_attention_bwd(ctypes.byref(d), _stream()), "gwd_attention_bwd")
 
 

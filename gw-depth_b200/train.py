@@ -225,12 +225,12 @@ class LineBranch:
     def _ln_bwd(self, dy, z, ln, add=None):
         return ops.layernorm_bwd(dy, z, ln[0], ln[2], ln[3], add=add)
 
-    def _attend_bwd(self, q, k, v, d_o, B, Lq, Lk, q_rs, k_rs, dq, dk, dv):
+    def _attend_bwd(self, q, k, v, o, d_o, B, Lq, Lk, q_rs, k_rs, dq, dk, dv):
         E, nh = self.cfg["hidden_dim"], self.cfg["nheads"]
         ops.attention_bwd(q, k, v, d_o, dq, dk, dv, items=B, heads=nh, Lq=Lq, Lk=Lk, hd=E // nh,
                           q_strides=(Lq * q_rs, q_rs), k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E),
                           do_strides=(Lq * E, E), dq_strides=(Lq * q_rs, q_rs), dk_strides=(Lk * k_rs, k_rs),
-                          dv_strides=(Lk * E, E), scale=(E // nh) ** -0.5)
+                          dv_strides=(Lk * E, E), scale=(E // nh) ** -0.5, o=o, o_strides=(Lq * E, E))
 
     def _ffn_bwd(self, ly, d_out, z, hm, x_in, ln):
         dz = self._ln_bwd(d_out, z, ln)
@@ -268,7 +268,7 @@ class LineBranch:
             dz2 = self._ln_bwd(d_x2, s["z2"], ly["n2"])
             d_o = self._lin_bwd(cr["o"], dz2, s["o2"])
             dq, dk, dv = torch.empty(B * Q, E, **bf), torch.empty(B * L, E, **bf), torch.empty(B * L, E, **bf)
-            self._attend_bwd(s["cq"], s["ck"], s["cv"], d_o, B, Q, L, E, E, dq, dk, dv)
+            self._attend_bwd(s["cq"], s["ck"], s["cv"], s["o2"], d_o, B, Q, L, E, E, dq, dk, dv)
             dtq = self._lin_bwd(cr["q"], dq, s["tq2"])
             gq += dtq.view(B, Q, E).sum(0, dtype=torch.float32)
             d_x1 = self._add(dtq, dz2)
@@ -279,7 +279,7 @@ class LineBranch:
             dz1 = self._ln_bwd(d_x1, s["z1"], ly["n1"])
             d_o = self._lin_bwd(sa["o"], dz1, s["o1"])
             dqk, dv = torch.empty(B * Q, 2 * E, **bf), torch.empty(B * Q, E, **bf)
-            self._attend_bwd(s["qk"], s["qk"][:, E:], s["v"], d_o, B, Q, Q, 2 * E, 2 * E, dqk, dqk[:, E:], dv)
+            self._attend_bwd(s["qk"], s["qk"][:, E:], s["v"], s["o1"], d_o, B, Q, Q, 2 * E, 2 * E, dqk, dqk[:, E:], dv)
             dtq = self._lin_bwd(sa["qk"], dqk, s["tq1"])
             gq += dtq.view(B, Q, E).sum(0, dtype=torch.float32)
             d_next = self._lin_bwd(sa["v"], dv, s["x0"], res=self._add(dtq, dz1))
@@ -293,7 +293,7 @@ class LineBranch:
             dz1 = self._ln_bwd(d_x1, s["z1"], ly["n1"])
             d_o = self._lin_bwd(a["o"], dz1, s["o"])
             dqk, dv = torch.empty(B * L, 2 * E, **bf), torch.empty(B * L, E, **bf)
-            self._attend_bwd(s["qk"], s["qk"][:, E:], s["v"], d_o, B, L, L, 2 * E, 2 * E, dqk, dqk[:, E:], dv)
+            self._attend_bwd(s["qk"], s["qk"][:, E:], s["v"], s["o"], d_o, B, L, L, 2 * E, 2 * E, dqk, dqk[:, E:], dv)
             t = self._lin_bwd(a["qk"], dqk, s["xp"], res=dz1)
             d_x = self._lin_bwd(a["v"], dv, s["x"], res=t)
         dc5 = self._lin_bwd(self.input_proj, d_x, tp["c5"])

@@ -243,7 +243,8 @@ int gwd_act_bwd(const void* dy, int32_t dy_f32, int64_t dy_rs, const void* y, in
 int gwd_transpose(const void* x, int64_t x_rs, void* out, int64_t out_rs, int64_t rows, int64_t rows_pad, int32_t C,
                   float* colsum, void* stream);
 /* backward of O = softmax(scale Q K^T) V for head_dim 32, Lq, Lk <= 512 (no bias / mask): the soft-max is recomputed
- * from Q, K; dQ, dK, dV are bf16 views addressed like gwd_attn_desc. */
+ * from Q, K; dQ, dK, dV are bf16 views addressed like gwd_attn_desc.  With the forward output `o` given the kernel runs
+ * on the tensor cores (mma.sync; D_i = dO_i . O_i); with o == NULL a CUDA-core kernel computes D itself. */
 typedef struct gwd_attn_bwd_desc {
   const void* q; const void* k; const void* v; const void* d_o;
   void* dq; void* dk; void* dv;
@@ -252,6 +253,8 @@ typedef struct gwd_attn_bwd_desc {
   int64_t do_item_stride, do_row_stride, dq_item_stride, dq_row_stride, dk_item_stride, dk_row_stride;
   int64_t dv_item_stride, dv_row_stride;
   float scale;
+  const void* o;          /* forward output (bf16), or NULL */
+  int64_t o_item_stride, o_row_stride;
 } gwd_attn_bwd_desc;
 int gwd_attention_bwd(const gwd_attn_bwd_desc* d, void* stream);
 /* *out_accum += sum g[i]^2 (fp64 accumulate; the caller zeroes it).  Input of the gradient clip below. */

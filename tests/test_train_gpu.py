@@ -96,8 +96,10 @@ def test_weight_gradient_gemm_on_transposed_operands():
         assert rel_l2(dX, dY.float() @ W.float()) < 6e-3
 
 
-@pytest.mark.parametrize("B,Lq,Lk,fused", [(2, 300, 300, True), (3, 100, 300, False), (2, 100, 100, True), (1, 37, 480, False)])
-def test_attention_bwd(B, Lq, Lk, fused):
+@pytest.mark.parametrize("use_o", [True, False])      # True: tensor-core kernel (needs the forward output), False: CUDA-core kernel
+@pytest.mark.parametrize("B,Lq,Lk,fused", [(2, 300, 300, True), (3, 100, 300, False), (2, 100, 100, True), (1, 37, 480, False),
+                                           (1, 512, 512, True), (2, 1, 5, False)])
+def test_attention_bwd(B, Lq, Lk, fused, use_o):
     ops = _ops()
     heads, hd = 8, 32
     E = heads * hd
@@ -126,14 +128,18 @@ def test_attention_bwd(B, Lq, Lk, fused):
         dq = torch.empty(B * Lq, E, dtype=torch.bfloat16, device="cuda")
         dk = torch.empty(B * Lk, E, dtype=torch.bfloat16, device="cuda")
     dv = torch.empty(B * Lk, E, dtype=torch.bfloat16, device="cuda")
+    o_fwd = flat(o.detach(), Lq).bfloat16().cuda().contiguous() if use_o else None
     ops.attention_bwd(q, k, v, d_o, dq, dk, dv, items=B, heads=heads, Lq=Lq, Lk=Lk, hd=hd, q_strides=(Lq * q_rs, q_rs),
                       k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E), do_strides=(Lq * E, E), dq_strides=(Lq * q_rs, q_rs),
-                      dk_strides=(Lk * k_rs, k_rs), dv_strides=(Lk * E, E), scale=scale)
+                      dk_strides=(Lk * k_rs, k_rs), dv_strides=(Lk * E, E), scale=scale, o=o_fwd, o_strides=(Lq * E, E))
     got_dq = dqk[:, :E] if fused else dq
     got_dk = dqk[:, E:] if fused else dk
-    assert rel_l2(got_dq, flat(qh.grad, Lq)) < 6e-3
-    assert rel_l2(got_dk, flat(kh.grad, Lk)) < 6e-3
-    assert rel_l2(dv, flat(vh.grad, Lk)) < 6e-3
+    # CUDA-core kernel: fp32 throughout, bf16 output rounding only; tensor-core kernel: P and dS are bf16 MMA operands and
+    # D comes from the bf16 forward output
+    tol = 1e-2 if use_o else 6e-3
+    assert rel_l2(got_dq, flat(qh.grad, Lq)) < tol
+    assert rel_l2(got_dk, flat(kh.grad, Lk)) < tol
+    assert rel_l2(dv, flat(vh.grad, Lk)) < tol
 
 
 @pytest.mark.parametrize("max_norm,world", [(0.1, 1), (0.0, 1), (0.1, 2)])
@@ -306,7 +312,7 @@ def test_graphed_and_eager_training_steps_agree():
     for it in range(2):         # second iteration: replay of an existing capture after an optimizer step
         ta, _, dca = a.loss_and_grads(c5, targets, criterion)
         tb, _, dcb = b.loss_and_grads(c5, targets, criterion)
-        assert float(ta) == float(tb)
+        assert abs(float(ta) - float(tb)) <= 1e-6 * abs(float(tb))     # index_add_ (atomics) sums the L1 terms
         # bias / LayerNorm gradients are atomicAdd column sums (order-dependent in the last bits); weights are exact
         assert rel_l2(a.G, b.G) < 1e-5 and torch.equal(dca, dcb)
         assert torch.equal(a.view(a.G, "transformer.encoder.layers.0.linear1.weight"),
