@@ -94,6 +94,7 @@ SIGNATURES = {
     "gwd_layernorm_bwd": (c_int, [P, L, P, L, P, F_, P, L, P, L, P, P, L, I, P]),
     "gwd_act_bwd": (c_int, [P, I, L, P, I, L, I, P, L, L, I, I, P]),
     "gwd_transpose": (c_int, [P, L, P, L, L, L, I, P, P]),
+    "gwd_linear_wgrad": (c_int, [P, L, P, L, L, I, I, P, L, P, P]),
     "gwd_attention_bwd": (c_int, [ctypes.POINTER(AttnBwdDesc), P]),
     "gwd_sumsq": (c_int, [P, L, P, P]),
     "gwd_adamw_step": (c_int, [P, P, P, P, P, L, F_, F_, F_, F_, F_, I, F_, F_, P, P]),

@@ -572,6 +572,120 @@ __global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParam
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Linear weight gradient  dW[n, k] += sum_r dY[r, n] X[r, k]  (+ db[n] += sum_r dY[r, n]).
+// Both operands are contracted over their SLOW axis (the token rows), i.e. they are "MN-major" for a GEMM: on
+// mma.sync that is simply ldmatrix.trans on both fragments, so no transposed copies of dY and X are made.  The
+// problem is short and fat (N x K up to 2048 x 256 outputs, R = 1 600 .. 9 600 rows), so the rows are split across
+// CTAs (split-K) until ~2 CTAs per SM exist, and partial tiles are reduced with vector fp32 atomics into the
+// (pre-zeroed) flat gradient buffer.  CTA tile 128 (n) x 128 (k) x 32 rows per stage, 3-stage cp.async ring,
+// 8 warps of 32 x 64.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWgT = 128, kWgR = 32, kWgLd = 136, kWgStages = 3;
+
+struct WgradParams {
+  const bf16* dy; const bf16* x;
+  float* dw; float* db;
+  int64_t dy_rs, x_rs, dw_rs;
+  int R, N, K, rows_per_split;
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(src), "r"(sz));
+}
+
+__global__ void __launch_bounds__(256) gwd_wgrad_kernel(WgradParams p) {
+  extern __shared__ __align__(16) uint8_t wsm[];
+  bf16* sA = reinterpret_cast<bf16*>(wsm);                          // [stages][32][136]  dY tile
+  bf16* sB = sA + kWgStages * kWgR * kWgLd;                         // [stages][32][136]  X tile
+  const int n0 = blockIdx.x * kWgT, k0 = blockIdx.y * kWgT;
+  const int r_begin = blockIdx.z * p.rows_per_split;
+  const int r_end = min(p.R, r_begin + p.rows_per_split);
+  const int iters = (r_end - r_begin + kWgR - 1) / kWgR;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wm = warp & 3, wn = warp >> 2;
+  const int g = lane >> 2, tq = lane & 3;
+  const uint32_t aBase = smem_u32(sA), bBase = smem_u32(sB);
+
+  auto load_stage = [&](int it, int st) {
+    const int r0 = r_begin + it * kWgR;
+#pragma unroll
+    for (int c = threadIdx.x; c < kWgR * 16; c += 256) {
+      const int rr = c >> 4, c8 = (c & 15) * 8;
+      const int r = r0 + rr;
+      const bool rin = r < r_end;
+      const bool va = rin && (n0 + c8 < p.N), vb = rin && (k0 + c8 < p.K);
+      cp_async16(aBase + static_cast<uint32_t>(((st * kWgR + rr) * kWgLd + c8) * 2), va ? p.dy + static_cast<int64_t>(r) * p.dy_rs + n0 + c8 : p.dy, va);
+      cp_async16(bBase + static_cast<uint32_t>(((st * kWgR + rr) * kWgLd + c8) * 2), vb ? p.x + static_cast<int64_t>(r) * p.x_rs + k0 + c8 : p.x, vb);
+    }
+  };
+
+  float acc[2][8][4];
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) { acc[mt][nt][0] = 0.f; acc[mt][nt][1] = 0.f; acc[mt][nt][2] = 0.f; acc[mt][nt][3] = 0.f; }
+  float bsum = 0.f;
+  const bool do_bias = p.db != nullptr && blockIdx.y == 0 && threadIdx.x < kWgT;
+
+#pragma unroll
+  for (int s = 0; s < kWgStages - 1; ++s) {
+    if (s < iters) load_stage(s, s);
+    asm volatile("cp.async.commit_group;");
+  }
+  for (int it = 0; it < iters; ++it) {
+    asm volatile("cp.async.wait_group %0;" :: "n"(kWgStages - 2));
+    __syncthreads();
+    if (it + kWgStages - 1 < iters) load_stage(it + kWgStages - 1, (it + kWgStages - 1) % kWgStages);
+    asm volatile("cp.async.commit_group;");
+    const int st = it % kWgStages;
+    const uint32_t aS = aBase + static_cast<uint32_t>(st * kWgR * kWgLd * 2), bS = bBase + static_cast<uint32_t>(st * kWgR * kWgLd * 2);
+#pragma unroll
+    for (int kk = 0; kk < kWgR / 16; ++kk) {
+      uint32_t a[2][4];
+#pragma unroll
+      for (int mt = 0; mt < 2; ++mt)       // A = dY^T: matrices (k+0,m+0) (k+0,m+8) (k+8,m+0) (k+8,m+8), transposed on load
+        ldsm4t(a[mt], aS + static_cast<uint32_t>(((kk * 16 + (lane & 7) + 8 * (lane >> 4)) * kWgLd + wm * 32 + mt * 16 + 8 * ((lane >> 3) & 1)) * 2));
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t b[4];
+        ldsm4t(b, bS + static_cast<uint32_t>(((kk * 16 + (lane & 7) + 8 * ((lane >> 3) & 1)) * kWgLd + wn * 64 + np * 16 + 8 * (lane >> 4)) * 2));
+#pragma unroll
+        for (int mt = 0; mt < 2; ++mt) {
+          mma16816(acc[mt][2 * np], a[mt], b[0], b[1]);
+          mma16816(acc[mt][2 * np + 1], a[mt], b[2], b[3]);
+        }
+      }
+    }
+    if (do_bias) {
+      const bf16* col = sA + st * kWgR * kWgLd + threadIdx.x;
+#pragma unroll 8
+      for (int rr = 0; rr < kWgR; ++rr) bsum += __bfloat162float(col[rr * kWgLd]);
+    }
+  }
+  asm volatile("cp.async.wait_group 0;");
+  const bool single = gridDim.z == 1;
+#pragma unroll
+  for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int kcol = k0 + wn * 64 + nt * 8 + 2 * tq;
+      if (kcol >= p.K) continue;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int n = n0 + wm * 32 + mt * 16 + g + 8 * h;
+        if (n >= p.N) continue;
+        float2* dst = reinterpret_cast<float2*>(p.dw + static_cast<int64_t>(n) * p.dw_rs + kcol);
+        const float2 v = make_float2(acc[mt][nt][2 * h], acc[mt][nt][2 * h + 1]);
+        if (single) { float2 o = *dst; o.x += v.x; o.y += v.y; *dst = o; }
+        else atomicAdd(dst, v);
+      }
+    }
+  if (do_bias && n0 + threadIdx.x < p.N) atomicAdd(p.db + n0 + threadIdx.x, bsum);
+}
+
 // ------------------------------------------------------------------------------------------------
 // optimizer
 // ------------------------------------------------------------------------------------------------
@@ -756,6 +870,30 @@ extern "C" int gwd_adamw_step(float* p, const float* g, float* m, float* v, void
   a.max_norm = max_norm; a.grad_scale = grad_scale;
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(n, 256 * 4), 8 * gwd_num_sms()));
   gwd_adamw_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, static_cast<bf16*>(mirror_bf16), n, a, sumsq);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_linear_wgrad(const void* dy, int64_t dy_rs, const void* x, int64_t x_rs, int64_t rows, int32_t N, int32_t K,
+                                float* dw, int64_t dw_rs, float* db, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(dy && x && dw && rows > 0 && N > 0 && K > 0, "gwd_linear_wgrad: null pointer / empty");
+  GWD_CHECK_ARG(N % 8 == 0 && K % 8 == 0 && dy_rs % 8 == 0 && x_rs % 8 == 0 && dw_rs % 2 == 0 && dy_rs >= N && x_rs >= K &&
+                    dw_rs >= K && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(dw) & 7) == 0,
+                "gwd_linear_wgrad: N, K, strides must be multiples of 8 (dw: 2) and pointers 16-byte (dw: 8-byte) aligned");
+  GWD_CHECK_ARG(rows < (1ll << 31), "gwd_linear_wgrad: too many rows");
+  WgradParams p;
+  p.dy = static_cast<const bf16*>(dy); p.x = static_cast<const bf16*>(x); p.dw = dw; p.db = db;
+  p.dy_rs = dy_rs; p.x_rs = x_rs; p.dw_rs = dw_rs; p.R = static_cast<int>(rows); p.N = N; p.K = K;
+  const int tiles = static_cast<int>(gwd_ceil_div(N, kWgT) * gwd_ceil_div(K, kWgT));
+  int64_t split = std::max<int64_t>(1, std::min<int64_t>(gwd_ceil_div(2 * gwd_num_sms(), tiles), gwd_ceil_div(rows, 2 * kWgR)));
+  p.rows_per_split = static_cast<int>(gwd_ceil_div(gwd_ceil_div(rows, split), kWgR) * kWgR);
+  split = gwd_ceil_div(rows, p.rows_per_split);
+  const size_t smem = static_cast<size_t>(2) * kWgStages * kWgR * kWgLd * sizeof(bf16);
+  GWD_CUDA(cudaFuncSetAttribute(gwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  dim3 grid(static_cast<unsigned>(gwd_ceil_div(N, kWgT)), static_cast<unsigned>(gwd_ceil_div(K, kWgT)), static_cast<unsigned>(split));
+  gwd_wgrad_kernel<<<grid, 256, smem, stream>>>(p);
   GWD_LAUNCHED();
   return GWD_OK;
 }

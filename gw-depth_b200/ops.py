@@ -476,6 +476,15 @@ def transpose(x, colsum=None, C=None, x_coff=0, pad_to=64, out=None):
     return out
 
 
+def linear_wgrad(dy, x, dw, db=None, N=None, K=None, x_coff=0):
+    """dw [N, K] (fp32 view) += dy[:, :N]^T x[:, x_coff:x_coff+K]; db [N] += column sums of dy.  dy, x: bf16 [rows, *]"""
+    N = N or dw.shape[0]
+    K = K or dw.shape[1]
+    assert dy.dtype == x.dtype == torch.bfloat16 and dw.dtype == torch.float32 and dw.stride(-1) == 1
+    capi.check(_L().gwd_linear_wgrad(_ptr(dy), dy.shape[-1], _off(x, x_coff), x.shape[-1], _rows(dy), N, K, _ptr(dw), dw.stride(0),
+                                     _ptr(db), _stream()), "gwd_linear_wgrad")
+
+
 def attention_bwd(q, k, v, d_o, dq, dk, dv, *, items, heads, Lq, Lk, hd, q_strides, k_strides, v_strides, do_strides,
                   dq_strides, dk_strides, dv_strides, scale=1.0, o=None, o_strides=None):
     """o: the forward output (bf16) -> tensor-core kernel; None -> CUDA-core kernel that recomputes D = rowsum(P dP)"""

@@ -13,8 +13,9 @@ B200 design
   one buffer, and clip + AdamW + mirror refresh are two launches (gwd_sumsq, gwd_adamw_step) with the clip coefficient
   read on the device;
 * forward = the inference kernel sequence of engine.Engine.detr with the pre-LayerNorm values kept (y_raw);
-* backward: dX = dY W and dW = dY^T X on gwd_conv_gemm (transposed operands from gwd_transpose, which also yields the
-  bias gradients as column sums), gwd_layernorm_bwd, gwd_act_bwd, gwd_attention_bwd (soft-max recomputed).
+* backward: dX = dY W on gwd_conv_gemm (tcgen05) with the transposed weight mirror (gwd_transpose), dW = dY^T X and
+  db on gwd_linear_wgrad (split-K mma.sync, both operands read as stored), gwd_layernorm_bwd, gwd_act_bwd,
+  gwd_attention_bwd (soft-max recomputed, tensor cores).
 
 Scope: gradients stop at the C5 feature map (the backbone / dense-branch backward is not built); `backward` returns
 dC5 so that a backbone backward can be attached.
@@ -72,7 +73,7 @@ class LineBranch:
         self.Wb = self.P.to(torch.bfloat16)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self._build_views()
-        self._tables, self._xt, self.tape, self._graphs = {}, {}, None, {}
+        self._tables, self.tape, self._graphs = {}, None, {}
         import os
         self.use_cuda_graph = os.environ.get("GWD_CUDA_GRAPH", "1") != "0"
 
@@ -159,7 +160,6 @@ class LineBranch:
         if key not in self._tables:
             self._tables[key] = sine_table(h, w, E // 2, True, self.dev).to(torch.bfloat16)
         pos = self._tables[key]
-        self._xt = {}
         tp = self.tape = {"B": B, "L": L, "enc": [], "dec": []}
         tp["c5"] = c5.reshape(B * L, c5.shape[-1])
         x = conv_gemm(tp["c5"], self.input_proj.pw)
@@ -206,18 +206,9 @@ class LineBranch:
         return logits.view(nl, B, Q, -1), lines.view(nl, B, Q, -1)
 
     # ------------------------------------------------------------------ backward
-    def _transposed(self, X):
-        k = X.data_ptr()
-        if k not in self._xt:
-            self._xt[k] = ops.transpose(X)
-        return self._xt[k]
-
     def _lin_bwd(self, lin, dY, X, need_dx=True, res=None):
-        """dY [R, n_pad] bf16, X [R, K] bf16: writes dW (fp32 view) and accumulates db; returns dX (+ res) or None"""
-        dYT = ops.transpose(dY, colsum=lin.gb, C=lin.n_pad)
-        XT = self._transposed(X)
-        conv_gemm(dYT, PackedWeight(XT.view(1, lin.k, XT.shape[1]), None, 1, lin.k, XT.shape[1]), out=lin.gw, out_f32=True,
-                  bias=False)
+        """dY [R, n_pad] bf16, X [R, K] bf16: accumulates dW / db into the flat gradient views; returns dX (+ res) or None"""
+        ops.linear_wgrad(dY, X, lin.gw, lin.gb)
         if not need_dx:
             return None
         return conv_gemm(dY, lin.pwT, bias=False, res=res, res_mode=RES_AFTER if res is not None else RES_NONE)
@@ -297,7 +288,6 @@ class LineBranch:
             t = self._lin_bwd(a["qk"], dqk, s["xp"], res=dz1)
             d_x = self._lin_bwd(a["v"], dv, s["x"], res=t)
         dc5 = self._lin_bwd(self.input_proj, d_x, tp["c5"])
-        self._xt = {}
         if not keep_tape:
             self.tape = None
         return dc5

@@ -242,6 +242,12 @@ int gwd_act_bwd(const void* dy, int32_t dy_f32, int64_t dy_rs, const void* y, in
  * [C]) is ACCUMULATED with the column sums of x = the bias gradient when x is dY. */
 int gwd_transpose(const void* x, int64_t x_rs, void* out, int64_t out_rs, int64_t rows, int64_t rows_pad, int32_t C,
                   float* colsum, void* stream);
+/* nn.Linear weight gradient: dw[n, k] (fp32, row stride dw_rs) += sum_r dy[r, n] * x[r, k], db[n] += sum_r dy[r, n]
+ * (db optional).  dy [rows, N] and x [rows, K] are bf16 with row strides; both are contracted over their slow axis, which
+ * the kernel handles with ldmatrix.trans (no transposed copies); rows are split across CTAs and reduced with fp32
+ * atomics, so dw / db must hold the running gradient (zeros at the start of a step). */
+int gwd_linear_wgrad(const void* dy, int64_t dy_rs, const void* x, int64_t x_rs, int64_t rows, int32_t N, int32_t K, float* dw,
+                     int64_t dw_rs, float* db, void* stream);
 /* backward of O = softmax(scale Q K^T) V for head_dim 32, Lq, Lk <= 512 (no bias / mask): the soft-max is recomputed
  * from Q, K; dQ, dK, dV are bf16 views addressed like gwd_attn_desc.  With the forward output `o` given the kernel runs
  * on the tensor cores (mma.sync; D_i = dO_i . O_i); with o == NULL a CUDA-core kernel computes D itself. */
