@@ -58,6 +58,7 @@ class AttnBwdDesc(ctypes.Structure):
         ("dq_item_stride", c_i64), ("dq_row_stride", c_i64), ("dk_item_stride", c_i64), ("dk_row_stride", c_i64),
         ("dv_item_stride", c_i64), ("dv_row_stride", c_i64),
         ("scale", c_float), ("o", c_void_p), ("o_item_stride", c_i64), ("o_row_stride", c_i64),
+        ("dq_mul", c_float), ("dk_mul", c_float),
     ]
 
 

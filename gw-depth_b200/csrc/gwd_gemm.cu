@@ -954,7 +954,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
     const size_t ep_bytes = 1024 + static_cast<size_t>(kMaxEpilogueWarps) * 4096;
     // one 4-warp group per 64 output columns: N tiles of 128 / 192 / 256 columns -> 8 / 12 / 16 epilogue warps
     if (enabled && d->taps == 1 && d->B == 1 && d->H == 1 && !strided_x && ctas == 1 && !p.tile_split && !has_ln && !d->y_f32 &&
-        d->y_raw == nullptr && !d->upsample2 && !d->w_per_image && d->pre_act == GWD_ACT_NONE &&
+        d->y_raw == nullptr && !d->upsample2 && !d->w_per_image && d->pre_act == GWD_ACT_NONE && d->out_scale == 1.f &&
         (d->post_act == GWD_ACT_NONE || d->post_act == GWD_ACT_RELU || d->post_act == GWD_ACT_GELU) &&
         (p.Nt == 128 || p.Nt == 192 || p.Nt == 256) &&
         store_n % 8 == 0 && d->y_cstride % 8 == 0 && d->y_coff % 8 == 0 &&

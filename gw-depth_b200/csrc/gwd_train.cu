@@ -205,7 +205,7 @@ struct AttnBwdParams {
   bf16 *dq, *dk, *dv;
   int Lq, Lk, Lq_pad, Lk_pad;
   int64_t q_is, q_rs, k_is, k_rs, v_is, v_rs, do_is, do_rs, dq_is, dq_rs, dk_is, dk_rs, dv_is, dv_rs, o_is, o_rs;
-  float scale;
+  float scale, dq_mul, dk_mul;
 };
 
 __device__ __forceinline__ float reduce_scatter32(float (&acc)[32], int lane) {
@@ -311,7 +311,7 @@ gwd_attention_bwd_kernel(AttnBwdParams p) {
         }
       }
     }
-    const float r = reduce_scatter32(acc, lane) * p.scale;
+    const float r = reduce_scatter32(acc, lane) * p.dq_mul;
     p.dq[item * p.dq_is + i * p.dq_rs + hoff + lane] = __float2bfloat16(r);
   }
   __syncthreads();
@@ -345,7 +345,7 @@ gwd_attention_bwd_kernel(AttnBwdParams p) {
 #pragma unroll
       for (int d = 0; d < 32; ++d) ak[d] = fmaf(ds, qr[d], ak[d]);
     }
-    const float rk = reduce_scatter32(ak, lane) * p.scale;
+    const float rk = reduce_scatter32(ak, lane) * p.dk_mul;
     const float rv = reduce_scatter32(av, lane);
     p.dk[item * p.dk_is + j * p.dk_rs + hoff + lane] = __float2bfloat16(rk);
     p.dv[item * p.dv_is + j * p.dv_rs + hoff + lane] = __float2bfloat16(rv);
@@ -535,7 +535,7 @@ __global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParam
         }
       fy(dq, s, bK, c0, lane);
     }
-    store_tile(p.dq + item * p.dq_is + hoff, p.dq_rs, m0, p.Lq, dq, p.scale, lane);
+    store_tile(p.dq + item * p.dq_is + hoff, p.dq_rs, m0, p.Lq, dq, p.dq_mul, lane);
   }
   __syncthreads();
 
@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParam
       fy(dv, st, bO, c0, lane);
       fy(dk, dpt, bQ, c0, lane);
     }
-    store_tile(p.dk + item * p.dk_is + hoff, p.dk_rs, n0, p.Lk, dk, p.scale, lane);
+    store_tile(p.dk + item * p.dk_is + hoff, p.dk_rs, n0, p.Lk, dk, p.dk_mul, lane);
     store_tile(p.dv + item * p.dv_is + hoff, p.dv_rs, n0, p.Lk, dv, 1.f, lane);
   }
 }
@@ -819,6 +819,8 @@ extern "C" int gwd_attention_bwd(const gwd_attn_bwd_desc* d, void* stream_) {
   p.do_is = strides[6]; p.do_rs = strides[7]; p.dq_is = strides[8]; p.dq_rs = strides[9]; p.dk_is = strides[10];
   p.dk_rs = strides[11]; p.dv_is = strides[12]; p.dv_rs = strides[13];
   p.scale = d->scale;
+  p.dq_mul = d->dq_mul != 0.f ? d->dq_mul : d->scale;
+  p.dk_mul = d->dk_mul != 0.f ? d->dk_mul : d->scale;
   dim3 grid(d->heads, d->items);
   static const bool mma_enabled = []() { const char* e = getenv("GWD_ATTN_BWD_MMA"); return !(e && e[0] == '0'); }();
   if (d->o != nullptr && mma_enabled) {

@@ -486,7 +486,7 @@ def linear_wgrad(dy, x, dw, db=None, N=None, K=None, x_coff=0):
 
 
 def attention_bwd(q, k, v, d_o, dq, dk, dv, *, items, heads, Lq, Lk, hd, q_strides, k_strides, v_strides, do_strides,
-                  dq_strides, dk_strides, dv_strides, scale=1.0, o=None, o_strides=None):
+                  dq_strides, dk_strides, dv_strides, scale=1.0, o=None, o_strides=None, dq_mul=0.0, dk_mul=0.0):
     """o: the forward output (bf16) -> tensor-core kernel; None -> CUDA-core kernel that recomputes D = rowsum(P dP)"""
     d = capi.AttnBwdDesc()
     d.q, d.k, d.v, d.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), d_o.data_ptr()
@@ -499,7 +499,7 @@ def attention_bwd(q, k, v, d_o, dq, dk, dv, *, items, heads, Lq, Lk, hd, q_strid
     d.dq_item_stride, d.dq_row_stride = dq_strides
     d.dk_item_stride, d.dk_row_stride = dk_strides
     d.dv_item_stride, d.dv_row_stride = dv_strides
-    d.scale = scale
+    d.scale, d.dq_mul, d.dk_mul = scale, dq_mul, dk_mul
     if o is not None:
         d.o = o.data_ptr()
         d.o_item_stride, d.o_row_stride = o_strides or do_strides

@@ -54,6 +54,10 @@ class LineBranch:
             raise RuntimeError("LineBranch runs on libgwd_b200 CUDA kernels only (no CPU fallback)")
         self.lr, self.betas, self.eps, self.weight_decay, self.max_norm = lr, betas, eps, weight_decay, max_norm
         self.t = 0
+        # soft-max scale hd^-0.5 (multi_head_attention.py:236): the q and k projections are stored pre-scaled by its square
+        # root each (fused q|k GEMM, out_scale) or q alone by the whole factor (cross attention), so the attention kernels
+        # run with scale 1 -- the tcgen05 forward kernel's fast path -- and the backward multiplies dQ / dK back
+        self.rs = float((self.cfg["hidden_dim"] // self.cfg["nheads"]) ** -0.25)
         # ---- flat layout: 2-D weights [N, K] are stored with N padded to 16 (zero rows), vectors padded to 16
         self.index, off = {}, 0
         for name, v in state_dict.items():
@@ -142,7 +146,7 @@ class LineBranch:
         E, nh = self.cfg["hidden_dim"], self.cfg["nheads"]
         o = torch.empty(B * Lq, E, dtype=torch.bfloat16, device=self.dev)
         ops.attention(q, k, v, o, items=B, heads=nh, Lq=Lq, Lk=Lk, hd=E // nh, q_strides=(Lq * q_rs, q_rs),
-                      k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E), o_strides=(Lq * E, E), scale=(E // nh) ** -0.5)
+                      k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E), o_strides=(Lq * E, E))
         return o
 
     def _ln_gemm(self, x, lin, res, ln):
@@ -166,7 +170,7 @@ class LineBranch:
         for ly in self.enc:
             a = ly["attn"]
             xp = ops.add_rows(x, pos, L)
-            qk = conv_gemm(xp, a["qk"].pw)
+            qk = conv_gemm(xp, a["qk"].pw, out_scale=self.rs)
             v = conv_gemm(x, a["v"].pw)
             o = self._attend(qk, qk[:, E:], v, B, L, L, 2 * E, 2 * E)
             x1, z1 = self._ln_gemm(o, a["o"], x, ly["n1"])
@@ -182,12 +186,12 @@ class LineBranch:
         for i, ly in enumerate(self.dec):
             s, cr = ly["self"], ly["cross"]
             tq1 = ops.add_rows(tgt, self.query_pos, Q)
-            qk = conv_gemm(tq1, s["qk"].pw)
+            qk = conv_gemm(tq1, s["qk"].pw, out_scale=self.rs)
             v = conv_gemm(tgt, s["v"].pw)
             o1 = self._attend(qk, qk[:, E:], v, B, Q, Q, 2 * E, 2 * E)
             x1, z1 = self._ln_gemm(o1, s["o"], tgt, ly["n1"])
             tq2 = ops.add_rows(x1, self.query_pos, Q)
-            cq, ck, cv = conv_gemm(tq2, cr["q"].pw), conv_gemm(mem_pos, cr["k"].pw), conv_gemm(memory, cr["v"].pw)
+            cq, ck, cv = conv_gemm(tq2, cr["q"].pw, out_scale=self.rs * self.rs), conv_gemm(mem_pos, cr["k"].pw), conv_gemm(memory, cr["v"].pw)
             o2 = self._attend(cq, ck, cv, B, Q, L, E, E)
             x2, z2 = self._ln_gemm(o2, cr["o"], x1, ly["n2"])
             hm = conv_gemm(x2, ly["l1"].pw, post_act=ACT_RELU)
@@ -216,12 +220,13 @@ class LineBranch:
     def _ln_bwd(self, dy, z, ln, add=None):
         return ops.layernorm_bwd(dy, z, ln[0], ln[2], ln[3], add=add)
 
-    def _attend_bwd(self, q, k, v, o, d_o, B, Lq, Lk, q_rs, k_rs, dq, dk, dv):
+    def _attend_bwd(self, q, k, v, o, d_o, B, Lq, Lk, q_rs, k_rs, dq, dk, dv, fused=True):
         E, nh = self.cfg["hidden_dim"], self.cfg["nheads"]
         ops.attention_bwd(q, k, v, d_o, dq, dk, dv, items=B, heads=nh, Lq=Lq, Lk=Lk, hd=E // nh,
                           q_strides=(Lq * q_rs, q_rs), k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E),
                           do_strides=(Lq * E, E), dq_strides=(Lq * q_rs, q_rs), dk_strides=(Lk * k_rs, k_rs),
-                          dv_strides=(Lk * E, E), scale=(E // nh) ** -0.5, o=o, o_strides=(Lq * E, E))
+                          dv_strides=(Lk * E, E), scale=1.0, o=o, o_strides=(Lq * E, E),
+                          dq_mul=self.rs if fused else self.rs * self.rs, dk_mul=self.rs if fused else 1.0)
 
     def _ffn_bwd(self, ly, d_out, z, hm, x_in, ln):
         dz = self._ln_bwd(d_out, z, ln)
@@ -259,7 +264,7 @@ class LineBranch:
             dz2 = self._ln_bwd(d_x2, s["z2"], ly["n2"])
             d_o = self._lin_bwd(cr["o"], dz2, s["o2"])
             dq, dk, dv = torch.empty(B * Q, E, **bf), torch.empty(B * L, E, **bf), torch.empty(B * L, E, **bf)
-            self._attend_bwd(s["cq"], s["ck"], s["cv"], s["o2"], d_o, B, Q, L, E, E, dq, dk, dv)
+            self._attend_bwd(s["cq"], s["ck"], s["cv"], s["o2"], d_o, B, Q, L, E, E, dq, dk, dv, fused=False)
             dtq = self._lin_bwd(cr["q"], dq, s["tq2"])
             gq += dtq.view(B, Q, E).sum(0, dtype=torch.float32)
             d_x1 = self._add(dtq, dz2)

@@ -261,6 +261,8 @@ typedef struct gwd_attn_bwd_desc {
   float scale;
   const void* o;          /* forward output (bf16), or NULL */
   int64_t o_item_stride, o_row_stride;
+  float dq_mul, dk_mul;   /* dQ = dq_mul * dS K, dK = dk_mul * dS^T Q; 0 = `scale`.  For projections that were stored pre-scaled
+                             (q' = a q, k' = b k, a b = softmax scale): scale = 1, dq_mul = a, dk_mul = b */
 } gwd_attn_bwd_desc;
 int gwd_attention_bwd(const gwd_attn_bwd_desc* d, void* stream);
 /* *out_accum += sum g[i]^2 (fp64 accumulate; the caller zeroes it).  Input of the gradient clip below. */
