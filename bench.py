@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the line-branch training-step measurement")
     return ap.parse_args()
 
 
@@ -128,6 +129,64 @@ def run_reference(args, rank):
                              "sample": "%d forwards of 1x3x480x640 through oracle/gwdepth_oracle.py" % args.steps},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def run_train(args, net, resident, rank, world, dev, barrier, reduce_max_ms):
+    """Data-parallel training step of the LINE BRANCH (gw-depth_b200/train.py): backbone forward (no gradient: the
+    backbone / dense-branch backward is not built), input_proj -> encoder -> decoder -> heads forward with saved
+    activations, SetCriterion with its 6 Hungarian matchings (scipy, host), backward kernels, ONE NCCL all-reduce of the
+    flat gradient buffer, fused clip + AdamW.  Reported as images/s over all ranks, device-timed, max over ranks."""
+    from helpers import synth, synth_weights
+    from gwdepth_b200 import capi, model as M, train
+    B = args.batch
+    _, crit, _ = M.build_model(M.default_args(device="cuda", dropout=0.0))
+    criterion = crit[0].to(dev)
+    lb = train.LineBranch(synth_weights(), net.cfg, device=dev)
+    targets = [[{k: v.to(dev) for k, v in t.items()} for t in synth.synth_batch(B, H, W, seed=100 + 7 * rank + i)[1]]
+               for i in range(len(resident))]
+    plan = net.plan()
+
+    backbone = lambda images: plan.backbone(images)[3]      # noqa: E731  (no gradient: captured into the forward graph)
+
+    def step(i):
+        return lb.train_step(resident[i % len(resident)], targets[i % len(resident)], criterion, producer=backbone)
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    capi.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        total, _ = step(i)
+    e1.record()
+    barrier()
+    ms = reduce_max_ms(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0))
+    # where the time goes on this rank (separate, un-timed-above passes)
+    def timed(fn, n=5):
+        fn()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t) * 1000.0 / n
+    with torch.no_grad():
+        c5 = plan.backbone(resident[0])[3].clone()
+        ms_backbone = timed(lambda: plan.backbone(resident[0]))
+    st = lb._captured(c5) if lb.use_cuda_graph else None
+    ms_graphs = timed(lambda: (st["fwd"].replay(), st["bwd"].replay())) if st else None
+    lo, li = (st["logits"], st["lines"]) if st else lb.forward(c5)
+    lo, li = lo.detach().clone(), li.detach().clone()
+    ms_crit = timed(lambda: criterion.forward_stacked(lo, li, targets[0]))
+    return {"metric": "images_per_sec_train_line_branch_480x640_bf16", "value": world * B * args.steps / (ms / 1000.0), "unit": UNIT,
+            "ms_per_step": ms / args.steps, "n_gpus": world, "global_batch": world * B, "loss": float(total),
+            "params": lb.numel, "allreduce_bytes_per_step": lb.numel * 4 if world > 1 else 0,
+            "breakdown_ms": {"backbone_forward_no_grad": ms_backbone, "branch_forward_plus_backward_graph_replays": ms_graphs,
+                             "set_criterion_6_hungarian_host": ms_crit},
+            "scope": "line branch only: gradients stop at the C5 map (backbone / dense-branch backward not built); "
+                     "dropout 0; lr 1e-4, weight decay 1e-4, clip 0.1 as the reference"}
 
 
 def main():
@@ -245,6 +304,11 @@ def main():
                     "flop_per_step": tot_flop, "kernel_ms_per_step": tot_ms, "kernel_share_of_step": tot_ms / (ms / args.steps),
                     "largest_launch": {"desc": big[3], "tflops": big[2] / (big[0].elapsed_time(big[1]) / 1000.0) / 1e12}}
 
+    # ------------------------------------------------------------ line-branch training step (extra key, not the headline)
+    train_line = None
+    if not args.no_train:
+        train_line = run_train(args, net, resident, rank, world, dev, barrier, reduce_max_ms)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -281,7 +345,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "pipeline": "model.infer_stream: 3 streams, double-buffered H2D / forward / D2H"},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
-            "gpu_eager_port": eager}
+            "gpu_eager_port": eager, "train_line_branch": train_line}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

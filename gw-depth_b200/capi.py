@@ -97,6 +97,7 @@ SIGNATURES = {
     "gwd_transpose": (c_int, [P, L, P, L, L, L, I, P, P]),
     "gwd_linear_wgrad": (c_int, [P, L, P, L, L, I, I, P, L, P, P]),
     "gwd_attention_bwd": (c_int, [ctypes.POINTER(AttnBwdDesc), P]),
+    "gwd_set_loss": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P, P, P, P]),
     "gwd_sumsq": (c_int, [P, L, P, P]),
     "gwd_adamw_step": (c_int, [P, P, P, P, P, L, F_, F_, F_, F_, F_, I, F_, F_, P, P]),
 }

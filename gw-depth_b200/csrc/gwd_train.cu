@@ -686,6 +686,94 @@ __global__ void __launch_bounds__(256) gwd_wgrad_kernel(WgradParams p) {
   if (do_bias && n0 + threadIdx.x < p.N) atomicAdd(p.db + n0 + threadIdx.x, bsum);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Set criterion, forward AND backward in one launch (src/models/glassrgbd.py:154-175 weighted cross entropy over
+// {line, no-object}, :231-244 L1 over matched pairs / num_items) for all S decoder stages: one CTA per stage.
+//   loss_ce[s]   = sum_i w[c_i] nll_i / sum_i w[c_i]         c_i = label of the target matched to query i, else C-1
+//   loss_line[s] = sum_{matched} |line - target|_1 / num_items
+//   dlogits = w_ce[s] w[c_i] / W_s (softmax - onehot),   dlines = w_line[s] sign(line - target) / num_items (0 unmatched)
+// The assignment (stage, image, query, target) comes from the Hungarian solve on the host as int32 columns.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxClasses = 8;
+
+struct SetLossParams {
+  const float* logits; const float* lines; const float* tgt_lines; const int64_t* tgt_labels;
+  const int32_t* match;        // [4][M]: stage, image, query, target (rows of the concatenated targets)
+  const int32_t* stage_off;    // [S+1] ranges of `match` per stage
+  const float* class_w;        // [C]
+  const float* w_ce; const float* w_line;   // [S]
+  const float* num_items;      // [1] (device: all-reduced over ranks by the caller)
+  float* losses;               // [S][2] = loss_ce, loss_line
+  float* dlogits; float* dlines;
+  int S, BQ, Q, C, D, M;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  v = gwd_warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int w = 0; w < (blockDim.x >> 5); ++w) t += red[w];
+  return t;
+}
+
+__global__ void __launch_bounds__(256) gwd_set_loss_kernel(SetLossParams p) {
+  extern __shared__ uint8_t cls[];       // [B*Q]
+  __shared__ float red[8];
+  const int s = blockIdx.x;
+  const float inv_items = 1.f / p.num_items[0];
+  for (int i = threadIdx.x; i < p.BQ; i += blockDim.x) cls[i] = static_cast<uint8_t>(p.C - 1);
+  float* dl = p.dlines + static_cast<int64_t>(s) * p.BQ * p.D;
+  for (int i = threadIdx.x; i < p.BQ * p.D; i += blockDim.x) dl[i] = 0.f;
+  __syncthreads();
+  float l1 = 0.f;
+  const float wl = p.w_line[s] * inv_items;
+  for (int m = p.stage_off[s] + threadIdx.x; m < p.stage_off[s + 1]; m += blockDim.x) {
+    const int b = p.match[p.M + m], q = p.match[2 * p.M + m], t = p.match[3 * p.M + m];
+    cls[b * p.Q + q] = static_cast<uint8_t>(p.tgt_labels[t]);
+    const float* src = p.lines + (static_cast<int64_t>(s) * p.BQ + b * p.Q + q) * p.D;
+    const float* tg = p.tgt_lines + static_cast<int64_t>(t) * p.D;
+    for (int d = 0; d < p.D; ++d) {
+      const float diff = src[d] - tg[d];
+      l1 += fabsf(diff);
+      dl[(b * p.Q + q) * p.D + d] = diff > 0.f ? wl : (diff < 0.f ? -wl : 0.f);
+    }
+  }
+  __syncthreads();
+  float wn = 0.f, wsum = 0.f;
+  const float* lg = p.logits + static_cast<int64_t>(s) * p.BQ * p.C;
+  for (int i = threadIdx.x; i < p.BQ; i += blockDim.x) {
+    float mx = -INFINITY;
+    for (int c = 0; c < p.C; ++c) mx = fmaxf(mx, lg[i * p.C + c]);
+    float se = 0.f;
+    for (int c = 0; c < p.C; ++c) se += expf(lg[i * p.C + c] - mx);
+    const int c = cls[i];
+    const float w = p.class_w[c];
+    wn += w * (mx + logf(se) - lg[i * p.C + c]);
+    wsum += w;
+  }
+  const float l1_all = block_sum(l1, red);
+  const float wn_all = block_sum(wn, red);
+  const float W = block_sum(wsum, red);
+  if (threadIdx.x == 0) {
+    p.losses[2 * s] = wn_all / W;
+    p.losses[2 * s + 1] = l1_all * inv_items;
+  }
+  float* dg = p.dlogits + static_cast<int64_t>(s) * p.BQ * p.C;
+  const float k = p.w_ce[s] / W;
+  for (int i = threadIdx.x; i < p.BQ; i += blockDim.x) {
+    float mx = -INFINITY;
+    for (int c = 0; c < p.C; ++c) mx = fmaxf(mx, lg[i * p.C + c]);
+    float se = 0.f;
+    for (int c = 0; c < p.C; ++c) se += expf(lg[i * p.C + c] - mx);
+    const int ci = cls[i];
+    const float kw = k * p.class_w[ci];
+    for (int c = 0; c < p.C; ++c) dg[i * p.C + c] = kw * (expf(lg[i * p.C + c] - mx) / se - (c == ci ? 1.f : 0.f));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // optimizer
 // ------------------------------------------------------------------------------------------------
@@ -896,6 +984,26 @@ extern "C" int gwd_linear_wgrad(const void* dy, int64_t dy_rs, const void* x, in
   GWD_CUDA(cudaFuncSetAttribute(gwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(static_cast<unsigned>(gwd_ceil_div(N, kWgT)), static_cast<unsigned>(gwd_ceil_div(K, kWgT)), static_cast<unsigned>(split));
   gwd_wgrad_kernel<<<grid, 256, smem, stream>>>(p);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_set_loss(const float* logits, const float* lines, const float* tgt_lines, const int64_t* tgt_labels,
+                            const int32_t* match, const int32_t* stage_off, const float* class_w, const float* w_ce,
+                            const float* w_line, const float* num_items, int32_t S, int32_t B, int32_t Q, int32_t C, int32_t D,
+                            int32_t M, float* losses, float* dlogits, float* dlines, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(logits && lines && tgt_lines && tgt_labels && match && stage_off && class_w && w_ce && w_line && num_items &&
+                    losses && dlogits && dlines, "gwd_set_loss: null pointer");
+  GWD_CHECK_ARG(S > 0 && B > 0 && Q > 0 && C >= 2 && C <= kMaxClasses && D > 0 && M >= 0 && B * Q <= 160 * 1024,
+                "gwd_set_loss: bad shape (2 <= classes <= 8, B*Q <= 163840)");
+  SetLossParams p;
+  p.logits = logits; p.lines = lines; p.tgt_lines = tgt_lines; p.tgt_labels = tgt_labels; p.match = match; p.stage_off = stage_off;
+  p.class_w = class_w; p.w_ce = w_ce; p.w_line = w_line; p.num_items = num_items; p.losses = losses; p.dlogits = dlogits;
+  p.dlines = dlines; p.S = S; p.BQ = B * Q; p.Q = Q; p.C = C; p.D = D; p.M = M;
+  const size_t smem = static_cast<size_t>(B) * Q;
+  if (smem > 48 * 1024) GWD_CUDA(cudaFuncSetAttribute(gwd_set_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  gwd_set_loss_kernel<<<S, 256, smem, stream>>>(p);
   GWD_LAUNCHED();
   return GWD_OK;
 }

@@ -391,6 +391,45 @@ class SetCriterion(nn.Module):
         self.last_indices = indices
         return losses
 
+    @torch.no_grad()
+    def forward_backward_stacked(self, logits, lines, targets):
+        """forward_stacked AND its gradient in one gwd_set_loss launch: -> (losses dict, dlogits, dlines) where the
+        gradients are those of sum_k weight_dict[k] * losses[k].  No autograd graph, no per-loss torch kernels: the host
+        only solves the assignments and uploads them (one int32 [4, M] copy)."""
+        S, B, Q = logits.shape[:3]
+        dev = logits.device
+        indices = self.matcher.forward_stacked(logits, lines, targets)
+        n = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float, device=dev)
+        if _world_size() > 1:
+            torch.distributed.all_reduce(n)
+        num_items = torch.clamp(n / _world_size(), min=1)
+        starts = [0]
+        for t in targets:
+            starts.append(starts[-1] + len(t["labels"]))
+        cols, stage_off = [], [0]
+        for s_, stage in enumerate(indices):
+            for b, (i, j) in enumerate(stage):
+                cols.append(torch.stack([torch.full_like(i, s_), torch.full_like(i, b), i, j + starts[b]]))
+            stage_off.append(stage_off[-1] + sum(len(i) for i, _ in stage))
+        match = torch.cat(cols, dim=1).to(torch.int32).contiguous().to(dev, non_blocking=True)
+        soff = torch.tensor(stage_off, dtype=torch.int32).to(dev, non_blocking=True)
+        key = [("loss_ce" + ("" if s_ == S - 1 else "_%d" % s_), "loss_line" + ("" if s_ == S - 1 else "_%d" % s_)) for s_ in range(S)]
+        wd = self.weight_dict
+        w_ce = torch.tensor([float(wd.get(a, 0.0)) if "lines_labels" in self.losses else 0.0 for a, _ in key]).to(dev, non_blocking=True)
+        w_line = torch.tensor([float(wd.get(b, 0.0)) if "lines" in self.losses else 0.0 for _, b in key]).to(dev, non_blocking=True)
+        tgt_lines = torch.cat([t["lines"] for t in targets]).float().contiguous()
+        tgt_labels = torch.cat([t["labels"] for t in targets]).to(torch.int64).contiguous()
+        vals, dlogits, dlines = ops.set_loss(logits.float().contiguous(), lines.float().contiguous(), tgt_lines, tgt_labels, match,
+                                             soff, self.empty_weight.to(dev).float().contiguous(), w_ce, w_line, num_items)
+        losses = {}
+        for s_, (a, b) in enumerate(key):
+            if "lines_labels" in self.losses:
+                losses[a] = vals[s_, 0]
+            if "lines" in self.losses:
+                losses[b] = vals[s_, 1]
+        self.last_indices = indices
+        return losses, dlogits, dlines
+
     def forward(self, outputs, targets, origin_indices=None, depth_gt=None):
         plain = {k: v for k, v in outputs.items() if k != "aux_outputs"}
         origin_indices = self.matcher(plain, targets)

@@ -506,6 +506,20 @@ def attention_bwd(q, k, v, d_o, dq, dk, dv, *, items, heads, Lq, Lk, hd, q_strid
     capi.check(_L().gwd_attention_bwd(ctypes.byref(d), _stream()), "gwd_attention_bwd")
 
 
+def set_loss(logits, lines, tgt_lines, tgt_labels, match, stage_off, class_w, w_ce, w_line, num_items):
+    """-> (losses fp32 [S,2], dlogits, dlines) of the weighted set criterion; see gwd_set_loss in include/gwd_b200.h"""
+    S, B, Q, C = logits.shape
+    D = lines.shape[-1]
+    assert logits.dtype == lines.dtype == torch.float32 and logits.is_contiguous() and lines.is_contiguous()
+    assert match.dtype == torch.int32 and match.is_contiguous() and match.shape[0] == 4
+    losses = torch.empty(S, 2, dtype=torch.float32, device=logits.device)
+    dlogits, dlines = torch.empty_like(logits), torch.empty_like(lines)
+    capi.check(_L().gwd_set_loss(_ptr(logits), _ptr(lines), _ptr(tgt_lines), _ptr(tgt_labels), _ptr(match), _ptr(stage_off),
+                                 _ptr(class_w), _ptr(w_ce), _ptr(w_line), _ptr(num_items), S, B, Q, C, D, match.shape[1], _ptr(losses),
+                                 _ptr(dlogits), _ptr(dlines), _stream()), "gwd_set_loss")
+    return losses, dlogits, dlines
+
+
 def sumsq(g, out):
     """out (fp64 [1], zeroed by the caller) += sum g^2"""
     capi.check(_L().gwd_sumsq(_ptr(g), g.numel(), _ptr(out), _stream()), "gwd_sumsq")

@@ -309,22 +309,25 @@ class LineBranch:
                        sumsq_buf=self.sumsq)
 
     # ------------------------------------------------------------------ CUDA graphs
-    def _captured(self, c5):
+    def _captured(self, c5, producer=None):
         """forward and backward have no host synchronisation, so each is captured once per input shape (same memory pool:
-        the backward graph reads the activations the forward graph leaves behind) and replayed as one launch."""
-        key = tuple(c5.shape)
+        the backward graph reads the activations the forward graph leaves behind) and replayed as one launch.  With a
+        `producer` (e.g. the frozen backbone: images -> C5) the input is the producer's input and its kernels are part of
+        the forward graph."""
+        key = (tuple(c5.shape), producer is not None)
         st = self._graphs.get(key)
         if st is None:
             st = {"c5": c5.clone()}
+            feed = (lambda: producer(st["c5"])) if producer is not None else (lambda: st["c5"])
             side = torch.cuda.Stream(device=self.dev)
             side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):          # warm-up: lazy kernel attributes, cached tables
-                lo, li = self.forward(st["c5"])
+            with torch.cuda.stream(side):          # warm-up: lazy kernel attributes, cached tables, cuDNN plans
+                lo, li = self.forward(feed())
                 self.backward(torch.zeros_like(lo), torch.zeros_like(li))
             torch.cuda.current_stream().wait_stream(side)
             st["fwd"] = torch.cuda.CUDAGraph()
             with torch.cuda.graph(st["fwd"]):
-                st["logits"], st["lines"] = self.forward(st["c5"])
+                st["logits"], st["lines"] = self.forward(feed())
             st["tape"] = self.tape
             st["dlogits"], st["dlines"] = torch.zeros_like(st["logits"]), torch.zeros_like(st["lines"])
             st["bwd"] = torch.cuda.CUDAGraph()
@@ -333,20 +336,19 @@ class LineBranch:
             self._graphs[key] = st
         return st
 
-    def loss_and_grads(self, c5, targets, criterion):
-        """forward + SetCriterion + backward; returns (weighted total loss tensor, dict of losses, dC5)"""
-        st = self._captured(c5) if self.use_cuda_graph else None
+    def loss_and_grads(self, c5, targets, criterion, producer=None):
+        """forward + SetCriterion + backward; returns (weighted total loss tensor, dict of losses, dC5).  `producer`: optional
+        gradient-free front end (images -> C5, e.g. Engine.backbone); then `c5` is ITS input."""
+        st = self._captured(c5, producer) if self.use_cuda_graph else None
         if st is not None:
             st["c5"].copy_(c5, non_blocking=True)
             st["fwd"].replay()
             logits, lines = st["logits"], st["lines"]
         else:
-            logits, lines = self.forward(c5)
-        logits = logits.detach().clone().requires_grad_(True)
-        lines = lines.detach().clone().requires_grad_(True)
-        losses = criterion.forward_stacked(logits, lines, targets)
+            with torch.no_grad():
+                logits, lines = self.forward(producer(c5) if producer is not None else c5)
+        losses, dlogits, dlines = criterion.forward_backward_stacked(logits, lines, targets)
         total = sum(losses[k] * criterion.weight_dict[k] for k in losses if k in criterion.weight_dict)
-        dlogits, dlines = torch.autograd.grad(total, (logits, lines))
         self.last_cotangents = (dlogits, dlines)
         if st is not None:
             st["dlogits"].copy_(dlogits, non_blocking=True)
@@ -357,7 +359,7 @@ class LineBranch:
             dc5 = self.backward(dlogits, dlines)
         return total.detach(), {k: v.detach() for k, v in losses.items()}, dc5
 
-    def train_step(self, c5, targets, criterion):
-        total, losses, _ = self.loss_and_grads(c5, targets, criterion)
+    def train_step(self, c5, targets, criterion, producer=None):
+        total, losses, _ = self.loss_and_grads(c5, targets, criterion, producer)
         self.step()
         return total, losses

@@ -265,6 +265,15 @@ typedef struct gwd_attn_bwd_desc {
                              (q' = a q, k' = b k, a b = softmax scale): scale = 1, dq_mul = a, dk_mul = b */
 } gwd_attn_bwd_desc;
 int gwd_attention_bwd(const gwd_attn_bwd_desc* d, void* stream);
+/* SetCriterion forward + backward for all S decoder stages in one launch (src/models/glassrgbd.py:154-175,231-244,308-358):
+ * logits fp32 [S,B,Q,C], lines fp32 [S,B,Q,D]; match int32 [4][M] = (stage, image, query, target row) of every matched
+ * pair, grouped by stage with stage_off int32 [S+1]; class_w fp32 [C] (eos_coef on the last class); num_items fp32 [1]
+ * on the device.  losses fp32 [S][2] = (loss_ce, loss_line); dlogits / dlines = gradients of
+ * sum_s w_ce[s] loss_ce[s] + w_line[s] loss_line[s]. */
+int gwd_set_loss(const float* logits, const float* lines, const float* tgt_lines, const int64_t* tgt_labels, const int32_t* match,
+                 const int32_t* stage_off, const float* class_w, const float* w_ce, const float* w_line, const float* num_items,
+                 int32_t S, int32_t B, int32_t Q, int32_t C, int32_t D, int32_t M, float* losses, float* dlogits, float* dlines,
+                 void* stream);
 /* *out_accum += sum g[i]^2 (fp64 accumulate; the caller zeroes it).  Input of the gradient clip below. */
 int gwd_sumsq(const float* g, int64_t n, double* out_accum, void* stream);
 /* torch.nn.utils.clip_grad_norm_(max_norm) + torch.optim.AdamW step `step` (1-based) over a flat fp32 segment:
