@@ -95,6 +95,7 @@ SIGNATURES = {
     "gwd_layernorm_bwd": (c_int, [P, L, P, L, P, F_, P, L, P, L, P, P, L, I, P]),
     "gwd_act_bwd": (c_int, [P, I, L, P, I, L, I, P, L, L, I, I, P]),
     "gwd_transpose": (c_int, [P, L, P, L, L, L, I, P, P]),
+    "gwd_transpose_batch": (c_int, [P, P, I, I, P]),
     "gwd_linear_wgrad": (c_int, [P, L, P, L, L, I, I, P, L, P, P]),
     "gwd_attention_bwd": (c_int, [ctypes.POINTER(AttnBwdDesc), P]),
     "gwd_set_loss": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P, P, P, P]),

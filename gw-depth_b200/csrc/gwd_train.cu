@@ -191,6 +191,54 @@ gwd_transpose_kernel(const bf16* __restrict__ x, int64_t x_rs, bf16* __restrict_
   }
 }
 
+
+// batched transpose: one launch for every weight mirror of the branch (89 matrices); CTA -> (matrix, 64x64 tile) through
+// a prefix table of tile counts.  table[m] = {src, dst, rows, cols, src row stride, dst row stride}
+__global__ void __launch_bounds__(256)
+gwd_transpose_batch_kernel(const int64_t* __restrict__ table, const int32_t* __restrict__ tile_prefix, int n_mats) {
+  __shared__ float tile[64][65];
+  int lo = 0, hi = n_mats;                 // largest m with tile_prefix[m] <= blockIdx.x
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (tile_prefix[mid] <= static_cast<int>(blockIdx.x)) lo = mid; else hi = mid;
+  }
+  const int64_t* e = table + 6 * lo;
+  const bf16* x = reinterpret_cast<const bf16*>(e[0]);
+  bf16* out = reinterpret_cast<bf16*>(e[1]);
+  const int rows = static_cast<int>(e[2]), C = static_cast<int>(e[3]);
+  const int64_t x_rs = e[4], out_rs = e[5];
+  const int local = blockIdx.x - tile_prefix[lo];
+  const int tiles_r = (rows + 63) >> 6;
+  const int r0 = (local % tiles_r) * 64, c0 = (local / tiles_r) * 64;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int rr = ty; rr < 64; rr += 8) {
+    const int r = r0 + rr, c = c0 + 2 * tx;
+    float2 v = make_float2(0.f, 0.f);
+    if (r < rows && c < C) v = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + r * x_rs + c));
+    tile[rr][2 * tx] = v.x;
+    tile[rr][2 * tx + 1] = v.y;
+  }
+  __syncthreads();
+  for (int cc = ty; cc < 64; cc += 8) {
+    const int c = c0 + cc, r = r0 + 2 * tx;
+    if (c < C && r < rows)
+      *reinterpret_cast<__nv_bfloat162*>(out + c * out_rs + r) = __floats2bfloat162_rn(tile[2 * tx][cc], tile[2 * tx + 1][cc]);
+  }
+}
+
+// vector path of gwd_act_bwd: bf16 dy, bf16 y, no padding, 8 elements per thread
+__global__ void __launch_bounds__(256)
+gwd_act_bwd_vec_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, int act, bf16* __restrict__ out, int64_t n8) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float d[8], v[8];
+    ld8(dy + i * 8, d);
+    ld8(y + i * 8, v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) d[e] = act == GWD_ACT_RELU ? (v[e] > 0.f ? d[e] : 0.f) : d[e] * v[e] * (1.f - v[e]);
+    st8(out + i * 8, d);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // attention backward, head_dim 32.  One CTA per (head, item): Q, K, V, dO of the head sit in shared memory as bf16
 // rows of 17 words (conflict-free when lanes walk rows).  Pass A: a warp owns a query row, lanes own keys;
@@ -858,8 +906,16 @@ extern "C" int gwd_act_bwd(const void* dy, int32_t dy_f32, int64_t dy_rs, const 
   GWD_CHECK_ARG(dy && out && rows > 0 && n > 0 && out_cols >= n && out_rs >= out_cols, "gwd_act_bwd: bad argument");
   GWD_CHECK_ARG(act == GWD_ACT_NONE || act == GWD_ACT_RELU || act == GWD_ACT_SIGMOID, "gwd_act_bwd: activation %d unsupported", act);
   GWD_CHECK_ARG(act == GWD_ACT_NONE || y != nullptr, "gwd_act_bwd: y needed");
-  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(rows * out_cols, 256), 8 * gwd_num_sms()));
   bf16* o = static_cast<bf16*>(out);
+  if (!dy_f32 && !y_f32 && act != GWD_ACT_NONE && n == out_cols && dy_rs == n && y_rs == n && out_rs == n && n % 8 == 0 &&
+      ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const int64_t n8 = rows * n / 8;
+    const unsigned g = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(n8, 256), 16 * gwd_num_sms()));
+    gwd_act_bwd_vec_kernel<<<g, 256, 0, stream>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(y), act, o, n8);
+    GWD_LAUNCHED();
+    return GWD_OK;
+  }
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(rows * out_cols, 256), 8 * gwd_num_sms()));
   if (dy_f32 && y_f32)
     gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(dy), dy_rs, static_cast<const float*>(y), y_rs, act, o, out_rs, rows, n, out_cols);
   else if (dy_f32)
@@ -1004,6 +1060,15 @@ extern "C" int gwd_set_loss(const float* logits, const float* lines, const float
   const size_t smem = static_cast<size_t>(B) * Q;
   if (smem > 48 * 1024) GWD_CUDA(cudaFuncSetAttribute(gwd_set_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   gwd_set_loss_kernel<<<S, 256, smem, stream>>>(p);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_transpose_batch(const int64_t* table, const int32_t* tile_prefix, int32_t n_mats, int32_t total_tiles,
+                                   void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(table && tile_prefix && n_mats > 0 && total_tiles > 0, "gwd_transpose_batch: bad argument");
+  gwd_transpose_batch_kernel<<<total_tiles, 256, 0, stream>>>(table, tile_prefix, n_mats);
   GWD_LAUNCHED();
   return GWD_OK;
 }

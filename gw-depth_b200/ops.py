@@ -476,6 +476,25 @@ def transpose(x, colsum=None, C=None, x_coff=0, pad_to=64, out=None):
     return out
 
 
+def transpose_batch_tables(pairs):
+    """pairs: list of (src [rows, cols] bf16 view with unit column stride, dst [cols, rows] bf16 contiguous) ->
+    device tables for transpose_batch"""
+    tab, prefix = [], [0]
+    for src, dst in pairs:
+        rows, cols = src.shape
+        assert src.dtype == dst.dtype == torch.bfloat16 and src.stride(1) == 1 and dst.shape == (cols, rows) and dst.is_contiguous()
+        assert rows % 2 == 0 and cols % 2 == 0
+        tab.append([src.data_ptr(), dst.data_ptr(), rows, cols, src.stride(0), dst.stride(0)])
+        prefix.append(prefix[-1] + ((rows + 63) // 64) * ((cols + 63) // 64))
+    dev = pairs[0][0].device
+    return (torch.tensor(tab, dtype=torch.int64, device=dev), torch.tensor(prefix, dtype=torch.int32, device=dev), len(pairs), prefix[-1])
+
+
+def transpose_batch(tables):
+    table, prefix, n, total = tables
+    capi.check(_L().gwd_transpose_batch(_ptr(table), _ptr(prefix), n, total, _stream()), "gwd_transpose_batch")
+
+
 def linear_wgrad(dy, x, dw, db=None, N=None, K=None, x_coff=0):
     """dw [N, K] (fp32 view) += dy[:, :N]^T x[:, x_coff:x_coff+K]; db [N] += column sums of dy.  dy, x: bf16 [rows, *]"""
     N = N or dw.shape[0]

@@ -77,7 +77,7 @@ class LineBranch:
         self.Wb = self.P.to(torch.bfloat16)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self._build_views()
-        self._tables, self.tape, self._graphs = {}, None, {}
+        self._tables, self.tape, self._graphs, self._wt_tables = {}, None, {}, None
         import os
         self.use_cuda_graph = os.environ.get("GWD_CUDA_GRAPH", "1") != "0"
 
@@ -138,8 +138,9 @@ class LineBranch:
 
     def refresh_transposes(self):
         """W^T mirrors for the data-gradient GEMMs (first thing in every backward: the mirror changes with every step)"""
-        for lin in self.lins:
-            ops.transpose(lin.w2d, out=lin.wT, pad_to=16)
+        if self._wt_tables is None:
+            self._wt_tables = ops.transpose_batch_tables([(lin.w2d, lin.wT) for lin in self.lins])
+        ops.transpose_batch(self._wt_tables)
 
     # ------------------------------------------------------------------ forward (activations kept for the backward)
     def _attend(self, q, k, v, B, Lq, Lk, q_rs, k_rs):

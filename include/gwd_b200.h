@@ -242,6 +242,10 @@ int gwd_act_bwd(const void* dy, int32_t dy_f32, int64_t dy_rs, const void* y, in
  * [C]) is ACCUMULATED with the column sums of x = the bias gradient when x is dY. */
 int gwd_transpose(const void* x, int64_t x_rs, void* out, int64_t out_rs, int64_t rows, int64_t rows_pad, int32_t C,
                   float* colsum, void* stream);
+/* n_mats transposes in one launch (the W^T mirrors of every Linear of the branch after an optimizer step).  Device
+ * tables: table int64 [n_mats][6] = {src ptr, dst ptr, rows, cols, src row stride, dst row stride} (bf16, even sizes,
+ * 4-byte aligned), tile_prefix int32 [n_mats+1] = running count of 64x64 tiles (ceil(rows/64) * ceil(cols/64) each). */
+int gwd_transpose_batch(const int64_t* table, const int32_t* tile_prefix, int32_t n_mats, int32_t total_tiles, void* stream);
 /* nn.Linear weight gradient: dw[n, k] (fp32, row stride dw_rs) += sum_r dy[r, n] * x[r, k], db[n] += sum_r dy[r, n]
  * (db optional).  dy [rows, N] and x [rows, K] are bf16 with row strides; both are contracted over their slow axis, which
  * the kernel handles with ldmatrix.trans (no transposed copies); rows are split across CTAs and reduced with fp32

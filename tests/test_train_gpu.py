@@ -79,6 +79,20 @@ def test_transpose_and_colsum(rows, C):
     assert rel_l2(cs, x.float().sum(0)) < 1e-5
 
 
+def test_transpose_batch():
+    ops = _ops()
+    g = _g(9)
+    flat = torch.randn(1_400_000, generator=g).bfloat16().cuda()
+    shapes, off, pairs = [(16, 256), (768, 256), (2048, 256), (256, 2048), (112, 256), (64, 80)], 0, []
+    for r, c in shapes:
+        pairs.append((flat[off:off + r * c].view(r, c), torch.zeros(c, r, dtype=torch.bfloat16, device="cuda")))
+        off += r * c
+    pairs.append((pairs[1][0][256:512], torch.zeros(256, 256, dtype=torch.bfloat16, device="cuda")))     # a row slice
+    ops.transpose_batch(ops.transpose_batch_tables(pairs))
+    for src, dst in pairs:
+        assert torch.equal(dst, src.t())
+
+
 def test_weight_gradient_gemm_on_transposed_operands():
     """dW = dY^T X and dX = dY W through gwd_conv_gemm (fp32 output, multi-tile N, K = rows padded to 64)"""
     ops = _ops()
