@@ -82,9 +82,9 @@ SIGNATURES = {
     "gwd_upsample_nearest": (c_int, [P, L, I, I, I, P, L, I, I, I, P, L, P]),
     "gwd_avgpool": (c_int, [P, L, I, I, I, I, P, L, I, P]),
     "gwd_bilinear_up": (c_int, [P, L, I, I, I, P, L, I, I, I, P]),
-    "gwd_sample_bilinear": (c_int, [P, L, I, P, I, I, I, I, P, I, P, P]),
+    "gwd_sample_bilinear": (c_int, [P, L, I, P, L, I, I, I, I, P, I, P, P]),
     "gwd_sample_scalar": (c_int, [P, I, I, I, P, I, P, P]),
-    "gwd_line_ref_gather": (c_int, [P, L, P, P, I, P, L, I, I, I, I, I, I, P]),
+    "gwd_line_ref_gather": (c_int, [P, L, P, L, P, I, P, L, I, I, I, I, I, I, P]),
     "gwd_anchor_mix": (c_int, [P, L, P, I, L, I, P, P]),
     "gwd_nchw_to_nhwc": (c_int, [P, I, I, L, P, I, P]),
     "gwd_stem_conv_pool": (c_int, [P, P, P, P, I, I, I, P]),

@@ -325,8 +325,8 @@ __device__ __forceinline__ float unnorm(float g, int size) { return ((g + 1.f) *
 
 // bilinear sample of a bf16 map (+ an fp32 [H,W,C] table, e.g. the sine position code) at K points per image:
 // out fp32 [B,K,C]
-__global__ void gwd_sample_bilinear_kernel(const bf16* x, int64_t x_rs, int x_coff, const float* table, int B, int H, int W,
-                                           int C, const float* coords, int K, float* out) {
+__global__ void gwd_sample_bilinear_kernel(const bf16* x, int64_t x_rs, int x_coff, const float* table, int64_t table_bs, int B,
+                                           int H, int W, int C, const float* coords, int K, float* out) {
   int64_t total = static_cast<int64_t>(B) * K * C;
   for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -347,7 +347,7 @@ __global__ void gwd_sample_bilinear_kernel(const bf16* x, int64_t x_rs, int x_co
         float wgt = (dx ? lx : 1.f - lx) * (dy ? ly : 1.f - ly);
         float v = 0.f;
         if (x) v += __bfloat162float(x[((static_cast<int64_t>(b) * H + yy) * W + xx) * x_rs + x_coff + c]);
-        if (table) v += table[(static_cast<int64_t>(yy) * W + xx) * C + c];
+        if (table) v += table[b * table_bs + (static_cast<int64_t>(yy) * W + xx) * C + c];
         acc = fmaf(wgt, v, acc);
       }
     out[idx] = acc;
@@ -374,8 +374,8 @@ __global__ void gwd_sample_scalar_kernel(const float* x, int B, int H, int W, co
 // reference tokens of the 1/32 line-window attention (multiscale_transformerr.py:676-701): nearest sample of the
 // windowed (LayerNorm'ed, padded, shifted) feature map + nearest sample of the shifted position table at R points.
 // win: [B*nW*N, C] (window layout produced by gwd_window_gather), pos: fp32 [H,W,C] (un-shifted), out bf16 [B,R,C]
-__global__ void gwd_line_ref_gather_kernel(const bf16* win, int64_t win_rs, const float* pos, const float* coords, int R,
-                                           bf16* out, int64_t out_rs, WinGeom gm, int C) {
+__global__ void gwd_line_ref_gather_kernel(const bf16* win, int64_t win_rs, const float* pos, int64_t pos_bs, const float* coords,
+                                           int R, bf16* out, int64_t out_rs, WinGeom gm, int C) {
   int64_t wid = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (wid >= static_cast<int64_t>(gm.B) * R) return;
@@ -403,7 +403,7 @@ __global__ void gwd_line_ref_gather_kernel(const bf16* win, int64_t win_rs, cons
     float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (fvalid) load8(win + wrow * win_rs + c, f);
     if (pvalid) {
-      const float* pp = pos + (static_cast<int64_t>(sy) * gm.W + sx) * C + c;
+      const float* pp = pos + b * pos_bs + (static_cast<int64_t>(sy) * gm.W + sx) * C + c;
 #pragma unroll
       for (int i = 0; i < 8; ++i) f[i] += pp[i];
     }
@@ -586,13 +586,14 @@ extern "C" int gwd_bilinear_up(const void* x, int64_t x_rs, int32_t B, int32_t h
   return GWD_OK;
 }
 
-extern "C" int gwd_sample_bilinear(const void* x, int64_t x_rs, int32_t x_coff, const float* table, int32_t B, int32_t H,
-                                   int32_t W, int32_t C, const float* coords, int32_t K, float* out, void* stream_) {
+extern "C" int gwd_sample_bilinear(const void* x, int64_t x_rs, int32_t x_coff, const float* table, int64_t table_bstride,
+                                   int32_t B, int32_t H, int32_t W, int32_t C, const float* coords, int32_t K, float* out,
+                                   void* stream_) {
   GWD_STREAM;
   GWD_CHECK_ARG((x || table) && coords && out, "gwd_sample_bilinear: null pointer");
   int64_t total = static_cast<int64_t>(B) * K * C;
-  gwd_sample_bilinear_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, x_coff, table, B,
-                                                                       H, W, C, coords, K, out);
+  gwd_sample_bilinear_kernel<<<grid_for(total, 256), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, x_coff, table,
+                                                                       table_bstride, B, H, W, C, coords, K, out);
   GWD_LAUNCHED();
   return GWD_OK;
 }
@@ -607,8 +608,8 @@ extern "C" int gwd_sample_scalar(const float* x, int32_t B, int32_t H, int32_t W
   return GWD_OK;
 }
 
-extern "C" int gwd_line_ref_gather(const void* win, int64_t win_rs, const float* pos, const float* coords, int32_t R,
-                                   void* out, int64_t out_rs, int32_t B, int32_t H, int32_t W, int32_t ws, int32_t shift,
+extern "C" int gwd_line_ref_gather(const void* win, int64_t win_rs, const float* pos, int64_t pos_bstride, const float* coords,
+                                   int32_t R, void* out, int64_t out_rs, int32_t B, int32_t H, int32_t W, int32_t ws, int32_t shift,
                                    int32_t C, void* stream_) {
   GWD_STREAM;
   GWD_CHECK_ARG(win && pos && coords && out && GWD_ALIGN8(C) && GWD_ALIGN8(win_rs) && GWD_ALIGN8(out_rs),
@@ -617,7 +618,7 @@ extern "C" int gwd_line_ref_gather(const void* win, int64_t win_rs, const float*
   make_geom(gm, B, H, W, ws, shift);
   int64_t warps = static_cast<int64_t>(B) * R;
   gwd_line_ref_gather_kernel<<<static_cast<unsigned>(gwd_ceil_div(warps * 32, 128)), 128, 0, stream>>>(
-      static_cast<const bf16*>(win), win_rs, pos, coords, R, static_cast<bf16*>(out), out_rs, gm, C);
+      static_cast<const bf16*>(win), win_rs, pos, pos_bstride, coords, R, static_cast<bf16*>(out), out_rs, gm, C);
   GWD_LAUNCHED();
   return GWD_OK;
 }

@@ -48,6 +48,32 @@ def sine_table(h, w, num_pos_feats, normalize, device):
     return torch.cat((py, px), dim=2).reshape(h * w, 2 * num_pos_feats).contiguous()
 
 
+def sine_tables_masked(mask, num_pos_feats, normalize):
+    """PositionEmbeddingSine for a PADDED batch (src/models/position_encoding.py:28-48): mask [B,h,w] bool (True =
+    padding) -> per-image fp32 tables [B, h*w, 2*num_pos_feats] (same channel order as sine_table).  A dozen small
+    torch ops on [B,h,w] maps; no host synchronisation."""
+    not_mask = ~mask
+    y = not_mask.cumsum(1, dtype=torch.float32)
+    x = not_mask.cumsum(2, dtype=torch.float32)
+    if normalize:
+        y = y / (y[:, -1:, :] + 1e-6) * (2 * math.pi)
+        x = x / (x[:, :, -1:] + 1e-6) * (2 * math.pi)
+    i = torch.arange(num_pos_feats, dtype=torch.float32, device=mask.device)
+    dim_t = 10000 ** (2 * torch.div(i, 2, rounding_mode="floor") / num_pos_feats)
+
+    def enc(v):
+        a = v[..., None] / dim_t
+        return torch.stack((a[..., 0::2].sin(), a[..., 1::2].cos()), dim=4).flatten(3)
+
+    B, h, w = mask.shape
+    return torch.cat((enc(y), enc(x)), dim=3).reshape(B, h * w, 2 * num_pos_feats).contiguous()
+
+
+def level_mask(mask, size):
+    """the padding mask at a backbone level (src/models/backbone.py:79: legacy nearest interpolation)"""
+    return F.interpolate(mask[None].float(), size=size).to(torch.bool)[0]
+
+
 def shift_mask(H, W, ws, shift, device):
     """the SW-MSA mask of multiscale_transformerr.py:937-955 (-100 between different regions), fp32 [nW, N, N]"""
     Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
@@ -330,7 +356,7 @@ class Engine:
         return self._tables[key]
 
     # ------------------------------------------------------------------ DETR transformer
-    def _mha(self, pk, q_in, k_in, v_in, B, Lq, Lk, E, nh, fused_qk):
+    def _mha(self, pk, q_in, k_in, v_in, B, Lq, Lk, E, nh, fused_qk, key_padding=None):
         """multi_head_attention_forward (src/models/multi_head_attention.py:188-380) without the dead head-averaged
         weights.  q_in/k_in/v_in are [B*L, E] token matrices; returns the un-projected attention output."""
         hd = E // nh
@@ -342,24 +368,28 @@ class Engine:
         v = conv_gemm(v_in, pk["v"])
         o = torch.empty(B * Lq, E, dtype=torch.bfloat16, device=self.dev)
         ops.attention(q, k, v, o, items=B, heads=nh, Lq=Lq, Lk=Lk, hd=hd, q_strides=(Lq * q_rs, q_rs),
-                      k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E), o_strides=(Lq * E, E))
+                      k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E), o_strides=(Lq * E, E), key_padding=key_padding)
         return o
 
-    def detr(self, src, B, h, w):
+    def detr(self, src, B, h, w, mask5=None):
         """Transformer.forward (src/models/transformer.py:47-61): 6 post-norm encoder layers (:149-162), 6 decoder layers
         (:212-233) with decoder.norm on every layer output (:105-123).  src: [B*L, E] bf16 tokens."""
         c = self.cfg
         E, nh, L, Q = c["hidden_dim"], c["nheads"], h * w, c["num_queries"]
-        pos = self.table(("pos5", h, w), lambda: sine_table(h, w, E // 2, True, self.dev).to(torch.bfloat16))
+        if mask5 is None:
+            pos, period, kpm = self.table(("pos5", h, w), lambda: sine_table(h, w, E // 2, True, self.dev).to(torch.bfloat16)), L, None
+        else:       # padded batch: per-image position codes, padded keys masked out (transformer.py:52-57, mha.py:343-349)
+            pos, period = sine_tables_masked(mask5, E // 2, True).view(B * L, E).to(torch.bfloat16), B * L
+            kpm = mask5.reshape(B, L).to(torch.uint8).contiguous()
         x = src
         for ly in self.enc:
-            xp = ops.add_rows(x, pos, L)
-            o = self._mha(ly["attn"], xp, xp, x, B, L, L, E, nh, True)
+            xp = ops.add_rows(x, pos, period)
+            o = self._mha(ly["attn"], xp, xp, x, B, L, L, E, nh, True, key_padding=kpm)
             x = conv_gemm(o, ly["attn"]["o"], res=x, res_mode=RES_BEFORE_NORM, ln=ly["n1"].pair)
             hmid = conv_gemm(x, ly["l1"], post_act=ACT_RELU)
             x = conv_gemm(hmid, ly["l2"], res=x, res_mode=RES_BEFORE_NORM, ln=ly["n2"].pair)
         memory = x
-        mem_pos = ops.add_rows(memory, pos, L)
+        mem_pos = ops.add_rows(memory, pos, period)
         tgt = torch.zeros(B * Q, E, dtype=torch.bfloat16, device=self.dev)
         hs = torch.empty(len(self.dec), B * Q, E, dtype=torch.bfloat16, device=self.dev)
         for i, ly in enumerate(self.dec):
@@ -367,7 +397,7 @@ class Engine:
             o = self._mha(ly["self"], tq, tq, tgt, B, Q, Q, E, nh, True)
             tgt = conv_gemm(o, ly["self"]["o"], res=tgt, res_mode=RES_BEFORE_NORM, ln=ly["n1"].pair)
             tq = ops.add_rows(tgt, self.query_pos, Q)
-            o = self._mha(ly["cross"], tq, mem_pos, memory, B, Q, L, E, nh, False)
+            o = self._mha(ly["cross"], tq, mem_pos, memory, B, Q, L, E, nh, False, key_padding=kpm)
             tgt = conv_gemm(o, ly["cross"]["o"], res=tgt, res_mode=RES_BEFORE_NORM, ln=ly["n2"].pair)
             hmid = conv_gemm(tgt, ly["l1"], post_act=ACT_RELU)
             tgt = conv_gemm(hmid, ly["l2"], res=tgt, res_mode=RES_BEFORE_NORM, ln=ly["n3"].pair)
@@ -390,7 +420,7 @@ class Engine:
         hmid = conv_gemm(x_ln, mlp[0], post_act=ACT_GELU)
         return conv_gemm(hmid, mlp[1], res=x_res, res_mode=RES_AFTER, out=out, y_coff=y_coff)
 
-    def line_stage(self, x, B, H, W, ref_xy):
+    def line_stage(self, x, B, H, W, ref_xy, mask=None):
         """BasicLayer of WindowAttention blocks at 1/32 (multiscale_transformerr.py:267-332,646-755,926-979).
         x: [B*H*W, D] bf16; ref_xy: fp32 [B, R, 2] line end points in [-1,1]."""
         c = self.cfg
@@ -399,7 +429,8 @@ class Engine:
         Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
         nW = (Hp // ws) * (Wp // ws)
         P = nW * N
-        pos = self.table(("pos32", H, W), lambda: sine_table(H, W, D // 2, False, self.dev))
+        pos = (self.table(("pos32", H, W), lambda: sine_table(H, W, D // 2, False, self.dev)) if mask is None
+               else sine_tables_masked(mask, D // 2, False))
         mask = self.table(("mask", H, W), lambda: shift_mask(H, W, ws, ws // 2, self.dev))
         a0 = torch.empty(B, nh, P, R, dtype=torch.float32, device=self.dev)
         a1 = torch.empty_like(a0)
@@ -509,7 +540,7 @@ class Engine:
         logits = self.pyramid(pb["pyr"], rg.view(B, H, W, Kp), B, H, W)
         return ops.anchor_mix(logits, anchor, B, H * W, K).view(B, H, W)
 
-    def dense_encoder(self, dense_in, feats, pred_lines, pred_logits, B, h5, w5, pinned, trace):
+    def dense_encoder(self, dense_in, feats, pred_lines, pred_logits, B, h5, w5, pinned, trace, masks=None):
         """ReferTransformer.forward (multiscale_transformerr.py:1151-1319)"""
         c = self.cfg
         D, td, R0 = c["dense_trans_dim"], c["class_token_dim"], c["num_ref"]
@@ -520,7 +551,7 @@ class Engine:
         if not c["with_dense_center"]:
             pts = pts[:, :, :2]
         ref_xy = pts.reshape(B, -1, 2).contiguous().float()
-        x32 = self.line_stage(dense_in, B, h5, w5, ref_xy)
+        x32 = self.line_stage(dense_in, B, h5, w5, ref_xy, mask=None if masks is None else masks[3])
         depth0 = conv_gemm(x32, self.depth32, post_act=ACT_SIGMOID, out_f32=True).view(B, h5, w5)
         edges = [c["min_depth_eval"] / c["max_depth_eval"]] + list(c["depth_interval"]) + [1.0]
         depths, prev, (ph, pw_) = [], x32.view(B, h5, w5, D), (h5, w5)
@@ -550,7 +581,8 @@ class Engine:
                 d = conv_gemm(buf, self.depth16, post_act=ACT_SIGMOID, out_f32=True).view(B, H, W)
             else:
                 pb = self.pbp[si - 1]
-                pos = self.table(("pos", H, W, C), lambda: sine_table(H, W, C // 2, False, self.dev))
+                pos = (self.table(("pos", H, W, C), lambda: sine_table(H, W, C // 2, False, self.dev)) if masks is None
+                       else sine_tables_masked(masks[2 - si], C // 2, False))
                 d = self.point_based_pred(pb, buf, depths[-1], coords, B, H, W, pos)
             depths.append(d)
             if si < 2:
@@ -623,23 +655,27 @@ class Engine:
 
     # ------------------------------------------------------------------ full forward
     @torch.no_grad()
-    def forward(self, images, pinned=None, trace=None):
-        """GlassRGBD.forward (src/models/glassrgbd.py:74-123) for an equal-size (un-padded) batch."""
+    def forward(self, images, pinned=None, trace=None, mask=None):
+        """GlassRGBD.forward (src/models/glassrgbd.py:74-123).  mask: None for an equal-size batch, else the bool
+        [B,H,W] padding mask of nested_tensor_from_tensor_list (True = padding): the convolutions run on the zero-padded
+        batch exactly as the reference's do; the mask enters through the per-image position codes (all four levels) and
+        the key-padding mask of the encoder self-attention and decoder cross-attention."""
         c = self.cfg
         pinned = pinned or {}
         B, _, H, W = images.shape
         feats = self.backbone(images)
+        masks = None if mask is None else [level_mask(mask, f.shape[1:3]) for f in feats]
         c5 = feats[3]
         h5, w5 = c5.shape[1:3]
         tok5 = c5.reshape(B * h5 * w5, c5.shape[-1])
         src = conv_gemm(tok5, self.input_proj)
-        hs, memory = self.detr(src, B, h5, w5)
+        hs, memory = self.detr(src, B, h5, w5, mask5=None if masks is None else masks[3])
         logits, lines = self.line_heads(hs, B)
         out = {"pred_logits": logits[-1], "pred_lines": lines[-1]}
         if c["aux_loss"]:
             out["aux_outputs"] = [{"pred_logits": a, "pred_lines": b} for a, b in zip(logits[:-1], lines[:-1])]
         dense_in = conv_gemm(tok5, self.dense_input_proj)
-        buf4, depths = self.dense_encoder(dense_in, feats, out["pred_lines"], out["pred_logits"], B, h5, w5, pinned, trace)
+        buf4, depths = self.dense_encoder(dense_in, feats, out["pred_lines"], out["pred_logits"], B, h5, w5, pinned, trace, masks)
         H4, W4 = feats[0].shape[1:3]
         depth, seg = self.dense_head(buf4, depths[-1], B, H4, W4, H, W)
         out["pred_depth"] = [d.unsqueeze(1) for d in depths] + [depth]

@@ -22,11 +22,13 @@ from .spec import model_spec
 class NestedTensor(object):
     """(tensors, padding mask) pair, src/util/misc.py:347-367"""
 
-    def __init__(self, tensors, mask):
-        self.tensors, self.mask = tensors, mask
+    def __init__(self, tensors, mask, padded=None):
+        # padded: host-side knowledge of whether any image was padded (None = unknown); lets the CUDA forward pick the
+        # masked path without reading the mask back
+        self.tensors, self.mask, self.padded = tensors, mask, padded
 
     def to(self, device):
-        return NestedTensor(self.tensors.to(device), self.mask.to(device) if self.mask is not None else None)
+        return NestedTensor(self.tensors.to(device), self.mask.to(device) if self.mask is not None else None, self.padded)
 
     def decompose(self):
         return self.tensors, self.mask
@@ -49,7 +51,8 @@ def nested_tensor_from_tensor_list(tensor_list):
     for i, t in enumerate(tensor_list):
         batch[i, :, : t.shape[1], : t.shape[2]].copy_(t)
         mask[i, : t.shape[1], : t.shape[2]] = False
-    return NestedTensor(batch, mask)
+    padded = any(t.shape[1] != hmax or t.shape[2] != wmax for t in tensor_list)
+    return NestedTensor(batch, mask, padded)
 
 
 class _Node(nn.Module):
@@ -161,11 +164,14 @@ class GlassRGBD(_Node):
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
             raise NotImplementedError("backward kernels are not built yet: run the forward under torch.no_grad() / "
                                       "model.eval() (DESIGN.md, 'what comes next')")
-        if mask is not None and bool(mask.any()):
-            raise NotImplementedError("padded (ragged) batches are not built yet on the CUDA path; batch equal-size images")
         plan = self.plan()      # raises off-GPU: there is no CPU path
+        padded = getattr(samples, "padded", None)      # set on the host by nested_tensor_from_tensor_list (no sync)
+        if mask is not None and padded is None:
+            padded = bool(mask.any())                  # a hand-made NestedTensor: one host read of the mask
         with torch.cuda.device(images.device):
             x = images.float().contiguous()
+            if padded:      # ragged batch: per-image position codes + key-padding masks, launched kernel by kernel
+                return plan.forward(x, pinned=_pinned, trace=_trace, mask=mask.to(x.device))
             if self.use_cuda_graph and _pinned is None and _trace is None:
                 return plan.forward_graphed(x)
             return plan.forward(x, pinned=_pinned, trace=_trace)

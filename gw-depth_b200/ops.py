@@ -333,9 +333,18 @@ def bilinear_up_into(x, out, y_coff, H, W):
     return out
 
 
+def _table_bstride(table, B):
+    """0 for a table shared by the batch ([H*W, C]), else the per-image stride of a [B, H*W, C] table"""
+    if table is None or table.dim() == 2:
+        return 0
+    assert table.dim() == 3 and table.shape[0] == B and table.is_contiguous()
+    return table.shape[1] * table.shape[2]
+
+
 def sample_bilinear(x, x_coff, table, B, H, W, C, coords, K):
     out = torch.empty(B, K, C, dtype=torch.float32, device=coords.device)
-    capi.check(_L().gwd_sample_bilinear(_ptr(x), x.shape[-1] if x is not None else 0, x_coff, _ptr(table), B, H, W, C,
+    capi.check(_L().gwd_sample_bilinear(_ptr(x), x.shape[-1] if x is not None else 0, x_coff, _ptr(table), _table_bstride(table, B),
+                                        B, H, W, C,
                                         _ptr(coords), K, _ptr(out), _stream()), "gwd_sample_bilinear")
     return out
 
@@ -349,7 +358,7 @@ def sample_scalar(x, coords, K):
 
 def line_ref_gather(win, pos, coords, R, B, H, W, ws, shift, C):
     out = torch.empty(B, R, C, dtype=torch.bfloat16, device=win.device)
-    capi.check(_L().gwd_line_ref_gather(_ptr(win), win.shape[-1], _ptr(pos), _ptr(coords), R, _ptr(out), C, B, H, W, ws,
+    capi.check(_L().gwd_line_ref_gather(_ptr(win), win.shape[-1], _ptr(pos), _table_bstride(pos, B), _ptr(coords), R, _ptr(out), C, B, H, W, ws,
                                         shift, C, _stream()), "gwd_line_ref_gather")
     return out
 

@@ -175,16 +175,17 @@ int gwd_avgpool(const void* x, int64_t x_rs, int32_t B, int32_t H, int32_t W, in
 int gwd_bilinear_up(const void* x, int64_t x_rs, int32_t B, int32_t h, int32_t w, void* out, int64_t out_rs, int32_t H,
                     int32_t W, int32_t C, void* stream);
 /* F.grid_sample(bilinear, align_corners=False, zeros) of a bf16 map (+ fp32 [H,W,C] table) at K points -> fp32 [B,K,C]
- * (points_sample.py:264-267) */
-int gwd_sample_bilinear(const void* x, int64_t x_rs, int32_t x_coff, const float* table, int32_t B, int32_t H, int32_t W,
-                        int32_t C, const float* coords, int32_t K, float* out, void* stream);
+ * (points_sample.py:264-267).  table_bstride: elements between the tables of consecutive images (0 = one table shared
+ * by the batch; per-image tables are what a padded batch has, src/models/position_encoding.py:33-35). */
+int gwd_sample_bilinear(const void* x, int64_t x_rs, int32_t x_coff, const float* table, int64_t table_bstride, int32_t B,
+                        int32_t H, int32_t W, int32_t C, const float* coords, int32_t K, float* out, void* stream);
 /* same for a 1-channel fp32 map -> fp32 [B,K]  (points_sample.py:268) */
 int gwd_sample_scalar(const float* x, int32_t B, int32_t H, int32_t W, const float* coords, int32_t K, float* out,
                       void* stream);
 /* nearest sample of the windowed feature map + shifted position table at R line end points
  * (multiscale_transformerr.py:676-701) -> bf16 [B,R,C] */
-int gwd_line_ref_gather(const void* win, int64_t win_rs, const float* pos, const float* coords, int32_t R, void* out,
-                        int64_t out_rs, int32_t B, int32_t H, int32_t W, int32_t ws, int32_t shift, int32_t C, void* stream);
+int gwd_line_ref_gather(const void* win, int64_t win_rs, const float* pos, int64_t pos_bstride, const float* coords, int32_t R,
+                        void* out, int64_t out_rs, int32_t B, int32_t H, int32_t W, int32_t ws, int32_t shift, int32_t C, void* stream);
 /* depth[p] = sum_k softmax_k(logits[p,:K]) anchor[b,k]  (points_sample.py:277-279) -> fp32 [B,HW] */
 int gwd_anchor_mix(const void* logits, int64_t l_rs, const float* anchor, int32_t B, int64_t HW, int32_t K, float* out,
                    void* stream);

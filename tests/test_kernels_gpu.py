@@ -209,6 +209,12 @@ def test_point_sampling_and_mixture():
     ref = (F.grid_sample(f, coords, align_corners=False) + F.grid_sample(t, coords, align_corners=False)).flatten(2).permute(0, 2, 1)
     got = ops.sample_bilinear(feat.cuda(), C, table.cuda(), B, H, W, C, coords.cuda().contiguous(), K)
     close(got, ref, 1e-5, "bilinear point sample")
+    # per-image tables (padded batches): image b samples table[b]
+    tables = torch.randn(B, H * W, C, generator=g)
+    tb = tables.view(B, H, W, C).permute(0, 3, 1, 2)
+    ref_b = (F.grid_sample(f, coords, align_corners=False) + F.grid_sample(tb, coords, align_corners=False)).flatten(2).permute(0, 2, 1)
+    got_b = ops.sample_bilinear(feat.cuda(), C, tables.cuda(), B, H, W, C, coords.cuda().contiguous(), K)
+    close(got_b, ref_b, 1e-5, "bilinear point sample, per-image table")
     depth = torch.rand(B, 9, 11, generator=g)
     ref_a = F.grid_sample(depth[:, None], coords, align_corners=False).flatten(1)
     close(ops.sample_scalar(depth.cuda(), coords.cuda().contiguous(), K), ref_a, 1e-6, "anchor depth")

@@ -73,6 +73,36 @@ def test_forward_matches_oracle_and_reference_fixture(B, H, W, fixture):
     assert rel(out["pred_logits"], torch.from_numpy(g["pred_logits"]))[1] < TOL["logits_max"]
 
 
+def test_ragged_batch_with_padding_mask():
+    """images of different sizes in one batch (src/util/misc.py:291-313 pads them, the mask reaches the position codes of
+    all four levels and the key-padding masks of the DETR attention): public API with a LIST of images vs the oracle,
+    which tests/test_oracle_vs_reference.py checks against the unmodified reference on exactly this kind of batch"""
+    net, _, M = model()
+    images, _, _, _ = synth.synth_batch(2, 224, 320, seed=1)
+    a, b = images[0], images[1][:, :160, :256].contiguous()
+    padded = torch.zeros(2, 3, 224, 320)
+    mask = torch.ones(2, 224, 320, dtype=torch.bool)
+    padded[0], mask[0] = a, False
+    padded[1, :, :160, :256] = b
+    mask[1, :160, :256] = False
+    trace = {}
+    ref = oracle.forward(synth_weights(), padded, mask, trace=trace)
+    nt = M.nested_tensor_from_tensor_list([a.cuda(), b.cuda()])
+    assert nt.padded is True and torch.equal(nt.mask.cpu(), mask)
+    with torch.no_grad():
+        out = net(nt, _pinned=pinned_from(trace))
+        plain = net(padded.cuda(), _pinned=pinned_from(trace))        # same pixels, no mask
+    assert rel(out["pred_logits"], ref["pred_logits"])[1] < TOL["logits_max"]
+    assert rel(out["pred_lines"], ref["pred_lines"])[1] < TOL["lines_max"]
+    m, x = rel(out["pred_depth"][3], ref["pred_depth"][3])
+    assert m < TOL["depth_mean"] and x < TOL["depth_max"], (m, x)
+    assert rel(out["pred_seg"], ref["pred_seg"])[0] < TOL["seg_mean"]
+    # the mask must matter for the padded image and must not for the full-size one's logits beyond round-off
+    d_masked = rel(out["pred_logits"][1], ref["pred_logits"][1])[1]
+    d_plain = rel(plain["pred_logits"][1], ref["pred_logits"][1])[1]
+    assert d_plain > 3 * d_masked, (d_plain, d_masked)
+
+
 def test_unpinned_selections_agree_with_oracle():
     """without pinning, the fp32-kept selection inputs must reproduce most of the oracle's choices"""
     net, _, _ = model()
