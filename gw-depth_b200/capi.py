@@ -90,6 +90,7 @@ SIGNATURES = {
     "gwd_stem_conv_pool": (c_int, [P, P, P, P, I, I, I, P]),
     "gwd_certain_sample": (c_int, [P, I, I, P, I, I, I, I, ctypes.POINTER(c_float), I, P, P, P]),
     "gwd_match_cost": (c_int, [P, P, P, P, P, I, I, I, I, F_, F_, P, P, P]),
+    "gwd_lsap_batch": (c_int, [P, P, P, I, I, P, P, P, I]),
     "gwd_depth_metrics": (c_int, [P, P, I, L, F_, F_, P, P, P]),
     "gwd_silog_sums": (c_int, [P, I, I, I, P, I, I, F_, F_, I, P, P]),
     "gwd_layernorm_bwd": (c_int, [P, L, P, L, P, F_, P, L, P, L, P, P, L, I, P]),

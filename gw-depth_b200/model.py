@@ -10,6 +10,8 @@ place of `models`.
 forward through the sm_100a kernel plan in engine.py.  There is no PyTorch fallback: without libgwd_b200.so or
 without a CUDA device the forward raises.
 """
+import os
+
 import torch
 import torch.nn.functional as F
 from torch import nn
@@ -298,14 +300,11 @@ class HungarianMatcher_Line(nn.Module):
                                  tgt_lines.repeat(S, 1).contiguous(), tgt_ids.repeat(S).contiguous(), offsets,
                                  float(self.cost_class), float(self.cost_line))
         flat = cost.cpu().numpy()
-        result = []
-        for s in range(S):
-            stage = []
-            for b in range(B):
-                o = offs[s * B + b]
-                i, j = linear_sum_assignment(flat[o * Q:(o + sizes[b]) * Q].reshape(Q, sizes[b]))
-                stage.append((torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)))
-            result.append(stage)
+        if os.environ.get("GWD_LSAP", "native") == "scipy":     # the reference's solver, problem by problem
+            pairs = [linear_sum_assignment(flat[offs[p] * Q:(offs[p] + sizes[p % B]) * Q].reshape(Q, sizes[p % B])) for p in range(S * B)]
+        else:       # same algorithm and tie rules, all S*B problems on the host cores at once (tests/test_lsap_cpu.py)
+            pairs = ops.lsap_batch(flat, [o * Q for o in offs[:-1]], sizes * S, Q)
+        result = [[(torch.from_numpy(pairs[s * B + b][0]), torch.from_numpy(pairs[s * B + b][1])) for b in range(B)] for s in range(S)]
         assert offs[-1] == S * total
         return result
 

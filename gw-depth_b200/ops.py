@@ -425,6 +425,23 @@ def match_cost(logits, lines, tgt_lines, tgt_labels, tgt_offsets, w_class, w_lin
     return cost, row_min
 
 
+def lsap_batch(cost_flat, offsets, sizes, Q, n_threads=0):
+    """HOST: cost_flat float32 numpy [sum Q*T_p], offsets / sizes per problem -> list of (query_idx, target_idx) int64 numpy
+    pairs, index-for-index what scipy.optimize.linear_sum_assignment returns for every [Q, T_p] block"""
+    import numpy as np
+    n = len(sizes)
+    cost_flat = np.ascontiguousarray(cost_flat, dtype=np.float32)
+    off = np.ascontiguousarray(offsets, dtype=np.int64)
+    T = np.ascontiguousarray(sizes, dtype=np.int32)
+    stride = max(Q, 1)
+    qi = np.empty((n, stride), dtype=np.int32)
+    ti = np.empty((n, stride), dtype=np.int32)
+    cnt = np.empty(n, dtype=np.int32)
+    capi.check(_L().gwd_lsap_batch(cost_flat.ctypes.data, off.ctypes.data, T.ctypes.data, Q, n, qi.ctypes.data, ti.ctypes.data,
+                                   cnt.ctypes.data, n_threads), "gwd_lsap_batch")
+    return [(qi[p, :cnt[p]].astype(np.int64), ti[p, :cnt[p]].astype(np.int64)) for p in range(n)]
+
+
 def depth_metrics(pred, gt, min_depth=1e-3, max_depth=10.0):
     """pred, gt fp32 [B,H,W] -> fp64 [B,9] (silog, abs_rel, log10, rms, sq_rel, log_rms, d1, d2, d3)"""
     B = pred.shape[0]

@@ -214,6 +214,14 @@ int gwd_certain_sample(const float* pred_small, int32_t h, int32_t w, const floa
 int gwd_match_cost(const float* logits, const float* lines, const float* tgt_lines, const int64_t* tgt_labels,
                    const int32_t* tgt_offsets, int32_t B, int32_t Q, int32_t num_classes, int32_t line_dim, float w_class,
                    float w_line, float* cost, float* row_min, void* stream);
+/* HOST function (no GPU work): the assignments of HungarianMatcher_Line for a batch of problems
+ * (src/models/matcher.py:73-74, scipy.optimize.linear_sum_assignment per image and decoder stage).  Problem p is the
+ * row-major fp32 [Q, T[p]] block at cost + cost_offsets[p] (host memory, e.g. the D2H copy of gwd_match_cost's output).
+ * Out: query_idx / target_idx int32 [n_problems][max(Q,1)], the first counts[p] = min(Q, T[p]) entries of row p are the
+ * matched (query, target) pairs ordered by query, index-for-index what scipy returns (same algorithm and tie rules).
+ * n_threads <= 0: one worker per host core (at most 16). */
+int gwd_lsap_batch(const float* cost, const int64_t* cost_offsets, const int32_t* T, int32_t Q, int32_t n_problems,
+                   int32_t* query_idx, int32_t* target_idx, int32_t* counts, int32_t n_threads);
 /* compute_depth_errors per image (src/util/metrics.py:197-218 after the scrub of src/engine_glassrgbd.py:249-253):
  * metrics fp64 [B,9] = silog, abs_rel, log10, rms, sq_rel, log_rms, d1, d2, d3; workspace fp64 [B,10]. */
 int gwd_depth_metrics(const float* pred, const float* gt, int32_t B, int64_t HW, float min_depth, float max_depth,
