@@ -305,6 +305,13 @@ class HungarianMatcher_Line(nn.Module):
         else:       # same algorithm and tie rules, all S*B problems on the host cores at once (tests/test_lsap_cpu.py)
             pairs = ops.lsap_batch(flat, [o * Q for o in offs[:-1]], sizes * S, Q)
         result = [[(torch.from_numpy(pairs[s * B + b][0]), torch.from_numpy(pairs[s * B + b][1])) for b in range(B)] for s in range(S)]
+        # the same assignment as int32 columns (stage, image, query, row of the concatenated targets) for gwd_set_loss
+        import numpy as np
+        starts = np.concatenate([[0], np.cumsum(sizes)])
+        cols = [np.stack([np.full(len(q), p // B), np.full(len(q), p % B), q, t + starts[p % B]]) for p, (q, t) in enumerate(pairs)]
+        per_stage = [sum(len(pairs[s * B + b][0]) for b in range(B)) for s in range(S)]
+        self.last_match = (np.ascontiguousarray(np.concatenate(cols, axis=1), dtype=np.int32),
+                           np.concatenate([[0], np.cumsum(per_stage)]).astype(np.int32))
         assert offs[-1] == S * total
         return result
 
@@ -408,24 +415,22 @@ class SetCriterion(nn.Module):
         if _world_size() > 1:
             torch.distributed.all_reduce(n)
         num_items = torch.clamp(n / _world_size(), min=1)
-        starts = [0]
-        for t in targets:
-            starts.append(starts[-1] + len(t["labels"]))
-        cols, stage_off = [], [0]
-        for s_, stage in enumerate(indices):
-            for b, (i, j) in enumerate(stage):
-                cols.append(torch.stack([torch.full_like(i, s_), torch.full_like(i, b), i, j + starts[b]]))
-            stage_off.append(stage_off[-1] + sum(len(i) for i, _ in stage))
-        match = torch.cat(cols, dim=1).to(torch.int32).contiguous().to(dev, non_blocking=True)
-        soff = torch.tensor(stage_off, dtype=torch.int32).to(dev, non_blocking=True)
+        match_np, soff_np = self.matcher.last_match
+        match = torch.from_numpy(match_np).to(dev, non_blocking=True)
+        soff = torch.from_numpy(soff_np).to(dev, non_blocking=True)
         key = [("loss_ce" + ("" if s_ == S - 1 else "_%d" % s_), "loss_line" + ("" if s_ == S - 1 else "_%d" % s_)) for s_ in range(S)]
         wd = self.weight_dict
-        w_ce = torch.tensor([float(wd.get(a, 0.0)) if "lines_labels" in self.losses else 0.0 for a, _ in key]).to(dev, non_blocking=True)
-        w_line = torch.tensor([float(wd.get(b, 0.0)) if "lines" in self.losses else 0.0 for _, b in key]).to(dev, non_blocking=True)
+        cache = getattr(self, "_stage_weights", None)
+        if cache is None or cache[0] != (S, str(dev)):
+            w_ce = torch.tensor([float(wd.get(a, 0.0)) if "lines_labels" in self.losses else 0.0 for a, _ in key]).to(dev)
+            w_line = torch.tensor([float(wd.get(b, 0.0)) if "lines" in self.losses else 0.0 for _, b in key]).to(dev)
+            cache = self._stage_weights = ((S, str(dev)), w_ce, w_line, self.empty_weight.to(dev).float().contiguous())
+        _, w_ce, w_line, class_w = cache
         tgt_lines = torch.cat([t["lines"] for t in targets]).float().contiguous()
         tgt_labels = torch.cat([t["labels"] for t in targets]).to(torch.int64).contiguous()
         vals, dlogits, dlines = ops.set_loss(logits.float().contiguous(), lines.float().contiguous(), tgt_lines, tgt_labels, match,
-                                             soff, self.empty_weight.to(dev).float().contiguous(), w_ce, w_line, num_items)
+                                             soff, class_w, w_ce, w_line, num_items)
+        self.last_total = (vals[:, 0] * w_ce + vals[:, 1] * w_line).sum()      # sum_k weight_dict[k] * losses[k]
         losses = {}
         for s_, (a, b) in enumerate(key):
             if "lines_labels" in self.losses:

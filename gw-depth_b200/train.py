@@ -349,7 +349,7 @@ class LineBranch:
             with torch.no_grad():
                 logits, lines = self.forward(producer(c5) if producer is not None else c5)
         losses, dlogits, dlines = criterion.forward_backward_stacked(logits, lines, targets)
-        total = sum(losses[k] * criterion.weight_dict[k] for k in losses if k in criterion.weight_dict)
+        total = criterion.last_total
         self.last_cotangents = (dlogits, dlines)
         if st is not None:
             st["dlogits"].copy_(dlogits, non_blocking=True)
