@@ -309,6 +309,7 @@ class HungarianMatcher_Line(nn.Module):
         import numpy as np
         starts = np.concatenate([[0], np.cumsum(sizes)])
         cols = [np.stack([np.full(len(q), p // B), np.full(len(q), p % B), q, t + starts[p % B]]) for p, (q, t) in enumerate(pairs)]
+        cols.append(np.zeros((4, 0), dtype=np.int64))
         per_stage = [sum(len(pairs[s * B + b][0]) for b in range(B)) for s in range(S)]
         self.last_match = (np.ascontiguousarray(np.concatenate(cols, axis=1), dtype=np.int32),
                            np.concatenate([[0], np.cumsum(per_stage)]).astype(np.int32))

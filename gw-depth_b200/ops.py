@@ -419,6 +419,8 @@ def match_cost(logits, lines, tgt_lines, tgt_labels, tgt_offsets, w_class, w_lin
     total_t = tgt_lines.shape[0]
     cost = torch.empty(Q * total_t, dtype=torch.float32, device=logits.device)
     row_min = torch.empty(B, Q, dtype=torch.float32, device=logits.device)
+    if total_t == 0:        # no target line in the whole batch: nothing to cost (the reference builds a [B*Q, 0] matrix)
+        return cost, row_min.fill_(float("inf"))
     capi.check(_L().gwd_match_cost(_ptr(logits), _ptr(lines), _ptr(tgt_lines), _ptr(tgt_labels), _ptr(tgt_offsets), B, Q,
                                    ncls, lines.shape[-1], w_class, w_line, _ptr(cost), _ptr(row_min), _stream()),
                "gwd_match_cost")
@@ -559,8 +561,14 @@ def set_loss(logits, lines, tgt_lines, tgt_labels, match, stage_off, class_w, w_
     assert match.dtype == torch.int32 and match.is_contiguous() and match.shape[0] == 4
     losses = torch.empty(S, 2, dtype=torch.float32, device=logits.device)
     dlogits, dlines = torch.empty_like(logits), torch.empty_like(lines)
+    M = match.shape[1]
+    if M == 0:              # no matched pair at all: the kernel still needs non-null (unread) pointers
+        match = torch.zeros(4, 1, dtype=torch.int32, device=logits.device)
+    if tgt_lines.numel() == 0:
+        tgt_lines = torch.zeros(1, D, dtype=torch.float32, device=logits.device)
+        tgt_labels = torch.zeros(1, dtype=torch.int64, device=logits.device)
     capi.check(_L().gwd_set_loss(_ptr(logits), _ptr(lines), _ptr(tgt_lines), _ptr(tgt_labels), _ptr(match), _ptr(stage_off),
-                                 _ptr(class_w), _ptr(w_ce), _ptr(w_line), _ptr(num_items), S, B, Q, C, D, match.shape[1], _ptr(losses),
+                                 _ptr(class_w), _ptr(w_ce), _ptr(w_line), _ptr(num_items), S, B, Q, C, D, M, _ptr(losses),
                                  _ptr(dlogits), _ptr(dlines), _stream()), "gwd_set_loss")
     return losses, dlogits, dlines
 

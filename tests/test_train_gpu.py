@@ -340,6 +340,37 @@ def test_stacked_criterion_equals_stage_by_stage_criterion():
     assert torch.equal(dli != 0, b_li.grad != 0)
 
 
+@pytest.mark.parametrize("case", ["one_image_without_lines", "no_lines_at_all", "more_targets_than_queries"])
+def test_criterion_edge_cases(case):
+    """images without any target line (the reference matches nothing and normalises by max(num_items, 1)) and an image
+    with more targets than queries (only Q of them can be matched): the three criterion paths agree"""
+    net, criterion, train, c5, targets = setup()
+    g = _g(17)
+    S, B, Q = 6, 2, 100
+    logits = torch.randn(S, B, Q, 2, generator=g).cuda()
+    lines = torch.rand(S, B, Q, 6, generator=g).cuda()
+    n = {"one_image_without_lines": (13, 0), "no_lines_at_all": (0, 0), "more_targets_than_queries": (120, 5)}[case]
+    tg = [{"lines": torch.rand(k, 6, generator=g).cuda(), "labels": torch.zeros(k, dtype=torch.int64).cuda()} for k in n]
+    a_lo, a_li = logits.clone().requires_grad_(True), lines.clone().requires_grad_(True)
+    out = {"pred_logits": a_lo[-1], "pred_lines": a_li[-1],
+           "aux_outputs": [{"pred_logits": x, "pred_lines": y} for x, y in zip(a_lo[:-1], a_li[:-1])]}
+    ref = criterion(out, tg)
+    wd = criterion.weight_dict
+    sum(ref[k] * wd[k] for k in ref).backward()
+    stacked = criterion.forward_stacked(logits, lines, tg)
+    fused, dlo, dli = criterion.forward_backward_stacked(logits, lines, tg)
+    for k in ref:
+        assert abs(float(stacked[k]) - float(ref[k])) <= 1e-5 * max(1.0, abs(float(ref[k]))), k
+        assert abs(float(fused[k]) - float(ref[k])) <= 1e-5 * max(1.0, abs(float(ref[k]))), k
+    assert rel_l2(dlo, a_lo.grad) < 1e-5
+    if sum(n) > 0:
+        assert rel_l2(dli, a_li.grad) < 1e-5
+    else:
+        assert float(dli.abs().max()) == 0.0 and float(a_li.grad.abs().max()) == 0.0
+    matched = sum(len(i) for i, _ in criterion.last_indices[0])
+    assert matched == sum(min(k, Q) for k in n)
+
+
 def test_graphed_and_eager_training_steps_agree():
     """the CUDA-graph replay (forward graph + backward graph) must produce the same gradients as kernel-by-kernel launches"""
     net, criterion, train, c5, targets = setup()
