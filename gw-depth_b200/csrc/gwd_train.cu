@@ -1033,7 +1033,8 @@ extern "C" int gwd_linear_wgrad(const void* dy, int64_t dy_rs, const void* x, in
   p.dy = static_cast<const bf16*>(dy); p.x = static_cast<const bf16*>(x); p.dw = dw; p.db = db;
   p.dy_rs = dy_rs; p.x_rs = x_rs; p.dw_rs = dw_rs; p.R = static_cast<int>(rows); p.N = N; p.K = K;
   const int tiles = static_cast<int>(gwd_ceil_div(N, kWgT) * gwd_ceil_div(K, kWgT));
-  int64_t split = std::max<int64_t>(1, std::min<int64_t>(gwd_ceil_div(2 * gwd_num_sms(), tiles), gwd_ceil_div(rows, 2 * kWgR)));
+  static const int ctas_per_sm_x2 = []() { const char* e = getenv("GWD_WGRAD_CTAS_X2"); return e ? atoi(e) : 4; }();
+  int64_t split = std::max<int64_t>(1, std::min<int64_t>(gwd_ceil_div(ctas_per_sm_x2 * gwd_num_sms() / 2, tiles), gwd_ceil_div(rows, 2 * kWgR)));
   p.rows_per_split = static_cast<int>(gwd_ceil_div(gwd_ceil_div(rows, split), kWgR) * kWgR);
   split = gwd_ceil_div(rows, p.rows_per_split);
   const size_t smem = static_cast<size_t>(2) * kWgStages * kWgR * kWgLd * sizeof(bf16);

@@ -121,6 +121,7 @@ class Engine:
         self.sd = sd
         self._tables = {}
         self._graphs = {}
+        self._side, self._side2 = torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)
         self._pack_backbone()
         self._pack_detr()
         self._pack_dense()
@@ -356,16 +357,22 @@ class Engine:
         return self._tables[key]
 
     # ------------------------------------------------------------------ DETR transformer
-    def _mha(self, pk, q_in, k_in, v_in, B, Lq, Lk, E, nh, fused_qk, key_padding=None):
+    def _mha(self, pk, q_in, k_in, v_in, B, Lq, Lk, E, nh, fused_qk, key_padding=None, kv=None):
         """multi_head_attention_forward (src/models/multi_head_attention.py:188-380) without the dead head-averaged
         weights.  q_in/k_in/v_in are [B*L, E] token matrices; returns the un-projected attention output."""
         hd = E // nh
-        if fused_qk:   # q and k share their input (self-attention on x + pos)
+        if kv is not None:       # cross attention: K / V of the memory were projected ahead of the decoder chain
+            q, k, v, q_rs, k_rs = conv_gemm(q_in, pk["q"]), kv[0], kv[1], E, E
+        else:
+            # the V projection does not depend on the Q|K projection: a parallel branch (side stream / graph fork)
+            main = torch.cuda.current_stream()
+            v = torch.empty(v_in.shape[0], E, dtype=torch.bfloat16, device=self.dev)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                conv_gemm(v_in, pk["v"], out=v)
             qk = conv_gemm(q_in, pk["qk"])
             q, k, q_rs, k_rs = qk, qk[:, E:], 2 * E, 2 * E
-        else:
-            q, k, q_rs, k_rs = conv_gemm(q_in, pk["q"]), conv_gemm(k_in, pk["k"]), E, E
-        v = conv_gemm(v_in, pk["v"])
+            main.wait_stream(self._side)
         o = torch.empty(B * Lq, E, dtype=torch.bfloat16, device=self.dev)
         ops.attention(q, k, v, o, items=B, heads=nh, Lq=Lq, Lk=Lk, hd=hd, q_strides=(Lq * q_rs, q_rs),
                       k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E), o_strides=(Lq * E, E), key_padding=key_padding)
@@ -392,12 +399,24 @@ class Engine:
         mem_pos = ops.add_rows(memory, pos, period)
         tgt = torch.zeros(B * Q, E, dtype=torch.bfloat16, device=self.dev)
         hs = torch.empty(len(self.dec), B * Q, E, dtype=torch.bfloat16, device=self.dev)
+        # cross-attention K / V projections of the memory for all decoder layers: independent of the decoder chain, so they
+        # run as a parallel branch while the first self-attention block is in flight
+        main = torch.cuda.current_stream()
+        ckv = [(torch.empty(B * L, E, dtype=torch.bfloat16, device=self.dev), torch.empty(B * L, E, dtype=torch.bfloat16, device=self.dev))
+               for _ in self.dec]
+        self._side2.wait_stream(main)
+        with torch.cuda.stream(self._side2):
+            for ly, (ck, cv) in zip(self.dec, ckv):
+                conv_gemm(mem_pos, ly["cross"]["k"], out=ck)
+                conv_gemm(memory, ly["cross"]["v"], out=cv)
         for i, ly in enumerate(self.dec):
             tq = ops.add_rows(tgt, self.query_pos, Q)
             o = self._mha(ly["self"], tq, tq, tgt, B, Q, Q, E, nh, True)
             tgt = conv_gemm(o, ly["self"]["o"], res=tgt, res_mode=RES_BEFORE_NORM, ln=ly["n1"].pair)
             tq = ops.add_rows(tgt, self.query_pos, Q)
-            o = self._mha(ly["cross"], tq, mem_pos, memory, B, Q, L, E, nh, False, key_padding=kpm)
+            if i == 0:
+                main.wait_stream(self._side2)
+            o = self._mha(ly["cross"], tq, mem_pos, memory, B, Q, L, E, nh, False, key_padding=kpm, kv=ckv[i])
             tgt = conv_gemm(o, ly["cross"]["o"], res=tgt, res_mode=RES_BEFORE_NORM, ln=ly["n2"].pair)
             hmid = conv_gemm(tgt, ly["l1"], post_act=ACT_RELU)
             tgt = conv_gemm(hmid, ly["l2"], res=tgt, res_mode=RES_BEFORE_NORM, ln=ly["n3"].pair)

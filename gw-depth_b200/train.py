@@ -80,6 +80,7 @@ class LineBranch:
         self._tables, self.tape, self._graphs, self._wt_tables = {}, None, {}, None
         import os
         self.use_cuda_graph = os.environ.get("GWD_CUDA_GRAPH", "1") != "0"
+        self._side, self._side2, self._keep = torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev), []
 
     # ------------------------------------------------------------------ flat-buffer views
     def view(self, flat, name):
@@ -150,6 +151,14 @@ class LineBranch:
                       k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E), o_strides=(Lq * E, E))
         return o
 
+    def _fork_gemm(self, x, lin):
+        """y = Linear(x) on the side stream (a parallel branch of the captured graph); the caller joins before using y"""
+        y = torch.empty(x.shape[0], lin.n_pad, dtype=torch.bfloat16, device=self.dev)
+        self._side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side):
+            conv_gemm(x, lin.pw, out=y)
+        return y
+
     def _ln_gemm(self, x, lin, res, ln):
         z = torch.empty(x.shape[0], lin.n_pad, dtype=torch.bfloat16, device=self.dev)
         y = conv_gemm(x, lin.pw, res=res, res_mode=RES_BEFORE_NORM, ln=(ln[0], ln[1]), y_raw=z)
@@ -171,8 +180,9 @@ class LineBranch:
         for ly in self.enc:
             a = ly["attn"]
             xp = ops.add_rows(x, pos, L)
+            v = self._fork_gemm(x, a["v"])
             qk = conv_gemm(xp, a["qk"].pw, out_scale=self.rs)
-            v = conv_gemm(x, a["v"].pw)
+            torch.cuda.current_stream().wait_stream(self._side)
             o = self._attend(qk, qk[:, E:], v, B, L, L, 2 * E, 2 * E)
             x1, z1 = self._ln_gemm(o, a["o"], x, ly["n1"])
             hm = conv_gemm(x1, ly["l1"].pw, post_act=ACT_RELU)
@@ -184,15 +194,27 @@ class LineBranch:
         tp["memory"], tp["mem_pos"] = memory, mem_pos
         tgt = torch.zeros(B * Q, E, dtype=torch.bfloat16, device=self.dev)
         hs = torch.empty(len(self.dec), B * Q, E, dtype=torch.bfloat16, device=self.dev)
+        # K / V projections of the memory for every decoder layer: a parallel branch next to the decoder chain
+        ckv = [(torch.empty(B * L, E, dtype=torch.bfloat16, device=self.dev), torch.empty(B * L, E, dtype=torch.bfloat16, device=self.dev))
+               for _ in self.dec]
+        self._side2.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self._side2):
+            for ly, (ck, cv) in zip(self.dec, ckv):
+                conv_gemm(mem_pos, ly["cross"]["k"].pw, out=ck)
+                conv_gemm(memory, ly["cross"]["v"].pw, out=cv)
         for i, ly in enumerate(self.dec):
             s, cr = ly["self"], ly["cross"]
             tq1 = ops.add_rows(tgt, self.query_pos, Q)
+            v = self._fork_gemm(tgt, s["v"])
             qk = conv_gemm(tq1, s["qk"].pw, out_scale=self.rs)
-            v = conv_gemm(tgt, s["v"].pw)
+            torch.cuda.current_stream().wait_stream(self._side)
             o1 = self._attend(qk, qk[:, E:], v, B, Q, Q, 2 * E, 2 * E)
             x1, z1 = self._ln_gemm(o1, s["o"], tgt, ly["n1"])
             tq2 = ops.add_rows(x1, self.query_pos, Q)
-            cq, ck, cv = conv_gemm(tq2, cr["q"].pw, out_scale=self.rs * self.rs), conv_gemm(mem_pos, cr["k"].pw), conv_gemm(memory, cr["v"].pw)
+            cq = conv_gemm(tq2, cr["q"].pw, out_scale=self.rs * self.rs)
+            ck, cv = ckv[i]
+            if i == 0:
+                torch.cuda.current_stream().wait_stream(self._side2)
             o2 = self._attend(cq, ck, cv, B, Q, L, E, E)
             x2, z2 = self._ln_gemm(o2, cr["o"], x1, ly["n2"])
             hm = conv_gemm(x2, ly["l1"].pw, post_act=ACT_RELU)
@@ -212,8 +234,14 @@ class LineBranch:
 
     # ------------------------------------------------------------------ backward
     def _lin_bwd(self, lin, dY, X, need_dx=True, res=None):
-        """dY [R, n_pad] bf16, X [R, K] bf16: accumulates dW / db into the flat gradient views; returns dX (+ res) or None"""
-        ops.linear_wgrad(dY, X, lin.gw, lin.gb)
+        """dY [R, n_pad] bf16, X [R, K] bf16: accumulates dW / db into the flat gradient views; returns dX (+ res) or None.
+        The weight gradient is off the critical path (nothing downstream reads it before the optimizer), so it runs on a
+        side stream: in the captured graph it becomes a parallel branch next to the dX chain."""
+        main = torch.cuda.current_stream()
+        self._side.wait_stream(main)                 # dY (and, first time round, the zeroed gradient buffer) is ready
+        with torch.cuda.stream(self._side):
+            ops.linear_wgrad(dY, X, lin.gw, lin.gb)
+        self._keep.append(dY)                        # the side stream still reads it: no reuse before the join
         if not need_dx:
             return None
         return conv_gemm(dY, lin.pwT, bias=False, res=res, res_mode=RES_AFTER if res is not None else RES_NONE)
@@ -245,6 +273,7 @@ class LineBranch:
         bf = dict(dtype=torch.bfloat16, device=self.dev)
         self.refresh_transposes()
         self.G.zero_()
+        self._keep = []
         gq = torch.zeros(Q, E, dtype=torch.float32, device=self.dev)
         # ---- heads
         dl = ops.act_bwd(dlogits.reshape(-1, dlogits.shape[-1]).contiguous(), None, ACT_NONE, out_cols=self.class_embed.n_pad)
@@ -294,6 +323,8 @@ class LineBranch:
             t = self._lin_bwd(a["qk"], dqk, s["xp"], res=dz1)
             d_x = self._lin_bwd(a["v"], dv, s["x"], res=t)
         dc5 = self._lin_bwd(self.input_proj, d_x, tp["c5"])
+        torch.cuda.current_stream().wait_stream(self._side)       # join: all weight gradients are in the flat buffer
+        self._keep = []
         if not keep_tape:
             self.tape = None
         return dc5
