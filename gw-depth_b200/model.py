@@ -281,7 +281,14 @@ class HungarianMatcher_Line(nn.Module):
         return result
 
     @torch.no_grad()
-    def forward_stacked(self, logits, lines, targets):
+    def pairs_from_raw(self):
+        """the last stacked assignment in the reference's format: list over stages of per-image (idx_pred, idx_tgt)"""
+        qi, ti, cnt, S, B = self.last_raw
+        return [[(torch.from_numpy(qi[s * B + b, :cnt[s * B + b]].astype("int64")), torch.from_numpy(ti[s * B + b, :cnt[s * B + b]].astype("int64")))
+                 for b in range(B)] for s in range(S)]
+
+    @torch.no_grad()
+    def forward_stacked(self, logits, lines, targets, want_pairs=True):
         """All S decoder stages at once (the reference calls the matcher once per stage, src/models/glassrgbd.py:318,344):
         logits [S,B,Q,C], lines [S,B,Q,D] -> list over stages of the per-image (idx_pred, idx_tgt) lists.  ONE
         gwd_match_cost launch over S*B (stage, image) pairs, ONE device-to-host copy, then the S*B assignments."""
@@ -300,19 +307,28 @@ class HungarianMatcher_Line(nn.Module):
                                  tgt_lines.repeat(S, 1).contiguous(), tgt_ids.repeat(S).contiguous(), offsets,
                                  float(self.cost_class), float(self.cost_line))
         flat = cost.cpu().numpy()
-        if os.environ.get("GWD_LSAP", "native") == "scipy":     # the reference's solver, problem by problem
-            pairs = [linear_sum_assignment(flat[offs[p] * Q:(offs[p] + sizes[p % B]) * Q].reshape(Q, sizes[p % B])) for p in range(S * B)]
-        else:       # same algorithm and tie rules, all S*B problems on the host cores at once (tests/test_lsap_cpu.py)
-            pairs = ops.lsap_batch(flat, [o * Q for o in offs[:-1]], sizes * S, Q)
-        result = [[(torch.from_numpy(pairs[s * B + b][0]), torch.from_numpy(pairs[s * B + b][1])) for b in range(B)] for s in range(S)]
-        # the same assignment as int32 columns (stage, image, query, row of the concatenated targets) for gwd_set_loss
         import numpy as np
         starts = np.concatenate([[0], np.cumsum(sizes)])
-        cols = [np.stack([np.full(len(q), p // B), np.full(len(q), p % B), q, t + starts[p % B]]) for p, (q, t) in enumerate(pairs)]
-        cols.append(np.zeros((4, 0), dtype=np.int64))
-        per_stage = [sum(len(pairs[s * B + b][0]) for b in range(B)) for s in range(S)]
-        self.last_match = (np.ascontiguousarray(np.concatenate(cols, axis=1), dtype=np.int32),
-                           np.concatenate([[0], np.cumsum(per_stage)]).astype(np.int32))
+        if os.environ.get("GWD_LSAP", "native") == "scipy":     # the reference's solver, problem by problem
+            pairs = [linear_sum_assignment(flat[offs[p] * Q:(offs[p] + sizes[p % B]) * Q].reshape(Q, sizes[p % B])) for p in range(S * B)]
+            qi = np.zeros((S * B, max(Q, 1)), dtype=np.int32)
+            ti = np.zeros_like(qi)
+            cnt = np.array([len(q) for q, _ in pairs], dtype=np.int32)
+            for p, (q, t) in enumerate(pairs):
+                qi[p, :len(q)], ti[p, :len(q)] = q, t
+        else:       # same algorithm and tie rules, all S*B problems on the host cores at once (tests/test_lsap_cpu.py)
+            qi, ti, cnt = ops.lsap_batch(flat, [o * Q for o in offs[:-1]], sizes * S, Q, raw=True)
+        # the assignment as int32 columns (stage, image, query, row of the concatenated targets) for gwd_set_loss, built
+        # without a Python loop over the S*B problems
+        p_idx, k_idx = np.nonzero(np.arange(qi.shape[1])[None, :] < cnt[:, None])
+        b_idx = p_idx % B
+        match = np.stack([p_idx // B, b_idx, qi[p_idx, k_idx], ti[p_idx, k_idx] + starts[b_idx]]).astype(np.int32)
+        per_stage = cnt.reshape(S, B).sum(1)
+        self.last_match = (np.ascontiguousarray(match), np.concatenate([[0], np.cumsum(per_stage)]).astype(np.int32))
+        self.last_raw = (qi, ti, cnt, S, B)
+        if not want_pairs:
+            return None
+        result = self.pairs_from_raw()
         assert offs[-1] == S * total
         return result
 
@@ -411,7 +427,7 @@ class SetCriterion(nn.Module):
         only solves the assignments and uploads them (one int32 [4, M] copy)."""
         S, B, Q = logits.shape[:3]
         dev = logits.device
-        indices = self.matcher.forward_stacked(logits, lines, targets)
+        self.matcher.forward_stacked(logits, lines, targets, want_pairs=False)
         n = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float, device=dev)
         if _world_size() > 1:
             torch.distributed.all_reduce(n)
@@ -438,8 +454,12 @@ class SetCriterion(nn.Module):
                 losses[a] = vals[s_, 0]
             if "lines" in self.losses:
                 losses[b] = vals[s_, 1]
-        self.last_indices = indices
+        self.last_indices = None        # built on demand from the matcher's raw arrays (`indices_of_last_call`)
         return losses, dlogits, dlines
+
+    def indices_of_last_call(self):
+        """assignments of the last stacked call, list over stages of per-image (idx_pred, idx_tgt)"""
+        return self.last_indices if self.last_indices is not None else self.matcher.pairs_from_raw()
 
     def forward(self, outputs, targets, origin_indices=None, depth_gt=None):
         plain = {k: v for k, v in outputs.items() if k != "aux_outputs"}

@@ -427,7 +427,7 @@ def match_cost(logits, lines, tgt_lines, tgt_labels, tgt_offsets, w_class, w_lin
     return cost, row_min
 
 
-def lsap_batch(cost_flat, offsets, sizes, Q, n_threads=0):
+def lsap_batch(cost_flat, offsets, sizes, Q, n_threads=0, raw=False):
     """HOST: cost_flat float32 numpy [sum Q*T_p], offsets / sizes per problem -> list of (query_idx, target_idx) int64 numpy
     pairs, index-for-index what scipy.optimize.linear_sum_assignment returns for every [Q, T_p] block"""
     import numpy as np
@@ -441,6 +441,8 @@ def lsap_batch(cost_flat, offsets, sizes, Q, n_threads=0):
     cnt = np.empty(n, dtype=np.int32)
     capi.check(_L().gwd_lsap_batch(cost_flat.ctypes.data, off.ctypes.data, T.ctypes.data, Q, n, qi.ctypes.data, ti.ctypes.data,
                                    cnt.ctypes.data, n_threads), "gwd_lsap_batch")
+    if raw:         # padded int32 arrays [n, max(Q,1)] + counts: for callers that vectorise over the problems
+        return qi, ti, cnt
     return [(qi[p, :cnt[p]].astype(np.int64), ti[p, :cnt[p]].astype(np.int64)) for p in range(n)]
 
 

@@ -321,7 +321,7 @@ def test_stacked_criterion_equals_stage_by_stage_criterion():
            "aux_outputs": [{"pred_logits": x, "pred_lines": y} for x, y in zip(b_lo[:-1], b_li[:-1])]}
     lb_ = criterion(out, targets)
     assert set(la) == set(lb_)
-    for s, stage in enumerate(criterion.last_indices):
+    for s, stage in enumerate(criterion.indices_of_last_call()):
         ref = criterion.matcher({"pred_logits": logits[s], "pred_lines": lines[s]}, targets)
         for (i, j), (ri, rj) in zip(stage, ref):
             assert torch.equal(i, ri) and torch.equal(j, rj)
@@ -367,7 +367,7 @@ def test_criterion_edge_cases(case):
         assert rel_l2(dli, a_li.grad) < 1e-5
     else:
         assert float(dli.abs().max()) == 0.0 and float(a_li.grad.abs().max()) == 0.0
-    matched = sum(len(i) for i, _ in criterion.last_indices[0])
+    matched = sum(len(i) for i, _ in criterion.indices_of_last_call()[0])
     assert matched == sum(min(k, Q) for k in n)
 
 
