@@ -179,7 +179,7 @@ def run_train(args, net, resident, rank, world, dev, barrier, reduce_max_ms):
     ms_graphs = timed(lambda: (st["fwd"].replay(), st["bwd"].replay())) if st else None
     lo, li = (st["logits"], st["lines"]) if st else lb.forward(c5)
     lo, li = lo.detach().clone(), li.detach().clone()
-    ms_crit = timed(lambda: criterion.forward_stacked(lo, li, targets[0]))
+    ms_crit = timed(lambda: criterion.forward_backward_stacked(lo, li, targets[0]))
     return {"metric": "images_per_sec_train_line_branch_480x640_bf16", "value": world * B * args.steps / (ms / 1000.0), "unit": UNIT,
             "ms_per_step": ms / args.steps, "n_gpus": world, "global_batch": world * B, "loss": float(total),
             "params": lb.numel, "allreduce_bytes_per_step": lb.numel * 4 if world > 1 else 0,

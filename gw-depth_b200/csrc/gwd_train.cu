@@ -867,11 +867,28 @@ gwd_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   const float step = a.lr / a.bc1;
   const float decay = 1.f - a.lr * a.wd;
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride) {
-    const float gi = g[i] * gs;
-    const float mi = a.beta1 * m[i] + (1.f - a.beta1) * gi;
-    const float vi = a.beta2 * v[i] + (1.f - a.beta2) * gi * gi;
-    const float pi = p[i] * decay - step * (mi / (sqrtf(vi) / a.bc2_sqrt + a.eps));
+  auto upd = [&](float gi, float& mi, float& vi, float& pi) {
+    gi *= gs;
+    mi = a.beta1 * mi + (1.f - a.beta1) * gi;
+    vi = a.beta2 * vi + (1.f - a.beta2) * gi * gi;
+    pi = pi * decay - step * (mi / (sqrtf(vi) / a.bc2_sqrt + a.eps));
+  };
+  // 16-byte vectors (the flat buffers are 16-byte aligned; the caller checks), scalar tail
+  const int64_t n4 = n >> 2;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i], p4 = reinterpret_cast<float4*>(p)[i];
+    upd(g4.x, m4.x, v4.x, p4.x); upd(g4.y, m4.y, v4.y, p4.y); upd(g4.z, m4.z, v4.z, p4.z); upd(g4.w, m4.w, v4.w, p4.w);
+    reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4; reinterpret_cast<float4*>(p)[i] = p4;
+    if (mirror != nullptr) {
+      uint2 o;
+      o.x = gwd_pack_bf16x2(p4.x, p4.y); o.y = gwd_pack_bf16x2(p4.z, p4.w);
+      reinterpret_cast<uint2*>(mirror)[i] = o;
+    }
+  }
+  for (int64_t i = (n4 << 2) + blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    float mi = m[i], vi = v[i], pi = p[i];
+    upd(g[i], mi, vi, pi);
     m[i] = mi; v[i] = vi; p[i] = pi;
     if (mirror != nullptr) mirror[i] = __float2bfloat16(pi);
   }
@@ -1009,12 +1026,15 @@ extern "C" int gwd_adamw_step(float* p, const float* g, float* m, float* v, void
                               const double* sumsq, void* stream_) {
   GWD_STREAM;
   GWD_CHECK_ARG(p && g && m && v && n > 0 && step >= 1, "gwd_adamw_step: bad argument");
+  GWD_CHECK_ARG(((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) |
+                  reinterpret_cast<uintptr_t>(v)) & 15) == 0 && (reinterpret_cast<uintptr_t>(mirror_bf16) & 7) == 0,
+                "gwd_adamw_step: buffers must be 16-byte (mirror: 8-byte) aligned");
   AdamParams a;
   a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.wd = weight_decay;
   a.bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), step));
   a.bc2_sqrt = static_cast<float>(sqrt(1.0 - pow(static_cast<double>(beta2), step)));
   a.max_norm = max_norm; a.grad_scale = grad_scale;
-  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(n, 256 * 4), 8 * gwd_num_sms()));
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(n, 256 * 4), 16 * gwd_num_sms()));
   gwd_adamw_kernel<<<grid, 256, 0, stream>>>(p, g, m, v, static_cast<bf16*>(mirror_bf16), n, a, sumsq);
   GWD_LAUNCHED();
   return GWD_OK;
