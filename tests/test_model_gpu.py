@@ -103,6 +103,27 @@ def test_ragged_batch_with_padding_mask():
     assert d_plain > 3 * d_masked, (d_plain, d_masked)
 
 
+def test_dense_center_configuration():
+    """--with_dense_center (BASELINE configs[3], the richest flag set that runs in the reference): three points
+    per selected line -> 60 reference tokens in the line-window attention instead of 40"""
+    _, _, M = model()
+    net, _, _ = M.build_model(M.default_args(device="cuda", with_dense_center=True))
+    net.load_state_dict(synth_weights())
+    net.cuda().eval()
+    images, _, _, _ = synth.synth_batch(2, 224, 320, seed=2)
+    trace = {}
+    ref = oracle.forward(synth_weights(), images, cfg={"with_dense_center": True}, trace=trace)
+    base = oracle.forward(synth_weights(), images, cfg={"with_dense_center": False})
+    with torch.no_grad():
+        out = net(images.cuda(), _pinned=pinned_from(trace))
+    m, x = rel(out["pred_depth"][3], ref["pred_depth"][3])
+    assert m < TOL["depth_mean"] and x < TOL["depth_max"], (m, x)
+    assert rel(out["pred_seg"], ref["pred_seg"])[0] < TOL["seg_mean"]
+    assert rel(out["pred_depth"][0], ref["pred_depth"][0])[0] < 6e-2
+    # the centre points must matter: the two configurations differ by more than the bf16 distance to the right one
+    assert rel(base["pred_depth"][3], ref["pred_depth"][3])[0] > 1.3 * m
+
+
 def test_unpinned_selections_agree_with_oracle():
     """without pinning, the fp32-kept selection inputs must reproduce most of the oracle's choices"""
     net, _, _ = model()
