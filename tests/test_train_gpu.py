@@ -199,6 +199,38 @@ def test_fused_clip_adamw_matches_torch(max_norm, world):
         assert torch.equal(mirror, P.bfloat16())
 
 
+def test_flat_adamw_is_a_drop_in_for_clip_plus_torch_adamw():
+    """optim.FlatAdamW on a real module with the reference's two parameter groups (src/main_glassrgbd.py:59-66) and
+    autograd gradients: same trajectory as clip_grad_norm_ + torch.optim.AdamW"""
+    import copy
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import optim
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(37, 64), torch.nn.ReLU(), torch.nn.Linear(64, 64), torch.nn.LayerNorm(64),
+                              torch.nn.Linear(64, 3)).cuda()
+    net[2].weight.requires_grad_(False)                                  # a frozen tensor, as the backbone stem is
+    ref = copy.deepcopy(net)
+
+    def groups(m):
+        return [{"params": [p for n, p in m.named_parameters() if not n.startswith("0.") and p.requires_grad]},
+                {"params": [p for n, p in m.named_parameters() if n.startswith("0.") and p.requires_grad], "lr": 1e-3}]
+    opt = optim.FlatAdamW(groups(net), lr=1e-2, weight_decay=1e-4, max_norm=0.1)
+    ref_opt = torch.optim.AdamW(groups(ref), lr=1e-2, weight_decay=1e-4)
+    x = torch.randn(50, 37, device="cuda")
+    y = torch.randn(50, 3, device="cuda")
+    for it in range(5):
+        for m, o in ((net, opt), (ref, ref_opt)):
+            o.zero_grad()
+            torch.nn.functional.mse_loss(m(x), y).mul(10.0 if it == 2 else 1e-3).backward()     # step 2 is clipped
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.1)
+        ref_opt.step()
+        opt.step()
+        for (n, a), b in zip(net.named_parameters(), ref.parameters()):
+            assert rel_l2(a, b) < 5e-6, (it, n)
+    assert torch.equal(net[2].weight, ref[2].weight)                     # frozen tensors untouched
+    assert all(p.data_ptr() >= g["P"].data_ptr() for g in opt.groups for p in g["params"])
+
+
 # ------------------------------------------------------------------------------------------ the branch
 _cache = {}
 
