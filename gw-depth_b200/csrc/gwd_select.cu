@@ -292,6 +292,34 @@ __global__ void gwd_silog_sums_kernel(const float* __restrict__ pred, int B, int
   }
 }
 
+
+// segmentation evaluation (src/engine_glassrgbd.py:232-240 + src/util/metrics.py:43-78): per-pixel argmax over the class
+// logits (first maximum, as torch.argmax) and the [C, C] confusion counts conf[gt][pred] over pixels with gt != ignore,
+// accumulated into an int64 matrix on the device (the reference copies both maps to the host and runs np.bincount).
+__global__ void __launch_bounds__(256)
+gwd_seg_confusion_kernel(const float* __restrict__ logits, int64_t pixel_stride, int64_t class_stride, int64_t image_stride,
+                         const int64_t* __restrict__ gt, int64_t HW, int64_t total, int C, int ignore,
+                         unsigned long long* __restrict__ conf) {
+  __shared__ unsigned int hist[64];
+  if (threadIdx.x < 64) hist[threadIdx.x] = 0;
+  __syncthreads();
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t g = gt[i];
+    if (g == ignore || g < 0 || g >= C) continue;
+    const float* px = logits + (i / HW) * image_stride + (i % HW) * pixel_stride;
+    int best = 0;
+    float bv = px[0];
+    for (int c = 1; c < C; ++c) {
+      const float v = px[c * class_stride];
+      if (v > bv) { bv = v; best = c; }
+    }
+    atomicAdd(&hist[static_cast<int>(g) * C + best], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < C * C && hist[threadIdx.x]) atomicAdd(&conf[threadIdx.x], static_cast<unsigned long long>(hist[threadIdx.x]));
+}
+
 }  // namespace
 
 extern "C" int gwd_certain_sample(const float* pred_small, int32_t h, int32_t w, const float* pred_large, int32_t H,
@@ -353,6 +381,20 @@ extern "C" int gwd_silog_sums(const float* pred, int32_t B, int32_t h, int32_t w
   int64_t total = static_cast<int64_t>(B) * h * w;
   int bx = static_cast<int>(std::min<int64_t>(gwd_ceil_div(total, 256 * 4), 4 * gwd_num_sms()));
   gwd_silog_sums_kernel<<<bx, 256, 0, stream>>>(pred, B, h, w, gt, H, W, lo, hi, log_only, sums3);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_seg_confusion(const float* logits, int64_t pixel_stride, int64_t class_stride, int64_t image_stride,
+                                 const int64_t* gt, int32_t B, int64_t HW, int32_t num_classes, int32_t ignore_index,
+                                 int64_t* confusion, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GWD_CHECK_ARG(logits && gt && confusion && B > 0 && HW > 0, "gwd_seg_confusion: bad argument");
+  GWD_CHECK_ARG(num_classes >= 2 && num_classes <= 8, "gwd_seg_confusion: 2..8 classes");
+  const int64_t total = static_cast<int64_t>(B) * HW;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(total, 256 * 8), 8 * gwd_num_sms()));
+  gwd_seg_confusion_kernel<<<grid, 256, 0, stream>>>(logits, pixel_stride, class_stride, image_stride, gt, HW, total, num_classes,
+                                                     ignore_index, reinterpret_cast<unsigned long long*>(confusion));
   GWD_LAUNCHED();
   return GWD_OK;
 }

@@ -457,6 +457,28 @@ def depth_metrics(pred, gt, min_depth=1e-3, max_depth=10.0):
     return out
 
 
+def seg_confusion(pred_seg, seg_gt, confusion=None, ignore_index=255):
+    """pred_seg fp32 [B,C,H,W] logits (any strides: the forward returns a channels-last view), seg_gt int64 [B,H,W] or
+    [B,1,H,W] -> int64 [C,C] confusion[gt][argmax pred], accumulated into `confusion` when given"""
+    B, C, H, W = pred_seg.shape
+    assert pred_seg.dtype == torch.float32 and pred_seg.stride(0) == C * H * W and pred_seg.stride(2) == W * pred_seg.stride(3)
+    gt = seg_gt.reshape(B, H * W).to(torch.int64).contiguous()
+    if confusion is None:
+        confusion = torch.zeros(C, C, dtype=torch.int64, device=pred_seg.device)
+    capi.check(_L().gwd_seg_confusion(_ptr(pred_seg), pred_seg.stride(3), pred_seg.stride(1), pred_seg.stride(0), _ptr(gt), B, H * W, C,
+                                      ignore_index, _ptr(confusion), _stream()), "gwd_seg_confusion")
+    return confusion
+
+
+def seg_scores(confusion):
+    """compute_mean_ioU's numbers from a confusion matrix (src/util/metrics.py:66-77), fp64 on the device:
+    -> (IoU per class * 100, pixel accuracy, mean accuracy, mean IoU)"""
+    cm = confusion.double()
+    pos, res, tp = cm.sum(1), cm.sum(0), cm.diag()
+    iou = tp / torch.clamp(pos + res - tp, min=1.0) * 100
+    return iou, tp.sum() / pos.sum() * 100, (tp / torch.clamp(pos, min=1.0)).mean() * 100, iou.mean()
+
+
 def silog_sums(pred, gt, lo=0.2, hi=10.0, log_only=False):
     """pred fp32 [B,1,h,w], gt fp32 [B,1,H,W] -> fp64 [3] = count, sum d, sum d^2"""
     B, _, h, w = pred.shape

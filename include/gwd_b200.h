@@ -226,6 +226,12 @@ int gwd_lsap_batch(const float* cost, const int64_t* cost_offsets, const int32_t
  * metrics fp64 [B,9] = silog, abs_rel, log10, rms, sq_rel, log_rms, d1, d2, d3; workspace fp64 [B,10]. */
 int gwd_depth_metrics(const float* pred, const float* gt, int32_t B, int64_t HW, float min_depth, float max_depth,
                       double* workspace, double* metrics, void* stream);
+/* segmentation evaluation (src/engine_glassrgbd.py:232-240, src/util/metrics.py:43-78): confusion[gt * C + argmax_c logits]
+ * += 1 over the pixels with gt != ignore_index (int64 [C*C], ACCUMULATED so a whole evaluation run can sum into it).
+ * logits fp32 addressed as base + image*image_stride + pixel*pixel_stride + class*class_stride (NCHW: HW*C, 1, HW; the
+ * channels-last map the forward produces: HW*C, C, 1); gt int64 [B, HW]. */
+int gwd_seg_confusion(const float* logits, int64_t pixel_stride, int64_t class_stride, int64_t image_stride, const int64_t* gt,
+                      int32_t B, int64_t HW, int32_t num_classes, int32_t ignore_index, int64_t* confusion, void* stream);
 /* SilogLoss sums over valid pixels with gt nearest-resized to the prediction (src/models/glassrgbd.py:366-374,
  * src/engine_glassrgbd.py:74-80): sums3 fp64 = {count, sum d, sum d^2}. */
 int gwd_silog_sums(const float* pred, int32_t B, int32_t h, int32_t w, const float* gt, int32_t H, int32_t W, float lo,

@@ -322,3 +322,55 @@ def test_stem_conv_pool(B, H, W):
     ref = F.max_pool2d(_bf(F.relu(conv)).float(), 3, 2, 1).permute(0, 2, 3, 1)
     assert tuple(got.shape) == tuple(ref.shape)
     close(got, ref, 1e-2, "stem")
+
+
+def test_seg_confusion_bit_exact():
+    """argmax + confusion matrix of the segmentation evaluation == torch.argmax + np.bincount (src/util/metrics.py:43-78),
+    on NCHW logits and on the channels-last view the forward returns, with ignored pixels and exact ties"""
+    ops = _ops()
+    g = _g(31)
+    B, C, H, W = 3, 2, 37, 53
+    logits = torch.randn(B, C, H, W, generator=g)
+    logits[:, 1, ::5] = logits[:, 0, ::5]                      # exact ties -> class 0, as torch.argmax
+    gt = (torch.rand(B, 1, H, W, generator=g) > 0.4).long()
+    gt[:, :, ::7, ::3] = 255                                   # ignored pixels
+    pred = logits.argmax(1).reshape(-1).numpy()
+    gtn = gt.reshape(-1).numpy()
+    keep = gtn != 255
+    ref = np.bincount(gtn[keep] * C + pred[keep], minlength=C * C).reshape(C, C)
+    got = ops.seg_confusion(logits.cuda(), gt.cuda())
+    assert np.array_equal(got.cpu().numpy(), ref)
+    nhwc = logits.permute(0, 2, 3, 1).contiguous().cuda().permute(0, 3, 1, 2)      # what GlassRGBD.forward returns
+    acc = ops.seg_confusion(nhwc, gt.cuda(), confusion=got.clone())
+    assert np.array_equal(acc.cpu().numpy(), 2 * ref)
+    iou, pix, macc, miou = ops.seg_scores(got)
+    cm = ref.astype(np.float64)
+    tp, pos, res = np.diag(cm), cm.sum(1), cm.sum(0)
+    assert np.allclose(iou.cpu().numpy(), tp / np.maximum(1.0, pos + res - tp) * 100)
+    assert abs(float(pix) - tp.sum() / pos.sum() * 100) < 1e-9 and abs(float(miou) - (tp / np.maximum(1.0, pos + res - tp)).mean() * 100) < 1e-9
+
+
+def test_dense_evaluator_batches_equal_the_batch_1_loop():
+    """evaluation.DenseEvaluator over batches of 3 and 2 == the reference's batch-1 bookkeeping (oracle.depth_metrics per
+    image, numpy confusion matrix over all images)"""
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import evaluation
+    g = _g(41)
+    N, H, W = 5, 48, 64
+    pred = torch.rand(N, 1, H, W, generator=g) * 11 - 0.2          # some values outside [1e-3, 10]
+    pred[0, 0, 0, 0], pred[1, 0, 1, 1] = float("nan"), float("inf")
+    gt = torch.rand(N, 1, H, W, generator=g) * 10.5
+    seg = torch.randn(N, 2, H, W, generator=g)
+    seg_gt = (torch.rand(N, 1, H, W, generator=g) > 0.5).long()
+    ev = evaluation.DenseEvaluator()
+    for sl in (slice(0, 3), slice(3, 5)):
+        ev.update({"pred_depth": [None, pred[sl].cuda()], "pred_seg": seg[sl].cuda()}, gt[sl].cuda(), seg_gt[sl].cuda())
+    got = ev.summary()
+    ref = torch.stack([torch.as_tensor(oracle.depth_metrics(pred[i, 0], gt[i, 0])) for i in range(N)]).double().mean(0)
+    for k, name in enumerate(evaluation.DEPTH_METRICS):
+        assert abs(got[name] - float(ref[k])) <= 1e-5 * max(1.0, abs(float(ref[k]))), name
+    p, t = seg.argmax(1).reshape(-1).numpy(), seg_gt.reshape(-1).numpy()
+    cm = np.bincount(t * 2 + p, minlength=4).reshape(2, 2).astype(np.float64)
+    tp, pos, res = np.diag(cm), cm.sum(1), cm.sum(0)
+    assert abs(got["Mean IU"] - (tp / np.maximum(1.0, pos + res - tp)).mean() * 100) < 1e-9
+    assert abs(got["Glass"] - tp[1] / max(1.0, pos[1] + res[1] - tp[1]) * 100) < 1e-9 and got["images"] == N
