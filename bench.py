@@ -272,6 +272,24 @@ def main():
         barrier()
         ms_e2e = reduce_max_ms(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0))
         e2e_value = world * B * args.steps / (ms_e2e / 1000.0)
+        # the same loop fed with raw uint8 HWC images (a quarter of the PCIe bytes; normalised on the GPU)
+        host_u8 = [torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(i)).pin_memory()
+                   for i in range(NB)]
+
+        def e2e_u8(n):
+            for _ in net.infer_stream(host_u8[i % NB] for i in range(n)):
+                pass
+            torch.cuda.synchronize()
+        e2e_u8(3)
+        barrier()
+        t0 = time.perf_counter()
+        e0.record()
+        e2e_u8(args.steps)
+        e1.record()
+        barrier()
+        ms_u8 = reduce_max_ms(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0))
+        e2e_uint8 = {"value": world * B * args.steps / (ms_u8 / 1000.0), "unit": UNIT, "ms_per_step": ms_u8 / args.steps,
+                     "h2d_bytes_per_step": host_u8[0].numel(), "input": "uint8 [B,H,W,3] pinned host images, ToTensor + Normalize on the GPU (gwd_images_to_batch)"}
         h2d = host[0].numel() * host[0].element_size()
         d2h = sum(t.numel() * t.element_size() for t in out_host)
 
@@ -345,7 +363,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "pipeline": "model.infer_stream: 3 streams, double-buffered H2D / forward / D2H"},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
-            "gpu_eager_port": eager, "train_line_branch": train_line}
+            "gpu_eager_port": eager, "e2e_uint8_inputs": e2e_uint8, "train_line_branch": train_line}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -474,6 +474,39 @@ int grid_for(int64_t total, int threads) {
   return static_cast<int>(blocks < cap ? (blocks > 0 ? blocks : 1) : cap);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Input builder: B uint8 HWC images (possibly of different sizes) -> the normalised, zero-padded fp32 NCHW batch and its
+// padding mask in one pass: ToTensor (/255), Normalize ((v - mean) / std) and nested_tensor_from_tensor_list of
+// src/datasets/coco.py:77-78, src/datasets/transforms_depth.py:618-637, src/util/misc.py:291-313.  IEEE division in the
+// reference's operation order, so the result is bit-identical to torchvision's.
+// ------------------------------------------------------------------------------------------------
+struct ImgNorm { float mean[3], std[3]; };
+
+__global__ void __launch_bounds__(256)
+gwd_images_to_batch_kernel(const int64_t* __restrict__ table, int B, int H, int W, ImgNorm nm, float* __restrict__ out,
+                           uint8_t* __restrict__ mask) {
+  const int64_t HW = static_cast<int64_t>(H) * W, total = HW * B;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / HW);
+    const int64_t p = i - b * HW;
+    const int y = static_cast<int>(p / W), x = static_cast<int>(p - static_cast<int64_t>(y) * W);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(table[3 * b]);
+    const int h = static_cast<int>(table[3 * b + 1]), w = static_cast<int>(table[3 * b + 2]);
+    const bool in = y < h && x < w;
+    float v[3] = {0.f, 0.f, 0.f};
+    if (in) {
+      const uint8_t* px = src + (static_cast<int64_t>(y) * w + x) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(px[c]), 255.f), nm.mean[c]), nm.std[c]);
+    }
+    float* o = out + static_cast<int64_t>(b) * 3 * HW + p;
+    o[0] = v[0]; o[HW] = v[1]; o[2 * HW] = v[2];
+    if (mask != nullptr) mask[i] = in ? 0 : 1;
+  }
+}
+
 }  // namespace
 
 #define GWD_STREAM cudaStream_t stream = static_cast<cudaStream_t>(stream_)
@@ -637,6 +670,17 @@ extern "C" int gwd_nchw_to_nhwc(const float* x, int32_t B, int32_t C, int64_t HW
   GWD_STREAM;
   GWD_CHECK_ARG(x && out && Cp >= C, "gwd_nchw_to_nhwc: bad argument");
   gwd_nchw_to_nhwc_kernel<<<grid_for(B * HW * Cp, 256), 256, 0, stream>>>(x, B, C, HW, static_cast<bf16*>(out), Cp);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_images_to_batch(const int64_t* table, int32_t B, int32_t H, int32_t W, const float* mean3, const float* std3,
+                                   float* out, uint8_t* mask, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(table && mean3 && std3 && out && B > 0 && H > 0 && W > 0, "gwd_images_to_batch: bad argument");
+  ImgNorm nm;
+  for (int c = 0; c < 3; ++c) { nm.mean[c] = mean3[c]; nm.std[c] = std3[c]; }
+  gwd_images_to_batch_kernel<<<grid_for(static_cast<int64_t>(B) * H * W, 256), 256, 0, stream>>>(table, B, H, W, nm, out, mask);
   GWD_LAUNCHED();
   return GWD_OK;
 }

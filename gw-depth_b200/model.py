@@ -181,8 +181,10 @@ class GlassRGBD(_Node):
 
     @torch.no_grad()
     def infer_stream(self, host_batches, keys=("pred_logits", "pred_lines", "pred_depth", "pred_seg")):
-        """Serving loop over an iterable of PINNED host batches [B,3,H,W]: yields, per batch, a dict of pinned host
-        tensors (`pred_depth` = the full-resolution map).  Uploads, the forward and downloads run on three streams with
+        """Serving loop over an iterable of PINNED host batches: yields, per batch, a dict of pinned host tensors
+        (`pred_depth` = the full-resolution map).  A batch is either fp32 [B,3,H,W] (already normalised, what the
+        reference's data loader hands over) or uint8 [B,H,W,3] raw images: those cross PCIe at a quarter of the bytes and
+        are normalised on the GPU (gwd_images_to_batch, bit-identical to ToTensor + Normalize of src/datasets/coco.py:77-78).  Uploads, the forward and downloads run on three streams with
         two buffers each, so the copy of batch i+1 and the read-back of batch i-1 overlap the forward of batch i.  A
         yielded dict is valid until the next one is requested."""
         plan = self.plan()
@@ -192,7 +194,8 @@ class GlassRGBD(_Node):
         st = self.__dict__.setdefault("_serve_state", {})
         if st.get("dev") != dev:
             st.clear()
-            st.update(dev=dev, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev), x_dev=[None, None],
+            st.update(dev=dev, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev), x_dev=[None, None], u_dev=[None, None],
+                      u_tab=[None, None],
                       out_dev=[None, None], out_host=[None, None],
                       ev=[[torch.cuda.Event() for _ in range(2)] for _ in range(4)])
         s_in, s_out = st["s_in"], st["s_out"]
@@ -210,14 +213,24 @@ class GlassRGBD(_Node):
 
         for i, hb in enumerate(host_batches):
             b = i & 1
+            raw = hb.dtype == torch.uint8
+            u_dev, u_tab = st["u_dev"], st["u_tab"]
             with torch.cuda.stream(s_in):
-                if x_dev[b] is None or x_dev[b].shape != hb.shape:
-                    x_dev[b] = torch.empty(hb.shape, dtype=torch.float32, device=dev)
+                stage = u_dev if raw else x_dev
+                if stage[b] is None or stage[b].shape != hb.shape:
+                    stage[b] = torch.empty(hb.shape, dtype=hb.dtype if raw else torch.float32, device=dev)
+                    u_tab[b] = None
                 elif i >= 2:
                     s_in.wait_event(ev_used[b])          # the forward of batch i-2 has consumed this buffer
-                x_dev[b].copy_(hb, non_blocking=True)
+                stage[b].copy_(hb, non_blocking=True)
                 ev_in[b].record(s_in)
             comp.wait_event(ev_in[b])
+            if raw:     # uint8 HWC -> normalised fp32 NCHW on the compute stream
+                B_, H_, W_ = hb.shape[:3]
+                if x_dev[b] is None or x_dev[b].shape != (B_, 3, H_, W_):
+                    x_dev[b] = torch.empty(B_, 3, H_, W_, dtype=torch.float32, device=dev)
+                ops.images_to_batch(u_dev[b], out=x_dev[b], want_mask=False, table=u_tab[b])
+                u_tab[b] = ops.images_to_batch.last_table
             out = pick(self.forward(x_dev[b]))
             ev_used[b].record(comp)
             if out_dev[b] is None or set(out_dev[b]) != set(out) or any(out_dev[b][k].shape != v.shape for k, v in out.items()):

@@ -377,6 +377,34 @@ def nchw_to_nhwc(x, Cp):
     return out
 
 
+IMAGE_MEAN, IMAGE_STD = (0.538, 0.494, 0.453), (0.257, 0.263, 0.273)      # src/datasets/coco.py:78
+
+
+def images_to_batch(images, mean=IMAGE_MEAN, std=IMAGE_STD, out=None, want_mask=True, table=None):
+    """uint8 HWC device images -> (normalised fp32 [B,3,H,W] padded batch, bool [B,H,W] padding mask or None, padded flag).
+    images: one uint8 [B,H,W,3] tensor or a list of [h,w,3] tensors (padded bottom / right to the largest)"""
+    if isinstance(images, torch.Tensor):
+        assert images.dtype == torch.uint8 and images.dim() == 4 and images.shape[-1] == 3 and images.is_contiguous()
+        B, H, W = images.shape[:3]
+        step = H * W * 3
+        rows = [[images.data_ptr() + b * step, H, W] for b in range(B)]
+        dev, padded = images.device, False
+    else:
+        assert all(t.dtype == torch.uint8 and t.dim() == 3 and t.shape[-1] == 3 and t.is_contiguous() for t in images)
+        B, H, W = len(images), max(t.shape[0] for t in images), max(t.shape[1] for t in images)
+        rows = [[t.data_ptr(), t.shape[0], t.shape[1]] for t in images]
+        dev, padded = images[0].device, any(t.shape[0] != H or t.shape[1] != W for t in images)
+    if table is None:       # callers that reuse their device buffers pass the table of the previous call
+        table = torch.tensor(rows, dtype=torch.int64).to(dev, non_blocking=True)
+    images_to_batch.last_table = table
+    if out is None:
+        out = torch.empty(B, 3, H, W, dtype=torch.float32, device=dev)
+    mask = torch.empty(B, H, W, dtype=torch.bool, device=dev) if want_mask else None
+    m3, s3 = (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std)
+    capi.check(_L().gwd_images_to_batch(_ptr(table), B, H, W, m3, s3, _ptr(out), _ptr(mask), _stream()), "gwd_images_to_batch")
+    return out, mask, padded
+
+
 def pack_stem(w, shift):
     """[64,3,7,7] BN-scaled stem filter -> bf16 [64,160] with column ky*22 + kx*3 + c (gwd_stem_conv_pool), fp32 shift"""
     assert tuple(w.shape) == (64, 3, 7, 7)

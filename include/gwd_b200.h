@@ -182,6 +182,12 @@ int gwd_sample_bilinear(const void* x, int64_t x_rs, int32_t x_coff, const float
 /* same for a 1-channel fp32 map -> fp32 [B,K]  (points_sample.py:268) */
 int gwd_sample_scalar(const float* x, int32_t B, int32_t H, int32_t W, const float* coords, int32_t K, float* out,
                       void* stream);
+/* Input builder (src/datasets/coco.py:77-78 ToTensor + Normalize, src/util/misc.py:291-313 padding + mask): table is a
+ * DEVICE int64 [B][3] = {pointer to a uint8 HWC image on the device, its height, its width}; out fp32 [B,3,H,W] =
+ * ((u8 / 255) - mean[c]) / std[c] inside an image and 0 in its padding (IEEE division: bit-identical to torchvision);
+ * mask uint8 [B,H,W] = 1 on padding (optional).  mean3 / std3 are HOST arrays. */
+int gwd_images_to_batch(const int64_t* table, int32_t B, int32_t H, int32_t W, const float* mean3, const float* std3, float* out,
+                        uint8_t* mask, void* stream);
 /* nearest sample of the windowed feature map + shifted position table at R line end points
  * (multiscale_transformerr.py:676-701) -> bf16 [B,R,C] */
 int gwd_line_ref_gather(const void* win, int64_t win_rs, const float* pos, int64_t pos_bstride, const float* coords, int32_t R,

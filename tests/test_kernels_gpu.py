@@ -374,3 +374,25 @@ def test_dense_evaluator_batches_equal_the_batch_1_loop():
     tp, pos, res = np.diag(cm), cm.sum(1), cm.sum(0)
     assert abs(got["Mean IU"] - (tp / np.maximum(1.0, pos + res - tp)).mean() * 100) < 1e-9
     assert abs(got["Glass"] - tp[1] / max(1.0, pos[1] + res[1] - tp[1]) * 100) < 1e-9 and got["images"] == N
+
+
+def test_images_to_batch_bit_exact():
+    """uint8 HWC images -> normalised, padded NCHW batch + mask == torchvision's to_tensor / normalize + the reference's
+    nested_tensor_from_tensor_list, bit for bit (uniform batch and a ragged list)"""
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import model as M
+    ops = _ops()
+    g = _g(51)
+    mean, std = torch.tensor(ops.IMAGE_MEAN), torch.tensor(ops.IMAGE_STD)
+
+    def reference(u8):      # torchvision.transforms.functional.to_tensor + normalize
+        t = u8.permute(2, 0, 1).contiguous().to(torch.float32).div(255)
+        return t.sub(mean[:, None, None]).div(std[:, None, None])
+    batch = torch.randint(0, 256, (3, 40, 56, 3), generator=g, dtype=torch.uint8)
+    out, mask, padded = ops.images_to_batch(batch.cuda())
+    assert not padded and not bool(mask.any())
+    assert torch.equal(out.cpu(), torch.stack([reference(b) for b in batch]))
+    ragged = [torch.randint(0, 256, (h, w, 3), generator=g, dtype=torch.uint8) for h, w in ((40, 56), (33, 56), (40, 21))]
+    out, mask, padded = ops.images_to_batch([t.cuda() for t in ragged])
+    nt = M.nested_tensor_from_tensor_list([reference(t) for t in ragged])
+    assert padded and torch.equal(out.cpu(), nt.tensors) and torch.equal(mask.cpu(), nt.mask)

@@ -240,3 +240,20 @@ def test_infer_stream_matches_forward():
         for k in w:
             # same kernels, same inputs; only the fp64 atomics of the diffusion statistics may reorder
             assert torch.allclose(g[k].float(), w[k].float(), rtol=2e-3, atol=2e-4), k
+
+
+def test_infer_stream_accepts_raw_uint8_images():
+    """uint8 [B,H,W,3] host batches through the serving loop == normalising on the host (ToTensor + Normalize) first"""
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import ops
+    net, _, _ = model()
+    g = torch.Generator().manual_seed(9)
+    mean, std = torch.tensor(ops.IMAGE_MEAN), torch.tensor(ops.IMAGE_STD)
+    raws = [torch.randint(0, 256, (2, 128, 160, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(3)]
+    floats = [r.permute(0, 3, 1, 2).float().div(255).sub(mean[None, :, None, None]).div(std[None, :, None, None]).contiguous().pin_memory()
+              for r in raws]
+    a = [{k: v.clone() for k, v in out.items()} for out in net.infer_stream(iter(raws))]
+    b = [{k: v.clone() for k, v in out.items()} for out in net.infer_stream(iter(floats))]
+    for x, y in zip(a, b):
+        for k in x:
+            assert torch.equal(x[k], y[k]), k
