@@ -100,6 +100,7 @@ SIGNATURES = {
     "gwd_transpose": (c_int, [P, L, P, L, L, L, I, P, P]),
     "gwd_transpose_batch": (c_int, [P, P, I, I, P]),
     "gwd_linear_wgrad": (c_int, [P, L, P, L, L, I, I, P, L, P, P]),
+    "gwd_conv3x3_wgrad": (c_int, [P, L, P, L, I, I, I, I, I, P, P, P]),
     "gwd_attention_bwd": (c_int, [ctypes.POINTER(AttnBwdDesc), P]),
     "gwd_set_loss": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, I, P, P, P, P]),
     "gwd_sumsq": (c_int, [P, L, P, P]),

@@ -637,6 +637,7 @@ struct WgradParams {
   float* dw; float* db;
   int64_t dy_rs, x_rs, dw_rs;
   int R, N, K, rows_per_split;
+  int H, W, sy, sx;      // H > 0: rows are pixels of [B,H,W] maps and X is read at (y + sy, x + sx), zero outside the map
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
@@ -664,9 +665,16 @@ __global__ void __launch_bounds__(256) gwd_wgrad_kernel(WgradParams p) {
       const int rr = c >> 4, c8 = (c & 15) * 8;
       const int r = r0 + rr;
       const bool rin = r < r_end;
-      const bool va = rin && (n0 + c8 < p.N), vb = rin && (k0 + c8 < p.K);
+      const bool va = rin && (n0 + c8 < p.N);
+      bool vb = rin && (k0 + c8 < p.K);
+      int64_t xr = r;
+      if (p.H > 0 && vb) {      // one tap of a 3x3 convolution: the input pixel this output pixel saw through that tap
+        const int x = r % p.W, y = (r / p.W) % p.H;
+        vb = (y + p.sy >= 0) && (y + p.sy < p.H) && (x + p.sx >= 0) && (x + p.sx < p.W);
+        xr = r + p.sy * p.W + p.sx;
+      }
       cp_async16(aBase + static_cast<uint32_t>(((st * kWgR + rr) * kWgLd + c8) * 2), va ? p.dy + static_cast<int64_t>(r) * p.dy_rs + n0 + c8 : p.dy, va);
-      cp_async16(bBase + static_cast<uint32_t>(((st * kWgR + rr) * kWgLd + c8) * 2), vb ? p.x + static_cast<int64_t>(r) * p.x_rs + k0 + c8 : p.x, vb);
+      cp_async16(bBase + static_cast<uint32_t>(((st * kWgR + rr) * kWgLd + c8) * 2), vb ? p.x + xr * p.x_rs + k0 + c8 : p.x, vb);
     }
   };
 
@@ -1040,9 +1048,34 @@ extern "C" int gwd_adamw_step(float* p, const float* g, float* m, float* v, void
   return GWD_OK;
 }
 
+static int launch_wgrad(const void* dy, int64_t dy_rs, const void* x, int64_t x_rs, int64_t rows, int32_t N, int32_t K, float* dw,
+                        int64_t dw_rs, float* db, int H, int W, int sy, int sx, cudaStream_t stream);
+
 extern "C" int gwd_linear_wgrad(const void* dy, int64_t dy_rs, const void* x, int64_t x_rs, int64_t rows, int32_t N, int32_t K,
                                 float* dw, int64_t dw_rs, float* db, void* stream_) {
   GWD_STREAM;
+  return launch_wgrad(dy, dy_rs, x, x_rs, rows, N, K, dw, dw_rs, db, 0, 0, 0, 0, stream);
+}
+
+// 3x3 convolution (stride 1, zero padding 1) weight gradient in the packed tap-major layout of gwd_conv_gemm:
+// dw[dx*3+dy][n][c] += sum_{b,y,x} dy[b,y,x,n] * x[b, y+dy-1, x+dx-1, c]; one split-K pass per tap
+extern "C" int gwd_conv3x3_wgrad(const void* dy, int64_t dy_cs, const void* x, int64_t x_cs, int32_t B, int32_t H, int32_t W,
+                                 int32_t N, int32_t C, float* dw, float* db, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(B > 0 && H > 0 && W > 0, "gwd_conv3x3_wgrad: empty map");
+  const int64_t rows = static_cast<int64_t>(B) * H * W;
+  for (int dx = 0; dx < 3; ++dx)
+    for (int dyy = 0; dyy < 3; ++dyy) {
+      const int tap = dx * 3 + dyy;
+      int rc = launch_wgrad(dy, dy_cs, x, x_cs, rows, N, C, dw + static_cast<int64_t>(tap) * N * C, C, tap == 4 ? db : nullptr, H, W,
+                            dyy - 1, dx - 1, stream);
+      if (rc != GWD_OK) return rc;
+    }
+  return GWD_OK;
+}
+
+static int launch_wgrad(const void* dy, int64_t dy_rs, const void* x, int64_t x_rs, int64_t rows, int32_t N, int32_t K, float* dw,
+                        int64_t dw_rs, float* db, int H, int W, int sy, int sx, cudaStream_t stream) {
   GWD_CHECK_ARG(dy && x && dw && rows > 0 && N > 0 && K > 0, "gwd_linear_wgrad: null pointer / empty");
   GWD_CHECK_ARG(N % 8 == 0 && K % 8 == 0 && dy_rs % 8 == 0 && x_rs % 8 == 0 && dw_rs % 2 == 0 && dy_rs >= N && x_rs >= K &&
                     dw_rs >= K && (reinterpret_cast<uintptr_t>(dy) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 &&
@@ -1052,6 +1085,7 @@ extern "C" int gwd_linear_wgrad(const void* dy, int64_t dy_rs, const void* x, in
   WgradParams p;
   p.dy = static_cast<const bf16*>(dy); p.x = static_cast<const bf16*>(x); p.dw = dw; p.db = db;
   p.dy_rs = dy_rs; p.x_rs = x_rs; p.dw_rs = dw_rs; p.R = static_cast<int>(rows); p.N = N; p.K = K;
+  p.H = H; p.W = W; p.sy = sy; p.sx = sx;
   const int tiles = static_cast<int>(gwd_ceil_div(N, kWgT) * gwd_ceil_div(K, kWgT));
   static const int ctas_per_sm_x2 = []() { const char* e = getenv("GWD_WGRAD_CTAS_X2"); return e ? atoi(e) : 4; }();
   int64_t split = std::max<int64_t>(1, std::min<int64_t>(gwd_ceil_div(ctas_per_sm_x2 * gwd_num_sms() / 2, tiles), gwd_ceil_div(rows, 2 * kWgR)));

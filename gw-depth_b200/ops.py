@@ -584,6 +584,27 @@ def linear_wgrad(dy, x, dw, db=None, N=None, K=None, x_coff=0):
                                      _ptr(db), _stream()), "gwd_linear_wgrad")
 
 
+def conv3x3_wgrad(dy, x, dw, db=None, N=None, C=None):
+    """dw fp32 [9, N, C] (tap = dx*3+dy, the packed layout of pack_conv3x3) += 3x3-conv weight gradient; dy, x: bf16
+    channels-last [B,H,W,*]"""
+    B, H, W = x.shape[:3]
+    N, C = N or dw.shape[1], C or dw.shape[2]
+    assert dy.dtype == x.dtype == torch.bfloat16 and dw.dtype == torch.float32 and dw.is_contiguous() and dw.shape == (9, N, C)
+    capi.check(_L().gwd_conv3x3_wgrad(_ptr(dy), dy.shape[-1], _ptr(x), x.shape[-1], B, H, W, N, C, _ptr(dw), _ptr(db), _stream()),
+               "gwd_conv3x3_wgrad")
+
+
+def pack_conv3x3_dgrad(weight, cin_pad=None):
+    """the filter whose gwd_conv_gemm on dY gives dX of a stride-1, pad-1 3x3 conv with `weight` [N, C, 3, 3]:
+    transposed in (n, c), flipped in (dy, dx)"""
+    return pack_conv3x3(weight.transpose(0, 1).flip(2, 3).contiguous(), None, cin_pad=cin_pad)
+
+
+def unpack_conv3x3_grad(dw, n, c):
+    """packed gradient [9, N_pad, C_pad] (tap = dx*3+dy) -> the reference's [n, c, 3(dy), 3(dx)] layout"""
+    return dw.view(3, 3, dw.shape[1], dw.shape[2])[:, :, :n, :c].permute(2, 3, 1, 0).contiguous()
+
+
 def attention_bwd(q, k, v, d_o, dq, dk, dv, *, items, heads, Lq, Lk, hd, q_strides, k_strides, v_strides, do_strides,
                   dq_strides, dk_strides, dv_strides, scale=1.0, o=None, o_strides=None, dq_mul=0.0, dk_mul=0.0):
     """o: the forward output (bf16) -> tensor-core kernel; None -> CUDA-core kernel that recomputes D = rowsum(P dP)"""

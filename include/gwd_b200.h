@@ -273,6 +273,12 @@ int gwd_transpose_batch(const int64_t* table, const int32_t* tile_prefix, int32_
  * atomics, so dw / db must hold the running gradient (zeros at the start of a step). */
 int gwd_linear_wgrad(const void* dy, int64_t dy_rs, const void* x, int64_t x_rs, int64_t rows, int32_t N, int32_t K, float* dw,
                      int64_t dw_rs, float* db, void* stream);
+/* 3x3 convolution (stride 1, zero padding 1) weight gradient in the packed layout of gwd_conv_gemm:
+ * dw[dx*3+dy][n][c] (fp32 [9][N][C]) += sum_{b,y,x} dy[b,y,x,n] * x[b,y+dy-1,x+dx-1,c]; db[n] += sum dy (optional).
+ * dy bf16 [B,H,W,dy_cs], x bf16 [B,H,W,x_cs] channels-last; N, C multiples of 8.  (The data gradient of the same
+ * convolution is gwd_conv_gemm of dy with the filter transposed in (n, c) and flipped in (dy, dx).) */
+int gwd_conv3x3_wgrad(const void* dy, int64_t dy_cs, const void* x, int64_t x_cs, int32_t B, int32_t H, int32_t W, int32_t N,
+                      int32_t C, float* dw, float* db, void* stream);
 /* backward of O = softmax(scale Q K^T) V for head_dim 32, Lq, Lk <= 512 (no bias / mask): the soft-max is recomputed
  * from Q, K; dQ, dK, dV are bf16 views addressed like gwd_attn_desc.  With the forward output `o` given the kernel runs
  * on the tensor cores (mma.sync; D_i = dO_i . O_i); with o == NULL a CUDA-core kernel computes D itself. */

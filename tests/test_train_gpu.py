@@ -125,6 +125,27 @@ def test_linear_wgrad_kernel(R, N, K):
     assert rel_l2(db + 1.0, dY.double().sum(0)) < 2e-5
 
 
+@pytest.mark.parametrize("B,H,W,C,N", [(2, 24, 40, 160, 160), (1, 17, 23, 64, 32), (3, 8, 8, 32, 16), (1, 30, 40, 800, 320)])
+def test_conv3x3_backward_building_blocks(B, H, W, C, N):
+    """weight gradient (gwd_conv3x3_wgrad, tap-shifted split-K mma.sync) and data gradient (gwd_conv_gemm with the
+    transposed / flipped filter) of a stride-1 3x3 convolution vs torch.autograd on the same bf16 operands"""
+    ops = _ops()
+    g = _g(B * H + C)
+    x = torch.randn(B, H, W, C, generator=g).bfloat16()
+    w = (torch.randn(N, C, 3, 3, generator=g) * (9 * C) ** -0.5).bfloat16()
+    dy = torch.randn(B, H, W, N, generator=g).bfloat16()
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    F.conv2d(xr, wr, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+    dw = torch.full((9, N, C), 0.25, device="cuda")          # accumulation semantics
+    db = torch.zeros(N, device="cuda")
+    ops.conv3x3_wgrad(dy.cuda(), x.cuda(), dw, db)
+    assert rel_l2(ops.unpack_conv3x3_grad(dw - 0.25, N, C), wr.grad) < 2e-4
+    assert rel_l2(db, dy.float().sum((0, 1, 2))) < 2e-5
+    dx = ops.conv_gemm(dy.cuda(), ops.pack_conv3x3_dgrad(w.float().cuda()), bias=False)
+    assert rel_l2(dx[..., :C], xr.grad.permute(0, 2, 3, 1)) < 6e-3
+
+
 @pytest.mark.parametrize("use_o", [True, False])      # True: tensor-core kernel (needs the forward output), False: CUDA-core kernel
 @pytest.mark.parametrize("B,Lq,Lk,fused", [(2, 300, 300, True), (3, 100, 300, False), (2, 100, 100, True), (1, 37, 480, False),
                                            (1, 512, 512, True), (2, 1, 5, False)])
