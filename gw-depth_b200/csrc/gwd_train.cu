@@ -37,17 +37,29 @@ __device__ __forceinline__ void st8(bf16* p, const float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kLnWarps = 8;
 
+// d act(v) / dv from the activation's INPUT v (GELU in its exact erf form, as the reference's nn.GELU differentiates)
+__device__ __forceinline__ float gwd_act_grad(float v, int act) {
+  switch (act) {
+    case GWD_ACT_RELU: return v > 0.f ? 1.f : 0.f;
+    case GWD_ACT_GELU: return 0.5f * (1.f + erff(v * 0.70710678f)) + v * 0.39894228f * __expf(-0.5f * v * v);
+    case GWD_ACT_ELU: return v > 0.f ? 1.f : __expf(v);
+    case GWD_ACT_SIGMOID: { const float s = 1.f / (1.f + __expf(-v)); return s * (1.f - s); }
+    default: return 1.f;
+  }
+}
+
 template <int NV>
 __global__ void __launch_bounds__(kLnWarps * 32)
 gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16* __restrict__ z, int64_t z_rs,
-                         const float* __restrict__ gamma, float eps, const bf16* __restrict__ add, int64_t add_rs,
+                         const float* __restrict__ gamma, const float* __restrict__ beta, int post_act, float eps,
+                         const bf16* __restrict__ add, int64_t add_rs,
                          bf16* __restrict__ dz, int64_t dz_rs, float* __restrict__ dgamma, float* __restrict__ dbeta,
                          int64_t rows, int C) {
   __shared__ float part[kLnWarps][NV * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t gwarp = static_cast<int64_t>(blockIdx.x) * kLnWarps + warp;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kLnWarps;
-  float ag[NV][8], ab[NV][8], gm[NV][8];
+  float ag[NV][8], ab[NV][8], gm[NV][8], bt[NV][8];
   bool on[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
@@ -56,6 +68,7 @@ gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16*
     for (int e = 0; e < 8; ++e) {
       ag[v][e] = 0.f; ab[v][e] = 0.f;
       gm[v][e] = on[v] ? gamma[(lane + 32 * v) * 8 + e] : 0.f;
+      bt[v][e] = (on[v] && post_act != GWD_ACT_NONE) ? beta[(lane + 32 * v) * 8 + e] : 0.f;
     }
   }
   const float invC = 1.f / static_cast<float>(C);
@@ -90,6 +103,7 @@ gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16*
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         zv[v][e] *= rstd;                                  // xh
+        if (post_act != GWD_ACT_NONE) dv[v][e] *= gwd_act_grad(fmaf(zv[v][e], gm[v][e], bt[v][e]), post_act);   // through act(LN(z))
         ag[v][e] += dv[v][e] * zv[v][e];
         ab[v][e] += dv[v][e];
         dv[v][e] *= gm[v][e];                              // g
@@ -150,7 +164,7 @@ __global__ void gwd_act_bwd_kernel(const TD* __restrict__ dy, int64_t dy_rs, con
       v = static_cast<float>(dy[r * dy_rs + c]);
       if (act != GWD_ACT_NONE) {
         const float yy = static_cast<float>(y[r * y_rs + c]);
-        v = act == GWD_ACT_RELU ? (yy > 0.f ? v : 0.f) : v * yy * (1.f - yy);
+        v = act == GWD_ACT_RELU ? (yy > 0.f ? v : 0.f) : (act == GWD_ACT_ELU ? (yy > 0.f ? v : v * (yy + 1.f)) : v * yy * (1.f - yy));
       }
     }
     out[r * out_rs + c] = __float2bfloat16(v);
@@ -234,7 +248,8 @@ gwd_act_bwd_vec_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, 
     ld8(dy + i * 8, d);
     ld8(y + i * 8, v);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) d[e] = act == GWD_ACT_RELU ? (v[e] > 0.f ? d[e] : 0.f) : d[e] * v[e] * (1.f - v[e]);
+    for (int e = 0; e < 8; ++e)
+      d[e] = act == GWD_ACT_RELU ? (v[e] > 0.f ? d[e] : 0.f) : (act == GWD_ACT_ELU ? (v[e] > 0.f ? d[e] : d[e] * (v[e] + 1.f)) : d[e] * v[e] * (1.f - v[e]));
     st8(out + i * 8, d);
   }
 }
@@ -906,16 +921,18 @@ gwd_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 
 #define GWD_STREAM cudaStream_t stream = static_cast<cudaStream_t>(stream_)
 
-extern "C" int gwd_layernorm_bwd(const void* dy, int64_t dy_rs, const void* z, int64_t z_rs, const float* gamma, float eps,
-                                 const void* add, int64_t add_rs, void* dz, int64_t dz_rs, float* dgamma, float* dbeta,
-                                 int64_t rows, int32_t C, void* stream_) {
+extern "C" int gwd_layernorm_bwd(const void* dy, int64_t dy_rs, const void* z, int64_t z_rs, const float* gamma, const float* beta,
+                                 int32_t post_act, float eps, const void* add, int64_t add_rs, void* dz, int64_t dz_rs,
+                                 float* dgamma, float* dbeta, int64_t rows, int32_t C, void* stream_) {
   GWD_STREAM;
   GWD_CHECK_ARG(dy && z && gamma && dz && rows > 0, "gwd_layernorm_bwd: null pointer / empty");
+  GWD_CHECK_ARG(post_act == GWD_ACT_NONE || beta != nullptr, "gwd_layernorm_bwd: beta needed to differentiate through act(LN(z))");
   GWD_CHECK_ARG(C % 8 == 0 && C > 0 && C <= 512 && dy_rs % 8 == 0 && z_rs % 8 == 0 && dz_rs % 8 == 0 && add_rs % 8 == 0,
                 "gwd_layernorm_bwd: C and strides must be multiples of 8, C <= 512");
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(rows, kLnWarps * 2), 4 * gwd_num_sms()));
   auto launch = [&](auto kern) {
-    kern<<<grid, kLnWarps * 32, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, static_cast<const bf16*>(z), z_rs, gamma, eps,
+    kern<<<grid, kLnWarps * 32, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, static_cast<const bf16*>(z), z_rs, gamma, beta,
+                                             post_act, eps,
                                              static_cast<const bf16*>(add), add_rs, static_cast<bf16*>(dz), dz_rs, dgamma,
                                              dbeta, rows, C);
   };
@@ -929,7 +946,8 @@ extern "C" int gwd_act_bwd(const void* dy, int32_t dy_f32, int64_t dy_rs, const 
                            int32_t act, void* out, int64_t out_rs, int64_t rows, int32_t n, int32_t out_cols, void* stream_) {
   GWD_STREAM;
   GWD_CHECK_ARG(dy && out && rows > 0 && n > 0 && out_cols >= n && out_rs >= out_cols, "gwd_act_bwd: bad argument");
-  GWD_CHECK_ARG(act == GWD_ACT_NONE || act == GWD_ACT_RELU || act == GWD_ACT_SIGMOID, "gwd_act_bwd: activation %d unsupported", act);
+  GWD_CHECK_ARG(act == GWD_ACT_NONE || act == GWD_ACT_RELU || act == GWD_ACT_SIGMOID || act == GWD_ACT_ELU,
+                "gwd_act_bwd: activation %d unsupported (GELU is not invertible from its output: see gwd_layernorm_bwd's post_act)", act);
   GWD_CHECK_ARG(act == GWD_ACT_NONE || y != nullptr, "gwd_act_bwd: y needed");
   bf16* o = static_cast<bf16*>(out);
   if (!dy_f32 && !y_f32 && act != GWD_ACT_NONE && n == out_cols && dy_rs == n && y_rs == n && out_rs == n && n % 8 == 0 &&

@@ -520,12 +520,12 @@ def silog_sums(pred, gt, lo=0.2, hi=10.0, log_only=False):
 # ------------------------------------------------------------------------------------------
 # training side of the line branch: backward + optimizer kernels (gwd_train.cu)
 # ------------------------------------------------------------------------------------------
-def layernorm_bwd(dy, z, gamma, dgamma, dbeta, add=None, eps=1e-5):
-    """dz (+ add) of y = LN(z); dgamma / dbeta (fp32 views, may be None) are accumulated"""
+def layernorm_bwd(dy, z, gamma, dgamma, dbeta, add=None, eps=1e-5, beta=None, post_act=ACT_NONE):
+    """dz (+ add) of y = post_act(LN(z)); dgamma / dbeta (fp32 views, may be None) are accumulated"""
     C = z.shape[-1]
     rows = _rows(z)
     dz = torch.empty(rows, C, dtype=torch.bfloat16, device=z.device)
-    capi.check(_L().gwd_layernorm_bwd(_ptr(dy), dy.shape[-1], _ptr(z), C, _ptr(gamma), eps, _ptr(add),
+    capi.check(_L().gwd_layernorm_bwd(_ptr(dy), dy.shape[-1], _ptr(z), C, _ptr(gamma), _ptr(beta), post_act, eps, _ptr(add),
                                       add.shape[-1] if add is not None else 0, _ptr(dz), C, _ptr(dgamma), _ptr(dbeta), rows, C,
                                       _stream()), "gwd_layernorm_bwd")
     return dz

@@ -250,13 +250,16 @@ int gwd_silog_sums(const float* pred, int32_t B, int32_t h, int32_t w, const flo
  * clip_grad_norm_ (src/main_glassrgbd.py:59-67, src/engine_glassrgbd.py:155-159).
  * Data gradients dX = dY W and weight gradients dW = dY^T X are gwd_conv_gemm calls on transposed operands.
  * ------------------------------------------------------------------------------------------ */
-/* y = LayerNorm_C(z) * gamma + beta:  dz[rows,C] (bf16) = LN backward of dy (+ `add`, an optional bf16 gradient that
- * joins at the same tensor, e.g. the residual branch); dgamma / dbeta fp32 [C] are ACCUMULATED (atomicAdd; NULL = skip). */
-int gwd_layernorm_bwd(const void* dy, int64_t dy_rs, const void* z, int64_t z_rs, const float* gamma, float eps,
-                      const void* add, int64_t add_rs, void* dz, int64_t dz_rs, float* dgamma, float* dbeta, int64_t rows,
-                      int32_t C, void* stream);
+/* y = post_act(LayerNorm_C(z) * gamma + beta):  dz[rows,C] (bf16) = backward of dy through the activation (evaluated from
+ * the recomputed LN output; GWD_ACT_NONE: plain LayerNorm, beta may be NULL) and the LayerNorm (+ `add`, an optional bf16
+ * gradient that joins at the same tensor, e.g. the residual branch); dgamma / dbeta fp32 [C] are ACCUMULATED (atomicAdd;
+ * NULL = skip).  z is the pre-norm value (gwd_conv_gemm's y_raw).  Covers LayerNorm (transformer.py:149-233) and the
+ * conv -> LayerNorm -> GELU blocks of src/models/points/points_sample.py:12-43. */
+int gwd_layernorm_bwd(const void* dy, int64_t dy_rs, const void* z, int64_t z_rs, const float* gamma, const float* beta,
+                      int32_t post_act, float eps, const void* add, int64_t add_rs, void* dz, int64_t dz_rs, float* dgamma,
+                      float* dbeta, int64_t rows, int32_t C, void* stream);
 /* out[r, c] (bf16, c < out_cols) = c < n ? dy[r,c] * act'(y[r,c]) : 0 with act' evaluated from the OUTPUT y
- * (GWD_ACT_RELU, GWD_ACT_SIGMOID, or GWD_ACT_NONE = dtype conversion + padding).  dy / y are fp32 or bf16. */
+ * (GWD_ACT_RELU, GWD_ACT_SIGMOID, GWD_ACT_ELU, or GWD_ACT_NONE = dtype conversion + padding).  dy / y are fp32 or bf16. */
 int gwd_act_bwd(const void* dy, int32_t dy_f32, int64_t dy_rs, const void* y, int32_t y_f32, int64_t y_rs, int32_t act,
                 void* out, int64_t out_rs, int64_t rows, int32_t n, int32_t out_cols, void* stream);
 /* out[c, r] = x[r, c] (bf16; r < rows, c < C), columns rows..rows_pad of out written as zeros; colsum (optional, fp32

@@ -50,6 +50,39 @@ def test_layernorm_bwd(rows, C, with_add):
     assert rel_l2(dbeta, br.grad) < 1e-4
 
 
+def test_conv_layernorm_gelu_block_backward():
+    """ConvLn + GELU + residual (src/models/points/points_sample.py:12-43, the PyramidLayer block that carries most of the
+    model's FLOPs): forward on gwd_conv_gemm with the pre-norm value kept, backward = gwd_layernorm_bwd(post_act=GELU) ->
+    gwd_conv3x3_wgrad + dgrad on gwd_conv_gemm, against torch.autograd (erf GELU) on the same bf16 operands"""
+    ops = _ops()
+    g = _g(23)
+    B, H, W, C = 2, 24, 32, 160
+    x = torch.randn(B, H, W, C, generator=g).bfloat16()
+    w = (torch.randn(C, C, 3, 3, generator=g) * (9 * C) ** -0.5).bfloat16()
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.2
+    dy = torch.randn(B, H, W, C, generator=g).bfloat16()
+    # reference
+    xr, wr = x.float().permute(0, 3, 1, 2).requires_grad_(True), w.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    conv = F.conv2d(xr, wr, padding=1).permute(0, 2, 3, 1)
+    y = F.gelu(F.layer_norm(conv, (C,), gr, br, 1e-5)) + xr.permute(0, 2, 3, 1)
+    y.backward(dy.float())
+    # CUDA path
+    xc = x.cuda()
+    z = torch.empty(B, H, W, C, dtype=torch.bfloat16, device="cuda")
+    yc = ops.conv_gemm(xc, ops.pack_conv3x3(w.float().cuda()), bias=False, ln=(gamma.cuda(), beta.cuda()), post_act=ops.ACT_GELU,
+                       res=xc, res_mode=ops.RES_AFTER, y_raw=z)
+    assert rel_l2(yc, y.detach()) < 1e-2
+    dgam, dbet = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dz = ops.layernorm_bwd(dy.cuda(), z.view(-1, C), gamma.cuda(), dgam, dbet, beta=beta.cuda(), post_act=ops.ACT_GELU).view(B, H, W, C)
+    dw = torch.zeros(9, C, C, device="cuda")
+    ops.conv3x3_wgrad(dz, xc, dw)
+    dx = ops.conv_gemm(dz, ops.pack_conv3x3_dgrad(w.float().cuda()), bias=False, res=dy.cuda(), res_mode=ops.RES_AFTER)
+    assert rel_l2(ops.unpack_conv3x3_grad(dw, C, C), wr.grad) < 2e-2
+    assert rel_l2(dgam, gr.grad) < 2e-2 and rel_l2(dbet, br.grad) < 2e-2
+    assert rel_l2(dx, xr.grad.permute(0, 2, 3, 1)) < 2e-2
+
+
 def test_act_bwd_and_padding():
     ops = _ops()
     g = _g(3)
@@ -63,6 +96,11 @@ def test_act_bwd_and_padding():
     dh = torch.randn(333, 2048, generator=g).bfloat16()
     out = ops.act_bwd(dh.cuda(), h.cuda(), ops.ACT_RELU).cpu()
     assert torch.equal(out, torch.where(h > 0, dh, torch.zeros_like(dh)))
+    e = F.elu(torch.randn(333, 64, generator=g)).bfloat16()
+    de = torch.randn(333, 64, generator=g).bfloat16()
+    out = ops.act_bwd(de.cuda(), e.cuda(), ops.ACT_ELU).float().cpu()
+    ref_e = torch.where(e.float() > 0, de.float(), de.float() * (e.float() + 1)).bfloat16().float()
+    assert torch.equal(out, ref_e)
     out = ops.act_bwd(dy[:, :2].contiguous().cuda(), None, ops.ACT_NONE, out_cols=16).float().cpu()
     assert torch.equal(out[:, :2], dy[:, :2].bfloat16().float()) and float(out[:, 2:].abs().max()) == 0.0
 
