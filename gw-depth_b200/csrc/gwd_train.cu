@@ -151,9 +151,21 @@ gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16*
 // activation backward from the OUTPUT value: ReLU: dy * (y > 0); sigmoid: dy * y * (1 - y); none: dy.
 // Converts fp32 / bf16 inputs to a bf16 [rows, out_cols] matrix whose columns n..out_cols are zero.
 // ------------------------------------------------------------------------------------------------
+// derivative factor of `act` from its OUTPUT yy (from_input == 0) or from its INPUT yy (from_input != 0)
+__device__ __forceinline__ float act_factor(float yy, int act, int from_input) {
+  if (from_input) return gwd_act_grad(yy, act);
+  switch (act) {
+    case GWD_ACT_RELU: return yy > 0.f ? 1.f : 0.f;
+    case GWD_ACT_ELU: return yy > 0.f ? 1.f : yy + 1.f;
+    case GWD_ACT_SIGMOID: return yy * (1.f - yy);
+    default: return 1.f;
+  }
+}
+
 template <typename TD, typename TY>
 __global__ void gwd_act_bwd_kernel(const TD* __restrict__ dy, int64_t dy_rs, const TY* __restrict__ y, int64_t y_rs, int act,
-                                   bf16* __restrict__ out, int64_t out_rs, int64_t rows, int n, int out_cols) {
+                                   bf16* __restrict__ out, int64_t out_rs, int64_t rows, int n, int out_cols, float y_mul,
+                                   float scale, int from_input) {
   const int64_t total = rows * out_cols;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -162,10 +174,8 @@ __global__ void gwd_act_bwd_kernel(const TD* __restrict__ dy, int64_t dy_rs, con
     float v = 0.f;
     if (c < n) {
       v = static_cast<float>(dy[r * dy_rs + c]);
-      if (act != GWD_ACT_NONE) {
-        const float yy = static_cast<float>(y[r * y_rs + c]);
-        v = act == GWD_ACT_RELU ? (yy > 0.f ? v : 0.f) : (act == GWD_ACT_ELU ? (yy > 0.f ? v : v * (yy + 1.f)) : v * yy * (1.f - yy));
-      }
+      if (act != GWD_ACT_NONE) v *= act_factor(static_cast<float>(y[r * y_rs + c]) * y_mul, act, from_input);
+      v *= scale;
     }
     out[r * out_rs + c] = __float2bfloat16(v);
   }
@@ -242,14 +252,14 @@ gwd_transpose_batch_kernel(const int64_t* __restrict__ table, const int32_t* __r
 
 // vector path of gwd_act_bwd: bf16 dy, bf16 y, no padding, 8 elements per thread
 __global__ void __launch_bounds__(256)
-gwd_act_bwd_vec_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, int act, bf16* __restrict__ out, int64_t n8) {
+gwd_act_bwd_vec_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, int act, bf16* __restrict__ out, int64_t n8,
+                       float y_mul, float scale, int from_input) {
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     float d[8], v[8];
     ld8(dy + i * 8, d);
     ld8(y + i * 8, v);
 #pragma unroll
-    for (int e = 0; e < 8; ++e)
-      d[e] = act == GWD_ACT_RELU ? (v[e] > 0.f ? d[e] : 0.f) : (act == GWD_ACT_ELU ? (v[e] > 0.f ? d[e] : d[e] * (v[e] + 1.f)) : d[e] * v[e] * (1.f - v[e]));
+    for (int e = 0; e < 8; ++e) d[e] = d[e] * act_factor(v[e] * y_mul, act, from_input) * scale;
     st8(out + i * 8, d);
   }
 }
@@ -943,30 +953,33 @@ extern "C" int gwd_layernorm_bwd(const void* dy, int64_t dy_rs, const void* z, i
 }
 
 extern "C" int gwd_act_bwd(const void* dy, int32_t dy_f32, int64_t dy_rs, const void* y, int32_t y_f32, int64_t y_rs,
-                           int32_t act, void* out, int64_t out_rs, int64_t rows, int32_t n, int32_t out_cols, void* stream_) {
+                           int32_t act, void* out, int64_t out_rs, int64_t rows, int32_t n, int32_t out_cols, float y_mul,
+                           float scale, int32_t from_input, void* stream_) {
   GWD_STREAM;
   GWD_CHECK_ARG(dy && out && rows > 0 && n > 0 && out_cols >= n && out_rs >= out_cols, "gwd_act_bwd: bad argument");
-  GWD_CHECK_ARG(act == GWD_ACT_NONE || act == GWD_ACT_RELU || act == GWD_ACT_SIGMOID || act == GWD_ACT_ELU,
-                "gwd_act_bwd: activation %d unsupported (GELU is not invertible from its output: see gwd_layernorm_bwd's post_act)", act);
+  GWD_CHECK_ARG(act == GWD_ACT_NONE || act == GWD_ACT_RELU || act == GWD_ACT_SIGMOID || act == GWD_ACT_ELU ||
+                    (act == GWD_ACT_GELU && from_input),
+                "gwd_act_bwd: activation %d unsupported (GELU is not invertible from its output: pass its input, from_input = 1)", act);
   GWD_CHECK_ARG(act == GWD_ACT_NONE || y != nullptr, "gwd_act_bwd: y needed");
   bf16* o = static_cast<bf16*>(out);
   if (!dy_f32 && !y_f32 && act != GWD_ACT_NONE && n == out_cols && dy_rs == n && y_rs == n && out_rs == n && n % 8 == 0 &&
       ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
     const int64_t n8 = rows * n / 8;
     const unsigned g = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(n8, 256), 16 * gwd_num_sms()));
-    gwd_act_bwd_vec_kernel<<<g, 256, 0, stream>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(y), act, o, n8);
+    gwd_act_bwd_vec_kernel<<<g, 256, 0, stream>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(y), act, o, n8, y_mul, scale,
+                                                  from_input);
     GWD_LAUNCHED();
     return GWD_OK;
   }
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(rows * out_cols, 256), 8 * gwd_num_sms()));
   if (dy_f32 && y_f32)
-    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(dy), dy_rs, static_cast<const float*>(y), y_rs, act, o, out_rs, rows, n, out_cols);
+    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(dy), dy_rs, static_cast<const float*>(y), y_rs, act, o, out_rs, rows, n, out_cols, y_mul, scale, from_input);
   else if (dy_f32)
-    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(dy), dy_rs, static_cast<const bf16*>(y), y_rs, act, o, out_rs, rows, n, out_cols);
+    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(dy), dy_rs, static_cast<const bf16*>(y), y_rs, act, o, out_rs, rows, n, out_cols, y_mul, scale, from_input);
   else if (y_f32)
-    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, static_cast<const float*>(y), y_rs, act, o, out_rs, rows, n, out_cols);
+    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, static_cast<const float*>(y), y_rs, act, o, out_rs, rows, n, out_cols, y_mul, scale, from_input);
   else
-    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, static_cast<const bf16*>(y), y_rs, act, o, out_rs, rows, n, out_cols);
+    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, static_cast<const bf16*>(y), y_rs, act, o, out_rs, rows, n, out_cols, y_mul, scale, from_input);
   GWD_LAUNCHED();
   return GWD_OK;
 }
@@ -1143,5 +1156,157 @@ extern "C" int gwd_transpose_batch(const int64_t* table, const int32_t* tile_pre
   GWD_CHECK_ARG(table && tile_prefix && n_mats > 0 && total_tiles > 0, "gwd_transpose_batch: bad argument");
   gwd_transpose_batch_kernel<<<total_tiles, 256, 0, stream>>>(table, tile_prefix, n_mats);
   GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dense losses, backward: SilogLoss (src/models/glassrgbd.py:360-374 under the per-scale loop of
+// src/engine_glassrgbd.py:65-82) and SegLoss = mean cross entropy (src/models/glassrgbd.py:376-383)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// loss = weight * 10 * sqrt(V), V = S2/n - vf (S1/n)^2 over the valid pixels (sums3 = n, S1, S2 from gwd_silog_sums):
+//   dloss/dd_i = weight * 10 / (2 sqrt(V)) * (2 d_i / n - 2 vf S1 / n^2);   dd/dp = 1/p (log only) or 1 + 1/p
+// sig_scale > 0: p = sig_scale * sigmoid(z) and the gradient is taken to z (times p (1 - p / sig_scale)).
+// out_cols == 0: fp32 [B*h*w]; else bf16 rows of out_cols columns, gradient in column 0, zeros elsewhere.
+__global__ void __launch_bounds__(256)
+gwd_silog_bwd_kernel(const float* __restrict__ pred, int B, int h, int w, const float* __restrict__ gt, int H, int W, float lo,
+                     float hi, int log_only, const double* __restrict__ sums, float vf, float weight, float sig_scale,
+                     void* __restrict__ out, int out_cols, float* __restrict__ loss_out) {
+  const double n = sums[0];
+  const double mean = n > 0 ? sums[1] / n : 0.0;
+  const double V = n > 0 ? sums[2] / n - static_cast<double>(vf) * mean * mean : 0.0;
+  const double root = V > 0 ? sqrt(V) : 0.0;
+  if (loss_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) loss_out[0] = static_cast<float>(weight * 10.0 * root);
+  const float a = root > 0 ? static_cast<float>(weight * 10.0 / root / n) : 0.f;   // d_i coefficient
+  const float c = static_cast<float>(static_cast<double>(vf) * mean);
+  const int64_t total = static_cast<int64_t>(B) * h * w;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int x = i % w;
+    const int y = (i / w) % h;
+    const int b = i / (static_cast<int64_t>(w) * h);
+    const int sy = min(static_cast<int>((static_cast<int64_t>(y) * H) / h), H - 1);
+    const int sx = min(static_cast<int>((static_cast<int64_t>(x) * W) / w), W - 1);
+    const float g = gt[(static_cast<int64_t>(b) * H + sy) * W + sx];
+    float v = 0.f;
+    if (g >= lo && g < hi) {
+      const float q = pred[i];
+      const float d = log_only ? (logf(q) - logf(g)) : ((q + logf(q)) - (g + logf(g)));
+      v = a * (d - c) * (log_only ? 1.f / q : 1.f + 1.f / q);
+      if (sig_scale > 0.f) v *= q * (1.f - q / sig_scale);
+    }
+    if (out_cols == 0) {
+      static_cast<float*>(out)[i] = v;
+    } else {
+      bf16* row = static_cast<bf16*>(out) + i * out_cols;
+      float r[8] = {v, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      st8(row, r);
+      r[0] = 0.f;
+      for (int k = 8; k < out_cols; k += 8) st8(row + k, r);
+    }
+  }
+}
+
+constexpr int kCeMaxClasses = 8;
+
+// sums[0] += valid pixels, sums[1] += sum of -log softmax(logits)[gt]
+__global__ void __launch_bounds__(256)
+gwd_seg_ce_sums_kernel(const float* __restrict__ logits, int64_t pixel_stride, int64_t class_stride, int64_t image_stride,
+                       const int64_t* __restrict__ gt, int64_t HW, int64_t total, int C, int ignore, double* __restrict__ sums) {
+  double a0 = 0, a1 = 0;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t g = gt[i];
+    if (g == ignore || g < 0 || g >= C) continue;
+    const float* px = logits + (i / HW) * image_stride + (i % HW) * pixel_stride;
+    float m = px[0];
+    for (int k = 1; k < C; ++k) m = fmaxf(m, px[k * class_stride]);
+    float s = 0.f;
+    for (int k = 0; k < C; ++k) s += expf(px[k * class_stride] - m);
+    a0 += 1.0;
+    a1 += static_cast<double>(m + logf(s) - px[g * class_stride]);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+  }
+  if ((threadIdx.x & 31) == 0 && a0 > 0) {
+    atomicAdd(&sums[0], a0);
+    atomicAdd(&sums[1], a1);
+  }
+}
+
+// dlogits[i, k] = weight / n * (softmax_k - [k == gt]) as bf16 rows of out_cols columns (zeros beyond C); loss = weight * S / n
+__global__ void __launch_bounds__(256)
+gwd_seg_ce_bwd_kernel(const float* __restrict__ logits, int64_t pixel_stride, int64_t class_stride, int64_t image_stride,
+                      const int64_t* __restrict__ gt, int64_t HW, int64_t total, int C, int ignore,
+                      const double* __restrict__ sums, float weight, bf16* __restrict__ out, int out_cols,
+                      float* __restrict__ loss_out) {
+  const double n = sums[0];
+  if (loss_out != nullptr && blockIdx.x == 0 && threadIdx.x == 0) loss_out[0] = n > 0 ? static_cast<float>(weight * sums[1] / n) : 0.f;
+  const float a = n > 0 ? static_cast<float>(weight / n) : 0.f;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    float r[kCeMaxClasses];
+#pragma unroll
+    for (int k = 0; k < kCeMaxClasses; ++k) r[k] = 0.f;
+    const int64_t g = gt[i];
+    if (!(g == ignore || g < 0 || g >= C)) {
+      const float* px = logits + (i / HW) * image_stride + (i % HW) * pixel_stride;
+      float m = px[0];
+      for (int k = 1; k < C; ++k) m = fmaxf(m, px[k * class_stride]);
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < kCeMaxClasses; ++k)
+        if (k < C) { r[k] = expf(px[k * class_stride] - m); s += r[k]; }
+      const float inv = a / s;
+#pragma unroll
+      for (int k = 0; k < kCeMaxClasses; ++k)
+        if (k < C) r[k] = r[k] * inv - (k == g ? a : 0.f);
+    }
+    bf16* row = out + i * out_cols;
+    st8(row, r);
+#pragma unroll
+    for (int k = 0; k < kCeMaxClasses; ++k) r[k] = 0.f;
+    for (int k = 8; k < out_cols; k += 8) st8(row + k, r);
+  }
+}
+
+}  // namespace
+
+extern "C" int gwd_silog_bwd(const float* pred, int32_t B, int32_t h, int32_t w, const float* gt, int32_t H, int32_t W, float lo,
+                             float hi, int32_t log_only, const double* sums3, float variance_focus, float weight,
+                             float sig_scale, void* out, int32_t out_cols, float* loss_out, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(pred && gt && sums3 && out && B > 0 && h > 0 && w > 0 && H > 0 && W > 0, "gwd_silog_bwd: bad argument");
+  GWD_CHECK_ARG(out_cols >= 0 && out_cols % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+                "gwd_silog_bwd: out_cols must be 0 (fp32) or a multiple of 8 (bf16 rows), out 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(B) * h * w;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(total, 256), 16 * gwd_num_sms()));
+  gwd_silog_bwd_kernel<<<grid, 256, 0, stream>>>(pred, B, h, w, gt, H, W, lo, hi, log_only, sums3, variance_focus, weight,
+                                                 sig_scale, out, out_cols, loss_out);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_seg_ce(const float* logits, int64_t pixel_stride, int64_t class_stride, int64_t image_stride,
+                          const int64_t* gt, int32_t B, int64_t HW, int32_t C, int32_t ignore_index, float weight, double* sums2,
+                          void* dlogits, int32_t out_cols, float* loss_out, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(logits && gt && sums2 && B > 0 && HW > 0 && C >= 2 && C <= kCeMaxClasses, "gwd_seg_ce: bad argument (2 <= classes <= 8)");
+  GWD_CHECK_ARG(dlogits == nullptr || (out_cols >= 8 && out_cols % 8 == 0 && (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0),
+                "gwd_seg_ce: dlogits rows must be a multiple of 8 bf16 columns, 16-byte aligned");
+  const int64_t total = static_cast<int64_t>(B) * HW;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(total, 256), 16 * gwd_num_sms()));
+  GWD_CUDA(cudaMemsetAsync(sums2, 0, sizeof(double) * 2, stream));
+  gwd_seg_ce_sums_kernel<<<grid, 256, 0, stream>>>(logits, pixel_stride, class_stride, image_stride, gt, HW, total, C, ignore_index, sums2);
+  GWD_LAUNCHED();
+  if (dlogits != nullptr) {
+    gwd_seg_ce_bwd_kernel<<<grid, 256, 0, stream>>>(logits, pixel_stride, class_stride, image_stride, gt, HW, total, C, ignore_index,
+                                                    sums2, weight, static_cast<bf16*>(dlogits), out_cols, loss_out);
+    GWD_LAUNCHED();
+  }
   return GWD_OK;
 }

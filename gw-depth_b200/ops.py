@@ -531,16 +531,44 @@ def layernorm_bwd(dy, z, gamma, dgamma, dbeta, add=None, eps=1e-5, beta=None, po
     return dz
 
 
-def act_bwd(dy, y, act, out_cols=None):
-    """bf16 [rows, out_cols] = dy * act'(y) evaluated from the output y (zeros in the padding columns)"""
+def act_bwd(dy, y, act, out_cols=None, y_mul=1.0, scale=1.0, from_input=False):
+    """bf16 [rows, out_cols] = dy * act'(.) * scale, act' from the output y * y_mul (or from the activation's input with
+    from_input=True); zeros in the padding columns"""
     n = dy.shape[-1]
     rows = _rows(dy)
     out_cols = out_cols or round_up(n, 8)
     out = torch.empty(rows, out_cols, dtype=torch.bfloat16, device=dy.device)
     capi.check(_L().gwd_act_bwd(_ptr(dy), int(dy.dtype == torch.float32), n, _ptr(y),
                                 int(y is not None and y.dtype == torch.float32), y.shape[-1] if y is not None else 0, act,
-                                _ptr(out), out_cols, rows, n, out_cols, _stream()), "gwd_act_bwd")
+                                _ptr(out), out_cols, rows, n, out_cols, y_mul, scale, int(from_input), _stream()), "gwd_act_bwd")
     return out
+
+
+def silog_bwd(pred, gt, sums, *, weight=1.0, lo=0.2, hi=10.0, log_only=False, variance_focus=0.85, sig_scale=0.0,
+              out_cols=0, loss_out=None):
+    """gradient of weight * SilogLoss to pred fp32 [B,1,h,w] (or, with sig_scale > 0, to the pre-sigmoid value) from the
+    device-resident sums of `silog_sums`: fp32 [B*h*w] (out_cols 0) or bf16 [B*h*w, out_cols] with the gradient in column 0"""
+    B, _, h, w = pred.shape
+    H, W = gt.shape[-2:]
+    n = B * h * w
+    out = (torch.empty(n, dtype=torch.float32, device=pred.device) if out_cols == 0
+           else torch.empty(n, out_cols, dtype=torch.bfloat16, device=pred.device))
+    capi.check(_L().gwd_silog_bwd(_ptr(pred), B, h, w, _ptr(gt), H, W, lo, hi, 1 if log_only else 0, _ptr(sums), variance_focus,
+                                  weight, sig_scale, _ptr(out), out_cols, _ptr(loss_out), _stream()), "gwd_silog_bwd")
+    return out
+
+
+def seg_ce(logits, seg_gt, *, weight=1.0, ignore_index=-100, out_cols=16, want_grad=True, loss_out=None, sums=None):
+    """weight * mean cross entropy of fp32 logits [B,C,H,W] (any strides: NCHW or a permuted channels-last buffer) against
+    int64 seg_gt [B,(1,)H,W]; returns (sums fp64 [2] = (n, sum nll), dlogits bf16 [B*H*W, out_cols] channels-last or None)"""
+    assert logits.dtype == torch.float32 and logits.dim() == 4 and seg_gt.dtype == torch.int64 and seg_gt.is_contiguous()
+    B, C, H, W = logits.shape
+    assert logits.stride(2) == W * logits.stride(3), "rows of the logits map must be contiguous in pixels"
+    sums = torch.empty(2, dtype=torch.float64, device=logits.device) if sums is None else sums
+    d = torch.empty(B * H * W, out_cols, dtype=torch.bfloat16, device=logits.device) if want_grad else None
+    capi.check(_L().gwd_seg_ce(_ptr(logits), logits.stride(3), logits.stride(1), logits.stride(0), _ptr(seg_gt), B, H * W, C,
+                               ignore_index, weight, _ptr(sums), _ptr(d), out_cols, _ptr(loss_out), _stream()), "gwd_seg_ce")
+    return sums, d
 
 
 def transpose(x, colsum=None, C=None, x_coff=0, pad_to=64, out=None):

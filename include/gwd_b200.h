@@ -258,10 +258,13 @@ int gwd_silog_sums(const float* pred, int32_t B, int32_t h, int32_t w, const flo
 int gwd_layernorm_bwd(const void* dy, int64_t dy_rs, const void* z, int64_t z_rs, const float* gamma, const float* beta,
                       int32_t post_act, float eps, const void* add, int64_t add_rs, void* dz, int64_t dz_rs, float* dgamma,
                       float* dbeta, int64_t rows, int32_t C, void* stream);
-/* out[r, c] (bf16, c < out_cols) = c < n ? dy[r,c] * act'(y[r,c]) : 0 with act' evaluated from the OUTPUT y
- * (GWD_ACT_RELU, GWD_ACT_SIGMOID, GWD_ACT_ELU, or GWD_ACT_NONE = dtype conversion + padding).  dy / y are fp32 or bf16. */
+/* out[r, c] (bf16, c < out_cols) = c < n ? dy[r,c] * act'(.) * scale : 0.  from_input == 0: act' is evaluated from the
+ * activation's OUTPUT y * y_mul (GWD_ACT_RELU, GWD_ACT_SIGMOID, GWD_ACT_ELU; y_mul = 1 / max_depth and scale = max_depth
+ * differentiate sigmoid * max_depth); from_input != 0: from its INPUT (also GWD_ACT_GELU, erf form).  GWD_ACT_NONE =
+ * dtype conversion + padding (+ scale).  dy / y are fp32 or bf16. */
 int gwd_act_bwd(const void* dy, int32_t dy_f32, int64_t dy_rs, const void* y, int32_t y_f32, int64_t y_rs, int32_t act,
-                void* out, int64_t out_rs, int64_t rows, int32_t n, int32_t out_cols, void* stream);
+                void* out, int64_t out_rs, int64_t rows, int32_t n, int32_t out_cols, float y_mul, float scale,
+                int32_t from_input, void* stream);
 /* out[c, r] = x[r, c] (bf16; r < rows, c < C), columns rows..rows_pad of out written as zeros; colsum (optional, fp32
  * [C]) is ACCUMULATED with the column sums of x = the bias gradient when x is dY. */
 int gwd_transpose(const void* x, int64_t x_rs, void* out, int64_t out_rs, int64_t rows, int64_t rows_pad, int32_t C,
@@ -317,6 +320,23 @@ int gwd_sumsq(const float* g, int64_t n, double* out_accum, void* stream);
 int gwd_adamw_step(float* p, const float* g, float* m, float* v, void* mirror_bf16, int64_t n, float lr, float beta1,
                    float beta2, float eps, float weight_decay, int32_t step, float max_norm, float grad_scale,
                    const double* sumsq, void* stream);
+
+/* Backward of the scale-invariant log loss of one prediction scale (src/models/glassrgbd.py:360-374 inside the loop of
+ * src/engine_glassrgbd.py:65-82): loss = weight * 10 * sqrt(S2/n - variance_focus (S1/n)^2) with sums3 = (n, S1, S2) from
+ * gwd_silog_sums on the same arguments (read on the DEVICE: no host sync).  sig_scale > 0: pred = sig_scale * sigmoid(z)
+ * and the gradient is taken to z.  out_cols == 0: out is fp32 [B*h*w]; otherwise bf16 rows of out_cols columns (multiple of
+ * 8) with the gradient in column 0 and zeros elsewhere = the dY operand of the last convolution's backward.  loss_out
+ * (optional, fp32 [1]) receives the weighted loss value. */
+int gwd_silog_bwd(const float* pred, int32_t B, int32_t h, int32_t w, const float* gt, int32_t H, int32_t W, float lo, float hi,
+                  int32_t log_only, const double* sums3, float variance_focus, float weight, float sig_scale, void* out,
+                  int32_t out_cols, float* loss_out, void* stream);
+/* SegLoss = nn.CrossEntropyLoss (mean over pixels with gt != ignore_index; src/models/glassrgbd.py:376-383) times `weight`
+ * (engine_glassrgbd.py:88-90), forward + backward: logits fp32 addressed as in gwd_seg_confusion, gt int64 [B*HW];
+ * sums2 fp64 [2] = (valid pixels, sum of -log p[gt]) (zeroed here); dlogits (optional) bf16 rows of out_cols columns =
+ * weight / n * (softmax - onehot), zeros beyond C; loss_out (optional, fp32 [1]) = weight * mean. */
+int gwd_seg_ce(const float* logits, int64_t pixel_stride, int64_t class_stride, int64_t image_stride, const int64_t* gt,
+               int32_t B, int64_t HW, int32_t C, int32_t ignore_index, float weight, double* sums2, void* dlogits,
+               int32_t out_cols, float* loss_out, void* stream);
 
 #ifdef __cplusplus
 }

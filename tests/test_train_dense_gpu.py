@@ -1,0 +1,172 @@
+"""GPU parity of the dense-prediction-head training path (DensePrediction + SilogLoss + SegLoss):
+the loss-gradient kernels against torch.autograd on the same fp32 inputs, then forward values, losses and every
+parameter / input gradient of train_dense.DenseHead against torch.autograd over the CPU oracle's `dense_head`.
+
+Tolerances: the loss kernels are fp32 (1e-5; their bf16 outputs to bf16 rounding); the head runs bf16 activations through
+7 convolutions per branch, so gradients must agree to a few per cent in relative L2 norm."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import oracle, synth_weights
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import ops
+    return ops
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def rel_l2(got, ref):
+    got, ref = got.double().cpu(), ref.double().cpu()
+    return float((got - ref).norm() / ref.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("log_only", [False, True])
+@pytest.mark.parametrize("h,w,H,W", [(24, 32, 24, 32), (12, 16, 48, 64), (15, 20, 60, 80)])
+def test_silog_bwd(h, w, H, W, log_only):
+    """gwd_silog_sums + gwd_silog_bwd == autograd of SilogLoss on the nearest-resized ground truth (engine_glassrgbd.py:74-80)"""
+    ops = _ops()
+    g = _g(h + H)
+    B = 3
+    pred = torch.rand(B, 1, h, w, generator=g) * 8 + 0.5
+    gt = torch.rand(B, 1, H, W, generator=g) * 12          # some pixels outside [0.2, 10): masked out
+    pr = pred.clone().requires_grad_(True)
+    loss = oracle.depth_losses([pr], gt, weights=(0.25,), log_depth_error=log_only)[0]
+    loss.backward()
+    sums = ops.silog_sums(pred.cuda(), gt.cuda(), log_only=log_only)
+    loss_out = torch.zeros(1, device="cuda")
+    d = ops.silog_bwd(pred.cuda(), gt.cuda(), sums, weight=0.25, log_only=log_only, loss_out=loss_out)
+    assert abs(float(loss_out) - float(loss.detach())) < 1e-5 * abs(float(loss.detach()))
+    assert rel_l2(d.view(B, 1, h, w), pr.grad) < 1e-5
+    # through max_depth * sigmoid, as padded bf16 rows
+    z = torch.randn(B, 1, h, w, generator=g).requires_grad_(True)
+    oracle.depth_losses([10.0 * torch.sigmoid(z)], gt, weights=(1.0,), log_depth_error=log_only)[0].backward()
+    p2 = (10.0 * torch.sigmoid(z.detach())).cuda()
+    s2 = ops.silog_sums(p2, gt.cuda(), log_only=log_only)
+    rows = ops.silog_bwd(p2, gt.cuda(), s2, log_only=log_only, sig_scale=10.0, out_cols=16)
+    assert rows.shape == (B * h * w, 16) and float(rows[:, 1:].float().abs().max()) == 0.0
+    assert rel_l2(rows[:, 0].float().view(B, 1, h, w), z.grad) < 4e-3
+
+
+@pytest.mark.parametrize("layout", ["nchw", "nhwc"])
+def test_seg_ce(layout):
+    """gwd_seg_ce == nn.CrossEntropyLoss (mean over non-ignored pixels) * weight, forward and backward"""
+    ops = _ops()
+    g = _g(5)
+    B, C, H, W = 2, 2, 20, 28
+    logits = torch.randn(B, C, H, W, generator=g) * 3
+    gt = (torch.rand(B, 1, H, W, generator=g) > 0.4).long()
+    gt[0, 0, :2] = -100                                   # ignored pixels
+    lr_ = logits.clone().requires_grad_(True)
+    loss = F.cross_entropy(lr_, gt.squeeze(1)) * 2.0
+    loss.backward()
+    lc = logits.cuda() if layout == "nchw" else logits.permute(0, 2, 3, 1).contiguous().cuda().permute(0, 3, 1, 2)
+    loss_out = torch.zeros(1, device="cuda")
+    sums, d = ops.seg_ce(lc, gt.cuda(), weight=2.0, out_cols=16, loss_out=loss_out)
+    assert int(sums[0]) == int((gt >= 0).sum())
+    assert abs(float(loss_out) - float(loss.detach())) < 1e-5 * abs(float(loss.detach()))
+    assert float(d[:, C:].float().abs().max()) == 0.0
+    assert rel_l2(d[:, :C].float().view(B, H, W, C).permute(0, 3, 1, 2), lr_.grad) < 4e-3
+
+
+def test_act_bwd_from_input_and_scales():
+    ops = _ops()
+    g = _g(8)
+    x = torch.randn(500, 144, generator=g).bfloat16()
+    dy = torch.randn(500, 144, generator=g).bfloat16()
+    xr = x.float().requires_grad_(True)
+    F.gelu(xr).backward(dy.float())
+    out = ops.act_bwd(dy.cuda(), x.cuda(), ops.ACT_GELU, from_input=True)
+    assert rel_l2(out, xr.grad) < 4e-3
+    # y = 10 * sigmoid(z): derivative from the output, dy fp32
+    z = torch.randn(700, 1, generator=g)
+    y = 10 * torch.sigmoid(z)
+    d = torch.randn(700, 1, generator=g)
+    out = ops.act_bwd(d.cuda(), y.cuda(), ops.ACT_SIGMOID, out_cols=16, y_mul=0.1, scale=10.0).float().cpu()
+    assert rel_l2(out[:, 0], (d * y * (1 - y / 10))[:, 0]) < 4e-3 and float(out[:, 1:].abs().max()) == 0.0
+    out = ops.act_bwd(dy.cuda(), None, ops.ACT_NONE, scale=4.0).float().cpu()
+    assert torch.equal(out, (dy.float() * 4).bfloat16().float())
+
+
+def _head_inputs(B, H4, W4, seed):
+    g = _g(seed)
+    feat = torch.randn(B, 64, H4, W4, generator=g)
+    dtok = torch.randn(B, 64, H4, W4, generator=g)
+    stok = torch.randn(B, 64, H4, W4, generator=g)
+    depth3 = torch.rand(B, 1, H4, W4, generator=g)
+    H, W = 4 * H4, 4 * W4
+    depth_gt = torch.rand(B, 1, H, W, generator=g) * 10.5 + 0.1
+    seg_gt = (torch.rand(B, 1, H, W, generator=g) > 0.5).long()
+    return feat, dtok, stok, depth3, depth_gt, seg_gt
+
+
+def _stage_buffer(feat, dtok, stok, depth3):
+    B, _, H4, W4 = feat.shape
+    buf = torch.zeros(B, H4, W4, 256)
+    buf[..., :64], buf[..., 64:128], buf[..., 128:192] = feat.permute(0, 2, 3, 1), dtok.permute(0, 2, 3, 1), stok.permute(0, 2, 3, 1)
+    buf[..., 192] = depth3[:, 0]
+    return buf.bfloat16()
+
+
+def _head_weights(scale=1.0):
+    sd = {k: v.clone() for k, v in synth_weights().items() if k.startswith("depth_decoder.")}
+    return sd
+
+
+def test_dense_head_gradients_match_oracle_autograd():
+    _ops()
+    from gwdepth_b200.train_dense import DenseHead
+    B, H4, W4 = 2, 12, 16
+    H, W = 4 * H4, 4 * W4
+    feat, dtok, stok, depth3, depth_gt, seg_gt = _head_inputs(B, H4, W4, 31)
+    buf = _stage_buffer(feat, dtok, stok, depth3)
+    sd = _head_weights()
+    # oracle (fp32 autograd) on the bf16-rounded inputs
+    bufr = buf.float().requires_grad_(True)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    nchw = lambda t: t.permute(0, 3, 1, 2)
+    depth_o, seg_o = oracle.dense_head(nchw(bufr[..., :64]), nchw(bufr[..., 192:193]), nchw(bufr[..., 64:128]),
+                                       nchw(bufr[..., 128:192]), (H, W), oracle.P(sdr, "depth_decoder."), 10.0)
+    l_depth = oracle.depth_losses([depth_o], depth_gt, weights=(1.0,))[0]
+    l_seg = oracle.seg_loss(seg_o, seg_gt)
+    (l_depth + l_seg).backward()
+    # CUDA path
+    head = DenseHead({k: v.cuda() for k, v in sd.items()})
+    back = head.state_dict()
+    for k, v in sd.items():
+        assert torch.equal(back[k].cpu(), v), k               # logical <-> physical layout round trip
+    depth, seg, losses, d_buf = head.loss_and_grads(buf.cuda(), depth_gt.cuda(), seg_gt.cuda())
+    assert rel_l2(depth, depth_o.detach()) < 2e-2 and rel_l2(seg, seg_o.detach()) < 2e-2
+    assert abs(float(losses[0]) - float(l_depth)) < 2e-2 * abs(float(l_depth))
+    assert abs(float(losses[1]) - float(l_seg)) < 2e-2 * abs(float(l_seg))
+    grads = head.grads()
+    worst = {}
+    for k, v in sdr.items():
+        worst[k] = rel_l2(grads[k], v.grad)
+    bad = {k: e for k, e in worst.items() if e > 5e-2}
+    assert not bad, bad
+    ref_dbuf = bufr.grad.view(-1, 256)
+    assert rel_l2(d_buf[:, :193], ref_dbuf[:, :193]) < 5e-2
+    assert float(d_buf[:, 193:].float().abs().max()) == 0.0       # padding columns carry no gradient
+
+
+def test_dense_head_training_lowers_the_loss():
+    _ops()
+    from gwdepth_b200.train_dense import DenseHead
+    B, H4, W4 = 2, 12, 16
+    feat, dtok, stok, depth3, depth_gt, seg_gt = _head_inputs(B, H4, W4, 32)
+    buf = _stage_buffer(feat, dtok, stok, depth3).cuda()
+    head = DenseHead({k: v.cuda() for k, v in _head_weights().items()}, lr=1e-3, max_norm=1.0)
+    hist = []
+    for _ in range(12):
+        hist.append(head.train_step(buf, depth_gt.cuda(), seg_gt.cuda()).sum().item())
+    assert hist[-1] < 0.9 * hist[0], hist
+    # the bf16 mirror follows the fp32 master
+    assert torch.equal(head.Wb, head.P.to(torch.bfloat16))
