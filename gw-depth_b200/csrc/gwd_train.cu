@@ -48,38 +48,50 @@ __device__ __forceinline__ float gwd_act_grad(float v, int act) {
   }
 }
 
-template <int NV>
+// LPR lanes own one row (32: one row per warp, NV chunks of 256 columns; 16 / 8: two / four rows per warp for C <= 128 / 64,
+// so that narrow rows -- the 64-channel maps of the dense head -- still fill every lane)
+template <int NV, int LPR>
 __global__ void __launch_bounds__(kLnWarps * 32)
 gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16* __restrict__ z, int64_t z_rs,
                          const float* __restrict__ gamma, const float* __restrict__ beta, int post_act, float eps,
                          const bf16* __restrict__ add, int64_t add_rs,
                          bf16* __restrict__ dz, int64_t dz_rs, float* __restrict__ dgamma, float* __restrict__ dbeta,
                          int64_t rows, int C) {
+  static_assert(LPR == 32 || NV == 1, "row groups narrower than a warp hold one chunk");
+  constexpr int RPW = 32 / LPR;                   // rows per warp and iteration
   __shared__ float part[kLnWarps][NV * 256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cl = lane % LPR, sub = lane / LPR;
   const int64_t gwarp = static_cast<int64_t>(blockIdx.x) * kLnWarps + warp;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * kLnWarps;
+  auto group_sum = [](float v) {
+#pragma unroll
+    for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+  };
   float ag[NV][8], ab[NV][8], gm[NV][8], bt[NV][8];
   bool on[NV];
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
-    on[v] = (lane + 32 * v) * 8 < C;
+    on[v] = (cl + 32 * v) * 8 < C;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       ag[v][e] = 0.f; ab[v][e] = 0.f;
-      gm[v][e] = on[v] ? gamma[(lane + 32 * v) * 8 + e] : 0.f;
-      bt[v][e] = (on[v] && post_act != GWD_ACT_NONE) ? beta[(lane + 32 * v) * 8 + e] : 0.f;
+      gm[v][e] = on[v] ? gamma[(cl + 32 * v) * 8 + e] : 0.f;
+      bt[v][e] = (on[v] && post_act != GWD_ACT_NONE) ? beta[(cl + 32 * v) * 8 + e] : 0.f;
     }
   }
   const float invC = 1.f / static_cast<float>(C);
-  for (int64_t row = gwarp; row < rows; row += nwarps) {
+  for (int64_t base = gwarp * RPW; base < rows; base += nwarps * RPW) {
+    const int64_t row = base + sub;
+    const bool live = row < rows;
     float zv[NV][8], dv[NV][8];
     float s = 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      if (on[v]) {
-        ld8(z + row * z_rs + (lane + 32 * v) * 8, zv[v]);
-        ld8(dy + row * dy_rs + (lane + 32 * v) * 8, dv[v]);
+      if (on[v] && live) {
+        ld8(z + row * z_rs + (cl + 32 * v) * 8, zv[v]);
+        ld8(dy + row * dy_rs + (cl + 32 * v) * 8, dv[v]);
       } else {
 #pragma unroll
         for (int e = 0; e < 8; ++e) { zv[v][e] = 0.f; dv[v][e] = 0.f; }
@@ -87,22 +99,22 @@ gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16*
 #pragma unroll
       for (int e = 0; e < 8; ++e) s += zv[v][e];
     }
-    const float mean = gwd_warp_sum(s) * invC;
+    const float mean = group_sum(s) * invC;
     float q = 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        zv[v][e] = on[v] ? zv[v][e] - mean : 0.f;
+        zv[v][e] = (on[v] && live) ? zv[v][e] - mean : 0.f;
         q += zv[v][e] * zv[v][e];
       }
-    const float rstd = rsqrtf(gwd_warp_sum(q) * invC + eps);
+    const float rstd = rsqrtf(group_sum(q) * invC + eps);
     float m1 = 0.f, m2 = 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v)
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        zv[v][e] *= rstd;                                  // xh
+        zv[v][e] *= rstd;                                  // xhat
         if (post_act != GWD_ACT_NONE) dv[v][e] *= gwd_act_grad(fmaf(zv[v][e], gm[v][e], bt[v][e]), post_act);   // through act(LN(z))
         ag[v][e] += dv[v][e] * zv[v][e];
         ab[v][e] += dv[v][e];
@@ -110,24 +122,24 @@ gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16*
         m1 += dv[v][e];
         m2 += dv[v][e] * zv[v][e];
       }
-    m1 = gwd_warp_sum(m1) * invC;
-    m2 = gwd_warp_sum(m2) * invC;
+    m1 = group_sum(m1) * invC;
+    m2 = group_sum(m2) * invC;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
-      if (!on[v]) continue;
+      if (!on[v] || !live) continue;
       float o[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) o[e] = rstd * (dv[v][e] - m1 - zv[v][e] * m2);
       if (add != nullptr) {
         float a[8];
-        ld8(add + row * add_rs + (lane + 32 * v) * 8, a);
+        ld8(add + row * add_rs + (cl + 32 * v) * 8, a);
 #pragma unroll
         for (int e = 0; e < 8; ++e) o[e] += a[e];
       }
-      st8(dz + row * dz_rs + (lane + 32 * v) * 8, o);
+      st8(dz + row * dz_rs + (cl + 32 * v) * 8, o);
     }
   }
-  // column sums: warps -> shared memory -> one atomic per column and CTA
+  // column sums: warps (and the row groups of a warp) -> shared memory -> one atomic per column and CTA
 #pragma unroll
   for (int pass = 0; pass < 2; ++pass) {
     float* dst = pass == 0 ? dgamma : dbeta;
@@ -140,7 +152,9 @@ gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16*
     for (int c = threadIdx.x; c < C; c += kLnWarps * 32) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < kLnWarps; ++w) t += part[w][c];
+      for (int w = 0; w < kLnWarps; ++w)
+#pragma unroll
+        for (int r = 0; r < RPW; ++r) t += part[w][r * LPR * 8 + c];
       atomicAdd(dst + c, t);
     }
     __syncthreads();
@@ -769,6 +783,129 @@ __global__ void __launch_bounds__(256) gwd_wgrad_kernel(WgradParams p) {
 
 
 // ------------------------------------------------------------------------------------------------
+// 3x3 weight gradient for NARROW convolutions (N, C <= 64: the dense prediction head at 1/2 and full resolution, where
+// the contraction runs over millions of pixels): dW[tap][n][c] += sum_p dY[p][n] X[p + shift(tap)][c] for all 9 taps in
+// ONE pass over dY and X.  The tap-by-tap kernel above reads both maps 9 times and fills 1/16 of its 128 x 128 tile here.
+// Persistent CTAs of 9 warps walk 4 x 64 pixel tiles: the dY tile and the X tile with its 1-pixel halo (zero-filled
+// outside the image) arrive by cp.async into a double buffer (pixel rows padded by 8 channels: conflict-free ldmatrix);
+// warp t owns tap t and keeps its whole N x C accumulator in registers across all tiles of the CTA (mma.sync m16n8k16,
+// 16 consecutive pixels of a row = one K step, both operands by ldmatrix.trans, the X fragment simply addressed at the
+// shifted pixel), so the only global writes are 9 N C vector atomics per CTA at the end.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWsTH = 4, kWsTW = 64, kWsThreads = 288;
+
+template <int NP, int CP>
+__global__ void __launch_bounds__(kWsThreads)
+gwd_conv3x3_wgrad_small_kernel(const bf16* __restrict__ dy, int64_t dy_cs, const bf16* __restrict__ x, int64_t x_cs, int B, int H,
+                               int W, float* __restrict__ dw, float* __restrict__ db) {
+  constexpr int LDA = NP + 8, LDB = CP + 8;
+  constexpr int kTileA = kWsTH * kWsTW * LDA, kTileB = (kWsTH + 2) * (kWsTW + 2) * LDB;
+  extern __shared__ __align__(16) uint8_t wsm[];
+  bf16* sA = reinterpret_cast<bf16*>(wsm);           // [2][TH*TW][LDA]           dY
+  bf16* sB = sA + 2 * kTileA;                         // [2][(TH+2)*(TW+2)][LDB]   X with halo
+  const int lane = threadIdx.x & 31, tap = threadIdx.x >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  const int sx = tap / 3 - 1, sy = tap % 3 - 1;      // tap = dx * 3 + dy
+  const int tiles_x = (W + kWsTW - 1) / kWsTW, tiles_y = (H + kWsTH - 1) / kWsTH;
+  const int64_t tiles = static_cast<int64_t>(B) * tiles_y * tiles_x;
+
+  auto load_tile = [&](int64_t t, int buf) {
+    const int tx = static_cast<int>(t % tiles_x), ty = static_cast<int>((t / tiles_x) % tiles_y), b = static_cast<int>(t / (tiles_x * tiles_y));
+    const int x0 = tx * kWsTW, y0 = ty * kWsTH;
+    const uint32_t aB = smem_u32(sA + buf * kTileA), bB = smem_u32(sB + buf * kTileB);
+    for (int i = threadIdx.x; i < kWsTH * kWsTW * (NP / 8); i += kWsThreads) {
+      const int c8 = (i % (NP / 8)) * 8, pix = i / (NP / 8);
+      const int px = x0 + pix % kWsTW, py = y0 + pix / kWsTW;
+      const bool v = px < W && py < H;
+      cp_async16(aB + static_cast<uint32_t>((pix * LDA + c8) * 2), v ? dy + ((static_cast<int64_t>(b) * H + py) * W + px) * dy_cs + c8 : dy, v);
+    }
+    for (int i = threadIdx.x; i < (kWsTH + 2) * (kWsTW + 2) * (CP / 8); i += kWsThreads) {
+      const int c8 = (i % (CP / 8)) * 8, pix = i / (CP / 8);
+      const int px = x0 - 1 + pix % (kWsTW + 2), py = y0 - 1 + pix / (kWsTW + 2);
+      const bool v = px >= 0 && px < W && py >= 0 && py < H;
+      cp_async16(bB + static_cast<uint32_t>((pix * LDB + c8) * 2), v ? x + ((static_cast<int64_t>(b) * H + py) * W + px) * x_cs + c8 : x, v);
+    }
+  };
+
+  float acc[NP / 16][CP / 8][4];
+#pragma unroll
+  for (int mt = 0; mt < NP / 16; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < CP / 8; ++nt) { acc[mt][nt][0] = 0.f; acc[mt][nt][1] = 0.f; acc[mt][nt][2] = 0.f; acc[mt][nt][3] = 0.f; }
+  float bsum = 0.f;
+  const int bch = threadIdx.x % NP, bgrp = threadIdx.x / NP;       // bias gradient: channel bch over every (288 / NP)-th pixel
+
+  int64_t t = blockIdx.x;
+  if (t < tiles) load_tile(t, 0);
+  asm volatile("cp.async.commit_group;");
+  int buf = 0;
+  for (; t < tiles; t += gridDim.x, buf ^= 1) {
+    if (t + gridDim.x < tiles) load_tile(t + gridDim.x, buf ^ 1);
+    asm volatile("cp.async.commit_group;");
+    asm volatile("cp.async.wait_group 1;");
+    __syncthreads();
+    const uint32_t aS = smem_u32(sA + buf * kTileA), bS = smem_u32(sB + buf * kTileB);
+#pragma unroll 1
+    for (int ry = 0; ry < kWsTH; ++ry) {
+#pragma unroll
+      for (int kx = 0; kx < kWsTW / 16; ++kx) {
+        // A = dY^T (n x pixels): matrices (k+0,m+0) (k+0,m+8) (k+8,m+0) (k+8,m+8), transposed on load
+        const int pa = ry * kWsTW + kx * 16 + (lane & 7) + 8 * (lane >> 4);
+        // B = X (pixels x c) at the pixel this output pixel saw through the tap (halo origin = (-1, -1))
+        const int pb = (ry + 1 + sy) * (kWsTW + 2) + kx * 16 + 1 + sx + (lane & 7) + 8 * ((lane >> 3) & 1);
+        uint32_t a[NP / 16][4];
+#pragma unroll
+        for (int mt = 0; mt < NP / 16; ++mt) ldsm4t(a[mt], aS + static_cast<uint32_t>((pa * LDA + mt * 16 + 8 * ((lane >> 3) & 1)) * 2));
+#pragma unroll
+        for (int np = 0; np < CP / 16; ++np) {
+          uint32_t bfr[4];
+          ldsm4t(bfr, bS + static_cast<uint32_t>((pb * LDB + np * 16 + 8 * (lane >> 4)) * 2));
+#pragma unroll
+          for (int mt = 0; mt < NP / 16; ++mt) {
+            mma16816(acc[mt][2 * np], a[mt], bfr[0], bfr[1]);
+            mma16816(acc[mt][2 * np + 1], a[mt], bfr[2], bfr[3]);
+          }
+        }
+      }
+    }
+    if (db != nullptr && bgrp < kWsThreads / NP) {
+      const bf16* col = sA + buf * kTileA + bch;
+      for (int pix = bgrp; pix < kWsTH * kWsTW; pix += kWsThreads / NP) bsum += __bfloat162float(col[pix * LDA]);
+    }
+    __syncthreads();       // the next iteration's prefetch overwrites this buffer's twin only; this one is refilled after it
+  }
+  asm volatile("cp.async.wait_group 0;");
+  float* out = dw + static_cast<int64_t>(tap) * NP * CP;
+#pragma unroll
+  for (int mt = 0; mt < NP / 16; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < CP / 8; ++nt)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        atomicAdd(reinterpret_cast<float2*>(out + (mt * 16 + g + 8 * h) * CP + nt * 8 + 2 * tq), make_float2(acc[mt][nt][2 * h], acc[mt][nt][2 * h + 1]));
+  if (db != nullptr && bgrp < kWsThreads / NP && blockIdx.x < tiles) atomicAdd(db + bch, bsum);
+}
+
+template <int NP, int CP>
+static int launch_wgrad_small(const void* dy, int64_t dy_cs, const void* x, int64_t x_cs, int B, int H, int W, float* dw, float* db,
+                              cudaStream_t stream) {
+  constexpr size_t smem = 2 * (static_cast<size_t>(kWsTH) * kWsTW * (NP + 8) + (kWsTH + 2) * (kWsTW + 2) * (CP + 8)) * sizeof(bf16);
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    GWD_CUDA(cudaFuncSetAttribute(gwd_conv3x3_wgrad_small_kernel<NP, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    int n = 0;
+    GWD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, gwd_conv3x3_wgrad_small_kernel<NP, CP>, kWsThreads, smem));
+    ctas_per_sm = std::max(1, n);
+  }
+  const int64_t tiles = static_cast<int64_t>(B) * gwd_ceil_div(H, kWsTH) * gwd_ceil_div(W, kWsTW);
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(tiles, static_cast<int64_t>(ctas_per_sm) * gwd_num_sms()));
+  gwd_conv3x3_wgrad_small_kernel<NP, CP><<<grid, kWsThreads, smem, stream>>>(static_cast<const bf16*>(dy), dy_cs, static_cast<const bf16*>(x),
+                                                                             x_cs, B, H, W, dw, db);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // Set criterion, forward AND backward in one launch (src/models/glassrgbd.py:154-175 weighted cross entropy over
 // {line, no-object}, :231-244 L1 over matched pairs / num_items) for all S decoder stages: one CTA per stage.
 //   loss_ce[s]   = sum_i w[c_i] nll_i / sum_i w[c_i]         c_i = label of the target matched to query i, else C-1
@@ -946,8 +1083,10 @@ extern "C" int gwd_layernorm_bwd(const void* dy, int64_t dy_rs, const void* z, i
                                              static_cast<const bf16*>(add), add_rs, static_cast<bf16*>(dz), dz_rs, dgamma,
                                              dbeta, rows, C);
   };
-  if (C <= 256) launch(gwd_layernorm_bwd_kernel<1>);
-  else launch(gwd_layernorm_bwd_kernel<2>);
+  if (C <= 64) launch(gwd_layernorm_bwd_kernel<1, 8>);
+  else if (C <= 128) launch(gwd_layernorm_bwd_kernel<1, 16>);
+  else if (C <= 256) launch(gwd_layernorm_bwd_kernel<1, 32>);
+  else launch(gwd_layernorm_bwd_kernel<2, 32>);
   GWD_LAUNCHED();
   return GWD_OK;
 }
@@ -1095,6 +1234,14 @@ extern "C" int gwd_conv3x3_wgrad(const void* dy, int64_t dy_cs, const void* x, i
   GWD_STREAM;
   GWD_CHECK_ARG(B > 0 && H > 0 && W > 0, "gwd_conv3x3_wgrad: empty map");
   const int64_t rows = static_cast<int64_t>(B) * H * W;
+  const bool small_ok = dy && x && dw && dy_cs % 8 == 0 && x_cs % 8 == 0 && dy_cs >= N && x_cs >= C &&
+                        ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x)) & 15) == 0 &&
+                        (reinterpret_cast<uintptr_t>(dw) & 7) == 0;
+  if (small_ok) {   // narrow convolutions over many pixels: all 9 taps in one pass
+#define GWD_WS(NP, CP) if (N == NP && C == CP) return launch_wgrad_small<NP, CP>(dy, dy_cs, x, x_cs, B, H, W, dw, db, stream)
+    GWD_WS(16, 16); GWD_WS(16, 32); GWD_WS(16, 64); GWD_WS(32, 16); GWD_WS(32, 32); GWD_WS(32, 64); GWD_WS(64, 16); GWD_WS(64, 32); GWD_WS(64, 64);
+#undef GWD_WS
+  }
   for (int dx = 0; dx < 3; ++dx)
     for (int dyy = 0; dyy < 3; ++dyy) {
       const int tap = dx * 3 + dyy;

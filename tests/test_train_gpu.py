@@ -29,7 +29,8 @@ def rel_l2(got, ref):
 
 
 # ------------------------------------------------------------------------------------------ kernels
-@pytest.mark.parametrize("rows,C,with_add", [(600, 256, False), (4800, 256, True), (77, 512, True), (5, 64, False)])
+@pytest.mark.parametrize("rows,C,with_add", [(600, 256, False), (4800, 256, True), (77, 512, True), (5, 64, False),
+                                             (4099, 64, True), (1001, 128, False), (3333, 32, True), (2050, 96, False)])
 def test_layernorm_bwd(rows, C, with_add):
     ops = _ops()
     g = _g(rows + C)
@@ -163,7 +164,9 @@ def test_linear_wgrad_kernel(R, N, K):
     assert rel_l2(db + 1.0, dY.double().sum(0)) < 2e-5
 
 
-@pytest.mark.parametrize("B,H,W,C,N", [(2, 24, 40, 160, 160), (1, 17, 23, 64, 32), (3, 8, 8, 32, 16), (1, 30, 40, 800, 320)])
+@pytest.mark.parametrize("B,H,W,C,N", [(2, 24, 40, 160, 160), (1, 17, 23, 64, 32), (3, 8, 8, 32, 16), (1, 30, 40, 800, 320),
+                                       (2, 37, 70, 32, 32), (1, 64, 130, 64, 64), (2, 50, 100, 32, 16), (1, 70, 64, 64, 32),
+                                       (3, 5, 200, 16, 64), (1, 120, 160, 64, 64)])
 def test_conv3x3_backward_building_blocks(B, H, W, C, N):
     """weight gradient (gwd_conv3x3_wgrad, tap-shifted split-K mma.sync) and data gradient (gwd_conv_gemm with the
     transposed / flipped filter) of a stride-1 3x3 convolution vs torch.autograd on the same bf16 operands"""
