@@ -95,7 +95,7 @@ SIGNATURES = {
     "gwd_depth_metrics": (c_int, [P, P, I, L, F_, F_, P, P, P]),
     "gwd_seg_confusion": (c_int, [P, L, L, L, P, I, L, I, I, P, P]),
     "gwd_silog_sums": (c_int, [P, I, I, I, P, I, I, F_, F_, I, P, P]),
-    "gwd_layernorm_bwd": (c_int, [P, L, P, L, P, P, I, F_, P, L, P, L, P, P, L, I, P]),
+    "gwd_layernorm_bwd": (c_int, [P, L, P, L, P, P, I, F_, P, L, P, L, P, P, L, I, I, P]),
     "gwd_act_bwd": (c_int, [P, I, L, P, I, L, I, P, L, L, I, I, F_, F_, I, P]),
     "gwd_transpose": (c_int, [P, L, P, L, L, L, I, P, P]),
     "gwd_transpose_batch": (c_int, [P, P, I, I, P]),
@@ -107,6 +107,8 @@ SIGNATURES = {
     "gwd_adamw_step": (c_int, [P, P, P, P, P, L, F_, F_, F_, F_, F_, I, F_, F_, P, P]),
     "gwd_silog_bwd": (c_int, [P, I, I, I, P, I, I, F_, F_, I, P, F_, F_, F_, P, I, P, P]),
     "gwd_seg_ce": (c_int, [P, L, L, L, P, I, L, I, I, F_, P, P, I, P, P]),
+    "gwd_bilinear_up_bwd": (c_int, [P, L, I, I, I, P, L, I, I, I, P]),
+    "gwd_avgpool_bwd": (c_int, [P, L, I, F_, P, L, P, L, I, I, I, I, P]),
 }
 
 _lib = None

@@ -56,7 +56,7 @@ gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16*
                          const float* __restrict__ gamma, const float* __restrict__ beta, int post_act, float eps,
                          const bf16* __restrict__ add, int64_t add_rs,
                          bf16* __restrict__ dz, int64_t dz_rs, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                         int64_t rows, int C) {
+                         int64_t rows, int C, int n) {
   static_assert(LPR == 32 || NV == 1, "row groups narrower than a warp hold one chunk");
   constexpr int RPW = 32 / LPR;                   // rows per warp and iteration
   __shared__ float part[kLnWarps][NV * 256];
@@ -69,6 +69,7 @@ gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16*
     for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
   };
+  // the statistics run over the n LOGICAL channels; channels n..C are padding (zeros in z, zeros out in dz)
   float ag[NV][8], ab[NV][8], gm[NV][8], bt[NV][8];
   bool on[NV];
 #pragma unroll
@@ -76,12 +77,13 @@ gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16*
     on[v] = (cl + 32 * v) * 8 < C;
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
+      const bool in = (cl + 32 * v) * 8 + e < n;
       ag[v][e] = 0.f; ab[v][e] = 0.f;
-      gm[v][e] = on[v] ? gamma[(cl + 32 * v) * 8 + e] : 0.f;
-      bt[v][e] = (on[v] && post_act != GWD_ACT_NONE) ? beta[(cl + 32 * v) * 8 + e] : 0.f;
+      gm[v][e] = in ? gamma[(cl + 32 * v) * 8 + e] : 0.f;
+      bt[v][e] = (in && post_act != GWD_ACT_NONE) ? beta[(cl + 32 * v) * 8 + e] : 0.f;
     }
   }
-  const float invC = 1.f / static_cast<float>(C);
+  const float invC = 1.f / static_cast<float>(n);
   for (int64_t base = gwarp * RPW; base < rows; base += nwarps * RPW) {
     const int64_t row = base + sub;
     const bool live = row < rows;
@@ -105,7 +107,7 @@ gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16*
     for (int v = 0; v < NV; ++v)
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
-        zv[v][e] = (on[v] && live) ? zv[v][e] - mean : 0.f;
+        zv[v][e] = (live && (cl + 32 * v) * 8 + e < n) ? zv[v][e] - mean : 0.f;
         q += zv[v][e] * zv[v][e];
       }
     const float rstd = rsqrtf(group_sum(q) * invC + eps);
@@ -118,7 +120,7 @@ gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16*
         if (post_act != GWD_ACT_NONE) dv[v][e] *= gwd_act_grad(fmaf(zv[v][e], gm[v][e], bt[v][e]), post_act);   // through act(LN(z))
         ag[v][e] += dv[v][e] * zv[v][e];
         ab[v][e] += dv[v][e];
-        dv[v][e] *= gm[v][e];                              // g
+        dv[v][e] *= gm[v][e];                              // g (0 in the padding channels)
         m1 += dv[v][e];
         m2 += dv[v][e] * zv[v][e];
       }
@@ -129,7 +131,7 @@ gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16*
       if (!on[v] || !live) continue;
       float o[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = rstd * (dv[v][e] - m1 - zv[v][e] * m2);
+      for (int e = 0; e < 8; ++e) o[e] = (cl + 32 * v) * 8 + e < n ? rstd * (dv[v][e] - m1 - zv[v][e] * m2) : 0.f;
       if (add != nullptr) {
         float a[8];
         ld8(add + row * add_rs + (cl + 32 * v) * 8, a);
@@ -1070,9 +1072,11 @@ gwd_adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 
 extern "C" int gwd_layernorm_bwd(const void* dy, int64_t dy_rs, const void* z, int64_t z_rs, const float* gamma, const float* beta,
                                  int32_t post_act, float eps, const void* add, int64_t add_rs, void* dz, int64_t dz_rs,
-                                 float* dgamma, float* dbeta, int64_t rows, int32_t C, void* stream_) {
+                                 float* dgamma, float* dbeta, int64_t rows, int32_t C, int32_t n, void* stream_) {
   GWD_STREAM;
   GWD_CHECK_ARG(dy && z && gamma && dz && rows > 0, "gwd_layernorm_bwd: null pointer / empty");
+  if (n <= 0) n = C;
+  GWD_CHECK_ARG(n <= C, "gwd_layernorm_bwd: n > C");
   GWD_CHECK_ARG(post_act == GWD_ACT_NONE || beta != nullptr, "gwd_layernorm_bwd: beta needed to differentiate through act(LN(z))");
   GWD_CHECK_ARG(C % 8 == 0 && C > 0 && C <= 512 && dy_rs % 8 == 0 && z_rs % 8 == 0 && dz_rs % 8 == 0 && add_rs % 8 == 0,
                 "gwd_layernorm_bwd: C and strides must be multiples of 8, C <= 512");
@@ -1081,7 +1085,7 @@ extern "C" int gwd_layernorm_bwd(const void* dy, int64_t dy_rs, const void* z, i
     kern<<<grid, kLnWarps * 32, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, static_cast<const bf16*>(z), z_rs, gamma, beta,
                                              post_act, eps,
                                              static_cast<const bf16*>(add), add_rs, static_cast<bf16*>(dz), dz_rs, dgamma,
-                                             dbeta, rows, C);
+                                             dbeta, rows, C, n);
   };
   if (C <= 64) launch(gwd_layernorm_bwd_kernel<1, 8>);
   else if (C <= 128) launch(gwd_layernorm_bwd_kernel<1, 16>);
@@ -1455,5 +1459,116 @@ extern "C" int gwd_seg_ce(const float* logits, int64_t pixel_stride, int64_t cla
                                                     sums2, weight, static_cast<bf16*>(dlogits), out_cols, loss_out);
     GWD_LAUNCHED();
   }
+  return GWD_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// PyramidLayer branches, backward (src/models/points/points_sample.py:106-125): bilinear (align_corners=True) up-sampling
+// and AvgPool2d(k, k)
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// dx[b, y, x, :] = sum over the high-resolution pixels (Y, X) whose bilinear footprint (computed exactly as the forward,
+// gwd_bilinear_up) touches (y, x).  A gather: block = 64 channel vectors x 4 row slices, the slices reduced in shared memory.
+__global__ void __launch_bounds__(256)
+gwd_bilinear_up_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, int H, int W, bf16* __restrict__ dx, int64_t dx_rs, int h,
+                           int w, int C) {
+  __shared__ float red[4][64][8];
+  const int cv = C / 8;
+  const int t = blockIdx.x * 64 + threadIdx.x;
+  const int y = blockIdx.y, b = blockIdx.z;
+  const bool live = t < w * cv;
+  const int x = live ? t / cv : 0, c = live ? (t - x * cv) * 8 : 0;
+  const float ry = (H > 1) ? static_cast<float>(h - 1) / (H - 1) : 0.f;
+  const float rx = (W > 1) ? static_cast<float>(w - 1) / (W - 1) : 0.f;
+  int Ylo = 0, Yhi = H - 1, Xlo = 0, Xhi = W - 1;
+  if (ry > 0.f) { Ylo = max(0, static_cast<int>(floorf((y - 1) / ry)) - 1); Yhi = min(H - 1, static_cast<int>(ceilf((y + 1) / ry)) + 1); }
+  if (rx > 0.f) { Xlo = max(0, static_cast<int>(floorf((x - 1) / rx)) - 1); Xhi = min(W - 1, static_cast<int>(ceilf((x + 1) / rx)) + 1); }
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (live) {
+    for (int Y = Ylo + threadIdx.y; Y <= Yhi; Y += 4) {
+      const float fy = ry * Y;
+      const int y0 = static_cast<int>(fy), y1 = min(y0 + 1, h - 1);
+      const float ly = fy - y0;
+      const float wy = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
+      if (wy == 0.f) continue;
+      const bf16* row = dy + (static_cast<int64_t>(b) * H + Y) * W * dy_rs + c;
+      for (int X = Xlo; X <= Xhi; ++X) {
+        const float fx = rx * X;
+        const int x0 = static_cast<int>(fx), x1 = min(x0 + 1, w - 1);
+        const float lx = fx - x0;
+        const float wx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
+        if (wx == 0.f) continue;
+        float f[8];
+        ld8(row + static_cast<int64_t>(X) * dy_rs, f);
+        const float wgt = wy * wx;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, f[i], acc[i]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.y][threadIdx.x][i] = acc[i];
+  __syncthreads();
+  if (threadIdx.y == 0 && live) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = red[0][threadIdx.x][i] + red[1][threadIdx.x][i] + red[2][threadIdx.x][i] + red[3][threadIdx.x][i];
+    st8(dx + ((static_cast<int64_t>(b) * h + y) * w + x) * dx_rs + c, acc);
+  }
+}
+
+// out[b, Y, X, :] = add[b, Y, X, :] + (Y / k < H / k and X / k < W / k ? d[b, Y / k, X / k, :] * scale / k^2 : 0)   (floor-mode pool)
+__global__ void __launch_bounds__(256)
+gwd_avgpool_bwd_kernel(const bf16* __restrict__ d, int64_t d_rs, int k, float scale, const bf16* __restrict__ add, int64_t add_rs,
+                       bf16* __restrict__ out, int64_t out_rs, int H, int W, int C) {
+  const int cv = C / 8;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= W * cv) return;
+  const int X = t / cv, c = (t - X * cv) * 8;
+  const int Y = blockIdx.y, b = blockIdx.z;
+  const int oh = H / k, ow = W / k;
+  const int64_t pix = (static_cast<int64_t>(b) * H + Y) * W + X;
+  float f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (Y / k < oh && X / k < ow) {
+    ld8(d + ((static_cast<int64_t>(b) * oh + Y / k) * ow + X / k) * d_rs + c, f);
+    const float m = scale / static_cast<float>(k * k);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] *= m;
+  }
+  if (add != nullptr) {
+    float u[8];
+    ld8(add + pix * add_rs + c, u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) f[i] += u[i];
+  }
+  st8(out + pix * out_rs + c, f);
+}
+
+}  // namespace
+
+extern "C" int gwd_bilinear_up_bwd(const void* dy, int64_t dy_rs, int32_t B, int32_t H, int32_t W, void* dx, int64_t dx_rs,
+                                   int32_t h, int32_t w, int32_t C, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(dy && dx && C > 0 && C % 8 == 0 && dy_rs % 8 == 0 && dx_rs % 8 == 0 && dy_rs >= C && dx_rs >= C,
+                "gwd_bilinear_up_bwd: bad argument");
+  GWD_CHECK_ARG(B > 0 && H > 0 && W > 0 && h > 0 && w > 0 && h <= 65535 && B <= 65535, "gwd_bilinear_up_bwd: bad extents");
+  const dim3 grid(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(w) * (C / 8), 64)), h, B);
+  gwd_bilinear_up_bwd_kernel<<<grid, dim3(64, 4), 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, H, W, static_cast<bf16*>(dx), dx_rs, h,
+                                                              w, C);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_avgpool_bwd(const void* d, int64_t d_rs, int32_t k, float scale, const void* add, int64_t add_rs, void* out,
+                               int64_t out_rs, int32_t B, int32_t H, int32_t W, int32_t C, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(d && out && k > 0 && H >= k && W >= k && C > 0 && C % 8 == 0 && d_rs % 8 == 0 && add_rs % 8 == 0 && out_rs % 8 == 0,
+                "gwd_avgpool_bwd: bad argument");
+  GWD_CHECK_ARG(B > 0 && H <= 65535 && B <= 65535, "gwd_avgpool_bwd: bad extents");
+  const dim3 grid(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(W) * (C / 8), 256)), H, B);
+  gwd_avgpool_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(d), d_rs, k, scale, static_cast<const bf16*>(add), add_rs,
+                                                   static_cast<bf16*>(out), out_rs, H, W, C);
+  GWD_LAUNCHED();
   return GWD_OK;
 }

@@ -520,15 +520,42 @@ def silog_sums(pred, gt, lo=0.2, hi=10.0, log_only=False):
 # ------------------------------------------------------------------------------------------
 # training side of the line branch: backward + optimizer kernels (gwd_train.cu)
 # ------------------------------------------------------------------------------------------
-def layernorm_bwd(dy, z, gamma, dgamma, dbeta, add=None, eps=1e-5, beta=None, post_act=ACT_NONE):
-    """dz (+ add) of y = post_act(LN(z)); dgamma / dbeta (fp32 views, may be None) are accumulated"""
+def _rs(t):
+    """row stride of a [..., C] tensor or of a channel slice of a wider buffer"""
+    return t.stride(-2) if t.dim() >= 2 and t.shape[-2] > 1 else t.shape[-1]
+
+
+def layernorm_bwd(dy, z, gamma, dgamma, dbeta, add=None, eps=1e-5, beta=None, post_act=ACT_NONE, n=0):
+    """dz (+ add) of y = post_act(LN(z)); dgamma / dbeta (fp32 views, may be None) are accumulated.  dy / add may be channel
+    slices of wider buffers; n: logical channels when z carries zero padding up to C"""
     C = z.shape[-1]
     rows = _rows(z)
+    assert z.is_contiguous() and dy.stride(-1) == 1
     dz = torch.empty(rows, C, dtype=torch.bfloat16, device=z.device)
-    capi.check(_L().gwd_layernorm_bwd(_ptr(dy), dy.shape[-1], _ptr(z), C, _ptr(gamma), _ptr(beta), post_act, eps, _ptr(add),
-                                      add.shape[-1] if add is not None else 0, _ptr(dz), C, _ptr(dgamma), _ptr(dbeta), rows, C,
+    capi.check(_L().gwd_layernorm_bwd(_ptr(dy), _rs(dy), _ptr(z), C, _ptr(gamma), _ptr(beta), post_act, eps, _ptr(add),
+                                      _rs(add) if add is not None else 0, _ptr(dz), C, _ptr(dgamma), _ptr(dbeta), rows, C, n,
                                       _stream()), "gwd_layernorm_bwd")
     return dz
+
+
+def bilinear_up_bwd(dy, h, w, C=None):
+    """backward of bilinear_up_into: dy bf16 [B,H,W,C] (may be a channel slice of the concat gradient) -> [B,h,w,C]"""
+    B, H, W, Cs = dy.shape
+    C = C or Cs
+    dx = torch.empty(B, h, w, C, dtype=torch.bfloat16, device=dy.device)
+    capi.check(_L().gwd_bilinear_up_bwd(_ptr(dy), dy.stride(2), B, H, W, _ptr(dx), C, h, w, C, _stream()), "gwd_bilinear_up_bwd")
+    return dx
+
+
+def avgpool_bwd(d, k, H, W, add=None, out=None, scale=1.0):
+    """backward of avgpool(k): d bf16 [B,H//k,W//k,C] -> out [B,H,W,C] = add + d spread over the k x k cells * scale / k^2
+    (out may be `add` itself or a channel slice)"""
+    B, oh, ow, C = d.shape
+    assert (oh, ow) == (H // k, W // k) and d.is_contiguous()
+    out = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=d.device) if out is None else out
+    capi.check(_L().gwd_avgpool_bwd(_ptr(d), C, k, scale, _ptr(add), add.stride(2) if add is not None else 0, _ptr(out),
+                                    out.stride(2), B, H, W, C, _stream()), "gwd_avgpool_bwd")
+    return out
 
 
 def act_bwd(dy, y, act, out_cols=None, y_mul=1.0, scale=1.0, from_input=False):

@@ -253,11 +253,12 @@ int gwd_silog_sums(const float* pred, int32_t B, int32_t h, int32_t w, const flo
 /* y = post_act(LayerNorm_C(z) * gamma + beta):  dz[rows,C] (bf16) = backward of dy through the activation (evaluated from
  * the recomputed LN output; GWD_ACT_NONE: plain LayerNorm, beta may be NULL) and the LayerNorm (+ `add`, an optional bf16
  * gradient that joins at the same tensor, e.g. the residual branch); dgamma / dbeta fp32 [C] are ACCUMULATED (atomicAdd;
- * NULL = skip).  z is the pre-norm value (gwd_conv_gemm's y_raw).  Covers LayerNorm (transformer.py:149-233) and the
+ * NULL = skip).  The statistics run over the n logical channels (n <= C; 0 = C), channels n..C are zero padding.
+ * z is the pre-norm value (gwd_conv_gemm's y_raw).  Covers LayerNorm (transformer.py:149-233) and the
  * conv -> LayerNorm -> GELU blocks of src/models/points/points_sample.py:12-43. */
 int gwd_layernorm_bwd(const void* dy, int64_t dy_rs, const void* z, int64_t z_rs, const float* gamma, const float* beta,
                       int32_t post_act, float eps, const void* add, int64_t add_rs, void* dz, int64_t dz_rs, float* dgamma,
-                      float* dbeta, int64_t rows, int32_t C, void* stream);
+                      float* dbeta, int64_t rows, int32_t C, int32_t n, void* stream);
 /* out[r, c] (bf16, c < out_cols) = c < n ? dy[r,c] * act'(.) * scale : 0.  from_input == 0: act' is evaluated from the
  * activation's OUTPUT y * y_mul (GWD_ACT_RELU, GWD_ACT_SIGMOID, GWD_ACT_ELU; y_mul = 1 / max_depth and scale = max_depth
  * differentiate sigmoid * max_depth); from_input != 0: from its INPUT (also GWD_ACT_GELU, erf form).  GWD_ACT_NONE =
@@ -337,6 +338,15 @@ int gwd_silog_bwd(const float* pred, int32_t B, int32_t h, int32_t w, const floa
 int gwd_seg_ce(const float* logits, int64_t pixel_stride, int64_t class_stride, int64_t image_stride, const int64_t* gt,
                int32_t B, int64_t HW, int32_t C, int32_t ignore_index, float weight, double* sums2, void* dlogits,
                int32_t out_cols, float* loss_out, void* stream);
+/* Backward of gwd_bilinear_up (F.interpolate(mode='bilinear', align_corners=True), the PyramidLayer branches of
+ * src/models/points/points_sample.py:118-121): dy bf16 [B,H,W,dy_rs] (a channel slice of the concat gradient) ->
+ * dx bf16 [B,h,w,dx_rs], C channels; a gather with the forward's own footprint arithmetic. */
+int gwd_bilinear_up_bwd(const void* dy, int64_t dy_rs, int32_t B, int32_t H, int32_t W, void* dx, int64_t dx_rs, int32_t h,
+                        int32_t w, int32_t C, void* stream);
+/* Backward of gwd_avgpool (nn.AvgPool2d(k, k), floor mode) fused with the accumulation into the gradient of the pooled
+ * map: out[b,Y,X,:] = add[b,Y,X,:] (optional; may alias out) + d[b,Y/k,X/k,:] * scale / k^2 inside the pooled region. */
+int gwd_avgpool_bwd(const void* d, int64_t d_rs, int32_t k, float scale, const void* add, int64_t add_rs, void* out,
+                    int64_t out_rs, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 
 #ifdef __cplusplus
 }

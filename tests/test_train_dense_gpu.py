@@ -170,3 +170,94 @@ def test_dense_head_training_lowers_the_loss():
     assert hist[-1] < 0.9 * hist[0], hist
     # the bf16 mirror follows the fp32 master
     assert torch.equal(head.Wb, head.P.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------ PyramidLayer (A19)
+@pytest.mark.parametrize("H,W,h,w,C", [(24, 32, 3, 4, 64), (30, 40, 15, 20, 160), (17, 23, 1, 1, 32), (16, 16, 8, 8, 64), (21, 37, 5, 9, 16)])
+def test_bilinear_up_bwd(H, W, h, w, C):
+    """gwd_bilinear_up_bwd == autograd of F.interpolate(bilinear, align_corners=True), reading a channel slice"""
+    ops = _ops()
+    g = _g(H + w)
+    B = 2
+    wide = torch.randn(B, H, W, C + 16, generator=g).bfloat16()
+    x = torch.zeros(B, C, h, w, requires_grad=True)
+    F.interpolate(x, size=(H, W), mode="bilinear", align_corners=True).backward(wide[..., 8:8 + C].float().permute(0, 3, 1, 2))
+    dx = ops.bilinear_up_bwd(wide.cuda()[..., 8:8 + C], h, w)
+    assert rel_l2(dx, x.grad.permute(0, 2, 3, 1)) < 4e-3
+
+
+@pytest.mark.parametrize("H,W,k", [(24, 32, 2), (30, 40, 4), (120, 160, 16), (17, 23, 8)])
+def test_avgpool_bwd(H, W, k):
+    ops = _ops()
+    g = _g(H + k)
+    B, C = 2, 32
+    d = torch.randn(B, H // k, W // k, C, generator=g).bfloat16()
+    add = torch.randn(B, H, W, C + 8, generator=g).bfloat16()
+    x = torch.zeros(B, C, H, W, requires_grad=True)
+    F.avg_pool2d(x, k, k).backward(d.float().permute(0, 3, 1, 2))
+    out = ops.avgpool_bwd(d.cuda(), k, H, W, add=add.cuda()[..., :C])
+    assert rel_l2(out, x.grad.permute(0, 2, 3, 1) + add[..., :C].float()) < 4e-3
+
+
+def test_layernorm_bwd_with_channel_padding():
+    """LayerNorm over n = 30 logical channels of a 32-wide buffer (K = 30 mixture components), GELU behind it"""
+    ops = _ops()
+    g = _g(77)
+    rows, n, C = 999, 30, 32
+    z = torch.zeros(rows, C)
+    z[:, :n] = torch.randn(rows, n, generator=g) * 2 + 0.3
+    z = z.bfloat16()
+    dy = torch.randn(rows, C, generator=g).bfloat16()
+    gamma, beta = torch.rand(n, generator=g) + 0.5, torch.randn(n, generator=g) * 0.3
+    zr, gr, br = z[:, :n].float().requires_grad_(True), gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    F.gelu(F.layer_norm(zr, (n,), gr, br, 1e-5)).backward(dy[:, :n].float())
+    gp, bp = torch.zeros(C), torch.zeros(C)
+    gp[:n], bp[:n] = gamma, beta
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    dz = ops.layernorm_bwd(dy.cuda(), z.cuda(), gp.cuda(), dg, db, beta=bp.cuda(), post_act=ops.ACT_GELU, n=n)
+    assert rel_l2(dz[:, :n], zr.grad) < 6e-3 and float(dz[:, n:].float().abs().max()) == 0.0
+    assert rel_l2(dg[:n], gr.grad) < 2e-3 and rel_l2(db[:n], br.grad) < 2e-3
+    assert float(dg[n:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("stage,K,B,H,W", [(1, 30, 2, 24, 32), (2, 80, 1, 18, 24)])
+def test_pyramid_gradients_match_oracle_autograd(stage, K, B, H, W):
+    """train_pyramid.Pyramid (forward + backward) against torch.autograd over the oracle's `pyramid` on the same bf16
+    input and cotangent: logits, d(input) and the gradient of every parameter (K = 30: channel counts padded to 16;
+    K = 80: LayerNorm over 320 channels as a separate pass, 800 -> 320 convolution)"""
+    _ops()
+    from gwdepth_b200.train_pyramid import Pyramid
+    prefix = "dense_encoder.point_based_pred%d.pyramid." % stage
+    sd = {k: v.clone() for k, v in synth_weights().items() if k.startswith(prefix)}
+    g = _g(K)
+    Kp = (K + 15) // 16 * 16
+    rg = torch.zeros(B, H, W, Kp)
+    rg[..., :K] = torch.randn(B, H, W, K, generator=g)
+    rg = rg.bfloat16()
+    dl = torch.zeros(B, H, W, Kp)
+    dl[..., :K] = torch.randn(B, H, W, K, generator=g)
+    dl = dl.bfloat16()
+    xr = rg[..., :K].float().permute(0, 3, 1, 2).requires_grad_(True)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = oracle.pyramid(xr, oracle.P(sdr, prefix))
+    ref.backward(dl[..., :K].float().permute(0, 3, 1, 2))
+    py = Pyramid({k: v.cuda() for k, v in sd.items()}, prefix, K)
+    back = py.state_dict()
+    for k, v in sd.items():
+        if ".layer4." not in k:
+            assert torch.equal(back[k].cpu(), v), k
+    logits = py.forward(rg.cuda())
+    assert rel_l2(logits[..., :K], ref.detach().permute(0, 2, 3, 1)) < 3e-2
+    assert float(logits[..., K:].float().abs().max()) == 0.0 if Kp > K else True
+    d_rg = py.backward(dl.cuda())
+    assert rel_l2(d_rg[..., :K], xr.grad.permute(0, 2, 3, 1)) < 6e-2
+    grads = py.grads()
+    bad = {}
+    for k, v in sdr.items():
+        if ".layer4." in k:
+            assert v.grad is None            # constructed by the reference, never run
+            continue
+        e = rel_l2(grads[k], v.grad)
+        if e > 6e-2:
+            bad[k] = e
+    assert not bad, bad
