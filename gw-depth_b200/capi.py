@@ -109,6 +109,9 @@ SIGNATURES = {
     "gwd_seg_ce": (c_int, [P, L, L, L, P, I, L, I, I, F_, P, P, I, P, P]),
     "gwd_bilinear_up_bwd": (c_int, [P, L, I, I, I, P, L, I, I, I, P]),
     "gwd_avgpool_bwd": (c_int, [P, L, I, F_, P, L, P, L, I, I, I, I, P]),
+    "gwd_anchor_mix_bwd": (c_int, [P, L, P, P, I, L, I, I, P, L, P, P]),
+    "gwd_sample_bilinear_bwd": (c_int, [P, P, I, P, L, I, I, I, I, P]),
+    "gwd_sample_scalar_bwd": (c_int, [P, P, I, P, P, I, I, I, P]),
 }
 
 _lib = None

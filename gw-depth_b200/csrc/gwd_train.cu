@@ -1572,3 +1572,170 @@ extern "C" int gwd_avgpool_bwd(const void* d, int64_t d_rs, int32_t k, float sca
   GWD_LAUNCHED();
   return GWD_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// PointBasedPred, backward (src/models/points/points_sample.py:257-280): soft-max mixture of anchor depths and the
+// bilinear point samples (F.grid_sample, align_corners=False, zero padding) of the reference features / previous depth
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kMaxPoints = 128;
+
+__device__ __forceinline__ float pt_unnorm(float g, int size) { return ((g + 1.f) * size - 1.f) * 0.5f; }
+
+// pred[p] = sum_k a_k A[b,k] with a = softmax_k(logits[p, :K]):
+//   dlogits[p,k] = a_k (A[b,k] - pred[p]) dpred[p]   (bf16 rows of Kp columns, exact zeros beyond K)
+//   danchor[b,k] += sum_p a_k dpred[p]               (warp shuffle -> shared memory -> one atomic per (CTA, k))
+// grid = (pixel blocks, B): a CTA never straddles two images.
+__global__ void __launch_bounds__(256)
+gwd_anchor_mix_bwd_kernel(const bf16* __restrict__ logits, int64_t l_rs, const float* __restrict__ anchor,
+                          const float* __restrict__ dpred, int64_t HW, int K, int Kp, bf16* __restrict__ dlogits, int64_t dl_rs,
+                          float* __restrict__ danchor) {
+  __shared__ float s_an[kMaxPoints], s_da[kMaxPoints];
+  const int b = blockIdx.y;
+  for (int k = threadIdx.x; k < kMaxPoints; k += blockDim.x) {
+    s_an[k] = k < K ? anchor[static_cast<int64_t>(b) * K + k] : 0.f;
+    s_da[k] = 0.f;
+  }
+  __syncthreads();
+  const int64_t p = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  const bool live = p < HW;
+  const int64_t pix = static_cast<int64_t>(b) * HW + (live ? p : 0);
+  const bf16* row = logits + pix * l_rs;
+  const float dp = live ? dpred[pix] : 0.f;
+  float mx = -INFINITY;
+  for (int k = 0; k < K; k += 8) {
+    float f[8];
+    ld8(row + k, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) if (k + i < K) mx = fmaxf(mx, f[i]);
+  }
+  float sum = 0.f, acc = 0.f;
+  for (int k = 0; k < K; k += 8) {
+    float f[8];
+    ld8(row + k, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      if (k + i < K) {
+        const float e = __expf(f[i] - mx);
+        sum += e;
+        acc = fmaf(e, s_an[k + i], acc);
+      }
+  }
+  const float inv = 1.f / sum, pred = acc * inv;
+  const int lane = threadIdx.x & 31;
+  for (int k = 0; k < Kp; k += 8) {
+    float f[8], o[8];
+    ld8(row + k, f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const bool in = k + i < K;
+      const float a = in ? __expf(f[i] - mx) * inv : 0.f;
+      o[i] = a * (s_an[k + i] - pred) * dp;
+      const float v = gwd_warp_sum(a * dp);
+      if (in && lane == 0) atomicAdd(&s_da[k + i], v);
+    }
+    if (live) st8(dlogits + pix * dl_rs + k, o);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < K; k += blockDim.x) atomicAdd(danchor + static_cast<int64_t>(b) * K + k, s_da[k]);
+}
+
+// Backward of the K-point bilinear sample of a C-channel map as a GATHER over the map's pixels (deterministic, no atomics,
+// writes the exact zeros of untouched pixels): dx[b,Y,X,c] = sum_k w_k(Y,X) d[b,k,c], w_k = the forward's corner weight of
+// point k at pixel (Y,X).  Point footprints (x0, y0, lx, ly) of the image sit in shared memory.
+__global__ void __launch_bounds__(256)
+gwd_sample_bilinear_bwd_kernel(const float* __restrict__ d, const float* __restrict__ coords, int K, bf16* __restrict__ dx,
+                               int64_t dx_rs, int H, int W, int C) {
+  __shared__ int s_x0[kMaxPoints], s_y0[kMaxPoints];
+  __shared__ float s_lx[kMaxPoints], s_ly[kMaxPoints];
+  const int Y = blockIdx.y, b = blockIdx.z;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float fx = pt_unnorm(coords[(static_cast<int64_t>(b) * K + k) * 2], W);
+    const float fy = pt_unnorm(coords[(static_cast<int64_t>(b) * K + k) * 2 + 1], H);
+    const int x0 = static_cast<int>(floorf(fx)), y0 = static_cast<int>(floorf(fy));
+    s_x0[k] = x0; s_y0[k] = y0; s_lx[k] = fx - x0; s_ly[k] = fy - y0;
+  }
+  __syncthreads();
+  const int cv = C / 8;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= W * cv) return;
+  const int X = t / cv, c = (t - X * cv) * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 0; k < K; ++k) {
+    const int ddx = X - s_x0[k], ddy = Y - s_y0[k];
+    if ((ddx | ddy) & ~1) continue;                       // both offsets must be 0 or 1
+    const float wgt = (ddx ? s_lx[k] : 1.f - s_lx[k]) * (ddy ? s_ly[k] : 1.f - s_ly[k]);
+    const float4* src = reinterpret_cast<const float4*>(d + (static_cast<int64_t>(b) * K + k) * C + c);
+    const float4 u = src[0], v = src[1];
+    acc[0] = fmaf(wgt, u.x, acc[0]); acc[1] = fmaf(wgt, u.y, acc[1]); acc[2] = fmaf(wgt, u.z, acc[2]); acc[3] = fmaf(wgt, u.w, acc[3]);
+    acc[4] = fmaf(wgt, v.x, acc[4]); acc[5] = fmaf(wgt, v.y, acc[5]); acc[6] = fmaf(wgt, v.z, acc[6]); acc[7] = fmaf(wgt, v.w, acc[7]);
+  }
+  st8(dx + ((static_cast<int64_t>(b) * H + Y) * W + X) * dx_rs + c, acc);
+}
+
+// the same for the single-channel fp32 map of anchor depths: out[b,Y,X] = add[b,Y,X] + sum_k w_k(Y,X) d[b,k]
+__global__ void __launch_bounds__(256)
+gwd_sample_scalar_bwd_kernel(const float* __restrict__ d, const float* __restrict__ coords, int K, const float* __restrict__ add,
+                             float* __restrict__ out, int H, int W) {
+  __shared__ int s_x0[kMaxPoints], s_y0[kMaxPoints];
+  __shared__ float s_lx[kMaxPoints], s_ly[kMaxPoints], s_d[kMaxPoints];
+  const int Y = blockIdx.y, b = blockIdx.z;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    const float fx = pt_unnorm(coords[(static_cast<int64_t>(b) * K + k) * 2], W);
+    const float fy = pt_unnorm(coords[(static_cast<int64_t>(b) * K + k) * 2 + 1], H);
+    const int x0 = static_cast<int>(floorf(fx)), y0 = static_cast<int>(floorf(fy));
+    s_x0[k] = x0; s_y0[k] = y0; s_lx[k] = fx - x0; s_ly[k] = fy - y0;
+    s_d[k] = d[static_cast<int64_t>(b) * K + k];
+  }
+  __syncthreads();
+  const int X = blockIdx.x * blockDim.x + threadIdx.x;
+  if (X >= W) return;
+  const int64_t pix = (static_cast<int64_t>(b) * H + Y) * W + X;
+  float acc = add != nullptr ? add[pix] : 0.f;
+  for (int k = 0; k < K; ++k) {
+    const int ddx = X - s_x0[k], ddy = Y - s_y0[k];
+    if ((ddx | ddy) & ~1) continue;
+    acc = fmaf((ddx ? s_lx[k] : 1.f - s_lx[k]) * (ddy ? s_ly[k] : 1.f - s_ly[k]), s_d[k], acc);
+  }
+  out[pix] = acc;
+}
+
+}  // namespace
+
+extern "C" int gwd_anchor_mix_bwd(const void* logits, int64_t l_rs, const float* anchor, const float* dpred, int32_t B, int64_t HW,
+                                  int32_t K, int32_t Kp, void* dlogits, int64_t dl_rs, float* danchor, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(logits && anchor && dpred && dlogits && danchor, "gwd_anchor_mix_bwd: null pointer");
+  GWD_CHECK_ARG(K > 0 && K <= Kp && Kp <= kMaxPoints && Kp % 8 == 0 && l_rs % 8 == 0 && dl_rs % 8 == 0 && l_rs >= Kp && dl_rs >= Kp,
+                "gwd_anchor_mix_bwd: bad K / Kp / row strides (K=%d Kp=%d)", K, Kp);
+  GWD_CHECK_ARG(B > 0 && B <= 65535 && HW > 0, "gwd_anchor_mix_bwd: bad extents");
+  const dim3 grid(static_cast<unsigned>(gwd_ceil_div(HW, 256)), B);
+  gwd_anchor_mix_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(logits), l_rs, anchor, dpred, HW, K, Kp,
+                                                      static_cast<bf16*>(dlogits), dl_rs, danchor);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_sample_bilinear_bwd(const float* d, const float* coords, int32_t K, void* dx, int64_t dx_rs, int32_t B,
+                                       int32_t H, int32_t W, int32_t C, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(d && coords && dx && K > 0 && K <= kMaxPoints && C > 0 && C % 8 == 0 && dx_rs % 8 == 0 && dx_rs >= C,
+                "gwd_sample_bilinear_bwd: bad argument");
+  GWD_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && H <= 65535 && W > 0, "gwd_sample_bilinear_bwd: bad extents");
+  const dim3 grid(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(W) * (C / 8), 256)), H, B);
+  gwd_sample_bilinear_bwd_kernel<<<grid, 256, 0, stream>>>(d, coords, K, static_cast<bf16*>(dx), dx_rs, H, W, C);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_sample_scalar_bwd(const float* d, const float* coords, int32_t K, const float* add, float* out, int32_t B,
+                                     int32_t H, int32_t W, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(d && coords && out && K > 0 && K <= kMaxPoints, "gwd_sample_scalar_bwd: bad argument");
+  GWD_CHECK_ARG(B > 0 && B <= 65535 && H > 0 && H <= 65535 && W > 0, "gwd_sample_scalar_bwd: bad extents");
+  const dim3 grid(static_cast<unsigned>(gwd_ceil_div(W, 256)), H, B);
+  gwd_sample_scalar_bwd_kernel<<<grid, 256, 0, stream>>>(d, coords, K, add, out, H, W);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}

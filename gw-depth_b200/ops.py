@@ -625,6 +625,36 @@ def transpose_batch_tables(pairs):
     return (torch.tensor(tab, dtype=torch.int64, device=dev), torch.tensor(prefix, dtype=torch.int32, device=dev), len(pairs), prefix[-1])
 
 
+def anchor_mix_bwd(logits, anchor, dpred, B, HW, K):
+    """backward of anchor_mix: -> (dlogits bf16 [B*HW, Kp] with zero padding columns, danchor fp32 [B, K])"""
+    Kp = logits.shape[-1]
+    dlogits = torch.empty(B * HW, Kp, dtype=torch.bfloat16, device=logits.device)
+    danchor = torch.zeros(B, K, dtype=torch.float32, device=logits.device)
+    assert dpred.dtype == torch.float32 and dpred.is_contiguous() and dpred.numel() == B * HW
+    capi.check(_L().gwd_anchor_mix_bwd(_ptr(logits), Kp, _ptr(anchor), _ptr(dpred), B, HW, K, Kp, _ptr(dlogits), Kp, _ptr(danchor),
+                                       _stream()), "gwd_anchor_mix_bwd")
+    return dlogits, danchor
+
+
+def sample_bilinear_bwd(d, coords, out, y_coff, H, W):
+    """backward of sample_bilinear w.r.t. the map: d fp32 [B,K,C] -> out[..., y_coff:y_coff+C] (bf16 [B*H*W, Cout] buffer)"""
+    B, K, C = d.shape
+    assert d.dtype == torch.float32 and d.is_contiguous() and out.dtype == torch.bfloat16 and out.is_contiguous()
+    capi.check(_L().gwd_sample_bilinear_bwd(_ptr(d), _ptr(coords), K, _off(out, y_coff), out.shape[-1], B, H, W, C, _stream()),
+               "gwd_sample_bilinear_bwd")
+    return out
+
+
+def sample_scalar_bwd(d, coords, H, W, add=None):
+    """backward of sample_scalar: d fp32 [B,K] -> fp32 [B,H,W] (+ add)"""
+    B, K = d.shape
+    out = torch.empty(B, H, W, dtype=torch.float32, device=d.device)
+    assert add is None or (add.dtype == torch.float32 and add.is_contiguous() and add.numel() == out.numel())
+    capi.check(_L().gwd_sample_scalar_bwd(_ptr(d), _ptr(coords), K, _ptr(add), _ptr(out), B, H, W, _stream()),
+               "gwd_sample_scalar_bwd")
+    return out
+
+
 def transpose_batch(tables):
     table, prefix, n, total = tables
     capi.check(_L().gwd_transpose_batch(_ptr(table), _ptr(prefix), n, total, _stream()), "gwd_transpose_batch")

@@ -158,11 +158,17 @@ class FlatModule:
         return conv_gemm(dY, lin.pwT, bias=False, res=res, res_mode=RES_AFTER if res is not None else RES_NONE)
 
     # ------------------------------------------------------------------ optimizer
-    def step(self, sumsq=None):
-        """gradient all-reduce + clip + AdamW + mirror refresh.  `sumsq` (fp64 [1] on the device): the squared gradient norm
-        of ALL modules of the model when the clip is global (the reference clips the whole model, engine_glassrgbd.py:155-159);
-        None = this module's own norm."""
-        world = parallel.allreduce_sum_(self.G)
+    def allreduce_grads(self):
+        """the data-parallel exchange of this module: ONE sum all-reduce of the flat gradient buffer"""
+        self._world = parallel.allreduce_sum_(self.G)
+        return self._world
+
+    def step(self, sumsq=None, reduced=False):
+        """gradient all-reduce + clip + AdamW + mirror refresh.  `sumsq` (fp64 [1] on the device): the squared norm of the
+        (all-reduced) gradients of ALL modules of the model when the clip is global (the reference clips the whole model,
+        engine_glassrgbd.py:155-159); None = this module's own norm.  `reduced`: allreduce_grads() was already called (a
+        shared norm has to be taken after the exchange)."""
+        world = self._world if reduced else self.allreduce_grads()
         self.t += 1
         if sumsq is None:
             self.sumsq.zero_()

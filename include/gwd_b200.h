@@ -348,6 +348,21 @@ int gwd_bilinear_up_bwd(const void* dy, int64_t dy_rs, int32_t B, int32_t H, int
 int gwd_avgpool_bwd(const void* d, int64_t d_rs, int32_t k, float scale, const void* add, int64_t add_rs, void* out,
                     int64_t out_rs, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 
+/* Backward of gwd_anchor_mix (PointBasedPred, src/models/points/points_sample.py:277-279): with a = softmax_k(logits[p,:K]) and
+ * pred[p] = sum_k a_k anchor[b,k]:  dlogits[p,k] = a_k (anchor[b,k] - pred[p]) dpred[p] as bf16 rows of Kp columns (exact
+ * zeros beyond K); danchor fp32 [B,K] += sum_p a_k dpred[p] (caller zeroes it).  K <= Kp <= 128. */
+int gwd_anchor_mix_bwd(const void* logits, int64_t l_rs, const float* anchor, const float* dpred, int32_t B, int64_t HW, int32_t K,
+                       int32_t Kp, void* dlogits, int64_t dl_rs, float* danchor, void* stream);
+/* Backward of gwd_sample_bilinear w.r.t. the sampled bf16 map (F.grid_sample, align_corners=False, zero padding;
+ * points_sample.py:264-267): d fp32 [B,K,C] -> dx bf16 [B,H,W,dx_rs] (C channels; every pixel written, zeros where no point
+ * footprint lands).  A deterministic gather over the pixels, K <= 128. */
+int gwd_sample_bilinear_bwd(const float* d, const float* coords, int32_t K, void* dx, int64_t dx_rs, int32_t B, int32_t H,
+                            int32_t W, int32_t C, void* stream);
+/* Backward of gwd_sample_scalar (anchor depths, points_sample.py:268): out fp32 [B,H,W] = add (optional, may alias out) +
+ * the bilinear spread of d fp32 [B,K]. */
+int gwd_sample_scalar_bwd(const float* d, const float* coords, int32_t K, const float* add, float* out, int32_t B, int32_t H,
+                          int32_t W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

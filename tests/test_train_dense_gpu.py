@@ -261,3 +261,136 @@ def test_pyramid_gradients_match_oracle_autograd(stage, K, B, H, W):
         if e > 6e-2:
             bad[k] = e
     assert not bad, bad
+
+
+# ------------------------------------------------------------------------------------------ PointBasedPred (A18)
+@pytest.mark.parametrize("K,B,HW", [(30, 2, 24 * 32), (80, 3, 999), (20, 1, 70)])
+def test_anchor_mix_bwd(K, B, HW):
+    """gwd_anchor_mix_bwd == autograd of sum_k softmax_k(logits) * anchor (points_sample.py:277-279)"""
+    ops = _ops()
+    g = _g(K)
+    Kp = (K + 15) // 16 * 16
+    logits = torch.zeros(B * HW, Kp)
+    logits[:, :K] = torch.randn(B * HW, K, generator=g) * 2
+    logits = logits.bfloat16()
+    anchor = torch.rand(B, K, generator=g)
+    dpred = torch.randn(B, HW, generator=g)
+    lr_ = logits[:, :K].float().view(B, HW, K).requires_grad_(True)
+    ar = anchor.clone().requires_grad_(True)
+    pred = (torch.softmax(lr_, dim=-1) * ar[:, None, :]).sum(-1)
+    pred.backward(dpred)
+    fwd = ops.anchor_mix(logits.cuda(), anchor.cuda(), B, HW, K)
+    assert rel_l2(fwd, pred.detach()) < 1e-5
+    dl, da = ops.anchor_mix_bwd(logits.cuda(), anchor.cuda(), dpred.cuda(), B, HW, K)
+    assert rel_l2(dl[:, :K].view(B, HW, K), lr_.grad) < 4e-3
+    assert Kp == K or float(dl[:, K:].float().abs().max()) == 0.0
+    assert rel_l2(da, ar.grad) < 1e-4
+
+
+def _sample_coords(B, K, g):
+    coords = torch.rand(B, K, 2, generator=g) * 2 - 1
+    coords[:, 0] = torch.tensor([-0.9999, 0.9999])        # footprints that hang over the border (zero padding)
+    coords[:, 1] = torch.tensor([1.0, -1.0])
+    coords[:, 2] = coords[:, 3]                            # two points on the same pixel
+    return coords
+
+
+@pytest.mark.parametrize("B,H,W,C,K", [(2, 24, 32, 64, 30), (1, 15, 20, 128, 80), (3, 9, 7, 16, 5)])
+def test_sample_bilinear_and_scalar_bwd(B, H, W, C, K):
+    """gwd_sample_bilinear_bwd / gwd_sample_scalar_bwd == autograd of F.grid_sample(bilinear, align_corners=False, zeros)"""
+    ops = _ops()
+    g = _g(H * W + K)
+    coords = _sample_coords(B, K, g)
+    d = torch.randn(B, K, C, generator=g)
+    x = torch.zeros(B, C, H, W, requires_grad=True)
+    F.grid_sample(x, coords.view(B, K, 1, 2), align_corners=False).backward(d.permute(0, 2, 1)[..., None])
+    out = torch.full((B * H * W, C + 32), 7.0, dtype=torch.bfloat16, device="cuda")
+    ops.sample_bilinear_bwd(d.cuda(), coords.cuda(), out, 16, H, W)
+    assert rel_l2(out[:, 16:16 + C].view(B, H, W, C), x.grad.permute(0, 2, 3, 1)) < 4e-3
+    assert float((out[:, :16].float() - 7).abs().max()) == 0.0 and float((out[:, 16 + C:].float() - 7).abs().max()) == 0.0
+    ds = torch.randn(B, K, generator=g)
+    add = torch.randn(B, H, W, generator=g)
+    xs = torch.zeros(B, 1, H, W, requires_grad=True)
+    F.grid_sample(xs, coords.view(B, K, 1, 2), align_corners=False).backward(ds.view(B, 1, K, 1))
+    got = ops.sample_scalar_bwd(ds.cuda(), coords.cuda(), H, W, add=add.cuda())
+    assert rel_l2(got, xs.grad[:, 0] + add) < 1e-5
+    assert rel_l2(ops.sample_scalar_bwd(ds.cuda(), coords.cuda(), H, W), xs.grad[:, 0]) < 1e-5
+
+
+@pytest.mark.parametrize("stage,dim,K,B,H,W", [(1, 128, 30, 2, 24, 32), (2, 64, 80, 1, 18, 24)])
+def test_point_pred_gradients_match_oracle_autograd(stage, dim, K, B, H, W):
+    """train_points.PointPred (forward + backward) against torch.autograd over the oracle's `point_based_pred` on the same
+    bf16 stage buffer, previous depth, sample points and cotangent: the depth map, d(stage buffer), d(previous depth) and the
+    gradient of every parameter (pre_proj, refer_proj, the whole pyramid)"""
+    _ops()
+    from gwdepth_b200.engine import sine_table
+    from gwdepth_b200.train_points import PointPred
+    prefix = "dense_encoder.point_based_pred%d." % stage
+    sd = {k: v.clone() for k, v in synth_weights().items() if k.startswith(prefix)}
+    g = _g(100 + K)
+    td, width = 64, dim + 3 * 64
+    buf = torch.zeros(B * H * W, width)
+    buf[:, :dim + 2 * td] = torch.randn(B * H * W, dim + 2 * td, generator=g)
+    buf = buf.bfloat16()
+    h, w = H // 2, W // 2
+    pre_depth = torch.rand(B, h, w, generator=g) * 0.9 + 0.05
+    coords = _sample_coords(B, K, g)
+    d_pred = torch.randn(B, H, W, generator=g)
+    d_pre_own = torch.randn(B, h, w, generator=g) * 0.1
+    # oracle under autograd
+    bufr = buf.float().view(B, H * W, width).requires_grad_(True)
+    prer = pre_depth.clone().requires_grad_(True)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    pos = oracle.sine_position(torch.zeros(B, H, W, dtype=torch.bool), dim // 2, False)
+    ref = oracle.point_based_pred(bufr[..., :dim], bufr[..., dim:dim + td], prer[:, None], coords.view(B, K, 1, 2), H, W, pos,
+                                  oracle.P(sdr, prefix), dim)
+    ref.backward(d_pred[:, None])
+    # CUDA path
+    pp = PointPred({k: v.cuda() for k, v in sd.items()}, prefix, dim, td, K, in_width=width)
+    back = pp.state_dict()
+    for k, v in sd.items():
+        if ".layer4." not in k:
+            assert torch.equal(back[k].cpu(), v), k
+    pred = pp.forward(buf.cuda(), pre_depth.cuda(), coords.cuda(), sine_table(H, W, dim // 2, False, "cuda"), B, H, W)
+    assert rel_l2(pred, ref.detach()[:, 0]) < 2e-2
+    d_buf, d_pre = pp.backward(d_pred.cuda(), d_pre_depth=d_pre_own.cuda())
+    ref_dbuf = bufr.grad.view(-1, width)
+    assert rel_l2(d_buf[:, :dim + td], ref_dbuf[:, :dim + td]) < 6e-2
+    assert float(d_buf[:, dim + td:].float().abs().max()) == 0.0       # seg token / padding columns: no gradient
+    assert rel_l2(d_pre, prer.grad + d_pre_own) < 3e-2
+    grads = pp.grads()
+    bad = {}
+    for k, v in sdr.items():
+        if ".layer4." in k:
+            continue
+        e = rel_l2(grads[k], v.grad)
+        if e > 6e-2:
+            bad[k] = e
+    assert not bad, bad
+
+
+def test_point_pred_training_lowers_a_depth_loss():
+    """a few steps of forward -> silog gradient -> backward -> shared-norm clip + AdamW on both flat buffers"""
+    ops = _ops()
+    from gwdepth_b200.engine import sine_table
+    from gwdepth_b200.train_points import PointPred
+    prefix, dim, K, B, H, W, td = "dense_encoder.point_based_pred1.", 128, 30, 2, 24, 32, 64
+    sd = {k: v.cuda() for k, v in synth_weights().items() if k.startswith(prefix)}
+    g = _g(9)
+    buf = torch.randn(B * H * W, dim + td, generator=g).bfloat16().cuda()
+    pre_depth = (torch.rand(B, H // 2, W // 2, generator=g) * 0.9 + 0.05).cuda()
+    coords = (torch.rand(B, K, 2, generator=g) * 2 - 1).cuda()
+    gt = (torch.rand(B, 1, H, W, generator=g) * 8 + 0.5).cuda()
+    pos = sine_table(H, W, dim // 2, False, "cuda")
+    pp = PointPred(sd, prefix, dim, td, K, lr=1e-3, max_norm=1.0)
+    hist = []
+    loss = torch.zeros(1, device="cuda")
+    for _ in range(10):
+        pred = pp.forward(buf, pre_depth, coords, pos, B, H, W) * 10.0                 # metres (max_depth 10)
+        sums = ops.silog_sums(pred.view(B, 1, H, W), gt)
+        d = ops.silog_bwd(pred.view(B, 1, H, W), gt, sums, weight=1.0, loss_out=loss)
+        pp.backward(d.view(B, H, W) * 10.0)
+        pp.step()
+        hist.append(float(loss))
+    assert hist[-1] < 0.9 * hist[0], hist
+    assert torch.equal(pp.Wb, pp.P.to(torch.bfloat16)) and torch.equal(pp.pyramid.Wb, pp.pyramid.P.to(torch.bfloat16))
