@@ -43,8 +43,9 @@ class DenseHead(FlatModule):
         C, td = c["dense_trans_dim"] >> 3, c["class_token_dim"]
         self.C, self.td, self.width = C, td, C + 3 * td     # stage buffer: [x3 | depth token | seg token | depth_pred3 (+ pad)]
         feat, dtok, stok = torch.arange(C), torch.arange(td) + C, torch.arange(td) + C + td
-        layout = {"depth_token_fuse.fc1.weight": dict(cin_pad=self.width, col_map=torch.cat([feat, torch.tensor([C + 2 * td]), dtok])),
-                  "seg_token_fuse.fc1.weight": dict(cin_pad=self.width, col_map=torch.cat([feat, stok]))}
+        layout = {"depth_token_fuse.fc1.weight": dict(cin_pad=self.width, col_map=torch.cat([feat, torch.tensor([C + 2 * td]), dtok]),
+                                                     shared_input=True),
+                  "seg_token_fuse.fc1.weight": dict(cin_pad=self.width, col_map=torch.cat([feat, stok]), shared_input=True)}
         tensors = {k[len(PREFIX):]: v for k, v in state_dict.items() if k.startswith(PREFIX) and v.is_floating_point()}
         super().__init__(tensors, layout, device=device, **optim)
         self.losses = torch.zeros(2, dtype=torch.float32, device=self.dev)     # weighted (depth, seg) loss of the last step
@@ -127,6 +128,7 @@ class DenseHead(FlatModule):
             d = self.lin_bwd(m["fc2"], d, s["t"])
             d = ops.act_bwd(d, s["h_raw"], ACT_GELU, from_input=True)
             d_x = self.lin_bwd(m["fc1"], d, tp["x"], res=d_x)
+        self.mask_grads()
         if not keep_tape:
             self.tape = None
         return d_x

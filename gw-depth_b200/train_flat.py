@@ -85,6 +85,14 @@ class FlatModule:
         self.Wb = self.P.to(torch.bfloat16)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self._wt_tables = None
+        # physical input columns a weight reads from a SHARED buffer but does not map (they belong to other consumers)
+        self._unmapped = {}
+        for short, lay in self.layout.items():
+            if lay.get("shared_input") and lay.get("col_map") is not None:
+                free = torch.ones(self.index[short][1][-1], dtype=torch.bool)
+                free[lay["col_map"]] = False
+                if bool(free.any()):
+                    self._unmapped[short] = free.nonzero().flatten().to(self.dev)
 
     # ------------------------------------------------------------------ views, logical <-> physical layout
     def view(self, flat, short):
@@ -141,6 +149,13 @@ class FlatModule:
                 pairs += w.transposes()
             self._wt_tables = ops.transpose_batch_tables(pairs)
         ops.transpose_batch(self._wt_tables)
+
+    def mask_grads(self):
+        """Weights that read a shared stage buffer in place (layout flag `shared_input`) have physical columns for channels
+        of OTHER consumers (e.g. the seg token under `pre_proj`): their value is zero, but the buffer holds data there, so
+        the weight-gradient kernel fills them.  Zero them, or AdamW would grow weights the reference does not have."""
+        for short, idx in self._unmapped.items():
+            self.view(self.G, short).index_fill_(-1, idx, 0.0)
 
     @staticmethod
     def conv_bwd(cv, dY, X, need_dx=True, res=None):

@@ -42,7 +42,7 @@ class PointPred(FlatModule):
         assert dim % 16 == 0 and self.in_width % 16 == 0 and self.in_width >= dim + token_dim
         names = ("pre_proj.weight", "pre_proj.bias", "refer_proj.weight", "refer_proj.bias")
         tensors = {n: state_dict[prefix + n] for n in names}
-        layout = {"pre_proj.weight": dict(cin_pad=self.in_width, col_map=torch.arange(dim + token_dim))}
+        layout = {"pre_proj.weight": dict(cin_pad=self.in_width, col_map=torch.arange(dim + token_dim), shared_input=True)}
         super().__init__(tensors, layout, device=device, **optim)
         self.pre = Linear(self, "pre_proj.weight", "pre_proj.bias")
         self.refer = Linear(self, "refer_proj.weight", "refer_proj.bias")
@@ -111,6 +111,7 @@ class PointPred(FlatModule):
         self.G.zero_()
         d_g = self.lin_bwd(self.refer, d_pr, tp["g"])
         d_buf = self.lin_bwd(self.pre, d_g, tp["buf"])
+        self.mask_grads()
         if not keep_tape:
             self.tape = None
         return d_buf, d_pre

@@ -394,3 +394,87 @@ def test_point_pred_training_lowers_a_depth_loss():
         hist.append(float(loss))
     assert hist[-1] < 0.9 * hist[0], hist
     assert torch.equal(pp.Wb, pp.P.to(torch.bfloat16)) and torch.equal(pp.pyramid.Wb, pp.pyramid.P.to(torch.bfloat16))
+
+
+# ------------------------------------------------------------------------------------------ dense tail (A18-A22 chained)
+def _tail_case(B, H4, W4, seed):
+    g = _g(seed)
+    C, td, K = 64, 64, 80
+    buf = torch.zeros(B, H4, W4, 256)
+    buf[..., :C + 2 * td] = torch.randn(B, H4, W4, C + 2 * td, generator=g)
+    depth2 = torch.rand(B, H4 // 2, W4 // 2, generator=g) * 0.9 + 0.05
+    coords = _sample_coords(B, K, g)
+    H, W = 4 * H4, 4 * W4
+    depth_gt = torch.rand(B, 1, H, W, generator=g) * 10.5 + 0.1
+    seg_gt = (torch.rand(B, 1, H, W, generator=g) > 0.5).long()
+    return buf.bfloat16(), depth2, coords, depth_gt, seg_gt
+
+
+def _tail_weights():
+    return {k: v.clone() for k, v in synth_weights().items()
+            if k.startswith("depth_decoder.") or k.startswith("dense_encoder.point_based_pred2.")}
+
+
+def test_dense_tail_gradients_match_oracle_autograd():
+    """train_tail.DenseTail: point_based_pred2 -> dense head -> silog(depth_pred3) * 0.25 + silog(depth) + 2 * seg CE, against
+    torch.autograd over the oracle's functions chained the same way: the three losses, d(stage buffer), d(depth_pred2) and
+    every parameter gradient"""
+    _ops()
+    from gwdepth_b200.engine import sine_table
+    from gwdepth_b200.train_tail import DenseTail
+    B, H4, W4 = 2, 16, 20
+    H, W, C, td, K = 4 * H4, 4 * W4, 64, 64, 80
+    buf, depth2, coords, depth_gt, seg_gt = _tail_case(B, H4, W4, 41)
+    sd = _tail_weights()
+    bufr = buf.float().requires_grad_(True)
+    d2r = depth2.clone().requires_grad_(True)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    tok = bufr.view(B, H4 * W4, 256)
+    pos = oracle.sine_position(torch.zeros(B, H4, W4, dtype=torch.bool), C // 2, False)
+    depth3_o = oracle.point_based_pred(tok[..., :C], tok[..., C:C + td], d2r[:, None], coords.view(B, K, 1, 2), H4, W4, pos,
+                                       oracle.P(sdr, "dense_encoder.point_based_pred2."), C)
+    nchw = lambda t: t.permute(0, 3, 1, 2)
+    depth_o, seg_o = oracle.dense_head(nchw(bufr[..., :C]), depth3_o, nchw(bufr[..., C:C + td]), nchw(bufr[..., C + td:C + 2 * td]),
+                                       (H, W), oracle.P(sdr, "depth_decoder."), 10.0)
+    l3, l4 = oracle.depth_losses([depth3_o, depth_o], depth_gt, weights=(0.25, 1.0))
+    ls = oracle.seg_loss(seg_o, seg_gt)
+    (l3 + l4 + ls).backward()
+    tail = DenseTail({k: v.cuda() for k, v in sd.items()})
+    depth3, depth, seg, losses, d_buf, d_depth2 = tail.loss_and_grads(buf.cuda(), depth2.cuda(), coords.cuda(),
+                                                                      sine_table(H4, W4, C // 2, False, "cuda"),
+                                                                      depth_gt.cuda(), seg_gt.cuda())
+    assert rel_l2(depth3, depth3_o.detach()[:, 0]) < 2e-2 and rel_l2(depth, depth_o.detach()) < 2e-2
+    for got, want in zip(losses.tolist(), (l3, l4, ls)):
+        assert abs(got - float(want)) < 2e-2 * abs(float(want)), (losses.tolist(), float(l3), float(l4), float(ls))
+    ref_dbuf = bufr.grad.view(-1, 256)
+    assert rel_l2(d_buf[:, :C + 2 * td], ref_dbuf[:, :C + 2 * td]) < 6e-2
+    assert float(d_buf[:, C + 2 * td:].float().abs().max()) == 0.0
+    assert rel_l2(d_depth2, d2r.grad) < 6e-2
+    grads = tail.grads()
+    bad = {}
+    for k, v in sdr.items():
+        if ".layer4." in k:
+            continue
+        e = rel_l2(grads[k], v.grad)
+        if e > 7e-2:
+            bad[k] = e
+    assert not bad, bad
+
+
+def test_dense_tail_training_keeps_unmapped_columns_zero_and_lowers_the_loss():
+    """weights that read the shared stage buffer through a column map must not grow entries for the other consumers'
+    channels (their gradient is masked), and a dozen steps lower the summed loss"""
+    _ops()
+    from gwdepth_b200.engine import sine_table
+    from gwdepth_b200.train_tail import DenseTail
+    B, H4, W4 = 2, 16, 20
+    buf, depth2, coords, depth_gt, seg_gt = _tail_case(B, H4, W4, 42)
+    tail = DenseTail({k: v.cuda() for k, v in _tail_weights().items()}, lr=1e-3, max_norm=1.0)
+    args = (buf.cuda(), depth2.cuda(), coords.cuda(), sine_table(H4, W4, 32, False, "cuda"), depth_gt.cuda(), seg_gt.cuda())
+    hist = [tail.train_step(*args).sum().item() for _ in range(12)]
+    assert hist[-1] < 0.95 * hist[0], hist
+    for m in tail.modules():
+        for short in m.index:
+            phys = m.view(m.P, short)
+            assert torch.equal(m._to_physical(short, m._to_logical(short, phys)), phys), short   # nothing outside the logical entries
+        assert torch.equal(m.Wb, m.P.to(torch.bfloat16))
