@@ -1231,6 +1231,9 @@ extern "C" int gwd_linear_wgrad(const void* dy, int64_t dy_rs, const void* x, in
   return launch_wgrad(dy, dy_rs, x, x_rs, rows, N, K, dw, dw_rs, db, 0, 0, 0, 0, stream);
 }
 
+int gwd_conv3x3_wgrad_tc_try(const void* dy, int64_t dy_cs, const void* x, int64_t x_cs, int B, int H, int W, int N, int C,
+                             float* dw, cudaStream_t stream);     // gwd_wgrad_tc.cu (tcgen05 path)
+
 // 3x3 convolution (stride 1, zero padding 1) weight gradient in the packed tap-major layout of gwd_conv_gemm:
 // dw[dx*3+dy][n][c] += sum_{b,y,x} dy[b,y,x,n] * x[b, y+dy-1, x+dx-1, c]; one split-K pass per tap
 extern "C" int gwd_conv3x3_wgrad(const void* dy, int64_t dy_cs, const void* x, int64_t x_cs, int32_t B, int32_t H, int32_t W,
@@ -1245,6 +1248,12 @@ extern "C" int gwd_conv3x3_wgrad(const void* dy, int64_t dy_cs, const void* x, i
 #define GWD_WS(NP, CP) if (N == NP && C == CP) return launch_wgrad_small<NP, CP>(dy, dy_cs, x, x_cs, B, H, W, dw, db, stream)
     GWD_WS(16, 16); GWD_WS(16, 32); GWD_WS(16, 64); GWD_WS(32, 16); GWD_WS(32, 32); GWD_WS(32, 64); GWD_WS(64, 16); GWD_WS(64, 32); GWD_WS(64, 64);
 #undef GWD_WS
+  }
+  // wide convolutions (the 1/4-scale pyramid): all taps on the tcgen05 kernel of gwd_wgrad_tc.cu (MN-major TMA operands)
+  static const bool force_mma = [] { const char* e = getenv("GWD_WGRAD"); return e && strcmp(e, "mma") == 0; }();
+  if (db == nullptr && dy && x && dw && !force_mma) {
+    const int rc = gwd_conv3x3_wgrad_tc_try(dy, dy_cs, x, x_cs, B, H, W, N, C, dw, stream);
+    if (rc <= 0) return rc;
   }
   for (int dx = 0; dx < 3; ++dx)
     for (int dyy = 0; dyy < 3; ++dyy) {

@@ -4,6 +4,8 @@ against torch.autograd over the CPU oracle, and a few optimisation steps.
 
 Tolerances: activations and activation gradients are bf16 (8-bit mantissa); a kernel alone must match fp32 torch to
 bf16 output rounding, the branch gradients (12 transformer layers deep) to a few per cent in relative L2 norm."""
+import ctypes
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -185,6 +187,28 @@ def test_conv3x3_backward_building_blocks(B, H, W, C, N):
     assert rel_l2(db, dy.float().sum((0, 1, 2))) < 2e-5
     dx = ops.conv_gemm(dy.cuda(), ops.pack_conv3x3_dgrad(w.float().cuda()), bias=False)
     assert rel_l2(dx[..., :C], xr.grad.permute(0, 2, 3, 1)) < 6e-3
+
+
+@pytest.mark.parametrize("B,H,W,C,N,cs", [(2, 64, 80, 160, 160, 0), (1, 70, 90, 800, 320, 0), (3, 37, 50, 80, 160, 32),
+                                          (1, 120, 160, 160, 80, 0), (2, 48, 48, 320, 320, 16), (1, 66, 67, 96, 208, 0)])
+def test_conv3x3_wgrad_tensor_core_path(B, H, W, C, N, cs):
+    """gwd_conv3x3_wgrad without bias on maps of >= 4096 pixels and more than 64 channels runs on the tcgen05 kernel
+    (gwd_wgrad_tc.cu: MN-major TMA operands, tap shift = box offset, zero padding = out-of-bounds fill; partial 16 x 4 pixel
+    blocks, channel counts that are not multiples of 64 / 128, both role assignments, channel-slice operands, += semantics):
+    equal to torch.autograd on the same bf16 operands"""
+    ops = _ops()
+    g = _g(B * H + C + N)
+    xw = torch.randn(B, H, W, C + cs, generator=g).bfloat16()
+    dyw = torch.randn(B, H, W, N + cs, generator=g).bfloat16()
+    w = torch.zeros(N, C, 3, 3, requires_grad=True)
+    F.conv2d(xw[..., :C].float().permute(0, 3, 1, 2), w, padding=1).backward(dyw[..., :N].float().permute(0, 3, 1, 2))
+    dw = torch.full((9, N, C), 0.25, device="cuda")          # accumulation semantics
+    xc, dyc = xw.cuda(), dyw.cuda()
+    capi = __import__("gwdepth_b200").capi
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    capi.check(capi.lib().gwd_conv3x3_wgrad(ctypes.c_void_p(dyc.data_ptr()), N + cs, ctypes.c_void_p(xc.data_ptr()), C + cs, B, H, W, N, C,
+                                            ctypes.c_void_p(dw.data_ptr()), None, st), "gwd_conv3x3_wgrad")
+    assert rel_l2(ops.unpack_conv3x3_grad(dw - 0.25, N, C), w.grad) < 2e-4
 
 
 @pytest.mark.parametrize("use_o", [True, False])      # True: tensor-core kernel (needs the forward output), False: CUDA-core kernel
