@@ -331,6 +331,16 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
+    # ------------------------------------------------------------ dense-tail training step (extra key, rank 0, one GPU's batch)
+    train_tail = None
+    if not args.no_train:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import bench_train_tail
+            train_tail = bench_train_tail.measure(B, max(5, min(args.steps, 10)), H, W)[0]
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001  (an extra key must not take the headline line down)
+            train_tail = {"value": None, "error": repr(e)[:300]}
     cpu = None
     eager = None
     if world == 1 and not args.no_cpu_baseline:
@@ -363,7 +373,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "pipeline": "model.infer_stream: 3 streams, double-buffered H2D / forward / D2H"},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
-            "gpu_eager_port": eager, "e2e_uint8_inputs": e2e_uint8, "train_line_branch": train_line}
+            "gpu_eager_port": eager, "e2e_uint8_inputs": e2e_uint8, "train_line_branch": train_line, "train_dense_tail": train_tail}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

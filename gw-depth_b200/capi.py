@@ -112,6 +112,8 @@ SIGNATURES = {
     "gwd_anchor_mix_bwd": (c_int, [P, L, P, P, I, L, I, I, P, L, P, P]),
     "gwd_sample_bilinear_bwd": (c_int, [P, P, I, P, L, I, I, I, I, P]),
     "gwd_sample_scalar_bwd": (c_int, [P, P, I, P, P, I, I, I, P]),
+    "gwd_window_attention_bwd": (c_int, [P, L, P, L, P, L, P, P, I, P, I, I, I, I, F_, P]),
+    "gwd_token_attention_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, F_, P]),
 }
 
 _lib = None

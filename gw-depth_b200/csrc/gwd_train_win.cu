@@ -1,0 +1,257 @@
+// gwd_train_win.cu -- backward of the two attention cores of the class-window Swin blocks
+// (WindowClassAttention, src/models/multiscale_transformerr.py:455-580, under torch.autograd):
+//   * gwd_window_attention_bwd : biased (shifted-)window multi-head self-attention over N = ws*ws <= 64 tokens, head dim
+//                                <= 32: dq | dk | dv into the fused projection-gradient buffer and the gradient of the
+//                                relative-position bias [heads, N, N]
+//   * gwd_token_attention_bwd  : class-token CHANNEL attention (soft-max over the key channels of a head, contraction over
+//                                the window's tokens): gradients of both token queries and of global_k | global_v
+// First version on CUDA cores (fp32 in shared memory): a (window, head) problem is 49 x 49 x <= 32 -- 1/40 of the smallest
+// tcgen05 tile -- and the whole pass is ~5 GFMA at the finest scale; CTAs are PERSISTENT over the windows of one head so
+// that the bias gradient is accumulated in registers and reaches HBM as one atomic per entry and CTA.
+#include "gwd_common.cuh"
+
+namespace {
+
+typedef __nv_bfloat16 bf16;
+constexpr int kMaxN = 64, kMaxHd = 32;
+
+struct WinBwdParams {
+  const bf16* qkv; const bf16* d_o; bf16* dqkv;
+  const float* bias; const float* mask; float* dbias;
+  int items, heads, N, hd, C, mask_windows;
+  int64_t qkv_rs, do_rs, dqkv_rs;
+  float scale;
+};
+
+// grid = (heads, ctas_per_head), 128 threads
+__global__ void __launch_bounds__(128) gwd_window_attention_bwd_kernel(const WinBwdParams p) {
+  extern __shared__ float sm[];
+  const int N = p.N, hd = p.hd, ld = hd + 1, lp = N + 1;
+  float* sq = sm;                    // [N][ld]
+  float* sk = sq + N * ld;
+  float* sv = sk + N * ld;
+  float* sdo = sv + N * ld;
+  float* sP = sdo + N * ld;          // [N][lp]  probabilities
+  float* sdS = sP + N * lp;          // [N][lp]  d scores
+  float* sD = sdS + N * lp;          // [N]      sum_j P dP
+  const int h = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int NN = N * N;
+  float dbacc[(kMaxN * kMaxN + 127) / 128];
+#pragma unroll
+  for (int e = 0; e < (kMaxN * kMaxN + 127) / 128; ++e) dbacc[e] = 0.f;
+  const float* bias_h = p.bias ? p.bias + static_cast<int64_t>(h) * NN : nullptr;
+
+  for (int item = blockIdx.y; item < p.items; item += gridDim.y) {
+    const int64_t row0 = static_cast<int64_t>(item) * N;
+    for (int idx = tid; idx < N * hd; idx += 128) {
+      const int n = idx / hd, d = idx - n * hd;
+      const bf16* r = p.qkv + (row0 + n) * p.qkv_rs + h * hd + d;
+      sq[n * ld + d] = __bfloat162float(r[0]);
+      sk[n * ld + d] = __bfloat162float(r[p.C]);
+      sv[n * ld + d] = __bfloat162float(r[2 * p.C]);
+      sdo[n * ld + d] = __bfloat162float(p.d_o[(row0 + n) * p.do_rs + h * hd + d]);
+    }
+    __syncthreads();
+    const float* mask_w = p.mask ? p.mask + static_cast<int64_t>(item % p.mask_windows) * NN : nullptr;
+    // scores and dP = dO V^T
+    for (int e = tid; e < NN; e += 128) {
+      const int i = e / N, j = e - i * N;
+      float s = 0.f, dp = 0.f;
+      for (int d = 0; d < hd; ++d) {
+        s = fmaf(sq[i * ld + d], sk[j * ld + d], s);
+        dp = fmaf(sdo[i * ld + d], sv[j * ld + d], dp);
+      }
+      s *= p.scale;
+      if (bias_h) s += bias_h[e];
+      if (mask_w) s += mask_w[e];
+      sP[i * lp + j] = s;
+      sdS[i * lp + j] = dp;
+    }
+    __syncthreads();
+    // soft-max rows, D_i = sum_j P_ij dP_ij, dS = P (dP - D)
+    for (int i = warp; i < N; i += 4) {
+      float mx = -INFINITY;
+      for (int j = lane; j < N; j += 32) mx = fmaxf(mx, sP[i * lp + j]);
+      mx = gwd_warp_max(mx);
+      float sum = 0.f;
+      for (int j = lane; j < N; j += 32) {
+        const float e = __expf(sP[i * lp + j] - mx);
+        sP[i * lp + j] = e;
+        sum += e;
+      }
+      sum = gwd_warp_sum(sum);
+      const float inv = 1.f / sum;
+      float dsum = 0.f;
+      for (int j = lane; j < N; j += 32) {
+        const float pr = sP[i * lp + j] * inv;
+        sP[i * lp + j] = pr;
+        dsum = fmaf(pr, sdS[i * lp + j], dsum);
+      }
+      dsum = gwd_warp_sum(dsum);
+      for (int j = lane; j < N; j += 32) sdS[i * lp + j] = sP[i * lp + j] * (sdS[i * lp + j] - dsum);
+      if (lane == 0) sD[i] = dsum;
+    }
+    __syncthreads();
+    if (p.dbias) {
+      int e = tid;
+#pragma unroll
+      for (int r = 0; r < (kMaxN * kMaxN + 127) / 128; ++r, e += 128)
+        if (e < NN) dbacc[r] += sdS[(e / N) * lp + (e % N)];
+    }
+    // dq = scale dS K, dk = scale dS^T Q, dv = P^T dO
+    for (int idx = tid; idx < N * hd; idx += 128) {
+      const int n = idx / hd, d = idx - n * hd;
+      float aq = 0.f, ak = 0.f, av = 0.f;
+      for (int j = 0; j < N; ++j) {
+        aq = fmaf(sdS[n * lp + j], sk[j * ld + d], aq);
+        ak = fmaf(sdS[j * lp + n], sq[j * ld + d], ak);
+        av = fmaf(sP[j * lp + n], sdo[j * ld + d], av);
+      }
+      bf16* o = p.dqkv + (row0 + n) * p.dqkv_rs + h * hd + d;
+      o[0] = __float2bfloat16(aq * p.scale);
+      o[p.C] = __float2bfloat16(ak * p.scale);
+      o[2 * p.C] = __float2bfloat16(av);
+    }
+    __syncthreads();
+  }
+  if (p.dbias) {
+    float* db = p.dbias + static_cast<int64_t>(h) * NN;
+    int e = tid;
+#pragma unroll
+    for (int r = 0; r < (kMaxN * kMaxN + 127) / 128; ++r, e += 128)
+      if (e < NN) atomicAdd(db + e, dbacc[r]);
+  }
+}
+
+struct TokBwdParams {
+  const bf16* dq; const bf16* sq; const bf16* tk; const bf16* tv;
+  const bf16* d_dout; const bf16* d_sout;
+  bf16* g_dq; bf16* g_sq; bf16* g_tk; bf16* g_tv;
+  int items, N, heads, td, tc;
+  int64_t q_rs, k_rs, v_rs, o_rs, gq_rs, gk_rs, gv_rs;
+  float scale;
+};
+
+constexpr int kTokR = 16, kTokC = 32;     // (depth | seg) query channels per head <= 16, key channels per head <= 32
+
+// one CTA (128 threads) per (window, head): rows r = [depth td | seg td], a[r][c] = softmax_c(scale sum_n q[n][r] k[n][c]),
+// out[n][r] = sum_c a[r][c] v[n][c]
+__global__ void __launch_bounds__(128) gwd_token_attention_bwd_kernel(const TokBwdParams p) {
+  __shared__ float q[kMaxN][kTokR + 1], go[kMaxN][kTokR + 1], k[kMaxN][kTokC + 1], v[kMaxN][kTokC + 1];
+  __shared__ float a[kTokR][kTokC + 1], dz[kTokR][kTokC + 1];
+  const int N = p.N, td = p.td, tc = p.tc, R = 2 * td;
+  const int tid = threadIdx.x;
+  for (int wh = blockIdx.x; wh < p.items * p.heads; wh += gridDim.x) {
+    const int item = wh / p.heads, h = wh - item * p.heads;
+    const int64_t row0 = static_cast<int64_t>(item) * N;
+    for (int idx = tid; idx < N * R; idx += 128) {
+      const int n = idx / R, r = idx - n * R;
+      const bool seg = r >= td;
+      const int c = h * td + (seg ? r - td : r);
+      q[n][r] = __bfloat162float((seg ? p.sq : p.dq)[(row0 + n) * p.q_rs + c]);
+      go[n][r] = __bfloat162float((seg ? p.d_sout : p.d_dout)[(row0 + n) * p.o_rs + c]);
+    }
+    for (int idx = tid; idx < N * tc; idx += 128) {
+      const int n = idx / tc, c = idx - n * tc;
+      k[n][c] = __bfloat162float(p.tk[(row0 + n) * p.k_rs + h * tc + c]);
+      v[n][c] = __bfloat162float(p.tv[(row0 + n) * p.v_rs + h * tc + c]);
+    }
+    __syncthreads();
+    // scores and d a = sum_n go[n][r] v[n][c]
+    for (int e = tid; e < R * tc; e += 128) {
+      const int r = e / tc, c = e - r * tc;
+      float s = 0.f, da = 0.f;
+      for (int n = 0; n < N; ++n) {
+        s = fmaf(q[n][r], k[n][c], s);
+        da = fmaf(go[n][r], v[n][c], da);
+      }
+      a[r][c] = s * p.scale;
+      dz[r][c] = da;
+    }
+    __syncthreads();
+    if (tid < R) {      // soft-max over the key channels of row tid and its backward (rows are <= 64 wide)
+      const int r = tid;
+      float mx = -INFINITY;
+      for (int c = 0; c < tc; ++c) mx = fmaxf(mx, a[r][c]);
+      float sum = 0.f;
+      for (int c = 0; c < tc; ++c) { const float e = __expf(a[r][c] - mx); a[r][c] = e; sum += e; }
+      const float inv = 1.f / sum;
+      float dsum = 0.f;
+      for (int c = 0; c < tc; ++c) { a[r][c] *= inv; dsum = fmaf(a[r][c], dz[r][c], dsum); }
+      for (int c = 0; c < tc; ++c) dz[r][c] = a[r][c] * (dz[r][c] - dsum) * p.scale;
+    }
+    __syncthreads();
+    // d q[n][r] = sum_c dz[r][c] k[n][c]
+    for (int idx = tid; idx < N * R; idx += 128) {
+      const int n = idx / R, r = idx - n * R;
+      float acc = 0.f;
+      for (int c = 0; c < tc; ++c) acc = fmaf(dz[r][c], k[n][c], acc);
+      const bool seg = r >= td;
+      (seg ? p.g_sq : p.g_dq)[(row0 + n) * p.gq_rs + h * td + (seg ? r - td : r)] = __float2bfloat16(acc);
+    }
+    // d k[n][c] = sum_r dz[r][c] q[n][r];  d v[n][c] = sum_r a[r][c] go[n][r]
+    for (int idx = tid; idx < N * tc; idx += 128) {
+      const int n = idx / tc, c = idx - n * tc;
+      float gk = 0.f, gv = 0.f;
+      for (int r = 0; r < R; ++r) {
+        gk = fmaf(dz[r][c], q[n][r], gk);
+        gv = fmaf(a[r][c], go[n][r], gv);
+      }
+      p.g_tk[(row0 + n) * p.gk_rs + h * tc + c] = __float2bfloat16(gk);
+      p.g_tv[(row0 + n) * p.gv_rs + h * tc + c] = __float2bfloat16(gv);
+    }
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+#define GWD_STREAM cudaStream_t stream = static_cast<cudaStream_t>(stream_)
+
+extern "C" int gwd_window_attention_bwd(const void* qkv, int64_t qkv_rs, const void* d_o, int64_t do_rs, void* dqkv, int64_t dqkv_rs,
+                                        const float* bias, const float* mask, int32_t mask_windows, float* dbias, int32_t items,
+                                        int32_t heads, int32_t N, int32_t hd, float scale, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(qkv && d_o && dqkv, "gwd_window_attention_bwd: null pointer");
+  GWD_CHECK_ARG(items > 0 && heads > 0 && heads <= 65535 && N > 0 && N <= kMaxN && hd > 0 && hd <= kMaxHd,
+                "gwd_window_attention_bwd: needs N <= 64 tokens and head dim <= 32 (N=%d hd=%d)", N, hd);
+  GWD_CHECK_ARG(mask == nullptr || mask_windows > 0, "gwd_window_attention_bwd: mask without mask_windows");
+  WinBwdParams p;
+  p.qkv = static_cast<const bf16*>(qkv); p.d_o = static_cast<const bf16*>(d_o); p.dqkv = static_cast<bf16*>(dqkv);
+  p.bias = bias; p.mask = mask; p.dbias = dbias;
+  p.items = items; p.heads = heads; p.N = N; p.hd = hd; p.C = heads * hd; p.mask_windows = mask_windows > 0 ? mask_windows : 1;
+  p.qkv_rs = qkv_rs; p.do_rs = do_rs; p.dqkv_rs = dqkv_rs; p.scale = scale;
+  GWD_CHECK_ARG(qkv_rs >= 3 * p.C && dqkv_rs >= 3 * p.C && do_rs >= p.C, "gwd_window_attention_bwd: row strides too small");
+  const size_t smem = sizeof(float) * (4 * N * (hd + 1) + 2 * N * (N + 1) + N);
+  static bool attr_set = false;
+  if (!attr_set) {
+    GWD_CUDA(cudaFuncSetAttribute(gwd_window_attention_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    attr_set = true;
+  }
+  int per_head = std::max(1, (gwd_num_sms() * 4) / heads);
+  per_head = std::min(per_head, items);
+  gwd_window_attention_bwd_kernel<<<dim3(heads, per_head), 128, smem, stream>>>(p);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_token_attention_bwd(const void* dq, const void* sq, const void* tk, const void* tv, const void* d_dout,
+                                       const void* d_sout, void* g_dq, void* g_sq, void* g_tk, void* g_tv, int32_t items, int32_t N,
+                                       int32_t heads, int32_t td, int32_t tc, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs,
+                                       int64_t gq_rs, int64_t gk_rs, int64_t gv_rs, float scale, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(dq && sq && tk && tv && d_dout && d_sout && g_dq && g_sq && g_tk && g_tv, "gwd_token_attention_bwd: null pointer");
+  GWD_CHECK_ARG(items > 0 && heads > 0 && N > 0 && N <= kMaxN && td > 0 && 2 * td <= kTokR && tc > 0 && tc <= kTokC,
+                "gwd_token_attention_bwd: needs N <= 64, 2 td <= 16, tc <= 32 (N=%d td=%d tc=%d)", N, td, tc);
+  TokBwdParams p;
+  p.dq = static_cast<const bf16*>(dq); p.sq = static_cast<const bf16*>(sq); p.tk = static_cast<const bf16*>(tk);
+  p.tv = static_cast<const bf16*>(tv); p.d_dout = static_cast<const bf16*>(d_dout); p.d_sout = static_cast<const bf16*>(d_sout);
+  p.g_dq = static_cast<bf16*>(g_dq); p.g_sq = static_cast<bf16*>(g_sq); p.g_tk = static_cast<bf16*>(g_tk); p.g_tv = static_cast<bf16*>(g_tv);
+  p.items = items; p.N = N; p.heads = heads; p.td = td; p.tc = tc;
+  p.q_rs = q_rs; p.k_rs = k_rs; p.v_rs = v_rs; p.o_rs = o_rs; p.gq_rs = gq_rs; p.gk_rs = gk_rs; p.gv_rs = gv_rs; p.scale = scale;
+  const int64_t units = static_cast<int64_t>(items) * heads;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(units, static_cast<int64_t>(gwd_num_sms()) * 8));
+  gwd_token_attention_bwd_kernel<<<grid, 128, 0, stream>>>(p);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}

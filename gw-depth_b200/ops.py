@@ -291,7 +291,7 @@ def window_gather(x, B, H, W, ws, shift, gamma=None, beta=None, n=None, eps=1e-5
 
 
 def window_merge(win, shortcut, B, H, W, ws, shift, gamma=None, beta=None, n=None, eps=1e-5, want_ln=False, C=None,
-                 sc_coff=0):
+                 sc_coff=0, win_coff=0):
     """-> (shortcut + unwindowed(win[:, :C]), LN(of that) or None), both [B*H*W, C] contiguous.  win may be wider than C
     (row stride = win.shape[-1]); shortcut may be a channel slice [sc_coff, sc_coff+C) of a wider buffer."""
     C = C or shortcut.shape[-1]
@@ -299,7 +299,7 @@ def window_merge(win, shortcut, B, H, W, ws, shift, gamma=None, beta=None, n=Non
     rows = B * H * W
     out = torch.empty(rows, C, dtype=torch.bfloat16, device=win.device)
     out_ln = torch.empty(rows, C, dtype=torch.bfloat16, device=win.device) if want_ln else None
-    capi.check(_L().gwd_window_merge(_ptr(win), win.shape[-1], _off(shortcut, sc_coff), shortcut.shape[-1], _ptr(out), C,
+    capi.check(_L().gwd_window_merge(_off(win, win_coff), win.shape[-1], _off(shortcut, sc_coff), shortcut.shape[-1], _ptr(out), C,
                                      _ptr(gamma), _ptr(beta), eps, _ptr(out_ln), C, B, H, W, ws, shift, C, n or C,
                                      _stream()), "gwd_window_merge")
     return out, out_ln
@@ -653,6 +653,31 @@ def sample_scalar_bwd(d, coords, H, W, add=None):
     capi.check(_L().gwd_sample_scalar_bwd(_ptr(d), _ptr(coords), K, _ptr(add), _ptr(out), B, H, W, _stream()),
                "gwd_sample_scalar_bwd")
     return out
+
+
+def window_attention_bwd(qkv, d_o, *, items, heads, N, hd, scale, bias=None, mask=None, dbias=None):
+    """backward of attention() on fused window projections: qkv bf16 [items*N, 3C], d_o bf16 [items*N, C] -> dqkv [items*N, 3C];
+    dbias fp32 [heads, N, N] (optional) is accumulated"""
+    C = heads * hd
+    assert qkv.dtype == d_o.dtype == torch.bfloat16 and qkv.is_contiguous() and d_o.is_contiguous()
+    assert qkv.shape == (items * N, 3 * C) and d_o.shape == (items * N, C)
+    dqkv = torch.empty_like(qkv)
+    capi.check(_L().gwd_window_attention_bwd(_ptr(qkv), 3 * C, _ptr(d_o), C, _ptr(dqkv), 3 * C, _ptr(bias), _ptr(mask),
+                                             mask.shape[0] if mask is not None else 0, _ptr(dbias), items, heads, N, hd, scale,
+                                             _stream()), "gwd_window_attention_bwd")
+    return dqkv
+
+
+def token_attention_bwd(dq, sq, gkv, d_dout, d_sout, *, items, N, heads, td, tc, scale):
+    """backward of token_attention(dq, sq, gkv[:, :tC], gkv[:, tC:]): -> (g_dq, g_sq [rows, heads*td], g_gkv [rows, 2*heads*tc])"""
+    tC = heads * tc
+    assert gkv.shape[-1] == 2 * tC and all(t.is_contiguous() for t in (dq, sq, gkv, d_dout, d_sout))
+    g_dq, g_sq, g_gkv = torch.empty_like(dq), torch.empty_like(sq), torch.empty_like(gkv)
+    capi.check(_L().gwd_token_attention_bwd(_ptr(dq), _ptr(sq), _ptr(gkv), _off(gkv, tC), _ptr(d_dout), _ptr(d_sout), _ptr(g_dq),
+                                            _ptr(g_sq), _ptr(g_gkv), _off(g_gkv, tC), items, N, heads, td, tc, dq.shape[-1],
+                                            2 * tC, 2 * tC, d_dout.shape[-1], g_dq.shape[-1], 2 * tC, 2 * tC, scale, _stream()),
+               "gwd_token_attention_bwd")
+    return g_dq, g_sq, g_gkv
 
 
 def transpose_batch(tables):

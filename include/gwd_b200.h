@@ -363,6 +363,23 @@ int gwd_sample_bilinear_bwd(const float* d, const float* coords, int32_t K, void
 int gwd_sample_scalar_bwd(const float* d, const float* coords, int32_t K, const float* add, float* out, int32_t B, int32_t H,
                           int32_t W, void* stream);
 
+/* Backward of the biased (shifted-)window self-attention core of the class-window Swin blocks (WindowClassAttention,
+ * src/models/multiscale_transformerr.py:539-556 under torch.autograd): qkv bf16 [items*N, qkv_rs] = q | k | v (C = heads*hd
+ * channels each, q un-scaled), S = scale q k^T + bias[head] + mask[item % mask_windows], P = softmax(S), O = P v.
+ * d_o bf16 [items*N, do_rs] -> dqkv bf16 [items*N, dqkv_rs] = dq | dk | dv; dbias (optional) fp32 [heads, N, N] +=
+ * sum over the windows of dS (the gradient of the gathered relative-position bias).  N <= 64, hd <= 32. */
+int gwd_window_attention_bwd(const void* qkv, int64_t qkv_rs, const void* d_o, int64_t do_rs, void* dqkv, int64_t dqkv_rs,
+                             const float* bias, const float* mask, int32_t mask_windows, float* dbias, int32_t items,
+                             int32_t heads, int32_t N, int32_t hd, float scale, void* stream);
+/* Backward of gwd_token_attention (class-token channel attention, multiscale_transformerr.py:561-578): inputs as the
+ * forward (dq / sq: [rows, q_rs] token queries, td channels per head; tk / tv: [rows, k_rs / v_rs], tc channels per head)
+ * plus the output gradients d_dout / d_sout [rows, o_rs]; writes the gradients of the queries (g_dq, g_sq: [rows, gq_rs])
+ * and of the keys / values (g_tk, g_tv: [rows, gk_rs / gv_rs]; both token rows contribute).  N <= 64, 2 td <= 16, tc <= 32. */
+int gwd_token_attention_bwd(const void* dq, const void* sq, const void* tk, const void* tv, const void* d_dout, const void* d_sout,
+                            void* g_dq, void* g_sq, void* g_tk, void* g_tv, int32_t items, int32_t N, int32_t heads, int32_t td,
+                            int32_t tc, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs, int64_t gq_rs, int64_t gk_rs,
+                            int64_t gv_rs, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
