@@ -1,0 +1,173 @@
+"""GPU parity of the class-window Swin stage training path (train_swin.ClassStage) and of
+the stage entries between the Swin stages (train_entry.StageEntry, A12 glue): the two attention-backward kernels against
+torch.autograd on the same bf16 operands, then forward values and every input / parameter gradient of the modules against
+torch.autograd over the CPU oracle's `swin_stage` / stage-entry expressions.
+
+Tolerances: single kernels to bf16 output rounding (6e-3 relative L2; fp32 outputs 1e-4); modules a few per cent (bf16
+activations through two blocks of ~25 kernels each)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import oracle, synth_weights
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import ops
+    return ops
+
+
+def _g(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def rel_l2(got, ref):
+    got, ref = got.double().cpu(), ref.double().cpu()
+    return float((got - ref).norm() / ref.norm().clamp_min(1e-30))
+
+
+# ------------------------------------------------------------------------------------------ class-window Swin stage (A13/A14/A16)
+@pytest.mark.parametrize("heads,hd,N,items,nWm", [(16, 4, 49, 12, 4), (16, 8, 49, 6, 0), (8, 32, 49, 5, 0), (4, 16, 64, 3, 3)])
+def test_window_attention_bwd(heads, hd, N, items, nWm):
+    """gwd_window_attention_bwd == autograd of softmax(scale q k^T + bias + mask) v on fused q | k | v rows"""
+    ops = _ops()
+    g = _g(heads * hd + items)
+    C = heads * hd
+    scale = hd ** -0.5
+    qkv = torch.randn(items * N, 3 * C, generator=g).bfloat16()
+    d_o = torch.randn(items * N, C, generator=g).bfloat16()
+    bias = torch.randn(heads, N, N, generator=g)
+    mask = None
+    if nWm:
+        mask = torch.where(torch.rand(nWm, N, N, generator=g) < 0.3, torch.full((nWm, N, N), -100.0), torch.zeros(nWm, N, N))
+        mask[:, torch.arange(N), torch.arange(N)] = 0.0
+    qr = qkv.float().view(items, N, 3, heads, hd).permute(2, 0, 3, 1, 4).clone().requires_grad_(True)   # [3, items, heads, N, hd]
+    br = bias.clone().requires_grad_(True)
+    a = (qr[0] * scale) @ qr[1].transpose(-2, -1) + br[None]
+    if mask is not None:
+        a = a + mask.repeat(items // nWm, 1, 1)[:, None]
+    out = torch.softmax(a, dim=-1) @ qr[2]
+    out.backward(d_o.float().view(items, N, heads, hd).permute(0, 2, 1, 3))
+    dbias = torch.full((heads, N, N), 0.5, device="cuda")
+    dqkv = ops.window_attention_bwd(qkv.cuda(), d_o.cuda(), items=items, heads=heads, N=N, hd=hd, scale=scale, bias=bias.cuda(),
+                                    mask=mask.cuda() if mask is not None else None, dbias=dbias)
+    ref = qr.grad.permute(1, 3, 0, 2, 4).reshape(items * N, 3 * C)
+    assert rel_l2(dqkv, ref) < 6e-3
+    assert rel_l2(dbias - 0.5, br.grad) < 1e-4
+
+
+@pytest.mark.parametrize("heads,td,tc,N,items", [(16, 4, 12, 49, 7), (16, 4, 24, 49, 3), (8, 8, 32, 49, 2)])
+def test_token_attention_bwd(heads, td, tc, N, items):
+    """gwd_token_attention_bwd == autograd of the class-token channel attention (multiscale_transformerr.py:561-578)"""
+    ops = _ops()
+    g = _g(heads + tc)
+    TD, TC = heads * td, heads * tc
+    scale = 0.37
+    rows = items * N
+    dq, sq = torch.randn(rows, TD, generator=g).bfloat16(), torch.randn(rows, TD, generator=g).bfloat16()
+    gkv = torch.randn(rows, 2 * TC, generator=g).bfloat16()
+    d_dout, d_sout = torch.randn(rows, TD, generator=g).bfloat16(), torch.randn(rows, TD, generator=g).bfloat16()
+    leaf = lambda t: t.float().clone().requires_grad_(True)
+    dqr, sqr, gr = leaf(dq), leaf(sq), leaf(gkv)
+    tk = gr[:, :TC].reshape(items, N, heads, tc).permute(0, 2, 1, 3)
+    tv = gr[:, TC:].reshape(items, N, heads, tc).permute(0, 2, 1, 3)
+
+    def chan(tok):
+        tq = tok.reshape(items, N, heads, td).permute(0, 2, 1, 3) * scale
+        a = torch.softmax(tq.transpose(-2, -1) @ tk, dim=-1)
+        return (a @ tv.transpose(-2, -1)).reshape(items, -1, N).permute(0, 2, 1).reshape(rows, TD)
+    (chan(dqr) * d_dout.float()).sum().add((chan(sqr) * d_sout.float()).sum()).backward()
+    # forward kernel agrees with the same formula
+    dout, sout = torch.empty(rows, TD, dtype=torch.bfloat16, device="cuda"), torch.empty(rows, TD, dtype=torch.bfloat16, device="cuda")
+    gc = gkv.cuda()
+    ops.token_attention(dq.cuda(), sq.cuda(), gc, gc[:, TC:], dout, sout, items=items, N=N, heads=heads, td=td, tc=tc, q_rs=TD,
+                        k_rs=2 * TC, v_rs=2 * TC, o_rs=TD, scale=scale)
+    assert rel_l2(dout, chan(dqr).detach()) < 1e-2
+    g_dq, g_sq, g_gkv = ops.token_attention_bwd(dq.cuda(), sq.cuda(), gc, d_dout.cuda(), d_sout.cuda(), items=items, N=N, heads=heads,
+                                                td=td, tc=tc, scale=scale)
+    assert rel_l2(g_dq, dqr.grad) < 6e-3 and rel_l2(g_sq, sqr.grad) < 6e-3
+    assert rel_l2(g_gkv, gr.grad) < 6e-3
+
+
+@pytest.mark.parametrize("stage,C,depth,B,H,W", [(3, 64, 1, 2, 10, 12), (2, 128, 2, 1, 14, 9), (1, 256, 2, 1, 7, 8)])
+def test_class_stage_gradients_match_oracle_autograd(stage, C, depth, B, H, W):
+    """train_swin.ClassStage (forward + backward) against torch.autograd over the oracle's `swin_stage` with class tokens:
+    the three output streams, the gradients of the three input streams and of every live parameter (window padding, the
+    shifted block with its mask, relative-position bias tables, the shared proj_dth)"""
+    _ops()
+    from gwdepth_b200.train_swin import ClassStage
+    prefix = "dense_encoder.class_transformer%d." % stage
+    sd = {k: v.clone() for k, v in synth_weights().items() if k.startswith(prefix)}
+    g = _g(stage * 11)
+    td, L = 64, H * W
+    x, d, s = (torch.randn(B * L, n, generator=g).bfloat16() for n in (C, td, td))
+    gx, gd, gs = (torch.randn(B * L, n, generator=g).bfloat16() for n in (C, td, td))
+    xr, dr, sr = (t.float().view(B, L, -1).requires_grad_(True) for t in (x, d, s))
+    sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    xo, do, so = oracle.swin_stage(xr, H, W, oracle.P(sdr, prefix), depth, 16, 7, dtok=dr, stok=sr)
+    ((xo * gx.float().view(B, L, -1)).sum() + (do * gd.float().view(B, L, -1)).sum() + (so * gs.float().view(B, L, -1)).sum()).backward()
+    st = ClassStage({k: v.cuda() for k, v in sd.items()}, prefix, C, depth)
+    back = st.state_dict()
+    for k, v in back.items():
+        assert torch.equal(v.cpu(), sd[k]), k
+    x1, d1, s1 = st.forward(x.cuda(), d.cuda(), s.cuda(), B, H, W)
+    assert rel_l2(x1, xo.detach().view(B * L, -1)) < 2e-2 and rel_l2(d1, do.detach().view(B * L, -1)) < 2e-2
+    assert rel_l2(s1, so.detach().view(B * L, -1)) < 2e-2
+    g_x, g_d, g_s = st.backward(gx.cuda(), gd.cuda(), gs.cuda())
+    assert rel_l2(g_x, xr.grad.view(B * L, -1)) < 5e-2 and rel_l2(g_d, dr.grad.view(B * L, -1)) < 5e-2
+    assert rel_l2(g_s, sr.grad.view(B * L, -1)) < 5e-2
+    grads = st.grads()
+    bad = {}
+    for k, v in sdr.items():
+        if not v.is_floating_point():
+            continue
+        if v.grad is None:
+            assert k not in grads, k                   # dead parameters (proj_seg, diff_*, border_*) are not stored
+            continue
+        e = rel_l2(grads[k], v.grad)
+        if e > 6e-2:
+            bad[k] = e
+    assert not bad, bad
+
+
+# ------------------------------------------------------------------------------------------ stage entries (A12 glue)
+@pytest.mark.parametrize("si,Cprev,C,Cb", [(3, 128, 64, 256), (2, 256, 128, 512)])
+def test_stage_entry_gradients_match_oracle_autograd(si, Cprev, C, Cb):
+    """train_entry.StageEntry against torch.autograd over the oracle's stage-entry expressions (dense_encoder lines for the
+    1/8 and 1/4 stages): outputs, gradients of the previous features / tokens / backbone map and of every parameter"""
+    _ops()
+    from gwdepth_b200.train_entry import StageEntry
+    B, h, w, td = 2, 6, 8, 64
+    H, W = 2 * h, 2 * w
+    sc = {2: "8", 3: "4"}[si]
+    g = _g(si)
+    prev_x = torch.randn(B, h, w, Cprev, generator=g).bfloat16()
+    prev_d, prev_s = torch.randn(B * h * w, td, generator=g).bfloat16(), torch.randn(B * h * w, td, generator=g).bfloat16()
+    feat = torch.randn(B, H, W, Cb, generator=g).bfloat16()
+    gx, gd, gs = (torch.randn(B * H * W, n, generator=g).bfloat16() for n in (C, td, td))
+    sd = {k: v.clone() for k, v in synth_weights().items() if k.startswith("dense_encoder.") and "transformer" not in k and "point_based" not in k}
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    p = oracle.P(sdr, "dense_encoder.")
+    pxr, pdr, psr, fr = (t.float().clone().requires_grad_(True) for t in (prev_x, prev_d, prev_s, feat))
+    up = F.interpolate(pxr.permute(0, 3, 1, 2), size=(H, W), mode="nearest")
+    xo = oracle.linear(up.flatten(2).permute(0, 2, 1), p, "proj_class%d" % si) + \
+        oracle.conv_a(fr.permute(0, 3, 1, 2), p, "proj_backbn%d" % si).flatten(2).permute(0, 2, 1)
+    do = oracle.mlp_norm(oracle.up_tokens(pdr.view(B, h * w, td), h, w, (H, W)).flatten(2).permute(0, 2, 1), p, "old_depth_token_proj" + sc)
+    so = oracle.mlp_norm(oracle.up_tokens(psr.view(B, h * w, td), h, w, (H, W)).flatten(2).permute(0, 2, 1), p, "old_seg_token_proj" + sc)
+    ((xo.reshape(-1, C) * gx.float()).sum() + (do.reshape(-1, td) * gd.float()).sum() + (so.reshape(-1, td) * gs.float()).sum()).backward()
+    ent = StageEntry({k: v.cuda() for k, v in sd.items()}, si)
+    for k, v in ent.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k
+    x, d, s = ent.forward(prev_x.cuda(), prev_d.cuda(), prev_s.cuda(), feat.cuda())
+    assert rel_l2(x, xo.detach().reshape(-1, C)) < 1e-2 and rel_l2(d, do.detach().reshape(-1, td)) < 1e-2
+    assert rel_l2(s, so.detach().reshape(-1, td)) < 1e-2
+    d_px, d_pd, d_ps, d_feat = ent.backward(gx.cuda(), gd.cuda(), gs.cuda(), need_dfeat=True)
+    assert rel_l2(d_px, pxr.grad) < 2e-2 and rel_l2(d_pd, pdr.grad) < 3e-2 and rel_l2(d_ps, psr.grad) < 3e-2
+    assert rel_l2(d_feat[..., :Cb], fr.grad) < 2e-2
+    grads = ent.grads()
+    bad = {k: rel_l2(grads[k], sdr[k].grad) for k in grads}
+    bad = {k: e for k, e in bad.items() if e > 3e-2}
+    assert not bad, bad
