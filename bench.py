@@ -332,13 +332,23 @@ def main():
             dist.destroy_process_group()
         return
     # ------------------------------------------------------------ dense-tail training step (extra key, rank 0, one GPU's batch)
+    # measured in a child process: its 9 GB of activations and any fault stay out of the headline measurement
     train_tail = None
     if not args.no_train:
         try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            import bench_train_tail
-            train_tail = bench_train_tail.measure(B, max(5, min(args.steps, 10)), H, W)[0]
-            torch.cuda.empty_cache()
+            import subprocess
+            import tempfile
+            with tempfile.TemporaryDirectory() as td_:
+                out = os.path.join(td_, "tail.json")
+                env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(dev.index if os.environ.get("CUDA_VISIBLE_DEVICES") is None else
+                                                                os.environ["CUDA_VISIBLE_DEVICES"].split(",")[dev.index]))
+                for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+                    env.pop(k, None)
+                subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_train_tail.py"), "--batch", str(B), "--steps",
+                                str(max(5, min(args.steps, 10))), "--json", out], check=True, timeout=600, env=env,
+                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+                with open(out) as f:
+                    train_tail = json.load(f)
         except Exception as e:  # noqa: BLE001  (an extra key must not take the headline line down)
             train_tail = {"value": None, "error": repr(e)[:300]}
     cpu = None

@@ -171,3 +171,81 @@ def test_stage_entry_gradients_match_oracle_autograd(si, Cprev, C, Cb):
     bad = {k: rel_l2(grads[k], sdr[k].grad) for k in grads}
     bad = {k: e for k, e in bad.items() if e > 3e-2}
     assert not bad, bad
+
+
+# ------------------------------------------------------------------------------------------ the dense branch behind the 1/32 stage
+def _oracle_dense_branch(sdr, x32, feats, coords1, coords2, depth_gt, seg_gt, size):
+    """the body of oracle.dense_encoder from the 1/16 stage on (sample points pinned) + dense head + the five losses"""
+    cfg = oracle.DEFAULT_CFG
+    p = oracle.P(sdr, "dense_encoder.")
+    heads, ws, D = cfg["dense_trans_heads"], cfg["window"], cfg["dense_trans_dim"]
+    B = x32.shape[0]
+    tokens = lambda m: m.flatten(2).permute(0, 2, 1)
+    depths, prev, dtok, stok = [], x32, None, None
+    for si, (feat, pts) in enumerate(zip(feats, (None, coords1, coords2)), start=1):
+        Hs, Ws = feat.shape[-2:]
+        hp, wp = prev.shape[-2:]
+        up = F.interpolate(prev, size=(Hs, Ws), mode="nearest")
+        x = oracle.linear(tokens(up), p, "proj_class%d" % si) + tokens(oracle.conv_a(feat, p, "proj_backbn%d" % si))
+        if si == 1:
+            dtok, stok = p["depth_token"].expand(B, Hs * Ws, -1), p["seg_token"].expand(B, Hs * Ws, -1)
+        else:
+            sc = {2: "8", 3: "4"}[si]
+            dtok = oracle.mlp_norm(tokens(oracle.up_tokens(dtok, hp, wp, (Hs, Ws))), p, "old_depth_token_proj" + sc)
+            stok = oracle.mlp_norm(tokens(oracle.up_tokens(stok, hp, wp, (Hs, Ws))), p, "old_seg_token_proj" + sc)
+        x, dtok, stok = oracle.swin_stage(x, Hs, Ws, p.sub("class_transformer%d" % si), cfg["class_trans_layers"][si - 1], heads, ws,
+                                          dtok=dtok, stok=stok)
+        if si == 1:
+            depth = oracle.depth_head(torch.cat([x, dtok], dim=-1), p, "depth_pred16").permute(0, 2, 1).reshape(B, -1, Hs, Ws)
+        else:
+            pos = oracle.sine_position(torch.zeros(B, Hs, Ws, dtype=torch.bool), D // (8 if si == 2 else 16), False)
+            depth = oracle.point_based_pred(x, dtok, depths[-1], pts.view(B, -1, 1, 2), Hs, Ws, pos, p.sub("point_based_pred%d" % (si - 1)),
+                                            D // (4 if si == 2 else 8))
+        depths.append(depth)
+        prev = x.permute(0, 2, 1).reshape(B, -1, Hs, Ws)
+    img = lambda t: t.permute(0, 2, 1).reshape(B, -1, *feats[2].shape[-2:])
+    depth, seg = oracle.dense_head(prev, depths[-1], img(dtok), img(stok), size, oracle.P(sdr, "depth_decoder."), 10.0)
+    losses = oracle.depth_losses(depths + [depth], depth_gt) + [oracle.seg_loss(seg, seg_gt)]
+    return depths + [depth], seg, losses
+
+
+def test_dense_branch_gradients_match_oracle_autograd():
+    """train_branch.DenseBranch (three class-window stages + entries + coarse depth head + both point predictions + dense head +
+    five losses) against torch.autograd over the oracle's functions chained as `dense_encoder` chains them: losses, the four
+    depth maps, d(x32), d(C4), d(C3) and every live parameter gradient of the dense branch behind the 1/32 stage"""
+    _ops()
+    from gwdepth_b200.train_branch import DenseBranch
+    B, h5, w5 = 1, 4, 5
+    H, W = 32 * h5, 32 * w5
+    g = _g(77)
+    x32 = torch.randn(B, h5, w5, 512, generator=g).bfloat16()
+    feats = [torch.randn(B, (2 ** k) * h5, (2 ** k) * w5, c, generator=g).bfloat16() for k, c in ((1, 1024), (2, 512), (3, 256))]
+    coords1, coords2 = torch.rand(B, 30, 2, generator=g) * 2 - 1, torch.rand(B, 80, 2, generator=g) * 2 - 1
+    depth_gt = torch.rand(B, 1, H, W, generator=g) * 10.5 + 0.1
+    seg_gt = (torch.rand(B, 1, H, W, generator=g) > 0.5).long()
+    live = ("dense_encoder.class_transformer", "dense_encoder.point_based_pred", "dense_encoder.proj_", "dense_encoder.old_",
+            "dense_encoder.depth_pred16", "dense_encoder.depth_token", "dense_encoder.seg_token", "depth_decoder.")
+    sd = {k: v.clone() for k, v in synth_weights().items() if k.startswith(live)}
+    sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    nchw = lambda t: t.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    x32r, featr = nchw(x32), [nchw(f) for f in feats]
+    depths_o, seg_o, losses_o = _oracle_dense_branch(sdr, x32r, featr, coords1, coords2, depth_gt, seg_gt, (H, W))
+    sum(losses_o).backward()
+    br = DenseBranch({k: v.cuda() for k, v in sd.items()})
+    outs, losses, d_x32, d_c4, d_c3 = br.loss_and_grads(x32.cuda(), torch.zeros(B, h5, w5, device="cuda"), [f.cuda() for f in feats],
+                                                        depth_gt.cuda(), seg_gt.cuda(),
+                                                        pinned={"sample1": coords1.cuda(), "sample2": coords2.cuda()})
+    errs = {"depth%d" % (i + 1): rel_l2(d_.reshape(-1), o.detach().reshape(-1)) for i, (d_, o) in enumerate(zip(outs["pred_depth"], depths_o))}
+    errs.update({"loss%d" % i: abs(a - float(b)) / abs(float(b)) for i, (a, b) in enumerate(zip(losses.tolist(), losses_o))})
+    errs["d_x32"] = rel_l2(d_x32, x32r.grad.permute(0, 2, 3, 1))
+    errs["d_c4"] = rel_l2(d_c4[..., :1024], featr[0].grad.permute(0, 2, 3, 1))
+    errs["d_c3"] = rel_l2(d_c3[..., :512], featr[1].grad.permute(0, 2, 3, 1))
+    grads = br.grads()
+    perr = {k: rel_l2(grads[k], v.grad) for k, v in sdr.items() if v.is_floating_point() and v.grad is not None}
+    missing = [k for k, v in sdr.items() if v.is_floating_point() and v.grad is not None and k not in grads]
+    assert not missing, missing
+    worst = sorted(perr.items(), key=lambda kv: -kv[1])[:5]
+    print("dense branch parity:", {k: round(v, 4) for k, v in errs.items()}, "worst parameter gradients:", worst)
+    assert all(v < 5e-2 for k, v in errs.items() if k.startswith(("depth", "loss"))), errs
+    assert errs["d_x32"] < 0.15 and errs["d_c4"] < 0.15 and errs["d_c3"] < 0.15, errs
+    assert worst[0][1] < 0.15, worst
