@@ -92,8 +92,9 @@ def test_token_attention_bwd(heads, td, tc, N, items):
     assert rel_l2(g_gkv, gr.grad) < 6e-3
 
 
-@pytest.mark.parametrize("stage,C,depth,B,H,W", [(3, 64, 1, 2, 10, 12), (2, 128, 2, 1, 14, 9), (1, 256, 2, 1, 7, 8)])
-def test_class_stage_gradients_match_oracle_autograd(stage, C, depth, B, H, W):
+@pytest.mark.parametrize("stage,C,depth,B,H,W,tok_scale", [(3, 64, 1, 2, 10, 12, 1.0), (2, 128, 2, 1, 14, 9, 1.0), (1, 256, 2, 1, 7, 8, 1.0),
+                                                          (3, 64, 1, 1, 32, 40, 1.0), (3, 64, 1, 1, 32, 40, 0.01), (3, 64, 1, 1, 32, 40, 100.0)])
+def test_class_stage_gradients_match_oracle_autograd(stage, C, depth, B, H, W, tok_scale):
     """train_swin.ClassStage (forward + backward) against torch.autograd over the oracle's `swin_stage` with class tokens:
     the three output streams, the gradients of the three input streams and of every live parameter (window padding, the
     shifted block with its mask, relative-position bias tables, the shared proj_dth)"""
@@ -105,6 +106,7 @@ def test_class_stage_gradients_match_oracle_autograd(stage, C, depth, B, H, W):
     td, L = 64, H * W
     x, d, s = (torch.randn(B * L, n, generator=g).bfloat16() for n in (C, td, td))
     gx, gd, gs = (torch.randn(B * L, n, generator=g).bfloat16() for n in (C, td, td))
+    gd, gs = (gd.float() * tok_scale).bfloat16(), (gs.float() * tok_scale).bfloat16()      # cross paths must be right at any ratio
     xr, dr, sr = (t.float().view(B, L, -1).requires_grad_(True) for t in (x, d, s))
     sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
     xo, do, so = oracle.swin_stage(xr, H, W, oracle.P(sdr, prefix), depth, 16, 7, dtok=dr, stok=sr)
@@ -129,7 +131,7 @@ def test_class_stage_gradients_match_oracle_autograd(stage, C, depth, B, H, W):
             continue
         e = rel_l2(grads[k], v.grad)
         if e > 6e-2:
-            bad[k] = e
+            bad[k] = round(e, 3)
     assert not bad, bad
 
 
@@ -209,43 +211,83 @@ def _oracle_dense_branch(sdr, x32, feats, coords1, coords2, depth_gt, seg_gt, si
     return depths + [depth], seg, losses
 
 
-def test_dense_branch_gradients_match_oracle_autograd():
-    """train_branch.DenseBranch (three class-window stages + entries + coarse depth head + both point predictions + dense head +
-    five losses) against torch.autograd over the oracle's functions chained as `dense_encoder` chains them: losses, the four
-    depth maps, d(x32), d(C4), d(C3) and every live parameter gradient of the dense branch behind the 1/32 stage"""
-    _ops()
-    from gwdepth_b200.train_branch import DenseBranch
+def _branch_case():
     B, h5, w5 = 1, 4, 5
-    H, W = 32 * h5, 32 * w5
     g = _g(77)
     x32 = torch.randn(B, h5, w5, 512, generator=g).bfloat16()
     feats = [torch.randn(B, (2 ** k) * h5, (2 ** k) * w5, c, generator=g).bfloat16() for k, c in ((1, 1024), (2, 512), (3, 256))]
     coords1, coords2 = torch.rand(B, 30, 2, generator=g) * 2 - 1, torch.rand(B, 80, 2, generator=g) * 2 - 1
-    depth_gt = torch.rand(B, 1, H, W, generator=g) * 10.5 + 0.1
-    seg_gt = (torch.rand(B, 1, H, W, generator=g) > 0.5).long()
+    depth_gt = torch.rand(B, 1, 32 * h5, 32 * w5, generator=g) * 10.5 + 0.1
+    seg_gt = (torch.rand(B, 1, 32 * h5, 32 * w5, generator=g) > 0.5).long()
+    return x32, feats, coords1, coords2, depth_gt, seg_gt
+
+
+def _oracle_branch_grads(sd, emulate_bf16):
+    """losses, depth maps and all gradients of the oracle chain; emulate_bf16: weights and the outputs of every linear / conv /
+    LayerNorm / activation rounded to bf16 (straight-through), i.e. the oracle run at the CUDA path's storage precision"""
+    x32, feats, coords1, coords2, depth_gt, seg_gt = _branch_case()
+    H, W = depth_gt.shape[-2:]
+    rnd = lambda t: t + (t.bfloat16().float() - t).detach()  # noqa: E731
+    sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    use = {k: (rnd(v) if (emulate_bf16 and v.is_floating_point() and v.dim() > 1) else v) for k, v in sdr.items()}
+    nchw = lambda t: t.float().permute(0, 3, 1, 2).clone().requires_grad_(True)  # noqa: E731
+    x32r, featr = nchw(x32), [nchw(f) for f in feats]
+    names = ["linear", "conv2d", "layer_norm", "gelu", "elu"]
+    orig = {n: getattr(F, n) for n in names}
+    try:
+        if emulate_bf16:
+            for n in names:
+                setattr(F, n, (lambda f: (lambda *a, **k: rnd(f(*a, **k))))(orig[n]))
+        depths, seg, losses = _oracle_dense_branch(use, x32r, featr, coords1, coords2, depth_gt, seg_gt, (H, W))
+        sum(losses).backward()
+    finally:
+        for n in names:
+            setattr(F, n, orig[n])
+    grads = {k: v.grad for k, v in sdr.items() if v.is_floating_point() and v.grad is not None}
+    grads.update({"d_x32": x32r.grad.permute(0, 2, 3, 1), "d_c4": featr[0].grad.permute(0, 2, 3, 1), "d_c3": featr[1].grad.permute(0, 2, 3, 1)})
+    return [d.detach() for d in depths], [float(l.detach()) for l in losses], grads
+
+
+def _module_of(k):
+    return ".".join(k.split(".")[:4] if k.startswith("dense_encoder.class_transformer") else k.split(".")[:2])
+
+
+def test_dense_branch_gradients_match_oracle_autograd():
+    """train_branch.DenseBranch (three class-window stages + entries + coarse depth head + both point predictions + dense head +
+    five losses) against torch.autograd over the oracle's functions chained as `dense_encoder` chains them.  Forward values and
+    losses must agree closely.  The gradients of this network are sensitive to bf16 storage (peaked channel soft-maxes in the
+    token attention): the ORACLE ITSELF, run with weights and layer outputs rounded to bf16, moves its Swin-stage gradients by
+    20-50 % -- so the bar for the CUDA path is the distance of that emulated run (per module: <= 1.5 x emulated + 3 %),
+    while modules whose gradients are insensitive (heads, point predictions, pyramids) must match to a few per cent."""
+    _ops()
+    from gwdepth_b200.train_branch import DenseBranch
     live = ("dense_encoder.class_transformer", "dense_encoder.point_based_pred", "dense_encoder.proj_", "dense_encoder.old_",
             "dense_encoder.depth_pred16", "dense_encoder.depth_token", "dense_encoder.seg_token", "depth_decoder.")
     sd = {k: v.clone() for k, v in synth_weights().items() if k.startswith(live)}
-    sdr = {k: (v.clone().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
-    nchw = lambda t: t.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
-    x32r, featr = nchw(x32), [nchw(f) for f in feats]
-    depths_o, seg_o, losses_o = _oracle_dense_branch(sdr, x32r, featr, coords1, coords2, depth_gt, seg_gt, (H, W))
-    sum(losses_o).backward()
+    depths_o, losses_o, g_ref = _oracle_branch_grads(sd, False)
+    _, _, g_emu = _oracle_branch_grads(sd, True)
+    x32, feats, coords1, coords2, depth_gt, seg_gt = _branch_case()
+    B, h5, w5 = x32.shape[:3]
     br = DenseBranch({k: v.cuda() for k, v in sd.items()})
     outs, losses, d_x32, d_c4, d_c3 = br.loss_and_grads(x32.cuda(), torch.zeros(B, h5, w5, device="cuda"), [f.cuda() for f in feats],
                                                         depth_gt.cuda(), seg_gt.cuda(),
                                                         pinned={"sample1": coords1.cuda(), "sample2": coords2.cuda()})
-    errs = {"depth%d" % (i + 1): rel_l2(d_.reshape(-1), o.detach().reshape(-1)) for i, (d_, o) in enumerate(zip(outs["pred_depth"], depths_o))}
-    errs.update({"loss%d" % i: abs(a - float(b)) / abs(float(b)) for i, (a, b) in enumerate(zip(losses.tolist(), losses_o))})
-    errs["d_x32"] = rel_l2(d_x32, x32r.grad.permute(0, 2, 3, 1))
-    errs["d_c4"] = rel_l2(d_c4[..., :1024], featr[0].grad.permute(0, 2, 3, 1))
-    errs["d_c3"] = rel_l2(d_c3[..., :512], featr[1].grad.permute(0, 2, 3, 1))
-    grads = br.grads()
-    perr = {k: rel_l2(grads[k], v.grad) for k, v in sdr.items() if v.is_floating_point() and v.grad is not None}
-    missing = [k for k, v in sdr.items() if v.is_floating_point() and v.grad is not None and k not in grads]
+    for i, (d_, o) in enumerate(zip(outs["pred_depth"], depths_o)):
+        assert rel_l2(d_.reshape(-1), o.reshape(-1)) < 2e-2, i
+    for a, b in zip(losses.tolist(), losses_o):
+        assert abs(a - b) < 5e-3 * abs(b), (losses.tolist(), losses_o)
+    got = dict(br.grads(), d_x32=d_x32, d_c4=d_c4[..., :1024], d_c3=d_c3[..., :512])
+    missing = [k for k in g_ref if k not in got]
     assert not missing, missing
-    worst = sorted(perr.items(), key=lambda kv: -kv[1])[:5]
-    print("dense branch parity:", {k: round(v, 4) for k, v in errs.items()}, "worst parameter gradients:", worst)
-    assert all(v < 5e-2 for k, v in errs.items() if k.startswith(("depth", "loss"))), errs
-    assert errs["d_x32"] < 0.15 and errs["d_c4"] < 0.15 and errs["d_c3"] < 0.15, errs
-    assert worst[0][1] < 0.15, worst
+    e_cuda, e_emu = {}, {}
+    for k, ref in g_ref.items():
+        m = _module_of(k)
+        e_cuda[m] = max(e_cuda.get(m, 0.0), rel_l2(got[k], ref))
+        e_emu[m] = max(e_emu.get(m, 0.0), rel_l2(g_emu[k], ref))
+    print("dense branch gradient distance to the fp32 oracle, per module (CUDA / bf16-emulated oracle):",
+          {m: (round(e_cuda[m], 3), round(e_emu[m], 3)) for m in e_cuda})
+    bad = {m: (e_cuda[m], e_emu[m]) for m in e_cuda if e_cuda[m] > 1.5 * e_emu[m] + 3e-2}
+    assert not bad, bad
+    for m in ("dense_encoder.depth_pred16", "dense_encoder.point_based_pred1", "dense_encoder.point_based_pred2"):
+        assert e_cuda[m] < 7e-2, (m, e_cuda[m])
+    assert all(e < 8e-2 for m, e in e_cuda.items() if m.startswith("depth_decoder.")), e_cuda

@@ -1,0 +1,105 @@
+"""Times the DENSE-BRANCH training step behind the 1/32 stage (train_branch.DenseBranch: three class-window Swin stages with
+their entries, coarse depth head, both point-based predictions + uncertainty sampling, dense head, five losses; forward +
+backward + one-norm clip + AdamW) at batch B x 480x640 with CUDA events on the launching stream; optional per-entry-point
+breakdown from events around every C-ABI call of one step.
+    python tools/bench_train_branch.py [--batch 16] [--steps 10] [--breakdown] [--json out.json]"""
+import argparse
+import json
+import os
+import sys
+from collections import defaultdict
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+
+def build(B, H=480, W=640, seed=5):
+    from helpers import synth_weights
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200.train_branch import DenseBranch
+    g = torch.Generator().manual_seed(seed)
+    h5, w5 = H // 32, W // 32
+    x32 = torch.randn(B, h5, w5, 512, generator=g).bfloat16().cuda()
+    depth0 = (torch.rand(B, h5, w5, generator=g) * 0.9 + 0.05).cuda()
+    feats = [torch.randn(B, (2 ** k) * h5, (2 ** k) * w5, c, generator=g).bfloat16().cuda() for k, c in ((1, 1024), (2, 512), (3, 256))]
+    depth_gt = (torch.rand(B, 1, H, W, generator=g) * 9.5 + 0.3).cuda()
+    seg_gt = (torch.rand(B, 1, H, W, generator=g) > 0.5).long().cuda()
+    live = ("dense_encoder.class_transformer", "dense_encoder.point_based_pred", "dense_encoder.proj_", "dense_encoder.old_",
+            "dense_encoder.depth_pred16", "dense_encoder.depth_token", "dense_encoder.seg_token", "depth_decoder.")
+    sd = {k: v.cuda() for k, v in synth_weights().items() if k.startswith(live)}
+    return DenseBranch(sd), (x32, depth0, feats, depth_gt, seg_gt)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=16)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--breakdown", action="store_true")
+    ap.add_argument("--json", default=None)
+    a = ap.parse_args()
+    from bench_train_tail import timed
+    from gwdepth_b200 import capi
+    br, args = build(a.batch)
+    lg = timed(lambda: br.loss_and_grads(*args), a.steps)
+    opt = timed(br.step, a.steps)
+    capi.reset_launch_count()
+    losses = br.train_step(*args)
+    torch.cuda.synchronize()
+    launches = capi.launch_count()
+    full = timed(lambda: br.train_step(*args), a.steps)
+    ms = max(full)
+    res = {"metric": "images_per_sec_train_dense_branch_480x640_bf16", "value": a.batch / (ms / 1000.0), "unit": "images/s",
+           "batch": a.batch, "ms_per_step": ms, "device_ms_per_step": full[0], "host_ms_per_step": full[1],
+           "breakdown_ms": {"forward_losses_backward": lg[0], "allreduce_clip_adamw": opt[0]}, "gpu_launches_per_step": launches,
+           "losses": [float(v) for v in losses.tolist()], "params": int(sum(m.numel for m in br.modules())),
+           "peak_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
+           "scope": "dense branch behind the 1/32 line-window stage: entries + class-window Swin stages at 1/16, 1/8, 1/4, depth_pred16, "
+                    "point_based_pred1/2 (+ PyramidLayer K=30 / 80), CertainSample, DensePrediction head, 4 silog losses + seg CE; "
+                    "gradients returned for x32, C4, C3 (line-window stage / backbone backward not built)"}
+    print(json.dumps(res))
+    if a.json:
+        with open(a.json, "w") as f:
+            json.dump(res, f, indent=1)
+    if a.breakdown:
+        lib = capi.lib()
+        rec = []
+        names = [n for n in capi.SIGNATURES if n not in ("gwd_last_error", "gwd_version", "gwd_launch_count", "gwd_reset_launch_count")]
+        orig = {n: getattr(lib, n) for n in names}
+
+        class Wrapped:
+            def __getattr__(self, n):
+                f = orig.get(n)
+                if f is None:
+                    return getattr(lib, n)
+
+                def call(*cargs):
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    r = f(*cargs)
+                    e1.record()
+                    rec.append((n, e0, e1))
+                    return r
+                return call
+        capi._lib = Wrapped()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        br.train_step(*args)
+        e1.record()
+        torch.cuda.synchronize()
+        capi._lib = lib
+        agg = defaultdict(lambda: [0.0, 0])
+        for n, s0, s1 in rec:
+            agg[n][0] += s0.elapsed_time(s1)
+            agg[n][1] += 1
+        tot = sum(v[0] for v in agg.values())
+        print("per entry point (events around each call, %d calls, %.2f ms inside C-ABI calls of %.2f ms step):" % (len(rec), tot, e0.elapsed_time(e1)))
+        for n, (t, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+            print("  %8.3f ms %5.1f%% x%-3d %s" % (t, 100 * t / tot, c, n))
+
+
+if __name__ == "__main__":
+    main()
