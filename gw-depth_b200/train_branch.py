@@ -92,7 +92,8 @@ class DenseBranch:
         x, d, s = e2.forward(x1.view(B, H1, W1, C1), d1, t1, feats[1])
         x2, d2, t2 = s2.forward(x, d, s, B, H2, W2)
         buf2 = torch.cat([x2, d2], dim=1)
-        depth2 = self.point1.forward(buf2, depth1, coords1.contiguous(), self._table(H2, W2, C2), B, H2, W2)
+        coords1 = coords1.reshape(B, -1, 2).float().contiguous()
+        depth2 = self.point1.forward(buf2, depth1, coords1, self._table(H2, W2, C2), B, H2, W2)
         coords2 = pinned["sample2"] if "sample2" in pinned else ops.certain_sample(depth1, depth2, c["interval_sample_num"][1], self.edges)[0]
         # ---- 1/4 + head + the losses on depth_pred3 / depth / seg
         x, d, s = e3.forward(x2.view(B, H2, W2, C2), d2, t2, feats[2])
@@ -100,8 +101,9 @@ class DenseBranch:
         buf4 = torch.zeros(B, H3, W3, C3 + 3 * td, dtype=torch.bfloat16, device=self.dev)
         b2d = buf4.view(-1, C3 + 3 * td)
         b2d[:, :C3], b2d[:, C3:C3 + td], b2d[:, C3 + td:C3 + 2 * td] = x3, d3, t3
-        depth3, depth, seg, l345, d_buf4, d_depth2 = self.tail.loss_and_grads(buf4, depth2, coords2.contiguous(),
-                                                                              self._table(H3, W3, C3), depth_gt, seg_gt)
+        coords2 = coords2.reshape(B, -1, 2).float().contiguous()
+        depth3, depth, seg, l345, d_buf4, d_depth2 = self.tail.loss_and_grads(buf4, depth2, coords2, self._table(H3, W3, C3),
+                                                                              depth_gt, seg_gt)
         # ---- backward
         g = s3.backward(d_buf4[:, :C3].contiguous(), d_buf4[:, C3:C3 + td].contiguous(), d_buf4[:, C3 + td:C3 + 2 * td].contiguous())
         d_x2, d_d2, d_t2, _ = e3.backward(*g)
