@@ -8,6 +8,8 @@
 // First version on CUDA cores (fp32 in shared memory): a (window, head) problem is 49 x 49 x <= 32 -- 1/40 of the smallest
 // tcgen05 tile -- and the whole pass is ~5 GFMA at the finest scale; CTAs are PERSISTENT over the windows of one head so
 // that the bias gradient is accumulated in registers and reaches HBM as one atomic per entry and CTA.
+#include <stdlib.h>
+#include <algorithm>
 #include "gwd_common.cuh"
 
 namespace {
@@ -204,6 +206,184 @@ __global__ void __launch_bounds__(128) gwd_token_attention_bwd_kernel(const TokB
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-row version for 7 x 7 windows (N = 49) and head dims 4 / 8 / 16 -- the shapes of the three class-window stages.
+// The first kernel above spends its time in shared-memory loads (2 LDS per FMA in every product).  Here a thread OWNS a score
+// row: q_i and dO_i live in registers, k_j / v_j arrive as 16-byte shared-memory BROADCASTS (one LDS serves the warp), the
+// soft-max statistics and D_i = sum_j P_ij dP_ij come from one online pass, a second pass re-forms the scores, emits P and dS
+// into a conflict-free [49][49] transpose buffer (odd row stride) for the column products (dk, dv), accumulates dq in
+// registers and the bias gradient in a shared-memory tile that only its owner thread touches.  A CTA = two 64-thread slots =
+// two heads of the same window (they share the shift mask); CTAs are persistent over the windows of their head pair, with
+// the two bias tables resident in shared memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWN = 49;
+
+template <int HD>
+__device__ __forceinline__ void load_row_bf16(const bf16* src, float* dst) {
+  if constexpr (HD == 4) {
+    const uint2 u = *reinterpret_cast<const uint2*>(src);
+    const float2 a = gwd_unpack_bf16x2(u.x), b = gwd_unpack_bf16x2(u.y);
+    *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, b.x, b.y);
+  } else {
+#pragma unroll
+    for (int c = 0; c < HD; c += 8) {
+      const uint4 u = *reinterpret_cast<const uint4*>(src + c);
+      const float2 a = gwd_unpack_bf16x2(u.x), b = gwd_unpack_bf16x2(u.y), e = gwd_unpack_bf16x2(u.z), f = gwd_unpack_bf16x2(u.w);
+      *reinterpret_cast<float4*>(dst + c) = make_float4(a.x, a.y, b.x, b.y);
+      *reinterpret_cast<float4*>(dst + c + 4) = make_float4(e.x, e.y, f.x, f.y);
+    }
+  }
+}
+template <int HD>
+__device__ __forceinline__ void store_row_bf16(bf16* dst, const float (&v)[HD], float mul) {
+  if constexpr (HD == 4) {
+    *reinterpret_cast<uint2*>(dst) = make_uint2(gwd_pack_bf16x2(v[0] * mul, v[1] * mul), gwd_pack_bf16x2(v[2] * mul, v[3] * mul));
+  } else {
+#pragma unroll
+    for (int c = 0; c < HD; c += 8)
+      *reinterpret_cast<uint4*>(dst + c) = make_uint4(gwd_pack_bf16x2(v[c] * mul, v[c + 1] * mul), gwd_pack_bf16x2(v[c + 2] * mul, v[c + 3] * mul),
+                                                      gwd_pack_bf16x2(v[c + 4] * mul, v[c + 5] * mul), gwd_pack_bf16x2(v[c + 6] * mul, v[c + 7] * mul));
+  }
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) gwd_window_attention_bwd_rows_kernel(const WinBwdParams p) {
+  extern __shared__ __align__(16) float smr[];
+  constexpr int N = kWN, NN = kWN * kWN;
+  float* sBias = smr;                         // [2][N*N]
+  float* sMask = sBias + 2 * NN;              // [N*N]
+  float* slot0 = sMask + NN + 1;              // keep 16-byte alignment: 3 * NN + 1 = 7204 floats
+  const int slot = threadIdx.x >> 6, t = threadIdx.x & 63;
+  const int h = 2 * blockIdx.x + slot;
+  float* sq = slot0 + slot * (4 * N * HD + 3 * NN + 1);           // + 1: 4 N HD + 3 NN + 1 is a multiple of 4 (16-byte rows)
+  float* sk = sq + N * HD;
+  float* sv = sk + N * HD;
+  float* sdo = sv + N * HD;
+  float* sP = sdo + N * HD;                   // [N][N]
+  float* sdS = sP + NN;
+  float* sDb = sdS + NN;                      // [N][N] bias-gradient accumulator of this slot's head (row t owned by thread t)
+  for (int e = threadIdx.x; e < 2 * NN; e += 128)
+    sBias[e] = p.bias ? p.bias[static_cast<int64_t>(2 * blockIdx.x) * NN + e] : 0.f;
+  for (int e = t; e < NN; e += 64) sDb[e] = 0.f;
+  const bool row = t < N;
+  const float* bias_row = sBias + slot * NN + (row ? t : 0) * N;
+
+  for (int item = blockIdx.y; item < p.items; item += gridDim.y) {
+    const int64_t row0 = static_cast<int64_t>(item) * N;
+    if (row) {
+      const bf16* r = p.qkv + (row0 + t) * p.qkv_rs + h * HD;
+      load_row_bf16<HD>(r, sq + t * HD);
+      load_row_bf16<HD>(r + p.C, sk + t * HD);
+      load_row_bf16<HD>(r + 2 * p.C, sv + t * HD);
+      load_row_bf16<HD>(p.d_o + (row0 + t) * p.do_rs + h * HD, sdo + t * HD);
+    }
+    if (p.mask) {
+      const float* mw = p.mask + static_cast<int64_t>(item % p.mask_windows) * NN;
+      for (int e = threadIdx.x; e < NN; e += 128) sMask[e] = mw[e];
+    }
+    __syncthreads();
+    if (row) {
+      float q[HD], g[HD];
+#pragma unroll
+      for (int c = 0; c < HD; c += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(sq + t * HD + c), b = *reinterpret_cast<const float4*>(sdo + t * HD + c);
+        q[c] = a.x; q[c + 1] = a.y; q[c + 2] = a.z; q[c + 3] = a.w;
+        g[c] = b.x; g[c + 1] = b.y; g[c + 2] = b.z; g[c + 3] = b.w;
+      }
+      // pass 1 (online): row max m, l = sum_j e^(s_j - m), acc = sum_j e^(s_j - m) dP_j  ->  D = acc / l
+      float m = -INFINITY, l = 0.f, acc = 0.f;
+#pragma unroll 7
+      for (int j = 0; j < N; ++j) {
+        float a = 0.f, b = 0.f;
+#pragma unroll
+        for (int c = 0; c < HD; c += 4) {
+          const float4 kk = *reinterpret_cast<const float4*>(sk + j * HD + c), vv = *reinterpret_cast<const float4*>(sv + j * HD + c);
+          a = fmaf(q[c], kk.x, a); a = fmaf(q[c + 1], kk.y, a); a = fmaf(q[c + 2], kk.z, a); a = fmaf(q[c + 3], kk.w, a);
+          b = fmaf(g[c], vv.x, b); b = fmaf(g[c + 1], vv.y, b); b = fmaf(g[c + 2], vv.z, b); b = fmaf(g[c + 3], vv.w, b);
+        }
+        a = fmaf(a, p.scale, bias_row[j]);
+        if (p.mask) a += sMask[t * N + j];
+        const float mn = fmaxf(m, a);
+        const float corr = __expf(m - mn), e = __expf(a - mn);
+        l = fmaf(l, corr, e);
+        acc = fmaf(acc, corr, e * b);
+        m = mn;
+      }
+      const float inv = 1.f / l, dsum = acc * inv;
+      // pass 2: P_j, dS_j = P_j (dP_j - D) -> shared memory (for the column products), bias gradient, dq
+      float dq[HD];
+#pragma unroll
+      for (int c = 0; c < HD; ++c) dq[c] = 0.f;
+#pragma unroll 7
+      for (int j = 0; j < N; ++j) {
+        float a = 0.f, b = 0.f;
+        float4 kk[HD / 4];
+#pragma unroll
+        for (int c = 0; c < HD; c += 4) {
+          kk[c / 4] = *reinterpret_cast<const float4*>(sk + j * HD + c);
+          const float4 vv = *reinterpret_cast<const float4*>(sv + j * HD + c);
+          a = fmaf(q[c], kk[c / 4].x, a); a = fmaf(q[c + 1], kk[c / 4].y, a); a = fmaf(q[c + 2], kk[c / 4].z, a); a = fmaf(q[c + 3], kk[c / 4].w, a);
+          b = fmaf(g[c], vv.x, b); b = fmaf(g[c + 1], vv.y, b); b = fmaf(g[c + 2], vv.z, b); b = fmaf(g[c + 3], vv.w, b);
+        }
+        a = fmaf(a, p.scale, bias_row[j]);
+        if (p.mask) a += sMask[t * N + j];
+        const float pr = __expf(a - m) * inv;
+        const float ds = pr * (b - dsum);
+        sP[t * N + j] = pr;
+        sdS[t * N + j] = ds;
+        sDb[t * N + j] += ds;
+#pragma unroll
+        for (int c = 0; c < HD; c += 4) {
+          dq[c] = fmaf(ds, kk[c / 4].x, dq[c]); dq[c + 1] = fmaf(ds, kk[c / 4].y, dq[c + 1]);
+          dq[c + 2] = fmaf(ds, kk[c / 4].z, dq[c + 2]); dq[c + 3] = fmaf(ds, kk[c / 4].w, dq[c + 3]);
+        }
+      }
+      store_row_bf16<HD>(p.dqkv + (row0 + t) * p.dqkv_rs + h * HD, dq, p.scale);
+    }
+    __syncthreads();
+    if (row) {      // thread = key / value row j: column sums over the query rows
+      float dk[HD], dv[HD];
+#pragma unroll
+      for (int c = 0; c < HD; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
+#pragma unroll 7
+      for (int i = 0; i < N; ++i) {
+        const float ds = sdS[i * N + t], pr = sP[i * N + t];
+#pragma unroll
+        for (int c = 0; c < HD; c += 4) {
+          const float4 qq = *reinterpret_cast<const float4*>(sq + i * HD + c), gg = *reinterpret_cast<const float4*>(sdo + i * HD + c);
+          dk[c] = fmaf(ds, qq.x, dk[c]); dk[c + 1] = fmaf(ds, qq.y, dk[c + 1]); dk[c + 2] = fmaf(ds, qq.z, dk[c + 2]); dk[c + 3] = fmaf(ds, qq.w, dk[c + 3]);
+          dv[c] = fmaf(pr, gg.x, dv[c]); dv[c + 1] = fmaf(pr, gg.y, dv[c + 1]); dv[c + 2] = fmaf(pr, gg.z, dv[c + 2]); dv[c + 3] = fmaf(pr, gg.w, dv[c + 3]);
+        }
+      }
+      bf16* o = p.dqkv + (row0 + t) * p.dqkv_rs + h * HD;
+      store_row_bf16<HD>(o + p.C, dk, p.scale);
+      store_row_bf16<HD>(o + 2 * p.C, dv, 1.f);
+    }
+    __syncthreads();
+  }
+  if (p.dbias) {
+    __syncthreads();
+    float* dst = p.dbias + static_cast<int64_t>(h) * NN;
+    for (int e = t; e < NN; e += 64) atomicAdd(dst + e, sDb[e]);
+  }
+}
+
+template <int HD>
+int launch_rows(const WinBwdParams& p, cudaStream_t stream) {
+  const size_t smem = sizeof(float) * (3 * kWN * kWN + 1 + 2 * (4 * kWN * HD + 3 * kWN * kWN + 1));
+  static bool attr_set = false;
+  if (!attr_set) {
+    GWD_CUDA(cudaFuncSetAttribute(gwd_window_attention_bwd_rows_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr_set = true;
+  }
+  const int pairs = p.heads / 2;
+  int per = std::max(1, (gwd_num_sms() * 2) / pairs);
+  per = std::min(per, p.items);
+  gwd_window_attention_bwd_rows_kernel<HD><<<dim3(pairs, per), 128, smem, stream>>>(p);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
 }  // namespace
 
 #define GWD_STREAM cudaStream_t stream = static_cast<cudaStream_t>(stream_)
@@ -222,6 +402,14 @@ extern "C" int gwd_window_attention_bwd(const void* qkv, int64_t qkv_rs, const v
   p.items = items; p.heads = heads; p.N = N; p.hd = hd; p.C = heads * hd; p.mask_windows = mask_windows > 0 ? mask_windows : 1;
   p.qkv_rs = qkv_rs; p.do_rs = do_rs; p.dqkv_rs = dqkv_rs; p.scale = scale;
   GWD_CHECK_ARG(qkv_rs >= 3 * p.C && dqkv_rs >= 3 * p.C && do_rs >= p.C, "gwd_window_attention_bwd: row strides too small");
+  static const bool generic_only = [] { const char* e = getenv("GWD_WINBWD"); return e && e[0] == 'g'; }();
+  const bool aligned = ((reinterpret_cast<uintptr_t>(qkv) | reinterpret_cast<uintptr_t>(d_o) | reinterpret_cast<uintptr_t>(dqkv)) & 15) == 0 &&
+                       qkv_rs % 8 == 0 && do_rs % 8 == 0 && dqkv_rs % 8 == 0;
+  if (!generic_only && N == kWN && heads % 2 == 0 && aligned) {
+    if (hd == 4) return launch_rows<4>(p, stream);
+    if (hd == 8) return launch_rows<8>(p, stream);
+    if (hd == 16) return launch_rows<16>(p, stream);
+  }
   const size_t smem = sizeof(float) * (4 * N * (hd + 1) + 2 * N * (N + 1) + N);
   static bool attr_set = false;
   if (!attr_set) {
