@@ -331,8 +331,9 @@ def main():
         if world > 1:
             dist.destroy_process_group()
         return
-    # ------------------------------------------------------------ dense-tail training step (extra key, rank 0, one GPU's batch)
-    # measured in a child process: its 9 GB of activations and any fault stay out of the headline measurement
+    # ------------------------------------------------------------ dense-branch training step (extra key, rank 0, one GPU's batch)
+    # (everything behind the 1/32 stage: tools/bench_train_branch.py) measured in a child process: its 13 GB of activations
+    # and any fault stay out of the headline measurement
     train_tail = None
     if not args.no_train:
         try:
@@ -344,7 +345,7 @@ def main():
                                                                 os.environ["CUDA_VISIBLE_DEVICES"].split(",")[dev.index]))
                 for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
                     env.pop(k, None)
-                subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_train_tail.py"), "--batch", str(B), "--steps",
+                subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_train_branch.py"), "--batch", str(B), "--steps",
                                 str(max(5, min(args.steps, 10))), "--json", out], check=True, timeout=600, env=env,
                                stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
                 with open(out) as f:
@@ -383,7 +384,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                     "pipeline": "model.infer_stream: 3 streams, double-buffered H2D / forward / D2H"},
             "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
-            "gpu_eager_port": eager, "e2e_uint8_inputs": e2e_uint8, "train_line_branch": train_line, "train_dense_tail": train_tail}
+            "gpu_eager_port": eager, "e2e_uint8_inputs": e2e_uint8, "train_line_branch": train_line, "train_dense_branch": train_tail}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
