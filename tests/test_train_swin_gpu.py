@@ -291,3 +291,39 @@ def test_dense_branch_gradients_match_oracle_autograd():
     for m in ("dense_encoder.depth_pred16", "dense_encoder.point_based_pred1", "dense_encoder.point_based_pred2"):
         assert e_cuda[m] < 7e-2, (m, e_cuda[m])
     assert all(e < 8e-2 for m, e in e_cuda.items() if m.startswith("depth_decoder.")), e_cuda
+
+
+def test_dense_branch_forward_equals_the_inference_engine_on_real_activations():
+    """train_branch.DenseBranch fed with the inference engine's own x32 / depth_pred32 / backbone maps of a synthetic image batch
+    (sample points pinned to the engine's) reproduces the engine's four depth maps and seg logits: the training forward (un-folded
+    weights, soft-max scale as a kernel argument, separate token streams) and the parity-tested inference forward are the same
+    function on real data; then one optimizer step lowers the summed dense loss on that batch."""
+    _ops()
+    from helpers import synth
+    from gwdepth_b200 import model as M
+    from gwdepth_b200.train_branch import DenseBranch
+    net, _, _ = M.build_model(M.default_args(device="cuda"))
+    sd = synth_weights()
+    net.load_state_dict(sd)
+    net.cuda().eval()
+    B, H, W = 2, 224, 320
+    images, _, depth_gt, seg_gt = synth.synth_batch(B, H, W, seed=1)
+    eng = net.plan()
+    trace = {}
+    with torch.no_grad():
+        out = eng.forward(images.cuda().float().contiguous(), trace=trace)
+        feats = eng.backbone(images.cuda().float().contiguous())
+    h5, w5 = feats[3].shape[1:3]
+    br = DenseBranch({k: v.cuda() for k, v in sd.items()}, lr=1e-4, max_norm=0.1)
+    args = (trace["x32"].view(B, h5, w5, -1).contiguous(), trace["depth0"].contiguous(), [feats[2], feats[1], feats[0]],
+            depth_gt.cuda().float(), seg_gt.cuda().long().view(B, 1, H, W))
+    pinned = {"sample1": trace["sample1"].cuda(), "sample2": trace["sample2"].cuda()}
+    outs, losses, d_x32, d_c4, d_c3 = br.loss_and_grads(*args, pinned=pinned)
+    for i, (a, b) in enumerate(zip(outs["pred_depth"], out["pred_depth"])):
+        assert rel_l2(a.reshape(-1), b.reshape(-1)) < 2e-2, i
+    assert rel_l2(outs["pred_seg"], out["pred_seg"]) < 3e-2
+    assert all(torch.isfinite(t.float()).all() for t in (d_x32, d_c4, d_c3, losses))
+    first = float(losses.sum())
+    for _ in range(6):
+        last = float(br.train_step(*args, pinned=pinned).sum())
+    assert last < first, (first, last)
