@@ -17,6 +17,16 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 
+def init_dist():
+    """one process per GPU under torchrun (NCCL over NVLink); returns (rank, world)"""
+    if int(os.environ.get("WORLD_SIZE", "1")) <= 1:
+        return 0, 1
+    import torch.distributed as dist
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0"))))
+    return dist.get_rank(), dist.get_world_size()
+
+
 def build(B, H=480, W=640, seed=5):
     from helpers import synth_weights
     import gwdepth_b200  # noqa: F401
@@ -42,8 +52,9 @@ def main():
     ap.add_argument("--json", default=None)
     a = ap.parse_args()
     from bench_train_tail import timed
+    rank, world = init_dist()
     from gwdepth_b200 import capi
-    br, args = build(a.batch)
+    br, args = build(a.batch, seed=5 + rank)          # same weights on every rank, a different batch per rank
     lg = timed(lambda: br.loss_and_grads(*args), a.steps)
     opt = timed(br.step, a.steps)
     capi.reset_launch_count()
@@ -52,7 +63,24 @@ def main():
     launches = capi.launch_count()
     full = timed(lambda: br.train_step(*args), a.steps)
     ms = max(full)
-    res = {"metric": "images_per_sec_train_dense_branch_480x640_bf16", "value": a.batch / (ms / 1000.0), "unit": "images/s",
+    replicas_equal = None
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        # data-parallel invariant: after the same number of steps every rank holds bit-identical parameters
+        replicas_equal = True
+        for m in br.modules():
+            ref = m.P.clone()
+            dist.broadcast(ref, 0)
+            replicas_equal = replicas_equal and bool(torch.equal(ref, m.P))
+        flag = torch.tensor([1.0 if replicas_equal else 0.0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        replicas_equal = bool(flag.item() == 1.0)
+    res = {"metric": "images_per_sec_train_dense_branch_480x640_bf16", "value": world * a.batch / (ms / 1000.0), "unit": "images/s",
+           "n_gpus": world, "replicas_bit_identical_after_training": replicas_equal,
+           "allreduce_bytes_per_step": int(sum(m.numel for m in br.modules())) * 4 if world > 1 else 0,
            "batch": a.batch, "ms_per_step": ms, "device_ms_per_step": full[0], "host_ms_per_step": full[1],
            "breakdown_ms": {"forward_losses_backward": lg[0], "allreduce_clip_adamw": opt[0]}, "gpu_launches_per_step": launches,
            "losses": [float(v) for v in losses.tolist()], "params": int(sum(m.numel for m in br.modules())),
@@ -60,7 +88,13 @@ def main():
            "scope": "dense branch behind the 1/32 line-window stage: entries + class-window Swin stages at 1/16, 1/8, 1/4, depth_pred16, "
                     "point_based_pred1/2 (+ PyramidLayer K=30 / 80), CertainSample, DensePrediction head, 4 silog losses + seg CE; "
                     "gradients returned for x32, C4, C3 (line-window stage / backbone backward not built)"}
-    print(json.dumps(res))
+    if rank == 0:
+        print(json.dumps(res))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     if a.json:
         with open(a.json, "w") as f:
             json.dump(res, f, indent=1)
