@@ -1251,9 +1251,56 @@ extern "C" int gwd_adamw_step(float* p, const float* g, float* m, float* v, void
 static int launch_wgrad(const void* dy, int64_t dy_rs, const void* x, int64_t x_rs, int64_t rows, int32_t N, int32_t K, float* dw,
                         int64_t dw_rs, float* db, int H, int W, int sy, int sx, cudaStream_t stream);
 
+int gwd_linear_wgrad_tc_try(const void* dy, int64_t dy_rs, const void* x, int64_t x_rs, int64_t rows, int N, int K, float* dw,
+                            int64_t dw_rs, cudaStream_t stream);     // gwd_wgrad_tc.cu (tcgen05 path)
+
+namespace {
+// db[n] += sum_r dY[r][n]: 8 columns per thread, a slab of rows per CTA row, one atomic per column and CTA
+__global__ void __launch_bounds__(256) gwd_colsum_kernel(const bf16* __restrict__ dy, int64_t dy_rs, int64_t rows, int N,
+                                                         float* __restrict__ db) {
+  __shared__ float red[8][32][8];
+  const int cv = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int c = (blockIdx.x * 32 + cv) * 8;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (c < N)
+    for (int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + ry; r < rows; r += static_cast<int64_t>(gridDim.y) * 8) {
+      float f[8];
+      ld8(dy + r * dy_rs + c, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += f[i];
+    }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[ry][cv][i] = acc[i];
+  __syncthreads();
+  if (ry == 0 && c < N) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) t += red[w][cv][i];
+      atomicAdd(db + c + i, t);
+    }
+  }
+}
+}  // namespace
+
 extern "C" int gwd_linear_wgrad(const void* dy, int64_t dy_rs, const void* x, int64_t x_rs, int64_t rows, int32_t N, int32_t K,
                                 float* dw, int64_t dw_rs, float* db, void* stream_) {
   GWD_STREAM;
+  // many-row Linears (window tokens of the 1/4- and 1/8-scale Swin stages): tcgen05 kernel of gwd_wgrad_tc.cu + a column-sum pass
+  static const bool force_mma = [] { const char* e = getenv("GWD_WGRAD"); return e && strcmp(e, "mma") == 0; }();
+  if (!force_mma && dy && x && dw && N % 8 == 0) {
+    const int rc = gwd_linear_wgrad_tc_try(dy, dy_rs, x, x_rs, rows, N, K, dw, dw_rs, stream);
+    if (rc < 0) return rc;
+    if (rc == 0) {
+      if (db != nullptr) {
+        const dim3 grid(static_cast<unsigned>(gwd_ceil_div(N, 256)), static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(rows, 64), 2 * gwd_num_sms())));
+        gwd_colsum_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, rows, N, db);
+        GWD_LAUNCHED();
+      }
+      return GWD_OK;
+    }
+  }
   return launch_wgrad(dy, dy_rs, x, x_rs, rows, N, K, dw, dw_rs, db, 0, 0, 0, 0, stream);
 }
 

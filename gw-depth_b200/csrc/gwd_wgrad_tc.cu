@@ -37,6 +37,9 @@ struct WgTcParams {
   int n_tile;                // N-side tile width (multiple of 16, <= 256)
   int m_tiles, n_tiles, splits;
   int B, H, W, tiles_x, tiles_y, chunks;
+  int taps;                  // 9: 3x3 convolution (tap = blockIdx-derived shift of the X box); 1: Linear (no shift)
+  int tw, th;                // pixel block of one 64-pixel chunk: 16 x 4 (maps) or 64 x 1 (plain row matrices)
+  int64_t dw_rs;             // row stride of dW (floats)
   uint32_t tmem_cols;
 };
 
@@ -117,7 +120,7 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
   const int nt = u % p.n_tiles; u /= p.n_tiles;
   const int mt = u % p.m_tiles; u /= p.m_tiles;
   const int tap = u;                                   // dx * 3 + dy
-  const int sx = tap / 3 - 1, sy = tap % 3 - 1;
+  const int sx = p.taps == 9 ? tap / 3 - 1 : 0, sy = p.taps == 9 ? tap % 3 - 1 : 0;
   const int per = (p.chunks + p.splits - 1) / p.splits;
   const int q_begin = split * per, q_end = min(p.chunks, q_begin + per);
   const int iters = q_end - q_begin;
@@ -163,7 +166,7 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
         int q = q_begin + it;
         const int tx = q % p.tiles_x; q /= p.tiles_x;
         const int ty = q % p.tiles_y; q /= p.tiles_y;
-        const int x0 = tx * kTW, y0 = ty * kTH, b = q;
+        const int x0 = tx * p.tw, y0 = ty * p.th, b = q;
         const uint32_t base = smem_u32(smem + s * stage_bytes);
         mbar_expect_tx(full + s, bytes);
         for (int a = 0; a < m_atoms; ++a)
@@ -197,13 +200,13 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
     const int m = warp * 32 + lane;
     const bool row_ok = m < m_valid;
     const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
-    float* dw_tap = p.dw + static_cast<int64_t>(tap) * p.N * p.C;
+    float* dw_tap = p.dw + static_cast<int64_t>(tap) * p.N * p.dw_rs;
     for (int c = 0; c < n_mma; c += 16) {
       uint32_t r[16];
       tmem_ld16(t_row + c, r);
       if (!row_ok) continue;
       if (!p.m_is_x) {          // D[m][j] = dW[n0'=m0+m][c = n0+c+j]: 16 consecutive floats of one row
-        float* dst = dw_tap + static_cast<int64_t>(m0 + m) * p.C + n0 + c;
+        float* dst = dw_tap + static_cast<int64_t>(m0 + m) * p.dw_rs + n0 + c;
 #pragma unroll
         for (int j = 0; j < 16; j += 4)
           if (c + j < n_valid)    // channel counts are multiples of 4 here (checked on the host)
@@ -212,7 +215,7 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
       } else {                  // D[m][j] = dW[n = n0+c+j][c = m0+m]: lanes of a warp are contiguous in c
 #pragma unroll
         for (int j = 0; j < 16; ++j)
-          if (c + j < n_valid) atomicAdd(dw_tap + static_cast<int64_t>(n0 + c + j) * p.C + m0 + m, __uint_as_float(r[j]));
+          if (c + j < n_valid) atomicAdd(dw_tap + static_cast<int64_t>(n0 + c + j) * p.dw_rs + m0 + m, __uint_as_float(r[j]));
       }
     }
   }
@@ -242,10 +245,10 @@ EncodeTiledFn encode_fn() {
 
 // 4D map over a channels-last bf16 map [B,H,W,cs] restricted to its first `ch` channels:
 // box = 64 channels x 16 x 4 pixels of one image, 128-byte swizzle, zero fill outside the map
-int make_map(CUtensorMap* m, const void* base, int B, int H, int W, int64_t cs, int ch) {
+int make_map(CUtensorMap* m, const void* base, int B, int H, int W, int64_t cs, int ch, int tw = kTW, int th = kTH) {
   cuuint64_t gdim[4] = {static_cast<cuuint64_t>(ch), static_cast<cuuint64_t>(W), static_cast<cuuint64_t>(H), static_cast<cuuint64_t>(B)};
   cuuint64_t gstr[3] = {static_cast<cuuint64_t>(cs) * 2, static_cast<cuuint64_t>(cs) * 2 * W, static_cast<cuuint64_t>(cs) * 2 * W * H};
-  cuuint32_t box[4] = {64, kTW, kTH, 1};
+  cuuint32_t box[4] = {64, static_cast<cuuint32_t>(tw), static_cast<cuuint32_t>(th), 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gdim, gstr, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -264,27 +267,18 @@ int64_t padded_work(int m_cnt, int n_cnt) {
 
 // returns 1 when the problem is not eligible for the tensor-core path (the caller falls back to the mma.sync kernels),
 // 0 on success, a negative gwd error code otherwise
-int gwd_conv3x3_wgrad_tc_try(const void* dy, int64_t dy_cs, const void* x, int64_t x_cs, int B, int H, int W, int N, int C,
-                             float* dw, cudaStream_t stream) {
-  if (N % 16 || C % 16 || (N <= 64 && C <= 64) || N > 1024 || C > 1024) return 1;
-  if (H < kTH || W < kTW || static_cast<int64_t>(B) * H * W < 4096) return 1;
-  if (dy_cs % 8 || x_cs % 8 || dy_cs < N || x_cs < C) return 1;
-  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dw)) & 15) return 1;
-  if (!encode_fn()) return 1;
-  WgTcParams p;
-  memset(&p, 0, sizeof(p));
-  p.dw = dw; p.N = N; p.C = C;
+static int launch_tc(WgTcParams& p, const void* dy, int64_t dy_cs, const void* x, int64_t x_cs, cudaStream_t stream) {
+  const int N = p.N, C = p.C;
   p.m_is_x = padded_work(C, N) < padded_work(N, C) ? 1 : 0;
   p.m_cnt = p.m_is_x ? C : N;
   p.n_cnt = p.m_is_x ? N : C;
   p.m_tiles = (p.m_cnt + 127) / 128;
   p.n_tiles = (p.n_cnt + 255) / 256;
   p.n_tile = ((p.n_cnt + p.n_tiles - 1) / p.n_tiles + 15) & ~15;
-  p.B = B; p.H = H; p.W = W;
-  p.tiles_x = (W + kTW - 1) / kTW;
-  p.tiles_y = (H + kTH - 1) / kTH;
-  p.chunks = B * p.tiles_x * p.tiles_y;
-  const int units = 9 * p.m_tiles * p.n_tiles;
+  p.tiles_x = (p.W + p.tw - 1) / p.tw;
+  p.tiles_y = (p.H + p.th - 1) / p.th;
+  p.chunks = p.B * p.tiles_x * p.tiles_y;
+  const int units = p.taps * p.m_tiles * p.n_tiles;
   int splits = (gwd_num_sms() + units / 2) / units;
   splits = max(1, min(splits, p.chunks / 8));
   p.splits = splits;
@@ -292,7 +286,7 @@ int gwd_conv3x3_wgrad_tc_try(const void* dy, int64_t dy_cs, const void* x, int64
   while (cols < static_cast<uint32_t>(p.n_tile)) cols <<= 1;
   p.tmem_cols = cols;
   CUtensorMap map_dy, map_x;
-  if (make_map(&map_dy, dy, B, H, W, dy_cs, N) || make_map(&map_x, x, B, H, W, x_cs, C)) return 1;
+  if (make_map(&map_dy, dy, p.B, p.H, p.W, dy_cs, N, p.tw, p.th) || make_map(&map_x, x, p.B, p.H, p.W, x_cs, C, p.tw, p.th)) return 1;
   const size_t smem = static_cast<size_t>(kStages) * (2 + kMaxNAtoms) * kAtomBytes + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
@@ -303,4 +297,37 @@ int gwd_conv3x3_wgrad_tc_try(const void* dy, int64_t dy_cs, const void* x, int64
   gwd_wgrad_tc_kernel<<<grid, 192, smem, stream>>>(p.m_is_x ? map_x : map_dy, p.m_is_x ? map_dy : map_x, p);
   GWD_LAUNCHED();
   return GWD_OK;
+}
+
+// returns 1 when the problem is not eligible for the tensor-core path (the caller falls back to the mma.sync kernels),
+// 0 on success, a negative gwd error code otherwise
+int gwd_conv3x3_wgrad_tc_try(const void* dy, int64_t dy_cs, const void* x, int64_t x_cs, int B, int H, int W, int N, int C,
+                             float* dw, cudaStream_t stream) {
+  if (N % 16 || C % 16 || (N <= 64 && C <= 64) || N > 1024 || C > 1024) return 1;
+  if (H < kTH || W < kTW || static_cast<int64_t>(B) * H * W < 4096) return 1;
+  if (dy_cs % 8 || x_cs % 8 || dy_cs < N || x_cs < C) return 1;
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dw)) & 15) return 1;
+  if (!encode_fn()) return 1;
+  WgTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.dw = dw; p.N = N; p.C = C; p.dw_rs = C;
+  p.B = B; p.H = H; p.W = W;
+  p.taps = 9; p.tw = kTW; p.th = kTH;
+  return launch_tc(p, dy, dy_cs, x, x_cs, stream);
+}
+
+// Linear weight gradient dW[n][k] += sum_r dY[r][n] X[r][k] over many rows (the 1/4- and 1/8-scale Swin stages: 85 k - 325 k window
+// tokens): the same kernel with one "tap", the row matrices seen as a [C, rows] map walked in 64-row boxes
+int gwd_linear_wgrad_tc_try(const void* dy, int64_t dy_rs, const void* x, int64_t x_rs, int64_t rows, int N, int K, float* dw,
+                            int64_t dw_rs, cudaStream_t stream) {
+  if (N % 16 || K % 16 || N > 1024 || K > 1024 || rows < 32768 || rows >= (1ll << 31)) return 1;
+  if (dy_rs % 8 || x_rs % 8 || dy_rs < N || x_rs < K || dw_rs % 4 || dw_rs < K) return 1;
+  if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dw)) & 15) return 1;
+  if (!encode_fn()) return 1;
+  WgTcParams p;
+  memset(&p, 0, sizeof(p));
+  p.dw = dw; p.N = N; p.C = K; p.dw_rs = dw_rs;
+  p.B = 1; p.H = 1; p.W = static_cast<int>(rows);
+  p.taps = 1; p.tw = 64; p.th = 1;
+  return launch_tc(p, dy, dy_rs, x, x_rs, stream);
 }

@@ -151,9 +151,12 @@ def test_weight_gradient_gemm_on_transposed_operands():
         assert rel_l2(dX, dY.float() @ W.float()) < 6e-3
 
 
-@pytest.mark.parametrize("R,N,K", [(600, 256, 2048), (4800, 2048, 256), (1200, 16, 256), (9600, 256, 256), (70, 512, 264)])
+@pytest.mark.parametrize("R,N,K", [(600, 256, 2048), (4800, 2048, 256), (1200, 16, 256), (9600, 256, 256), (70, 512, 264),
+                                   (40000, 192, 64), (33001, 64, 64), (50000, 384, 192), (40000, 160, 80), (36000, 16, 128)])
 def test_linear_wgrad_kernel(R, N, K):
-    """gwd_linear_wgrad: dW += dY^T X, db += column sums (accumulating into a non-zero buffer), operands read in place"""
+    """gwd_linear_wgrad: dW += dY^T X, db += column sums (accumulating into a non-zero buffer), operands read in place.
+    From 32 768 rows on (N, K multiples of 16) the tcgen05 kernel of gwd_wgrad_tc.cu runs (one "tap", 64-row TMA boxes, both role
+    assignments, a partial last box) with gwd_colsum_kernel for the bias gradient; below, the split-K mma.sync kernel."""
     ops = _ops()
     g = _g(R + N)
     dY = (torch.randn(R, N, generator=g) * 0.1).bfloat16()
