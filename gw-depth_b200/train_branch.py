@@ -24,7 +24,7 @@ from .train_tail import DenseTail
 
 
 class DenseBranch:
-    def __init__(self, state_dict, cfg=None, device="cuda", scale_weights=(0.25, 0.25, 0.25), **optim):
+    def __init__(self, state_dict, cfg=None, device="cuda", scale_weights=(0.25, 0.25, 0.25), cuda_graph=False, **optim):
         self.cfg = c = dict(DEFAULT_CFG, **(cfg or {}))
         self.dev = torch.device(device)
         D, td, nh, ws = c["dense_trans_dim"], c["class_token_dim"], c["dense_trans_heads"], c["window"]
@@ -43,6 +43,10 @@ class DenseBranch:
         self.loss12 = torch.zeros(2, dtype=torch.float32, device=self.dev)
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self._pos = {}
+        # forward + losses + backward have no host synchronisation and no data-dependent control flow: with cuda_graph=True
+        # the ~720 launches are captured once per input shape and replayed as one graph (the optimizer step stays outside:
+        # its bias corrections are host scalars)
+        self.use_cuda_graph, self._graphs = cuda_graph, {}
 
     def modules(self):
         return self.entries + self.stages + [self.head16, self.point1, self.point1.pyramid] + self.tail.modules()
@@ -72,6 +76,33 @@ class DenseBranch:
                              variance_focus=float(self.cfg.get("variance_focus", 0.85)), loss_out=loss_out)
 
     def loss_and_grads(self, x32, depth0, feats, depth_gt, seg_gt, pinned=None):
+        """see _loss_and_grads; replays the captured graph when cuda_graph=True (the returned tensors are then the graph's
+        static outputs: consume them before the next call with the same shapes)"""
+        if not self.use_cuda_graph:
+            return self._loss_and_grads(x32, depth0, feats, depth_gt, seg_gt, pinned)
+        pinned = pinned or {}
+        flat = [x32, depth0, *feats, depth_gt, seg_gt] + [pinned[k] for k in sorted(pinned)]
+        key = tuple((tuple(t.shape), t.dtype) for t in flat) + tuple(sorted(pinned))
+        st = self._graphs.get(key)
+        if st is None:
+            static = [t.clone() for t in flat]
+            call = lambda: self._loss_and_grads(static[0], static[1], static[2:5], static[5], static[6],  # noqa: E731
+                                                dict(zip(sorted(pinned), static[7:])))
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):          # warm-up: lazy kernel attributes, cached tables, transpose tables
+                call()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                result = call()
+            st = self._graphs[key] = dict(graph=graph, static=static, result=result)
+        for dst, src in zip(st["static"], flat):
+            dst.copy_(src, non_blocking=True)
+        st["graph"].replay()
+        return st["result"]
+
+    def _loss_and_grads(self, x32, depth0, feats, depth_gt, seg_gt, pinned=None):
         """x32 bf16 [B,h,w,D] (output of the 1/32 line-window stage); depth0 fp32 [B,h,w] (depth_pred32 of it, only feeds the
         sampling); feats = (C4, C3, C2) bf16 channels-last backbone maps at 1/16, 1/8, 1/4; depth_gt fp32 [B,1,H,W] metres;
         seg_gt int64 [B,1,H,W]; pinned: optional {'sample1', 'sample2'} coordinates overriding the uncertainty sampling.

@@ -41,7 +41,7 @@ def build(B, H=480, W=640, seed=5):
     live = ("dense_encoder.class_transformer", "dense_encoder.point_based_pred", "dense_encoder.proj_", "dense_encoder.old_",
             "dense_encoder.depth_pred16", "dense_encoder.depth_token", "dense_encoder.seg_token", "depth_decoder.")
     sd = {k: v.cuda() for k, v in synth_weights().items() if k.startswith(live)}
-    return DenseBranch(sd), (x32, depth0, feats, depth_gt, seg_gt)
+    return DenseBranch(sd, cuda_graph=os.environ.get("GWD_CUDA_GRAPH", "1") != "0"), (x32, depth0, feats, depth_gt, seg_gt)
 
 
 def main():
@@ -55,13 +55,18 @@ def main():
     rank, world = init_dist()
     from gwdepth_b200 import capi
     br, args = build(a.batch, seed=5 + rank)          # same weights on every rank, a different batch per rank
-    lg = timed(lambda: br.loss_and_grads(*args), a.steps)
-    opt = timed(br.step, a.steps)
+    graphed = br.use_cuda_graph
+    br.use_cuda_graph = False               # launch count and the eager time first
     capi.reset_launch_count()
     losses = br.train_step(*args)
     torch.cuda.synchronize()
     launches = capi.launch_count()
+    eager = timed(lambda: br.train_step(*args), a.steps)
+    br.use_cuda_graph = graphed
+    lg = timed(lambda: br.loss_and_grads(*args), a.steps)
+    opt = timed(br.step, a.steps)
     full = timed(lambda: br.train_step(*args), a.steps)
+    losses = br.train_step(*args).clone()
     ms = max(full)
     replicas_equal = None
     if world > 1:
@@ -83,7 +88,7 @@ def main():
            "allreduce_bytes_per_step": int(sum(m.numel for m in br.modules())) * 4 if world > 1 else 0,
            "batch": a.batch, "ms_per_step": ms, "device_ms_per_step": full[0], "host_ms_per_step": full[1],
            "breakdown_ms": {"forward_losses_backward": lg[0], "allreduce_clip_adamw": opt[0]}, "gpu_launches_per_step": launches,
-           "losses": [float(v) for v in losses.tolist()], "params": int(sum(m.numel for m in br.modules())),
+           "cuda_graph": bool(graphed), "eager_ms_per_step": max(eager), "losses": [float(v) for v in losses.tolist()], "params": int(sum(m.numel for m in br.modules())),
            "peak_memory_gb": torch.cuda.max_memory_allocated() / 2 ** 30,
            "scope": "dense branch behind the 1/32 line-window stage: entries + class-window Swin stages at 1/16, 1/8, 1/4, depth_pred16, "
                     "point_based_pred1/2 (+ PyramidLayer K=30 / 80), CertainSample, DensePrediction head, 4 silog losses + seg CE; "
@@ -119,6 +124,7 @@ def main():
                     return r
                 return call
         capi._lib = Wrapped()
+        br.use_cuda_graph = False           # the per-call events need the eager launch sequence
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         br.train_step(*args)
