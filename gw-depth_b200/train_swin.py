@@ -24,7 +24,7 @@ B200 design
 import torch
 
 from . import ops
-from .engine import rel_pos_bias, shift_mask
+from .engine import shift_mask
 from .ops import ACT_GELU, RES_AFTER, PackedWeight, conv_gemm
 from .train_flat import FlatModule, Linear
 
@@ -136,7 +136,8 @@ class ClassStage(FlatModule):
         for i, blk in enumerate(self.blocks):
             shift = 0 if i % 2 == 0 else ws // 2
             mask = self._mask(H, W) if shift else None
-            bias = rel_pos_bias(self.view(self.P, blk["table"])[:(2 * ws - 1) ** 2], ws, nh)
+            # relative-position bias [heads, N, N] gathered from the fp32 table (device index: no host copy, graph-capturable)
+            bias = self.view(self.P, blk["table"])[self.rel_index].view(N, N, nh).permute(2, 0, 1).contiguous()
             xw = ops.window_gather(x, B, H, W, ws, shift, blk["n1"][0], blk["n1"][1], C=C)
             tx = torch.empty(rows_w, tC, dtype=torch.bfloat16, device=self.dev)          # cat[x_attn, depth tok, seg tok]
             ops.window_gather(d, B, H, W, ws, shift, blk["nd1"][0], blk["nd1"][1], C=td, out=tx, y_coff=C)

@@ -139,6 +139,9 @@ def main():
         print("per entry point (events around each call, %d calls, %.2f ms inside C-ABI calls of %.2f ms step):" % (len(rec), tot, e0.elapsed_time(e1)))
         for n, (t, c) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
             print("  %8.3f ms %5.1f%% x%-3d %s" % (t, 100 * t / tot, c, n))
+        print("slowest calls:")
+        for i, (n, s0, s1) in sorted(enumerate(rec), key=lambda r: -r[1][1].elapsed_time(r[1][2]))[:40]:
+            print("  %8.3f ms %s (call #%d)" % (s0.elapsed_time(s1), n, i))
 
 
 if __name__ == "__main__":
