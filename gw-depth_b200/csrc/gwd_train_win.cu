@@ -384,6 +384,104 @@ int launch_rows(const WinBwdParams& p, cudaStream_t stream) {
   return GWD_OK;
 }
 
+// Warp-per-problem version of the class-token channel attention backward: the CTA-per-(window, head) kernel above spends its
+// time in four block-wide barriers around a few hundred FMAs per thread.  Here every warp owns a (window, head) problem in its
+// own shared-memory slice (__syncwarp only), loads and stores move 8-byte vectors (td and tc are multiples of 4), and the
+// outputs are computed four channels at a time.
+template <int TD>      // token-query channels per head (4 in the reference configuration); rows R = 2 TD
+__global__ void __launch_bounds__(128) gwd_token_attention_bwd_warp_kernel(const TokBwdParams p) {
+  extern __shared__ __align__(16) float smw[];
+  constexpr int R = 2 * TD;
+  const int N = p.N, tc = p.tc;
+  const int tcp = (tc + 4) % 8 == 0 ? tc + 8 : tc + 4;   // row pitch of the key / value tiles: 16-byte aligned, = 4 mod 8 (banks)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* q = smw + warp * (2 * N * R + 2 * N * tcp + 2 * R * tcp);   // [N][R]
+  float* go = q + N * R;                                 // [N][R]
+  float* k = go + N * R;                                 // [N][tcp]
+  float* v = k + N * tcp;                                // [N][tcp]
+  float* a = v + N * tcp;                                // [R][tcp]
+  float* dz = a + R * tcp;                               // [R][tcp]
+  const int c4n = tc >> 2;
+  auto ld4 = [](const bf16* src, float* dst) {
+    const uint2 u = *reinterpret_cast<const uint2*>(src);
+    const float2 x = gwd_unpack_bf16x2(u.x), y = gwd_unpack_bf16x2(u.y);
+    *reinterpret_cast<float4*>(dst) = make_float4(x.x, x.y, y.x, y.y);
+  };
+  const int64_t total = static_cast<int64_t>(p.items) * p.heads;
+  for (int64_t wh = static_cast<int64_t>(blockIdx.x) * 4 + warp; wh < total; wh += static_cast<int64_t>(gridDim.x) * 4) {
+    const int item = static_cast<int>(wh / p.heads), h = static_cast<int>(wh - static_cast<int64_t>(item) * p.heads);
+    const int64_t row0 = static_cast<int64_t>(item) * N;
+    for (int idx = lane; idx < N * (R / 4); idx += 32) {           // query / output-gradient pieces: [depth TD | seg TD]
+      const int n = idx / (R / 4), r4 = (idx - n * (R / 4)) * 4;
+      const bool seg = r4 >= TD;
+      const int c = h * TD + (seg ? r4 - TD : r4);
+      ld4((seg ? p.sq : p.dq) + (row0 + n) * p.q_rs + c, q + n * R + r4);
+      ld4((seg ? p.d_sout : p.d_dout) + (row0 + n) * p.o_rs + c, go + n * R + r4);
+    }
+    for (int idx = lane; idx < N * c4n; idx += 32) {
+      const int n = idx / c4n, c = (idx - n * c4n) * 4;
+      ld4(p.tk + (row0 + n) * p.k_rs + h * tc + c, k + n * tcp + c);
+      ld4(p.tv + (row0 + n) * p.v_rs + h * tc + c, v + n * tcp + c);
+    }
+    __syncwarp();
+    // scores[r][c..c+3] and d a = sum_n go[n][r] v[n][c..c+3]
+    for (int e = lane; e < R * c4n; e += 32) {
+      const int r = e / c4n, c = (e - r * c4n) * 4;
+      float4 sc = make_float4(0.f, 0.f, 0.f, 0.f), da = sc;
+      for (int n = 0; n < N; ++n) {
+        const float qq = q[n * R + r], gg = go[n * R + r];
+        const float4 kk = *reinterpret_cast<const float4*>(k + n * tcp + c), vv = *reinterpret_cast<const float4*>(v + n * tcp + c);
+        sc.x = fmaf(qq, kk.x, sc.x); sc.y = fmaf(qq, kk.y, sc.y); sc.z = fmaf(qq, kk.z, sc.z); sc.w = fmaf(qq, kk.w, sc.w);
+        da.x = fmaf(gg, vv.x, da.x); da.y = fmaf(gg, vv.y, da.y); da.z = fmaf(gg, vv.z, da.z); da.w = fmaf(gg, vv.w, da.w);
+      }
+      *reinterpret_cast<float4*>(a + r * tcp + c) = make_float4(sc.x * p.scale, sc.y * p.scale, sc.z * p.scale, sc.w * p.scale);
+      *reinterpret_cast<float4*>(dz + r * tcp + c) = da;
+    }
+    __syncwarp();
+    if (lane < R) {      // soft-max over the key channels of row `lane` and its backward
+      float* ar = a + lane * tcp;
+      float* dr = dz + lane * tcp;
+      float mx = -INFINITY;
+      for (int c = 0; c < tc; ++c) mx = fmaxf(mx, ar[c]);
+      float sum = 0.f;
+      for (int c = 0; c < tc; ++c) { const float e = __expf(ar[c] - mx); ar[c] = e; sum += e; }
+      const float inv = 1.f / sum;
+      float dsum = 0.f;
+      for (int c = 0; c < tc; ++c) { ar[c] *= inv; dsum = fmaf(ar[c], dr[c], dsum); }
+      for (int c = 0; c < tc; ++c) dr[c] = ar[c] * (dr[c] - dsum) * p.scale;
+    }
+    __syncwarp();
+    // d q[n][r..r+3] = sum_c dz[r..r+3][c] k[n][c]
+    for (int idx = lane; idx < N * (R / 4); idx += 32) {
+      const int n = idx / (R / 4), r4 = (idx - n * (R / 4)) * 4;
+      float o0 = 0.f, o1 = 0.f, o2 = 0.f, o3 = 0.f;
+      for (int c = 0; c < tc; ++c) {
+        const float kk = k[n * tcp + c];
+        o0 = fmaf(dz[r4 * tcp + c], kk, o0); o1 = fmaf(dz[(r4 + 1) * tcp + c], kk, o1);
+        o2 = fmaf(dz[(r4 + 2) * tcp + c], kk, o2); o3 = fmaf(dz[(r4 + 3) * tcp + c], kk, o3);
+      }
+      const bool seg = r4 >= TD;
+      bf16* dst = (seg ? p.g_sq : p.g_dq) + (row0 + n) * p.gq_rs + h * TD + (seg ? r4 - TD : r4);
+      *reinterpret_cast<uint2*>(dst) = make_uint2(gwd_pack_bf16x2(o0, o1), gwd_pack_bf16x2(o2, o3));
+    }
+    // d k[n][c..c+3] = sum_r dz[r][c..c+3] q[n][r];  d v[n][c..c+3] = sum_r a[r][c..c+3] go[n][r]
+    for (int idx = lane; idx < N * c4n; idx += 32) {
+      const int n = idx / c4n, c = (idx - n * c4n) * 4;
+      float4 gk = make_float4(0.f, 0.f, 0.f, 0.f), gv = gk;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float qq = q[n * R + r], gg = go[n * R + r];
+        const float4 zz = *reinterpret_cast<const float4*>(dz + r * tcp + c), aa = *reinterpret_cast<const float4*>(a + r * tcp + c);
+        gk.x = fmaf(zz.x, qq, gk.x); gk.y = fmaf(zz.y, qq, gk.y); gk.z = fmaf(zz.z, qq, gk.z); gk.w = fmaf(zz.w, qq, gk.w);
+        gv.x = fmaf(aa.x, gg, gv.x); gv.y = fmaf(aa.y, gg, gv.y); gv.z = fmaf(aa.z, gg, gv.z); gv.w = fmaf(aa.w, gg, gv.w);
+      }
+      *reinterpret_cast<uint2*>(p.g_tk + (row0 + n) * p.gk_rs + h * tc + c) = make_uint2(gwd_pack_bf16x2(gk.x, gk.y), gwd_pack_bf16x2(gk.z, gk.w));
+      *reinterpret_cast<uint2*>(p.g_tv + (row0 + n) * p.gv_rs + h * tc + c) = make_uint2(gwd_pack_bf16x2(gv.x, gv.y), gwd_pack_bf16x2(gv.z, gv.w));
+    }
+    __syncwarp();
+  }
+}
+
 }  // namespace
 
 #define GWD_STREAM cudaStream_t stream = static_cast<cudaStream_t>(stream_)
@@ -438,6 +536,26 @@ extern "C" int gwd_token_attention_bwd(const void* dq, const void* sq, const voi
   p.items = items; p.N = N; p.heads = heads; p.td = td; p.tc = tc;
   p.q_rs = q_rs; p.k_rs = k_rs; p.v_rs = v_rs; p.o_rs = o_rs; p.gq_rs = gq_rs; p.gk_rs = gk_rs; p.gv_rs = gv_rs; p.scale = scale;
   const int64_t units = static_cast<int64_t>(items) * heads;
+  static const bool generic_only = [] { const char* e = getenv("GWD_TOKBWD"); return e && e[0] == 'g'; }();
+  const bool vec_ok = td == 4 && tc % 4 == 0 && q_rs % 4 == 0 && k_rs % 4 == 0 && v_rs % 4 == 0 && o_rs % 4 == 0 && gq_rs % 4 == 0 &&
+                      gk_rs % 4 == 0 && gv_rs % 4 == 0 &&
+                      ((reinterpret_cast<uintptr_t>(dq) | reinterpret_cast<uintptr_t>(sq) | reinterpret_cast<uintptr_t>(tk) |
+                        reinterpret_cast<uintptr_t>(tv) | reinterpret_cast<uintptr_t>(d_dout) | reinterpret_cast<uintptr_t>(d_sout) |
+                        reinterpret_cast<uintptr_t>(g_dq) | reinterpret_cast<uintptr_t>(g_sq) | reinterpret_cast<uintptr_t>(g_tk) |
+                        reinterpret_cast<uintptr_t>(g_tv)) & 7) == 0;
+  if (vec_ok && !generic_only) {      // warp per (window, head): the reference configuration (token_dim 64 over 16 heads)
+    const int tcp = (tc + 4) % 8 == 0 ? tc + 8 : tc + 4;
+    const size_t smem = sizeof(float) * 4 * (2 * N * 8 + 2 * N * tcp + 2 * 8 * tcp);
+    static bool attr_set = false;
+    if (!attr_set) {
+      GWD_CUDA(cudaFuncSetAttribute(gwd_token_attention_bwd_warp_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      attr_set = true;
+    }
+    const unsigned g = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(units, 4), static_cast<int64_t>(gwd_num_sms()) * 4));
+    gwd_token_attention_bwd_warp_kernel<4><<<g, 128, smem, stream>>>(p);
+    GWD_LAUNCHED();
+    return GWD_OK;
+  }
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(units, static_cast<int64_t>(gwd_num_sms()) * 8));
   gwd_token_attention_bwd_kernel<<<grid, 128, 0, stream>>>(p);
   GWD_LAUNCHED();
