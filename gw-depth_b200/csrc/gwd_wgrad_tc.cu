@@ -9,10 +9,11 @@
 // tiles (64-channel x 64-pixel atoms, 128-byte swizzle, exactly what one TMA box of the channels-last map produces);
 // the tap shift is a coordinate offset of the X box and the zero padding of the convolution is the TMA out-of-bounds fill.
 //
-//   CTA = (tap, 128-row tile of the M-side channels, <=256-column tile of the N-side channels, pixel split), 6 warps:
+//   CTA = (tap, one or TWO 128-row tiles of the M-side channels -- two accumulators in TMEM share every N-side tile load --,
+//          <=256-column tile of the N-side channels, pixel split), 6 warps:
 //     warp 4 (one lane) : TMA producer -- per 64-pixel chunk (16 x 4 pixel block of one image) the M-side and N-side atoms
-//                         into a 4-stage ring (full / empty mbarriers)
-//     warp 5 (one lane) : 4 x tcgen05.mma (M = 128, K = 16 pixels) per chunk, fp32 accumulator [128 x N] in TMEM,
+//                         into a 3-stage ring of 64 KB (full / empty mbarriers)
+//     warp 5 (one lane) : 4 (x 2) x tcgen05.mma (M = 128, K = 16 pixels) per chunk, fp32 accumulators [128 x N] in TMEM,
 //                         tcgen05.commit releases the stage; the last commit signals the epilogue
 //     warps 0..3        : TMEM -> registers -> vector atomics into the flat fp32 gradient buffer (the pixel splits and the
 //                         optimizer's accumulate-into-G contract both want +=)
@@ -24,10 +25,11 @@
 namespace {
 
 typedef __nv_bfloat16 bf16;
-constexpr int kStages = 4;
+constexpr int kStages = 3;
 constexpr int kTW = 16, kTH = 4;                 // pixel block of one chunk (64 pixels = 4 MMA K-steps)
 constexpr int kAtomBytes = 64 * 128;             // 64 pixels x 64 channels bf16
 constexpr int kMaxNAtoms = 4;                    // N tile <= 256 channels
+constexpr int kMaxMAtoms = 4;                    // up to TWO 128-row M tiles per CTA (they share every N-side tile load)
 
 struct WgTcParams {
   float* dw;                 // [9][N][C] (tap-major), += semantics
@@ -36,6 +38,8 @@ struct WgTcParams {
   int m_cnt, n_cnt;          // channel counts of the M-side / N-side operand
   int n_tile;                // N-side tile width (multiple of 16, <= 256)
   int m_tiles, n_tiles, splits;
+  int m_pair, m_units;       // 128-row M tiles per CTA (1 or 2) and CTAs along M
+  uint32_t acc_stride;       // TMEM columns between the two accumulators
   int B, H, W, tiles_x, tiles_y, chunks;
   int taps;                  // 9: 3x3 convolution (tap = blockIdx-derived shift of the X box); 1: Linear (no shift)
   int tw, th;                // pixel block of one 64-pixel chunk: 16 x 4 (maps) or 64 x 1 (plain row matrices)
@@ -118,19 +122,21 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
   int u = blockIdx.x;
   const int split = u % p.splits; u /= p.splits;
   const int nt = u % p.n_tiles; u /= p.n_tiles;
-  const int mt = u % p.m_tiles; u /= p.m_tiles;
+  const int mt = u % p.m_units; u /= p.m_units;
   const int tap = u;                                   // dx * 3 + dy
   const int sx = p.taps == 9 ? tap / 3 - 1 : 0, sy = p.taps == 9 ? tap % 3 - 1 : 0;
   const int per = (p.chunks + p.splits - 1) / p.splits;
   const int q_begin = split * per, q_end = min(p.chunks, q_begin + per);
   const int iters = q_end - q_begin;
   if (iters <= 0) return;
-  const int m0 = mt * 128, n0 = nt * p.n_tile;
+  const int m0 = mt * p.m_pair * 128, n0 = nt * p.n_tile;
   const int m_valid = min(128, p.m_cnt - m0), n_valid = min(p.n_tile, p.n_cnt - n0);
   const int m_atoms = (m_valid + 63) >> 6;             // atoms that hold any valid channel (the rest are never read out)
+  const int m_valid_b = p.m_pair == 2 ? max(0, min(128, p.m_cnt - m0 - 128)) : 0;     // second M tile of this CTA (may be absent)
+  const int m_atoms_b = (m_valid_b + 63) >> 6;
   const int n_mma = (n_valid + 15) & ~15;
   const int n_atoms = (n_mma + 63) >> 6;
-  const int stage_bytes = (2 + kMaxNAtoms) * kAtomBytes;
+  const int stage_bytes = (kMaxMAtoms + kMaxNAtoms) * kAtomBytes;
 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
   uint64_t* full = bars;
@@ -159,7 +165,7 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
       // the shifted operand is X: dY[pixel] meets X[pixel + (sy, sx)]
       const int msx = p.m_is_x ? sx : 0, msy = p.m_is_x ? sy : 0;
       const int nsx = p.m_is_x ? 0 : sx, nsy = p.m_is_x ? 0 : sy;
-      const uint32_t bytes = static_cast<uint32_t>(m_atoms + n_atoms) * kAtomBytes;
+      const uint32_t bytes = static_cast<uint32_t>(m_atoms + m_atoms_b + n_atoms) * kAtomBytes;
       for (int it = 0; it < iters; ++it) {
         const int s = it % kStages;
         if (it >= kStages) mbar_wait(empty + s, ((it / kStages) - 1) & 1);
@@ -171,8 +177,10 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
         mbar_expect_tx(full + s, bytes);
         for (int a = 0; a < m_atoms; ++a)
           tma_load_4d(base + a * kAtomBytes, &map_m, full + s, m0 + a * 64, x0 + msx, y0 + msy, b);
+        for (int a = 0; a < m_atoms_b; ++a)
+          tma_load_4d(base + (2 + a) * kAtomBytes, &map_m, full + s, m0 + 128 + a * 64, x0 + msx, y0 + msy, b);
         for (int a = 0; a < n_atoms; ++a)
-          tma_load_4d(base + (2 + a) * kAtomBytes, &map_n, full + s, n0 + a * 64, x0 + nsx, y0 + nsy, b);
+          tma_load_4d(base + (kMaxMAtoms + a) * kAtomBytes, &map_n, full + s, n0 + a * 64, x0 + nsx, y0 + nsy, b);
       }
     }
   } else if (warp == 5) {
@@ -186,9 +194,12 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
         fence_after();
         const uint32_t base = smem_u32(smem + s * stage_bytes);
 #pragma unroll
-        for (int k = 0; k < 4; ++k)      // 16 pixels = 16 rows of 128 bytes per K step
-          umma(tmem_base, make_desc_mn(base + k * 2048, kAtomBytes), make_desc_mn(base + 2 * kAtomBytes + k * 2048, kAtomBytes),
-               idesc, (it > 0 || k > 0) ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) {    // 16 pixels = 16 rows of 128 bytes per K step
+          const uint64_t bdesc = make_desc_mn(base + kMaxMAtoms * kAtomBytes + k * 2048, kAtomBytes);
+          umma(tmem_base, make_desc_mn(base + k * 2048, kAtomBytes), bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          if (m_valid_b > 0)
+            umma(tmem_base + p.acc_stride, make_desc_mn(base + 2 * kAtomBytes + k * 2048, kAtomBytes), bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
         umma_commit(empty + s);
       }
       umma_commit(done);
@@ -198,24 +209,29 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
     mbar_wait(done, 0);
     fence_after();
     const int m = warp * 32 + lane;
-    const bool row_ok = m < m_valid;
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(warp * 32) << 16);
     float* dw_tap = p.dw + static_cast<int64_t>(tap) * p.N * p.dw_rs;
-    for (int c = 0; c < n_mma; c += 16) {
-      uint32_t r[16];
-      tmem_ld16(t_row + c, r);
-      if (!row_ok) continue;
-      if (!p.m_is_x) {          // D[m][j] = dW[n0'=m0+m][c = n0+c+j]: 16 consecutive floats of one row
-        float* dst = dw_tap + static_cast<int64_t>(m0 + m) * p.dw_rs + n0 + c;
+    for (int tile = 0; tile < 2; ++tile) {
+      const int mv = tile == 0 ? m_valid : m_valid_b;
+      if (mv <= 0) break;
+      const int mb = m0 + tile * 128;
+      const bool row_ok = m < mv;
+      const uint32_t t_row = tmem_base + tile * p.acc_stride + (static_cast<uint32_t>(warp * 32) << 16);
+      for (int c = 0; c < n_mma; c += 16) {
+        uint32_t r[16];
+        tmem_ld16(t_row + c, r);
+        if (!row_ok) continue;
+        if (!p.m_is_x) {          // D[m][j] = dW[n = mb + m][c = n0 + c + j]: 16 consecutive floats of one row
+          float* dst = dw_tap + static_cast<int64_t>(mb + m) * p.dw_rs + n0 + c;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          if (c + j < n_valid)    // channel counts are multiples of 4 here (checked on the host)
-            atomicAdd(reinterpret_cast<float4*>(dst + j), make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
-                                                                       __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
-      } else {                  // D[m][j] = dW[n = n0+c+j][c = m0+m]: lanes of a warp are contiguous in c
+          for (int j = 0; j < 16; j += 4)
+            if (c + j < n_valid)    // channel counts are multiples of 4 here (checked on the host)
+              atomicAdd(reinterpret_cast<float4*>(dst + j), make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]),
+                                                                         __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+        } else {                  // D[m][j] = dW[n = n0 + c + j][c = mb + m]: lanes of a warp are contiguous in c
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c + j < n_valid) atomicAdd(dw_tap + static_cast<int64_t>(n0 + c + j) * p.dw_rs + m0 + m, __uint_as_float(r[j]));
+          for (int j = 0; j < 16; ++j)
+            if (c + j < n_valid) atomicAdd(dw_tap + static_cast<int64_t>(n0 + c + j) * p.dw_rs + mb + m, __uint_as_float(r[j]));
+        }
       }
     }
   }
@@ -278,16 +294,19 @@ static int launch_tc(WgTcParams& p, const void* dy, int64_t dy_cs, const void* x
   p.tiles_x = (p.W + p.tw - 1) / p.tw;
   p.tiles_y = (p.H + p.th - 1) / p.th;
   p.chunks = p.B * p.tiles_x * p.tiles_y;
-  const int units = p.taps * p.m_tiles * p.n_tiles;
+  p.m_pair = p.m_tiles >= 2 ? 2 : 1;
+  p.m_units = (p.m_tiles + p.m_pair - 1) / p.m_pair;
+  p.acc_stride = static_cast<uint32_t>((p.n_tile + 31) & ~31);
+  const int units = p.taps * p.m_units * p.n_tiles;
   int splits = (gwd_num_sms() + units / 2) / units;
   splits = max(1, min(splits, p.chunks / 8));
   p.splits = splits;
   uint32_t cols = 32;
-  while (cols < static_cast<uint32_t>(p.n_tile)) cols <<= 1;
+  while (cols < p.acc_stride * (p.m_pair - 1) + static_cast<uint32_t>(p.n_tile)) cols <<= 1;
   p.tmem_cols = cols;
   CUtensorMap map_dy, map_x;
   if (make_map(&map_dy, dy, p.B, p.H, p.W, dy_cs, N, p.tw, p.th) || make_map(&map_x, x, p.B, p.H, p.W, x_cs, C, p.tw, p.th)) return 1;
-  const size_t smem = static_cast<size_t>(kStages) * (2 + kMaxNAtoms) * kAtomBytes + 1024 + 256;
+  const size_t smem = static_cast<size_t>(kStages) * (kMaxMAtoms + kMaxNAtoms) * kAtomBytes + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     GWD_CUDA(cudaFuncSetAttribute(gwd_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
