@@ -114,6 +114,19 @@ SIGNATURES = {
     "gwd_sample_scalar_bwd": (c_int, [P, P, I, P, P, I, I, I, P]),
     "gwd_window_attention_bwd": (c_int, [P, L, P, L, P, L, P, P, I, P, I, I, I, I, F_, P]),
     "gwd_token_attention_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, I, L, L, L, L, L, L, L, F_, P]),
+    "gwd_ref_diffuse_dev": (c_int, [P, P, P, P, P, I, I, I, I, P]),
+    "gwd_ref_diffuse_conv_dev": (c_int, [P, P, P, P, P, I, I, I, I, P]),
+    "gwd_diffuse_filter_pack": (c_int, [P, P, P, P, P]),
+    "gwd_ref_diffuse_bwd": (c_int, [P, P, P, P, P, P, P, P, P, P, I, I, I, I, P]),
+    "gwd_ref_affine": (c_int, [P, L, P, P, P, L, I, P]),
+    "gwd_ref_affine_bwd": (c_int, [P, P, L, P, P, P, P, I, I, P]),
+    "gwd_ref_requery_bwd": (c_int, [P, P, L, P, L, P, P, L, I, I, I, I, I, F_, P]),
+    "gwd_ref_scores_bwd": (c_int, [P, P, L, P, L, P, L, P, L, I, I, I, I, I, F_, P]),
+    "gwd_line_ref_scatter": (c_int, [P, L, P, I, P, L, I, I, I, I, I, I, P]),
+    "gwd_subsample2": (c_int, [P, P, I, I, I, I, P]),
+    "gwd_zero_stuff2": (c_int, [P, P, P, I, I, I, I, P]),
+    "gwd_scale_rows": (c_int, [P, P, L, P]),
+    "gwd_fold_mirror": (c_int, [P, P, P, L, P]),
 }
 
 _lib = None

@@ -287,8 +287,13 @@ struct DiffuseFilter {
 // grid (row bands of kDiffBand rows, B), block 256.
 __global__ void __launch_bounds__(256) gwd_ref_diffuse_conv_kernel(const float* __restrict__ a, float* __restrict__ raw,
                                                                    const __grid_constant__ DiffuseFilter flt,
-                                                                   double* __restrict__ stats, int P, int R) {
+                                                                   double* __restrict__ stats, int P, int R,
+                                                                   const float* __restrict__ fdev, const float* __restrict__ add) {
   extern __shared__ __align__(16) float dsm[];
+  // training: the filter is a parameter that the optimizer updates on the device -> read it from `fdev`
+  // ([oc][ic][ky][kx] then the 16 biases) instead of the by-value copy of the inference plan
+  const float* fw = fdev ? fdev : flt.w;
+  const float* fb = fdev ? fdev + kDiffHeads * kDiffHeads * 9 : flt.b;
   constexpr int heads = kDiffHeads;
   const int y0 = blockIdx.x * kDiffBand, b = blockIdx.y;
   const int rows = min(kDiffBand, P - y0);
@@ -299,7 +304,7 @@ __global__ void __launch_bounds__(256) gwd_ref_diffuse_conv_kernel(const float* 
   for (int i = threadIdx.x; i < heads * heads * 9; i += blockDim.x) {
     int oc = i / (heads * 9), rem = i - oc * heads * 9;
     int ic = rem / 9, k = rem - ic * 9;
-    wsm[(ic * 9 + k) * heads + oc] = flt.w[i];
+    wsm[(ic * 9 + k) * heads + oc] = fw[i];
   }
   for (int rowid = threadIdx.x >> 5; rowid < heads * TR; rowid += blockDim.x >> 5) {
     int ic = rowid / TR, ty = rowid - ic * TR;
@@ -319,7 +324,7 @@ __global__ void __launch_bounds__(256) gwd_ref_diffuse_conv_kernel(const float* 
     int ty = pix / R, tx = pix - ty * R;
     float acc[4];
 #pragma unroll
-    for (int o = 0; o < 4; ++o) acc[o] = flt.b[ocg * 4 + o];
+    for (int o = 0; o < 4; ++o) acc[o] = fb[ocg * 4 + o];
 #pragma unroll 2
     for (int ic = 0; ic < heads; ++ic) {
       const float* t = tile + (ic * TR + ty) * TC + tx;
@@ -336,7 +341,9 @@ __global__ void __launch_bounds__(256) gwd_ref_diffuse_conv_kernel(const float* 
     }
 #pragma unroll
     for (int o = 0; o < 4; ++o) {
-      raw[((static_cast<int64_t>(b) * heads + ocg * 4 + o) * P + y0 + ty) * R + tx] = acc[o];
+      const int64_t oi = ((static_cast<int64_t>(b) * heads + ocg * 4 + o) * P + y0 + ty) * R + tx;
+      if (add) acc[o] += add[oi];
+      raw[oi] = acc[o];
       s[o] += acc[o];
       ss[o] += acc[o] * acc[o];
     }
@@ -378,8 +385,11 @@ constexpr int kDiffWarps = 9;
 __global__ void __launch_bounds__(kDiffWarps * 32) gwd_ref_diffuse_mma_kernel(const float* __restrict__ a, float* __restrict__ raw,
                                                                            const __grid_constant__ DiffuseFilter flt,
                                                                            double* __restrict__ stats, int P, int R,
-                                                                           int plane, int terms, int nimg) {
+                                                                           int plane, int terms, int nimg,
+                                                                           const float* __restrict__ fdev, const float* __restrict__ add) {
   extern __shared__ __align__(16) float dsm[];
+  const float* fw = fdev ? fdev : flt.w;      // see gwd_ref_diffuse_conv_kernel
+  const float* fb = fdev ? fdev + kDiffHeads * kDiffHeads * 9 : flt.b;
   constexpr int heads = kDiffHeads;
   constexpr int TR = kDiffBand + 2;
   const int TC = R + 2;
@@ -390,7 +400,7 @@ __global__ void __launch_bounds__(kDiffWarps * 32) gwd_ref_diffuse_mma_kernel(co
   const int g = lane >> 2, t = lane & 3;
   // the filter leaves the parameter bank with consecutive lanes on consecutive words (a per-lane gather out of the
   // constant bank is serialised address by address), parked in the tile area, then re-laid-out as fragments
-  for (int i = tid; i < heads * heads * 9; i += blockDim.x) tile[i] = flt.w[i];
+  for (int i = tid; i < heads * heads * 9; i += blockDim.x) tile[i] = fw[i];
   __syncthreads();
   // weight fragments: k-step ks = tap * 2 + kb covers input channels 8 kb .. 8 kb + 7 of tap `tap`
   for (int i = tid; i < 18 * 2 * 32; i += blockDim.x) {
@@ -441,8 +451,8 @@ __global__ void __launch_bounds__(kDiffWarps * 32) gwd_ref_diffuse_mma_kernel(co
     float acc[2][4];
 #pragma unroll
     for (int nt = 0; nt < 2; ++nt) {
-      acc[nt][0] = flt.b[8 * nt + 2 * t];
-      acc[nt][1] = flt.b[8 * nt + 2 * t + 1];
+      acc[nt][0] = fb[8 * nt + 2 * t];
+      acc[nt][1] = fb[8 * nt + 2 * t + 1];
       acc[nt][2] = acc[nt][0];
       acc[nt][3] = acc[nt][1];
     }
@@ -482,6 +492,11 @@ __global__ void __launch_bounds__(kDiffWarps * 32) gwd_ref_diffuse_mma_kernel(co
       for (int j = 0; j < 2; ++j) {
         const int oc = 8 * nt + 2 * t + j;
         float* dst = raw + ((static_cast<int64_t>(b) * heads + oc) * P + y0) * R;
+        if (add) {
+          const float* ad = add + ((static_cast<int64_t>(b) * heads + oc) * P + y0) * R;
+          if (ok0) acc[nt][j] += ad[ty0 * R + tx0];
+          if (ok1) acc[nt][2 + j] += ad[ty1 * R + tx1];
+        }
         if (ok0) {
           dst[ty0 * R + tx0] = acc[nt][j];
           s[2 * nt + j] += acc[nt][j];
@@ -713,15 +728,11 @@ extern "C" int gwd_ref_scores(const void* q, int64_t q_rs, const float* refk, in
   return GWD_OK;
 }
 
-extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w_host, const float* bias_host, float* raw_ws,
-                               double* stats_ws, int32_t B, int32_t heads, int32_t P, int32_t R, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  GWD_CHECK_ARG(a_in && a_out && w_host && bias_host && raw_ws && stats_ws && a_in != a_out,
-                "gwd_ref_diffuse: null / aliased pointer");
+// conv phase of one diffusion round: raw = conv3x3(a_in) (+ add), per-(image, channel) sum / sum of squares into stats.
+// The filter is either the by-value host copy `flt` (inference plan) or the device array `fdev` (training).
+static int launch_diffuse_conv(const float* a_in, const DiffuseFilter& flt, const float* fdev, const float* add, float* raw,
+                               double* stats_ws, int B, int heads, int P, int R, cudaStream_t stream) {
   GWD_CHECK_ARG(heads == kDiffHeads, "gwd_ref_diffuse: built for %d heads (got %d)", kDiffHeads, heads);
-  DiffuseFilter flt;
-  memcpy(flt.w, w_host, sizeof(flt.w));
-  memcpy(flt.b, bias_host, sizeof(flt.b));
   GWD_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * B * heads, stream));
   static const bool use_mma = []() { const char* e = getenv("GWD_DIFFUSE_MMA"); return !(e && e[0] == '0'); }();
   dim3 grid(static_cast<unsigned>(gwd_ceil_div(P, kDiffBand)), B);
@@ -743,7 +754,7 @@ extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w_h
     if (per_sm < 1) per_sm = 1;
     unsigned ctas = static_cast<unsigned>(per_sm * gwd_num_sms());
     if (ctas > grid.x * grid.y) ctas = grid.x * grid.y;
-    gwd_ref_diffuse_mma_kernel<<<ctas, kDiffWarps * 32, smem, stream>>>(a_in, raw_ws, flt, stats_ws, P, R, plane, terms, B);
+    gwd_ref_diffuse_mma_kernel<<<ctas, kDiffWarps * 32, smem, stream>>>(a_in, raw, flt, stats_ws, P, R, plane, terms, B, fdev, add);
   } else {
     size_t smem = (static_cast<size_t>(heads) * (kDiffBand + 2) * (R + 2) + static_cast<size_t>(heads) * heads * 9) * sizeof(float);
     GWD_CHECK_ARG(smem <= 200 * 1024, "gwd_ref_diffuse: %d reference points do not fit shared memory", R);
@@ -754,16 +765,56 @@ extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w_h
         configured = true;
       }
     }
-    gwd_ref_diffuse_conv_kernel<<<grid, 256, smem, stream>>>(a_in, raw_ws, flt, stats_ws, P, R);
+    gwd_ref_diffuse_conv_kernel<<<grid, 256, smem, stream>>>(a_in, raw, flt, stats_ws, P, R, fdev, add);
   }
   GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+static int launch_diffuse_norm(const float* a_in, const float* raw, const double* stats_ws, float* a_out, int B, int heads, int P,
+                               int R, cudaStream_t stream) {
   const int per_img = P * R;
   int chunks = static_cast<int>(gwd_ceil_div(per_img, 256 * 4 * 4));
   if (chunks < 1) chunks = 1;
   gwd_ref_diffuse_norm_kernel<<<dim3(static_cast<unsigned>(chunks), static_cast<unsigned>(B * heads)), 256, 0, stream>>>(
-      a_in, raw_ws, stats_ws, a_out, per_img);
+      a_in, raw, stats_ws, a_out, per_img);
   GWD_LAUNCHED();
   return GWD_OK;
+}
+
+extern "C" int gwd_ref_diffuse(const float* a_in, float* a_out, const float* w_host, const float* bias_host, float* raw_ws,
+                               double* stats_ws, int32_t B, int32_t heads, int32_t P, int32_t R, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GWD_CHECK_ARG(a_in && a_out && w_host && bias_host && raw_ws && stats_ws && a_in != a_out,
+                "gwd_ref_diffuse: null / aliased pointer");
+  DiffuseFilter flt;
+  memcpy(flt.w, w_host, sizeof(flt.w));
+  memcpy(flt.b, bias_host, sizeof(flt.b));
+  int rc = launch_diffuse_conv(a_in, flt, nullptr, nullptr, raw_ws, stats_ws, B, heads, P, R, stream);
+  if (rc != GWD_OK) return rc;
+  return launch_diffuse_norm(a_in, raw_ws, stats_ws, a_out, B, heads, P, R, stream);
+}
+
+// training forward: the same round with the filter read from DEVICE memory (filt_dev = [oc][ic][ky][kx] fp32 then 16
+// biases, produced by gwd_diffuse_filter_pack); raw / stats are kept by the caller for gwd_ref_diffuse_bwd
+extern "C" int gwd_ref_diffuse_dev(const float* a_in, float* a_out, const float* filt_dev, float* raw, double* stats,
+                                   int32_t B, int32_t heads, int32_t P, int32_t R, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GWD_CHECK_ARG(a_in && a_out && filt_dev && raw && stats && a_in != a_out, "gwd_ref_diffuse_dev: null / aliased pointer");
+  static const DiffuseFilter none = {};
+  int rc = launch_diffuse_conv(a_in, none, filt_dev, nullptr, raw, stats, B, heads, P, R, stream);
+  if (rc != GWD_OK) return rc;
+  return launch_diffuse_norm(a_in, raw, stats, a_out, B, heads, P, R, stream);
+}
+
+// out = add + conv3x3(a_in) with a device filter: the data-gradient convolution of the diffusion backward (the caller
+// passes the flipped / transposed filter with zero biases); stats_scratch: fp64 [2 * B * heads] scratch
+extern "C" int gwd_ref_diffuse_conv_dev(const float* a_in, const float* filt_dev, const float* add, float* out,
+                                        double* stats_scratch, int32_t B, int32_t heads, int32_t P, int32_t R, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GWD_CHECK_ARG(a_in && filt_dev && out && stats_scratch && a_in != out, "gwd_ref_diffuse_conv_dev: null / aliased pointer");
+  static const DiffuseFilter none = {};
+  return launch_diffuse_conv(a_in, none, filt_dev, add, out, stats_scratch, B, heads, P, R, stream);
 }
 
 extern "C" int gwd_ref_requery(const float* a, const float* refv, int64_t ref_rs, void* out, int64_t o_rs, int32_t B,

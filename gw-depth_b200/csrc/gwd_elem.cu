@@ -411,6 +411,37 @@ __global__ void gwd_line_ref_gather_kernel(const bf16* win, int64_t win_rs, cons
   }
 }
 
+// adjoint of the FEATURE part of gwd_line_ref_gather (the position table carries no gradient, and grid_sample(nearest) has
+// none w.r.t. the coordinates): d_win[row(b, r)] += d_ref[b, r].  One CTA per image walks its R points in order (several
+// points may hit the same token), a thread owns 8 channels: deterministic, no atomics.
+__global__ void gwd_line_ref_scatter_kernel(const bf16* d_ref, int64_t dref_rs, const float* coords, int R, bf16* d_win,
+                                            int64_t win_rs, WinGeom gm, int C) {
+  const int b = blockIdx.x;
+  const int nWx = gm.Wp / gm.ws;
+  for (int r = 0; r < R; ++r) {
+    const int64_t wid = static_cast<int64_t>(b) * R + r;
+    float gx = coords[wid * 2], gy = coords[wid * 2 + 1];
+    if (gm.shift > 0) {
+      gx -= (static_cast<float>(gm.shift) / (gm.Wp - 1)) * 2.f;
+      gy -= (static_cast<float>(gm.shift) / (gm.Hp - 1)) * 2.f;
+      if (gx < -1.f) gx = -1.f - (1.f + gx);
+      if (gy < -1.f) gy = -1.f - (1.f + gy);
+    }
+    const int ix = static_cast<int>(nearbyintf(unnorm(gx, gm.Wp))), iy = static_cast<int>(nearbyintf(unnorm(gy, gm.Hp)));
+    if (!(ix >= 0 && ix < gm.Wp && iy >= 0 && iy < gm.Hp)) continue;      // uniform over the CTA
+    const int64_t wrow = ((static_cast<int64_t>(b) * (gm.Hp / gm.ws) + iy / gm.ws) * nWx + ix / gm.ws) * (gm.ws * gm.ws) +
+                         (iy % gm.ws) * gm.ws + ix % gm.ws;
+    for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8) {
+      float f[8], g[8];
+      load8(d_win + wrow * win_rs + c, f);
+      load8(d_ref + wid * dref_rs + c, g);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] += g[i];
+      store8(d_win + wrow * win_rs + c, f);
+    }
+  }
+}
+
 // depth[p] = sum_k softmax_k(logits[p, :K]) * anchor[b, k]        (points_sample.py:277-279)
 __global__ void gwd_anchor_mix_kernel(const bf16* logits, int64_t l_rs, const float* anchor, int B, int64_t HW, int K,
                                       float* out) {
@@ -652,6 +683,19 @@ extern "C" int gwd_line_ref_gather(const void* win, int64_t win_rs, const float*
   int64_t warps = static_cast<int64_t>(B) * R;
   gwd_line_ref_gather_kernel<<<static_cast<unsigned>(gwd_ceil_div(warps * 32, 128)), 128, 0, stream>>>(
       static_cast<const bf16*>(win), win_rs, pos, pos_bstride, coords, R, static_cast<bf16*>(out), out_rs, gm, C);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_line_ref_scatter(const void* d_ref, int64_t dref_rs, const float* coords, int32_t R, void* d_win, int64_t win_rs,
+                                    int32_t B, int32_t H, int32_t W, int32_t ws, int32_t shift, int32_t C, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(d_ref && coords && d_win && GWD_ALIGN8(C) && GWD_ALIGN8(win_rs) && GWD_ALIGN8(dref_rs),
+                "gwd_line_ref_scatter: bad argument");
+  WinGeom gm;
+  make_geom(gm, B, H, W, ws, shift);
+  gwd_line_ref_scatter_kernel<<<static_cast<unsigned>(B), 64, 0, stream>>>(static_cast<const bf16*>(d_ref), dref_rs, coords, R,
+                                                                          static_cast<bf16*>(d_win), win_rs, gm, C);
   GWD_LAUNCHED();
   return GWD_OK;
 }

@@ -766,3 +766,98 @@ def adamw_step(p, g, m, v, mirror, *, lr, betas=(0.9, 0.999), eps=1e-8, weight_d
     assert p.dtype == g.dtype == m.dtype == v.dtype == torch.float32 and p.is_contiguous() and g.is_contiguous()
     capi.check(_L().gwd_adamw_step(_ptr(p), _ptr(g), _ptr(m), _ptr(v), _ptr(mirror), p.numel(), lr, betas[0], betas[1], eps,
                                    weight_decay, step, max_norm, grad_scale, _ptr(sumsq_buf), _stream()), "gwd_adamw_step")
+
+
+# ------------------------------------------------------------------------------------------
+# training side of the 1/32 line-window stage (gwd_train_line.cu) and backbone-backward helpers
+# ------------------------------------------------------------------------------------------
+def diffuse_filter_pack(w_phys, bias, fwd=None, bwd=None):
+    """w_phys fp32 [9,16,16] (tap = kx*3+ky: the flat-buffer layout of the 16x16x3x3 filter), bias fp32 [>=16] -> (fwd, bwd)
+    device filters (2 320 floats) for ref_diffuse_dev / ref_diffuse_bwd"""
+    fwd = torch.empty(2320, dtype=torch.float32, device=w_phys.device) if fwd is None else fwd
+    bwd = torch.empty(2320, dtype=torch.float32, device=w_phys.device) if bwd is None else bwd
+    capi.check(_L().gwd_diffuse_filter_pack(_ptr(w_phys), _ptr(bias), _ptr(fwd), _ptr(bwd), _stream()), "gwd_diffuse_filter_pack")
+    return fwd, bwd
+
+
+def ref_diffuse_dev(a_in, filt, B, heads, P, R):
+    """one diffusion round with a device filter -> (a_out, raw, stats) (all kept for the backward)"""
+    a_out, raw = torch.empty_like(a_in), torch.empty_like(a_in)
+    stats = torch.empty(B * heads * 2, dtype=torch.float64, device=a_in.device)
+    capi.check(_L().gwd_ref_diffuse_dev(_ptr(a_in), _ptr(a_out), _ptr(filt), _ptr(raw), _ptr(stats), B, heads, P, R, _stream()),
+               "gwd_ref_diffuse_dev")
+    return a_out, raw, stats
+
+
+def ref_diffuse_bwd(g, raw, stats, a_in, filt_bwd, dw_phys, db, B, heads, P, R, ws=None):
+    """-> d a_in; accumulates dw_phys [9,16,16] / db [16].  ws: optional (d_raw, stats2) workspaces"""
+    d_raw = torch.empty_like(g) if ws is None else ws[0]
+    stats2 = torch.empty(4 * B * heads, dtype=torch.float64, device=g.device) if ws is None else ws[1]
+    d_in = torch.empty_like(g)
+    capi.check(_L().gwd_ref_diffuse_bwd(_ptr(g), _ptr(raw), _ptr(stats), _ptr(a_in), _ptr(filt_bwd), _ptr(d_raw), _ptr(stats2),
+                                        _ptr(d_in), _ptr(dw_phys), _ptr(db), B, heads, P, R, _stream()), "gwd_ref_diffuse_bwd")
+    return d_in
+
+
+def ref_affine(ref, mu, logsigma, D):
+    """ref fp32 [rows, >= D] -> ref_k fp32 [rows, D] = mu + exp(logsigma) * ref[:, :D]"""
+    rows = ref.shape[0]
+    out = torch.empty(rows, D, dtype=torch.float32, device=ref.device)
+    capi.check(_L().gwd_ref_affine(_ptr(ref), ref.shape[-1], _ptr(mu), _ptr(logsigma), _ptr(out), rows, D, _stream()), "gwd_ref_affine")
+    return out
+
+
+def ref_affine_bwd(d_kv, ref, logsigma, dmu, dlogsigma, D):
+    """d_kv fp32 [rows, 2D] -> d_ref bf16 [rows, 2D]; dmu / dlogsigma (fp32 [D] views) accumulated"""
+    rows = d_kv.shape[0]
+    assert d_kv.shape[1] == 2 * D and d_kv.is_contiguous() and ref.is_contiguous()
+    d_ref = torch.empty(rows, 2 * D, dtype=torch.bfloat16, device=d_kv.device)
+    capi.check(_L().gwd_ref_affine_bwd(_ptr(d_kv), _ptr(ref), ref.shape[-1], _ptr(logsigma), _ptr(d_ref), _ptr(dmu), _ptr(dlogsigma),
+                                       rows, D, _stream()), "gwd_ref_affine_bwd")
+    return d_ref
+
+
+def ref_requery_bwd(a, refv, ref_rs, d_qnew, dq_rs, d_refv, drv_rs, B, T, heads, hd, R, scale):
+    """-> d a (soft-max backward included); d_refv (a channel slice of an fp32 [B*R, *] buffer) is written"""
+    d_a = torch.empty_like(a)
+    capi.check(_L().gwd_ref_requery_bwd(_ptr(a), _ptr(refv), ref_rs, _ptr(d_qnew), dq_rs, _ptr(d_a), _ptr(d_refv), drv_rs, B, T, heads,
+                                        hd, R, scale, _stream()), "gwd_ref_requery_bwd")
+    return d_a
+
+
+def ref_scores_bwd(d_a, refk, ref_rs, q, q_rs, d_q, dq_rs, d_refk, drk_rs, B, T, heads, hd, R, scale):
+    capi.check(_L().gwd_ref_scores_bwd(_ptr(d_a), _ptr(refk), ref_rs, _ptr(q), q_rs, _ptr(d_q), dq_rs, _ptr(d_refk), drk_rs, B, T, heads,
+                                       hd, R, scale, _stream()), "gwd_ref_scores_bwd")
+
+
+def line_ref_scatter(d_ref, coords, R, d_win, B, H, W, ws, shift, C):
+    """d_win[row of point (b, r)] += d_ref[b, r]: the adjoint of the feature part of line_ref_gather (in place)"""
+    capi.check(_L().gwd_line_ref_scatter(_ptr(d_ref), d_ref.shape[-1], _ptr(coords), R, _ptr(d_win), d_win.shape[-1], B, H, W, ws, shift,
+                                         C, _stream()), "gwd_line_ref_scatter")
+    return d_win
+
+
+def subsample2(x):
+    """bf16 [B,H,W,C] -> x[:, ::2, ::2, :] contiguous"""
+    B, H, W, C = x.shape
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    y = torch.empty(B, (H + 1) // 2, (W + 1) // 2, C, dtype=torch.bfloat16, device=x.device)
+    capi.check(_L().gwd_subsample2(_ptr(x), _ptr(y), B, H, W, C, _stream()), "gwd_subsample2")
+    return y
+
+
+def zero_stuff2(s, H, W, add=None):
+    """bf16 [B,h,w,C] -> [B,H,W,C] with s at the even pixels (zeros elsewhere) (+ add)"""
+    B, h, w, C = s.shape
+    assert (h, w) == ((H + 1) // 2, (W + 1) // 2) and s.is_contiguous() and (add is None or (add.is_contiguous() and add.numel() == B * H * W * C))
+    y = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=s.device)
+    capi.check(_L().gwd_zero_stuff2(_ptr(s), _ptr(add), _ptr(y), B, H, W, C, _stream()), "gwd_zero_stuff2")
+    return y
+
+
+def scale_rows(g, scale):
+    capi.check(_L().gwd_scale_rows(_ptr(g), _ptr(scale), g.numel(), _stream()), "gwd_scale_rows")
+
+
+def fold_mirror(p, scale, mirror):
+    capi.check(_L().gwd_fold_mirror(_ptr(p), _ptr(scale), _ptr(mirror), p.numel(), _stream()), "gwd_fold_mirror")

@@ -380,6 +380,61 @@ int gwd_token_attention_bwd(const void* dq, const void* sq, const void* tk, cons
                             int32_t tc, int64_t q_rs, int64_t k_rs, int64_t v_rs, int64_t o_rs, int64_t gq_rs, int64_t gk_rs,
                             int64_t gv_rs, float scale, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training path of the 1/32 line-window stage ("glass-structure context", WindowAttention.forward,
+ * src/models/multiscale_transformerr.py:267-332 under torch.autograd) -- gwd_train_line.cu
+ * ------------------------------------------------------------------------------------------ */
+/* One diffusion round (:299-302) with the filter read from DEVICE memory (the optimizer updates it there): filt_dev = fp32
+ * [oc][ic][ky][kx] (16x16x3x3) followed by the 16 biases, as written by gwd_diffuse_filter_pack.  a_out = a_in +
+ * gelu(instance_norm(conv(a_in))); raw (the convolution output) and stats (fp64 [B*heads][2] = sum, sum of squares per plane)
+ * are kept by the caller for gwd_ref_diffuse_bwd.  Same kernels as gwd_ref_diffuse. */
+int gwd_ref_diffuse_dev(const float* a_in, float* a_out, const float* filt_dev, float* raw, double* stats, int32_t B, int32_t heads,
+                        int32_t P, int32_t R, void* stream);
+/* out = add (optional) + conv3x3(a_in) with a device filter in the gwd_ref_diffuse_dev layout; stats_scratch fp64 [2*B*heads] */
+int gwd_ref_diffuse_conv_dev(const float* a_in, const float* filt_dev, const float* add, float* out, double* stats_scratch,
+                             int32_t B, int32_t heads, int32_t P, int32_t R, void* stream);
+/* w_phys fp32 [9][16][16] (tap = kx*3+ky, the packed 3x3 layout of the flat parameter buffers) + bias [16] -> fwd / bwd filters
+ * (2 320 floats each) in the gwd_ref_diffuse_dev layout; bwd = the adjoint filter (channels transposed, taps flipped, no bias) */
+int gwd_diffuse_filter_pack(const float* w_phys, const float* bias, float* fwd, float* bwd, void* stream);
+/* Backward of one diffusion round: g = d a_out fp32 [B,heads,P,R]; raw / stats / a_in from the forward; filt_bwd from
+ * gwd_diffuse_filter_pack.  d_a_in = g + conv(d raw, adjoint filter); dw_phys ([9][16][16]) and db ([16]) are ACCUMULATED.
+ * Workspaces: d_raw_ws fp32 [B,heads,P,R], stats2_ws fp64 [4*B*heads]. */
+int gwd_ref_diffuse_bwd(const float* g, const float* raw, const double* stats, const float* a_in, const float* filt_bwd,
+                        float* d_raw_ws, double* stats2_ws, float* d_a_in, float* dw_phys, float* db, int32_t B, int32_t heads,
+                        int32_t P, int32_t R, void* stream);
+/* ref_k = mu + exp(logsigma) * ref[:, :D]  (:281-288): ref fp32 [rows, ref_rs] -> out fp32 [rows, D] */
+int gwd_ref_affine(const float* ref, int64_t ref_rs, const float* mu, const float* logsigma, float* out, int64_t rows, int32_t D,
+                   void* stream);
+/* d_kv fp32 [rows, 2D] = (d ref_k | d ref_v) -> d_ref bf16 [rows, 2D] = the output gradient of the ref_qk Linear;
+ * dmu / dlogsigma fp32 [D] are accumulated */
+int gwd_ref_affine_bwd(const float* d_kv, const float* ref, int64_t ref_rs, const float* logsigma, void* d_ref, float* dmu,
+                       float* dlogsigma, int32_t rows, int32_t D, void* stream);
+/* Backward of gwd_ref_requery: a = the diffused scores fp32 [B,heads,T,R], refv fp32 rows b*R+r (row stride ref_rs), d_qnew
+ * bf16 rows b*T+t (row stride dq_rs) -> d_a fp32 [B,heads,T,R] (soft-max backward included), d_refv fp32 (row stride drv_rs) */
+int gwd_ref_requery_bwd(const float* a, const float* refv, int64_t ref_rs, const void* d_qnew, int64_t dq_rs, float* d_a,
+                        float* d_refv, int64_t drv_rs, int32_t B, int32_t T, int32_t heads, int32_t hd, int32_t R, float scale,
+                        void* stream);
+/* Backward of gwd_ref_scores: d_a fp32 [B,heads,T,R], refk fp32, q bf16 -> d_q bf16 (row stride dq_rs), d_refk fp32 */
+int gwd_ref_scores_bwd(const float* d_a, const float* refk, int64_t ref_rs, const void* q, int64_t q_rs, void* d_q, int64_t dq_rs,
+                       float* d_refk, int64_t drk_rs, int32_t B, int32_t T, int32_t heads, int32_t hd, int32_t R, float scale,
+                       void* stream);
+/* Adjoint of the feature part of gwd_line_ref_gather: d_win[row of point (b, r)] += d_ref[b, r]  (bf16, deterministic) */
+int gwd_line_ref_scatter(const void* d_ref, int64_t dref_rs, const float* coords, int32_t R, void* d_win, int64_t win_rs, int32_t B,
+                         int32_t H, int32_t W, int32_t ws, int32_t shift, int32_t C, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Backbone backward helpers (stride-2 convolutions of torchvision's ResNet-50 v1.5 as wrapped by
+ * src/models/backbone.py:58-92; FrozenBatchNorm2d :19-55 folded into the filters)
+ * ------------------------------------------------------------------------------------------ */
+/* y[b,i,j,:] = x[b,2i,2j,:]: bf16 [B,H,W,C] -> [B,ceil(H/2),ceil(W/2),C] */
+int gwd_subsample2(const void* x, void* y, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+/* y[b,i,j,:] = add[b,i,j,:] (optional) + (i, j even ? s[b,i/2,j/2,:] : 0): the adjoint of gwd_subsample2 */
+int gwd_zero_stuff2(const void* s, const void* add, void* y, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+/* g[i] *= scale[i] (gradient w.r.t. the folded filter -> gradient w.r.t. the parameter) */
+int gwd_scale_rows(float* g, const float* scale, int64_t n, void* stream);
+/* mirror[i] = bf16(p[i] * scale[i]) (the folded bf16 filter the forward kernels read) */
+int gwd_fold_mirror(const float* p, const float* scale, void* mirror_bf16, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
