@@ -127,6 +127,8 @@ SIGNATURES = {
     "gwd_zero_stuff2": (c_int, [P, P, P, I, I, I, I, P]),
     "gwd_scale_rows": (c_int, [P, P, L, P]),
     "gwd_fold_mirror": (c_int, [P, P, P, L, P]),
+    "gwd_im2col3x3_s2": (c_int, [P, P, I, I, I, I, P]),
+    "gwd_col2im3x3_s2": (c_int, [P, P, P, I, I, I, I, P]),
 }
 
 _lib = None

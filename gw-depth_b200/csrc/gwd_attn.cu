@@ -736,9 +736,11 @@ static int launch_diffuse_conv(const float* a_in, const DiffuseFilter& flt, cons
   GWD_CUDA(cudaMemsetAsync(stats_ws, 0, sizeof(double) * 2 * B * heads, stream));
   static const bool use_mma = []() { const char* e = getenv("GWD_DIFFUSE_MMA"); return !(e && e[0] == '0'); }();
   dim3 grid(static_cast<unsigned>(gwd_ceil_div(P, kDiffBand)), B);
-  if (use_mma) {
-    int plane = (kDiffBand + 2) * (R + 2);
-    plane += ((8 - plane % 32) + 32) % 32;     // plane stride == 8 (mod 32): the 4 channels x 8 pixels of a fragment load hit 32 banks
+  int plane = (kDiffBand + 2) * (R + 2);
+  plane += ((8 - plane % 32) + 32) % 32;       // plane stride == 8 (mod 32): the 4 channels x 8 pixels of a fragment load hit 32 banks
+  // the MMA kernel parks the filter in its tile area while it builds the fragments: very few reference points (R < 14) do not
+  // give it the room -> direct kernel
+  if (use_mma && heads * plane >= heads * heads * 9) {
     size_t smem = (static_cast<size_t>(heads) * plane + 18 * 2 * 32 * 4) * sizeof(float);
     GWD_CHECK_ARG(smem <= 200 * 1024, "gwd_ref_diffuse: %d reference points do not fit shared memory", R);
     if (smem > 48 * 1024) {

@@ -861,3 +861,23 @@ def scale_rows(g, scale):
 
 def fold_mirror(p, scale, mirror):
     capi.check(_L().gwd_fold_mirror(_ptr(p), _ptr(scale), _ptr(mirror), p.numel(), _stream()), "gwd_fold_mirror")
+
+
+def im2col3x3_s2(x):
+    """bf16 [B,H,W,C] -> [B,ho,wo,9C]: the patches of a stride-2, padding-1 3x3 convolution, K order (ky, kx, c)"""
+    B, H, W, C = x.shape
+    assert x.is_contiguous() and x.dtype == torch.bfloat16
+    col = torch.empty(B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, 9 * C, dtype=torch.bfloat16, device=x.device)
+    capi.check(_L().gwd_im2col3x3_s2(_ptr(x), _ptr(col), B, H, W, C, _stream()), "gwd_im2col3x3_s2")
+    return col
+
+
+def col2im3x3_s2(dcol, H, W, add=None):
+    """adjoint of im2col3x3_s2: bf16 [B,ho,wo,9C] -> [B,H,W,C] (+ add)"""
+    B, ho, wo, C9 = dcol.shape
+    C = C9 // 9
+    assert dcol.is_contiguous() and (ho, wo) == ((H - 1) // 2 + 1, (W - 1) // 2 + 1)
+    assert add is None or (add.is_contiguous() and add.numel() == B * H * W * C)
+    dx = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dcol.device)
+    capi.check(_L().gwd_col2im3x3_s2(_ptr(dcol), _ptr(add), _ptr(dx), B, H, W, C, _stream()), "gwd_col2im3x3_s2")
+    return dx

@@ -434,6 +434,12 @@ int gwd_zero_stuff2(const void* s, const void* add, void* y, int32_t B, int32_t 
 int gwd_scale_rows(float* g, const float* scale, int64_t n, void* stream);
 /* mirror[i] = bf16(p[i] * scale[i]) (the folded bf16 filter the forward kernels read) */
 int gwd_fold_mirror(const float* p, const float* scale, void* mirror_bf16, int64_t n, void* stream);
+/* Stride-2 3x3 convolution (padding 1) as im2col + Linear: x bf16 [B,H,W,C] -> col bf16 [B,ho,wo,9C] with
+ * col[.., (ky*3+kx)*C + c] = x[2 oy + ky - 1, 2 ox + kx - 1, c] (0 outside), ho = (H-1)/2+1, wo = (W-1)/2+1.  Replaces the
+ * cuDNN call behind conv2 of layer2.0 / layer3.0 / layer4.0 (torchvision ResNet-50 v1.5, src/models/backbone.py:58-92). */
+int gwd_im2col3x3_s2(const void* x, void* col, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+/* adjoint of gwd_im2col3x3_s2: dx bf16 [B,H,W,C] = add (optional) + the taps of dcol bf16 [B,ho,wo,9C] that land on each pixel */
+int gwd_col2im3x3_s2(const void* dcol, const void* add, void* dx, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,90 @@
+"""GPU parity of the backbone training path (train_backbone.BackboneTrain): the stride-2 helpers against
+torch, then C3 / C4 / C5 and the gradient of every trained convolution (layer2-4 of the ResNet-50 with FrozenBatchNorm folded)
+against torch.autograd over the CPU oracle's `resnet50_features` (src/models/backbone.py:19-92).
+
+Tolerances: helpers bit-exact / bf16 rounding; feature maps 2e-2, parameter gradients 6e-2 relative L2 (bf16 activations
+through 13 bottlenecks; ReLU derivatives evaluated at bf16 activations)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import oracle, synth, synth_weights
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import ops
+    return ops
+
+
+def rel_l2(got, ref):
+    got, ref = got.double().cpu(), ref.double().cpu()
+    return float((got - ref).norm() / ref.norm().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("B,H,W,C", [(2, 10, 12, 16), (1, 9, 13, 32)])
+def test_stride2_helpers(B, H, W, C):
+    """gwd_im2col3x3_s2 / gwd_col2im3x3_s2 / gwd_subsample2 / gwd_zero_stuff2 against F.unfold and its adjoint"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(H * W)
+    x = torch.randn(B, H, W, C, generator=g).bfloat16()
+    ho, wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    col = ops.im2col3x3_s2(x.cuda())
+    ref = F.unfold(x.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)               # [B, C*9, L], channel-major (c, ky, kx)
+    ref = ref.view(B, C, 9, ho, wo).permute(0, 3, 4, 2, 1).reshape(B, ho, wo, 9 * C)
+    assert torch.equal(col.float().cpu(), ref)
+    d = torch.randn(B, ho, wo, 9 * C, generator=g).bfloat16()
+    add = torch.randn(B, H, W, C, generator=g).bfloat16()
+    dx = ops.col2im3x3_s2(d.cuda(), H, W, add=add.cuda())
+    fold_in = d.float().view(B, ho * wo, 9, C).permute(0, 3, 2, 1).reshape(B, C * 9, ho * wo)
+    want = F.fold(fold_in, (H, W), 3, padding=1, stride=2).permute(0, 2, 3, 1) + add.float()
+    assert rel_l2(dx, want) < 4e-3
+    sub = ops.subsample2(x.cuda())
+    assert torch.equal(sub.cpu(), x[:, ::2, ::2].contiguous())
+    z = ops.zero_stuff2(sub, H, W, add=add.cuda())
+    want = add.float().clone()
+    want[:, ::2, ::2] += x[:, ::2, ::2].float()
+    assert rel_l2(z, want) < 4e-3
+    z0 = ops.zero_stuff2(sub, H, W)
+    assert float(z0.float().abs().sum().cpu()) == float(x[:, ::2, ::2].float().abs().sum())
+
+
+@pytest.mark.parametrize("B,H,W", [(1, 64, 96), (2, 72, 104)])
+def test_backbone_gradients_match_oracle_autograd(B, H, W):
+    _ops()
+    from gwdepth_b200.train_backbone import BODY, BackboneTrain
+    sd = {k: v.clone() for k, v in synth_weights().items() if k.startswith(BODY)}
+    images, _, _, _ = synth.synth_batch(B, H, W, seed=3)
+    sdr = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and k.endswith(".weight") and ("conv" in k or "downsample.0" in k)
+                                                   and any(("layer%d." % i) in k for i in (2, 3, 4))) else v) for k, v in sd.items()}
+    feats = oracle.resnet50_features(images, oracle.P(sdr, BODY))                       # C2..C5, NCHW fp32
+    g = torch.Generator().manual_seed(B)
+    cots = [torch.randn(f.shape, generator=g) * (f > 0) for f in feats[1:]]
+    sum((f * c).sum() for f, c in zip(feats[1:], cots)).backward()
+    bb = BackboneTrain({k: v.cuda() for k, v in sd.items()}, lr=1e-5)
+    for k, v in bb.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), k
+    c2 = bb.frozen_front(images.cuda())
+    assert rel_l2(c2.permute(0, 3, 1, 2), feats[0].detach()) < 2e-2
+    outs = bb.forward(c2)
+    for o, f in zip(outs, feats[1:]):
+        assert rel_l2(o.permute(0, 3, 1, 2), f.detach()) < 3e-2
+    bb.backward(*[c.permute(0, 2, 3, 1).contiguous().bfloat16().cuda() for c in cots])
+    grads = bb.grads()
+    bad = {}
+    n = 0
+    for k, v in sdr.items():
+        if not (isinstance(v, torch.Tensor) and v.requires_grad):
+            continue
+        n += 1
+        e = rel_l2(grads[k], v.grad)
+        if e > 6e-2:
+            bad[k] = round(e, 3)
+    assert n == 13 * 3 + 3 and not bad, (n, bad)
+    # one optimizer step keeps the folded mirror = bf16(parameter * frozen-BN scale)
+    before = bb.P.clone()
+    bb.step()
+    assert not torch.equal(before, bb.P)
+    assert torch.equal(bb.Wb, (bb.P * bb.S).to(torch.bfloat16))
