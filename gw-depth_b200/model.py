@@ -301,16 +301,14 @@ class HungarianMatcher_Line(nn.Module):
                  for b in range(B)] for s in range(S)]
 
     @torch.no_grad()
-    def forward_stacked(self, logits, lines, targets, want_pairs=True):
-        """All S decoder stages at once (the reference calls the matcher once per stage, src/models/glassrgbd.py:318,344):
-        logits [S,B,Q,C], lines [S,B,Q,D] -> list over stages of the per-image (idx_pred, idx_tgt) lists.  ONE
-        gwd_match_cost launch over S*B (stage, image) pairs, ONE device-to-host copy, then the S*B assignments."""
-        from scipy.optimize import linear_sum_assignment
+    def stacked_cost(self, logits, lines, targets):
+        """first half of `forward_stacked`: ONE gwd_match_cost launch over the S*B (stage, image) pairs and an ASYNCHRONOUS
+        copy of the costs into pinned host memory.  Returns a handle for `stacked_solve`; the caller may enqueue more GPU work
+        (e.g. the dense branch, which does not depend on the matching) before it solves."""
         S, B, Q = logits.shape[:3]
         sizes = [len(v["lines"]) for v in targets]
         tgt_lines = torch.cat([v["lines"] for v in targets]).float()
         tgt_ids = torch.cat([v["labels"] for v in targets]).to(torch.int64)
-        total = sum(sizes)
         offs = [0]
         for _ in range(S):
             for n in sizes:
@@ -319,8 +317,23 @@ class HungarianMatcher_Line(nn.Module):
         cost, _ = ops.match_cost(logits.float().reshape(S * B, Q, -1).contiguous(), lines.float().reshape(S * B, Q, -1).contiguous(),
                                  tgt_lines.repeat(S, 1).contiguous(), tgt_ids.repeat(S).contiguous(), offsets,
                                  float(self.cost_class), float(self.cost_line))
-        flat = cost.cpu().numpy()
+        host = getattr(self, "_host_cost", None)
+        if host is None or host.numel() < cost.numel():
+            host = self._host_cost = torch.empty(max(cost.numel(), 1), dtype=torch.float32).pin_memory()
+        host[:cost.numel()].copy_(cost, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        return dict(host=host, n=cost.numel(), event=ev, offs=offs, sizes=sizes, S=S, B=B, Q=Q, keep=cost)
+
+    @torch.no_grad()
+    def stacked_solve(self, pending, want_pairs=True):
+        """second half of `forward_stacked`: wait for the cost copy, solve the S*B assignments on the host"""
+        from scipy.optimize import linear_sum_assignment
         import numpy as np
+        pending["event"].synchronize()
+        S, B, Q, offs, sizes = pending["S"], pending["B"], pending["Q"], pending["offs"], pending["sizes"]
+        flat = pending["host"][:pending["n"]].numpy()
+        total = sum(sizes)
         starts = np.concatenate([[0], np.cumsum(sizes)])
         if os.environ.get("GWD_LSAP", "native") == "scipy":     # the reference's solver, problem by problem
             pairs = [linear_sum_assignment(flat[offs[p] * Q:(offs[p] + sizes[p % B]) * Q].reshape(Q, sizes[p % B])) for p in range(S * B)]
@@ -330,7 +343,7 @@ class HungarianMatcher_Line(nn.Module):
             for p, (q, t) in enumerate(pairs):
                 qi[p, :len(q)], ti[p, :len(q)] = q, t
         else:       # same algorithm and tie rules, all S*B problems on the host cores at once (tests/test_lsap_cpu.py)
-            qi, ti, cnt = ops.lsap_batch(flat, [o * Q for o in offs[:-1]], sizes * S, Q, raw=True)
+            qi, ti, cnt = ops.lsap_batch(flat, [o * Q for o in offs[:-1]], sizes * S, Q, n_threads=_lsap_threads(), raw=True)
         # the assignment as int32 columns (stage, image, query, row of the concatenated targets) for gwd_set_loss, built
         # without a Python loop over the S*B problems
         p_idx, k_idx = np.nonzero(np.arange(qi.shape[1])[None, :] < cnt[:, None])
@@ -344,6 +357,23 @@ class HungarianMatcher_Line(nn.Module):
         result = self.pairs_from_raw()
         assert offs[-1] == S * total
         return result
+
+    @torch.no_grad()
+    def forward_stacked(self, logits, lines, targets, want_pairs=True):
+        """All S decoder stages at once (the reference calls the matcher once per stage, src/models/glassrgbd.py:318,344):
+        logits [S,B,Q,C], lines [S,B,Q,D] -> list over stages of the per-image (idx_pred, idx_tgt) lists.  ONE
+        gwd_match_cost launch over S*B (stage, image) pairs, ONE device-to-host copy, then the S*B assignments."""
+        return self.stacked_solve(self.stacked_cost(logits, lines, targets), want_pairs)
+
+
+def _lsap_threads():
+    """host threads for gwd_lsap_batch: the box's cores divided by the ranks that share them (8 ranks solving on
+    hardware_concurrency() threads each oversubscribe the cores: 1.4 -> 2.7 ms per step in SCALE_r01); GWD_LSAP_THREADS overrides"""
+    env = os.environ.get("GWD_LSAP_THREADS")
+    if env:
+        return max(1, int(env))
+    local = int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")) or 1)
+    return max(1, min(16, (os.cpu_count() or 1) // max(local, 1)))
 
 
 def build_matcher(args, type=None):
@@ -434,13 +464,15 @@ class SetCriterion(nn.Module):
         return losses
 
     @torch.no_grad()
-    def forward_backward_stacked(self, logits, lines, targets):
+    def forward_backward_stacked(self, logits, lines, targets, pending=None):
         """forward_stacked AND its gradient in one gwd_set_loss launch: -> (losses dict, dlogits, dlines) where the
         gradients are those of sum_k weight_dict[k] * losses[k].  No autograd graph, no per-loss torch kernels: the host
         only solves the assignments and uploads them (one int32 [4, M] copy)."""
         S, B, Q = logits.shape[:3]
         dev = logits.device
-        self.matcher.forward_stacked(logits, lines, targets, want_pairs=False)
+        # `pending`: a handle of matcher.stacked_cost issued earlier (the host solve then overlaps whatever GPU work the caller
+        # enqueued in between)
+        self.matcher.stacked_solve(pending if pending is not None else self.matcher.stacked_cost(logits, lines, targets), want_pairs=False)
         n = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float, device=dev)
         if _world_size() > 1:
             torch.distributed.all_reduce(n)

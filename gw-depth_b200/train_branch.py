@@ -102,15 +102,16 @@ class DenseBranch:
         st["graph"].replay()
         return st["result"]
 
-    def _loss_and_grads(self, x32, depth0, feats, depth_gt, seg_gt, pinned=None):
+    def forward(self, x32, depth0, feats, H, W, pinned=None):
         """x32 bf16 [B,h,w,D] (output of the 1/32 line-window stage); depth0 fp32 [B,h,w] (depth_pred32 of it, only feeds the
-        sampling); feats = (C4, C3, C2) bf16 channels-last backbone maps at 1/16, 1/8, 1/4; depth_gt fp32 [B,1,H,W] metres;
-        seg_gt int64 [B,1,H,W]; pinned: optional {'sample1', 'sample2'} coordinates overriding the uncertainty sampling.
-        Returns (outputs dict, losses fp32 [5] = weighted (depth1, depth2, depth3, depth, seg), d x32, d C4, d C3)."""
+        sampling); feats = (C4, C3, C2) bf16 channels-last backbone maps at 1/16, 1/8, 1/4; (H, W): the input size; pinned:
+        optional {'sample1', 'sample2'} coordinates overriding the uncertainty sampling.  Returns the outputs dict
+        (pred_depth = [depth1, depth2, depth3 fp32 [B,h_i,w_i] in [0,1], depth fp32 [B,1,H,W] metres], pred_seg, sample1/2);
+        the stage modules keep their tapes for `backward`."""
         pinned = pinned or {}
         c, td = self.cfg, self.td
         C1, C2, C3 = self.Cs
-        B, h5, w5, _ = x32.shape
+        B = x32.shape[0]
         (H1, W1), (H2, W2), (H3, W3) = [f.shape[1:3] for f in feats]
         e1, e2, e3 = self.entries
         s1, s2, s3 = self.stages
@@ -126,28 +127,61 @@ class DenseBranch:
         coords1 = coords1.reshape(B, -1, 2).float().contiguous()
         depth2 = self.point1.forward(buf2, depth1, coords1, self._table(H2, W2, C2), B, H2, W2)
         coords2 = pinned["sample2"] if "sample2" in pinned else ops.certain_sample(depth1, depth2, c["interval_sample_num"][1], self.edges)[0]
-        # ---- 1/4 + head + the losses on depth_pred3 / depth / seg
+        # ---- 1/4 + head
         x, d, s = e3.forward(x2.view(B, H2, W2, C2), d2, t2, feats[2])
         x3, d3, t3 = s3.forward(x, d, s, B, H3, W3)
         buf4 = torch.zeros(B, H3, W3, C3 + 3 * td, dtype=torch.bfloat16, device=self.dev)
         b2d = buf4.view(-1, C3 + 3 * td)
         b2d[:, :C3], b2d[:, C3:C3 + td], b2d[:, C3 + td:C3 + 2 * td] = x3, d3, t3
         coords2 = coords2.reshape(B, -1, 2).float().contiguous()
-        depth3, depth, seg, l345, d_buf4, d_depth2 = self.tail.loss_and_grads(buf4, depth2, coords2, self._table(H3, W3, C3),
-                                                                              depth_gt, seg_gt)
-        # ---- backward
+        depth3, depth, seg = self.tail.forward(buf4, depth2, coords2, self._table(H3, W3, C3), H, W)
+        self._shapes = (B, (H1, W1), (H2, W2), (H3, W3))
+        return dict(pred_depth=[depth1, depth2, depth3, depth], pred_seg=seg, sample1=coords1, sample2=coords2)
+
+    def backward(self, g_depth1, g_depth2, g_depth3, g_depth_rows, g_seg_rows):
+        """g_depth1..3: fp32 [B,h_i,w_i] gradients of the three coarse maps from THEIR OWN losses (what later stages add through
+        the anchor depths is accumulated here); g_depth_rows / g_seg_rows: bf16 [B*H*W, 16] gradients to the outputs of
+        get_depth (ahead of the sigmoid) / get_seg.  Fills every flat gradient buffer; returns (d x32 [B,h,w,D], d C4, d C3)."""
+        td = self.td
+        C1, C2, C3 = self.Cs
+        B, (H1, W1), (H2, W2), (H3, W3) = self._shapes
+        e1, e2, e3 = self.entries
+        s1, s2, s3 = self.stages
+        d_buf4, d_depth2 = self.tail.backward(g_depth3, g_depth_rows, g_seg_rows)
         g = s3.backward(d_buf4[:, :C3].contiguous(), d_buf4[:, C3:C3 + td].contiguous(), d_buf4[:, C3 + td:C3 + 2 * td].contiguous())
         d_x2, d_d2, d_t2, _ = e3.backward(*g)
-        d_depth2 = d_depth2 + self._silog(depth2.view(B, 1, H2, W2), depth_gt, self.scale_weights[1], self.loss12[1:2]).view(B, H2, W2)
+        d_depth2 = d_depth2 + g_depth2.view(B, H2, W2)
         d_buf2, d_depth1 = self.point1.backward(d_depth2)
         g = s2.backward(d_x2.view(-1, C2) + d_buf2[:, :C2], d_d2 + d_buf2[:, C2:C2 + td], d_t2)
         d_x1, d_d1, d_t1, d_c3 = e2.backward(*g, need_dfeat=True)
-        d_depth1 = d_depth1 + self._silog(depth1.view(B, 1, H1, W1), depth_gt, self.scale_weights[0], self.loss12[0:1]).view(B, H1, W1)
+        d_depth1 = d_depth1 + g_depth1.view(B, H1, W1)
         dh_x, dh_d = self.head16.backward(d_depth1.view(-1))
         g = s1.backward(d_x1.view(-1, C1) + dh_x, d_d1 + dh_d, d_t1)
         d_x32, _, _, d_c4 = e1.backward(*g, need_dfeat=True)
-        outs = dict(pred_depth=[depth1, depth2, depth3, depth], pred_seg=seg, sample1=coords1, sample2=coords2)
-        return outs, torch.cat([self.loss12, l345]), d_x32, d_c4, d_c3
+        return d_x32, d_c4, d_c3
+
+    def loss_grads(self, outs, depth_gt, seg_gt):
+        """the five dense losses of the engine's loop (src/engine_glassrgbd.py:65-90) on the forward outputs: fills the loss
+        buffers and returns the five gradients `backward` takes"""
+        B, (H1, W1), (H2, W2), (H3, W3) = self._shapes
+        d1, d2, d3, depth = outs["pred_depth"]
+        g1 = self._silog(d1.view(B, 1, H1, W1), depth_gt, self.scale_weights[0], self.loss12[0:1])
+        g2 = self._silog(d2.view(B, 1, H2, W2), depth_gt, self.scale_weights[1], self.loss12[1:2])
+        g3 = self._silog(d3.view(B, 1, H3, W3), depth_gt, self.scale_weights[2], self.tail.loss3)
+        g_depth_rows, g_seg_rows = self.tail.head.loss_grads(depth, outs["pred_seg"], depth_gt, seg_gt)
+        return g1, g2, g3, g_depth_rows, g_seg_rows
+
+    def losses(self):
+        """fp32 [5] on the device: weighted (depth1, depth2, depth3, depth, seg) of the last loss_grads call"""
+        return torch.cat([self.loss12, self.tail.loss3, self.tail.head.losses])
+
+    def _loss_and_grads(self, x32, depth0, feats, depth_gt, seg_gt, pinned=None):
+        """forward + the five losses + backward.  depth_gt fp32 [B,1,H,W] metres; seg_gt int64 [B,1,H,W].
+        Returns (outputs dict, losses fp32 [5] = weighted (depth1, depth2, depth3, depth, seg), d x32, d C4, d C3)."""
+        H, W = depth_gt.shape[-2:]
+        outs = self.forward(x32, depth0, feats, H, W, pinned)
+        d_x32, d_c4, d_c3 = self.backward(*self.loss_grads(outs, depth_gt, seg_gt))
+        return outs, self.losses(), d_x32, d_c4, d_c3
 
     def step(self):
         """one gradient exchange per flat buffer, ONE clip norm over all of them (src/engine_glassrgbd.py:155-159), AdamW"""

@@ -134,17 +134,32 @@ class DenseHead(FlatModule):
         return d_x
 
     # ------------------------------------------------------------------ losses
-    def loss_and_grads(self, buf4, depth_gt, seg_gt, H=None, W=None):
-        """forward + SilogLoss (last scale) + SegLoss + backward.  depth_gt fp32 [B,1,H,W] metres, seg_gt int64 [B,1,H,W].
-        Returns (depth, seg, losses fp32 [2] on the device = weighted (loss_depth, loss_seg), d(buf4))."""
-        H, W = H or depth_gt.shape[-2], W or depth_gt.shape[-1]
-        depth, seg = self.forward(buf4, H, W)
+    def loss_grads(self, depth, seg, depth_gt, seg_gt):
+        """SilogLoss (last scale, weight 1) + SegLoss x 2 on the forward outputs: fills self.losses (weighted (loss_depth,
+        loss_seg)) and returns the bf16 [B*H*W, 16] gradient rows `backward` takes"""
         log_only = bool(self.cfg.get("log_depth_error", False))
         sums = ops.silog_sums(depth, depth_gt, log_only=log_only)
         g_depth = ops.silog_bwd(depth, depth_gt, sums, weight=self.depth_weight, log_only=log_only,
                                 variance_focus=float(self.cfg.get("variance_focus", 0.85)), sig_scale=float(self.cfg["max_depth"]),
                                 out_cols=16, loss_out=self.losses[0:1])
         _, g_seg = ops.seg_ce(seg, seg_gt.contiguous(), weight=self.seg_weight, out_cols=16, loss_out=self.losses[1:2])
+        return g_depth, g_seg
+
+    def cotangent_rows(self, depth, d_depth, d_seg):
+        """external cotangents (the reference engine's autograd: d depth fp32 [B,1,H,W] in metres, d seg fp32 [B,2,H,W]) -> the
+        bf16 [B*H*W, 16] gradient rows `backward` takes (sigmoid * max_depth derivative from the kept output)"""
+        md = float(self.cfg["max_depth"])
+        g_depth = ops.act_bwd(d_depth.reshape(-1, 1).float().contiguous(), depth.reshape(-1, 1), ACT_SIGMOID, out_cols=16,
+                              y_mul=1.0 / md, scale=md)
+        g_seg = ops.act_bwd(d_seg.permute(0, 2, 3, 1).reshape(-1, d_seg.shape[1]).float().contiguous(), None, ACT_NONE, out_cols=16)
+        return g_depth, g_seg
+
+    def loss_and_grads(self, buf4, depth_gt, seg_gt, H=None, W=None):
+        """forward + SilogLoss (last scale) + SegLoss + backward.  depth_gt fp32 [B,1,H,W] metres, seg_gt int64 [B,1,H,W].
+        Returns (depth, seg, losses fp32 [2] on the device = weighted (loss_depth, loss_seg), d(buf4))."""
+        H, W = H or depth_gt.shape[-2], W or depth_gt.shape[-1]
+        depth, seg = self.forward(buf4, H, W)
+        g_depth, g_seg = self.loss_grads(depth, seg, depth_gt, seg_gt)
         d_buf4 = self.backward(g_depth, g_seg)
         return depth, seg, self.losses, d_buf4
 

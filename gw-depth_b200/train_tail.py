@@ -52,30 +52,48 @@ class DenseTail:
         g.update(self.point.grads())
         return g
 
-    def loss_and_grads(self, buf4, depth2, coords, pos, depth_gt, seg_gt):
-        """buf4: bf16 [B, H/4, W/4, width] stage buffer (the depth_pred3 column and the padding are overwritten);
-        depth2: fp32 [B, H/8, W/8]; coords: fp32 [B,K,2]; pos: fp32 [H/4*W/4, C] position table; depth_gt fp32 [B,1,H,W] metres;
-        seg_gt int64 [B,1,H,W].  Returns (depth3, depth, seg, losses fp32 [3] = weighted (scale-3 depth, full depth, seg),
-        d(buf4) bf16 [rows, width] with zeros beyond the token columns, d(depth2) fp32 [B, H/8, W/8])."""
+    def forward(self, buf4, depth2, coords, pos, H, W):
+        """buf4: bf16 [B, H/4, W/4, width] stage buffer (the depth_pred3 column and the padding are overwritten); depth2:
+        fp32 [B, H/8, W/8]; coords: fp32 [B,K,2]; pos: fp32 [H/4*W/4, C] position table.  Returns (depth3 fp32 [B,H/4,W/4] in
+        [0,1], depth fp32 [B,1,H,W] metres, seg fp32 [B,2,H,W] logits); the modules keep their tapes."""
         B, H4, W4, width = buf4.shape
+        col = self.C + 2 * self.td
+        buf2d = buf4.view(B * H4 * W4, width)
+        buf2d[:, col:] = 0
+        depth3 = self.point.forward(buf2d, depth2, coords, pos, B, H4, W4)
+        buf2d[:, col] = depth3.reshape(-1).to(torch.bfloat16)
+        depth, seg = self.head.forward(buf4, H, W)
+        self._shape = (B, H4, W4)
+        return depth3, depth, seg
+
+    def backward(self, g_depth3, g_depth_rows, g_seg_rows):
+        """g_depth3: fp32 [B,H/4,W/4] gradient of depth_pred3 from ITS OWN loss (the head's use of it is added here);
+        g_depth_rows / g_seg_rows: bf16 [B*H*W, 16] gradients to the outputs of get_depth (ahead of the sigmoid) / get_seg.
+        Returns (d(buf4) bf16 [rows, width] with zeros beyond the token columns, d(depth2) fp32 [B, H/8, W/8])."""
+        B, H4, W4 = self._shape
         C, td = self.C, self.td
         col = C + 2 * td
-        rows = B * H4 * W4
-        buf2d = buf4.view(rows, width)
-        buf2d[:, col:] = 0
-        depth3 = self.point.forward(buf2d, depth2, coords, pos, B, H4, W4)                       # fp32 [B,H4,W4] in [0,1]
-        buf2d[:, col] = depth3.reshape(-1).to(torch.bfloat16)
-        depth, seg, head_losses, d_buf = self.head.loss_and_grads(buf4, depth_gt, seg_gt)
+        d_buf = self.head.backward(g_depth_rows, g_seg_rows)
+        d_depth3 = g_depth3.view(B, H4, W4) + d_buf[:, col].float().view(B, H4, W4)
+        d_pp, d_depth2 = self.point.backward(d_depth3)
+        d_buf[:, :C + td] += d_pp[:, :C + td]
+        d_buf[:, col:] = 0
+        return d_buf, d_depth2
+
+    def loss_and_grads(self, buf4, depth2, coords, pos, depth_gt, seg_gt):
+        """forward + the three losses that sit on this tail + backward.  depth_gt fp32 [B,1,H,W] metres; seg_gt int64 [B,1,H,W].
+        Returns (depth3, depth, seg, losses fp32 [3] = weighted (scale-3 depth, full depth, seg), d(buf4), d(depth2))."""
+        B, H4, W4, _ = buf4.shape
+        H, W = depth_gt.shape[-2:]
+        depth3, depth, seg = self.forward(buf4, depth2, coords, pos, H, W)
+        g_depth_rows, g_seg_rows = self.head.loss_grads(depth, seg, depth_gt, seg_gt)
         log_only = bool(self.cfg.get("log_depth_error", False))
         p3 = depth3.view(B, 1, H4, W4)
         sums = ops.silog_sums(p3, depth_gt, log_only=log_only)
         d3 = ops.silog_bwd(p3, depth_gt, sums, weight=self.scale3_weight, log_only=log_only,
                            variance_focus=float(self.cfg.get("variance_focus", 0.85)), loss_out=self.loss3)
-        d_depth3 = d3.view(B, H4, W4) + d_buf[:, col].float().view(B, H4, W4)
-        d_pp, d_depth2 = self.point.backward(d_depth3)
-        d_buf[:, :C + td] += d_pp[:, :C + td]
-        d_buf[:, col:] = 0
-        return depth3, depth, seg, torch.cat([self.loss3, head_losses]), d_buf, d_depth2
+        d_buf, d_depth2 = self.backward(d3, g_depth_rows, g_seg_rows)
+        return depth3, depth, seg, torch.cat([self.loss3, self.head.losses]), d_buf, d_depth2
 
     def step(self):
         """one gradient exchange per flat buffer, ONE clip norm over all of them (src/engine_glassrgbd.py:155-159), AdamW"""

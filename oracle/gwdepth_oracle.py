@@ -533,15 +533,16 @@ def dense_head(feat4, depth3, dt4, st4, size, p, max_depth):
 # ----------------------------------------------------------------------------------------------
 # full model                                                    src/models/glassrgbd.py:74-123
 # ----------------------------------------------------------------------------------------------
-def forward(sd, images, mask=None, cfg=None, pinned=None, trace=None):
+def forward(sd, images, mask=None, cfg=None, pinned=None, trace=None, grad=False):
     """images [B,3,H,W] float32 (already padded to a common size), mask [B,H,W] bool (True = pad) or None.
-    Returns the reference's output dict: pred_logits, pred_lines, aux_outputs, pred_depth (list of 4), pred_seg."""
+    Returns the reference's output dict: pred_logits, pred_lines, aux_outputs, pred_depth (list of 4), pred_seg.
+    grad=True keeps the autograd graph (weights with requires_grad: the gradient oracle of the training tests)."""
     cfg = dict(DEFAULT_CFG, **(cfg or {}))
     p = P(sd)
     B, _, H, W = images.shape
     if mask is None:
         mask = torch.zeros(B, H, W, dtype=torch.bool, device=images.device)
-    with torch.no_grad():
+    with torch.set_grad_enabled(grad):
         feats = resnet50_features(images, p.sub("backbone.0.body"))
         masks = [downsample_mask(mask, f.shape[-2:]) for f in feats]
         c5, m5 = feats[3], masks[3]
@@ -588,7 +589,7 @@ def hungarian(costs):
     from scipy.optimize import linear_sum_assignment
     res = []
     for c in costs:
-        i, j = linear_sum_assignment(c.cpu().numpy())
+        i, j = linear_sum_assignment(c.detach().cpu().numpy())
         res.append((torch.as_tensor(i, dtype=torch.int64), torch.as_tensor(j, dtype=torch.int64)))
     return res
 

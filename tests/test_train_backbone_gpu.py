@@ -47,22 +47,51 @@ def test_stride2_helpers(B, H, W, C):
     want = add.float().clone()
     want[:, ::2, ::2] += x[:, ::2, ::2].float()
     assert rel_l2(z, want) < 4e-3
-    z0 = ops.zero_stuff2(sub, H, W)
-    assert float(z0.float().abs().sum().cpu()) == float(x[:, ::2, ::2].float().abs().sum())
+    z0 = ops.zero_stuff2(sub, H, W).cpu()
+    want0 = torch.zeros_like(x)
+    want0[:, ::2, ::2] = x[:, ::2, ::2]
+    assert torch.equal(z0, want0)
+
+
+def _bf16_emulated_bottleneck():
+    """the oracle's bottleneck with every stored activation rounded to bf16 (straight-through): the yard-stick that separates
+    bf16 storage noise (ReLU masks of a random network flip under rounding) from kernel defects"""
+    q = lambda t: t + (t.bfloat16().float() - t).detach()  # noqa: E731
+
+    def bottleneck(x, p, stride):
+        out = q(F.relu(oracle.frozen_bn(F.conv2d(x, p["conv1.weight"]), p, "bn1")))
+        out = q(F.relu(oracle.frozen_bn(F.conv2d(out, p["conv2.weight"], stride=stride, padding=1), p, "bn2")))
+        out = oracle.frozen_bn(F.conv2d(out, p["conv3.weight"]), p, "bn3")
+        if p.has("downsample.0.weight"):
+            x = q(oracle.frozen_bn(F.conv2d(x, p["downsample.0.weight"], stride=stride), p, "downsample.1"))
+        return q(F.relu(out + x))
+    return bottleneck
+
+
+def _oracle_grads(sd, images, seed, monkeypatch=None):
+    from gwdepth_b200.train_backbone import BODY
+    sdr = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and k.endswith(".weight") and ("conv" in k or "downsample.0" in k)
+                                                   and any(("layer%d." % i) in k for i in (2, 3, 4))) else v) for k, v in sd.items()}
+    feats = oracle.resnet50_features(images, oracle.P(sdr, BODY))                       # C2..C5, NCHW fp32
+    g = torch.Generator().manual_seed(seed)
+    cots = [torch.randn(f.shape, generator=g) * (f > 0) for f in feats[1:]]
+    sum((f * c).sum() for f, c in zip(feats[1:], cots)).backward()
+    return feats, cots, {k: v.grad for k, v in sdr.items() if isinstance(v, torch.Tensor) and v.requires_grad}
 
 
 @pytest.mark.parametrize("B,H,W", [(1, 64, 96), (2, 72, 104)])
-def test_backbone_gradients_match_oracle_autograd(B, H, W):
+def test_backbone_gradients_match_oracle_autograd(B, H, W, monkeypatch):
+    """forward maps against the fp32 oracle (3e-2); every parameter gradient against torch.autograd over the fp32 oracle, with the
+    bf16-emulated oracle as the yard-stick: with these random weights the ORACLE's own gradients move by 5-16 % when its stored
+    activations are rounded to bf16 (ReLU masks flip), so the bar per tensor is 1.5 x that distance + 3 % (and 0.25 absolute)"""
     _ops()
     from gwdepth_b200.train_backbone import BODY, BackboneTrain
     sd = {k: v.clone() for k, v in synth_weights().items() if k.startswith(BODY)}
     images, _, _, _ = synth.synth_batch(B, H, W, seed=3)
-    sdr = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and k.endswith(".weight") and ("conv" in k or "downsample.0" in k)
-                                                   and any(("layer%d." % i) in k for i in (2, 3, 4))) else v) for k, v in sd.items()}
-    feats = oracle.resnet50_features(images, oracle.P(sdr, BODY))                       # C2..C5, NCHW fp32
-    g = torch.Generator().manual_seed(B)
-    cots = [torch.randn(f.shape, generator=g) * (f > 0) for f in feats[1:]]
-    sum((f * c).sum() for f, c in zip(feats[1:], cots)).backward()
+    feats, cots, ref = _oracle_grads(sd, images, B)
+    monkeypatch.setattr(oracle, "bottleneck", _bf16_emulated_bottleneck())
+    _, cots_e, emu = _oracle_grads(sd, images, B)
+    monkeypatch.undo()
     bb = BackboneTrain({k: v.cuda() for k, v in sd.items()}, lr=1e-5)
     for k, v in bb.state_dict().items():
         assert torch.equal(v.cpu(), sd[k]), k
@@ -74,15 +103,11 @@ def test_backbone_gradients_match_oracle_autograd(B, H, W):
     bb.backward(*[c.permute(0, 2, 3, 1).contiguous().bfloat16().cuda() for c in cots])
     grads = bb.grads()
     bad = {}
-    n = 0
-    for k, v in sdr.items():
-        if not (isinstance(v, torch.Tensor) and v.requires_grad):
-            continue
-        n += 1
-        e = rel_l2(grads[k], v.grad)
-        if e > 6e-2:
-            bad[k] = round(e, 3)
-    assert n == 13 * 3 + 3 and not bad, (n, bad)
+    for k, r in ref.items():
+        e, yard = rel_l2(grads[k], r), rel_l2(emu[k], r)
+        if e > min(1.5 * yard + 0.03, 0.25):
+            bad[k] = (round(e, 3), round(yard, 3))
+    assert len(ref) == 13 * 3 + 3 and not bad, (len(ref), bad)
     # one optimizer step keeps the folded mirror = bf16(parameter * frozen-BN scale)
     before = bb.P.clone()
     bb.step()
