@@ -104,6 +104,44 @@ def _init_parameters(module):
             b.fill_(1.0)
 
 
+class _TrainStep(torch.autograd.Function):
+    """autograd edge between the reference's training loop and train_model.Trainer: forward runs the engine's forward with
+    the activations kept, backward takes the cotangents of every output the criteria touched, runs the engine's backward and
+    returns the gradient of every trained nn.Parameter (so DistributedDataParallel's hooks fire exactly as in the reference;
+    the 54 never-used tensors are not inputs, which is what find_unused_parameters=True expects)."""
+
+    @staticmethod
+    def forward(ctx, module, images, pinned, *params):
+        tr = module.trainer()
+        with torch.no_grad():
+            logits, lines, outs = tr.forward(images, pinned)
+        d1, d2, d3, depth = outs["pred_depth"]
+        ctx.module, ctx.depth = module, depth
+        ctx.shapes = [tuple(t.shape) for t in (logits, lines, d1, d2, d3, depth, outs["pred_seg"])]
+        return logits, lines, d1.unsqueeze(1), d2.unsqueeze(1), d3.unsqueeze(1), depth, outs["pred_seg"]
+
+    @staticmethod
+    def backward(ctx, g_logits, g_lines, g1, g2, g3, g_depth, g_seg):
+        module = ctx.module
+        tr = module.trainer()
+        dev = ctx.depth.device
+        def dense(g, shp, keep_layout=False):      # outputs no criterion touched arrive as None
+            if g is None:
+                return torch.zeros(shp, dtype=torch.float32, device=dev)
+            return g.float() if keep_layout else g.float().reshape(shp).contiguous()
+        shp = ctx.shapes
+        g_logits, g_lines = dense(g_logits, shp[0]), dense(g_lines, shp[1])
+        g1, g2, g3, g_depth = dense(g1, shp[2]), dense(g2, shp[3]), dense(g3, shp[4]), dense(g_depth, shp[5])
+        g_seg = dense(g_seg, shp[6], keep_layout=True)        # [B,2,H,W]; cotangent_rows makes it channels-last
+        with torch.no_grad(), torch.cuda.device(dev):
+            rows_d, rows_s = tr.dense.tail.head.cotangent_rows(ctx.depth, g_depth, g_seg)
+            tr.backward_dense(g1, g2, g3, rows_d, rows_s)
+            tr.backward_line(g_logits, g_lines)
+            grads = tr.grads()
+            out = tuple(grads[n].clone() for n, _ in module.__dict__["_live"])
+        return (None, None, None) + out
+
+
 class GlassRGBD(_Node):
     """Drop-in for src/models/glassrgbd.py:44-123 (flag set --with_line --with_center --with_dense)."""
 
@@ -164,8 +202,7 @@ class GlassRGBD(_Node):
             images, mask = samples.decompose()
             assert mask is not None
         if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("backward kernels are not built yet: run the forward under torch.no_grad() / "
-                                      "model.eval() (DESIGN.md, 'what comes next')")
+            return self._forward_train(samples, images, mask, _pinned)
         plan = self.plan()      # raises off-GPU: there is no CPU path
         padded = getattr(samples, "padded", None)      # set on the host by nested_tensor_from_tensor_list (no sync)
         if mask is not None and padded is None:
@@ -178,6 +215,76 @@ class GlassRGBD(_Node):
                 return plan.forward_graphed(x)
             return plan.forward(x, pinned=_pinned, trace=_trace)
 
+
+    # ------------------------------------------------------------------ training (src/engine_glassrgbd.py:45-166)
+    def trainer(self, **optim):
+        """the whole-model training engine (train_model.Trainer) behind this module, built on first use from the module's
+        parameters.  Two ways to train:
+          * drop-in: `out = model(samples)` under model.train() returns tensors with an autograd edge into the engine, so the
+            reference's loop (criteria on `out`, `losses.backward()`, clip_grad_norm_, optimizer.step()) runs unmodified; the
+            engine's flat buffers are re-loaded from the nn.Parameters whenever an optimizer has changed them;
+          * fused: `model.trainer(lr=..., ...).train_step(images, targets, depth_gt, seg_gt, criterion)` does forward, losses,
+            backward, gradient exchange, clip and AdamW on the flat buffers (call `model.sync_from_trainer()` before
+            `state_dict()` / evaluation)."""
+        from .train_model import Trainer
+        if self.__dict__.get("_trainer") is None:
+            dev = next(self.parameters()).device
+            if dev.type != "cuda":
+                raise RuntimeError("GlassRGBD trains on sm_100a CUDA kernels only; move the model to a CUDA device")
+            if float(getattr(self.args, "dropout", 0.0)) != 0.0:
+                raise NotImplementedError("train-mode dropout in the DETR layers is not built: construct the model with "
+                                          "--dropout 0.0 (the gradient-parity configuration, SURVEY.md 8c)")
+            a = self.args
+            kw = dict(lr=getattr(a, "lr", 1e-4), lr_backbone=getattr(a, "lr_backbone", 1e-5), weight_decay=getattr(a, "weight_decay", 1e-4),
+                      max_norm=getattr(a, "clip_max_norm", 0.1),
+                      depth_loss_weights=tuple(getattr(a, "depth_loss_weights", (0.25, 0.25, 0.25, 1.0))),
+                      seg_loss_weight=float(getattr(a, "seg_loss_weight", 2.0)))
+            kw.update(optim)
+            cfg = dict(self.cfg, log_depth_error=bool(getattr(a, "log_depth_error", False)),
+                       variance_focus=float(getattr(a, "variance_focus", 0.85)))
+            self.__dict__["_trainer"] = Trainer(self.state_dict(), cfg, device=dev, **kw)
+            self.__dict__["_trainer_versions"] = self._param_versions()
+            live = set(self.__dict__["_trainer"].state_dict())
+            self.__dict__["_live"] = [(n, p) for n, p in self.named_parameters() if n in live and p.requires_grad]
+        return self.__dict__["_trainer"]
+
+    def _param_versions(self):
+        return tuple(p._version for p in self.parameters())
+
+    def sync_from_trainer(self):
+        """copy the engine's master parameters back into the nn.Parameters (after fused training steps)"""
+        tr = self.__dict__.get("_trainer")
+        if tr is not None:
+            sd = tr.state_dict()
+            with torch.no_grad():
+                for n, p in self.named_parameters():
+                    if n in sd:
+                        p.copy_(sd[n])
+            self.__dict__["_trainer_versions"] = self._param_versions()
+            self._plan = None
+
+    def _forward_train(self, samples, images, mask, pinned):
+        padded = getattr(samples, "padded", None)
+        if mask is not None and padded is None:
+            padded = bool(mask.any())
+        if padded:
+            raise NotImplementedError("training on padded (ragged) batches is not built: collate equal-size images")
+        tr = self.trainer()
+        vers = self._param_versions()
+        if vers != self.__dict__["_trainer_versions"]:        # an optimizer (or load_state_dict) changed the nn.Parameters
+            tr.load_params(self.state_dict())
+            self.__dict__["_trainer_versions"] = vers
+        tr.exchange_grads = False          # the caller's DistributedDataParallel (or nobody) reduces the .grad tensors
+        live = self.__dict__["_live"]
+        with torch.cuda.device(images.device):
+            res = _TrainStep.apply(self, images.float().contiguous(), pinned, *[p for _, p in live])
+        logits, lines, d1, d2, d3, depth, seg = res
+        out = {"pred_logits": logits[-1], "pred_lines": lines[-1]}
+        if self.cfg["aux_loss"]:
+            out["aux_outputs"] = [{"pred_logits": a, "pred_lines": b} for a, b in zip(logits[:-1], lines[:-1])]
+        out["pred_depth"] = [d1, d2, d3, depth]
+        out["pred_seg"] = seg
+        return out
 
     @torch.no_grad()
     def infer_stream(self, host_batches, keys=("pred_logits", "pred_lines", "pred_depth", "pred_seg")):
@@ -359,6 +466,26 @@ class HungarianMatcher_Line(nn.Module):
         return result
 
     @torch.no_grad()
+    def set_pairs(self, pairs, targets):
+        """install a given stacked assignment (list over stages of per-image (idx_pred, idx_tgt)) as if `stacked_solve` had
+        found it: parity tests pin the discrete matching to the oracle's, exactly like the line / sample selections"""
+        import numpy as np
+        S, B = len(pairs), len(pairs[0])
+        sizes = [len(v["lines"]) for v in targets]
+        starts = np.concatenate([[0], np.cumsum(sizes)])
+        cols, per_stage = [], []
+        for s_, stage in enumerate(pairs):
+            n = 0
+            for b, (qi, ti) in enumerate(stage):
+                qi, ti = np.asarray(qi, dtype=np.int64), np.asarray(ti, dtype=np.int64)
+                cols.append(np.stack([np.full_like(qi, s_), np.full_like(qi, b), qi, ti + starts[b]]))
+                n += len(qi)
+            per_stage.append(n)
+        match = np.concatenate(cols, axis=1).astype(np.int32) if cols else np.zeros((4, 0), np.int32)
+        self.last_match = (np.ascontiguousarray(match), np.concatenate([[0], np.cumsum(per_stage)]).astype(np.int32))
+        self.last_raw = None
+
+    @torch.no_grad()
     def forward_stacked(self, logits, lines, targets, want_pairs=True):
         """All S decoder stages at once (the reference calls the matcher once per stage, src/models/glassrgbd.py:318,344):
         logits [S,B,Q,C], lines [S,B,Q,D] -> list over stages of the per-image (idx_pred, idx_tgt) lists.  ONE
@@ -464,7 +591,7 @@ class SetCriterion(nn.Module):
         return losses
 
     @torch.no_grad()
-    def forward_backward_stacked(self, logits, lines, targets, pending=None):
+    def forward_backward_stacked(self, logits, lines, targets, pending=None, pinned_pairs=None):
         """forward_stacked AND its gradient in one gwd_set_loss launch: -> (losses dict, dlogits, dlines) where the
         gradients are those of sum_k weight_dict[k] * losses[k].  No autograd graph, no per-loss torch kernels: the host
         only solves the assignments and uploads them (one int32 [4, M] copy)."""
@@ -472,7 +599,10 @@ class SetCriterion(nn.Module):
         dev = logits.device
         # `pending`: a handle of matcher.stacked_cost issued earlier (the host solve then overlaps whatever GPU work the caller
         # enqueued in between)
-        self.matcher.stacked_solve(pending if pending is not None else self.matcher.stacked_cost(logits, lines, targets), want_pairs=False)
+        if pinned_pairs is not None:
+            self.matcher.set_pairs(pinned_pairs, targets)
+        else:
+            self.matcher.stacked_solve(pending if pending is not None else self.matcher.stacked_cost(logits, lines, targets), want_pairs=False)
         n = torch.as_tensor([sum(len(t["labels"]) for t in targets)], dtype=torch.float, device=dev)
         if _world_size() > 1:
             torch.distributed.all_reduce(n)

@@ -59,7 +59,7 @@ class LineBranch:
         # run with scale 1 -- the tcgen05 forward kernel's fast path -- and the backward multiplies dQ / dK back
         self.rs = float((self.cfg["hidden_dim"] // self.cfg["nheads"]) ** -0.25)
         # ---- flat layout: 2-D weights [N, K] are stored with N padded to 16 (zero rows), vectors padded to 16
-        self.index, off = {}, 0
+        self.index, self.shapes, off = {}, {}, 0
         for name, v in state_dict.items():
             if not (name.startswith(PREFIXES) and v.is_floating_point()):
                 continue
@@ -68,6 +68,7 @@ class LineBranch:
             assert len(logical) <= 2 and (len(logical) == 1 or logical[1] % 16 == 0), name
             size = padded[0] * (padded[1] if len(padded) == 2 else 1)
             self.index[name] = (off, padded, logical)
+            self.shapes[name] = tuple(v.shape)           # e.g. input_proj.weight is [256, 2048, 1, 1] in the reference
             off += size
         self.numel = off
         self.P = torch.zeros(off, dtype=torch.float32, device=self.dev)
@@ -90,10 +91,17 @@ class LineBranch:
 
     def state_dict(self):
         """logical fp32 parameters under the reference's key names"""
-        return {name: self.view(self.P, name)[: lg[0]].clone() for name, (_, _, lg) in self.index.items()}
+        return {name: self.view(self.P, name)[: lg[0]].clone().view(self.shapes[name]) for name, (_, _, lg) in self.index.items()}
 
     def grads(self):
-        return {name: self.view(self.G, name)[: lg[0]] for name, (_, _, lg) in self.index.items()}
+        """logical gradients in the reference's shapes (views of the flat gradient buffer)"""
+        return {name: self.view(self.G, name)[: lg[0]].view(self.shapes[name]) for name, (_, _, lg) in self.index.items()}
+
+    def load_params(self, state_dict):
+        """overwrite the master parameters (and the bf16 mirror) from a reference-keyed state dict; optimizer moments are kept"""
+        for name, (_, _, logical) in self.index.items():
+            self.view(self.P, name)[: logical[0]] = state_dict[name].detach().to(self.dev, torch.float32).reshape(logical)
+        self.Wb.copy_(self.P)
 
     def _mha(self, p, fused):
         E = self.cfg["hidden_dim"]

@@ -116,6 +116,11 @@ class BackboneTrain(FlatModule):
             out[BODY + k] = v
         return out
 
+    def _adapt(self, short, v):
+        if short in self._s2:
+            return v.permute(0, 2, 3, 1).reshape(v.shape[0], -1)
+        return v.reshape(self.index[short][2])
+
     def state_dict(self):
         return self._names(super().state_dict(""))
 
@@ -125,8 +130,6 @@ class BackboneTrain(FlatModule):
     # ------------------------------------------------------------------ folded FrozenBatchNorm
     def refresh_mirror(self):
         """bf16 mirror = parameter * s[n] (after construction and after every optimizer step)"""
-        if not hasattr(self, "Wb"):
-            return
         ops.fold_mirror(self.P, self.S, self.Wb)
 
     def finish_grads(self):

@@ -133,6 +133,29 @@ class FlatModule:
     def grads(self, prefix=""):
         return {prefix + s: self._to_logical(s, self.view(self.G, s)) for s in self.index}
 
+    # ------------------------------------------------------------------ re-loading parameters (drop-in path: torch optimizers
+    # update the nn.Parameters, the flat buffers follow)
+    def _key_map(self):
+        """{short name: reference state_dict key}; state_dict() walks self.index in order, so the two lists align"""
+        if getattr(self, "_keys", None) is None:
+            full = list(self.state_dict().keys())[:len(self.index)]
+            self._keys = dict(zip(self.index.keys(), full))
+        return self._keys
+
+    def _adapt(self, short, v):
+        """reference-shaped tensor -> this module's logical shape"""
+        return v.reshape(self.index[short][2])
+
+    def refresh_mirror(self):
+        self.Wb.copy_(self.P)
+
+    def load_params(self, state_dict):
+        """overwrite the master parameters (and the bf16 mirror) from a reference-keyed state dict; optimizer moments are kept"""
+        for short, full in self._key_map().items():
+            v = state_dict[full].detach().to(self.dev, torch.float32)
+            self.view(self.P, short).copy_(self._to_physical(short, self._adapt(short, v)))
+        self.refresh_mirror()
+
     def ln(self, name):
         """(gamma, beta, dgamma, dbeta) views of a LayerNorm"""
         return tuple(self.view(f, "%s.%s" % (name, wb)) for f in (self.P, self.G) for wb in ("weight", "bias"))

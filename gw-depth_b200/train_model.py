@@ -53,6 +53,7 @@ class Trainer:
         self.dense.tail.head.depth_weight, self.dense.tail.head.seg_weight = depth_loss_weights[3], seg_loss_weight
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self._works = []
+        self.exchange_grads = True
         self.last = {}
 
     # ------------------------------------------------------------------ bookkeeping
@@ -63,19 +64,25 @@ class Trainer:
     def state_dict(self):
         """logical fp32 parameters under the reference's key names (the trained tensors only)"""
         sd = {}
-        for m in (self.backbone, self.stage32, self.dense):
+        for m in (self.backbone, self.line, self.stage32, self.dense):
             sd.update(m.state_dict())
-        for k, v in self.line.state_dict().items():
-            sd[k] = v.view(v.shape[0], v.shape[1], 1, 1) if k == "input_proj.weight" else v
         return sd
 
     def grads(self):
+        """gradients of the last backward under the reference's key names and shapes"""
         g = {}
-        for m in (self.backbone, self.stage32, self.dense):
+        for m in (self.backbone, self.line, self.stage32, self.dense):
             g.update(m.grads())
-        for k, v in self.line.grads().items():
-            g[k] = v.view(v.shape[0], v.shape[1], 1, 1) if k == "input_proj.weight" else v
         return g
+
+    def load_params(self, state_dict):
+        """overwrite every flat master buffer (and its bf16 mirror) from a reference-keyed state dict: the drop-in path calls
+        this when a torch optimizer has updated the nn.Parameters; the optimizer moments of the fused step are kept"""
+        for m in self.modules():
+            if isinstance(m, FlatModule):
+                FlatModule.load_params(m, state_dict)
+            else:
+                m.load_params(state_dict)
 
     def numel(self):
         return sum(m.numel for m in self.modules())
@@ -122,8 +129,9 @@ class Trainer:
 
     # ------------------------------------------------------------------ backward
     def _exchange(self, mods):
-        """asynchronous all-reduce of flat gradient buffers whose backward has been enqueued"""
-        if parallel.world_size() > 1:
+        """asynchronous all-reduce of flat gradient buffers whose backward has been enqueued (exchange_grads = False: someone
+        else reduces the gradients, e.g. DistributedDataParallel around the drop-in module)"""
+        if self.exchange_grads and parallel.world_size() > 1:
             for m in mods:
                 self._works.append(dist.all_reduce(m.G, async_op=True))
 

@@ -62,6 +62,10 @@ class PointPred(FlatModule):
         g.update(self.pyramid.grads())
         return g
 
+    def load_params(self, state_dict):
+        super().load_params(state_dict)
+        self.pyramid.load_params(state_dict)
+
     # ------------------------------------------------------------------ forward
     def forward(self, buf, pre_depth, coords, pos, B, H, W):
         """buf: bf16 [B*H*W, in_width] stage buffer; pre_depth: fp32 [B,h,w] previous scale's depth; coords: fp32 [B,K,2]

@@ -17,7 +17,10 @@ from unittest.mock import MagicMock
 
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("GWD_REFERENCE_ROOT", "/root/reference")
+_STAGED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+# the build container mounts the reference read-only at /root/reference; oracle/stage_ref.sh stages an unmodified copy under
+# baseline/_ref (git-ignored, travels with gpurun) for the GPU box
+REFERENCE_ROOT = os.environ.get("GWD_REFERENCE_ROOT") or ("/root/reference" if os.path.isdir("/root/reference/src/models") else _STAGED)
 
 # the flag set of the only working full configuration
 DEFAULT_FLAGS = ["--device", "cpu", "--num_queries", "100", "--with_line",

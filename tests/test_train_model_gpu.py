@@ -1,0 +1,208 @@
+"""GPU parity of the WHOLE-MODEL training step (train_model.Trainer behind GlassRGBD, SURVEY 8b / VERDICT r1 items 1-3):
+  * gradients of all 684 trained tensors (738 trainable minus the 54 the reference never reaches) against
+    torch.autograd over the fp32 CPU oracle on the same batch, selections and matchings pinned to the oracle's;
+  * the drop-in surface: the reference's own `train_one_epoch` (src/engine_glassrgbd.py:22-171, imported unmodified from
+    baseline/_ref when it is staged; a line-by-line mirror of its loop otherwise) drives `model(samples)` ->
+    criteria -> `losses.backward()` -> clip_grad_norm_ -> torch AdamW for two steps;
+  * the fused step (Trainer.train_step) equals the drop-in step's losses and gradients.
+
+Gradient tolerances: this synthetic network is sensitive to bf16 storage itself -- the ORACLE's own gradients move by 5-50 % per
+module when its weights and stored activations are rounded to bf16 (straight-through), see DESIGN.md section 4 -- so every module
+is held to 1.5 x that distance + 3 % (the modules next to the losses, where no amplification happens, to 8 % absolute)."""
+import collections
+import math
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import oracle, synth, synth_weights
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _mods():
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import model as M
+    from gwdepth_b200.train_model import Trainer
+    return M, Trainer
+
+
+def rel_l2(got, ref):
+    got, ref = got.double().cpu(), ref.double().cpu()
+    return float((got - ref).norm() / ref.norm().clamp_min(1e-30))
+
+
+def _group(k):
+    return ".".join(k.split(".")[:3]) if k.startswith(("backbone", "transformer")) else ".".join(k.split(".")[:2])
+
+
+def _trainable(sd):
+    """the reference's trainable set: everything but the stem, layer1 and the FrozenBatchNorm buffers (backbone.py:62-64)"""
+    frozen = ("backbone.0.body.conv1", "backbone.0.body.layer1")
+    return {k for k, v in sd.items() if v.is_floating_point() and "running" not in k and ".bn" not in k and "downsample.1" not in k
+            and not k.startswith(frozen)}
+
+
+def _oracle_grads(sd, images, targets, depth_gt, seg_gt, wd, pin=None, emulate=False):
+    """total loss of the engine's loop and its gradients by torch.autograd over the oracle; emulate=True rounds the weights and
+    every stored activation to bf16 (straight-through)"""
+    names = ["linear", "conv2d", "layer_norm", "gelu", "relu", "elu"]
+    orig = {n: getattr(F, n) for n in names}
+    st = lambda t: t + (t.bfloat16().float() - t).detach()  # noqa: E731
+    train = _trainable(sd)
+    leaves = {k: (v.clone().requires_grad_(True) if k in train else v) for k, v in sd.items()}
+    use = {k: (st(v) if (emulate and k in train and v.dim() > 1) else v) for k, v in leaves.items()}
+    try:
+        if emulate:
+            for n in names:
+                setattr(F, n, (lambda f: (lambda *a, **k: st(f(*a, **k))))(orig[n]))
+        trace = {}
+        out = oracle.forward(use, images, pinned=pin, trace=trace, grad=True)
+        tl = [t["lines"] for t in targets]
+        set_l, idx = oracle.set_criterion(out, tl)
+        dl = oracle.depth_losses(out["pred_depth"], depth_gt)
+        total = sum(v * wd[k] for k, v in set_l.items()) + sum(dl) + oracle.seg_loss(out["pred_seg"], seg_gt)
+        total.backward()
+    finally:
+        for n in names:
+            setattr(F, n, orig[n])
+    return float(total), {k: v.grad for k, v in leaves.items() if k in train}, trace, idx
+
+
+def test_whole_model_gradients_match_oracle_autograd():
+    M, Trainer = _mods()
+    B, H, W = 2, 128, 160
+    images, targets, depth_gt, seg_gt = synth.synth_batch(B, H, W, seed=0)
+    sd = synth_weights()
+    _, crit, _ = M.build_model(M.default_args(device="cuda", dropout=0.0))
+    wd = crit[0].weight_dict
+    total, ref, trace, idx = _oracle_grads(sd, images, targets, depth_gt, seg_gt, wd)
+    pin_o = {"line_ids": trace["line_ids"], "sample1": (trace["sample1"], trace["sample1_idx"]), "sample2": (trace["sample2"], trace["sample2_idx"])}
+    _, emu, _, _ = _oracle_grads(sd, images, targets, depth_gt, seg_gt, wd, pin=pin_o, emulate=True)
+    assert sum(g is not None for g in ref.values()) == 684 and len(ref) == 738       # 54 never-used tensors
+
+    tr = Trainer(sd)
+    pinned = {"line_ids": trace["line_ids"].cuda(), "sample1": trace["sample1"].cuda(), "sample2": trace["sample2"].cuda()}
+    tg = [{k: v.cuda() for k, v in t.items()} for t in targets]
+    logits, lines, outs = tr.forward(images.cuda(), pinned)
+    g = tr.dense.loss_grads(outs, depth_gt.cuda(), seg_gt.cuda())
+    tr.backward_dense(*g)
+    stacked = idx[1:] + idx[:1]                    # the oracle lists the final stage first, the stacked layout has it last
+    _, dlogits, dlines = crit[0].cuda().forward_backward_stacked(logits, lines, tg, pinned_pairs=stacked)
+    tr.backward_line(dlogits, dlines)
+    got_total = float(crit[0].last_total + tr.dense.losses().sum())
+    assert abs(got_total - total) < 5e-3 * abs(total), (got_total, total)
+    grads = tr.grads()
+    live = {k for k, v in ref.items() if v is not None}
+    assert set(grads) == live, (sorted(live - set(grads))[:5], sorted(set(grads) - live)[:5])
+    agg = collections.defaultdict(lambda: [0.0, 0.0, 0.0])
+    for k in live:
+        a = agg[_group(k)]
+        a[0] += float((grads[k].double().cpu() - ref[k].double()).pow(2).sum())
+        a[1] += float((emu[k].double() - ref[k].double()).pow(2).sum())
+        a[2] += float(ref[k].double().pow(2).sum())
+        assert grads[k].shape == ref[k].shape and torch.isfinite(grads[k]).all(), k
+    bad = {}
+    near_loss = ("depth_decoder.", "dense_encoder.point_based_pred", "dense_encoder.depth_pred16", "class_embed.")
+    for grp, (e, y, n) in agg.items():
+        e, y = math.sqrt(e / n), math.sqrt(y / n)
+        bar = 0.08 if grp.startswith(near_loss) else 1.5 * y + 0.03
+        if e > bar:
+            bad[grp] = (round(e, 3), round(y, 3))
+    assert not bad, bad
+
+
+def _loader(B, H, W, steps, NestedTensor):
+    for s in range(steps):
+        images, targets, depth_gt, seg_gt = synth.synth_batch(B, H, W, seed=s)
+        mask = torch.zeros(B, H, W, dtype=torch.bool)
+        yield (NestedTensor(images, mask), NestedTensor(depth_gt, mask), NestedTensor(seg_gt, mask), targets, ["synthetic_%d" % s] * B)
+
+
+def _mirror_train_loop(model, criterions, loader, optimizer, device, max_norm, args):
+    """src/engine_glassrgbd.py:22-171 without the logging (used only when the reference tree is not staged under baseline/_ref)"""
+    model.train()
+    criterion, criterion_depth, criterion_seg, _ = criterions
+    log = []
+    for samples, depth_gt, seg_gt, targets, _ in loader:
+        samples, depth_gt, seg_gt = samples.to(device), depth_gt.to(device), seg_gt.to(device)
+        targets = [{k: v.to(device) for k, v in t.items()} for t in targets]
+        outputs = model(samples, reflc_mat=None, img_name="x")
+        loss_dict = criterion(outputs, targets, depth_gt=depth_gt.tensors)
+        mask = (depth_gt.tensors >= 0.2) & (depth_gt.tensors < 10.0)
+        loss_depth = 0.0
+        for i, pd in enumerate(outputs["pred_depth"]):
+            size = pd.shape[-2:]
+            d_gt = F.interpolate(depth_gt.tensors, size=size, mode="nearest")
+            m_rs = F.interpolate(mask.to(torch.uint8), size=size, mode="nearest")
+            loss_depth = loss_depth + criterion_depth(pd, d_gt, m_rs.to(torch.bool)) * args.depth_loss_weights[i]
+        loss_seg = criterion_seg(outputs["pred_seg"], seg_gt.tensors.squeeze(1)) * args.seg_loss_weight
+        losses = sum(loss_dict[k] * criterion.weight_dict[k] for k in loss_dict if k in criterion.weight_dict) + loss_depth + loss_seg
+        assert math.isfinite(float(losses))
+        optimizer.zero_grad()
+        losses.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), max_norm)
+        optimizer.step()
+        log.append(float(losses))
+    return {"loss": sum(log) / len(log)}
+
+
+def test_drop_in_training_loop_and_fused_step():
+    M, Trainer = _mods()
+    B, H, W = 2, 128, 160
+    sd = synth_weights()
+    args = M.default_args(device="cuda", dropout=0.0, lr=1e-4, weight_decay=1e-4, clip_max_norm=0.1, input_log_freq=2.0,
+                          with_plane_norm_loss=False)
+    net, criterions, _ = M.build_model(args)
+    net.load_state_dict(sd)
+    net.cuda()
+    # the reference's optimizer (src/main_glassrgbd.py:59-66)
+    groups = [{"params": [p for n, p in net.named_parameters() if "backbone" not in n and p.requires_grad]},
+              {"params": [p for n, p in net.named_parameters() if "backbone" in n and p.requires_grad], "lr": args.lr_backbone}]
+    assert sum(len(g["params"]) for g in groups) == 738
+    opt = torch.optim.AdamW(groups, lr=args.lr, weight_decay=args.weight_decay)
+    before = {n: p.detach().clone() for n, p in net.named_parameters()}
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shims
+    if ref_shims.reference_available():        # the reference's own loop, unmodified
+        ref_shims.install()
+        from engine_glassrgbd import train_one_epoch
+        from util.misc import NestedTensor
+        stats = train_one_epoch(net, criterions, None, list(_loader(B, H, W, 2, NestedTensor)), opt, torch.device("cuda"), 0,
+                                args.clip_max_norm, args)
+    else:
+        stats = _mirror_train_loop(net, criterions, _loader(B, H, W, 2, M.NestedTensor), opt, torch.device("cuda"), args.clip_max_norm, args)
+    assert math.isfinite(stats["loss"])
+    with_grad = {n for n, p in net.named_parameters() if p.grad is not None}
+    assert len(with_grad) == 684, len(with_grad)                 # the 54 never-used tensors keep grad None, as in the reference
+    moved = [n for n, p in net.named_parameters() if n in with_grad and not torch.equal(p.detach(), before[n])]
+    assert len(moved) == 684
+    assert all(torch.equal(p.detach(), before[n]) for n, p in net.named_parameters() if n not in with_grad)
+
+    # fused step == drop-in step on the same batch (same forward / backward kernels; torch criteria vs the fused loss kernels)
+    net2, criterions2, _ = M.build_model(args)
+    net2.load_state_dict(sd)
+    net2.cuda().train()
+    images, targets, depth_gt, seg_gt = synth.synth_batch(B, H, W, seed=0)
+    tg = [{k: v.cuda() for k, v in t.items()} for t in targets]
+    log = _mirror_train_loop(net2, criterions2, [(M.NestedTensor(images, torch.zeros(B, H, W, dtype=torch.bool)),
+                                                  M.NestedTensor(depth_gt, None), M.NestedTensor(seg_gt, None), targets, ["x"])],
+                             torch.optim.SGD([p for p in net2.parameters() if p.requires_grad], lr=0.0), torch.device("cuda"), 1e9, args)
+    drop_grads = {n: p.grad.clone() for n, p in net2.named_parameters() if p.grad is not None}
+    tr = Trainer(sd)
+    total, losses = tr.train_step(images.cuda(), tg, depth_gt.cuda(), seg_gt.cuda(), criterions2[0].cuda())
+    assert abs(float(total) - log["loss"]) < 2e-3 * abs(log["loss"]), (float(total), log["loss"])
+    assert set(losses) >= {"loss_ce", "loss_line", "loss_ce_4", "loss_depth", "loss_seg"}
+    # gradients were taken before the optimizer step of train_step modified the parameters: compare the kept flat buffers
+    fused = tr.grads()
+    worst = max(rel_l2(fused[n], g) for n, g in drop_grads.items())
+    assert worst < 2e-2, worst
+    # parameters moved, and the module can be re-synchronised for evaluation / checkpoints
+    net2.sync_from_trainer()
+    sd_after = tr.state_dict()
+    assert any(not torch.equal(sd_after[k].cpu(), sd[k]) for k in sd_after)

@@ -1,0 +1,57 @@
+"""CPU experiment (test infrastructure, uses the oracle): where does the bf16 distance of the full-resolution depth come from?
+Rounds the outputs of Linear / conv / LayerNorm / activations to bf16 inside ONE region of the oracle at a time (selections
+pinned to the fp32 run) and prints the mean / max relative error of pred_depth[3] against the fp32 oracle."""
+import os, sys, torch, torch.nn.functional as F
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+sys.path.insert(0, os.path.join(ROOT, "tests")); sys.path.insert(0, ROOT)
+from helpers import oracle, synth, synth_weights
+
+B, H, W = 1, int(os.environ.get("H", 224)), int(os.environ.get("W", 320))
+images, _, _, _ = synth.synth_batch(B, H, W, seed=0)
+sd = synth_weights()
+trace = {}
+ref = oracle.forward(sd, images, trace=trace)
+pin = {"line_ids": trace["line_ids"], "sample1": (trace["sample1"], trace["sample1_idx"]), "sample2": (trace["sample2"], trace["sample2_idx"])}
+rnd = lambda t: t.bfloat16().float()
+names = ["linear", "conv2d", "layer_norm", "gelu", "relu", "elu"]
+orig = {n: getattr(F, n) for n in names}
+active = {"on": False, "ops": set(names)}
+for n in names:
+    setattr(F, n, (lambda f, n=n: (lambda *a, **k: rnd(f(*a, **k)) if (active["on"] and n in active["ops"]) else f(*a, **k)))(orig[n]))
+
+def region(fn):
+    def wrapped(*a, **k):
+        prev = active["on"]; active["on"] = True
+        try: return fn(*a, **k)
+        finally: active["on"] = prev
+    return wrapped
+
+def rel(a, b):
+    d = (a.double() - b.double()).abs()
+    return float(d.mean() / b.double().abs().mean()), float((d / b.double().abs().clamp_min(1e-3)).max())
+
+stages = {"backbone": ["resnet50_features"], "detr": ["detr_transformer"], "line32": ["line_swin_block"], "class": ["class_swin_block"],
+          "entries": ["conv_a", "mlp_norm"], "points": ["point_based_pred"], "head": ["dense_head"]}
+saved = {n: getattr(oracle, n) for v in stages.values() for n in v}
+def run(label, regions, weights=False, ops=None):
+    active["ops"] = set(ops or names)
+    for v in stages.values():
+        for n in v: setattr(oracle, n, saved[n])
+    for r in regions:
+        for n in stages[r]: setattr(oracle, n, region(saved[n]))
+    sdw = {k: (rnd(v) if (weights and v.is_floating_point() and v.dim() > 1) else v) for k, v in sd.items()}
+    out = oracle.forward(sdw, images, pinned=pin)
+    m, x = rel(out["pred_depth"][3], ref["pred_depth"][3])
+    lm = float((out["pred_logits"] - ref["pred_logits"]).abs().max() / ref["pred_logits"].abs().max())
+    print("%-46s depth mean-rel %.4f max-rel %.3f  logits max-rel %.4f" % (label, m, x, lm), flush=True)
+
+run("fp32 (sanity)", [])
+run("weights bf16 only", [], weights=True)
+for r in stages:
+    run("activations bf16 in %s" % r, [r])
+run("activations bf16 everywhere", list(stages))
+run("weights + activations everywhere", list(stages), weights=True)
+run("everywhere, GEMM outputs only (linear, conv2d)", list(stages), ops=["linear", "conv2d"])
+run("everywhere, LN + act outputs only", list(stages), ops=["layer_norm", "gelu", "relu", "elu"])
+run("all but points", [r for r in stages if r != "points"], weights=True)
+run("all but points+head", [r for r in stages if r not in ("points", "head")], weights=True)

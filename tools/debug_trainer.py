@@ -31,7 +31,14 @@ torch.cuda.synchronize(); t0 = time.time()
 logits, lines, outs = tr.forward(images.cuda(), pinned)
 g = tr.dense.loss_grads(outs, depth_gt.cuda(), seg_gt.cuda())
 tr.backward_dense(*g)
-set_losses, dlogits, dlines = crit[0].cuda().forward_backward_stacked(logits, lines, tg)
+stacked = idx[1:] + idx[:1]          # the oracle lists the final stage first, the stacked layout has it last
+if os.environ.get("PIN_MATCH", "1") == "1":
+    set_losses, dlogits, dlines = crit[0].cuda().forward_backward_stacked(logits, lines, tg, pinned_pairs=stacked)
+else:
+    set_losses, dlogits, dlines = crit[0].cuda().forward_backward_stacked(logits, lines, tg)
+    mine = crit[0].matcher.pairs_from_raw()
+    diff = sum(int(not (torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]))) for sa, sb in zip(mine, stacked) for a, b in zip(sa, sb))
+    print("assignment problems that differ from the oracle's: %d of %d" % (diff, len(stacked) * B))
 tr.backward_line(dlogits, dlines)
 torch.cuda.synchronize()
 print("trainer fwd+bwd %.3f s" % (time.time() - t0))
