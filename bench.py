@@ -1,20 +1,27 @@
 #!/usr/bin/env python
-"""bench.py -- images/sec of the GW-Depth forward hot path at 480x640, bf16, batch 16 per GPU
-(BASELINE.json configs[1]: "stage-1 ResNet-50 inference bf16 batch 16 synthetic GlassRGBD-shaped 480x640 on 1xB200").
+"""bench.py -- images/sec of the GW-Depth model hot path at 480x640, bf16 (BASELINE.json `metric`:
+"images/sec @480x640 bf16 fwd+bwd at 1/2/4/8 B200").
 
     python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torch.distributed.run, one rank per GPU)
     python bench.py --impl reference --gpus N --steps K --warmup W
 
-A step = one forward of the model over one batch of 16 synthetic images per GPU.
-  value     : images/s with the input batches already resident in HBM (4 distinct batches are rotated: 236 MB of
-              inputs > the 126 MB L2, and the step's activation working set is several GB)
-  e2e       : the same metric through the public API (`model(samples)`) from PINNED HOST buffers: the H2D copy of the
-              step's images and the D2H read of its outputs (line logits / end points, full-resolution depth and
-              segmentation) are inside the timed region
-  roofline  : the tcgen05 implicit-GEMM kernel (gwd_tapgemm_kernel, every launch of the step): algorithmic FLOPs
-              (2*M*N*K*taps on logical dims) / sum of per-launch CUDA-event durations, against the measured bf16 peak
-  cpu_baseline : the CPU oracle (oracle/gwdepth_oracle.py, a port of the reference's PyTorch forward) on the host cores
-The reference arm (--impl reference) times that same CPU oracle; the reference is Python and is not on the GPU box.
+HEADLINE (value / e2e / scaling): the WHOLE-MODEL TRAINING STEP of BASELINE configs[2] -- batch 8 per GPU, data parallel:
+forward with saved activations, SetCriterion (6 Hungarian matchings on the host, hidden behind the dense branch), 4 x SilogLoss +
+SegLoss, backward of all 684 trained tensors, NCCL all-reduce of the flat gradient buffers (overlapped with the backward), ONE
+global clip norm, AdamW.  A step = one such iteration on one batch of 8 synthetic images per GPU.
+  value     : images/s with the step's inputs already resident in HBM (4 distinct batches are rotated; the step's activation
+              working set is several GB >> the 126 MB L2)
+  e2e       : the same step through the public API (`model.trainer().train_step(...)`) from PINNED HOST buffers: the H2D copy of the
+              step's images, depth / segmentation ground truth and line targets and the D2H read of its loss are inside the
+              timed region
+  roofline  : the tcgen05 implicit-GEMM kernel (gwd_tapgemm_kernel: every forward / data-gradient GEMM of the step), algorithmic
+              FLOPs / sum of per-launch CUDA-event durations against the measured bf16 peak; `step` = the whole step against
+              the reference's 1 049.5 GFLOP per image fwd+bwd
+  forward   : BASELINE configs[1] -- inference forward, batch 16 per GPU (round 1's headline) -- device-resident and end to end
+  gpu_eager_reference : the UNMODIFIED reference (staged under baseline/_ref by oracle/stage_ref.sh) as eager fp32 PyTorch on the
+              same GPU: forward at batch 16 (the 10x denominator of north_star) and the training step at batch 8
+  cpu_baseline : the CPU oracle (oracle/gwdepth_oracle.py) forward + backward under torch.autograd on the host cores
+The reference arm (--impl reference) times that CPU oracle training pass, 1 image per step (a bounded sample of the 8-image batch).
 """
 import argparse
 import json
@@ -26,13 +33,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
 
 import torch  # noqa: E402
 
-METRIC = "images_per_sec_fwd_480x640_bf16"
+METRIC = "images_per_sec_train_fwd_bwd_480x640_bf16"
 UNIT = "images/s"
-BATCH, H, W = 16, 480, 640
-WORKLOAD = "GW-Depth stage-1 ResNet-50 line+depth model, inference forward, batch 16 per GPU, 480x640 (BASELINE configs[1])"
+TRAIN_BATCH, FWD_BATCH, H, W = 8, 16, 480, 640
+WORKLOAD = ("GW-Depth stage-1 ResNet-50 line+depth model, whole-model training step (forward + 17 losses + backward + gradient "
+            "all-reduce + clip + AdamW), batch 8 per GPU, 480x640 (BASELINE configs[2])")
+FLOP_PER_IMAGE_TRAIN, FLOP_PER_IMAGE_FWD = 1049.5e9, 359.0e9          # SURVEY section 6 (FlopCounterMode over the reference)
 
 
 def parse():
@@ -41,9 +51,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=("b200", "reference"))
-    ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--batch", type=int, default=TRAIN_BATCH)
+    ap.add_argument("--dense-center", action="store_true", help="BASELINE configs[3]: --with_dense_center (3 points per line)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-train", action="store_true", help="skip the line-branch training-step measurement")
+    ap.add_argument("--no-forward", action="store_true", help="skip the inference-forward section")
+    ap.add_argument("--no-reference-eager", action="store_true")
     return ap.parse_args()
 
 
@@ -91,102 +103,119 @@ def use_all_host_threads():
     return torch.get_num_threads()
 
 
-def cpu_oracle_rate(max_seconds=20.0, min_iters=2):
-    """images/s of the CPU oracle at B=1, 480x640 (a bounded sample of the batch-16 workload)"""
-    from helpers import oracle, synth, synth_weights
+def cpu_train_pass(sd_leaves, batch, wd):
+    """one forward + backward of the CPU oracle under torch.autograd (the engine's 17 losses) on `batch`"""
+    from helpers import oracle
+    images, targets, depth_gt, seg_gt = batch
+    for v in sd_leaves.values():
+        if v.requires_grad:
+            v.grad = None
+    out = oracle.forward(sd_leaves, images, grad=True)
+    set_l, _ = oracle.set_criterion(out, [t["lines"] for t in targets])
+    total = sum(v * wd[k] for k, v in set_l.items()) + sum(oracle.depth_losses(out["pred_depth"], depth_gt)) + oracle.seg_loss(out["pred_seg"], seg_gt)
+    total.backward()
+    return float(total.detach())
+
+
+def cpu_setup():
+    from helpers import synth, synth_weights
     use_all_host_threads()
     sd = synth_weights()
-    images, _, _, _ = synth.synth_batch(1, H, W, seed=0)
-    oracle.forward(sd, images)  # warm
-    t0, n = time.time(), 0
-    while n < min_iters or (time.time() - t0 < max_seconds and n < 12):
-        oracle.forward(sd, images)
-        n += 1
-    dt = time.time() - t0
-    return n / dt, n
+    frozen = ("backbone.0.body.conv1", "backbone.0.body.layer1")
+    leaves = {k: (v.clone().requires_grad_(True) if (v.is_floating_point() and "running" not in k and ".bn" not in k and "downsample.1" not in k
+                                                     and not k.startswith(frozen)) else v) for k, v in sd.items()}
+    wd = {"loss_ce": 1.0, "loss_line": 5.0}
+    wd.update({"%s_%d" % (k, i): v for i in range(5) for k, v in list(wd.items())[:2]})
+    return leaves, synth.synth_batch(1, H, W, seed=0), wd
 
 
 def run_reference(args, rank):
-    """the reference arm: the CPU port of the reference forward (oracle), all host threads, rank 0 only"""
+    """the reference arm: the CPU oracle's training pass (forward + losses + backward, torch.autograd), all host threads, rank 0
+    only; every step is ONE image of the 8-image batch (a bounded sample: the full batch takes ~8x as long)"""
     if rank != 0:
         return
-    from helpers import oracle, synth, synth_weights
-    use_all_host_threads()
-    sd = synth_weights()
-    images, _, _, _ = synth.synth_batch(1, H, W, seed=0)
-    for _ in range(min(args.warmup, 2)):
-        oracle.forward(sd, images)
+    leaves, batch, wd = cpu_setup()
+    for _ in range(min(args.warmup, 1)):
+        cpu_train_pass(leaves, batch, wd)
     t0 = time.time()
     for _ in range(args.steps):
-        oracle.forward(sd, images)
+        cpu_train_pass(leaves, batch, wd)
     dt = time.time() - t0
     v = args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": "1 image of the 16-image batch per step (CPU)"},
+            "config": {"workload": WORKLOAD, "sample": "1 image of the 8-image batch per step, forward + 17 losses + backward on the CPU "
+                       "(no optimizer step); per-image rate"},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "%d forwards of 1x3x480x640 through oracle/gwdepth_oracle.py" % args.steps},
+                             "sample": "%d training passes of 1x3x480x640 through oracle/gwdepth_oracle.py under torch.autograd" % args.steps},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def run_train(args, net, resident, rank, world, dev, barrier, reduce_max_ms):
-    """Data-parallel training step of the LINE BRANCH (gw-depth_b200/train.py): backbone forward (no gradient: the
-    backbone / dense-branch backward is not built), input_proj -> encoder -> decoder -> heads forward with saved
-    activations, SetCriterion with its 6 Hungarian matchings (scipy, host), backward kernels, ONE NCCL all-reduce of the
-    flat gradient buffer, fused clip + AdamW.  Reported as images/s over all ranks, device-timed, max over ranks."""
+def gpu_eager_reference(dev, n_fwd=5, n_train=3):
+    """the unmodified reference on this GPU, eager fp32, as shipped (no AMP / TF32 override / cudnn.benchmark): forward at batch 16
+    (north_star's 10x denominator) and one training step at batch 8 (its own criteria, AdamW, clip)"""
+    import ref_shims
+    if not ref_shims.reference_available():
+        return {"unavailable": "reference tree not staged (run oracle/stage_ref.sh in the build container)"}
     from helpers import synth, synth_weights
-    from gwdepth_b200 import capi, model as M, train
-    B = args.batch
-    _, crit, _ = M.build_model(M.default_args(device="cuda", dropout=0.0))
-    criterion = crit[0].to(dev)
-    lb = train.LineBranch(synth_weights(), net.cfg, device=dev)
-    targets = [[{k: v.to(dev) for k, v in t.items()} for t in synth.synth_batch(B, H, W, seed=100 + 7 * rank + i)[1]]
-               for i in range(len(resident))]
-    plan = net.plan()
+    res = {"what": "unmodified reference (baseline/_ref), eager fp32 PyTorch on the same GPU"}
+    try:
+        model, criterions, _, rargs = ref_shims.build_reference(["--device", "cuda", "--dropout", "0.0"])
+        model.load_state_dict(synth_weights(), strict=True)
+        model.to(dev).eval()
+        images = synth.synth_batch(FWD_BATCH, H, W, seed=100)[0].to(dev)
+        with torch.no_grad():
+            for _ in range(2):
+                model(images)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n_fwd):
+                model(images)
+            e1.record()
+            torch.cuda.synchronize()
+        res["forward_b16"] = {"value": n_fwd * FWD_BATCH / (e0.elapsed_time(e1) / 1000.0), "unit": UNIT, "ms_per_step": e0.elapsed_time(e1) / n_fwd}
+        # training step, batch 8
+        import torch.nn.functional as F
+        model.train()
+        crit, crit_d, crit_s = criterions[0].to(dev), criterions[1], criterions[2]
+        crit.train()
+        opt = torch.optim.AdamW([{"params": [p for n, p in model.named_parameters() if "backbone" not in n and p.requires_grad]},
+                                 {"params": [p for n, p in model.named_parameters() if "backbone" in n and p.requires_grad], "lr": 1e-5}],
+                                lr=1e-4, weight_decay=1e-4)
+        imgs, targets, depth_gt, seg_gt = synth.synth_batch(TRAIN_BATCH, H, W, seed=100)
+        imgs, depth_gt, seg_gt = imgs.to(dev), depth_gt.to(dev), seg_gt.to(dev)
+        targets = [{k: v.to(dev) for k, v in t.items()} for t in targets]
 
-    backbone = lambda images: plan.backbone(images)[3]      # noqa: E731  (no gradient: captured into the forward graph)
-
-    def step(i):
-        return lb.train_step(resident[i % len(resident)], targets[i % len(resident)], criterion, producer=backbone)
-
-    for i in range(max(args.warmup, 3)):
-        step(i)
-    barrier()
-    capi.reset_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0 = time.perf_counter()
-    e0.record()
-    for i in range(args.steps):
-        total, _ = step(i)
-    e1.record()
-    barrier()
-    ms = reduce_max_ms(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0))
-    # where the time goes on this rank (separate, un-timed-above passes)
-    def timed(fn, n=5):
-        fn()
+        def step():
+            out = model(imgs)
+            ld = crit(out, targets)
+            loss = sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict)
+            mask = (depth_gt >= 0.2) & (depth_gt < 10.0)
+            for i, pd in enumerate(out["pred_depth"]):
+                sz = pd.shape[-2:]
+                loss = loss + crit_d(pd, F.interpolate(depth_gt, size=sz, mode="nearest"),
+                                     F.interpolate(mask.to(torch.uint8), size=sz, mode="nearest").to(torch.bool)) * (0.25, 0.25, 0.25, 1.0)[i]
+            loss = loss + crit_s(out["pred_seg"], seg_gt.squeeze(1)) * 2.0
+            opt.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
+            opt.step()
+        step()
         torch.cuda.synchronize()
-        t = time.perf_counter()
-        for _ in range(n):
-            fn()
+        e0.record()
+        for _ in range(n_train):
+            step()
+        e1.record()
         torch.cuda.synchronize()
-        return (time.perf_counter() - t) * 1000.0 / n
-    with torch.no_grad():
-        c5 = plan.backbone(resident[0])[3].clone()
-        ms_backbone = timed(lambda: plan.backbone(resident[0]))
-    st = lb._captured(c5) if lb.use_cuda_graph else None
-    ms_graphs = timed(lambda: (st["fwd"].replay(), st["bwd"].replay())) if st else None
-    lo, li = (st["logits"], st["lines"]) if st else lb.forward(c5)
-    lo, li = lo.detach().clone(), li.detach().clone()
-    ms_crit = timed(lambda: criterion.forward_backward_stacked(lo, li, targets[0]))
-    return {"metric": "images_per_sec_train_line_branch_480x640_bf16", "value": world * B * args.steps / (ms / 1000.0), "unit": UNIT,
-            "ms_per_step": ms / args.steps, "n_gpus": world, "global_batch": world * B, "loss": float(total),
-            "params": lb.numel, "allreduce_bytes_per_step": lb.numel * 4 if world > 1 else 0,
-            "breakdown_ms": {"backbone_forward_no_grad": ms_backbone, "branch_forward_plus_backward_graph_replays": ms_graphs,
-                             "set_criterion_6_hungarian_host": ms_crit},
-            "scope": "line branch only: gradients stop at the C5 map (backbone / dense-branch backward not built); "
-                     "dropout 0; lr 1e-4, weight decay 1e-4, clip 0.1 as the reference"}
+        res["train_b8"] = {"value": n_train * TRAIN_BATCH / (e0.elapsed_time(e1) / 1000.0), "unit": UNIT, "ms_per_step": e0.elapsed_time(e1) / n_train}
+        del model, opt
+        torch.cuda.empty_cache()
+    except Exception as e:  # noqa: BLE001  (context numbers must not take the headline down)
+        res["error"] = repr(e)[:300]
+    return res
 
 
 def main():
@@ -206,15 +235,7 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
-
-    net, _, _ = M.build_model(M.default_args(device="cuda"))
-    net.load_state_dict(synth_weights())
-    net.to(dev).eval()
-    NB = 4
-    host = [synth.synth_batch(B, H, W, seed=100 + 7 * rank + i)[0].pin_memory() for i in range(NB)]
-    resident = [h.to(dev) for h in host]
-    plan = net.plan()
+    B, steps, warm = args.batch, args.steps, max(args.warmup, 3)
 
     def barrier():
         if world > 1:
@@ -228,163 +249,208 @@ def main():
             return float(t.item())
         return ms
 
-    # ------------------------------------------------------------ device-resident throughput
-    with torch.no_grad():
-        step = plan.forward_graphed if net.use_cuda_graph else plan.forward
-        for i in range(max(args.warmup, 3)):
-            step(resident[i % NB])
-        barrier()
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        capi.reset_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
-        e0.record()
-        for i in range(args.steps):
-            step(resident[i % NB])
-        e1.record()
-        barrier()
-        launches = capi.launch_count()
-        if net.use_cuda_graph:   # replayed launches are not re-issued through the C ABI: count one eager step instead
-            capi.reset_launch_count()
-            plan.forward(resident[0])
-            torch.cuda.synchronize()
-            launches = capi.launch_count() * args.steps
-        sampler.stop_flag = True
-        ms = reduce_max_ms(e0.elapsed_time(e1))
-        value = world * B * args.steps / (ms / 1000.0)
+    margs = M.default_args(device="cuda", dropout=0.0, with_dense_center=bool(args.dense_center))
+    net, criterions, _ = M.build_model(margs)
+    net.load_state_dict(synth_weights())
+    net.to(dev)
+    criterion = criterions[0].to(dev)
+    tr = net.trainer()
+    NB = 4
+    host = []
+    for i in range(NB):
+        im, tg, dg, sg = synth.synth_batch(B, H, W, seed=100 + 7 * rank + i)
+        host.append((im.pin_memory(), tg, dg.pin_memory(), sg.pin_memory()))
+    to_dev = lambda hb: (hb[0].to(dev, non_blocking=True), [{k: v.to(dev, non_blocking=True) for k, v in t.items()} for t in hb[1]],  # noqa: E731
+                         hb[2].to(dev, non_blocking=True), hb[3].to(dev, non_blocking=True))
+    resident = [to_dev(hb) for hb in host]
 
-        # -------------------------------------------------------- end to end through the public API, host buffers
-        # net.infer_stream: the serving loop of the public API (H2D of batch i+1 and D2H of batch i-1 overlap the forward
-        # of batch i on three streams); every step's upload and read-back are inside the timed region
-        def e2e_run(n):
-            last = None
-            for last in net.infer_stream(host[i % NB] for i in range(n)):
-                pass
-            torch.cuda.synchronize()
-            return last
-        out_host = list(e2e_run(3).values())
-        barrier()
-        t0 = time.perf_counter()
-        e0.record()
-        e2e_run(args.steps)
-        e1.record()
-        barrier()
-        ms_e2e = reduce_max_ms(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0))
-        e2e_value = world * B * args.steps / (ms_e2e / 1000.0)
-        # the same loop fed with raw uint8 HWC images (a quarter of the PCIe bytes; normalised on the GPU)
-        host_u8 = [torch.randint(0, 256, (B, H, W, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(i)).pin_memory()
-                   for i in range(NB)]
+    # ------------------------------------------------------------ headline: training step, inputs resident in HBM
+    def step(i):
+        im, tg, dg, sg = resident[i % NB]
+        return tr.train_step(im, tg, dg, sg, criterion)
 
-        def e2e_u8(n):
-            for _ in net.infer_stream(host_u8[i % NB] for i in range(n)):
-                pass
-            torch.cuda.synchronize()
-        e2e_u8(3)
-        barrier()
-        t0 = time.perf_counter()
-        e0.record()
-        e2e_u8(args.steps)
-        e1.record()
-        barrier()
-        ms_u8 = reduce_max_ms(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0))
-        e2e_uint8 = {"value": world * B * args.steps / (ms_u8 / 1000.0), "unit": UNIT, "ms_per_step": ms_u8 / args.steps,
-                     "h2d_bytes_per_step": host_u8[0].numel(), "input": "uint8 [B,H,W,3] pinned host images, ToTensor + Normalize on the GPU (gwd_images_to_batch)"}
-        h2d = host[0].numel() * host[0].element_size()
-        d2h = sum(t.numel() * t.element_size() for t in out_host)
+    for i in range(warm):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    capi.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(steps):
+        total, losses = step(i)
+    e1.record()
+    barrier()
+    launches = capi.launch_count()
+    sampler.stop_flag = True
+    ms = reduce_max_ms(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0))
+    value = world * B * steps / (ms / 1000.0)
+    loss_value = float(total)
 
-        # -------------------------------------------------------- roofline of the dominant kernel (instrumented pass)
-        roof = None
-        if rank == 0:
-            ops.PROFILE = []
-            # keep the GPU busy while the host enqueues the eager pass, so that the event pairs bracket back-to-back
-            # kernels and not host launch gaps (the ~120 small DETR Linears would otherwise be charged ~10 us each)
-            torch.cuda._sleep(int(0.15 * 1.9e9))
-            plan.forward(resident[0])
-            torch.cuda.synchronize()
-            recs, ops.PROFILE = ops.PROFILE, None
-            tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
-            tot_flop = sum(f for _, _, f, _ in recs)
-            big = max(recs, key=lambda r: r[2])
-            peak, peak_src = measured_peak()
-            ach = tot_flop / (tot_ms / 1000.0) / 1e12
-            traffic, traffic_src = None, None
-            try:      # DRAM bytes of the same launches from the committed ncu pass (profiles/README.md); bench.py cannot run ncu
-                with open(os.path.join(ROOT, "profiles", "r1_tapgemm_dram.json")) as f:
-                    tj = json.load(f)
-                traffic = tj["dram_bytes_per_launch"]
-                traffic_src = "profiles/r1_tapgemm_dram.json: mean dram__bytes_read+write per launch over the %d launches of a step" % tj["launches"]
-            except (OSError, KeyError, ValueError):
-                pass
-            roof = {"bound": "tensor", "kernel": "gwd_tapgemm_kernel (tcgen05 implicit GEMM, all %d launches of a step)" % len(recs),
-                    "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic,
-                    "traffic_source": traffic_src, "algorithmic_flop_per_launch": tot_flop / len(recs), "peak_source": peak_src,
-                    "flop_per_step": tot_flop, "kernel_ms_per_step": tot_ms, "kernel_share_of_step": tot_ms / (ms / args.steps),
-                    "largest_launch": {"desc": big[3], "tflops": big[2] / (big[0].elapsed_time(big[1]) / 1000.0) / 1e12}}
+    # ------------------------------------------------------------ end to end: the same step from pinned host buffers
+    # the upload of batch i+1 runs on a side stream while step i computes; the loss of step i is copied to pinned host memory
+    # asynchronously and read one step later (the reference's loop reads it with .item() every step)
+    side = torch.cuda.Stream(device=dev)
+    loss_host = torch.zeros(steps + warm, dtype=torch.float32).pin_memory()
 
-    # ------------------------------------------------------------ line-branch training step (extra key, not the headline)
-    train_line = None
-    if not args.no_train:
-        train_line = run_train(args, net, resident, rank, world, dev, barrier, reduce_max_ms)
+    def e2e_run(n):
+        main_s = torch.cuda.current_stream()
+        with torch.cuda.stream(side):
+            nxt = to_dev(host[0])
+            ev = torch.cuda.Event()
+            ev.record(side)
+        seen = 0.0
+        for i in range(n):
+            main_s.wait_event(ev)
+            cur = nxt
+            if i + 1 < n:
+                with torch.cuda.stream(side):
+                    nxt = to_dev(host[(i + 1) % NB])
+                    ev = torch.cuda.Event()
+                    ev.record(side)
+            tot, _ = tr.train_step(cur[0], cur[1], cur[2], cur[3], criterion)
+            for t in (cur[0], cur[2], cur[3]):
+                t.record_stream(main_s)
+            loss_host[i:i + 1].copy_(tot.reshape(1), non_blocking=True)
+            if i:
+                seen += float(loss_host[i - 1])       # (the copy of step i-1 finished before the matching of step i was solved)
+        torch.cuda.synchronize()
+        return seen + float(loss_host[n - 1])
+    e2e_run(2)
+    barrier()
+    t0 = time.perf_counter()
+    e0.record()
+    e2e_run(steps)
+    e1.record()
+    barrier()
+    ms_e2e = reduce_max_ms(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0))
+    e2e_value = world * B * steps / (ms_e2e / 1000.0)
+    h2d = sum(t.numel() * t.element_size() for t in (host[0][0], host[0][2], host[0][3])) + sum(v.numel() * v.element_size() for t in host[0][1] for v in t.values())
+    e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + sum(t["lines"].shape[0] for t in host[0][1]) * 0 + 6 * B * 100 * 60 * 4,
+           "ms_per_step": ms_e2e / steps, "api": "model.trainer().train_step(images, targets, depth_gt, seg_gt, criterion) from pinned host batches; "
+           "d2h = the matching costs the host solver reads + the loss"}
 
+    # ------------------------------------------------------------ where the step goes + roofline (instrumented, un-timed above)
+    def timed(fn, n=3):
+        fn()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t) * 1000.0 / n
+    roof, breakdown = None, None
+    if rank == 0:
+        im, tg, dg, sg = resident[0]
+        ops.PROFILE = []
+        torch.cuda._sleep(int(0.2 * 1.9e9))       # keep the GPU busy while the host enqueues: events bracket kernels, not launch gaps
+        lo, li, outs = tr.forward(im)
+        g = tr.dense.loss_grads(outs, dg, sg)
+        tr.backward_dense(*g)
+        _, dlo, dli = criterion.forward_backward_stacked(lo, li, tg)
+        tr.backward_line(dlo, dli)
+        torch.cuda.synchronize()
+        recs, ops.PROFILE = ops.PROFILE, None
+        tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
+        tot_flop = sum(f for _, _, f, _ in recs)
+        big = max(recs, key=lambda r: r[2])
+        peak, peak_src = measured_peak()
+        ach = tot_flop / (tot_ms / 1000.0) / 1e12
+        step_ach = value / world * FLOP_PER_IMAGE_TRAIN / 1e12
+        roof = {"bound": "tensor", "kernel": "gwd_tapgemm_kernel (tcgen05 implicit GEMM: the %d forward + data-gradient launches of a step)" % len(recs),
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "algorithmic_flop_per_launch": tot_flop / len(recs), "peak_source": peak_src, "flop_per_step": tot_flop,
+                "kernel_ms_per_step": tot_ms, "kernel_share_of_step": tot_ms / (ms / steps),
+                "largest_launch": {"desc": big[3], "tflops": big[2] / (big[0].elapsed_time(big[1]) / 1000.0) / 1e12},
+                "step": {"achieved": step_ach, "frac": step_ach / peak, "flop_per_image": FLOP_PER_IMAGE_TRAIN,
+                         "what": "whole training step per GPU against the reference's fwd+bwd FLOPs (SURVEY section 6)"}}
+        ms_fwd = timed(lambda: tr.forward(im))
+        lo, li, outs = tr.forward(im)
+        g = tr.dense.loss_grads(outs, dg, sg)
+
+        def bwd():
+            tr.forward(im)
+            tr.backward_dense(*tr.dense.loss_grads(outs, dg, sg))
+            tr.backward_line(dlo, dli)
+        ms_fb = timed(bwd)
+        ms_crit = timed(lambda: criterion.forward_backward_stacked(lo, li, tg))
+        tr._works = []
+        breakdown = {"forward_ms": ms_fwd, "forward_plus_backward_ms": ms_fb, "matching_host_ms": ms_crit, "optimizer_ms": timed(tr.step),
+                     "lsap_threads": M._lsap_threads(), "allreduce_bytes_per_step": tr.numel() * 4 if world > 1 else 0,
+                     "flat_buffers": len(tr.modules()), "trained_parameters": tr.numel()}
+
+    # ------------------------------------------------------------ BASELINE configs[1]: inference forward, batch 16 per GPU
+    fwd = None
+    if not args.no_forward:
+        net.sync_from_trainer()
+        net.eval()
+        plan = net.plan()
+        hostf = [synth.synth_batch(FWD_BATCH, H, W, seed=200 + 7 * rank + i)[0].pin_memory() for i in range(NB)]
+        resf = [h.to(dev) for h in hostf]
+        with torch.no_grad():
+            fstep = plan.forward_graphed if net.use_cuda_graph else plan.forward
+            for i in range(warm):
+                fstep(resf[i % NB])
+            barrier()
+            e0.record()
+            for i in range(steps):
+                fstep(resf[i % NB])
+            e1.record()
+            barrier()
+            ms_f = reduce_max_ms(e0.elapsed_time(e1))
+
+            def fe2e(n):
+                for _ in net.infer_stream(hostf[i % NB] for i in range(n)):
+                    pass
+                torch.cuda.synchronize()
+            fe2e(3)
+            barrier()
+            t0 = time.perf_counter()
+            e0.record()
+            fe2e(steps)
+            e1.record()
+            barrier()
+            ms_fe = reduce_max_ms(max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0))
+        fv = world * FWD_BATCH * steps / (ms_f / 1000.0)
+        fwd = {"metric": "images_per_sec_fwd_480x640_bf16", "value": fv, "unit": UNIT, "ms_per_step": ms_f / steps, "batch_per_gpu": FWD_BATCH,
+               "e2e": world * FWD_BATCH * steps / (ms_fe / 1000.0), "frac_of_peak": fv / world * FLOP_PER_IMAGE_FWD / 1e12 / measured_peak()[0],
+               "workload": "BASELINE configs[1]: inference forward, one CUDA-graph replay per batch; e2e = model.infer_stream from pinned host batches"}
+        del resf, plan
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    # ------------------------------------------------------------ dense-branch training step (extra key, rank 0, one GPU's batch)
-    # (everything behind the 1/32 stage: tools/bench_train_branch.py) measured in a child process: its 13 GB of activations
-    # and any fault stay out of the headline measurement
-    train_tail = None
-    if not args.no_train:
-        try:
-            import subprocess
-            import tempfile
-            with tempfile.TemporaryDirectory() as td_:
-                out = os.path.join(td_, "tail.json")
-                env = dict(os.environ, CUDA_VISIBLE_DEVICES=str(dev.index if os.environ.get("CUDA_VISIBLE_DEVICES") is None else
-                                                                os.environ["CUDA_VISIBLE_DEVICES"].split(",")[dev.index]))
-                for k in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
-                    env.pop(k, None)
-                subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_train_branch.py"), "--batch", str(B), "--steps",
-                                str(max(5, min(args.steps, 10))), "--json", out], check=True, timeout=600, env=env,
-                               stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-                with open(out) as f:
-                    train_tail = json.load(f)
-        except Exception as e:  # noqa: BLE001  (an extra key must not take the headline line down)
-            train_tail = {"value": None, "error": repr(e)[:300]}
-    cpu = None
-    eager = None
-    if world == 1 and not args.no_cpu_baseline:
-        # context only (not the reference arm): the same oracle restatement run as eager fp32 PyTorch ON THE GPU, i.e.
-        # what the reference's op-by-op structure (library kernels, per-image Python loops, host syncs) costs on a B200
-        try:
-            from helpers import oracle
-            sd_gpu = {k: v.to(dev) for k, v in synth_weights().items()}
-            with torch.no_grad():
-                oracle.forward(sd_gpu, resident[0])
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                for i in range(3):
-                    oracle.forward(sd_gpu, resident[i % NB])
-                torch.cuda.synchronize()
-            eager = {"value": 3 * B / (time.perf_counter() - t0), "unit": UNIT,
-                     "what": "oracle/gwdepth_oracle.py (port of the reference forward) as eager fp32 PyTorch on the same GPU, batch 16"}
-            del sd_gpu
-        except Exception as e:  # noqa: BLE001
-            eager = {"value": None, "error": repr(e)[:200]}
-        rate, n = cpu_oracle_rate()
-        cpu = {"value": rate, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "%d forwards of 1x3x480x640 (1/16 of a step) through oracle/gwdepth_oracle.py" % n}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic",
-            "config": {"workload": WORKLOAD, "global_batch": world * B, "image": [H, W], "parallelism": "dp%d (replicas, no data-path collective)" % world,
-                       "l2": "4 rotating input batches (236 MB > L2); per-step activations are several GB",
-                       "cuda_graph": bool(net.use_cuda_graph)},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
-                    "pipeline": "model.infer_stream: 3 streams, double-buffered H2D / forward / D2H"},
-            "gpu_launches": launches, "clocks": sampler.summary(), "roofline": roof, "cpu_baseline": cpu,
-            "gpu_eager_port": eager, "e2e_uint8_inputs": e2e_uint8, "train_line_branch": train_line, "train_dense_branch": train_tail}
+
+    cpu, eager = None, None
+    if world == 1:
+        if not args.no_reference_eager:
+            del tr
+            net.__dict__["_trainer"] = None
+            torch.cuda.empty_cache()
+            eager = gpu_eager_reference(dev)
+            if fwd and isinstance(eager.get("forward_b16"), dict):
+                eager["forward_speedup"] = fwd["value"] / eager["forward_b16"]["value"]
+            if isinstance(eager.get("train_b8"), dict):
+                eager["train_speedup"] = value / eager["train_b8"]["value"]
+        if not args.no_cpu_baseline:
+            leaves, batch, wd = cpu_setup()
+            cpu_train_pass(leaves, batch, wd)
+            t0, n = time.time(), 0
+            while n < 2 or (time.time() - t0 < 20.0 and n < 6):
+                cpu_train_pass(leaves, batch, wd)
+                n += 1
+            cpu = {"value": n / (time.time() - t0), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": "%d training passes (forward + 17 losses + backward) of 1x3x480x640 (1/8 of a step) through oracle/gwdepth_oracle.py" % n}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic", "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
+            "config": {"workload": WORKLOAD, "global_batch": world * B, "image": [H, W], "with_dense_center": bool(args.dense_center),
+                       "parallelism": "dp%d: batch sharded over the ranks, NCCL all-reduce of %d flat gradient buffers overlapped with the backward" % (world, len(net.__dict__.get("_live") or []) and 22),
+                       "l2": "4 rotating input batches; per-step activations are several GB", "loss": loss_value,
+                       "optimizer": "AdamW lr 1e-4 (backbone 1e-5), weight decay 1e-4, global clip 0.1; dropout 0"},
+            "breakdown": breakdown, "forward": fwd, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_reference": eager}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

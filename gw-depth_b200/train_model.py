@@ -167,7 +167,8 @@ class Trainer:
         for m in mods:
             if isinstance(m, FlatModule):
                 m._world = world
-                m.step(self.sumsq, reduced=True)
+                # (not m.step: PointPred / DenseTail override it to clip over their own buffers only)
+                (BackboneTrain.step if isinstance(m, BackboneTrain) else FlatModule.step)(m, self.sumsq, reduced=True)
             else:       # LineBranch: the same flat-buffer update
                 m.t += 1
                 ops.adamw_step(m.P, m.G, m.M, m.V, m.Wb, lr=m.lr, betas=m.betas, eps=m.eps, weight_decay=m.weight_decay, step=m.t,

@@ -7,8 +7,8 @@
   * the fused step (Trainer.train_step) equals the drop-in step's losses and gradients.
 
 Gradient tolerances: this synthetic network is sensitive to bf16 storage itself -- the ORACLE's own gradients move by 5-50 % per
-module when its weights and stored activations are rounded to bf16 (straight-through), see DESIGN.md section 4 -- so every module
-is held to 1.5 x that distance + 3 % (the modules next to the losses, where no amplification happens, to 8 % absolute)."""
+module when its weights, stored activations and activation gradients are rounded to bf16, see DESIGN.md section 4 -- so every
+module is held to 1.5 x that distance + 3 % (the modules next to the losses, where no amplification happens, to 8 % absolute)."""
 import collections
 import math
 import os
@@ -48,19 +48,34 @@ def _trainable(sd):
             and not k.startswith(frozen)}
 
 
+class _Bf16Store(torch.autograd.Function):
+    """what storing a tensor in bf16 does to a training step: the value is rounded on the way forward, its gradient on the way back"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().float()
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.bfloat16().float()
+
+
 def _oracle_grads(sd, images, targets, depth_gt, seg_gt, wd, pin=None, emulate=False):
-    """total loss of the engine's loop and its gradients by torch.autograd over the oracle; emulate=True rounds the weights and
-    every stored activation to bf16 (straight-through)"""
-    names = ["linear", "conv2d", "layer_norm", "gelu", "relu", "elu"]
-    orig = {n: getattr(F, n) for n in names}
-    st = lambda t: t + (t.bfloat16().float() - t).detach()  # noqa: E731
+    """total loss of the engine's loop and its gradients by torch.autograd over the oracle; emulate=True stores the weights and
+    every activation (and activation gradient) in bf16"""
+    # what the CUDA path stores in bf16: the outputs of every Linear / convolution / LayerNorm / activation, attention
+    # probabilities and attention outputs (torch.softmax / bmm / @ in the oracle), and the weights themselves
+    patches = [(F, n) for n in ("linear", "conv2d", "layer_norm", "gelu", "relu", "elu")] + [(torch, "softmax"), (torch, "bmm"),
+                                                                                           (torch.Tensor, "__matmul__")]
+    orig = [(o, n, getattr(o, n)) for o, n in patches]
+    st = _Bf16Store.apply
     train = _trainable(sd)
     leaves = {k: (v.clone().requires_grad_(True) if k in train else v) for k, v in sd.items()}
     use = {k: (st(v) if (emulate and k in train and v.dim() > 1) else v) for k, v in leaves.items()}
     try:
         if emulate:
-            for n in names:
-                setattr(F, n, (lambda f: (lambda *a, **k: st(f(*a, **k))))(orig[n]))
+            for o, n, f in orig:
+                setattr(o, n, (lambda f: (lambda *a, **k: st(f(*a, **k))))(f))
         trace = {}
         out = oracle.forward(use, images, pinned=pin, trace=trace, grad=True)
         tl = [t["lines"] for t in targets]
@@ -69,8 +84,8 @@ def _oracle_grads(sd, images, targets, depth_gt, seg_gt, wd, pin=None, emulate=F
         total = sum(v * wd[k] for k, v in set_l.items()) + sum(dl) + oracle.seg_loss(out["pred_seg"], seg_gt)
         total.backward()
     finally:
-        for n in names:
-            setattr(F, n, orig[n])
+        for o, n, f in orig:
+            setattr(o, n, f)
     return float(total), {k: v.grad for k, v in leaves.items() if k in train}, trace, idx
 
 
@@ -180,8 +195,11 @@ def test_drop_in_training_loop_and_fused_step():
     assert math.isfinite(stats["loss"])
     with_grad = {n for n, p in net.named_parameters() if p.grad is not None}
     assert len(with_grad) == 684, len(with_grad)                 # the 54 never-used tensors keep grad None, as in the reference
-    moved = [n for n, p in net.named_parameters() if n in with_grad and not torch.equal(p.detach(), before[n])]
-    assert len(moved) == 684
+    # (the bias of the diffusion convolution has an analytically zero gradient -- the plane normalisation removes constant
+    # shifts -- so whether round-off moves it is an accident of the summation order, here as in the reference)
+    still = [n for n, p in net.named_parameters() if n in with_grad and torch.equal(p.detach(), before[n])
+             and not n.endswith("ref_attn_diffusion.bias")]
+    assert not still, still
     assert all(torch.equal(p.detach(), before[n]) for n, p in net.named_parameters() if n not in with_grad)
 
     # fused step == drop-in step on the same batch (same forward / backward kernels; torch criteria vs the fused loss kernels)
