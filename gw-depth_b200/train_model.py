@@ -54,6 +54,11 @@ class Trainer:
         self.sumsq = torch.zeros(1, dtype=torch.float64, device=self.dev)
         self._works = []
         self.exchange_grads = True
+        self._defer = None                 # list collecting the modules to exchange while a CUDA graph is captured / replayed
+        import os
+        # the fused step replays its three kernel sequences as CUDA graphs (GWD_CUDA_GRAPH=0: launched kernel by kernel)
+        self.use_cuda_graph = os.environ.get("GWD_CUDA_GRAPH", "1") != "0"
+        self._graphs = {}
         self.last = {}
 
     # ------------------------------------------------------------------ bookkeeping
@@ -131,6 +136,9 @@ class Trainer:
     def _exchange(self, mods):
         """asynchronous all-reduce of flat gradient buffers whose backward has been enqueued (exchange_grads = False: someone
         else reduces the gradients, e.g. DistributedDataParallel around the drop-in module)"""
+        if self._defer is not None:          # inside a captured region: the collective is issued after the replay
+            self._defer += mods
+            return
         if self.exchange_grads and parallel.world_size() > 1:
             for m in mods:
                 self._works.append(dist.all_reduce(m.G, async_op=True))
@@ -183,6 +191,8 @@ class Trainer:
         """images fp32 [B,3,H,W]; targets: list of {'lines' [T,D], 'labels' [T]} on the device; depth_gt fp32 [B,1,H,W] metres;
         seg_gt int64 [B,1,H,W]; criterion: model.SetCriterion.  Returns (total loss tensor [1] on the device, dict of the 17
         un-weighted losses as the engine logs them)."""
+        if self.use_cuda_graph and not pinned:
+            return self._train_step_graphed(images, targets, depth_gt, seg_gt, criterion)
         pend = {}
         logits, lines, outs = self.forward(images, pinned,
                                            after_line=lambda lo, li: pend.update(h=criterion.matcher.stacked_cost(lo, li, targets)))
@@ -191,10 +201,82 @@ class Trainer:
         set_losses, dlogits, dlines = criterion.forward_backward_stacked(logits, lines, targets, pending=pend["h"])
         self.backward_line(dlogits, dlines)
         self.step()
+        return self._report(criterion, set_losses, outs, logits, lines)
+
+    def _report(self, criterion, set_losses, outs, logits, lines):
         dl = self.dense.losses()
         total = criterion.last_total + dl.sum()
         losses = dict(set_losses)
-        w = self.dense.scale_weights
         losses.update(loss_depth=dl[:4].sum(), loss_seg=dl[4] / self.dense.tail.head.seg_weight)
-        self.last = dict(outs=outs, logits=logits, lines=lines, dense_losses=dl, scale_weights=w)
+        self.last = dict(outs=outs, logits=logits, lines=lines, dense_losses=dl)
         return total, losses
+
+    # ---- the same step as three CUDA-graph replays around the two host-side pieces (matching costs / assignments)
+    def _forward_line(self, images):
+        c2 = self.backbone.frozen_front(images)
+        c3, c4, c5 = self.backbone.forward(c2)
+        logits, lines = self.line.forward(c5)
+        self._c5_shape = c5.shape
+        return (c2, c3, c4, c5), logits, lines
+
+    def _dense_part(self, feats, logits, lines, depth_gt, seg_gt, H, W):
+        c2, c3, c4, c5 = feats
+        ref_xy, ids = self.reference_points(logits[-1], lines[-1])
+        x32, depth0 = self.stage32.forward(c5, ref_xy)
+        outs = self.dense.forward(x32, depth0, (c4, c3, c2), H, W)
+        outs.update(line_ids=ids, depth0=depth0)
+        self.backward_dense(*self.dense.loss_grads(outs, depth_gt, seg_gt))
+        return outs
+
+    def _capture(self, images, depth_gt, seg_gt, criterion, targets):
+        B, _, H, W = images.shape
+        if H % 32 or W % 32:
+            raise NotImplementedError("the training path is built for input sizes that are multiples of 32 (exact x2 pyramids)")
+        st = dict(images=images.float().clone(), depth_gt=depth_gt.clone(), seg_gt=seg_gt.clone())
+        # warm-up (eager, on a side stream): lazy kernel attributes, cached tables, transpose tables
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            self._defer = []
+            feats, lo, li = self._forward_line(st["images"])
+            self._dense_part(feats, lo, li, st["depth_gt"], st["seg_gt"], H, W)
+            _, dlo, dli = criterion.forward_backward_stacked(lo, li, targets)
+            self.backward_line(dlo, dli)
+            self._defer = None
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        self._defer = []
+        st["g1"] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(st["g1"]):
+            st["feats"], st["logits"], st["lines"] = self._forward_line(st["images"])
+        st["g2"] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(st["g2"], pool=st["g1"].pool()):
+            st["outs"] = self._dense_part(st["feats"], st["logits"], st["lines"], st["depth_gt"], st["seg_gt"], H, W)
+        st["ex2"], self._defer = self._defer, []
+        st["dlogits"], st["dlines"] = torch.zeros_like(st["logits"]), torch.zeros_like(st["lines"])
+        st["g3"] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(st["g3"], pool=st["g1"].pool()):
+            self.backward_line(st["dlogits"], st["dlines"])
+        st["ex3"], self._defer = self._defer, None
+        return st
+
+    def _train_step_graphed(self, images, targets, depth_gt, seg_gt, criterion):
+        key = (tuple(images.shape), tuple(depth_gt.shape), id(criterion))
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = self._capture(images, depth_gt, seg_gt, criterion, targets)
+        st["images"].copy_(images, non_blocking=True)
+        st["depth_gt"].copy_(depth_gt, non_blocking=True)
+        st["seg_gt"].copy_(seg_gt, non_blocking=True)
+        st["g1"].replay()                                                    # backbone + line branch forward
+        pend = criterion.matcher.stacked_cost(st["logits"], st["lines"], targets)
+        st["g2"].replay()                                                    # 1/32 stage + dense branch: forward, losses, backward
+        self._defer = None
+        self._exchange(st["ex2"])
+        set_losses, dlogits, dlines = criterion.forward_backward_stacked(st["logits"], st["lines"], targets, pending=pend)
+        st["dlogits"].copy_(dlogits, non_blocking=True)
+        st["dlines"].copy_(dlines, non_blocking=True)
+        st["g3"].replay()                                                    # line branch + backbone backward
+        self._exchange(st["ex3"])
+        self.step()
+        return self._report(criterion, set_losses, st["outs"], st["logits"], st["lines"])
