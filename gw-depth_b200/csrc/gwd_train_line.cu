@@ -62,33 +62,44 @@ __global__ void gwd_ref_affine_kernel(const float* __restrict__ ref, int64_t ref
 }
 
 // d_kv fp32 [rows, 2D] = (d ref_k | d ref_v)  ->  d_ref bf16 [rows, 2D] = (d ref_k * sigma | d ref_v);
-// dmu[c] += sum_rows d ref_k, dls[c] += sum_rows d ref_k * sigma * ref[:, c].  One thread per column: deterministic.
-__global__ void gwd_ref_affine_bwd_kernel(const float* __restrict__ d_kv, const float* __restrict__ ref, int64_t ref_rs,
-                                          const float* __restrict__ ls, bf16* __restrict__ d_ref, float* __restrict__ dmu,
-                                          float* __restrict__ dls, int rows, int D) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= 2 * D) return;
-  if (c >= D) {
-    for (int r = 0; r < rows; ++r) d_ref[static_cast<int64_t>(r) * 2 * D + c] = __float2bfloat16(d_kv[static_cast<int64_t>(r) * 2 * D + c]);
-    return;
-  }
-  const float sig = __expf(ls[c]);
+// dmu[c] += sum_rows d ref_k, dls[c] += sum_rows d ref_k * sigma * ref[:, c].  A CTA owns 32 columns (one warp-wide coalesced
+// segment per row) and splits the rows over its 8 warps; the 8 partial sums meet in shared memory (fixed order: deterministic).
+__global__ void __launch_bounds__(256) gwd_ref_affine_bwd_kernel(const float* __restrict__ d_kv, const float* __restrict__ ref,
+                                                                int64_t ref_rs, const float* __restrict__ ls, bf16* __restrict__ d_ref,
+                                                                float* __restrict__ dmu, float* __restrict__ dls, int rows, int D) {
+  __shared__ float red[2][8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  if (c >= 2 * D) return;                       // (2D is a multiple of 32: whole CTAs leave together)
+  const bool is_k = c < D;
+  const float sig = is_k ? __expf(ls[c]) : 1.f;
   float sm = 0.f, sl = 0.f;
-  for (int r = 0; r < rows; ++r) {
+  for (int r = warp; r < rows; r += 8) {
     const float g = d_kv[static_cast<int64_t>(r) * 2 * D + c];
-    sm += g;
-    sl = fmaf(g * sig, ref[r * ref_rs + c], sl);
+    if (is_k) {
+      sm += g;
+      sl = fmaf(g * sig, ref[r * ref_rs + c], sl);
+    }
     d_ref[static_cast<int64_t>(r) * 2 * D + c] = __float2bfloat16(g * sig);
   }
-  dmu[c] += sm;
-  dls[c] += sl;
+  red[0][warp][lane] = sm;
+  red[1][warp][lane] = sl;
+  __syncthreads();
+  if (warp == 0 && is_k) {
+    float a = 0.f, b2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { a += red[0][w][lane]; b2 += red[1][w][lane]; }
+    dmu[c] += a;
+    dls[c] += b2;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared structure of the two score-side backward kernels: one CTA per (image, head) walks the T tokens in tiles of
-// 128.  Per tile: the [tile][R] score rows (coalesced, staged in shared memory with a padded row), the [tile][hd] bf16
-// token rows; a thread owns a token for the per-token part, then the threads re-map to the R x hd outputs of the
-// token reduction (a warp = one reference point x 32 channels: broadcast + stride-1 shared-memory reads).
+// shared structure of the two score-side backward kernels: one CTA per (head, image, tile of 128 tokens).  The [tile][R] score
+// rows are staged in shared memory (coalesced, padded rows) next to the [tile][hd] bf16 token rows; a thread owns a token for
+// the per-token part, then the threads re-map to the R x hd outputs of the token reduction (a warp = one reference point x 32
+// channels: broadcast + stride-1 shared-memory reads) and add the tile's partial sums to the (pre-zeroed) output with one
+// atomic per value: 4 tiles per (image, head) at 480x640.
 // ------------------------------------------------------------------------------------------------
 template <bool SOFTMAX>
 __global__ void __launch_bounds__(kTokTile) gwd_ref_bwd_kernel(
@@ -112,9 +123,9 @@ __global__ void __launch_bounds__(kTokTile) gwd_ref_bwd_kernel(
   float acc[16];                         // R * hd / 128 <= 16 outputs of the token reduction per thread (R <= 64, hd <= 32)
 #pragma unroll
   for (int e = 0; e < 16; ++e) acc[e] = 0.f;
-  for (int tok0 = 0; tok0 < T; tok0 += kTokTile) {
+  {
+    const int tok0 = blockIdx.z * kTokTile;
     const int ntok = min(kTokTile, T - tok0);
-    __syncthreads();                     // previous tile's reduction has finished with st / xt (and rv is loaded)
     const int64_t sbase = ((static_cast<int64_t>(b) * heads + h) * T + tok0) * R;
     for (int i = tid; i < ntok * R; i += kTokTile) st[(i / R) * (R + 1) + i % R] = __ldg(S + sbase + i);
     for (int i = tid; i < ntok * hd; i += kTokTile) {
@@ -175,7 +186,7 @@ __global__ void __launch_bounds__(kTokTile) gwd_ref_bwd_kernel(
     const int o = tid + e * kTokTile;
     if (o < nout) {
       const int r = o / hd, d = o - r * hd;
-      dRV[(static_cast<int64_t>(b) * R + r) * drv_rs + h * hd + d] = acc[e] * scale;
+      atomicAdd(dRV + (static_cast<int64_t>(b) * R + r) * drv_rs + h * hd + d, acc[e] * scale);
     }
   }
 }
@@ -369,7 +380,8 @@ extern "C" int gwd_ref_affine_bwd(const float* d_kv, const float* ref, int64_t r
   GWD_STREAM;
   GWD_CHECK_ARG(d_kv && ref && logsigma && d_ref && dmu && dlogsigma && rows > 0 && D > 0 && ref_rs >= D,
                 "gwd_ref_affine_bwd: bad argument");
-  gwd_ref_affine_bwd_kernel<<<static_cast<unsigned>(gwd_ceil_div(2 * D, 128)), 128, 0, stream>>>(
+  GWD_CHECK_ARG(D % 32 == 0, "gwd_ref_affine_bwd: D must be a multiple of 32");
+  gwd_ref_affine_bwd_kernel<<<static_cast<unsigned>(2 * D / 32), 256, 0, stream>>>(
       d_kv, ref, ref_rs, logsigma, static_cast<bf16*>(d_ref), dmu, dlogsigma, rows, D);
   GWD_LAUNCHED();
   return GWD_OK;
@@ -389,7 +401,7 @@ extern "C" int gwd_ref_requery_bwd(const float* a, const float* refv, int64_t re
   size_t smem;
   GWD_CHECK_ARG(ref_bwd_smem(R, hd, &smem), "gwd_ref_requery_bwd: %d reference points do not fit shared memory", R);
   GWD_CUDA(cudaFuncSetAttribute(gwd_ref_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  gwd_ref_bwd_kernel<true><<<dim3(heads, B), kTokTile, smem, stream>>>(a, refv, ref_rs, static_cast<const bf16*>(d_qnew), dq_rs, d_a,
+  gwd_ref_bwd_kernel<true><<<dim3(heads, B, static_cast<unsigned>(gwd_ceil_div(T, kTokTile))), kTokTile, smem, stream>>>(a, refv, ref_rs, static_cast<const bf16*>(d_qnew), dq_rs, d_a,
                                                                      nullptr, 0, d_refv, drv_rs, T, heads, hd, R, scale);
   GWD_LAUNCHED();
   return GWD_OK;
@@ -405,7 +417,7 @@ extern "C" int gwd_ref_scores_bwd(const float* d_a, const float* refk, int64_t r
   size_t smem;
   GWD_CHECK_ARG(ref_bwd_smem(R, hd, &smem), "gwd_ref_scores_bwd: %d reference points do not fit shared memory", R);
   GWD_CUDA(cudaFuncSetAttribute(gwd_ref_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  gwd_ref_bwd_kernel<false><<<dim3(heads, B), kTokTile, smem, stream>>>(d_a, refk, ref_rs, static_cast<const bf16*>(q), q_rs, nullptr,
+  gwd_ref_bwd_kernel<false><<<dim3(heads, B, static_cast<unsigned>(gwd_ceil_div(T, kTokTile))), kTokTile, smem, stream>>>(d_a, refk, ref_rs, static_cast<const bf16*>(q), q_rs, nullptr,
                                                                       static_cast<bf16*>(d_q), dq_rs, d_refk, drk_rs, T, heads, hd, R,
                                                                       scale);
   GWD_LAUNCHED();

@@ -198,7 +198,7 @@ class LineStage(FlatModule):
                                              mask=t["mask"], dbias=blk["dbias"])
             self.view(self.G, blk["table"]).index_add_(0, self.rel_index, blk["dbias"].permute(1, 2, 0).reshape(N * N, nh))
             # q_new = scale * softmax_R(a3) @ ref_v
-            d_kv = torch.empty(B * R, 2 * D, dtype=torch.float32, device=self.dev)         # d ref_k | d ref_v
+            d_kv = torch.zeros(B * R, 2 * D, dtype=torch.float32, device=self.dev)         # d ref_k | d ref_v (accumulated)
             d_a = ops.ref_requery_bwd(t["a3"], t["ref"][:, D:], 2 * D, dqkv3, 3 * D, d_kv[:, D:], 2 * D, B, P, nh, hd, R, self.scale)
             for a_in, raw, stats in reversed(t["rounds"]):
                 d_a = ops.ref_diffuse_bwd(d_a, raw, stats, a_in, blk["filt"][1], blk["gfw"], blk["gfb"], B, nh, P, R,

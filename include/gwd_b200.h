@@ -411,6 +411,7 @@ int gwd_ref_affine_bwd(const float* d_kv, const float* ref, int64_t ref_rs, cons
                        float* dlogsigma, int32_t rows, int32_t D, void* stream);
 /* Backward of gwd_ref_requery: a = the diffused scores fp32 [B,heads,T,R], refv fp32 rows b*R+r (row stride ref_rs), d_qnew
  * bf16 rows b*T+t (row stride dq_rs) -> d_a fp32 [B,heads,T,R] (soft-max backward included), d_refv fp32 (row stride drv_rs) */
+/* (d_refv / d_refk below are ACCUMULATED with atomics over the token tiles: zero them first) */
 int gwd_ref_requery_bwd(const float* a, const float* refv, int64_t ref_rs, const void* d_qnew, int64_t dq_rs, float* d_a,
                         float* d_refv, int64_t drv_rs, int32_t B, int32_t T, int32_t heads, int32_t hd, int32_t R, float scale,
                         void* stream);
