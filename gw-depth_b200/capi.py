@@ -129,6 +129,7 @@ SIGNATURES = {
     "gwd_fold_mirror": (c_int, [P, P, P, L, P]),
     "gwd_im2col3x3_s2": (c_int, [P, P, I, I, I, I, P]),
     "gwd_col2im3x3_s2": (c_int, [P, P, P, I, I, I, I, P]),
+    "gwd_select_lines": (c_int, [P, I, P, I, I, I, I, I, P, P, P]),
 }
 
 _lib = None

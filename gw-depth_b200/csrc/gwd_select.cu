@@ -320,6 +320,30 @@ gwd_seg_confusion_kernel(const float* __restrict__ logits, int64_t pixel_stride,
   if (threadIdx.x < C * C && hist[threadIdx.x]) atomicAdd(&conf[threadIdx.x], static_cast<unsigned long long>(hist[threadIdx.x]));
 }
 
+// ------------------------------------------------------------------------------------------------
+// reference-line selection of the dense encoder (multiscale_transformerr.py:1165-1179): the num_ref lines with the largest
+// RAW line logit (class 0), in descending order (torch.topk, ties by the lower index), and their points mapped to [-1,1].
+// One CTA per image, thread t ranks query t by counting the queries that beat it (Q = 100: 10 k comparisons).
+// ------------------------------------------------------------------------------------------------
+__global__ void gwd_select_lines_kernel(const float* __restrict__ logits, int ncls, const float* __restrict__ lines, int D, int Q,
+                                        int num_ref, int npts, float* __restrict__ ref_xy, int64_t* __restrict__ ids) {
+  extern __shared__ float sl[];
+  const int b = blockIdx.x;
+  for (int t = threadIdx.x; t < Q; t += blockDim.x) sl[t] = logits[(static_cast<int64_t>(b) * Q + t) * ncls];
+  __syncthreads();
+  for (int t = threadIdx.x; t < Q; t += blockDim.x) {
+    const float v = sl[t];
+    int rank = 0;
+    for (int j = 0; j < Q; ++j) rank += (sl[j] > v) || (sl[j] == v && j < t);
+    if (rank < num_ref) {
+      ids[static_cast<int64_t>(b) * num_ref + rank] = t;
+      const float* ln = lines + (static_cast<int64_t>(b) * Q + t) * D;
+      float* o = ref_xy + (static_cast<int64_t>(b) * num_ref + rank) * npts * 2;
+      for (int i = 0; i < npts * 2; ++i) o[i] = ln[i] * 2.f - 1.f;
+    }
+  }
+}
+
 }  // namespace
 
 extern "C" int gwd_certain_sample(const float* pred_small, int32_t h, int32_t w, const float* pred_large, int32_t H,
@@ -343,6 +367,18 @@ extern "C" int gwd_certain_sample(const float* pred_small, int32_t h, int32_t w,
     }
   }
   gwd_certain_sample_kernel<<<B, kCsThreads, smem, stream>>>(p);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_select_lines(const float* logits, int32_t num_classes, const float* lines, int32_t line_dim, int32_t B, int32_t Q,
+                                int32_t num_ref, int32_t points_per_line, float* ref_xy, int64_t* ids, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  GWD_CHECK_ARG(logits && lines && ref_xy && ids && B > 0 && Q > 0, "gwd_select_lines: null pointer / empty");
+  GWD_CHECK_ARG(num_ref > 0 && num_ref <= Q && points_per_line > 0 && 2 * points_per_line <= line_dim && Q <= 8192,
+                "gwd_select_lines: needs num_ref <= Q <= 8192 and 2 * points_per_line <= line_dim");
+  gwd_select_lines_kernel<<<static_cast<unsigned>(B), 128, sizeof(float) * Q, stream>>>(logits, num_classes, lines, line_dim, Q, num_ref,
+                                                                                      points_per_line, ref_xy, ids);
   GWD_LAUNCHED();
   return GWD_OK;
 }

@@ -881,3 +881,15 @@ def col2im3x3_s2(dcol, H, W, add=None):
     dx = torch.empty(B, H, W, C, dtype=torch.bfloat16, device=dcol.device)
     capi.check(_L().gwd_col2im3x3_s2(_ptr(dcol), _ptr(add), _ptr(dx), B, H, W, C, _stream()), "gwd_col2im3x3_s2")
     return dx
+
+
+def select_lines(logits, lines, num_ref, points_per_line):
+    """logits fp32 [B,Q,C], lines fp32 [B,Q,D] -> (ref_xy fp32 [B, num_ref * points_per_line, 2] in [-1,1], ids int64 [B,num_ref]):
+    the top-num_ref lines by raw line logit and their points (multiscale_transformerr.py:1165-1179)"""
+    B, Q, C = logits.shape
+    assert logits.dtype == lines.dtype == torch.float32 and logits.is_contiguous() and lines.is_contiguous()
+    ref_xy = torch.empty(B, num_ref * points_per_line, 2, dtype=torch.float32, device=logits.device)
+    ids = torch.empty(B, num_ref, dtype=torch.int64, device=logits.device)
+    capi.check(_L().gwd_select_lines(_ptr(logits), C, _ptr(lines), lines.shape[-1], B, Q, num_ref, points_per_line, _ptr(ref_xy),
+                                     _ptr(ids), _stream()), "gwd_select_lines")
+    return ref_xy, ids

@@ -97,13 +97,7 @@ class Trainer:
         """top-num_ref lines by RAW line logit -> end points (and centre with --with_dense_center) in [-1,1]
         (src/models/multiscale_transformerr.py:1165-1179); no gradient flows through the selection or the coordinates"""
         c = self.cfg
-        B = logits.shape[0]
-        ids = torch.topk(logits[:, :, 0], c["num_ref"], dim=-1).indices
-        chosen = torch.gather(lines, 1, ids[:, :, None].expand(-1, -1, lines.shape[-1]))
-        pts = chosen.reshape(B, c["num_ref"], -1, 2) * 2 - 1.0
-        if not c["with_dense_center"]:
-            pts = pts[:, :, :2]
-        return pts.reshape(B, -1, 2).contiguous().float(), ids
+        return ops.select_lines(logits.contiguous(), lines.contiguous(), c["num_ref"], 3 if c["with_dense_center"] else 2)
 
     def forward(self, images, pinned=None, after_line=None):
         """images fp32 [B,3,H,W] (equal sizes, H and W multiples of 32).  Returns (logits [S,B,Q,2], lines [S,B,Q,D] fp32 of all

@@ -441,6 +441,12 @@ int gwd_fold_mirror(const float* p, const float* scale, void* mirror_bf16, int64
 int gwd_im2col3x3_s2(const void* x, void* col, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
 /* adjoint of gwd_im2col3x3_s2: dx bf16 [B,H,W,C] = add (optional) + the taps of dcol bf16 [B,ho,wo,9C] that land on each pixel */
 int gwd_col2im3x3_s2(const void* dcol, const void* add, void* dx, int32_t B, int32_t H, int32_t W, int32_t C, void* stream);
+/* Reference-line selection of the dense encoder (src/models/multiscale_transformerr.py:1165-1179: torch.topk over the RAW line
+ * logit + gather + * 2 - 1): logits fp32 [B,Q,num_classes] (class 0 is ranked), lines fp32 [B,Q,line_dim] -> ids int64
+ * [B,num_ref] (descending logit, ties by the lower index) and ref_xy fp32 [B, num_ref * points_per_line, 2] = the first
+ * points_per_line (x, y) pairs of every selected line mapped to [-1, 1]. */
+int gwd_select_lines(const float* logits, int32_t num_classes, const float* lines, int32_t line_dim, int32_t B, int32_t Q,
+                     int32_t num_ref, int32_t points_per_line, float* ref_xy, int64_t* ids, void* stream);
 
 #ifdef __cplusplus
 }

@@ -396,3 +396,20 @@ def test_images_to_batch_bit_exact():
     out, mask, padded = ops.images_to_batch([t.cuda() for t in ragged])
     nt = M.nested_tensor_from_tensor_list([reference(t) for t in ragged])
     assert padded and torch.equal(out.cpu(), nt.tensors) and torch.equal(mask.cpu(), nt.mask)
+
+
+@pytest.mark.parametrize("B,Q,num_ref,npts", [(3, 100, 20, 2), (2, 100, 20, 3), (1, 37, 37, 2)])
+def test_select_lines_matches_topk_gather(B, Q, num_ref, npts):
+    """gwd_select_lines == torch.topk over the raw line logit + gather + * 2 - 1 (multiscale_transformerr.py:1165-1179),
+    index-identical (descending order), ties broken by the lower index"""
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import ops
+    g = torch.Generator().manual_seed(Q + npts)
+    logits = torch.randn(B, Q, 2, generator=g)
+    logits[0, 5, 0] = logits[0, 9, 0] = logits[0].max() + 1.0           # an exact tie at the top
+    lines = torch.rand(B, Q, 6, generator=g)
+    ref_xy, ids = ops.select_lines(logits.cuda(), lines.cuda(), num_ref, npts)
+    want = torch.sort(logits[:, :, 0], dim=-1, descending=True, stable=True).indices[:, :num_ref]
+    assert torch.equal(ids.cpu(), want)
+    pts = torch.gather(lines, 1, want[:, :, None].expand(-1, -1, 6)).reshape(B, num_ref, 3, 2)[:, :, :npts] * 2 - 1.0
+    assert torch.equal(ref_xy.cpu(), pts.reshape(B, -1, 2))
