@@ -19,7 +19,7 @@ import torch
 
 from . import ops
 from .ops import ACT_RELU, RES_AFTER, RES_BEFORE_NORM, RES_NONE, PackedWeight, conv_gemm, pack_conv3x3, pack_linear
-from .train_flat import Conv3x3, FlatModule, Linear
+from .train_flat import join_wgrads, Conv3x3, FlatModule, Linear
 
 BODY = "backbone.0.body."
 LAYERS = ((1, 3), (2, 4), (3, 6), (4, 3))
@@ -217,6 +217,7 @@ class BackboneTrain(FlatModule):
                 else:
                     d_x = self.lin_bwd(blk["c1"], d_y1, x.view(B * H * W, -1), res=gs)                       # + identity shortcut
                 g = d_x.view(B, H, W, -1) if d_x is not None else None
+        join_wgrads()
         self.finish_grads()
         if not keep_tape:
             self.tape = None

@@ -29,7 +29,7 @@ import torch
 from . import ops
 from .engine import DEFAULT_CFG
 from .ops import ACT_ELU, ACT_GELU, ACT_NONE, ACT_SIGMOID, conv_gemm
-from .train_flat import Conv3x3, FlatModule, Linear
+from .train_flat import join_wgrads, Conv3x3, FlatModule, Linear
 
 PREFIX = "depth_decoder."
 KINDS = ("depth", "seg")
@@ -128,6 +128,7 @@ class DenseHead(FlatModule):
             d = self.lin_bwd(m["fc2"], d, s["t"])
             d = ops.act_bwd(d, s["h_raw"], ACT_GELU, from_input=True)
             d_x = self.lin_bwd(m["fc1"], d, tp["x"], res=d_x)
+        join_wgrads()
         self.mask_grads()
         if not keep_tape:
             self.tape = None

@@ -12,7 +12,7 @@ import torch
 
 from . import ops
 from .ops import ACT_GELU, ACT_NONE, PackedWeight, conv_gemm
-from .train_flat import Conv3x3, FlatModule, Linear
+from .train_flat import join_wgrads, Conv3x3, FlatModule, Linear
 
 P0 = "dense_encoder."
 
@@ -106,6 +106,7 @@ class StageEntry(FlatModule):
             prev, t1, t2 = tp[kind]
             d_t2 = ops.layernorm_bwd(low(g, td), t2, ln[0], ln[2], ln[3])
             outs[0 if kind == "d" else 1] = self.lin_bwd(fc1, self.lin_bwd(fc2, d_t2, t1), prev)
+        join_wgrads()
         if not keep_tape:
             self.tape = None
         return d_prev_x, outs[0], outs[1], d_feat
@@ -147,6 +148,7 @@ class DepthHead16(FlatModule):
         self.G.zero_()
         d_z = ops.act_bwd(d_depth.contiguous().view(-1, 1), y, ops.ACT_SIGMOID, out_cols=self.l1.n_pad)
         d_cat = self.lin_bwd(self.l0, self.lin_bwd(self.l1, d_z, t), cat)
+        join_wgrads()
         if not keep_tape:
             self.tape = None
         return d_cat[:, :C], d_cat[:, C:cat.shape[1]]

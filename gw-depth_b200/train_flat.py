@@ -14,6 +14,41 @@ from . import ops, parallel
 from .ops import RES_AFTER, RES_NONE, PackedWeight, conv_gemm, round_up
 
 
+# Weight gradients are off the critical path of a backward pass (nothing reads them before the optimizer), so they run on a SIDE
+# stream: in the captured training step they become parallel graph branches next to the data-gradient chain, which matters for
+# the many launches that do not fill 148 SMs (1/32 ... 1/8 scale maps at batch 8).  Operands are kept alive until the join.
+_SIDE = {}
+_KEEP = []
+FORK_WGRAD = True
+
+
+def _side_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=key)
+    return _SIDE[key]
+
+
+def fork_wgrad(fn, *operands):
+    """run fn() (a weight-gradient launch reading `operands`) on the side stream, ordered after everything enqueued so far"""
+    if not FORK_WGRAD:
+        return fn()
+    main = torch.cuda.current_stream()
+    side = _side_stream(operands[0].device)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        fn()
+    _KEEP.extend(operands)
+
+
+def join_wgrads(dev=None):
+    """the main stream waits for every forked weight gradient (call at the end of a module's backward, before the flat
+    gradient buffer is read or the operands' memory is reused)"""
+    if _KEEP:
+        torch.cuda.current_stream().wait_stream(_side_stream(_KEEP[0].device))
+        del _KEEP[:]
+
+
 def _numel(shape):
     n = 1
     for s in shape:
@@ -183,14 +218,14 @@ class FlatModule:
     @staticmethod
     def conv_bwd(cv, dY, X, need_dx=True, res=None):
         """dY [B,H,W,n_pad], X [B,H,W,cin_pad] bf16: dW accumulated into the flat gradient view; returns dX (+ res)"""
-        ops.conv3x3_wgrad(dY, X, cv.gw)
+        fork_wgrad(lambda: ops.conv3x3_wgrad(dY, X, cv.gw), dY, X)
         if not need_dx:
             return None
         return conv_gemm(dY, cv.pwT, bias=False, res=res, res_mode=RES_AFTER if res is not None else RES_NONE)
 
     @staticmethod
     def lin_bwd(lin, dY, X, need_dx=True, res=None, x_coff=0):
-        ops.linear_wgrad(dY, X, lin.gw, lin.gb, x_coff=x_coff)
+        fork_wgrad(lambda: ops.linear_wgrad(dY, X, lin.gw, lin.gb, x_coff=x_coff), dY, X)
         if not need_dx:
             return None
         return conv_gemm(dY, lin.pwT, bias=False, res=res, res_mode=RES_AFTER if res is not None else RES_NONE)

@@ -35,7 +35,7 @@ import torch
 from . import ops
 from .engine import shift_mask, sine_table, _compose
 from .ops import ACT_GELU, ACT_SIGMOID, RES_AFTER, PackedWeight, conv_gemm, pack_linear
-from .train_flat import FlatModule, Linear
+from .train_flat import join_wgrads, FlatModule, Linear
 
 PREFIX = "dense_encoder.dense_transformer."
 DIP = "dense_input_proj."
@@ -212,6 +212,7 @@ class LineStage(FlatModule):
             d_n1, _ = ops.window_merge(d_xw, zeros, B, H, W, ws, shift)
             g = ops.layernorm_bwd(d_n1, t["x"], blk["n1"][0], blk["n1"][2], blk["n1"][3], add=g_new)
         d_c5 = self.lin_bwd(self.dip, g, tp["c5"])
+        join_wgrads()
         if not keep_tape:
             self.tape = None
         return d_c5

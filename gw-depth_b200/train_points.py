@@ -27,7 +27,7 @@ import torch
 
 from . import ops
 from .ops import PackedWeight, conv_gemm, round_up
-from .train_flat import FlatModule, Linear
+from .train_flat import join_wgrads, FlatModule, Linear
 from .train_pyramid import Pyramid
 
 
@@ -115,6 +115,7 @@ class PointPred(FlatModule):
         self.G.zero_()
         d_g = self.lin_bwd(self.refer, d_pr, tp["g"])
         d_buf = self.lin_bwd(self.pre, d_g, tp["buf"])
+        join_wgrads()
         self.mask_grads()
         if not keep_tape:
             self.tape = None

@@ -21,7 +21,7 @@ import torch
 
 from . import ops
 from .ops import ACT_GELU, ACT_NONE, RES_AFTER, RES_NONE, conv_gemm, round_up
-from .train_flat import Conv3x3, FlatModule, Linear
+from .train_flat import join_wgrads, Conv3x3, FlatModule, Linear
 
 POOLS = (16, 8, 4, 2)
 
@@ -126,6 +126,7 @@ class Pyramid(FlatModule):
             d = self._conv_ln_bwd(dy, z1, c1, x, ACT_GELU, res=d)
         d = self._conv_ln_bwd(d, tp["z_f2"], self.first[1], tp["x_f0"], ACT_GELU)
         d = self._conv_ln_bwd(d, tp["z_f0"], self.first[0], tp["rg"], ACT_GELU, need_dx=need_dx)
+        join_wgrads()
         if not keep_tape:
             self.tape = None
         return d

@@ -26,7 +26,7 @@ import torch
 from . import ops
 from .engine import shift_mask
 from .ops import ACT_GELU, RES_AFTER, PackedWeight, conv_gemm
-from .train_flat import FlatModule, Linear
+from .train_flat import join_wgrads, FlatModule, Linear
 
 _DEAD = ("attn.diff_mu", "attn.diff_logsigma", "attn.border_mu", "attn.border_logsigma", "attn.proj_seg.weight",
          "attn.proj_seg.bias")
@@ -217,6 +217,7 @@ class ClassStage(FlatModule):
                 d_ln, _ = ops.window_merge(win, zeros, B, H, W, ws, shift, C=width, win_coff=coff)
                 outs.append(ops.layernorm_bwd(d_ln, src, blk[ln][0], blk[ln][2], blk[ln][3], add=g_sc))
             g_x, g_d, g_s = outs
+        join_wgrads()
         if not keep_tape:
             self.tape = None
         return g_x, g_d, g_s

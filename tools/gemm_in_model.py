@@ -5,6 +5,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
+os.environ["GWD_CUDA_GRAPH"] = "0"      # eager launches: the per-launch events need them
 import torch  # noqa: E402
 from helpers import synth, synth_weights  # noqa: E402
 import gwdepth_b200  # noqa: F401,E402
