@@ -224,6 +224,30 @@ def test_benchmark_size_properties():
     assert rel(full["pred_logits"][5:6], solo["pred_logits"])[1] < TOL["logits_max"]
 
 
+@pytest.mark.parametrize("B,H,W,seed", [(16, 480, 640, 3), (1, 960, 1280, 4)])
+def test_benchmark_and_large_sizes_match_oracle(B, H, W, seed):
+    """oracle parity AT the benchmark configuration (BASELINE configs[1]: 16 x 480 x 640) and at the large eval size of config 5
+    (960 x 1280, L = 1 200 tokens): every output of every image against the fp32 CPU oracle, selections pinned"""
+    net, _, _ = model()
+    images, _, _, _ = synth.synth_batch(B, H, W, seed=seed)
+    trace = {}
+    ref = oracle.forward(synth_weights(), images, trace=trace)
+    with torch.no_grad():
+        out = net(images.cuda(), _pinned=pinned_from(trace))
+    per_image = [rel(out["pred_depth"][3][b], ref["pred_depth"][3][b]) for b in range(B)]
+    m, x = rel(out["pred_depth"][3], ref["pred_depth"][3])
+    print("depth %dx%dx%d: mean-rel %.4f max-rel %.4f (worst image mean %.4f); logits max-rel %.4f, lines %.4f, seg mean-rel %.4f" % (
+        B, H, W, m, x, max(p[0] for p in per_image), rel(out["pred_logits"], ref["pred_logits"])[1],
+        rel(out["pred_lines"], ref["pred_lines"])[1], rel(out["pred_seg"], ref["pred_seg"])[0]))
+    assert m < TOL["depth_mean"] and x < TOL["depth_max"], (m, x)
+    assert max(p[0] for p in per_image) < 1.5 * TOL["depth_mean"]
+    assert rel(out["pred_logits"], ref["pred_logits"])[1] < TOL["logits_max"]
+    assert rel(out["pred_lines"], ref["pred_lines"])[1] < TOL["lines_max"]
+    assert rel(out["pred_seg"], ref["pred_seg"])[0] < TOL["seg_mean"]
+    for i in range(3):
+        assert rel(out["pred_depth"][i], ref["pred_depth"][i])[0] < 6e-2, i
+
+
 def test_infer_stream_matches_forward():
     """the pipelined serving loop (three streams, double buffers) returns exactly what model(x) returns, batch by batch"""
     net, _, _ = model()
