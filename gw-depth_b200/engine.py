@@ -122,6 +122,7 @@ class Engine:
         self._tables = {}
         self._graphs = {}
         self._side, self._side2 = torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)
+        self._side3 = torch.cuda.Stream(device=self.dev)
         self._pack_backbone()
         self._pack_detr()
         self._pack_dense()
@@ -565,7 +566,7 @@ class Engine:
         logits = self.pyramid(pb["pyr"], rg.view(B, H, W, Kp), B, H, W)
         return ops.anchor_mix(logits, anchor, B, H * W, K).view(B, H, W)
 
-    def dense_encoder(self, dense_in, feats, pred_lines, pred_logits, B, h5, w5, pinned, trace, masks=None):
+    def dense_encoder(self, dense_in, feats, pred_lines, pred_logits, B, h5, w5, pinned, trace, masks=None, cbs=None):
         """ReferTransformer.forward (multiscale_transformerr.py:1151-1319)"""
         c = self.cfg
         D, td, R0 = c["dense_trans_dim"], c["class_token_dim"], c["num_ref"]
@@ -593,7 +594,7 @@ class Engine:
             buf = torch.empty(B * H * W, C + 3 * td, dtype=torch.bfloat16, device=self.dev)
             buf[:, C + 2 * td:] = 0
             pc = conv_gemm(prev, st["proj_class"])       # proj_class commutes with the nearest up-sampling: run it at low res
-            cb = conv_gemm(f, st["proj_backbn"], post_act=ACT_GELU)
+            cb = cbs[si] if cbs is not None else conv_gemm(f, st["proj_backbn"], post_act=ACT_GELU)
             ops.upsample_nearest(pc.view(B, ph, pw_, C), H, W, add=cb, out=buf.view(B, H, W, -1), y_coff=0)
             if si == 0:
                 buf[:, C:C + td] = self.depth_token
@@ -696,14 +697,21 @@ class Engine:
         c5 = feats[3]
         h5, w5 = c5.shape[1:3]
         tok5 = c5.reshape(B * h5 * w5, c5.shape[-1])
+        # the dense branch's projections of the backbone maps (dense_input_proj, proj_backbn1-3: 0.4 ms of wide GEMMs) do not depend
+        # on the line branch: a parallel branch next to the latency-bound DETR chain (side stream / graph fork)
+        main = torch.cuda.current_stream()
+        self._side3.wait_stream(main)
+        with torch.cuda.stream(self._side3):
+            dense_in = conv_gemm(tok5, self.dense_input_proj)
+            cbs = [conv_gemm(feats[2 - si], st["proj_backbn"], post_act=ACT_GELU) for si, st in enumerate(self.class_stages)]
         src = conv_gemm(tok5, self.input_proj)
         hs, memory = self.detr(src, B, h5, w5, mask5=None if masks is None else masks[3])
         logits, lines = self.line_heads(hs, B)
         out = {"pred_logits": logits[-1], "pred_lines": lines[-1]}
         if c["aux_loss"]:
             out["aux_outputs"] = [{"pred_logits": a, "pred_lines": b} for a, b in zip(logits[:-1], lines[:-1])]
-        dense_in = conv_gemm(tok5, self.dense_input_proj)
-        buf4, depths = self.dense_encoder(dense_in, feats, out["pred_lines"], out["pred_logits"], B, h5, w5, pinned, trace, masks)
+        main.wait_stream(self._side3)
+        buf4, depths = self.dense_encoder(dense_in, feats, out["pred_lines"], out["pred_logits"], B, h5, w5, pinned, trace, masks, cbs)
         H4, W4 = feats[0].shape[1:3]
         depth, seg = self.dense_head(buf4, depths[-1], B, H4, W4, H, W)
         out["pred_depth"] = [d.unsqueeze(1) for d in depths] + [depth]

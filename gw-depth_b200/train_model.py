@@ -92,6 +92,29 @@ class Trainer:
     def numel(self):
         return sum(m.numel for m in self.modules())
 
+    def set_lr(self, lr, lr_backbone=None):
+        """what `StepLR.step()` does to the reference's two parameter groups (src/main_glassrgbd.py:59-67)"""
+        for m in self.modules():
+            if m is self.backbone:
+                m.lr = lr_backbone if lr_backbone is not None else m.lr
+            else:
+                m.lr = lr
+
+    def optimizer_state(self):
+        """Adam moments and step counts of every flat buffer (physical layout) for a resumable checkpoint: the counterpart of
+        `optimizer.state_dict()` in src/main_glassrgbd.py:214-226"""
+        return {"format": "gwd_flat_adamw_v1",
+                "buffers": [{"numel": m.numel, "t": m.t, "lr": m.lr, "M": m.M.detach().cpu(), "V": m.V.detach().cpu()} for m in self.modules()]}
+
+    def load_optimizer_state(self, state):
+        bufs = state["buffers"]
+        assert state.get("format") == "gwd_flat_adamw_v1" and len(bufs) == len(self.modules()), "optimizer state of another layout"
+        for m, b in zip(self.modules(), bufs):
+            assert b["numel"] == m.numel
+            m.M.copy_(b["M"])
+            m.V.copy_(b["V"])
+            m.t, m.lr = b["t"], b["lr"]
+
     # ------------------------------------------------------------------ forward
     def reference_points(self, logits, lines):
         """top-num_ref lines by RAW line logit -> end points (and centre with --with_dense_center) in [-1,1]
