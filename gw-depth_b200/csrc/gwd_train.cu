@@ -1255,29 +1255,48 @@ int gwd_linear_wgrad_tc_try(const void* dy, int64_t dy_rs, const void* x, int64_
                             int64_t dw_rs, cudaStream_t stream);     // gwd_wgrad_tc.cu (tcgen05 path)
 
 namespace {
-// db[n] += sum_r dY[r][n]: 8 columns per thread, a slab of rows per CTA row, one atomic per column and CTA
-__global__ void __launch_bounds__(256) gwd_colsum_kernel(const bf16* __restrict__ dy, int64_t dy_rs, int64_t rows, int N,
+// db[n] += sum_r dY[r][n]: 8 columns per thread.  A row segment of min(N, 256) columns is held by LPR = 1..32 lanes (a power of
+// two >= columns / 8), so narrow matrices (N = 64: the 1/4-scale Swin stage) put 32 / LPR rows in every warp instead of leaving
+// three quarters of the lanes idle; four independent 16-byte loads per thread and iteration; the lanes that share a column meet
+// by shuffles, the 8 warps in shared memory, one atomic per column and CTA.
+__global__ void __launch_bounds__(256) gwd_colsum_kernel(const bf16* __restrict__ dy, int64_t dy_rs, int64_t rows, int N, int lpr,
                                                          float* __restrict__ db) {
   __shared__ float red[8][32][8];
-  const int cv = threadIdx.x & 31, ry = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cv = lane & (lpr - 1), sub = lane / lpr, rpw = 32 / lpr;
   const int c = (blockIdx.x * 32 + cv) * 8;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (c < N)
-    for (int64_t r = static_cast<int64_t>(blockIdx.y) * 8 + ry; r < rows; r += static_cast<int64_t>(gridDim.y) * 8) {
+  if (c < N) {
+    const int64_t step = static_cast<int64_t>(gridDim.y) * 8 * rpw;
+    int64_t r = (static_cast<int64_t>(blockIdx.y) * 8 + warp) * rpw + sub;
+    for (; r + 3 * step < rows; r += 4 * step) {
+      float f0[8], f1[8], f2[8], f3[8];
+      ld8(dy + r * dy_rs + c, f0);
+      ld8(dy + (r + step) * dy_rs + c, f1);
+      ld8(dy + (r + 2 * step) * dy_rs + c, f2);
+      ld8(dy + (r + 3 * step) * dy_rs + c, f3);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += (f0[i] + f1[i]) + (f2[i] + f3[i]);
+    }
+    for (; r < rows; r += step) {
       float f[8];
       ld8(dy + r * dy_rs + c, f);
 #pragma unroll
       for (int i = 0; i < 8; ++i) acc[i] += f[i];
     }
+  }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) red[ry][cv][i] = acc[i];
+  for (int i = 0; i < 8; ++i) {
+    for (int o = lpr; o < 32; o <<= 1) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], o);
+    red[warp][lane][i] = acc[i];
+  }
   __syncthreads();
-  if (ry == 0 && c < N) {
+  if (warp == 0 && lane < lpr && c < N) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float t = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) t += red[w][cv][i];
+      for (int w = 0; w < 8; ++w) t += red[w][lane][i];
       atomicAdd(db + c + i, t);
     }
   }
@@ -1294,8 +1313,11 @@ extern "C" int gwd_linear_wgrad(const void* dy, int64_t dy_rs, const void* x, in
     if (rc < 0) return rc;
     if (rc == 0) {
       if (db != nullptr) {
-        const dim3 grid(static_cast<unsigned>(gwd_ceil_div(N, 256)), static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(rows, 64), 2 * gwd_num_sms())));
-        gwd_colsum_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, rows, N, db);
+        int lpr = 1;
+        while (lpr < 32 && lpr * 8 < N) lpr <<= 1;
+        const dim3 grid(static_cast<unsigned>(gwd_ceil_div(N, 256)),
+                        static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(rows, 64 * (32 / lpr)), 2 * gwd_num_sms())));
+        gwd_colsum_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, rows, N, lpr, db);
         GWD_LAUNCHED();
       }
       return GWD_OK;

@@ -13,8 +13,11 @@ from helpers import golden, oracle, synth, synth_weights
 
 pytestmark = pytest.mark.gpu
 
-# mean / max relative error bounds vs the fp32 oracle (bf16 path, selections pinned)
-TOL = {"depth_mean": 3e-2, "depth_max": 0.2, "logits_max": 8e-2, "lines_max": 0.15, "seg_mean": 0.2}
+# mean / max relative error bounds vs the fp32 oracle (bf16 path, selections pinned).  Measured on the B200 at 2x224x320,
+# 1x480x640, 16x480x640 and 1x960x1280: depth mean 1.2-1.4 % / max 10-13 %, logits max 1.6-2.5 %, end points 2.6-4.6 %, seg mean
+# 7.7-8.2 % (logits around zero).  north_star's 1e-2 on the depth mean is NOT met: rounding the WEIGHTS alone to bf16 moves the
+# oracle's own depth by 1.34 % (tools/bf16_sensitivity.py), so the bound sits at 1.5 x that distance.
+TOL = {"depth_mean": 2e-2, "depth_max": 0.16, "logits_max": 4e-2, "lines_max": 8e-2, "seg_mean": 0.12}
 
 
 def _model():
