@@ -1,5 +1,6 @@
 // gwd_attn_tc.cu -- fused multi-head attention on the 5th-gen tensor cores (tcgen05 + TMEM + TMA) for the DETR
-// encoder / decoder attention of the line branch (head_dim 32, Lk <= 480: the whole key axis fits one TMEM pass).
+// encoder / decoder attention of the line branch (head_dim 32).  Two kernels: Lk <= 480 -- the whole key axis fits one TMEM
+// pass (below) --, longer key axes -- key tiles + online soft-max (gwd_attention_flash_tc_kernel, further down).
 //
 //   CTA = one (batch item, head, 128-query tile), 5 warps:
 //     warp 4 (one lane) : TMA loads of the Q tile, all K rows and all V rows of the (item, head); then
@@ -12,6 +13,7 @@
 // Replaces the bmm / masked_fill / softmax / bmm chain of src/models/multi_head_attention.py:317-372 (the q scaling of
 // :276 is folded into the projection weights; the head-averaged weights of :375-378 are dead and not produced).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 #include "gwd_common.cuh"
 
@@ -90,6 +92,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 32 columns without the wait (the caller issues tcgen05.wait::ld once per batch of loads)
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, "
+      "%19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // UMMA shared-memory descriptor: start>>4 | LBO>>4 @16 | SBO>>4 @32 | version 1 @46 | layout @61 (2=SW128, 4=SW64)
 __device__ __forceinline__ uint64_t make_desc(uint32_t addr, uint32_t sbo_bytes, uint32_t layout) {
   uint64_t d = 0;
@@ -187,22 +201,24 @@ gwd_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     fence_after();
     // full 16-key chunks without key padding take the check-free path: 1 FMNMX per score in the first pass and
     // FFMA + MUFU.EX2 + FADD in the second (the per-element validity tests made this 4-warp soft-max the critical path)
-    float mx = -INFINITY;
+    // (four independent partial maxima / sums: one serial chain over Lk keys costs ~4 clocks per key)
+    float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
     for (int c = 0; c < Lk_pad; c += 16) {
       uint32_t r[16];
       tmem_ld16(t_row + c, r);
       if (kp == nullptr && c + 16 <= p.Lk) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
+        for (int i = 0; i < 16; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           bool ok = (c + i < p.Lk) && !(kp && kp[c + i]);
-          if (ok) mx = fmaxf(mx, __uint_as_float(r[i]));
+          if (ok) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
         }
       }
     }
-    float sum = 0.f;
+    const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+    float sum4[4] = {0.f, 0.f, 0.f, 0.f};
     const float l2e = 1.4426950408889634f;
     const float mxs = mx * l2e;
     for (int c = 0; c < Lk_pad; c += 16) {
@@ -213,14 +229,14 @@ gwd_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           e[i] = ex2_fast(fmaf(__uint_as_float(r[i]), l2e, -mxs));
-          sum += e[i];
+          sum4[i & 3] += e[i];
         }
       } else {
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           bool ok = (c + i < p.Lk) && !(kp && kp[c + i]);
           e[i] = ok ? ex2_fast(fmaf(__uint_as_float(r[i]), l2e, -mxs)) : 0.f;
-          sum += e[i];
+          sum4[i & 3] += e[i];
         }
       }
       // 16 keys = two 16-byte units of the 64-key chunk (c / 64), row `row`, 128-byte swizzle
@@ -234,6 +250,7 @@ gwd_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
         *reinterpret_cast<uint4*>(chunk + (((u0 + h) ^ (row & 7)) << 4)) = w;
       }
     }
+    const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
     // make the generic-proxy writes of P visible to the tensor core (async proxy), then signal
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     fence_before();
@@ -262,6 +279,195 @@ gwd_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   if (warp == 4) {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Long key axes (Lk > 480: the DETR encoder at 960x1280 has L = 1 200 tokens): the same CTA organisation with the keys
+// walked in TILES of 128 and an ONLINE soft-max (running row max m and row sum l; flash-attention recurrence):
+//     per tile t:  S_t = Q K_t^T (tcgen05, TMEM)  ->  m' = max(m, rowmax S_t), alpha = 2^((m - m') log2 e)
+//                  P_t = 2^((S_t - m') log2 e) -> bf16 -> shared memory;  l = l alpha + rowsum P_t;  O = O alpha
+//                  PV_t = P_t V_t (tcgen05, a fresh 32-column TMEM accumulator)  ->  O += PV_t
+// O lives in REGISTERS (one query row = one thread = 32 fp32 values), so the rescale costs 32 FMULs per tile and TMEM never
+// has to be read-modified-written.  K_t / V_t are double-buffered: the TMA of tile t+1 is issued before the soft-max of tile
+// t.  Inside a CTA the steps of one tile are serial (MMA -> soft-max -> MMA); the kernel needs 72 KB of shared memory and 256
+// TMEM columns, so up to THREE CTAs share an SM and one CTA's soft-max overlaps another's MMAs.  With head dim 32 the kernel
+// is bound by the exponentials, not by the tensor pipe: a 128 x 128 tile needs 16 384 ex2 (MUFU: 16 per clock and SM = 1 024
+// clocks) for 2 MFLOP of MMA (256 clocks at the dense bf16 rate), i.e. the tensor pipe cannot exceed ~25 % with MUFU exponentials.
+// ------------------------------------------------------------------------------------------------------------------
+#ifndef GWD_FLASH_KT
+#define GWD_FLASH_KT 64
+#endif
+constexpr uint32_t kFlashTmem = GWD_FLASH_KT + 32 <= 128 ? 128u : 256u;
+constexpr int kPChunks = (GWD_FLASH_KT + 63) / 64;      // 64-key chunks of the P tile in shared memory
+constexpr int kKT = GWD_FLASH_KT;    // keys per tile: S (KT) + PV (32) TMEM columns.  Measured at B = 64, L = 1 200: 128 keys (2 CTAs per SM) 548 us,
+                                     // 96 keys (3 CTAs) 417 us, 64 keys (4 CTAs) 368 us: the soft-max latency chains want co-resident CTAs
+
+__global__ void __launch_bounds__(160, 4)
+gwd_attention_flash_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
+                              const __grid_constant__ CUtensorMap map_v, const __grid_constant__ TcAttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                        // [128][64 B]          SW64
+  uint8_t* sK = sQ + kQTile * 64;                            // 2 x [128][64 B]      SW64
+  uint8_t* sV = sK + 2 * kKT * 64;                           // 2 x [128][64 B]      SW64 (MN-major B operand)
+  uint8_t* sP = sV + 2 * kKT * 64;                           // [2][128][128 B]      SW128
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kPChunks * kQTile * 128);
+  uint64_t* ld_bar = bars;          // [2] K_t / V_t landed (Q rides on buffer 0's first phase)
+  uint64_t* s_bar = bars + 2;       // S_t complete
+  uint64_t* p_bar = bars + 3;       // P_t written by the 128 soft-max threads
+  uint64_t* o_bar = bars + 4;       // PV_t complete
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.z, head = blockIdx.y, q0 = blockIdx.x * kQTile;
+  const int T = (p.Lk + kKT - 1) / kKT;
+
+  if (threadIdx.x == 0) {
+    mbar_init(ld_bar, 1);
+    mbar_init(ld_bar + 1, 1);
+    mbar_init(s_bar, 1);
+    mbar_init(p_bar, 128);
+    mbar_init(o_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(kFlashTmem) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  fence_before();
+  __syncthreads();
+  fence_after();
+  const uint32_t tmem_s = *tmem_ptr;
+  const uint32_t tmem_pv = tmem_s + kKT;
+
+  if (warp == 4) {
+    if (elect_one()) {
+      const uint32_t qa = smem_u32(sQ), pa = smem_u32(sP);
+      mbar_expect_tx(ld_bar, kQTile * 64 + 2u * kKT * 64);
+      tma_load_2d(sQ, &map_q, ld_bar, head * kHD, item * p.Lq + q0);
+      tma_load_2d(sK, &map_k, ld_bar, head * kHD, item * p.Lk);
+      tma_load_2d(sV, &map_v, ld_bar, head * kHD, item * p.Lk);
+      for (int t = 0; t < T; ++t) {
+        const int b = t & 1;
+        if (t + 1 < T) {          // prefetch tile t+1 into the other buffer: PV_{t-1} (its last reader) must have completed
+          if (t >= 1) mbar_wait(o_bar, (t - 1) & 1);
+          mbar_expect_tx(ld_bar + (b ^ 1), 2u * kKT * 64);
+          tma_load_2d(sK + (b ^ 1) * kKT * 64, &map_k, ld_bar + (b ^ 1), head * kHD, item * p.Lk + (t + 1) * kKT);
+          tma_load_2d(sV + (b ^ 1) * kKT * 64, &map_v, ld_bar + (b ^ 1), head * kHD, item * p.Lk + (t + 1) * kKT);
+        }
+        mbar_wait(ld_bar + b, (t >> 1) & 1);
+        fence_after();
+        const uint32_t ka = smem_u32(sK + b * kKT * 64), va = smem_u32(sV + b * kKT * 64);
+        for (int k = 0; k < 2; ++k) umma(tmem_s, make_desc(qa + k * 32, 512, 4), make_desc(ka + k * 32, 512, 4), p.idesc_s0, k);
+        umma_commit(s_bar);
+        mbar_wait(p_bar, t & 1);
+        fence_after();
+        for (int k = 0; k < kKT / 16; ++k)
+          umma(tmem_pv, make_desc(pa + (k >> 2) * (kQTile * 128) + (k & 3) * 32, 1024, 2), make_desc(va + k * (16 * 64), 512, 4),
+               p.idesc_o, k);
+        umma_commit(o_bar);
+      }
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const uint32_t t_row = tmem_s + (static_cast<uint32_t>(warp * 32) << 16);
+    const uint8_t* kp = p.kpm ? p.kpm + static_cast<int64_t>(item) * p.Lk : nullptr;
+    const float l2e = 1.4426950408889634f;
+    float m = -INFINITY, l = 0.f, O[kHD];
+#pragma unroll
+    for (int i = 0; i < kHD; ++i) O[i] = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const int k0 = t * kKT;
+      const bool plain = kp == nullptr && k0 + kKT <= p.Lk;      // no masked key in this tile: check-free path
+      mbar_wait(s_bar, t & 1);
+      fence_after();
+      // (four independent partial maxima / sums: a serial chain over the tile's keys would cost ~4 clocks per key)
+      float mx4[4] = {m, m, m, m};
+      for (int c = 0; c < kKT; c += 32) {
+        uint32_t r[32];
+        tmem_ld32_nowait(t_row + c, r);
+        tmem_ld_wait();
+        if (plain) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kk = k0 + c + i;
+            if (kk < p.Lk && !(kp && kp[kk])) mx4[i & 3] = fmaxf(mx4[i & 3], __uint_as_float(r[i]));
+          }
+        }
+      }
+      const float mx = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+      const float mxs = mx == -INFINITY ? 0.f : mx * l2e;          // every key so far masked: keep the exponent finite
+      const float alpha = m == -INFINITY ? 0.f : ex2_fast(m * l2e - mxs);
+      float sum4[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int c = 0; c < kKT; c += 32) {
+        uint32_t r[32];
+        tmem_ld32_nowait(t_row + c, r);
+        tmem_ld_wait();
+        // 32 keys = four 16-byte units of the 64-key chunk (c / 64), row `row`, 128-byte swizzle
+        uint8_t* chunk = sP + static_cast<size_t>(c >> 6) * (kQTile * 128) + row * 128;
+        const int u0 = (c & 63) >> 3;
+        float e[32];
+        if (plain) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            e[i] = ex2_fast(fmaf(__uint_as_float(r[i]), l2e, -mxs));
+            sum4[i & 3] += e[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int kk = k0 + c + i;
+            const bool ok = kk < p.Lk && !(kp && kp[kk]);
+            e[i] = ok ? ex2_fast(fmaf(__uint_as_float(r[i]), l2e, -mxs)) : 0.f;
+            sum4[i & 3] += e[i];
+          }
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          uint4 w;
+          w.x = gwd_pack_bf16x2(e[8 * h + 0], e[8 * h + 1]); w.y = gwd_pack_bf16x2(e[8 * h + 2], e[8 * h + 3]);
+          w.z = gwd_pack_bf16x2(e[8 * h + 4], e[8 * h + 5]); w.w = gwd_pack_bf16x2(e[8 * h + 6], e[8 * h + 7]);
+          *reinterpret_cast<uint4*>(chunk + (((u0 + h) ^ (row & 7)) << 4)) = w;
+        }
+      }
+      const float sum = (sum4[0] + sum4[1]) + (sum4[2] + sum4[3]);
+      l = fmaf(l, alpha, sum);
+      m = mx;
+#pragma unroll
+      for (int i = 0; i < kHD; ++i) O[i] *= alpha;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      fence_before();
+      mbar_arrive(p_bar);
+      mbar_wait(o_bar, t & 1);
+      fence_after();
+      uint32_t pv[32];
+      tmem_ld32_nowait(t_row + kKT, pv);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < kHD; ++i) O[i] += __uint_as_float(pv[i]);
+      fence_before();             // the next tile's MMAs overwrite these TMEM columns: order the loads ahead of them
+    }
+    const int qi = q0 + row;
+    if (qi < p.Lq) {
+      const float inv = l > 0.f ? 1.f / l : 0.f;
+      bf16* orow = p.o + item * p.o_is + static_cast<int64_t>(qi) * p.o_rs + head * kHD;
+      uint4 w[4];
+      uint32_t* wp = reinterpret_cast<uint32_t*>(w);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) wp[i] = gwd_pack_bf16x2(O[2 * i] * inv, O[2 * i + 1] * inv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) reinterpret_cast<uint4*>(orow)[i] = w[i];
+    }
+  }
+  fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_s), "r"(kFlashTmem) : "memory");
   }
 }
 
@@ -303,7 +509,12 @@ uint32_t idesc_bf16(int n, bool b_mn_major) {
 
 // returns 1 when the problem is not eligible for the tensor-core path (caller falls back to the CUDA-core kernel)
 int gwd_attention_tc_try(const gwd_attn_desc* d, cudaStream_t stream) {
-  if (d->hd != kHD || d->bias || d->mask || d->Lk > kMaxLk || d->Lk < 16) return 1;
+  if (d->hd != kHD || d->bias || d->mask || d->Lk < 16) return 1;
+  // key tiles + online soft-max: always for long key axes; also for self-attention over a few hundred tokens, where its
+  // four co-resident CTAs per SM beat the one-CTA-per-SM single pass (encoder, B = 16, L = 300: 19.3 vs 28.9 us), but not
+  // for the decoder's 100 queries (one query tile per (image, head): 14.9 vs 12.7 us)
+  static const int flash_min = [] { const char* e = getenv("GWD_FLASH_MIN_LK"); return e ? atoi(e) : 0; }();
+  const bool flash = d->Lk > kMaxLk || (flash_min > 0 ? d->Lk >= flash_min : (d->Lq >= 256 && d->Lk >= 192));
   // tensors must be plain [items*L, row_stride] matrices (item stride = L * row stride) with 16-byte aligned rows
   if (d->q_item_stride != static_cast<int64_t>(d->Lq) * d->q_row_stride ||
       d->k_item_stride != static_cast<int64_t>(d->Lk) * d->k_row_stride ||
@@ -326,14 +537,28 @@ int gwd_attention_tc_try(const gwd_attn_desc* d, cudaStream_t stream) {
   // (pointers are already 16-byte aligned, so the maps can simply start at the slice)
   p.q_coff = p.k_coff = p.v_coff = 0;
   CUtensorMap mq, mk, mv;
-  const int kbox = 160 < p.Lk_pad ? 160 : p.Lk_pad;
-  if (p.Lk_pad % kbox) return 1;      // Lk_pad is 32..160, 320 or 480
+  const int kbox = flash ? kKT : (160 < p.Lk_pad ? 160 : p.Lk_pad);
+  if (!flash && p.Lk_pad % kbox) return 1;      // Lk_pad is 32..160, 320 or 480
   const int cols = d->heads * kHD;
   if (make_map(&mq, d->q, static_cast<int64_t>(d->items) * d->Lq, d->q_row_stride, cols, kQTile) ||
       make_map(&mk, d->k, static_cast<int64_t>(d->items) * d->Lk, d->k_row_stride, cols, kbox) ||
       make_map(&mv, d->v, static_cast<int64_t>(d->items) * d->Lk, d->v_row_stride, cols, kbox)) {
     gwd_set_error("gwd_attention: cuTensorMapEncodeTiled failed");
     return GWD_ERR_CUDA;
+  }
+  if (flash) {
+    p.idesc_s0 = idesc_bf16(kKT, false);
+    p.idesc_o = idesc_bf16(kHD, true);
+    const size_t smem_f = 1024 + kQTile * 64 + 4 * static_cast<size_t>(kKT) * 64 + kPChunks * kQTile * 128 + 64;
+    static bool configured_f = false;
+    if (!configured_f) {
+      GWD_CUDA(cudaFuncSetAttribute(gwd_attention_flash_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem_f)));
+      configured_f = true;
+    }
+    dim3 gridf(static_cast<unsigned>(gwd_ceil_div(d->Lq, kQTile)), d->heads, d->items);
+    gwd_attention_flash_tc_kernel<<<gridf, 160, smem_f, stream>>>(mq, mk, mv, p);
+    GWD_LAUNCHED();
+    return GWD_OK;
   }
   if (p.Lk_pad <= 256) { p.n0 = p.Lk_pad; p.n1 = 0; }
   else { p.n0 = p.Lk_pad / 2; p.n1 = p.Lk_pad - p.n0; if (p.n0 % 16 || p.n1 % 16) return 1; }

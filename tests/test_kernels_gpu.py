@@ -35,7 +35,10 @@ def close(got, ref, tol, what=""):
 
 # ------------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("B,Lq,Lk,heads,hd,pad", [(2, 300, 300, 8, 32, False), (3, 100, 300, 8, 32, True), (2, 100, 100, 8, 32, False),
-                                                 (1, 37, 53, 4, 16, True)])
+                                                 (1, 37, 53, 4, 16, True),
+                                                 # long key axes (960x1280: L = 1 200): key tiles + online soft-max on tcgen05
+                                                 (2, 1200, 1200, 8, 32, False), (2, 100, 1200, 8, 32, True), (3, 700, 700, 8, 32, True),
+                                                 (1, 513, 481, 8, 32, False)])
 def test_attention_detr(B, Lq, Lk, heads, hd, pad):
     ops = _ops()
     g = _g(Lq + Lk + hd)
