@@ -44,6 +44,7 @@ class AttnDesc(ctypes.Structure):
         ("v_item_stride", c_i64), ("v_row_stride", c_i64), ("o_item_stride", c_i64), ("o_row_stride", c_i64),
         ("bias", c_void_p), ("mask", c_void_p), ("mask_windows", c_int), ("key_padding", c_void_p),
         ("scale", c_float),
+        ("dropout_seed", c_void_p), ("dropout_site", ctypes.c_uint32), ("dropout_p", c_float),
     ]
 
 
@@ -59,6 +60,7 @@ class AttnBwdDesc(ctypes.Structure):
         ("dv_item_stride", c_i64), ("dv_row_stride", c_i64),
         ("scale", c_float), ("o", c_void_p), ("o_item_stride", c_i64), ("o_row_stride", c_i64),
         ("dq_mul", c_float), ("dk_mul", c_float),
+        ("dropout_seed", c_void_p), ("dropout_site", ctypes.c_uint32), ("dropout_p", c_float),
     ]
 
 
@@ -130,6 +132,7 @@ SIGNATURES = {
     "gwd_im2col3x3_s2": (c_int, [P, P, I, I, I, I, P]),
     "gwd_col2im3x3_s2": (c_int, [P, P, P, I, I, I, I, P]),
     "gwd_select_lines": (c_int, [P, I, P, I, I, I, I, I, P, P, P]),
+    "gwd_dropout": (c_int, [P, P, P, L, P, ctypes.c_uint32, F_, P]),
 }
 
 _lib = None

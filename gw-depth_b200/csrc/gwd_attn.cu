@@ -651,6 +651,8 @@ extern "C" int gwd_attention(const gwd_attn_desc* d, void* stream_) {
       if (rc <= 0) return rc;   // 0 = launched, < 0 = error, 1 = not eligible
     }
   }
+  GWD_CHECK_ARG(!(d->dropout_seed != nullptr && d->dropout_p > 0.f),
+                "gwd_attention: dropout is built on the tcgen05 path only (head dim 32, scale 1, no bias / window mask)");
   {  // biased (shifted-)window attention, N <= 64 tokens: persistent-CTA kernel with the bias table in shared memory
     static const bool win_enabled = []() { const char* e = getenv("GWD_ATTN_WINDOW"); return !(e && e[0] == '0'); }();
     if (win_enabled) {

@@ -34,6 +34,9 @@ struct TcAttnParams {
   uint32_t idesc_s0, idesc_s1, idesc_o;   // S MMA (two N halves), O MMA
   int n0, n1;                             // N of the two S MMAs (n1 may be 0)
   int q_coff, k_coff, v_coff;             // channel offset of head 0 inside the q / k / v buffers
+  const uint32_t* drop_seed;              // train-mode dropout of the probabilities (nullptr: none)
+  uint32_t drop_site, drop_thr;
+  float drop_scale;                       // 1 / (1 - p)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -221,6 +224,7 @@ gwd_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
     float sum4[4] = {0.f, 0.f, 0.f, 0.f};
     const float l2e = 1.4426950408889634f;
     const float mxs = mx * l2e;
+    const uint32_t drop_key = p.drop_seed ? gwd_drop_key(*p.drop_seed, p.drop_site, static_cast<uint32_t>(item * p.heads + head)) : 0u;
     for (int c = 0; c < Lk_pad; c += 16) {
       uint32_t r[16];
       tmem_ld16(t_row + c, r);
@@ -238,6 +242,11 @@ gwd_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
           e[i] = ok ? ex2_fast(fmaf(__uint_as_float(r[i]), l2e, -mxs)) : 0.f;
           sum4[i & 3] += e[i];
         }
+      }
+      if (p.drop_seed) {        // the row sum keeps every key; only the P that meets V is dropped (and re-scaled)
+        const uint32_t base = static_cast<uint32_t>(q0 + row) * static_cast<uint32_t>(p.Lk) + c;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) e[i] = gwd_drop_keep(drop_key, base + i, p.drop_thr) ? e[i] * p.drop_scale : 0.f;
       }
       // 16 keys = two 16-byte units of the 64-key chunk (c / 64), row `row`, 128-byte swizzle
       uint8_t* chunk = sP + static_cast<size_t>(c >> 6) * (kQTile * 128) + row * 128;
@@ -374,6 +383,7 @@ gwd_attention_flash_tc_kernel(const __grid_constant__ CUtensorMap map_q, const _
     const uint32_t t_row = tmem_s + (static_cast<uint32_t>(warp * 32) << 16);
     const uint8_t* kp = p.kpm ? p.kpm + static_cast<int64_t>(item) * p.Lk : nullptr;
     const float l2e = 1.4426950408889634f;
+    const uint32_t drop_key = p.drop_seed ? gwd_drop_key(*p.drop_seed, p.drop_site, static_cast<uint32_t>(item * p.heads + head)) : 0u;
     float m = -INFINITY, l = 0.f, O[kHD];
 #pragma unroll
     for (int i = 0; i < kHD; ++i) O[i] = 0.f;
@@ -425,6 +435,11 @@ gwd_attention_flash_tc_kernel(const __grid_constant__ CUtensorMap map_q, const _
             e[i] = ok ? ex2_fast(fmaf(__uint_as_float(r[i]), l2e, -mxs)) : 0.f;
             sum4[i & 3] += e[i];
           }
+        }
+        if (p.drop_seed) {
+          const uint32_t base = static_cast<uint32_t>(q0 + row) * static_cast<uint32_t>(p.Lk) + k0 + c;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) e[i] = gwd_drop_keep(drop_key, base + i, p.drop_thr) ? e[i] * p.drop_scale : 0.f;
         }
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
@@ -533,6 +548,12 @@ int gwd_attention_tc_try(const gwd_attn_desc* d, cudaStream_t stream) {
   p.o = static_cast<bf16*>(d->o); p.o_is = d->o_item_stride; p.o_rs = d->o_row_stride;
   p.kpm = d->key_padding; p.scale = d->scale;
   if (d->scale != 1.0f) return 1;    // the model folds the q scaling into the projection weights
+  if (d->dropout_seed != nullptr && d->dropout_p > 0.f) {
+    if (static_cast<int64_t>(d->Lq) * d->Lk >= (1ll << 32)) return 1;
+    p.drop_seed = d->dropout_seed; p.drop_site = d->dropout_site;
+    p.drop_thr = static_cast<uint32_t>(static_cast<double>(d->dropout_p) * 4294967296.0);
+    p.drop_scale = 1.f / (1.f - d->dropout_p);
+  }
   // the channel slice may start anywhere inside the row: express it as a column offset of an aligned base
   // (pointers are already 16-byte aligned, so the maps can simply start at the slice)
   p.q_coff = p.k_coff = p.v_coff = 0;

@@ -92,6 +92,25 @@ __device__ __forceinline__ float2 gwd_unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(t);
 }
 
+// ----------------------------------------------------------------------------------------------
+// dropout masks (train-mode nn.Dropout of the DETR layers, src/models/transformer.py:149-162,212-233 and the attention-
+// probability dropout of src/models/multi_head_attention.py:368).  The mask of an element is a pure function of (step seed in
+// device memory, site id, element index): the forward and the backward kernels regenerate it instead of storing it, and the
+// seed lives in device memory so that a replayed CUDA graph draws new masks every step.  32-bit integer mixer (two
+// multiply-xorshift rounds, full avalanche); keep probability = 1 - p to 2^-32.
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gwd_mix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x7feb352dU; x ^= x >> 15; x *= 0x846ca68bU; x ^= x >> 16;
+  return x;
+}
+// stream key of one dropout site (and, for attention, one (image, head)): mixed once per thread, then one mix per element
+__device__ __forceinline__ uint32_t gwd_drop_key(uint32_t seed, uint32_t site, uint32_t sub) {
+  return gwd_mix32(seed ^ gwd_mix32(site * 0x9E3779B9U + sub * 0x85EBCA6BU + 0x6A09E667U));
+}
+__device__ __forceinline__ bool gwd_drop_keep(uint32_t key, uint32_t idx, uint32_t threshold) {
+  return gwd_mix32(idx ^ key) >= threshold;          // threshold = p * 2^32
+}
+
 __device__ __forceinline__ float gwd_warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -321,6 +321,10 @@ struct AttnBwdParams {
   int Lq, Lk, Lq_pad, Lk_pad;
   int64_t q_is, q_rs, k_is, k_rs, v_is, v_rs, do_is, do_rs, dq_is, dq_rs, dk_is, dk_rs, dv_is, dv_rs, o_is, o_rs;
   float scale, dq_mul, dk_mul;
+  const uint32_t* drop_seed;      // dropout of the probabilities (nullptr: none); the forward's mask is regenerated
+  uint32_t drop_site, drop_thr;
+  float drop_scale;
+  int heads;
 };
 
 __device__ __forceinline__ float reduce_scatter32(float (&acc)[32], int lane) {
@@ -589,6 +593,10 @@ __global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParam
   __syncthreads();
   const uint32_t bQ = smem_u32(sQ), bK = smem_u32(sK), bV = smem_u32(sV), bO = smem_u32(sO);
   const float sc = p.scale * kLog2eT;
+  // dropout: O = (P o M / (1 - p)) V, so dV sees the dropped P, dP = M / (1 - p) o (dO V^T), and D = rowsum(dO o O) still equals
+  // rowsum(P o dP); the mask of (query, key) is regenerated from the forward's (seed, site, image, head)
+  const bool drop = p.drop_seed != nullptr;
+  const uint32_t drop_key = drop ? gwd_drop_key(*p.drop_seed, p.drop_site, static_cast<uint32_t>(item * p.heads + head)) : 0u;
 
   // ---------------- pass A
   for (int m0 = warp * 16; m0 < p.Lq; m0 += 8 * 16) {
@@ -646,7 +654,12 @@ __global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParam
         for (int e = 0; e < 4; ++e) {
           const int col = c0 + nt * 8 + 2 * tq + (e & 1);
           const float pr = col < p.Lk ? ex2f(s[nt][e] * sc - lse[e >> 1]) : 0.f;
-          s[nt][e] = pr * (dp[nt][e] - D[e >> 1]);           // dS
+          float dpe = dp[nt][e];
+          if (drop) {
+            const uint32_t row = static_cast<uint32_t>(m0 + g + 8 * (e >> 1));
+            dpe = gwd_drop_keep(drop_key, row * static_cast<uint32_t>(p.Lk) + col, p.drop_thr) ? dpe * p.drop_scale : 0.f;
+          }
+          s[nt][e] = pr * (dpe - D[e >> 1]);           // dS
         }
       fy(dq, s, bK, c0, lane);
     }
@@ -675,8 +688,13 @@ __global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParam
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float pr = ex2f(st[nt][e] * sc - ((e & 1) ? ls.y : ls.x));        // lse = +inf beyond Lq -> 0
-          st[nt][e] = pr;                                                         // P^T
-          dpt[nt][e] = pr * (dpt[nt][e] - ((e & 1) ? dd.y : dd.x));               // dS^T
+          float mk = 1.f;
+          if (drop) {
+            const uint32_t qrow = static_cast<uint32_t>(c0 + nt * 8 + 2 * tq + (e & 1)), key = static_cast<uint32_t>(n0 + g + 8 * (e >> 1));
+            mk = gwd_drop_keep(drop_key, qrow * static_cast<uint32_t>(p.Lk) + key, p.drop_thr) ? p.drop_scale : 0.f;
+          }
+          st[nt][e] = pr * mk;                                                    // (dropped) P^T: what met V in the forward
+          dpt[nt][e] = pr * (dpt[nt][e] * mk - ((e & 1) ? dd.y : dd.x));          // dS^T
         }
       }
       fy(dv, st, bO, c0, lane);
@@ -1190,6 +1208,13 @@ extern "C" int gwd_attention_bwd(const gwd_attn_bwd_desc* d, void* stream_) {
   p.scale = d->scale;
   p.dq_mul = d->dq_mul != 0.f ? d->dq_mul : d->scale;
   p.dk_mul = d->dk_mul != 0.f ? d->dk_mul : d->scale;
+  p.drop_seed = nullptr; p.drop_site = 0; p.drop_thr = 0; p.drop_scale = 1.f; p.heads = d->heads;
+  if (d->dropout_seed != nullptr && d->dropout_p > 0.f) {
+    GWD_CHECK_ARG(d->o != nullptr, "gwd_attention_bwd: dropout needs the forward output `o` (tensor-core kernel)");
+    p.drop_seed = d->dropout_seed; p.drop_site = d->dropout_site;
+    p.drop_thr = static_cast<uint32_t>(static_cast<double>(d->dropout_p) * 4294967296.0);
+    p.drop_scale = 1.f / (1.f - d->dropout_p);
+  }
   dim3 grid(d->heads, d->items);
   static const bool mma_enabled = []() { const char* e = getenv("GWD_ATTN_BWD_MMA"); return !(e && e[0] == '0'); }();
   if (d->o != nullptr && mma_enabled) {

@@ -348,6 +348,31 @@ __global__ void gwd_fold_mirror_kernel(const float* __restrict__ p, const float*
     mirror[i] = __float2bfloat16(p[i] * scale[i]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// element-wise dropout of a [rows, C] bf16 matrix: out = res (optional) + keep(row, col) ? x / (1 - p) : 0.  The same launch
+// with the same (seed, site) is the BACKWARD of itself (the mask is regenerated).  8 channels per thread.
+// ------------------------------------------------------------------------------------------------
+__global__ void gwd_dropout_kernel(const uint4* __restrict__ x, const uint4* __restrict__ res, uint4* __restrict__ out, int64_t n8,
+                                   const uint32_t* __restrict__ seed, uint32_t site, uint32_t threshold, float inv_keep) {
+  const uint32_t key = gwd_drop_key(*seed, site, 0u);
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const uint4 u = x[i];
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t r[4] = {0u, 0u, 0u, 0u};
+    if (res) { const uint4 q = res[i]; r[0] = q.x; r[1] = q.y; r[2] = q.z; r[3] = q.w; }
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 v = gwd_unpack_bf16x2(w[j]), a = gwd_unpack_bf16x2(r[j]);
+      const uint32_t e = static_cast<uint32_t>(i) * 8u + 2u * j;
+      const float lo = gwd_drop_keep(key, e, threshold) ? v.x * inv_keep : 0.f;
+      const float hi = gwd_drop_keep(key, e + 1u, threshold) ? v.y * inv_keep : 0.f;
+      o[j] = gwd_pack_bf16x2(a.x + lo, a.y + hi);
+    }
+    out[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 unsigned grid_1d(int64_t n, int block) {
   int64_t g = gwd_ceil_div(n, block);
   const int64_t cap = static_cast<int64_t>(gwd_num_sms()) * 16;
@@ -483,6 +508,18 @@ extern "C" int gwd_fold_mirror(const float* p, const float* scale, void* mirror,
   GWD_STREAM;
   GWD_CHECK_ARG(p && scale && mirror && n > 0, "gwd_fold_mirror: bad argument");
   gwd_fold_mirror_kernel<<<grid_1d(n, 256), 256, 0, stream>>>(p, scale, static_cast<bf16*>(mirror), n);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_dropout(const void* x, const void* res, void* out, int64_t n, const uint32_t* seed, uint32_t site, float p,
+                           void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(x && out && seed && n > 0 && n % 8 == 0 && n < (1ll << 32), "gwd_dropout: null pointer / n must be a multiple of 8 below 2^32");
+  GWD_CHECK_ARG(p >= 0.f && p < 1.f, "gwd_dropout: p must be in [0, 1)");
+  const uint32_t threshold = static_cast<uint32_t>(static_cast<double>(p) * 4294967296.0);
+  gwd_dropout_kernel<<<grid_1d(n / 8, 256), 256, 0, stream>>>(static_cast<const uint4*>(x), static_cast<const uint4*>(res),
+                                                              static_cast<uint4*>(out), n / 8, seed, site, threshold, 1.f / (1.f - p));
   GWD_LAUNCHED();
   return GWD_OK;
 }

@@ -121,6 +121,7 @@ class Engine:
         self.sd = sd
         self._tables = {}
         self._graphs = {}
+        self.max_graphs = 8
         self._side, self._side2 = torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)
         self._side3 = torch.cuda.Stream(device=self.dev)
         self._pack_backbone()
@@ -657,28 +658,36 @@ class Engine:
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole forward
     @torch.no_grad()
-    def forward_graphed(self, images):
-        """The forward has no host synchronisation and no data-dependent control flow, so the ~600 launches of a step
+    def forward_graphed(self, images, mask=None):
+        """The forward has no host synchronisation and no data-dependent control flow, so the ~480 launches of a step
         are captured once per input shape and replayed as one CUDA graph (the reference cannot: 36 `torch.equal` syncs,
-        `int()` reads in CertainSample, ...).  Returns the graph's static output tensors: consume (or clone) them before
-        the next call with the same shape."""
-        key = tuple(images.shape)
-        entry = self._graphs.get(key)
+        `int()` reads in CertainSample, ...).  A padded batch is captured with its padding mask as a second STATIC input (the
+        per-image position codes and key-padding masks are computed from it inside the graph).  Returns the graph's static
+        output tensors: consume (or clone) them before the next call with the same shape.  At most `max_graphs` shapes are
+        kept (least recently used first out): evaluation over many image sizes would otherwise hold one memory pool per shape."""
+        key = (tuple(images.shape), mask is not None)
+        entry = self._graphs.pop(key, None)
         if entry is None:
+            while len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
             static_in = torch.empty_like(images)
             static_in.copy_(images)
+            static_mask = mask.clone() if mask is not None else None
             side = torch.cuda.Stream(device=self.dev)
             side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):          # warm-up: cuDNN autotuning, lazy kernel attributes, cached tables
+            with torch.cuda.stream(side):          # warm-up: lazy kernel attributes, cached tables
                 for _ in range(2):
-                    self.forward(static_in)
+                    self.forward(static_in, mask=static_mask)
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
-                static_out = self.forward(static_in)
-            entry = self._graphs[key] = (graph, static_in, static_out)
-        graph, static_in, static_out = entry
+                static_out = self.forward(static_in, mask=static_mask)
+            entry = (graph, static_in, static_out, static_mask)
+        self._graphs[key] = entry                  # (re-)inserted last = most recently used
+        graph, static_in, static_out, static_mask = entry
         static_in.copy_(images, non_blocking=True)
+        if static_mask is not None:
+            static_mask.copy_(mask, non_blocking=True)
         graph.replay()
         return static_out
 

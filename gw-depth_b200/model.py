@@ -104,6 +104,14 @@ def _init_parameters(module):
             b.fill_(1.0)
 
 
+def _clone_outputs(out):
+    if isinstance(out, dict):
+        return {k: _clone_outputs(v) for k, v in out.items()}
+    if isinstance(out, (list, tuple)):
+        return type(out)(_clone_outputs(v) for v in out)
+    return out.clone() if isinstance(out, torch.Tensor) else out
+
+
 class _TrainStep(torch.autograd.Function):
     """autograd edge between the reference's training loop and train_model.Trainer: forward runs the engine's forward with
     the activations kept, backward takes the cotangents of every output the criteria touched, runs the engine's backward and
@@ -178,7 +186,7 @@ class GlassRGBD(_Node):
 
     # the kernel plan caches re-laid-out weights; rebuild it whenever a parameter changed or moved
     def _current_key(self):
-        vers = tuple(t._version for t in self.state_dict(keep_vars=True).values())
+        vers = tuple(t._version for t in self.parameters()) + tuple(t._version for t in self.buffers())
         dev = next(self.parameters()).device
         return (vers, str(dev))
 
@@ -193,7 +201,7 @@ class GlassRGBD(_Node):
             self._plan_key = key
         return self._plan
 
-    def forward(self, samples, reflc_points=None, reflc_mat=None, img_name=None, _pinned=None, _trace=None):
+    def forward(self, samples, reflc_points=None, reflc_mat=None, img_name=None, _pinned=None, _trace=None, _static=False):
         if isinstance(samples, torch.Tensor) and samples.dim() == 4:
             images, mask = samples, None      # one equal-size batch: no padding mask to build (or to synchronise on)
         else:
@@ -209,12 +217,19 @@ class GlassRGBD(_Node):
             padded = bool(mask.any())                  # a hand-made NestedTensor: one host read of the mask
         with torch.cuda.device(images.device):
             x = images.float().contiguous()
-            if padded:      # ragged batch: per-image position codes + key-padding masks, launched kernel by kernel
-                return plan.forward(x, pinned=_pinned, trace=_trace, mask=mask.to(x.device))
+            m = mask.to(x.device) if padded else None  # ragged batch: per-image position codes + key-padding masks
             if self.use_cuda_graph and _pinned is None and _trace is None:
-                return plan.forward_graphed(x)
-            return plan.forward(x, pinned=_pinned, trace=_trace)
+                out = plan.forward_graphed(x, mask=m)
+                # the graph's static outputs are overwritten by the next call with the same shape: hand out copies (59 MB at
+                # 16 x 480 x 640) unless the caller asked for the static tensors (infer_stream copies them itself)
+                return out if _static else _clone_outputs(out)
+            return plan.forward(x, pinned=_pinned, trace=_trace, mask=m)
 
+    def invalidate_plan(self):
+        """drop the cached kernel plan (re-laid-out weights, CUDA graphs): call after writing parameters through raw pointers
+        (in-place writes through torch bump the version counters the cache is keyed on; kernels do not)"""
+        self._plan = None
+        self._plan_key = None
 
     # ------------------------------------------------------------------ training (src/engine_glassrgbd.py:45-166)
     def trainer(self, **optim):
@@ -261,7 +276,7 @@ class GlassRGBD(_Node):
                     if n in sd:
                         p.copy_(sd[n])
             self.__dict__["_trainer_versions"] = self._param_versions()
-            self._plan = None
+            self.invalidate_plan()
 
     def _forward_train(self, samples, images, mask, pinned):
         padded = getattr(samples, "padded", None)
@@ -338,7 +353,7 @@ class GlassRGBD(_Node):
                     x_dev[b] = torch.empty(B_, 3, H_, W_, dtype=torch.float32, device=dev)
                 ops.images_to_batch(u_dev[b], out=x_dev[b], want_mask=False, table=u_tab[b])
                 u_tab[b] = ops.images_to_batch.last_table
-            out = pick(self.forward(x_dev[b]))
+            out = pick(self.forward(x_dev[b], _static=True))
             ev_used[b].record(comp)
             if out_dev[b] is None or set(out_dev[b]) != set(out) or any(out_dev[b][k].shape != v.shape for k, v in out.items()):
                 out_dev[b] = {k: torch.empty_like(v) for k, v in out.items()}

@@ -193,7 +193,7 @@ def _L():
 
 
 def attention(q, k, v, o, *, items, heads, Lq, Lk, hd, q_strides, k_strides, v_strides, o_strides,
-              bias=None, mask=None, key_padding=None, scale=1.0):
+              bias=None, mask=None, key_padding=None, scale=1.0, dropout=None):
     """q/k/v/o: bf16 tensors (possibly channel slices via .data_ptr() of a narrowed view); *_strides = (item, row)
     in elements; head h is at +h*hd."""
     d = capi.AttnDesc()
@@ -214,6 +214,8 @@ def attention(q, k, v, o, *, items, heads, Lq, Lk, hd, q_strides, k_strides, v_s
         assert key_padding.dtype == torch.uint8 and key_padding.is_contiguous()
         d.key_padding = key_padding.data_ptr()
     d.scale = scale
+    if dropout is not None:     # (seed tensor uint32/int32 [1] on the device, site id, p)
+        d.dropout_seed, d.dropout_site, d.dropout_p = dropout[0].data_ptr(), int(dropout[1]), float(dropout[2])
     capi.check(_L().gwd_attention(ctypes.byref(d), _stream()), "gwd_attention")
     return o
 
@@ -716,7 +718,7 @@ def unpack_conv3x3_grad(dw, n, c):
 
 
 def attention_bwd(q, k, v, d_o, dq, dk, dv, *, items, heads, Lq, Lk, hd, q_strides, k_strides, v_strides, do_strides,
-                  dq_strides, dk_strides, dv_strides, scale=1.0, o=None, o_strides=None, dq_mul=0.0, dk_mul=0.0):
+                  dq_strides, dk_strides, dv_strides, scale=1.0, o=None, o_strides=None, dq_mul=0.0, dk_mul=0.0, dropout=None):
     """o: the forward output (bf16) -> tensor-core kernel; None -> CUDA-core kernel that recomputes D = rowsum(P dP)"""
     d = capi.AttnBwdDesc()
     d.q, d.k, d.v, d.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), d_o.data_ptr()
@@ -733,6 +735,8 @@ def attention_bwd(q, k, v, d_o, dq, dk, dv, *, items, heads, Lq, Lk, hd, q_strid
     if o is not None:
         d.o = o.data_ptr()
         d.o_item_stride, d.o_row_stride = o_strides or do_strides
+    if dropout is not None:
+        d.dropout_seed, d.dropout_site, d.dropout_p = dropout[0].data_ptr(), int(dropout[1]), float(dropout[2])
     capi.check(_L().gwd_attention_bwd(ctypes.byref(d), _stream()), "gwd_attention_bwd")
 
 
@@ -893,3 +897,13 @@ def select_lines(logits, lines, num_ref, points_per_line):
     capi.check(_L().gwd_select_lines(_ptr(logits), C, _ptr(lines), lines.shape[-1], B, Q, num_ref, points_per_line, _ptr(ref_xy),
                                      _ptr(ids), _stream()), "gwd_select_lines")
     return ref_xy, ids
+
+
+def dropout(x, seed, site, p, res=None, out=None):
+    """bf16 element-wise dropout: out = res + (keep ? x / (1 - p) : 0); seed: int32 [1] device tensor, site: call-site id.
+    Applied to a gradient with the same (seed, site) it is its own backward (the mask is regenerated, never stored)."""
+    assert x.dtype == torch.bfloat16 and x.is_contiguous() and x.numel() % 8 == 0
+    assert res is None or (res.dtype == torch.bfloat16 and res.is_contiguous() and res.numel() == x.numel())
+    out = torch.empty_like(x) if out is None else out
+    capi.check(_L().gwd_dropout(_ptr(x), _ptr(res), _ptr(out), x.numel(), _ptr(seed), int(site), float(p), _stream()), "gwd_dropout")
+    return out

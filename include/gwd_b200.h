@@ -125,6 +125,13 @@ typedef struct gwd_attn_desc {
   int32_t mask_windows;
   const uint8_t* key_padding;
   float scale;
+  /* train-mode dropout of the attention probabilities (src/models/multi_head_attention.py:368): P <- keep ? P / (1 - p) : 0
+   * ahead of P V.  dropout_seed: DEVICE uint32 (NULL or dropout_p == 0: no dropout), dropout_site: id of the call site; the mask
+   * of element (item, head, query, key) is a pure function of (*dropout_seed, dropout_site, indices) and is regenerated by
+   * gwd_attention_bwd.  Supported on the tcgen05 path (head dim 32, no bias / window mask). */
+  const uint32_t* dropout_seed;
+  uint32_t dropout_site;
+  float dropout_p;
 } gwd_attn_desc;
 int gwd_attention(const gwd_attn_desc* d, void* stream);
 
@@ -301,6 +308,9 @@ typedef struct gwd_attn_bwd_desc {
   int64_t o_item_stride, o_row_stride;
   float dq_mul, dk_mul;   /* dQ = dq_mul * dS K, dK = dk_mul * dS^T Q; 0 = `scale`.  For projections that were stored pre-scaled
                              (q' = a q, k' = b k, a b = softmax scale): scale = 1, dq_mul = a, dk_mul = b */
+  const uint32_t* dropout_seed;   /* as in gwd_attn_desc: the forward's mask is regenerated (needs `o`, the forward output) */
+  uint32_t dropout_site;
+  float dropout_p;
 } gwd_attn_bwd_desc;
 int gwd_attention_bwd(const gwd_attn_bwd_desc* d, void* stream);
 /* SetCriterion forward + backward for all S decoder stages in one launch (src/models/glassrgbd.py:154-175,231-244,308-358):
@@ -447,6 +457,10 @@ int gwd_col2im3x3_s2(const void* dcol, const void* add, void* dx, int32_t B, int
  * points_per_line (x, y) pairs of every selected line mapped to [-1, 1]. */
 int gwd_select_lines(const float* logits, int32_t num_classes, const float* lines, int32_t line_dim, int32_t B, int32_t Q,
                      int32_t num_ref, int32_t points_per_line, float* ref_xy, int64_t* ids, void* stream);
+/* element-wise train-mode dropout of a bf16 [n] buffer (n % 8 == 0): out = res (optional) + (keep ? x / (1 - p) : 0); seed: DEVICE
+ * uint32, site: id of the call site.  The same call on a gradient is the backward (the mask is regenerated).  Replaces
+ * nn.Dropout of src/models/transformer.py:149-162,212-233. */
+int gwd_dropout(const void* x, const void* res, void* out, int64_t n, const uint32_t* seed, uint32_t site, float p, void* stream);
 
 #ifdef __cplusplus
 }

@@ -106,6 +106,29 @@ def test_ragged_batch_with_padding_mask():
     assert d_plain > 3 * d_masked, (d_plain, d_masked)
 
 
+def test_padded_batch_graph_replay_and_output_ownership():
+    """a padded batch replays a CUDA graph too (the padding mask is a static input of the graph) and equals the kernel-by-kernel
+    launch; the public forward hands out tensors the next call does not overwrite"""
+    net, _, M = model()
+    images, _, _, _ = synth.synth_batch(2, 224, 320, seed=7)
+    a, b = images[0], images[1][:, :192, :288].contiguous()
+    nt = M.nested_tensor_from_tensor_list([a.cuda(), b.cuda()])
+    nt2 = M.nested_tensor_from_tensor_list([images[1].cuda(), images[0][:, :160, :320].contiguous().cuda()])
+    with torch.no_grad():
+        eager = net(nt, _trace={})                 # a trace request takes the un-graphed path
+        g1 = net(nt)
+        keep = g1["pred_depth"][3].clone()
+        g2 = net(nt2)                              # same shape, other images AND another mask: replays the same graph
+        e2 = net(nt2, _trace={})
+    assert torch.equal(g1["pred_depth"][3], keep), "the second call overwrote the first call's outputs"
+    for k in ("pred_logits", "pred_lines", "pred_seg"):
+        assert torch.allclose(g1[k].float(), eager[k].float(), rtol=2e-3, atol=2e-4), k
+        assert torch.allclose(g2[k].float(), e2[k].float(), rtol=2e-3, atol=2e-4), k
+    assert torch.allclose(g1["pred_depth"][3], eager["pred_depth"][3], rtol=2e-3, atol=2e-4)
+    assert torch.allclose(g2["pred_depth"][3], e2["pred_depth"][3], rtol=2e-3, atol=2e-4)
+    assert not torch.allclose(g1["pred_depth"][3], g2["pred_depth"][3], rtol=1e-2, atol=1e-2)
+
+
 def test_dense_center_configuration():
     """--with_dense_center (BASELINE configs[3], the richest flag set that runs in the reference): three points
     per selected line -> 60 reference tokens in the line-window attention instead of 40"""

@@ -1,6 +1,6 @@
 """debug helper (not a test): per-parameter gradient error of the line branch vs oracle autograd"""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
 import torch
 from helpers import oracle, synth_weights
 import test_train_gpu as T
