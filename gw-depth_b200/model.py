@@ -246,9 +246,6 @@ class GlassRGBD(_Node):
             dev = next(self.parameters()).device
             if dev.type != "cuda":
                 raise RuntimeError("GlassRGBD trains on sm_100a CUDA kernels only; move the model to a CUDA device")
-            if float(getattr(self.args, "dropout", 0.0)) != 0.0:
-                raise NotImplementedError("train-mode dropout in the DETR layers is not built: construct the model with "
-                                          "--dropout 0.0 (the gradient-parity configuration, SURVEY.md 8c)")
             a = self.args
             kw = dict(lr=getattr(a, "lr", 1e-4), lr_backbone=getattr(a, "lr_backbone", 1e-5), weight_decay=getattr(a, "weight_decay", 1e-4),
                       max_norm=getattr(a, "clip_max_norm", 0.1),
@@ -256,7 +253,7 @@ class GlassRGBD(_Node):
                       seg_loss_weight=float(getattr(a, "seg_loss_weight", 2.0)))
             kw.update(optim)
             cfg = dict(self.cfg, log_depth_error=bool(getattr(a, "log_depth_error", False)),
-                       variance_focus=float(getattr(a, "variance_focus", 0.85)))
+                       variance_focus=float(getattr(a, "variance_focus", 0.85)), dropout=float(getattr(a, "dropout", 0.0) or 0.0))
             self.__dict__["_trainer"] = Trainer(self.state_dict(), cfg, device=dev, **kw)
             self.__dict__["_trainer_versions"] = self._param_versions()
             live = set(self.__dict__["_trainer"].state_dict())

@@ -4,7 +4,8 @@ criterion (6 Hungarian matchings), the backward through hand-written kernels and
 Reference: the modules of src/models/transformer.py:47-233, src/models/multi_head_attention.py:188-380 and
 src/models/glassrgbd.py:87-90 under torch.autograd; SetCriterion (src/models/glassrgbd.py:308-358); the optimizer of
 src/main_glassrgbd.py:59-67 (AdamW, lr 1e-4, weight decay 1e-4) and the clip of src/engine_glassrgbd.py:155-159
-(max_norm 0.1).  Dropout must be 0 (`--dropout 0.0` is the gradient-parity configuration).
+(max_norm 0.1).  Train-mode dropout (`--dropout`, default 0.1) is built with regenerated masks (see __init__); `--dropout 0.0`
+is the gradient-parity configuration (masks of another generator cannot be compared element by element).
 
 B200 design
 * every trainable tensor of the branch lives in ONE flat fp32 master buffer with flat gradient / Adam-moment twins and
@@ -58,6 +59,14 @@ class LineBranch:
         # root each (fused q|k GEMM, out_scale) or q alone by the whole factor (cross attention), so the attention kernels
         # run with scale 1 -- the tcgen05 forward kernel's fast path -- and the backward multiplies dQ / dK back
         self.rs = float((self.cfg["hidden_dim"] // self.cfg["nheads"]) ** -0.25)
+        # train-mode dropout of the DETR layers (src/args.py:51 default 0.1; transformer.py:149-162,212-233: dropout1/2/3 on the
+        # sub-layer outputs, `dropout` on the FFN hidden layer; multi_head_attention.py:368: on the attention probabilities).
+        # Masks are never stored: every site regenerates its mask from (step seed in device memory, site id, element index)
+        # in the backward; the seed is incremented by the forward itself, so a replayed CUDA graph draws new masks every step.
+        self.p_drop = float(self.cfg.get("dropout", 0.0) or 0.0)
+        import torch.distributed as _dist
+        rank = _dist.get_rank() if _dist.is_available() and _dist.is_initialized() else 0
+        self.drop_seed = torch.full((1,), (torch.initial_seed() * 2654435761 + rank * 7919) & 0x3FFFFFFF, dtype=torch.int32, device=self.dev)
         # ---- flat layout: 2-D weights [N, K] are stored with N padded to 16 (zero rows), vectors padded to 16
         self.index, self.shapes, off = {}, {}, 0
         for name, v in state_dict.items():
@@ -152,11 +161,14 @@ class LineBranch:
         ops.transpose_batch(self._wt_tables)
 
     # ------------------------------------------------------------------ forward (activations kept for the backward)
-    def _attend(self, q, k, v, B, Lq, Lk, q_rs, k_rs):
+    def _drop(self, site):
+        return (self.drop_seed, site, self.p_drop) if self.p_drop > 0 else None
+
+    def _attend(self, q, k, v, B, Lq, Lk, q_rs, k_rs, site=0):
         E, nh = self.cfg["hidden_dim"], self.cfg["nheads"]
         o = torch.empty(B * Lq, E, dtype=torch.bfloat16, device=self.dev)
         ops.attention(q, k, v, o, items=B, heads=nh, Lq=Lq, Lk=Lk, hd=E // nh, q_strides=(Lq * q_rs, q_rs),
-                      k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E), o_strides=(Lq * E, E))
+                      k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E), o_strides=(Lq * E, E), dropout=self._drop(site))
         return o
 
     def _fork_gemm(self, x, lin):
@@ -167,10 +179,20 @@ class LineBranch:
             conv_gemm(x, lin.pw, out=y)
         return y
 
-    def _ln_gemm(self, x, lin, res, ln):
+    def _ln_gemm(self, x, lin, res, ln, site=0):
+        """LN(res + dropout(Linear(x))) -> (output, pre-LayerNorm sum kept for the backward)"""
+        if self.p_drop > 0:      # the dropout sits between the GEMM and the residual add: un-fused epilogue
+            z = ops.dropout(conv_gemm(x, lin.pw), self.drop_seed, site, self.p_drop, res=res)
+            return ops.layernorm(z, ln[0], ln[1]), z
         z = torch.empty(x.shape[0], lin.n_pad, dtype=torch.bfloat16, device=self.dev)
         y = conv_gemm(x, lin.pw, res=res, res_mode=RES_BEFORE_NORM, ln=(ln[0], ln[1]), y_raw=z)
         return y, z
+
+    def _ffn_hidden(self, x, lin, site):
+        hm = conv_gemm(x, lin.pw, post_act=ACT_RELU)
+        if self.p_drop > 0:
+            ops.dropout(hm, self.drop_seed, site, self.p_drop, out=hm)
+        return hm
 
     def forward(self, c5):
         """c5: bf16 channels-last [B, h, w, 2048] (no gradient flows further back).  Returns fp32 (logits [6,B,Q,2],
@@ -183,18 +205,21 @@ class LineBranch:
             self._tables[key] = sine_table(h, w, E // 2, True, self.dev).to(torch.bfloat16)
         pos = self._tables[key]
         tp = self.tape = {"B": B, "L": L, "enc": [], "dec": []}
+        if self.p_drop > 0:
+            self.drop_seed.add_(1)          # new masks every step (captured: every graph replay increments it too)
         tp["c5"] = c5.reshape(B * L, c5.shape[-1])
         x = conv_gemm(tp["c5"], self.input_proj.pw)
-        for ly in self.enc:
+        for li, ly in enumerate(self.enc):
             a = ly["attn"]
+            st = 10 * li
             xp = ops.add_rows(x, pos, L)
             v = self._fork_gemm(x, a["v"])
             qk = conv_gemm(xp, a["qk"].pw, out_scale=self.rs)
             torch.cuda.current_stream().wait_stream(self._side)
-            o = self._attend(qk, qk[:, E:], v, B, L, L, 2 * E, 2 * E)
-            x1, z1 = self._ln_gemm(o, a["o"], x, ly["n1"])
-            hm = conv_gemm(x1, ly["l1"].pw, post_act=ACT_RELU)
-            x2, z2 = self._ln_gemm(hm, ly["l2"], x1, ly["n2"])
+            o = self._attend(qk, qk[:, E:], v, B, L, L, 2 * E, 2 * E, site=st + 1)
+            x1, z1 = self._ln_gemm(o, a["o"], x, ly["n1"], site=st + 2)
+            hm = self._ffn_hidden(x1, ly["l1"], st + 3)
+            x2, z2 = self._ln_gemm(hm, ly["l2"], x1, ly["n2"], site=st + 4)
             tp["enc"].append(dict(x=x, xp=xp, qk=qk, v=v, o=o, z1=z1, x1=x1, h=hm, z2=z2))
             x = x2
         memory = x
@@ -212,21 +237,22 @@ class LineBranch:
                 conv_gemm(memory, ly["cross"]["v"].pw, out=cv)
         for i, ly in enumerate(self.dec):
             s, cr = ly["self"], ly["cross"]
+            st = 100 + 10 * i
             tq1 = ops.add_rows(tgt, self.query_pos, Q)
             v = self._fork_gemm(tgt, s["v"])
             qk = conv_gemm(tq1, s["qk"].pw, out_scale=self.rs)
             torch.cuda.current_stream().wait_stream(self._side)
-            o1 = self._attend(qk, qk[:, E:], v, B, Q, Q, 2 * E, 2 * E)
-            x1, z1 = self._ln_gemm(o1, s["o"], tgt, ly["n1"])
+            o1 = self._attend(qk, qk[:, E:], v, B, Q, Q, 2 * E, 2 * E, site=st + 1)
+            x1, z1 = self._ln_gemm(o1, s["o"], tgt, ly["n1"], site=st + 2)
             tq2 = ops.add_rows(x1, self.query_pos, Q)
             cq = conv_gemm(tq2, cr["q"].pw, out_scale=self.rs * self.rs)
             ck, cv = ckv[i]
             if i == 0:
                 torch.cuda.current_stream().wait_stream(self._side2)
-            o2 = self._attend(cq, ck, cv, B, Q, L, E, E)
-            x2, z2 = self._ln_gemm(o2, cr["o"], x1, ly["n2"])
-            hm = conv_gemm(x2, ly["l1"].pw, post_act=ACT_RELU)
-            x3, z3 = self._ln_gemm(hm, ly["l2"], x2, ly["n3"])
+            o2 = self._attend(cq, ck, cv, B, Q, L, E, E, site=st + 3)
+            x2, z2 = self._ln_gemm(o2, cr["o"], x1, ly["n2"], site=st + 4)
+            hm = self._ffn_hidden(x2, ly["l1"], st + 5)
+            x3, z3 = self._ln_gemm(hm, ly["l2"], x2, ly["n3"], site=st + 6)
             ops.layernorm(x3, self.dec_norm[0], self.dec_norm[1], out=hs[i])
             tp["dec"].append(dict(x0=tgt, tq1=tq1, qk=qk, v=v, o1=o1, z1=z1, x1=x1, tq2=tq2, cq=cq, ck=ck, cv=cv, o2=o2,
                                   z2=z2, x2=x2, h=hm, z3=z3, x3=x3))
@@ -257,18 +283,23 @@ class LineBranch:
     def _ln_bwd(self, dy, z, ln, add=None):
         return ops.layernorm_bwd(dy, z, ln[0], ln[2], ln[3], add=add)
 
-    def _attend_bwd(self, q, k, v, o, d_o, B, Lq, Lk, q_rs, k_rs, dq, dk, dv, fused=True):
+    def _sub_grad(self, dz, site):
+        """gradient of the sub-layer output from the gradient of the pre-LayerNorm sum z = res + dropout(y)"""
+        return ops.dropout(dz, self.drop_seed, site, self.p_drop) if self.p_drop > 0 else dz
+
+    def _attend_bwd(self, q, k, v, o, d_o, B, Lq, Lk, q_rs, k_rs, dq, dk, dv, fused=True, site=0):
         E, nh = self.cfg["hidden_dim"], self.cfg["nheads"]
         ops.attention_bwd(q, k, v, d_o, dq, dk, dv, items=B, heads=nh, Lq=Lq, Lk=Lk, hd=E // nh,
                           q_strides=(Lq * q_rs, q_rs), k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E),
                           do_strides=(Lq * E, E), dq_strides=(Lq * q_rs, q_rs), dk_strides=(Lk * k_rs, k_rs),
                           dv_strides=(Lk * E, E), scale=1.0, o=o, o_strides=(Lq * E, E),
-                          dq_mul=self.rs if fused else self.rs * self.rs, dk_mul=self.rs if fused else 1.0)
+                          dq_mul=self.rs if fused else self.rs * self.rs, dk_mul=self.rs if fused else 1.0, dropout=self._drop(site))
 
-    def _ffn_bwd(self, ly, d_out, z, hm, x_in, ln):
+    def _ffn_bwd(self, ly, d_out, z, hm, x_in, ln, site_hidden=0, site_out=0):
         dz = self._ln_bwd(d_out, z, ln)
-        dh = self._lin_bwd(ly["l2"], dz, hm)
-        dpre = ops.act_bwd(dh, hm, ACT_RELU)
+        dh = self._lin_bwd(ly["l2"], self._sub_grad(dz, site_out), hm)
+        # hm is the hidden layer AFTER its dropout: hm > 0 <=> active and kept, and kept units carry the factor 1 / (1 - p)
+        dpre = ops.act_bwd(dh, hm, ACT_RELU, scale=1.0 / (1.0 - self.p_drop) if self.p_drop > 0 else 1.0)
         return self._lin_bwd(ly["l1"], dpre, x_in, res=dz)
 
     def _add(self, a, b):
@@ -295,14 +326,15 @@ class LineBranch:
         dmem, d_next = None, None
         for i in reversed(range(len(self.dec))):
             ly, s = self.dec[i], tp["dec"][i]
+            st = 100 + 10 * i
             d_x3 = self._ln_bwd(dhs[i], s["x3"], self.dec_norm, add=d_next)
-            d_x2 = self._ffn_bwd(ly, d_x3, s["z3"], s["h"], s["x2"], ly["n3"])
+            d_x2 = self._ffn_bwd(ly, d_x3, s["z3"], s["h"], s["x2"], ly["n3"], st + 5, st + 6)
             # cross attention
             cr = ly["cross"]
             dz2 = self._ln_bwd(d_x2, s["z2"], ly["n2"])
-            d_o = self._lin_bwd(cr["o"], dz2, s["o2"])
+            d_o = self._lin_bwd(cr["o"], self._sub_grad(dz2, st + 4), s["o2"])
             dq, dk, dv = torch.empty(B * Q, E, **bf), torch.empty(B * L, E, **bf), torch.empty(B * L, E, **bf)
-            self._attend_bwd(s["cq"], s["ck"], s["cv"], s["o2"], d_o, B, Q, L, E, E, dq, dk, dv, fused=False)
+            self._attend_bwd(s["cq"], s["ck"], s["cv"], s["o2"], d_o, B, Q, L, E, E, dq, dk, dv, fused=False, site=st + 3)
             dtq = self._lin_bwd(cr["q"], dq, s["tq2"])
             gq += dtq.view(B, Q, E).sum(0, dtype=torch.float32)
             d_x1 = self._add(dtq, dz2)
@@ -311,9 +343,9 @@ class LineBranch:
             # self attention
             sa = ly["self"]
             dz1 = self._ln_bwd(d_x1, s["z1"], ly["n1"])
-            d_o = self._lin_bwd(sa["o"], dz1, s["o1"])
+            d_o = self._lin_bwd(sa["o"], self._sub_grad(dz1, st + 2), s["o1"])
             dqk, dv = torch.empty(B * Q, 2 * E, **bf), torch.empty(B * Q, E, **bf)
-            self._attend_bwd(s["qk"], s["qk"][:, E:], s["v"], s["o1"], d_o, B, Q, Q, 2 * E, 2 * E, dqk, dqk[:, E:], dv)
+            self._attend_bwd(s["qk"], s["qk"][:, E:], s["v"], s["o1"], d_o, B, Q, Q, 2 * E, 2 * E, dqk, dqk[:, E:], dv, site=st + 1)
             dtq = self._lin_bwd(sa["qk"], dqk, s["tq1"])
             gq += dtq.view(B, Q, E).sum(0, dtype=torch.float32)
             d_next = self._lin_bwd(sa["v"], dv, s["x0"], res=self._add(dtq, dz1))
@@ -322,12 +354,13 @@ class LineBranch:
         d_x = dmem
         for i in reversed(range(len(self.enc))):
             ly, s = self.enc[i], tp["enc"][i]
-            d_x1 = self._ffn_bwd(ly, d_x, s["z2"], s["h"], s["x1"], ly["n2"])
+            st = 10 * i
+            d_x1 = self._ffn_bwd(ly, d_x, s["z2"], s["h"], s["x1"], ly["n2"], st + 3, st + 4)
             a = ly["attn"]
             dz1 = self._ln_bwd(d_x1, s["z1"], ly["n1"])
-            d_o = self._lin_bwd(a["o"], dz1, s["o"])
+            d_o = self._lin_bwd(a["o"], self._sub_grad(dz1, st + 2), s["o"])
             dqk, dv = torch.empty(B * L, 2 * E, **bf), torch.empty(B * L, E, **bf)
-            self._attend_bwd(s["qk"], s["qk"][:, E:], s["v"], s["o"], d_o, B, L, L, 2 * E, 2 * E, dqk, dqk[:, E:], dv)
+            self._attend_bwd(s["qk"], s["qk"][:, E:], s["v"], s["o"], d_o, B, L, L, 2 * E, 2 * E, dqk, dqk[:, E:], dv, site=st + 1)
             t = self._lin_bwd(a["qk"], dqk, s["xp"], res=dz1)
             d_x = self._lin_bwd(a["v"], dv, s["x"], res=t)
         dc5 = self._lin_bwd(self.input_proj, d_x, tp["c5"])
