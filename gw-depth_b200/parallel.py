@@ -1,8 +1,9 @@
 """Host-side data-parallel plumbing (one process per GPU, torch.distributed; NCCL on the box, gloo in the CPU tests).
 
 The path shards over the batch with no data-path collective.  What does cross ranks:
-  * training: ONE sum all-reduce of the flat gradient buffer (train.LineBranch.G) per step, and the scalar
-    `num_items` of SetCriterion (src/models/glassrgbd.py:324-326);
+  * training: one sum all-reduce per flat gradient buffer per step (15 buffers for the whole model, started asynchronously as
+    their backward completes: allreduce_async / wait_all), and the scalar `num_items` of SetCriterion
+    (src/models/glassrgbd.py:324-326);
   * evaluation: one all-reduce of [9 metric sums, image count] (src/engine_glassrgbd.py:243-264 averages per image);
   * benchmarking: the max over ranks of the device-timed interval.
 Every helper is a no-op for a single process.
@@ -34,6 +35,23 @@ def allreduce_sum_(flat):
     if w > 1:
         dist.all_reduce(flat)
     return w
+
+
+def allreduce_async(buffers):
+    """start the sum all-reduce of several flat gradient buffers and return the work handles (empty for one process): the
+    whole-model training step issues one per stage module as soon as its backward has been enqueued, so the exchange overlaps
+    the rest of the backward (train_model.Trainer._exchange)"""
+    if world_size() == 1:
+        return []
+    return [dist.all_reduce(b, async_op=True) for b in buffers]
+
+
+def wait_all(works):
+    """block the current stream (CUDA) / the caller (CPU) until every started all-reduce has finished; returns the world size
+    the summed gradients have to be divided by"""
+    for w in works:
+        w.wait()
+    return world_size()
 
 
 def max_over_ranks(value, device="cpu"):

@@ -156,9 +156,8 @@ class Trainer:
         if self._defer is not None:          # inside a captured region: the collective is issued after the replay
             self._defer += mods
             return
-        if self.exchange_grads and parallel.world_size() > 1:
-            for m in mods:
-                self._works.append(dist.all_reduce(m.G, async_op=True))
+        if self.exchange_grads:
+            self._works += parallel.allreduce_async([m.G for m in mods])
 
     def backward_dense(self, g_depth1, g_depth2, g_depth3, g_depth_rows, g_seg_rows):
         """dense branch + 1/32 line-window stage; returns its part of d C5 (and keeps d C4, d C3 for `backward_line`)"""
@@ -181,10 +180,8 @@ class Trainer:
     # ------------------------------------------------------------------ optimizer
     def step(self):
         """wait for the gradient exchange, ONE clip norm over every flat buffer (src/engine_glassrgbd.py:155-159), AdamW"""
-        for w in self._works:
-            w.wait()
+        world = parallel.wait_all(self._works)
         self._works = []
-        world = parallel.world_size()
         mods = self.modules()
         self.sumsq.zero_()
         for m in mods:

@@ -34,7 +34,14 @@ def _worker(rk, world, port, out):
         # 4. timing: max over ranks; 5. the criterion's normaliser
         t = parallel.max_over_ranks(10.0 + rk)
         n = parallel.global_num_items(12 + 5 * rk)
-        torch.save({"mine": mine, "G": G / w, "mean": mean, "t": t, "n": n, "w": w}, os.path.join(out, "r%d.pt" % rk))
+        # 6. the whole-model step's exchange: several flat buffers started asynchronously in backward order, one wait, then ONE
+        #    clip norm over all of them (what Trainer._exchange / Trainer.step do with gwd_sumsq / gwd_adamw_step on the GPU)
+        bufs = [torch.full((n_,), float(rk + 1 + i), dtype=torch.float32) for i, n_ in enumerate((5, 1000, 33))]
+        works = parallel.allreduce_async(bufs[:2]) + parallel.allreduce_async(bufs[2:])
+        wa = parallel.wait_all(works)
+        sumsq = sum(float((b / wa).double().pow(2).sum()) for b in bufs)
+        torch.save({"mine": mine, "G": G / w, "mean": mean, "t": t, "n": n, "w": w, "bufs": [b / wa for b in bufs], "sumsq": sumsq},
+                   os.path.join(out, "r%d.pt" % rk))
     finally:
         dist.destroy_process_group()
 
@@ -49,6 +56,9 @@ def test_two_rank_gloo(tmp_path):
         assert x["w"] == 2 and torch.equal(x["G"], base * 1.5)
         assert torch.allclose(x["mean"], torch.full((9,), 3.0, dtype=torch.float64))
         assert x["t"] == 11.0 and x["n"] == (12 + 17) / 2
+        for i, b in enumerate(x["bufs"]):                       # mean over the two ranks of (rank + 1 + i)
+            assert torch.equal(b, torch.full_like(b, 1.5 + i))
+        assert abs(x["sumsq"] - (5 * 1.5 ** 2 + 1000 * 2.5 ** 2 + 33 * 3.5 ** 2)) < 1e-6
 
 
 def test_single_process_is_a_no_op():
@@ -56,5 +66,6 @@ def test_single_process_is_a_no_op():
     g = torch.ones(4)
     assert parallel.allreduce_sum_(g) == 1 and torch.equal(g, torch.ones(4))
     assert parallel.max_over_ranks(3.5) == 3.5 and parallel.global_num_items(0) == 1.0
+    assert parallel.allreduce_async([g]) == [] and parallel.wait_all([]) == 1
     m = parallel.mean_depth_metrics(torch.tensor([[1.0] * 9, [3.0] * 9], dtype=torch.float64))
     assert torch.allclose(m, torch.full((9,), 2.0, dtype=torch.float64))
