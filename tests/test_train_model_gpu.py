@@ -234,3 +234,44 @@ def test_drop_in_training_loop_and_fused_step():
     net2.sync_from_trainer()
     sd_after = tr.state_dict()
     assert any(not torch.equal(sd_after[k].cpu(), sd[k]) for k in sd_after)
+
+
+def test_reference_evaluate_loop_on_the_drop_in_and_fused_evaluator(tmp_path):
+    """the reference's own `evaluate` (src/engine_glassrgbd.py:174-342, imported unmodified from baseline/_ref: batch 1, maps to
+    the host, numpy compute_depth_errors, compute_mean_ioU, eval_results.txt) runs on the drop-in model, and the fused device-side
+    bookkeeping (`evaluation.DenseEvaluator`: gwd_depth_metrics + gwd_seg_confusion) reports the same numbers"""
+    M, _ = _mods()
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_shims
+    if not ref_shims.reference_available():
+        pytest.skip("reference tree not staged under baseline/_ref (oracle/stage_ref.sh)")
+    ref_shims.install()
+    from engine_glassrgbd import evaluate
+    from util.misc import NestedTensor
+    from gwdepth_b200 import evaluation
+    n_img, H, W = 3, 224, 320
+    args = M.default_args(device="cuda", dropout=0.0, coco_path=None, append_word=None, resume="", dataset="val")
+    net, criterions, post = M.build_model(args)
+    net.load_state_dict(synth_weights())
+    net.cuda()
+    batches = []
+    for i in range(n_img):
+        images, targets, depth_gt, seg_gt = synth.synth_batch(1, H, W, seed=40 + i)
+        targets[0]["image_id"] = torch.tensor([i])
+        mask = torch.zeros(1, H, W, dtype=torch.bool)
+        batches.append((NestedTensor(images, mask), NestedTensor(depth_gt, mask), NestedTensor(seg_gt, mask), targets, ["img_%d" % i]))
+
+    class Loader(list):
+        dataset = type("D", (), {"id_to_img": {i: "img_%d" % i for i in range(n_img)}})()
+    stats = evaluate(net, criterions, post, Loader(batches), None, torch.device("cuda"), str(tmp_path), args, save_dir=str(tmp_path))
+    assert os.path.exists(os.path.join(str(tmp_path), "eval_results.txt"))
+    ev = evaluation.DenseEvaluator(min_depth_eval=args.min_depth_eval, max_depth_eval=args.max_depth_eval)
+    net.eval()
+    with torch.no_grad():
+        for samples, depth_gt, seg_gt, _, _ in batches:
+            ev.update(net(samples.tensors.cuda()), depth_gt.tensors.cuda(), seg_gt.tensors.cuda())
+    mine = ev.summary()
+    for k in ("silog", "abs_rel", "log10", "rms", "sq_rel", "log_rms", "d1", "d2", "d3"):
+        assert abs(float(stats[k]) - mine[k]) <= 2e-5 * max(1.0, abs(mine[k])), (k, float(stats[k]), mine[k])
+    assert abs(float(stats["Mean IU"]) - mine["Mean IU"]) < 1e-3 and abs(float(stats["Pixel accuracy"]) - mine["Pixel accuracy"]) < 1e-3
+    assert math.isfinite(float(stats["loss"])) and mine["images"] == n_img
