@@ -14,8 +14,10 @@ import torch
 from . import ops, parallel
 
 
-class FlatAdamW:
-    """Drop-in for `torch.optim.AdamW(param_groups, lr, weight_decay)` + `clip_grad_norm_` on CUDA parameters.
+class FlatAdamW(torch.optim.Optimizer):
+    """Drop-in for `torch.optim.AdamW(param_groups, lr, weight_decay)` + `clip_grad_norm_` on CUDA parameters.  A
+    `torch.optim.Optimizer`, so `StepLR(optimizer, lr_drop)` of src/main_glassrgbd.py:67 works on it, with
+    `state_dict()` / `load_state_dict()` for the resume path (:160-163, :222).
 
     param_groups: list of dicts {"params": [...], "lr": optional} exactly as src/main_glassrgbd.py:59-66 builds them.
     After construction every parameter's storage is a view into the group's flat buffer and `p.grad` is a persistent
@@ -24,6 +26,8 @@ class FlatAdamW:
     def __init__(self, param_groups, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, max_norm=0.0, bf16_mirror=False):
         if isinstance(param_groups, (list, tuple)) and param_groups and not isinstance(param_groups[0], dict):
             param_groups = [{"params": list(param_groups)}]
+        plain = [dict(g, params=list(g["params"])) for g in param_groups]
+        torch.optim.Optimizer.__init__(self, plain, dict(lr=lr, weight_decay=weight_decay))
         self.betas, self.eps, self.max_norm, self.t = betas, eps, max_norm, 0
         self.groups = []
         for g in param_groups:
@@ -47,7 +51,24 @@ class FlatAdamW:
                                 "mirror": torch.empty(n, dtype=torch.bfloat16, device=dev) if bf16_mirror else None,
                                 "lr": g.get("lr", lr), "weight_decay": g.get("weight_decay", weight_decay)})
         self.param_groups = self.groups          # the reference's lr scheduler edits param_groups[i]["lr"]
+        for g in self.groups:
+            g.setdefault("initial_lr", g["lr"])
         self._sumsq = torch.zeros(1, dtype=torch.float64, device=self.groups[0]["P"].device) if self.groups else None
+
+    def state_dict(self):
+        """step count, learning rates and the flat Adam moments per group (the parameter order is the construction order)"""
+        return {"format": "gwd_flat_adamw_v1", "t": self.t,
+                "groups": [{"lr": g["lr"], "initial_lr": g.get("initial_lr", g["lr"]), "weight_decay": g["weight_decay"],
+                            "numel": g["P"].numel(), "M": g["M"].detach().cpu(), "V": g["V"].detach().cpu()} for g in self.groups]}
+
+    def load_state_dict(self, state):
+        assert state.get("format") == "gwd_flat_adamw_v1" and len(state["groups"]) == len(self.groups), "optimizer state of another layout"
+        self.t = int(state["t"])
+        for g, s in zip(self.groups, state["groups"]):
+            assert s["numel"] == g["P"].numel()
+            g["M"].copy_(s["M"])
+            g["V"].copy_(s["V"])
+            g["lr"], g["initial_lr"], g["weight_decay"] = s["lr"], s["initial_lr"], s["weight_decay"]
 
     def zero_grad(self, set_to_none=False):
         for g in self.groups:
@@ -64,7 +85,7 @@ class FlatAdamW:
             off += ops.round_up(p.numel(), 4)
 
     @torch.no_grad()
-    def step(self):
+    def step(self, closure=None):
         """all-reduce (if distributed) + global-norm clip + AdamW; returns the device tensor holding sum g^2 (before the
         1/world scale), so the caller can log the gradient norm without forcing a sync here"""
         world = 1

@@ -318,6 +318,25 @@ def test_flat_adamw_is_a_drop_in_for_clip_plus_torch_adamw():
             assert rel_l2(a, b) < 5e-6, (it, n)
     assert torch.equal(net[2].weight, ref[2].weight)                     # frozen tensors untouched
     assert all(p.data_ptr() >= g["P"].data_ptr() for g in opt.groups for p in g["params"])
+    # it is a torch Optimizer: the reference's StepLR (src/main_glassrgbd.py:67) drives its learning rates, and a resumed run
+    # (state_dict -> load_state_dict, :160-163) continues on the same trajectory
+    assert isinstance(opt, torch.optim.Optimizer)
+    sched, ref_sched = torch.optim.lr_scheduler.StepLR(opt, 1), torch.optim.lr_scheduler.StepLR(ref_opt, 1)
+    sched.step(); ref_sched.step()
+    assert abs(opt.param_groups[0]["lr"] - 1e-3) < 1e-12 and abs(opt.param_groups[1]["lr"] - 1e-4) < 1e-12
+    state = opt.state_dict()
+    net2 = copy.deepcopy(ref)
+    for a, b in zip(net2.parameters(), net.parameters()):
+        a.data.copy_(b.data)
+    opt2 = optim.FlatAdamW(groups(net2), lr=1e-2, weight_decay=1e-4, max_norm=0.1)
+    opt2.load_state_dict(state)
+    for m, o in ((net, opt), (net2, opt2), (ref, ref_opt)):
+        o.zero_grad()
+        torch.nn.functional.mse_loss(m(x), y).mul(1e-3).backward()
+    torch.nn.utils.clip_grad_norm_(ref.parameters(), 0.1)
+    ref_opt.step(); opt.step(); opt2.step()
+    for (n, a), b, c in zip(net.named_parameters(), ref.parameters(), net2.parameters()):
+        assert rel_l2(a, b) < 5e-6 and torch.equal(a, c), n
 
 
 # ------------------------------------------------------------------------------------------ the branch
