@@ -14,5 +14,5 @@ echo "# per kernel (only kernels with tensor-core or TMA instructions)"
 awk '/Function :/ {name=$3} 
      / UTCHMMA/ {t[name]++} / LDTM/ {l[name]++} / UTMALDG/ {g[name]++} / UTMASTG/ {s[name]++} / UTCBAR/ {b[name]++} / HMMA/ {h[name]++}
      END {for (n in t) names[n]=1; for (n in l) names[n]=1; for (n in g) names[n]=1; for (n in s) names[n]=1; for (n in h) names[n]=1;
-          for (n in names) printf "%s UTCHMMA=%d LDTM=%d UTMALDG=%d UTMASTG=%d UTCBAR=%d HMMA=%d\n", n, t[n], l[n], g[n], s[n], b[n], h[n]}' "$TMP" | sort | c++filt | cut -c1-200
+          for (n in names) printf "UTCHMMA=%-4d LDTM=%-3d UTMALDG=%-3d UTMASTG=%-2d UTCBAR=%-3d HMMA=%-4d %s\n", t[n], l[n], g[n], s[n], b[n], h[n], n}' "$TMP" | sort -k7 | c++filt | sed 's/(anonymous namespace):://g' | cut -c1-190
 rm -f "$TMP"
