@@ -658,14 +658,17 @@ class Engine:
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole forward
     @torch.no_grad()
-    def forward_graphed(self, images, mask=None):
+    def forward_graphed(self, images, mask=None, slot=0):
         """The forward has no host synchronisation and no data-dependent control flow, so the ~480 launches of a step
         are captured once per input shape and replayed as one CUDA graph (the reference cannot: 36 `torch.equal` syncs,
         `int()` reads in CertainSample, ...).  A padded batch is captured with its padding mask as a second STATIC input (the
         per-image position codes and key-padding masks are computed from it inside the graph).  Returns the graph's static
         output tensors: consume (or clone) them before the next call with the same shape.  At most `max_graphs` shapes are
         kept (least recently used first out): evaluation over many image sizes would otherwise hold one memory pool per shape."""
-        key = (tuple(images.shape), mask is not None)
+        # slot: independent graph instances (own static buffers and memory pool) of the same shape, so that a serving loop can
+        # replay batch i+1 on another stream while batch i is still in flight (the latency-bound phases of one batch -- DETR
+        # chain, coarse Swin stages -- leave most SMs idle; two interleaved replays fill them)
+        key = (tuple(images.shape), mask is not None, slot)
         entry = self._graphs.pop(key, None)
         if entry is None:
             while len(self._graphs) >= self.max_graphs:
