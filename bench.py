@@ -57,6 +57,7 @@ def parse():
                     "0.0 is the parity configuration the headline is quoted on)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-forward", action="store_true", help="skip the inference-forward section")
+    ap.add_argument("--fwd-streams", type=int, default=2, help="inference-forward section: graph instances / streams consecutive batches alternate on")
     ap.add_argument("--no-reference-eager", action="store_true")
     return ap.parse_args()
 
@@ -393,13 +394,27 @@ def main():
         hostf = [synth.synth_batch(FWD_BATCH, H, W, seed=200 + 7 * rank + i)[0].pin_memory() for i in range(NB)]
         resf = [h.to(dev) for h in hostf]
         with torch.no_grad():
-            fstep = plan.forward_graphed if net.use_cuda_graph else plan.forward
-            for i in range(warm):
-                fstep(resf[i % NB])
+            # consecutive batches replay two CUDA-graph instances on two streams (what model.infer_stream does): the latency-bound
+            # phases of one forward share the SMs with the wide phases of the next.  --fwd-streams 1: one stream, one instance.
+            nstr = args.fwd_streams if net.use_cuda_graph else 1
+            fstreams = [torch.cuda.Stream(dev) for _ in range(nstr)]
+
+            def frun(n):
+                cur = torch.cuda.current_stream()
+                for st_ in fstreams:
+                    st_.wait_stream(cur)
+                for i in range(n):
+                    with torch.cuda.stream(fstreams[i % nstr]):
+                        if net.use_cuda_graph:
+                            plan.forward_graphed(resf[i % NB], slot=i % nstr)
+                        else:
+                            plan.forward(resf[i % NB])
+                for st_ in fstreams:
+                    cur.wait_stream(st_)
+            frun(max(warm, 2 * nstr))
             barrier()
             e0.record()
-            for i in range(steps):
-                fstep(resf[i % NB])
+            frun(steps)
             e1.record()
             barrier()
             ms_f = reduce_max_ms(e0.elapsed_time(e1))
@@ -419,7 +434,9 @@ def main():
         fv = world * FWD_BATCH * steps / (ms_f / 1000.0)
         fwd = {"metric": "images_per_sec_fwd_480x640_bf16", "value": fv, "unit": UNIT, "ms_per_step": ms_f / steps, "batch_per_gpu": FWD_BATCH,
                "e2e": world * FWD_BATCH * steps / (ms_fe / 1000.0), "frac_of_peak": fv / world * FLOP_PER_IMAGE_FWD / 1e12 / measured_peak()[0],
-               "workload": "BASELINE configs[1]: inference forward, one CUDA-graph replay per batch; e2e = model.infer_stream from pinned host batches"}
+               "streams": nstr,
+               "workload": "BASELINE configs[1]: inference forward, one CUDA-graph replay per batch, consecutive batches on %d alternating streams "
+                           "(ms_per_step = timed region / batches); e2e = model.infer_stream from pinned host batches" % nstr}
         del resf, plan
     if rank != 0:
         if world > 1:

@@ -84,6 +84,8 @@ SIGNATURES = {
     "gwd_upsample_nearest": (c_int, [P, L, I, I, I, P, L, I, I, I, P, L, P]),
     "gwd_avgpool": (c_int, [P, L, I, I, I, I, P, L, I, P]),
     "gwd_bilinear_up": (c_int, [P, L, I, I, I, P, L, I, I, I, P]),
+    "gwd_avgpool_pyramid": (c_int, [P, L, I, I, I, P, P, P, P, I, P]),
+    "gwd_bilinear_up4": (c_int, [P, P, P, P, P, I, P, L, I, I, I, P]),
     "gwd_sample_bilinear": (c_int, [P, L, I, P, L, I, I, I, I, P, I, P, P]),
     "gwd_sample_scalar": (c_int, [P, I, I, I, P, I, P, P]),
     "gwd_line_ref_gather": (c_int, [P, L, P, L, P, I, P, L, I, I, I, I, I, I, P]),

@@ -3,6 +3,7 @@
 // nearest / bilinear resampling, average pooling, point sampling and the anchor-mixture depth read-out.
 // All activations are channels-last bf16; statistics and small depth maps are fp32.
 // One warp owns one token (pixel) row: 16-byte vector loads, shuffle reductions, no shared memory.
+#include <stdlib.h>
 #include "gwd_common.cuh"
 
 namespace {
@@ -159,6 +160,33 @@ __global__ void gwd_layernorm_kernel(const bf16* x, int64_t x_rs, const bf16* re
   if (live) row_store(r, out + row * out_rs, C, rg);
 }
 
+// the same with TWO rows per lane group in flight (both rows' loads are issued before either row's reduction): on big maps the
+// one-row kernel is bound by the load -> shuffle-reduce -> store latency chain of its single row, not by HBM
+template <int NV>
+__global__ void gwd_layernorm_x2_kernel(const bf16* x, int64_t x_rs, const bf16* res, int64_t res_rs, const float* g,
+                                        const float* b, float eps, int act, bf16* out, int64_t out_rs, int64_t rows, int C,
+                                        int n) {
+  RowGroup rg = row_group(C);
+  const int64_t r0 = rg.row * 2, r1 = r0 + 1;
+  const bool l0 = r0 < rows, l1 = r1 < rows;
+  const int64_t a0 = l0 ? r0 : 0, a1 = l1 ? r1 : 0;
+  WarpRow<NV> ra, rb;
+  row_load(ra, x + a0 * x_rs, C, rg, l0);
+  row_load(rb, x + a1 * x_rs, C, rg, l1);
+  if (res) {
+    if (l0) row_add(ra, res + a0 * res_rs, C, rg);
+    if (l1) row_add(rb, res + a1 * res_rs, C, rg);
+  }
+  if (g) {
+    row_layernorm(ra, C, n, rg, g, b, eps);
+    row_layernorm(rb, C, n, rg, g, b, eps);
+  }
+  row_act(ra, act, C, rg);
+  row_act(rb, act, C, rg);
+  if (l0) row_store(ra, out + a0 * out_rs, C, rg);
+  if (l1) row_store(rb, out + a1 * out_rs, C, rg);
+}
+
 // out[row] = x[row] + addend[row % period]
 template <int NV>
 __global__ void gwd_add_rows_kernel(const bf16* x, int64_t x_rs, const bf16* addend, int64_t a_rs, int64_t period,
@@ -289,6 +317,112 @@ __global__ void gwd_avgpool_kernel(const bf16* x, int64_t x_rs, int B, int H, in
 #pragma unroll
   for (int i = 0; i < 8; ++i) acc[i] *= inv;
   store8(out + pix * out_rs + c, acc);
+}
+
+// nn.AvgPool2d(k, k), floor mode, for k = 2, 4, 8 and 16 of the same map in ONE pass over it: the four pooling branches of
+// PyramidLayer (points_sample.py:61-75,115-121).  A CTA owns a 16 x 16 pixel block: 2 x 2 sums from global memory (fp32, kept in
+// shared memory), then 4 x 4, 8 x 8 and 16 x 16 sums as a tree over them.  A cell of size k at (Y, X) exists iff Y < H/k and
+// X < W/k, and then all of its sub-cells exist, so edge blocks need no special case beyond that test.
+// shared memory: (64 + 16 + 4) x C floats.
+__global__ void __launch_bounds__(256)
+gwd_avgpool_pyramid_kernel(const bf16* __restrict__ x, int64_t x_rs, int H, int W, bf16* __restrict__ o2, bf16* __restrict__ o4,
+                           bf16* __restrict__ o8, bf16* __restrict__ o16, int C) {
+  extern __shared__ __align__(16) float pyr_s[];
+  float* s2 = pyr_s;              // [8][8][C]
+  float* s4 = s2 + 64 * C;        // [4][4][C]
+  float* s8 = s4 + 16 * C;        // [2][2][C]
+  const int cv = C / 8;
+  const int bx = blockIdx.x, by = blockIdx.y, b = blockIdx.z;
+  const bf16* xb = x + static_cast<int64_t>(b) * H * W * x_rs;
+  // ---- 2 x 2 ----
+  {
+    const int h2 = H / 2, w2 = W / 2;
+    for (int it = threadIdx.x; it < 64 * cv; it += blockDim.x) {
+      const int cell = it / cv, c = (it - cell * cv) * 8;
+      const int Y = 8 * by + (cell >> 3), X = 8 * bx + (cell & 7);
+      float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      if (Y < h2 && X < w2) {
+        const bf16* p0 = xb + (static_cast<int64_t>(2 * Y) * W + 2 * X) * x_rs + c;
+        float f0[8], f1[8], f2[8], f3[8];
+        load8(p0, f0); load8(p0 + x_rs, f1); load8(p0 + W * x_rs, f2); load8(p0 + (W + 1) * x_rs, f3);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = ((f0[i] + f1[i]) + f2[i]) + f3[i];      // the order of the k = 2 loop of gwd_avgpool_kernel
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = acc[i] * 0.25f;
+        store8(o2 + ((static_cast<int64_t>(b) * h2 + Y) * w2 + X) * C + c, o);
+      }
+      float4* d = reinterpret_cast<float4*>(s2 + cell * C + c);
+      d[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      d[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+  }
+  __syncthreads();
+  // ---- 4 x 4, 8 x 8, 16 x 16: each level sums the 2 x 2 cells of the level below ----
+  const float* src = s2;
+  float* dst = s4;
+  bf16* outs[3] = {o4, o8, o16};
+#pragma unroll
+  for (int lv = 0; lv < 3; ++lv) {
+    const int k = 4 << lv, side = 4 >> lv;      // cells per block side at this level: 4, 2, 1
+    const int hk = H / k, wk = W / k;
+    const float inv = 1.f / (k * k);
+    for (int it = threadIdx.x; it < side * side * cv; it += blockDim.x) {
+      const int cell = it / cv, c = (it - cell * cv) * 8;
+      const int cy = cell / side, cx = cell - cy * side;
+      const int Y = side * by + cy, X = side * bx + cx;
+      const float* q = src + ((2 * cy) * (2 * side) + 2 * cx) * C + c;
+      float acc[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = (q[i] + q[C + i]) + (q[2 * side * C + i] + q[(2 * side + 1) * C + i]);
+      if (lv < 2) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[cell * C + c + i] = acc[i];
+      }
+      if (Y < hk && X < wk) {
+        float o[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = acc[i] * inv;
+        store8(outs[lv] + ((static_cast<int64_t>(b) * hk + Y) * wk + X) * C + c, o);
+      }
+    }
+    __syncthreads();
+    src = dst;
+    dst = s8;
+  }
+}
+
+// F.interpolate(mode='bilinear', align_corners=True) of FOUR maps into four adjacent channel slices of one concat buffer
+// (the branches of PyramidLayer, points_sample.py:115-121): a pixel's 4 x C channels leave as one contiguous run.
+struct Up4 {
+  const bf16* src[4];
+  int h[4], w[4];
+};
+__global__ void __launch_bounds__(256)
+gwd_bilinear_ac4_kernel(const Up4 u, bf16* __restrict__ out, int64_t out_rs, int H, int W, int C) {
+  const int cv = C / 8;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= W * 4 * cv) return;
+  const int X = t / (4 * cv), r = t - X * 4 * cv;
+  const int j = r / cv, c = (r - j * cv) * 8;
+  const int Y = blockIdx.y, b = blockIdx.z;
+  const int h = u.h[j], w = u.w[j];
+  const float ry = (H > 1) ? static_cast<float>(h - 1) / (H - 1) : 0.f;
+  const float rx = (W > 1) ? static_cast<float>(w - 1) / (W - 1) : 0.f;
+  const float fy = ry * Y, fx = rx * X;
+  const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
+  const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
+  const float ly = fy - y0, lx = fx - x0;
+  const bf16* base = u.src[j] + static_cast<int64_t>(b) * h * w * C + c;
+  float f00[8], f01[8], f10[8], f11[8], o[8];
+  load8(base + (static_cast<int64_t>(y0) * w + x0) * C, f00);
+  load8(base + (static_cast<int64_t>(y0) * w + x1) * C, f01);
+  load8(base + (static_cast<int64_t>(y1) * w + x0) * C, f10);
+  load8(base + (static_cast<int64_t>(y1) * w + x1) * C, f11);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    o[i] = (1.f - ly) * ((1.f - lx) * f00[i] + lx * f01[i]) + ly * ((1.f - lx) * f10[i] + lx * f11[i]);
+  store8(out + ((static_cast<int64_t>(b) * H + Y) * W + X) * out_rs + j * C + c, o);
 }
 
 // F.interpolate(mode='bilinear', align_corners=True)
@@ -550,9 +684,16 @@ extern "C" int gwd_layernorm(const void* x, int64_t x_rs, const void* res, int64
   GWD_CHECK_ARG(x && out && rows > 0, "gwd_layernorm: null pointer / empty");
   GWD_CHECK_ARG(GWD_ALIGN8(C) && C <= 2048 && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs) && GWD_ALIGN8(res_rs),
                 "gwd_layernorm: C and strides must be multiples of 8, C <= 2048");
-  GWD_ROW_DISPATCH(gwd_layernorm_kernel, C, static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), stream,
-                   static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(res), res_rs, gamma, beta, eps, act,
-      static_cast<bf16*>(out), out_rs, rows, C, n);
+  static const bool x2 = []() { const char* e = getenv("GWD_LN_X2"); return !e || atoi(e) != 0; }();
+  if (x2 && rows >= 32768 && slots_for(C) <= 2) {
+    GWD_ROW_DISPATCH(gwd_layernorm_x2_kernel, C, static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div((rows + 1) / 2, rows_per_warp(C)) * 32, 256)),
+                     stream, static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(res), res_rs, gamma, beta, eps, act,
+                     static_cast<bf16*>(out), out_rs, rows, C, n);
+  } else {
+    GWD_ROW_DISPATCH(gwd_layernorm_kernel, C, static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), stream,
+                     static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(res), res_rs, gamma, beta, eps, act,
+                     static_cast<bf16*>(out), out_rs, rows, C, n);
+  }
   GWD_LAUNCHED();
   return GWD_OK;
 }
@@ -634,6 +775,43 @@ extern "C" int gwd_avgpool(const void* x, int64_t x_rs, int32_t B, int32_t H, in
   GWD_CHECK_ARG(total > 0 && H / k <= 65535 && B <= 65535, "gwd_avgpool: bad extents");
   gwd_avgpool_kernel<<<dim3(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(W / k) * (C / 8), 256)), H / k, B), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, H, W, k,
                                                                static_cast<bf16*>(out), out_rs, C);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_avgpool_pyramid(const void* x, int64_t x_rs, int32_t B, int32_t H, int32_t W, void* o2, void* o4, void* o8,
+                                   void* o16, int32_t C, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(x && o2 && o4 && o8 && o16 && H >= 16 && W >= 16 && GWD_ALIGN8(C) && GWD_ALIGN8(x_rs), "gwd_avgpool_pyramid: bad argument");
+  const size_t smem = static_cast<size_t>(84) * C * sizeof(float);
+  GWD_CHECK_ARG(C > 0 && smem <= 200 * 1024 && B > 0 && B <= 65535 && (H + 15) / 16 <= 65535, "gwd_avgpool_pyramid: bad extents");
+  static size_t attr = 0;
+  if (smem > attr) {
+    GWD_CUDA(cudaFuncSetAttribute(gwd_avgpool_pyramid_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    attr = smem;
+  }
+  gwd_avgpool_pyramid_kernel<<<dim3((W + 15) / 16, (H + 15) / 16, B), 256, smem, stream>>>(
+      static_cast<const bf16*>(x), x_rs, H, W, static_cast<bf16*>(o2), static_cast<bf16*>(o4), static_cast<bf16*>(o8),
+      static_cast<bf16*>(o16), C);
+  GWD_LAUNCHED();
+  return GWD_OK;
+}
+
+extern "C" int gwd_bilinear_up4(const void* x0, const void* x1, const void* x2, const void* x3, const int32_t* hw, int32_t B,
+                                void* out, int64_t out_rs, int32_t H, int32_t W, int32_t C, void* stream_) {
+  GWD_STREAM;
+  GWD_CHECK_ARG(x0 && x1 && x2 && x3 && hw && out && GWD_ALIGN8(C) && GWD_ALIGN8(out_rs), "gwd_bilinear_up4: bad argument");
+  GWD_CHECK_ARG(B > 0 && H > 0 && W > 0 && H <= 65535 && B <= 65535, "gwd_bilinear_up4: bad extents");
+  Up4 u;
+  const void* xs[4] = {x0, x1, x2, x3};
+  for (int j = 0; j < 4; ++j) {
+    u.src[j] = static_cast<const bf16*>(xs[j]);
+    u.h[j] = hw[2 * j];
+    u.w[j] = hw[2 * j + 1];
+    GWD_CHECK_ARG(u.h[j] > 0 && u.w[j] > 0, "gwd_bilinear_up4: empty source");
+  }
+  gwd_bilinear_ac4_kernel<<<dim3(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(W) * 4 * (C / 8), 256)), H, B), 256, 0, stream>>>(
+      u, static_cast<bf16*>(out), out_rs, H, W, C);
   GWD_LAUNCHED();
   return GWD_OK;
 }

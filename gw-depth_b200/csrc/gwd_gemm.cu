@@ -147,11 +147,64 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-template <int N, typename P>
+// ---- CTA-pair (cta_group::2) forms: the two CTAs of a cluster run ONE M = 256 MMA, each holding its own 128 rows of A and HALF
+// of the B tile in shared memory, so every SM reads A + B/2 per MMA instead of A + B (the wide 3x3 convolutions are bound by
+// shared-memory bandwidth, not by the tensor pipe).  Only the leader (cluster rank 0) issues MMAs; both CTAs issue TMA loads that
+// complete on the LEADER's full barrier; MMA completion is multicast to both CTAs' empty / accumulator-full barriers.
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  // default semantics (.release.cta), as for the local arrive: the TMEM reads are ordered by tcgen05.fence::before_thread_sync; a
+  // .release.cluster here compiles to MEMBAR.ALL.GPU, i.e. waits for the tile's global stores (16 % of the kernel's stall samples)
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1,
+                                                int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(void* dst, const CUtensorMap* map, uint32_t bar_cluster_addr, int c0, int c1,
+                                                int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {   // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+template <int N, bool CTA2, typename P>
 __device__ __forceinline__ void issue_mmas(const P& p, uint32_t d_tmem, uint64_t adesc0, uint64_t bdesc0,
                                            uint32_t accumulate) {
 #pragma unroll
-  for (int i = 0; i < N; ++i) umma_bf16(d_tmem, adesc0 + p.a_tab[i], bdesc0 + p.b_tab[i], p.idesc, i > 0 ? 1u : accumulate);
+  for (int i = 0; i < N; ++i) {
+    if (CTA2) umma_bf16_2sm(d_tmem, adesc0 + p.a_tab[i], bdesc0 + p.b_tab[i], p.idesc, i > 0 ? 1u : accumulate);
+    else umma_bf16(d_tmem, adesc0 + p.a_tab[i], bdesc0 + p.b_tab[i], p.idesc, i > 0 ? 1u : accumulate);
+  }
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -282,7 +335,9 @@ __device__ __forceinline__ void store_bf16_16(__nv_bfloat16* dst, const float (&
 // in place (conflict-free: chunk ^ (row & 7)), and the result leaves by TMA store.  Ragged row / column tails are
 // clipped by the tensor maps.  A separate instantiation: the other epilogues do not carry this code (the kernel is
 // sensitive to its instruction footprint).
-template <int PRE_ACT, int POST_ACT, bool HAS_LN, bool TMAEP = false>
+// CTA2: the CTA-pair variant (see the cta_group::2 wrappers above).  The pair owns two consecutive M tiles of the same N tile (rank r
+// = M tile 2q + r; an odd tail gives rank 1 a ghost tile: its loads are zero-filled out-of-bounds boxes and its stores are masked).
+template <int PRE_ACT, int POST_ACT, bool HAS_LN, bool TMAEP = false, bool CTA2 = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap map_res,
@@ -302,12 +357,22 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2 * kMaxAcc + 1);
 
   float2* ln_stats = reinterpret_cast<float2*>(tmem_ptr + 4);
+  float* ln_gs = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ln_stats + 2 * 4 * 128) + 15) & ~uintptr_t(15));   // HAS_LN: [256] scale, [256] shift (16-byte aligned)
+  float* ln_bs = ln_gs + 256;
   uint64_t* ep_bar = reinterpret_cast<uint64_t*>(smem + p.stage_off);   // TMAEP: [16] one barrier per epilogue warp
   uint8_t* ep_stage = smem + p.stage_off + 1024;                        // TMAEP: [16][32 rows][128 B]   // [2][4 column groups][128 rows] partial (sum, sum of squares)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.m_tiles * p.n_tiles;
+  // work items: tiles, or (M-tile pair, N tile) for the CTA pair
+  const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+  const int q_first = CTA2 ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int q_step = CTA2 ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int total_q = CTA2 ? ((p.m_tiles + 1) >> 1) * p.n_tiles : total_tiles;
+  auto tile_of = [&](int q) -> int {
+    return CTA2 ? (2 * (q / p.n_tiles) + static_cast<int>(rank)) * p.n_tiles + q % p.n_tiles : q;
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
@@ -316,7 +381,8 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     }
     for (int a = 0; a < p.nacc; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], p.tile_split ? 4 : (blockDim.x >> 5) - 2);
+      // CTA pair: the epilogue warps of BOTH CTAs release the leader's barrier
+      mbar_init(&tmem_empty[a], (p.tile_split ? 4 : (blockDim.x >> 5) - 2) * (CTA2 ? 2 : 1));
     }
     mbar_init(w_bar, 1);
     if (TMAEP)
@@ -326,13 +392,28 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
-                 "r"(p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CTA2) {   // the same warp of both CTAs allocates the pair's columns
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                   "r"(p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)),
+                   "r"(p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+  }
+  if (HAS_LN) {
+    const int cnt = p.phase_n > 0 ? p.phase_n : p.Nt;
+    for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
+      ln_gs[i] = __ldg(p.ln_g + i);
+      ln_bs[i] = __ldg(p.ln_b + i);
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all();   // the peer's barriers are initialised before anything arrives on them remotely
+  else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -346,11 +427,26 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         for (int kc = 0; kc < p.kchunks; ++kc)
           tma_load_3d(smem_b + static_cast<size_t>(kc) * p.w_kc_bytes, &map_b, w_bar, kc * p.BK, 0, 0);
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        TileCoord t = decode_tile(p, tile);
+      for (int q = q_first; q < total_q; q += q_step) {
+        TileCoord t = decode_tile(p, tile_of(q));
         for (int kc = 0; kc < p.kchunks; ++kc) {
           for (int dx = 0; dx < p.ndx; ++dx) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
+            if (CTA2) {
+              // both CTAs' boxes complete on the leader's barrier, which expects the bytes of both; each CTA fetches its own
+              // 128 rows of A and its half of the B tile's rows
+              const uint32_t full_addr = mapa_u32(smem_u32(&full_bar[stage]), 0u);
+              if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (p.a_tx_bytes + p.b_tx_bytes));
+              tma_load_4d_2sm(smem_a + static_cast<size_t>(stage) * p.a_stage_bytes, &map_a, full_addr,
+                              p.x_coff + kc * p.BK, t.x0 + dx - p.pad, t.y0 - p.pad, t.b);
+              tma_load_3d_2sm(smem_b + static_cast<size_t>(stage) * p.b_stage_bytes, &map_b, full_addr,
+                              kc * p.BK, t.n0 + static_cast<int>(rank) * (p.Nt >> 1), dx * p.nsub);
+              if (++stage == p.stages) {
+                stage = 0;
+                phase ^= 1u;
+              }
+              continue;
+            }
             mbar_arrive_expect_tx(&full_bar[stage], p.a_tx_bytes + p.b_tx_bytes);
             tma_load_4d(smem_a + static_cast<size_t>(stage) * p.a_stage_bytes, &map_a, &full_bar[stage],
                         p.x_coff + kc * p.BK, t.x0 + dx - p.pad, t.y0 - p.pad, t.b);
@@ -369,7 +465,7 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     // ===================================== MMA issuer =======================================
     // elect.sync (not `lane == 0`): ptxas then knows exactly one thread runs this region and keeps the descriptors on
     // the uniform datapath; with a lane test every tcgen05.mma was wrapped in an R2UR waterfall loop (~100 clk each)
-    if (elect_one()) {
+    if ((!CTA2 || rank == 0) && elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -379,7 +475,7 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         mbar_wait(w_bar, 0);
         tcgen05_fence_after();
       }
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int q = q_first; q < total_q; q += q_step) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);
         tcgen05_fence_after();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc) * p.acc_stride;
@@ -403,24 +499,26 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           // which is the critical path of small-K tiles)
           // and branch-free: a branch between two MMAs makes ptxas re-materialise every uniform register
           switch (nmma) {
-            case 1: issue_mmas<1>(p, d_tmem, adesc0, bdesc0, accumulate); break;
-            case 2: issue_mmas<2>(p, d_tmem, adesc0, bdesc0, accumulate); break;
-            case 3: issue_mmas<3>(p, d_tmem, adesc0, bdesc0, accumulate); break;
-            case 4: issue_mmas<4>(p, d_tmem, adesc0, bdesc0, accumulate); break;
-            case 6: issue_mmas<6>(p, d_tmem, adesc0, bdesc0, accumulate); break;
-            case 9: issue_mmas<9>(p, d_tmem, adesc0, bdesc0, accumulate); break;
-            case 12: issue_mmas<12>(p, d_tmem, adesc0, bdesc0, accumulate); break;
-            case 18: issue_mmas<18>(p, d_tmem, adesc0, bdesc0, accumulate); break;
-            default: issue_mmas<36>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 1: issue_mmas<1, CTA2>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 2: issue_mmas<2, CTA2>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 3: issue_mmas<3, CTA2>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 4: issue_mmas<4, CTA2>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 6: issue_mmas<6, CTA2>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 9: issue_mmas<9, CTA2>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 12: issue_mmas<12, CTA2>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            case 18: issue_mmas<18, CTA2>(p, d_tmem, adesc0, bdesc0, accumulate); break;
+            default: issue_mmas<36, CTA2>(p, d_tmem, adesc0, bdesc0, accumulate); break;
           }
           accumulate = 1;
-          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
+          if (CTA2) umma_commit_2sm(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs retire
           if (++stage == p.stages) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+        if (CTA2) umma_commit_2sm(&tmem_full[acc]);
+        else umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
         if (++acc == p.nacc) {
           acc = 0;
           acc_phase ^= 1u;
@@ -444,15 +542,15 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
     const int c_begin = (nchunks * half + ngrp - 1) / ngrp;
     const int c_end = (nchunks * (half + 1) + ngrp - 1) / ngrp;
     int j = p.tile_split ? ew >> 2 : 0;
-    for (int tile = blockIdx.x + j * gridDim.x; tile < total_tiles; tile += j_step * gridDim.x, j += j_step) {
+    for (int q = q_first + j * q_step; q < total_q; q += j_step * q_step, j += j_step) {
       const int acc = j & acc_mask;
       const uint32_t acc_phase = (j >> acc_shift) & 1;
-      TileCoord t = decode_tile(p, tile);
+      TileCoord t = decode_tile(p, tile_of(q));
       RowCtx rc;
       {
         int py = t.y0 + row / p.TW;
         int px = t.x0 + row % p.TW;
-        rc.valid = (py < p.H) && (px < p.W);
+        rc.valid = (py < p.H) && (px < p.W) && (!CTA2 || t.b < p.B);   // t.b >= B: the ghost tile of an odd pair tail
         rc.pix = (static_cast<int64_t>(t.b) * p.H + py) * p.W + px;
         rc.b = t.b; rc.py = py; rc.px = px;
       }
@@ -474,7 +572,9 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
         __syncwarp();
       }
       uint4 rpre0 = make_uint4(0u, 0u, 0u, 0u), rpre1 = rpre0;
-      const bool res_pf = !TMAEP && !HAS_LN && p.res_mode != GWD_RES_NONE && rc.valid;
+      // (LayerNorm epilogues: only the residual that is added AFTER the norm; the one added before it enters the statistics pass
+      // through load_chunk)
+      const bool res_pf = !TMAEP && p.res_mode != GWD_RES_NONE && rc.valid && (!HAS_LN || p.res_mode == GWD_RES_AFTER);
       const __nv_bfloat16* res_row = p.res + rc.pix * p.res_cstride + p.res_coff + t.n0;
       if (res_pf && c_begin < c_end) {
         const bool after = p.res_mode == GWD_RES_AFTER;
@@ -547,7 +647,7 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           float v[16];
           load_chunk<PRE_ACT, !HAS_LN>(p, t_row + c * 16, n_base, rc, v);
           const uint4 rcur0 = rpre0, rcur1 = rpre1;
-          if (!HAS_LN && res_pf && c + 1 < my_end) {
+          if (res_pf && c + 1 < my_end) {
             const bool after = p.res_mode == GWD_RES_AFTER;
             rpre0 = rpre1 = make_uint4(0u, 0u, 0u, 0u);
             if (!after || n_base + 24 <= p.store_n) rpre0 = __ldg(reinterpret_cast<const uint4*>(res_row + (c + 1) * 16));
@@ -576,12 +676,14 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             opix = (static_cast<int64_t>(rc.b) * (2 * p.H) + 2 * rc.py + (phase >> 1)) * (2 * p.W) + 2 * rc.px + (phase & 1);
           }
           if (HAS_LN) {
-            const float4* gp = reinterpret_cast<const float4*>(p.ln_g + och);
-            const float4* bp = reinterpret_cast<const float4*>(p.ln_b + och);
             const float shift = -mean * rstd;   // (v - mean) * rstd * g + b as two FMAs
+            // scale / shift from the shared-memory copy made at kernel start (broadcast reads; the global loads here were the top
+            // stall of the LayerNorm epilogues)
+            const float4* gp = reinterpret_cast<const float4*>(ln_gs + och);
+            const float4* bp = reinterpret_cast<const float4*>(ln_bs + och);
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-              float4 g4 = __ldg(gp + i), b4 = __ldg(bp + i);
+              const float4 g4 = gp[i], b4 = bp[i];
               v[4 * i + 0] = fmaf(fmaf(v[4 * i + 0], rstd, shift), g4.x, b4.x);
               v[4 * i + 1] = fmaf(fmaf(v[4 * i + 1], rstd, shift), g4.y, b4.y);
               v[4 * i + 2] = fmaf(fmaf(v[4 * i + 2], rstd, shift), g4.z, b4.z);
@@ -605,18 +707,9 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
               add_bf16x8(v, *ep_p0);
               add_bf16x8(v + 8, *ep_p1);
             }
-          } else if (p.res_mode == GWD_RES_AFTER && rc.valid) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + rc.pix * p.res_cstride + p.res_coff + n_base);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (n_base + 8 * h + 8 <= p.store_n) {
-                uint4 u = __ldg(rp + h);
-                float2 f0 = gwd_unpack_bf16x2(u.x), f1 = gwd_unpack_bf16x2(u.y), f2 = gwd_unpack_bf16x2(u.z),
-                       f3 = gwd_unpack_bf16x2(u.w);
-                v[8 * h + 0] += f0.x; v[8 * h + 1] += f0.y; v[8 * h + 2] += f1.x; v[8 * h + 3] += f1.y;
-                v[8 * h + 4] += f2.x; v[8 * h + 5] += f2.y; v[8 * h + 6] += f3.x; v[8 * h + 7] += f3.y;
-              }
-            }
+          } else if (res_pf) {   // LayerNorm, residual added after it: the pieces were prefetched (zeros beyond store_n)
+            add_bf16x8(v, rcur0);
+            add_bf16x8(v + 8, rcur1);
           }
           // channels beyond the logical width are padding: keep them exactly zero
           if (n_base + 16 > p.n) {
@@ -647,7 +740,10 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       // release the accumulator (all TMEM reads of this tile are done)
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) {
+        if (CTA2) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0u));
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       if (TMAEP) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA engine
         __syncwarp();
@@ -661,11 +757,15 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CTA2) cluster_sync_all();   // neither CTA leaves (or frees the pair's columns) while the other still works
+  else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols)
-                 : "memory");
+    if (CTA2)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(p.tmem_cols)
+                   : "memory");
   }
 }
 
@@ -806,6 +906,16 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
       }
     }
   }
+  // CTA pair (cta_group::2, see the kernel): streamed-weight 3x3 convolutions with enough M tiles.  Per stage an SM then holds its
+  // own activation box and HALF of the weight box, and every MMA reads A + B/2 from shared memory instead of A + B: at N = 160,
+  // K chunk 32 that is 133 instead of 195 bytes per clock of shared-memory traffic (TMA writes + MMA reads) against 128 B/clk.
+  static const bool cta2_enabled = []() { const char* e = getenv("GWD_GEMM_CTA2"); return !(e && e[0] == '0'); }();
+  // (measured on 16 x 120 x 160 maps: 800->320 1 217 -> 1 014 us = 1.40 PFLOP/s; 160->160 unchanged; 64->128 and 64->256, whose tiles
+  // carry few MMAs per epilogue, 20-25 % SLOWER: the pair couples the two CTAs' epilogues) -> long reductions only
+  static const int cta2_min_k = []() { const char* e = getenv("GWD_GEMM_CTA2_MIN_K"); return e ? atoi(e) : 0; }();
+  const bool cta2 = cta2_enabled && conv && !p.resident && !d->w_per_image && ctas == 1 && p.m_tiles >= 2 * gwd_num_sms() &&
+                    (p.Nt / 2) % 8 == 0 && p.Nt >= 64 && d->taps * d->cin >= cta2_min_k;
+  const int Nb = cta2 ? p.Nt / 2 : p.Nt;      // rows of the B tile one CTA holds
   const uint32_t budget = ctas == 2 ? 104 * 1024 : 200 * 1024;
   uint32_t w_region = 0;
   if (p.resident) {
@@ -821,7 +931,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   } else {
     while (true) {
       p.a_tx_bytes = static_cast<uint32_t>(a_rows) * p.BK * 2;
-      p.b_tx_bytes = static_cast<uint32_t>(p.nsub) * p.Nt * p.BK * 2;
+      p.b_tx_bytes = static_cast<uint32_t>(p.nsub) * Nb * p.BK * 2;
       p.a_stage_bytes = round1k(p.a_tx_bytes);
       p.b_stage_bytes = round1k(p.b_tx_bytes);
       if ((p.a_stage_bytes + p.b_stage_bytes) * 3 <= budget || p.BK == 16) break;
@@ -843,7 +953,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
     } else {
       p.a_off[sub] = static_cast<uint32_t>(sub) * p.TW * row_bytes;   // dy shift of TW rows
     }
-    p.b_off[sub] = static_cast<uint32_t>(sub) * p.Nt * row_bytes;
+    p.b_off[sub] = static_cast<uint32_t>(sub) * Nb * row_bytes;
   }
   {
     const int ks = p.BK / 16;
@@ -854,7 +964,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   }
   // instruction descriptor: D=f32 (bits 4-5 = 1), A=B=bf16 (bits 7-9, 10-12 = 1), K-major both, N>>3 @17, M>>4 @24
   p.idesc = (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(p.Nt >> 3) << 17) |
-            (static_cast<uint32_t>(kTileM >> 4) << 24);
+            (static_cast<uint32_t>((cta2 ? 2 * kTileM : kTileM) >> 4) << 24);
   // Epilogue organisation.  Column split (the 4-warp groups share each tile): lowest latency for one tile, right for
   // wide plain tiles and for launches with about one tile per CTA.  Tile split (each group drains whole tiles on its
   // own TMEM accumulators): narrow tiles (no columns to share) and LayerNorm epilogues (whose statistics pass would be
@@ -929,7 +1039,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
     cuuint64_t gdim[3] = {static_cast<cuuint64_t>(d->cin), static_cast<cuuint64_t>(d->n_pad),
                           static_cast<cuuint64_t>(d->taps) * (d->w_per_image ? d->B : 1)};
     cuuint64_t gstr[2] = {static_cast<cuuint64_t>(d->cin) * 2, static_cast<cuuint64_t>(d->n_pad) * d->cin * 2};
-    cuuint32_t box[3] = {static_cast<cuuint32_t>(p.BK), static_cast<cuuint32_t>(p.Nt),
+    cuuint32_t box[3] = {static_cast<cuuint32_t>(p.BK), static_cast<cuuint32_t>(Nb),
                          static_cast<cuuint32_t>(p.resident ? d->taps : p.nsub)};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(d->w), gdim, gstr, box, estr,
@@ -942,7 +1052,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   }
 
   const size_t bar_bytes =
-      ((2 * kMaxStages + 2 * kMaxAcc + 1) * sizeof(uint64_t) + 16 + (has_ln ? 2 * 4 * 128 * sizeof(float2) : 0) + 127) & ~size_t(127);
+      ((2 * kMaxStages + 2 * kMaxAcc + 1) * sizeof(uint64_t) + 16 + (has_ln ? 2 * 4 * 128 * sizeof(float2) + 512 * sizeof(float) + 16 : 0) + 127) & ~size_t(127);
   // TMA epilogue (see the kernel): plain dense [rows, N] Linears whose epilogue warps own 64 columns each
   CUtensorMap map_res, map_y;
   memset(&map_res, 0, sizeof(map_res));
@@ -1008,6 +1118,12 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   const int total_tiles = p.m_tiles * p.n_tiles;
   int grid = ctas * gwd_num_sms();
   if (grid > total_tiles) grid = total_tiles;
+  if (cta2) {   // one CTA pair per two SMs
+    const int pairs_all = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    int pairs = gwd_num_sms() / 2;
+    if (pairs > pairs_all) pairs = pairs_all;
+    grid = 2 * pairs;
+  }
 #define GWD_GEMM_CASE_TMAEP(POST)                                                                             \
   if (tma_ep && d->post_act == POST) {                                                                        \
     static bool attr_set = false;                                                                             \
@@ -1020,7 +1136,23 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
     launched = true;                                                                                          \
   }
 #define GWD_GEMM_CASE(PRE, POST, LN)                                                                          \
-  if (d->pre_act == PRE && d->post_act == POST && has_ln == LN) {                                             \
+  if (d->pre_act == PRE && d->post_act == POST && has_ln == LN && cta2) {                                     \
+    auto kfn = gwd_tapgemm_kernel<PRE, POST, LN, false, true>;                                                \
+    static bool attr_set = false;                                                                             \
+    if (!attr_set) {                                                                                          \
+      GWD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));           \
+      attr_set = true;                                                                                        \
+    }                                                                                                         \
+    cudaLaunchConfig_t cfg;                                                                                   \
+    memset(&cfg, 0, sizeof(cfg));                                                                             \
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream; \
+    cudaLaunchAttribute at[1];                                                                                \
+    at[0].id = cudaLaunchAttributeClusterDimension;                                                           \
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                       \
+    cfg.attrs = at; cfg.numAttrs = 1;                                                                         \
+    GWD_CUDA(cudaLaunchKernelEx(&cfg, kfn, map_a, map_b, p, map_res, map_y));                                 \
+    launched = true;                                                                                          \
+  } else if (d->pre_act == PRE && d->post_act == POST && has_ln == LN) {                                      \
     static bool attr_set = false;                                                                             \
     if (!attr_set) {                                                                                          \
       GWD_CUDA(cudaFuncSetAttribute(gwd_tapgemm_kernel<PRE, POST, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, \

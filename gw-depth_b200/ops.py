@@ -327,6 +327,27 @@ def avgpool(x, k, C=None):
     return out
 
 
+def avgpool_pyramid(x, C=None):
+    """AvgPool2d(k, k) of the first C channels of x [B,H,W,Cx] for k = 16, 8, 4, 2 in one pass -> [p16, p8, p4, p2]"""
+    B, H, W, Cx = x.shape
+    C = C or Cx
+    outs = [torch.empty(B, H // k, W // k, C, dtype=torch.bfloat16, device=x.device) for k in (16, 8, 4, 2)]
+    capi.check(_L().gwd_avgpool_pyramid(_ptr(x), Cx, B, H, W, _ptr(outs[3]), _ptr(outs[2]), _ptr(outs[1]), _ptr(outs[0]), C, _stream()),
+               "gwd_avgpool_pyramid")
+    return outs
+
+
+def bilinear_up4_into(xs, out, y_coff, H, W):
+    """bilinear_up_into of four contiguous maps x_j [B,h_j,w_j,C] into the adjacent slices [y_coff + j*C, y_coff + (j+1)*C) of out"""
+    B, _, _, C = xs[0].shape
+    assert len(xs) == 4 and all(x.is_contiguous() and x.shape[0] == B and x.shape[3] == C for x in xs)
+    hw = (ctypes.c_int32 * 8)(*[v for x in xs for v in x.shape[1:3]])
+    dst = ctypes.c_void_p(out.data_ptr() + y_coff * 2)
+    capi.check(_L().gwd_bilinear_up4(_ptr(xs[0]), _ptr(xs[1]), _ptr(xs[2]), _ptr(xs[3]), hw, B, dst, out.shape[-1], H, W, C, _stream()),
+               "gwd_bilinear_up4")
+    return out
+
+
 def bilinear_up_into(x, out, y_coff, H, W):
     """align_corners=True bilinear resize of x [B,h,w,C] into channels [y_coff, y_coff+C) of out [B,H,W,Ctot]"""
     B, h, w, C = x.shape

@@ -81,11 +81,12 @@ class Pyramid(FlatModule):
             tp["blocks"].append((x, z1, y, z2))
             x = xn
         tp["branches"] = []
-        for j, (pool, br) in enumerate(zip(POOLS, self.branches), start=1):
-            pooled = ops.avgpool(cat, pool, C=C2p)
+        ups = []
+        for pooled, br in zip(ops.avgpool_pyramid(cat, C=C2p), self.branches):        # POOLS order (16, 8, 4, 2), one pass
             b, zb = self._conv_ln(pooled, br, ACT_GELU)
-            ops.bilinear_up_into(b, cat, j * C2p, H, W)
+            ups.append(b)
             tp["branches"].append((pooled, zb))
+        ops.bilinear_up4_into(ups, cat, C2p, H, W)
         cv, ln = self.last0
         if cv.n_pad <= 256:
             y, z = self._conv_ln(cat, self.last0, ACT_GELU)

@@ -178,6 +178,14 @@ int gwd_upsample_nearest(const void* x, int64_t x_rs, int32_t B, int32_t h, int3
 /* nn.AvgPool2d(k, stride=k)  (points_sample.py:61-75) */
 int gwd_avgpool(const void* x, int64_t x_rs, int32_t B, int32_t H, int32_t W, int32_t k, void* out, int64_t out_rs,
                 int32_t C, void* stream);
+/* The four pooling branches of PyramidLayer (nn.AvgPool2d(k, k) for k = 2, 4, 8, 16, points_sample.py:61-75,115-121) in one pass
+ * over x [B,H,W,C] (row stride x_rs): o2 / o4 / o8 / o16 = contiguous bf16 [B, H/k, W/k, C], floor mode; H, W >= 16. */
+int gwd_avgpool_pyramid(const void* x, int64_t x_rs, int32_t B, int32_t H, int32_t W, void* o2, void* o4, void* o8, void* o16,
+                        int32_t C, void* stream);
+/* gwd_bilinear_up of four contiguous maps x_j [B, hw[2j], hw[2j+1], C] (hw: HOST array of 8) into the adjacent channel slices
+ * [j*C, (j+1)*C) of out (row stride out_rs, already offset to the first slice): the PyramidLayer concat, points_sample.py:115-121 */
+int gwd_bilinear_up4(const void* x0, const void* x1, const void* x2, const void* x3, const int32_t* hw, int32_t B, void* out,
+                     int64_t out_rs, int32_t H, int32_t W, int32_t C, void* stream);
 /* F.interpolate(mode='bilinear', align_corners=True)  (points_sample.py:115-121) */
 int gwd_bilinear_up(const void* x, int64_t x_rs, int32_t B, int32_t h, int32_t w, void* out, int64_t out_rs, int32_t H,
                     int32_t W, int32_t C, void* stream);

@@ -102,6 +102,11 @@ CONV_CASES = [
     # >= 592 M tiles, filter too large to stay resident
     (4, 120, 160, 160, 160, 0, 2, 0, True),
     (7, 97, 100, 80, 160, 0, 0, 0, False),    # 637 M tiles (odd), ragged borders
+    # CTA-pair path (cta_group::2: >= 296 M tiles, streamed weights): LayerNorm + residual, two N tiles, an odd tile count whose
+    # last pair has a ghost tile, the 64-byte-swizzle K chunk (C = 32 * odd)
+    (4, 120, 160, 160, 160, 0, 0, 2, True),
+    (8, 64, 80, 64, 320, 0, 3, 0, False),
+    (3, 125, 103, 96, 192, 0, 2, 1, False),
 ]
 
 

@@ -200,6 +200,33 @@ def test_resampling():
     assert (out[..., :C] == 0).all() and (out[..., 2 * C:] == 0).all()
 
 
+@pytest.mark.parametrize("H,W,C", [(33, 47, 64), (120, 160, 160), (60, 80, 168), (16, 16, 8)])
+def test_pyramid_pool_and_upsample(H, W, C):
+    """the one-pass pooling pyramid (k = 16, 8, 4, 2) == the per-k kernel (k = 2 bit for bit, the tree-summed levels to the bf16
+    rounding of an fp32 re-association) == F.avg_pool2d; the four-branch bilinear up-sampling == four gwd_bilinear_up launches bit
+    for bit.  Extents include blocks cut by the border and channel counts that are not a multiple of 32"""
+    ops = _ops()
+    g = _g(H + C)
+    B = 2
+    big = _bf(torch.randn(B, H, W, C + 16, generator=g)).cuda()     # pooled channels are a slice of a wider buffer
+    pyr = ops.avgpool_pyramid(big, C=C)
+    for k, got in zip((16, 8, 4, 2), pyr):
+        ref = F.avg_pool2d(big[..., :C].float().permute(0, 3, 1, 2), k, k).permute(0, 2, 3, 1)
+        assert tuple(got.shape) == tuple(ref.shape)
+        close(got, ref, 4e-3, "pyramid pool %d" % k)
+        one = ops.avgpool(big, k, C=C)
+        if k == 2:
+            assert torch.equal(got, one)
+        else:
+            close(got, one, 4e-3, "pyramid pool %d vs single" % k)
+    out = torch.zeros(B, H, W, 5 * C + 8, dtype=torch.bfloat16, device="cuda")
+    ref = torch.zeros_like(out)
+    ops.bilinear_up4_into(pyr, out, C, H, W)
+    for j, p_ in enumerate(pyr, start=1):
+        ops.bilinear_up_into(p_, ref, j * C, H, W)
+    assert torch.equal(out, ref)
+
+
 def test_point_sampling_and_mixture():
     ops = _ops()
     g = _g(4)

@@ -41,6 +41,18 @@ def main(which):
         g, bt = torch.ones(64, device=dev), torch.zeros(64, device=dev)
         us = timeit(lambda: ops.window_gather(x.view(16, 120, 160, 64), 16, 120, 160, 7, 3, g, bt))
         print("window_gather 1/4 C=64    %8.1f us  %.2f TB/s" % (us, 2 * x.numel() * 2 / us / 1e6))
+    if "pyr" in which:
+        B, H, W, C = 16, 120, 160, 160
+        cat = torch.randn(B, H, W, 5 * C, device=dev).bfloat16()
+        us = timeit(lambda: [ops.avgpool(cat, k, C=C) for k in (16, 8, 4, 2)])
+        print("avgpool x4 (16,8,4,2)      %8.1f us" % us)
+        us = timeit(lambda: ops.avgpool_pyramid(cat, C=C))
+        print("avgpool_pyramid            %8.1f us  %.2f TB/s" % (us, B * H * W * C * 2 / us / 1e6))
+        pyr = ops.avgpool_pyramid(cat, C=C)
+        us = timeit(lambda: [ops.bilinear_up_into(p_, cat, j * C, H, W) for j, p_ in enumerate(pyr, start=1)])
+        print("bilinear_up x4             %8.1f us" % us)
+        us = timeit(lambda: ops.bilinear_up4_into(pyr, cat, C, H, W))
+        print("bilinear_up4               %8.1f us  %.2f TB/s" % (us, B * H * W * 4 * C * 2 / us / 1e6))
     if "attn" in which:
         B, L, E = 16, 300, 256
         qk = torch.randn(B * L, 2 * E, device=dev).bfloat16()
@@ -52,4 +64,4 @@ def main(which):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1:] or ["diffuse", "ln", "attn"])
+    main(sys.argv[1:] or ["diffuse", "ln", "pyr", "attn"])
