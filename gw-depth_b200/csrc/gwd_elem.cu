@@ -160,31 +160,25 @@ __global__ void gwd_layernorm_kernel(const bf16* x, int64_t x_rs, const bf16* re
   if (live) row_store(r, out + row * out_rs, C, rg);
 }
 
-// the same with TWO rows per lane group in flight (both rows' loads are issued before either row's reduction): on big maps the
-// one-row kernel is bound by the load -> shuffle-reduce -> store latency chain of its single row, not by HBM
+// the same for row widths that fill the power-of-two lane groups badly (C = 320: 40 vectors on 32 lanes x 2 slots = 37 % idle lanes,
+// and the kernel is bound by instruction issue, not by HBM): groups of 8 lanes x NV = C / 64 slots, four rows per warp, no idle lane
 template <int NV>
-__global__ void gwd_layernorm_x2_kernel(const bf16* x, int64_t x_rs, const bf16* res, int64_t res_rs, const float* g,
+__global__ void gwd_layernorm_g8_kernel(const bf16* x, int64_t x_rs, const bf16* res, int64_t res_rs, const float* g,
                                         const float* b, float eps, int act, bf16* out, int64_t out_rs, int64_t rows, int C,
                                         int n) {
-  RowGroup rg = row_group(C);
-  const int64_t r0 = rg.row * 2, r1 = r0 + 1;
-  const bool l0 = r0 < rows, l1 = r1 < rows;
-  const int64_t a0 = l0 ? r0 : 0, a1 = l1 ? r1 : 0;
-  WarpRow<NV> ra, rb;
-  row_load(ra, x + a0 * x_rs, C, rg, l0);
-  row_load(rb, x + a1 * x_rs, C, rg, l1);
-  if (res) {
-    if (l0) row_add(ra, res + a0 * res_rs, C, rg);
-    if (l1) row_add(rb, res + a1 * res_rs, C, rg);
-  }
-  if (g) {
-    row_layernorm(ra, C, n, rg, g, b, eps);
-    row_layernorm(rb, C, n, rg, g, b, eps);
-  }
-  row_act(ra, act, C, rg);
-  row_act(rb, act, C, rg);
-  if (l0) row_store(ra, out + a0 * out_rs, C, rg);
-  if (l1) row_store(rb, out + a1 * out_rs, C, rg);
+  RowGroup rg;
+  const int lane = threadIdx.x & 31;
+  rg.G = 8;
+  rg.sub = lane & 7;
+  rg.row = ((blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5) * 4 + (lane >> 3);
+  bool live = rg.row < rows;
+  int64_t row = live ? rg.row : 0;
+  WarpRow<NV> r;
+  row_load(r, x + row * x_rs, C, rg, live);
+  if (res && live) row_add(r, res + row * res_rs, C, rg);
+  if (g) row_layernorm(r, C, n, rg, g, b, eps);
+  row_act(r, act, C, rg);
+  if (live) row_store(r, out + row * out_rs, C, rg);
 }
 
 // out[row] = x[row] + addend[row % period]
@@ -206,28 +200,21 @@ __global__ void gwd_add_rows_kernel(const bf16* x, int64_t x_rs, const bf16* add
 struct WinGeom {
   int B, H, W, Hp, Wp, ws, shift;
 };
-__device__ __forceinline__ bool win_source(const WinGeom& gm, int64_t orow, int& b, int& y, int& x) {
-  int N = gm.ws * gm.ws;
-  int nWx = gm.Wp / gm.ws, nWy = gm.Hp / gm.ws;
-  int t = orow % N;
-  int64_t wi = orow / N;
-  int w = wi % (nWx * nWy);
-  b = wi / (nWx * nWy);
-  int ys = (w / nWx) * gm.ws + t / gm.ws;
-  int xs = (w % nWx) * gm.ws + t % gm.ws;
-  y = (ys + gm.shift) % gm.Hp;
-  x = (xs + gm.shift) % gm.Wp;
-  return y < gm.H && x < gm.W;
-}
+// grid (row groups of one map row, padded map rows, images): the window arithmetic is one 32-bit division per thread (a linear row
+// index decoded with 64-bit div / mod chains cost ~500 instructions per 16-byte vector and capped these kernels at 1.5 TB/s)
 template <int NV>
 __global__ void gwd_window_gather_kernel(const bf16* x, int64_t x_rs, const float* g, const float* b, float eps, bf16* out,
                                          int64_t out_rs, WinGeom gm, int C, int n) {
   RowGroup rg = row_group(C);
-  int64_t rows = static_cast<int64_t>(gm.B) * gm.Hp * gm.Wp;
-  bool live = rg.row < rows;
-  int64_t orow = live ? rg.row : 0;
-  int bb, y, xx;
-  bool valid = win_source(gm, orow, bb, y, xx) && live;
+  const int xs = static_cast<int>(rg.row), ys = blockIdx.y, bb = blockIdx.z;     // position on the shifted, padded map
+  const bool live = xs < gm.Wp;
+  const int nWx = gm.Wp / gm.ws, nWy = gm.Hp / gm.ws;
+  const int wy = ys / gm.ws, wx = xs / gm.ws;
+  const int64_t orow = ((static_cast<int64_t>(bb) * nWy + wy) * nWx + wx) * (gm.ws * gm.ws) + (ys - wy * gm.ws) * gm.ws + (xs - wx * gm.ws);
+  int y = ys + gm.shift, xx = xs + gm.shift;
+  if (y >= gm.Hp) y -= gm.Hp;
+  if (xx >= gm.Wp) xx -= gm.Wp;
+  const bool valid = live && y < gm.H && xx < gm.W;
   WarpRow<NV> r;
   row_load(r, x + ((static_cast<int64_t>(bb) * gm.H + (valid ? y : 0)) * gm.W + (valid ? xx : 0)) * x_rs, C, rg, valid);
   if (g) row_layernorm(r, C, n, rg, g, b, eps);
@@ -241,21 +228,22 @@ __global__ void gwd_window_gather_kernel(const bf16* x, int64_t x_rs, const floa
 }
 
 // Swin window merge: y[b,y,x] = shortcut[b,y,x] + win[row(b,y,x)]; optionally y_ln = LN(y)   (:731-755)
+// grid (row groups of one map row, map rows, images).  (Several positions per lane group with their loads issued together were
+// measured: 4 % slower on the whole forward -- these kernels are not bound by load latency.)
 template <int NV>
 __global__ void gwd_window_merge_kernel(const bf16* win, int64_t win_rs, const bf16* shortcut, int64_t sc_rs, bf16* out,
                                         int64_t out_rs, const float* g, const float* b, float eps, bf16* out_ln,
                                         int64_t ln_rs, WinGeom gm, int C, int n) {
   RowGroup rg = row_group(C);
-  int64_t rows = static_cast<int64_t>(gm.B) * gm.H * gm.W;
-  bool live = rg.row < rows;
-  int64_t pix = live ? rg.row : 0;
-  int x = pix % gm.W;
-  int y = (pix / gm.W) % gm.H;
-  int bb = pix / (static_cast<int64_t>(gm.W) * gm.H);
-  int ys = (y - gm.shift + gm.Hp) % gm.Hp, xs = (x - gm.shift + gm.Wp) % gm.Wp;
-  int nWx = gm.Wp / gm.ws, nWy = gm.Hp / gm.ws;
-  int64_t wrow = ((static_cast<int64_t>(bb) * nWy + ys / gm.ws) * nWx + xs / gm.ws) * (gm.ws * gm.ws) +
-                 (ys % gm.ws) * gm.ws + xs % gm.ws;
+  const int x = static_cast<int>(rg.row), y = blockIdx.y, bb = blockIdx.z;
+  const bool live = x < gm.W;
+  const int64_t pix = (static_cast<int64_t>(bb) * gm.H + y) * gm.W + (live ? x : 0);
+  int ys = y - gm.shift, xs = (live ? x : 0) - gm.shift;
+  if (ys < 0) ys += gm.Hp;
+  if (xs < 0) xs += gm.Wp;
+  const int nWx = gm.Wp / gm.ws, nWy = gm.Hp / gm.ws;
+  const int wy = ys / gm.ws, wx = xs / gm.ws;
+  const int64_t wrow = ((static_cast<int64_t>(bb) * nWy + wy) * nWx + wx) * (gm.ws * gm.ws) + (ys - wy * gm.ws) * gm.ws + (xs - wx * gm.ws);
   WarpRow<NV> r;
   row_load(r, win + wrow * win_rs, C, rg, live);
   if (live) {
@@ -400,11 +388,13 @@ struct Up4 {
 };
 __global__ void __launch_bounds__(256)
 gwd_bilinear_ac4_kernel(const Up4 u, bf16* __restrict__ out, int64_t out_rs, int H, int W, int C) {
+  // four lanes per (pixel, branch): the source coordinates and weights are computed once and shared by the lanes' C / 32 vectors each
+  // (this kernel is bound by instruction issue: 89 instructions per 16-byte vector at HBM speed is the budget on this part)
   const int cv = C / 8;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= W * 4 * cv) return;
-  const int X = t / (4 * cv), r = t - X * 4 * cv;
-  const int j = r / cv, c = (r - j * cv) * 8;
+  const int pb = t >> 2, q = t & 3;
+  if (pb >= W * 4) return;
+  const int X = pb >> 2, j = pb & 3;
   const int Y = blockIdx.y, b = blockIdx.z;
   const int h = u.h[j], w = u.w[j];
   const float ry = (H > 1) ? static_cast<float>(h - 1) / (H - 1) : 0.f;
@@ -413,16 +403,24 @@ gwd_bilinear_ac4_kernel(const Up4 u, bf16* __restrict__ out, int64_t out_rs, int
   const int y0 = static_cast<int>(fy), x0 = static_cast<int>(fx);
   const int y1 = min(y0 + 1, h - 1), x1 = min(x0 + 1, w - 1);
   const float ly = fy - y0, lx = fx - x0;
-  const bf16* base = u.src[j] + static_cast<int64_t>(b) * h * w * C + c;
-  float f00[8], f01[8], f10[8], f11[8], o[8];
-  load8(base + (static_cast<int64_t>(y0) * w + x0) * C, f00);
-  load8(base + (static_cast<int64_t>(y0) * w + x1) * C, f01);
-  load8(base + (static_cast<int64_t>(y1) * w + x0) * C, f10);
-  load8(base + (static_cast<int64_t>(y1) * w + x1) * C, f11);
+  const bf16* base = u.src[j] + static_cast<int64_t>(b) * h * w * C;
+  const bf16* p00 = base + (static_cast<int64_t>(y0) * w + x0) * C;
+  const bf16* p01 = base + (static_cast<int64_t>(y0) * w + x1) * C;
+  const bf16* p10 = base + (static_cast<int64_t>(y1) * w + x0) * C;
+  const bf16* p11 = base + (static_cast<int64_t>(y1) * w + x1) * C;
+  bf16* dst = out + ((static_cast<int64_t>(b) * H + Y) * W + X) * out_rs + j * C;
+  for (int v = q; v < cv; v += 4) {
+    const int c = v * 8;
+    float f00[8], f01[8], f10[8], f11[8], o[8];
+    load8(p00 + c, f00);
+    load8(p01 + c, f01);
+    load8(p10 + c, f10);
+    load8(p11 + c, f11);
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
-    o[i] = (1.f - ly) * ((1.f - lx) * f00[i] + lx * f01[i]) + ly * ((1.f - lx) * f10[i] + lx * f11[i]);
-  store8(out + ((static_cast<int64_t>(b) * H + Y) * W + X) * out_rs + j * C + c, o);
+    for (int i = 0; i < 8; ++i)     // the expression of gwd_bilinear_ac_kernel, bit for bit
+      o[i] = (1.f - ly) * ((1.f - lx) * f00[i] + lx * f01[i]) + ly * ((1.f - lx) * f10[i] + lx * f11[i]);
+    store8(dst + c, o);
+  }
 }
 
 // F.interpolate(mode='bilinear', align_corners=True)
@@ -684,11 +682,17 @@ extern "C" int gwd_layernorm(const void* x, int64_t x_rs, const void* res, int64
   GWD_CHECK_ARG(x && out && rows > 0, "gwd_layernorm: null pointer / empty");
   GWD_CHECK_ARG(GWD_ALIGN8(C) && C <= 2048 && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs) && GWD_ALIGN8(res_rs),
                 "gwd_layernorm: C and strides must be multiples of 8, C <= 2048");
-  static const bool x2 = []() { const char* e = getenv("GWD_LN_X2"); return !e || atoi(e) != 0; }();
-  if (x2 && rows >= 32768 && slots_for(C) <= 2) {
-    GWD_ROW_DISPATCH(gwd_layernorm_x2_kernel, C, static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div((rows + 1) / 2, rows_per_warp(C)) * 32, 256)),
-                     stream, static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(res), res_rs, gamma, beta, eps, act,
-                     static_cast<bf16*>(out), out_rs, rows, C, n);
+  const int nv64 = C % 64 == 0 ? C / 64 : 0;
+  if (nv64 == 3 || nv64 == 5 || nv64 == 6 || nv64 == 7) {
+    const unsigned grid = static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, 4) * 32, 256));
+#define GWD_LN_G8(NV)                                                                                                  \
+  gwd_layernorm_g8_kernel<NV><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(res), res_rs, \
+                                                        gamma, beta, eps, act, static_cast<bf16*>(out), out_rs, rows, C, n)
+    if (nv64 == 3) GWD_LN_G8(3);
+    else if (nv64 == 5) GWD_LN_G8(5);
+    else if (nv64 == 6) GWD_LN_G8(6);
+    else GWD_LN_G8(7);
+#undef GWD_LN_G8
   } else {
     GWD_ROW_DISPATCH(gwd_layernorm_kernel, C, static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), stream,
                      static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(res), res_rs, gamma, beta, eps, act,
@@ -726,8 +730,9 @@ extern "C" int gwd_window_gather(const void* x, int64_t x_rs, const float* gamma
   GWD_CHECK_ARG(GWD_ALIGN8(C) && C <= 2048 && GWD_ALIGN8(x_rs) && GWD_ALIGN8(out_rs), "gwd_window_gather: alignment");
   WinGeom gm;
   make_geom(gm, B, H, W, ws, shift);
-  int64_t rows = static_cast<int64_t>(B) * gm.Hp * gm.Wp;
-  GWD_ROW_DISPATCH(gwd_window_gather_kernel, C, static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), stream,
+  GWD_CHECK_ARG(B > 0 && B <= 65535 && gm.Hp <= 65535, "gwd_window_gather: bad extents");
+  const dim3 grid(static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(gm.Wp, rows_per_warp(C)) * 32, 256)), gm.Hp, B);
+  GWD_ROW_DISPATCH(gwd_window_gather_kernel, C, grid, stream,
                    static_cast<const bf16*>(x), x_rs, gamma, beta, eps, static_cast<bf16*>(out), out_rs, gm, C, n);
   GWD_LAUNCHED();
   return GWD_OK;
@@ -744,8 +749,9 @@ extern "C" int gwd_window_merge(const void* win, int64_t win_rs, const void* sho
                 "gwd_window_merge: alignment");
   WinGeom gm;
   make_geom(gm, B, H, W, ws, shift);
-  int64_t rows = static_cast<int64_t>(B) * H * W;
-  GWD_ROW_DISPATCH(gwd_window_merge_kernel, C, static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, rows_per_warp(C)) * 32, 256)), stream,
+  GWD_CHECK_ARG(B > 0 && B <= 65535 && H <= 65535, "gwd_window_merge: bad extents");
+  const dim3 grid(static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(W, rows_per_warp(C)) * 32, 256)), H, B);
+  GWD_ROW_DISPATCH(gwd_window_merge_kernel, C, grid, stream,
                    static_cast<const bf16*>(win), win_rs, static_cast<const bf16*>(shortcut), sc_rs, static_cast<bf16*>(out), out_rs,
       gamma, beta, eps, static_cast<bf16*>(out_ln), ln_rs, gm, C, n);
   GWD_LAUNCHED();
@@ -810,7 +816,7 @@ extern "C" int gwd_bilinear_up4(const void* x0, const void* x1, const void* x2, 
     u.w[j] = hw[2 * j + 1];
     GWD_CHECK_ARG(u.h[j] > 0 && u.w[j] > 0, "gwd_bilinear_up4: empty source");
   }
-  gwd_bilinear_ac4_kernel<<<dim3(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(W) * 4 * (C / 8), 256)), H, B), 256, 0, stream>>>(
+  gwd_bilinear_ac4_kernel<<<dim3(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(W) * 16, 256)), H, B), 256, 0, stream>>>(
       u, static_cast<bf16*>(out), out_rs, H, W, C);
   GWD_LAUNCHED();
   return GWD_OK;

@@ -143,7 +143,7 @@ def test_line_requery_chain():
 
 
 # ------------------------------------------------------------------------------------------ bandwidth kernels
-@pytest.mark.parametrize("rows,C,n", [(1000, 256, 256), (777, 64, 64), (513, 320, 320), (300, 128, 120), (64, 512, 512), (99, 80, 80)])
+@pytest.mark.parametrize("rows,C,n", [(1000, 256, 256), (777, 64, 64), (513, 320, 320), (300, 128, 120), (64, 512, 512), (99, 80, 80), (1001, 192, 190), (35, 448, 448), (130, 384, 384)])
 def test_layernorm_and_add(rows, C, n):
     ops = _ops()
     g = _g(rows + C)

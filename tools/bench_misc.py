@@ -41,6 +41,9 @@ def main(which):
         g, bt = torch.ones(64, device=dev), torch.zeros(64, device=dev)
         us = timeit(lambda: ops.window_gather(x.view(16, 120, 160, 64), 16, 120, 160, 7, 3, g, bt))
         print("window_gather 1/4 C=64    %8.1f us  %.2f TB/s" % (us, 2 * x.numel() * 2 / us / 1e6))
+        win = ops.window_gather(x.view(16, 120, 160, 64), 16, 120, 160, 7, 3, g, bt)
+        us = timeit(lambda: ops.window_merge(win, x, 16, 120, 160, 7, 3, g, bt, want_ln=True))
+        print("window_merge+LN 1/4 C=64  %8.1f us  %.2f TB/s" % (us, 4 * x.numel() * 2 / us / 1e6))
     if "pyr" in which:
         B, H, W, C = 16, 120, 160, 160
         cat = torch.randn(B, H, W, 5 * C, device=dev).bfloat16()
