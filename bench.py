@@ -57,7 +57,7 @@ def parse():
                     "0.0 is the parity configuration the headline is quoted on)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-forward", action="store_true", help="skip the inference-forward section")
-    ap.add_argument("--fwd-streams", type=int, default=2, help="inference-forward section: graph instances / streams consecutive batches alternate on")
+    ap.add_argument("--fwd-streams", type=int, default=3, help="inference-forward section: graph instances / streams consecutive batches alternate on")
     ap.add_argument("--no-reference-eager", action="store_true")
     return ap.parse_args()
 

@@ -304,22 +304,21 @@ class GlassRGBD(_Node):
         (`pred_depth` = the full-resolution map).  A batch is either fp32 [B,3,H,W] (already normalised, what the
         reference's data loader hands over) or uint8 [B,H,W,3] raw images: those cross PCIe at a quarter of the bytes and
         are normalised on the GPU (gwd_images_to_batch, bit-identical to ToTensor + Normalize of src/datasets/coco.py:77-78).  Uploads and downloads run on
-        their own streams with two buffers each, and consecutive batches replay two CUDA-graph instances on two compute
+        their own streams with three buffers each, and consecutive batches replay three CUDA-graph instances on three compute
         streams: the copy of batch i+1 and the read-back of batch i-1 overlap the forward of batch i, and the latency-bound
         phases of one forward (DETR chain, coarse Swin stages) share the SMs with the wide phases of the next (+12 % images/s
         at 16 x 480 x 640).  A yielded dict is valid until the next one is requested."""
         plan = self.plan()
         dev = plan.dev
+        NBUF = 3        # batches in flight: one uploading / computing, one computing, one being read back
         caller = torch.cuda.current_stream(dev)
         # streams, events and the device / pinned-host buffers live on the module: pinned allocations cost milliseconds
         st = self.__dict__.setdefault("_serve_state", {})
         if st.get("dev") != dev:
             st.clear()
-            st.update(dev=dev, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev), s_comp=[torch.cuda.Stream(dev), torch.cuda.Stream(dev)],
-                      x_dev=[None, None], u_dev=[None, None],
-                      u_tab=[None, None],
-                      out_dev=[None, None], out_host=[None, None],
-                      ev=[[torch.cuda.Event() for _ in range(2)] for _ in range(4)])
+            st.update(dev=dev, s_in=torch.cuda.Stream(dev), s_out=torch.cuda.Stream(dev), s_comp=[torch.cuda.Stream(dev) for _ in range(NBUF)],
+                      x_dev=[None] * NBUF, u_dev=[None] * NBUF, u_tab=[None] * NBUF, out_dev=[None] * NBUF, out_host=[None] * NBUF,
+                      ev=[[torch.cuda.Event() for _ in range(NBUF)] for _ in range(4)])
         s_in, s_out = st["s_in"], st["s_out"]
         x_dev, out_dev, out_host = st["x_dev"], st["out_dev"], st["out_host"]
         ev_in, ev_used, ev_out, ev_done = st["ev"]
@@ -335,7 +334,7 @@ class GlassRGBD(_Node):
             return res
 
         for i, hb in enumerate(host_batches):
-            b = i & 1
+            b = i % NBUF
             comp = st["s_comp"][b] if two else caller
             raw = hb.dtype == torch.uint8
             u_dev, u_tab = st["u_dev"], st["u_tab"]
@@ -344,8 +343,8 @@ class GlassRGBD(_Node):
                 if stage[b] is None or stage[b].shape != hb.shape:
                     stage[b] = torch.empty(hb.shape, dtype=hb.dtype if raw else torch.float32, device=dev)
                     u_tab[b] = None
-                elif i >= 2:
-                    s_in.wait_event(ev_used[b])          # the forward of batch i-2 has consumed this buffer
+                elif i >= NBUF:
+                    s_in.wait_event(ev_used[b])          # the forward of batch i-NBUF has consumed this buffer
                 stage[b].copy_(hb, non_blocking=True)
                 ev_in[b].record(s_in)
             with torch.cuda.stream(comp):
@@ -361,8 +360,8 @@ class GlassRGBD(_Node):
                 if out_dev[b] is None or set(out_dev[b]) != set(out) or any(out_dev[b][k].shape != v.shape for k, v in out.items()):
                     out_dev[b] = {k: torch.empty_like(v) for k, v in out.items()}
                     out_host[b] = {k: torch.empty(v.shape, dtype=v.dtype).pin_memory() for k, v in out.items()}
-                elif i >= 2:
-                    comp.wait_event(ev_done[b])              # read-back of batch i-2 has left this buffer
+                elif i >= NBUF:
+                    comp.wait_event(ev_done[b])              # read-back of batch i-NBUF has left this buffer
                 for k, v in out.items():
                     out_dev[b][k].copy_(v, non_blocking=True)    # the graph's static outputs are reused by the next replay
                 ev_out[b].record(comp)
@@ -372,7 +371,7 @@ class GlassRGBD(_Node):
                     out_host[b][k].copy_(v, non_blocking=True)
                 ev_done[b].record(s_out)
             pending.append(b)
-            if len(pending) == 2:
+            if len(pending) == NBUF:
                 pb = pending.pop(0)
                 ev_done[pb].synchronize()
                 yield out_host[pb]
