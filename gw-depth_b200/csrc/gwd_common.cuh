@@ -63,6 +63,16 @@ __device__ __forceinline__ float gwd_gelu(float v) {
   const float h = 0.5f * v;
   return fmaf(h, gwd_tanh_approx(u), h);
 }
+// d gelu(v) / dv of the tanh form above: 0.5 (1 + t) + 0.5 v (1 - t^2) u' with u = sqrt(2/pi) (v + 0.044715 v^3), t = tanh u.
+// 9 FP instructions + 1 MUFU instead of ~45 for erff + expf; within 9e-4 of the erf form's derivative (nn.GELU) everywhere, and
+// it is the exact derivative of what the forward kernels compute.  The LayerNorm / activation backward kernels evaluate it per
+// element and are bound by instruction issue.
+__device__ __forceinline__ float gwd_gelu_grad(float v) {
+  const float v2 = v * v;
+  const float t = gwd_tanh_approx(v * fmaf(0.0356774081f, v2, 0.7978845608f));
+  const float du = fmaf(0.1070322243f, v2, 0.7978845608f);
+  return fmaf(0.5f * v * fmaf(-t, t, 1.f), du, fmaf(0.5f, t, 0.5f));
+}
 // erf(x) by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), kept for callers that need erf itself
 __device__ __forceinline__ float gwd_erf(float x) {
   float ax = fabsf(x);

@@ -37,11 +37,11 @@ __device__ __forceinline__ void st8(bf16* p, const float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kLnWarps = 8;
 
-// d act(v) / dv from the activation's INPUT v (GELU in its exact erf form, as the reference's nn.GELU differentiates)
+// d act(v) / dv from the activation's INPUT v (GELU: gwd_gelu_grad, the derivative of the tanh form the forward evaluates)
 __device__ __forceinline__ float gwd_act_grad(float v, int act) {
   switch (act) {
     case GWD_ACT_RELU: return v > 0.f ? 1.f : 0.f;
-    case GWD_ACT_GELU: return 0.5f * (1.f + erff(v * 0.70710678f)) + v * 0.39894228f * __expf(-0.5f * v * v);
+    case GWD_ACT_GELU: return gwd_gelu_grad(v);
     case GWD_ACT_ELU: return v > 0.f ? 1.f : __expf(v);
     case GWD_ACT_SIGMOID: { const float s = 1.f / (1.f + __expf(-v)); return s * (1.f - s); }
     default: return 1.f;

@@ -23,10 +23,7 @@ constexpr int kHeads = 16;          // channels of the diffusion convolution = a
 constexpr int kFilt = kHeads * kHeads * 9;
 constexpr int kTokTile = 128;
 
-// d gelu(v) / dv, exact erf form (what nn.GELU differentiates)
-__device__ __forceinline__ float gelu_grad(float v) {
-  return 0.5f * (1.f + erff(v * 0.70710678f)) + v * 0.39894228f * __expf(-0.5f * v * v);
-}
+__device__ __forceinline__ float gelu_grad(float v) { return gwd_gelu_grad(v); }   // derivative of the forward's tanh-form GELU
 
 // ------------------------------------------------------------------------------------------------
 // filter re-layout: FlatModule keeps the 16x16x3x3 filter as [tap = kx*3+ky][oc][ic]; the convolution kernels of
