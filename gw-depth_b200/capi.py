@@ -91,6 +91,12 @@ SIGNATURES = {
     "gwd_line_ref_gather": (c_int, [P, L, P, L, P, I, P, L, I, I, I, I, I, I, P]),
     "gwd_anchor_mix": (c_int, [P, L, P, I, L, I, P, P]),
     "gwd_nchw_to_nhwc": (c_int, [P, I, I, L, P, I, P]),
+    "gwd_pil_bilinear_ksize": (c_int, [I, I]),
+    "gwd_pil_bilinear_coeffs": (c_int, [I, I, P, P, P]),
+    "gwd_pil_nearest_index": (c_int, [I, I, P]),
+    "gwd_resample_u8": (c_int, [P, L, I, I, I, P, I, I, P, P, P, I, I, P]),
+    "gwd_gather2d": (c_int, [P, L, I, I, I, P, I, I, P, P, I, I, P]),
+    "gwd_jitter_u8": (c_int, [P, L, I, P, P, P, P, P]),
     "gwd_images_to_batch": (c_int, [P, I, I, I, ctypes.POINTER(c_float), ctypes.POINTER(c_float), P, P, P]),
     "gwd_stem_conv_pool": (c_int, [P, P, P, P, I, I, I, P]),
     "gwd_certain_sample": (c_int, [P, I, I, P, I, I, I, I, ctypes.POINTER(c_float), I, P, P, P]),

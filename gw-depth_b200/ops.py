@@ -403,6 +403,101 @@ def nchw_to_nhwc(x, Cp):
 IMAGE_MEAN, IMAGE_STD = (0.538, 0.494, 0.453), (0.257, 0.263, 0.273)      # src/datasets/coco.py:78
 
 
+# ---------------------------------------------------------------------------------------------- training data path (pixel side)
+_PIL_TABLES = {}
+
+
+def pil_bilinear_tables(in_size, out_size, device):
+    """Pillow's BILINEAR resize tables of one axis as device int32 tensors (xmin [out], cnt [out], kk [out, ksize]); cached"""
+    key = ("bl", in_size, out_size, str(device))
+    t = _PIL_TABLES.get(key)
+    if t is None:
+        ks = _L().gwd_pil_bilinear_ksize(in_size, out_size)
+        xmin, cnt = torch.empty(out_size, dtype=torch.int32), torch.empty(out_size, dtype=torch.int32)
+        kk = torch.empty(out_size, ks, dtype=torch.int32)
+        capi.check(_L().gwd_pil_bilinear_coeffs(in_size, out_size, _ptr(xmin), _ptr(cnt), _ptr(kk)), "gwd_pil_bilinear_coeffs")
+        t = _PIL_TABLES[key] = (xmin.to(device), cnt.to(device), kk.to(device))
+        if len(_PIL_TABLES) > 512:
+            _PIL_TABLES.pop(next(iter(_PIL_TABLES)))
+    return t
+
+
+def pil_nearest_index(in_size, out_size, device):
+    """source index of every output index of a Pillow NEAREST resize, device int32 [out]; cached"""
+    key = ("nn", in_size, out_size, str(device))
+    t = _PIL_TABLES.get(key)
+    if t is None:
+        idx = torch.empty(out_size, dtype=torch.int32)
+        capi.check(_L().gwd_pil_nearest_index(in_size, out_size, _ptr(idx)), "gwd_pil_nearest_index")
+        t = _PIL_TABLES[key] = idx.to(device)
+    return t
+
+
+def resize_bilinear_u8(img, oh, ow, hflip=False, vflip=False):
+    """Pillow `resize((ow, oh), BILINEAR)` of a uint8 image [H,W,C] on the device, after an optional horizontal / vertical flip
+    (transforms_depth.py:206-263,316-372).  img may be a crop view (rows any stride, pixels contiguous)."""
+    H, W, C = img.shape
+    assert img.dtype == torch.uint8 and img.is_cuda and img.stride(2) == 1 and img.stride(1) == C
+    out, rs = img, img.stride(0)
+    if ow != W or hflip:
+        xmin, cnt, kk = pil_bilinear_tables(W, ow, img.device)
+        tmp = torch.empty(H, ow, C, dtype=torch.uint8, device=img.device)
+        capi.check(_L().gwd_resample_u8(_ptr(out), rs, H, W, C, _ptr(tmp), ow, 1, _ptr(xmin), _ptr(cnt), _ptr(kk), kk.shape[1],
+                                        int(hflip), _stream()), "gwd_resample_u8")
+        out, rs, W = tmp, ow * C, ow
+    if oh != H or vflip:
+        xmin, cnt, kk = pil_bilinear_tables(H, oh, img.device)
+        dst = torch.empty(oh, W, C, dtype=torch.uint8, device=img.device)
+        capi.check(_L().gwd_resample_u8(_ptr(out), rs, H, W, C, _ptr(dst), oh, 0, _ptr(xmin), _ptr(cnt), _ptr(kk), kk.shape[1],
+                                        int(vflip), _stream()), "gwd_resample_u8")
+        out = dst
+    return out if out.is_contiguous() else out.contiguous()
+
+
+def gather2d(mat, oh=None, ow=None, hflip=False, vflip=False, nearest=True):
+    """auxiliary map [H,W] (any 1/2/4/8-byte dtype; may be a crop view) -> [oh,ow]: Pillow NEAREST resize after optional flips"""
+    H, W = mat.shape
+    oh, ow = oh or H, ow or W
+    assert mat.is_cuda and mat.stride(1) == 1
+    iy = pil_nearest_index(H, oh, mat.device) if oh != H else None
+    ix = pil_nearest_index(W, ow, mat.device) if ow != W else None
+    out = torch.empty(oh, ow, dtype=mat.dtype, device=mat.device)
+    capi.check(_L().gwd_gather2d(_ptr(mat), mat.stride(0), mat.element_size(), H, W, _ptr(out), oh, ow, _ptr(iy), _ptr(ix), int(hflip),
+                                 int(vflip), _stream()), "gwd_gather2d")
+    return out
+
+
+JITTER_BRIGHTNESS, JITTER_CONTRAST, JITTER_SATURATION, JITTER_HUE = 0, 1, 2, 3
+
+
+def color_jitter_u8(img, order, factors):
+    """ColorJitter (transforms_depth.py:582-604) in place on a contiguous uint8 [H,W,3] device image: `order` = op ids in the drawn
+    order, `factors` = their factors.  One launch, or two around a contrast op (which needs the mean grey level of the image at that
+    point)."""
+    assert img.dtype == torch.uint8 and img.is_cuda and img.is_contiguous() and img.shape[-1] == 3
+    npix = img.numel() // 3
+    segments, cur = [], []
+    for op, f in zip(order, factors):
+        if op == JITTER_CONTRAST and cur:      # a contrast op opens a new launch
+            segments.append(cur)
+            cur = []
+        cur.append((int(op), float(f)))
+    if cur:
+        segments.append(cur)
+    gray = None
+    for i, seg in enumerate(segments):
+        contrast_first = seg[0][0] == JITTER_CONTRAST
+        if contrast_first and i == 0:          # contrast is the very first op: measure the input image
+            gray = torch.empty(1, dtype=torch.int64, device=img.device)
+            capi.check(_L().gwd_jitter_u8(_ptr(img), npix, 0, None, None, None, _ptr(gray), _stream()), "gwd_jitter_u8")
+        gout = torch.empty(1, dtype=torch.int64, device=img.device) if i + 1 < len(segments) else None
+        n = len(seg)
+        capi.check(_L().gwd_jitter_u8(_ptr(img), npix, n, (ctypes.c_int32 * n)(*[o for o, _ in seg]), (ctypes.c_float * n)(*[f for _, f in seg]),
+                                      _ptr(gray) if contrast_first else None, _ptr(gout), _stream()), "gwd_jitter_u8")
+        gray = gout
+    return img
+
+
 def images_to_batch(images, mean=IMAGE_MEAN, std=IMAGE_STD, out=None, want_mask=True, table=None):
     """uint8 HWC device images -> (normalised fp32 [B,3,H,W] padded batch, bool [B,H,W] padding mask or None, padded flag).
     images: one uint8 [B,H,W,3] tensor or a list of [h,w,3] tensors (padded bottom / right to the largest)"""

@@ -197,6 +197,27 @@ int gwd_sample_bilinear(const void* x, int64_t x_rs, int32_t x_coff, const float
 /* same for a 1-channel fp32 map -> fp32 [B,K]  (points_sample.py:268) */
 int gwd_sample_scalar(const float* x, int32_t B, int32_t H, int32_t W, const float* coords, int32_t K, float* out,
                       void* stream);
+/* ---- Training data path, pixel side: src/datasets/transforms_depth.py on decoded uint8 images, bit for bit
+ * what Pillow / torchvision do to the PIL image in the reference's DataLoader workers. ---- */
+/* HOST: Pillow ImagingResample coefficient tables of a BILINEAR (antialiased) resize of one axis (transforms_depth.py:343 F.resize):
+ * ksize = table width; xmin / cnt int32 [out_size], kk int32 [out_size * ksize] (22-bit fixed point). */
+int gwd_pil_bilinear_ksize(int32_t in_size, int32_t out_size);
+int gwd_pil_bilinear_coeffs(int32_t in_size, int32_t out_size, int32_t* xmin, int32_t* cnt, int32_t* kk);
+/* HOST: source index of every output index of a Pillow NEAREST resize (transforms_depth.py:368-370, the auxiliary maps) */
+int gwd_pil_nearest_index(int32_t in_size, int32_t out_size, int32_t* idx);
+/* One 8-bit pass of the resize along x (axis 1: src [H,W,C] rows src_rs bytes apart -> dst [H,out_size,C]) or y (axis 0: -> dst
+ * [out_size,W,C]); tables on the DEVICE; flip != 0 mirrors the source index along that axis (hflip :206 / vflip :234 come first). */
+int gwd_resample_u8(const void* src, int64_t src_rs, int32_t H, int32_t W, int32_t C, void* dst, int32_t out_size, int32_t axis,
+                    const int32_t* xmin, const int32_t* cnt, const int32_t* kk, int32_t ksize, int32_t flip, void* stream);
+/* dst[y,x] = src[sy, sx] for maps of 1 / 2 / 4 / 8-byte elements (rows src_rs ELEMENTS apart): sy = iy[y] (device int32 table, null =
+ * y), mirrored when flip_v; same for x.  Nearest resize, flips and crops of the depth / segmentation maps in one pass. */
+int gwd_gather2d(const void* src, int64_t src_rs, int32_t elem_bytes, int32_t H, int32_t W, void* dst, int32_t oh, int32_t ow,
+                 const int32_t* iy, const int32_t* ix, int32_t flip_h, int32_t flip_v, void* stream);
+/* ColorJitter (transforms_depth.py:551-604) in place on uint8 [npix,3]: up to 4 ops (HOST arrays; 0 brightness, 1 contrast,
+ * 2 saturation, 3 hue) in the given order.  Contrast must be the first op of a launch and reads the L sum of the image from gray_in
+ * (device uint64, written by the previous launch through gray_out; n_ops = 0 just measures). */
+int gwd_jitter_u8(void* img, int64_t npix, int32_t n_ops, const int32_t* ops, const float* factors, const void* gray_in, void* gray_out,
+                  void* stream);
 /* Input builder (src/datasets/coco.py:77-78 ToTensor + Normalize, src/util/misc.py:291-313 padding + mask): table is a
  * DEVICE int64 [B][3] = {pointer to a uint8 HWC image on the device, its height, its width}; out fp32 [B,3,H,W] =
  * ((u8 / 255) - mean[c]) / std[c] inside an image and 0 in its padding (IEEE division: bit-identical to torchvision);
