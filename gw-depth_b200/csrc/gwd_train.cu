@@ -1647,6 +1647,55 @@ gwd_bilinear_up_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, int H, in
   }
 }
 
+// the same gather for LARGE footprints (the pool-8 / pool-16 branches: a low-resolution pixel collects ~18 x 18 / ~34 x 34
+// high-resolution ones, and there are only h x w x B = 120 ... 2 400 of them): one CTA per low-resolution pixel, its 256 threads
+// are (footprint slots) x (channel vectors), the slots meet in shared memory.  The row-slice kernel above ran these on 24-48 CTAs
+// with ~300 dependent loads per thread (0.19 ms for a 3 x 5 map).
+__global__ void __launch_bounds__(256)
+gwd_bilinear_up_bwd_wide_kernel(const bf16* __restrict__ dy, int64_t dy_rs, int H, int W, bf16* __restrict__ dx, int64_t dx_rs, int h,
+                                int w, int C) {
+  __shared__ float red[256][8];
+  const int cv = C / 8;
+  const int slots = 256 / cv;
+  const int x = blockIdx.x, y = blockIdx.y, b = blockIdx.z;
+  const int slot = threadIdx.x / cv, vec = threadIdx.x - slot * cv;
+  const float ry = (H > 1) ? static_cast<float>(h - 1) / (H - 1) : 0.f;
+  const float rx = (W > 1) ? static_cast<float>(w - 1) / (W - 1) : 0.f;
+  int Ylo = 0, Yhi = H - 1, Xlo = 0, Xhi = W - 1;
+  if (ry > 0.f) { Ylo = max(0, static_cast<int>(floorf((y - 1) / ry)) - 1); Yhi = min(H - 1, static_cast<int>(ceilf((y + 1) / ry)) + 1); }
+  if (rx > 0.f) { Xlo = max(0, static_cast<int>(floorf((x - 1) / rx)) - 1); Xhi = min(W - 1, static_cast<int>(ceilf((x + 1) / rx)) + 1); }
+  const int wf = Xhi - Xlo + 1, nf = (Yhi - Ylo + 1) * wf;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (slot < slots) {
+    for (int p = slot; p < nf; p += slots) {
+      const int Y = Ylo + p / wf, X = Xlo + p % wf;
+      const float fy = ry * Y, fx = rx * X;                      // the forward's footprint arithmetic (gwd_bilinear_ac_kernel)
+      const int y0 = static_cast<int>(fy), y1 = min(y0 + 1, h - 1);
+      const int x0 = static_cast<int>(fx), x1 = min(x0 + 1, w - 1);
+      const float ly = fy - y0, lx = fx - x0;
+      const float wy = (y0 == y ? 1.f - ly : 0.f) + (y1 == y ? ly : 0.f);
+      const float wx = (x0 == x ? 1.f - lx : 0.f) + (x1 == x ? lx : 0.f);
+      const float wgt = wy * wx;
+      if (wgt == 0.f) continue;
+      float f[8];
+      ld8(dy + ((static_cast<int64_t>(b) * H + Y) * W + X) * dy_rs + vec * 8, f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, f[i], acc[i]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < cv) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+    for (int sl = 0; sl < slots; ++sl)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += red[sl * cv + threadIdx.x][i];
+    st8(dx + ((static_cast<int64_t>(b) * h + y) * w + x) * dx_rs + threadIdx.x * 8, acc);
+  }
+}
+
 // out[b, Y, X, :] = add[b, Y, X, :] + (Y / k < H / k and X / k < W / k ? d[b, Y / k, X / k, :] * scale / k^2 : 0)   (floor-mode pool)
 __global__ void __launch_bounds__(256)
 gwd_avgpool_bwd_kernel(const bf16* __restrict__ d, int64_t d_rs, int k, float scale, const bf16* __restrict__ add, int64_t add_rs,
@@ -1682,6 +1731,13 @@ extern "C" int gwd_bilinear_up_bwd(const void* dy, int64_t dy_rs, int32_t B, int
   GWD_CHECK_ARG(dy && dx && C > 0 && C % 8 == 0 && dy_rs % 8 == 0 && dx_rs % 8 == 0 && dy_rs >= C && dx_rs >= C,
                 "gwd_bilinear_up_bwd: bad argument");
   GWD_CHECK_ARG(B > 0 && H > 0 && W > 0 && h > 0 && w > 0 && h <= 65535 && B <= 65535, "gwd_bilinear_up_bwd: bad extents");
+  const int64_t footprint = (2 * static_cast<int64_t>(H) / h + 2) * (2 * static_cast<int64_t>(W) / w + 2);
+  if (footprint >= 200 && C / 8 <= 256 && w <= 65535) {
+    gwd_bilinear_up_bwd_wide_kernel<<<dim3(w, h, B), 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, H, W, static_cast<bf16*>(dx),
+                                                                         dx_rs, h, w, C);
+    GWD_LAUNCHED();
+    return GWD_OK;
+  }
   const dim3 grid(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(w) * (C / 8), 64)), h, B);
   gwd_bilinear_up_bwd_kernel<<<grid, dim3(64, 4), 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, H, W, static_cast<bf16*>(dx), dx_rs, h,
                                                               w, C);

@@ -173,7 +173,7 @@ def test_dense_head_training_lowers_the_loss():
 
 
 # ------------------------------------------------------------------------------------------ PyramidLayer (A19)
-@pytest.mark.parametrize("H,W,h,w,C", [(24, 32, 3, 4, 64), (30, 40, 15, 20, 160), (17, 23, 1, 1, 32), (16, 16, 8, 8, 64), (21, 37, 5, 9, 16)])
+@pytest.mark.parametrize("H,W,h,w,C", [(24, 32, 3, 4, 64), (30, 40, 15, 20, 160), (17, 23, 1, 1, 32), (16, 16, 8, 8, 64), (21, 37, 5, 9, 16), (120, 160, 7, 10, 160), (60, 80, 3, 5, 160), (60, 80, 7, 10, 168)])
 def test_bilinear_up_bwd(H, W, h, w, C):
     """gwd_bilinear_up_bwd == autograd of F.interpolate(bilinear, align_corners=True), reading a channel slice"""
     ops = _ops()
