@@ -1277,7 +1277,7 @@ static int launch_wgrad(const void* dy, int64_t dy_rs, const void* x, int64_t x_
                         int64_t dw_rs, float* db, int H, int W, int sy, int sx, cudaStream_t stream);
 
 int gwd_linear_wgrad_tc_try(const void* dy, int64_t dy_rs, const void* x, int64_t x_rs, int64_t rows, int N, int K, float* dw,
-                            int64_t dw_rs, cudaStream_t stream);     // gwd_wgrad_tc.cu (tcgen05 path)
+                            int64_t dw_rs, float* db, int* db_done, cudaStream_t stream);     // gwd_wgrad_tc.cu (tcgen05 path)
 
 namespace {
 // db[n] += sum_r dY[r][n]: 8 columns per thread.  A row segment of min(N, 256) columns is held by LPR = 1..32 lanes (a power of
@@ -1334,10 +1334,11 @@ extern "C" int gwd_linear_wgrad(const void* dy, int64_t dy_rs, const void* x, in
   // many-row Linears (window tokens of the 1/4- and 1/8-scale Swin stages): tcgen05 kernel of gwd_wgrad_tc.cu + a column-sum pass
   static const bool force_mma = [] { const char* e = getenv("GWD_WGRAD"); return e && strcmp(e, "mma") == 0; }();
   if (!force_mma && dy && x && dw && N % 8 == 0) {
-    const int rc = gwd_linear_wgrad_tc_try(dy, dy_rs, x, x_rs, rows, N, K, dw, dw_rs, stream);
+    int db_done = 0;
+    const int rc = gwd_linear_wgrad_tc_try(dy, dy_rs, x, x_rs, rows, N, K, dw, dw_rs, db, &db_done, stream);
     if (rc < 0) return rc;
     if (rc == 0) {
-      if (db != nullptr) {
+      if (db != nullptr && !db_done) {
         int lpr = 1;
         while (lpr < 32 && lpr * 8 < N) lpr <<= 1;
         const dim3 grid(static_cast<unsigned>(gwd_ceil_div(N, 256)),

@@ -19,6 +19,7 @@
 //                         optimizer's accumulate-into-G contract both want +=)
 //   Which operand plays M is chosen per shape to minimise padded work (dW^T is accumulated when X plays M).
 #include <cuda.h>
+#include <stdlib.h>
 #include <string.h>
 #include "gwd_common.cuh"
 
@@ -45,6 +46,8 @@ struct WgTcParams {
   int tw, th;                // pixel block of one 64-pixel chunk: 16 x 4 (maps) or 64 x 1 (plain row matrices)
   int64_t dw_rs;             // row stride of dW (floats)
   uint32_t tmem_cols;
+  float* db;                 // optional (Linear, dY on the M side): db[n] += sum_r dY[r][n] from one extra N = 16 MMA per K step
+  uint32_t ones_col;         // against a shared-memory tile of ones; its accumulators live at this TMEM column (+16: second M tile)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -138,7 +141,10 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
   const int n_atoms = (n_mma + 63) >> 6;
   const int stage_bytes = (kMaxMAtoms + kMaxNAtoms) * kAtomBytes;
 
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  // bias gradient: only the CTAs of the first N tile, which see every row of dY exactly once per M tile
+  const bool do_db = p.db != nullptr && nt == 0;
+  uint8_t* ones = smem + kStages * stage_bytes;        // one 8 KB atom of bf16 ones (any swizzle of all-ones is all-ones)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ones + kAtomBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* done = bars + 2 * kStages;
@@ -149,6 +155,10 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
     for (int s = 0; s < kStages; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
     mbar_init(done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (do_db) {
+    for (int i = threadIdx.x; i < kAtomBytes / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(ones)[i] = 0x3F803F80u;   // bf16 1.0 x 2
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the tensor core's reads
   }
   if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "r"(p.tmem_cols)
@@ -188,6 +198,8 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
       // instruction descriptor: D fp32, A / B bf16, both MN-major, N, M = 128
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) |
                              (static_cast<uint32_t>(n_mma >> 3) << 17) | (static_cast<uint32_t>(128 >> 4) << 24);
+      const uint32_t idesc_ones = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | (static_cast<uint32_t>(16 >> 3) << 17) |
+                                  (static_cast<uint32_t>(128 >> 4) << 24);
       for (int it = 0; it < iters; ++it) {
         const int s = it % kStages;
         mbar_wait(full + s, (it / kStages) & 1);
@@ -199,6 +211,13 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
           umma(tmem_base, make_desc_mn(base + k * 2048, kAtomBytes), bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
           if (m_valid_b > 0)
             umma(tmem_base + p.acc_stride, make_desc_mn(base + 2 * kAtomBytes + k * 2048, kAtomBytes), bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          if (do_db) {   // D1[m][0..15] += sum over the 16 pixels of dY[pixel][m] * 1
+            const uint64_t odesc = make_desc_mn(smem_u32(ones), kAtomBytes);
+            umma(tmem_base + p.ones_col, make_desc_mn(base + k * 2048, kAtomBytes), odesc, idesc_ones, (it > 0 || k > 0) ? 1u : 0u);
+            if (m_valid_b > 0)
+              umma(tmem_base + p.ones_col + 16, make_desc_mn(base + 2 * kAtomBytes + k * 2048, kAtomBytes), odesc, idesc_ones,
+                   (it > 0 || k > 0) ? 1u : 0u);
+          }
         }
         umma_commit(empty + s);
       }
@@ -216,6 +235,11 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
       const int mb = m0 + tile * 128;
       const bool row_ok = m < mv;
       const uint32_t t_row = tmem_base + tile * p.acc_stride + (static_cast<uint32_t>(warp * 32) << 16);
+      if (do_db) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + p.ones_col + tile * 16 + (static_cast<uint32_t>(warp * 32) << 16), r);
+        if (row_ok) atomicAdd(p.db + mb + m, __uint_as_float(r[0]));
+      }
       for (int c = 0; c < n_mma; c += 16) {
         uint32_t r[16];
         tmem_ld16(t_row + c, r);
@@ -301,12 +325,18 @@ static int launch_tc(WgTcParams& p, const void* dy, int64_t dy_cs, const void* x
   int splits = (gwd_num_sms() + units / 2) / units;
   splits = max(1, min(splits, p.chunks / 8));
   p.splits = splits;
+  uint32_t need = p.acc_stride * (p.m_pair - 1) + static_cast<uint32_t>(p.n_tile);
+  if (p.db != nullptr) {     // bias gradient on the tensor core: needs dY on the M side and 32 spare TMEM columns
+    p.ones_col = (need + 15u) & ~15u;
+    if (p.m_is_x || p.taps != 1 || p.ones_col + 32 > 512) p.db = nullptr;
+    else need = p.ones_col + 32;
+  }
   uint32_t cols = 32;
-  while (cols < p.acc_stride * (p.m_pair - 1) + static_cast<uint32_t>(p.n_tile)) cols <<= 1;
+  while (cols < need) cols <<= 1;
   p.tmem_cols = cols;
   CUtensorMap map_dy, map_x;
   if (make_map(&map_dy, dy, p.B, p.H, p.W, dy_cs, N, p.tw, p.th) || make_map(&map_x, x, p.B, p.H, p.W, x_cs, C, p.tw, p.th)) return 1;
-  const size_t smem = static_cast<size_t>(kStages) * (kMaxMAtoms + kMaxNAtoms) * kAtomBytes + 1024 + 256;
+  const size_t smem = static_cast<size_t>(kStages) * (kMaxMAtoms + kMaxNAtoms) * kAtomBytes + kAtomBytes + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     GWD_CUDA(cudaFuncSetAttribute(gwd_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -337,8 +367,10 @@ int gwd_conv3x3_wgrad_tc_try(const void* dy, int64_t dy_cs, const void* x, int64
 
 // Linear weight gradient dW[n][k] += sum_r dY[r][n] X[r][k] over many rows (the 1/4- and 1/8-scale Swin stages: 85 k - 325 k window
 // tokens): the same kernel with one "tap", the row matrices seen as a [C, rows] map walked in 64-row boxes
+// db (optional): the bias gradient; *db_done tells the caller whether it was accumulated here (else: a column-sum pass)
 int gwd_linear_wgrad_tc_try(const void* dy, int64_t dy_rs, const void* x, int64_t x_rs, int64_t rows, int N, int K, float* dw,
-                            int64_t dw_rs, cudaStream_t stream) {
+                            int64_t dw_rs, float* db, int* db_done, cudaStream_t stream) {
+  if (db_done) *db_done = 0;
   if (N % 16 || K % 16 || N > 1024 || K > 1024 || rows < 32768 || rows >= (1ll << 31)) return 1;
   if (dy_rs % 8 || x_rs % 8 || dy_rs < N || x_rs < K || dw_rs % 4 || dw_rs < K) return 1;
   if ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dw)) & 15) return 1;
@@ -348,5 +380,9 @@ int gwd_linear_wgrad_tc_try(const void* dy, int64_t dy_rs, const void* x, int64_
   p.dw = dw; p.N = N; p.C = K; p.dw_rs = dw_rs;
   p.B = 1; p.H = 1; p.W = static_cast<int>(rows);
   p.taps = 1; p.tw = 64; p.th = 1;
-  return launch_tc(p, dy, dy_rs, x, x_rs, stream);
+  static const bool fuse_db = [] { const char* e = getenv("GWD_WGRAD_DB"); return !(e && e[0] == '0'); }();
+  p.db = fuse_db ? db : nullptr;
+  const int rc = launch_tc(p, dy, dy_rs, x, x_rs, stream);
+  if (rc == 0 && db_done) *db_done = p.db != nullptr;
+  return rc;
 }

@@ -152,7 +152,7 @@ def test_weight_gradient_gemm_on_transposed_operands():
 
 
 @pytest.mark.parametrize("R,N,K", [(600, 256, 2048), (4800, 2048, 256), (1200, 16, 256), (9600, 256, 256), (70, 512, 264),
-                                   (40000, 192, 64), (33001, 64, 64), (50000, 384, 192), (40000, 160, 80), (36000, 16, 128)])
+                                   (40000, 192, 64), (33001, 64, 64), (50000, 384, 192), (40000, 160, 80), (36000, 16, 128), (40000, 256, 64), (34000, 512, 256), (33000, 1024, 64)])
 def test_linear_wgrad_kernel(R, N, K):
     """gwd_linear_wgrad: dW += dY^T X, db += column sums (accumulating into a non-zero buffer), operands read in place.
     From 32 768 rows on (N, K multiples of 16) the tcgen05 kernel of gwd_wgrad_tc.cu runs (one "tap", 64-row TMA boxes, both role
