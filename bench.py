@@ -57,6 +57,7 @@ def parse():
                     "0.0 is the parity configuration the headline is quoted on)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-forward", action="store_true", help="skip the inference-forward section")
+    ap.add_argument("--no-data-path", action="store_true", help="skip the data-path (augmentation pipeline) measurement")
     ap.add_argument("--fwd-streams", type=int, default=3, help="inference-forward section: graph instances / streams consecutive batches alternate on")
     ap.add_argument("--no-reference-eager", action="store_true")
     return ap.parse_args()
@@ -154,6 +155,88 @@ def run_reference(args, rank):
                              "sample": "%d training passes of 1x3x480x640 through oracle/gwdepth_oracle.py under torch.autograd" % args.steps},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def data_path_rate(dev, n=48):
+    """the training augmentation pipeline (make_coco_transforms('train'), src/datasets/coco.py:74-103) on 480x640
+    samples -- gw-depth_b200/data.py on the GPU (one host thread) and, when the staged reference + Pillow are there, the reference's own
+    PIL pipeline on one host core (what one of its DataLoader workers delivers)."""
+    import random
+    import types
+    import numpy as np
+    from gwdepth_b200 import data as gdata
+    out = {"what": "augmentation pipeline of the training loader, 480x640 uint8 samples (flip / multi-scale resize / size crop / ColorJitter / "
+                   "normalise), images already decoded", "unit": "samples/s"}
+    rng = np.random.default_rng(0)
+    samples = []
+    for s_ in range(4):
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        depth = rng.integers(300, 9000, (H, W)).astype(np.int32)
+        seg = rng.integers(0, 3, (H, W)).astype(np.uint8)
+        lines = torch.tensor([[100., 120., 300., 140.], [300., 140., 320., 330.], [110., 320., 320., 330.], [100., 120., 110., 320.]])
+        tgt = {"lines": lines, "poly_centers": lines[:, :2] * 0 + torch.tensor([210., 230.]), "poly_ids": torch.zeros(4, dtype=torch.int64),
+               "labels": torch.zeros(4, dtype=torch.int64), "area": torch.ones(4), "iscrowd": torch.zeros(4),
+               "orig_size": torch.as_tensor([H, W]), "size": torch.as_tensor([H, W])}
+        samples.append((img, depth, seg, tgt))
+    args_ = types.SimpleNamespace(eval=False)
+
+    def run(tf, conv, count):
+        done = 0
+        for i in range(count):
+            img, depth, seg, tgt = samples[i % 4]
+            try:
+                tf(conv(img, "RGB"), {k: v.clone() for k, v in tgt.items()}, aux_mats=[conv(depth, "I"), conv(seg, "L")])
+                done += 1
+            except ImportError:        # the one crop branch that needs shapely
+                pass
+        return done
+    try:
+        tf = gdata.make_coco_transforms("train", args_)
+        dev_cache = {}
+
+        def to_dev(a, _mode):
+            k = id(a)
+            if k not in dev_cache:
+                dev_cache[k] = torch.from_numpy(a).to(dev)
+            return dev_cache[k]
+        random.seed(0); torch.manual_seed(0)
+        run(tf, to_dev, 8)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        done = run(tf, to_dev, n)
+        torch.cuda.synchronize()
+        out["value"] = done / (time.perf_counter() - t0)
+    except Exception as e:      # noqa: BLE001
+        out["error"] = repr(e)[:200]
+    try:
+        from PIL import Image
+        import ref_shims
+        if ref_shims.reference_available():
+            ref_shims.install()
+            src = os.path.join(ref_shims.REFERENCE_ROOT, "src")
+            if src not in sys.path:
+                sys.path.insert(0, src)
+            try:
+                import shapely.geometry  # noqa: F401
+            except ImportError:
+                def _no(*a, **k):
+                    raise ImportError("shapely is not installed")
+                sh, g = types.ModuleType("shapely"), types.ModuleType("shapely.geometry")
+                g.Polygon, g.mapping, sh.geometry = _no, _no, g
+                sys.modules["shapely"], sys.modules["shapely.geometry"] = sh, g
+            import datasets.coco as rcoco
+            rtf = rcoco.make_coco_transforms("train", args_)
+            random.seed(0); torch.manual_seed(0)
+            nt = torch.get_num_threads()
+            torch.set_num_threads(1)
+            run(rtf, lambda a, m: Image.fromarray(a, mode=None if m == "RGB" else m), 2)
+            t0 = time.perf_counter()
+            done = run(rtf, lambda a, m: Image.fromarray(a, mode=None if m == "RGB" else m), max(8, n // 4))
+            out["reference_pil_one_core"] = done / (time.perf_counter() - t0)
+            torch.set_num_threads(nt)
+    except Exception as e:      # noqa: BLE001
+        out["reference_error"] = repr(e)[:200]
+    return out
 
 
 def gpu_eager_reference(dev, n_fwd=5, n_train=3):
@@ -463,6 +546,9 @@ def main():
                 n += 1
             cpu = {"value": n / (time.time() - t0), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                    "sample": "%d training passes (forward + 17 losses + backward) of 1x3x480x640 (1/8 of a step) through oracle/gwdepth_oracle.py" % n}
+    data_path = None
+    if world == 1 and not args.no_data_path:
+        data_path = data_path_rate(dev)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
@@ -470,7 +556,8 @@ def main():
                        "parallelism": "dp%d: batch sharded over the ranks, NCCL all-reduce of %d flat gradient buffers overlapped with the backward" % (world, len(net.__dict__.get("_live") or []) and 22),
                        "l2": "4 rotating input batches; per-step activations are several GB", "loss": loss_value,
                        "optimizer": "AdamW lr 1e-4 (backbone 1e-5), weight decay 1e-4, global clip 0.1; dropout %g" % args.dropout},
-            "breakdown": breakdown, "forward": fwd, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_reference": eager}
+            "breakdown": breakdown, "forward": fwd, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_reference": eager,
+            "data_path": data_path}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
