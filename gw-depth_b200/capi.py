@@ -61,6 +61,7 @@ class AttnBwdDesc(ctypes.Structure):
         ("scale", c_float), ("o", c_void_p), ("o_item_stride", c_i64), ("o_row_stride", c_i64),
         ("dq_mul", c_float), ("dk_mul", c_float),
         ("dropout_seed", c_void_p), ("dropout_site", ctypes.c_uint32), ("dropout_p", c_float),
+        ("key_padding", c_void_p), ("stats_ws", c_void_p),
     ]
 
 

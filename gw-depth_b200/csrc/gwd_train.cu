@@ -325,6 +325,8 @@ struct AttnBwdParams {
   uint32_t drop_site, drop_thr;
   float drop_scale;
   int heads;
+  const uint8_t* key_padding;     // [items, Lk], 1 = padded key (src_key_padding_mask of nn.MultiheadAttention), or nullptr
+  float* stats;                   // split kernels (long sequences): fp32 [items, heads, Lq, 2] = (lse, D) per query
 };
 
 __device__ __forceinline__ float reduce_scatter32(float (&acc)[32], int lane) {
@@ -552,6 +554,19 @@ __device__ __forceinline__ void store_tile(bf16* base, int64_t rs, int row0, int
   }
 }
 
+// bit j of word c: key 64 c + j exists (below Lk) and is not a padded key of this item
+__device__ __forceinline__ void build_key_mask(unsigned long long* sKm, const AttnBwdParams& p, int item) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int c = warp; c < p.Lk_pad / 64; c += nwarps) {
+    const int k0 = c * 64 + lane, k1 = k0 + 32;
+    const bool r0 = k0 < p.Lk && !(p.key_padding != nullptr && p.key_padding[static_cast<int64_t>(item) * p.Lk + k0]);
+    const bool r1 = k1 < p.Lk && !(p.key_padding != nullptr && p.key_padding[static_cast<int64_t>(item) * p.Lk + k1]);
+    const unsigned lo = __ballot_sync(0xffffffffu, r0), hi = __ballot_sync(0xffffffffu, r1);
+    if (lane == 0) sKm[c] = (static_cast<unsigned long long>(hi) << 32) | lo;
+  }
+}
+__device__ __forceinline__ bool key_is_real(const unsigned long long* sKm, int key) { return (sKm[key >> 6] >> (key & 63)) & 1ull; }
+
 __global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParams p) {
   extern __shared__ __align__(16) uint32_t smem[];
   const int head = blockIdx.x, item = blockIdx.y;
@@ -563,7 +578,9 @@ __global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParam
   uint32_t* sO = sV + p.Lk_pad * kMW;                 // dO
   float* sLse = reinterpret_cast<float*>(sO + p.Lq_pad * kMW);
   float* sD = sLse + p.Lq_pad;
+  unsigned long long* sKm = reinterpret_cast<unsigned long long*>(sD + p.Lq_pad);     // [Lk_pad / 64] bit j of word c: key 64 c + j is real
   const int64_t hoff = static_cast<int64_t>(head) * kHD;
+  build_key_mask(sKm, p, item);
   {
     const bf16* gq = p.q + item * p.q_is + hoff;
     const bf16* gk = p.k + item * p.k_is + hoff;
@@ -608,12 +625,12 @@ __global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParam
       float s[8][4];
       xyT(s, qa, bK, c0, lane);
       float cm[2] = {-INFINITY, -INFINITY};
+      const unsigned long long km = sKm[c0 >> 6] >> (2 * tq);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const int col = c0 + nt * 8 + 2 * tq + (e & 1);
-          if (col >= p.Lk) s[nt][e] = -INFINITY;
+          if (!((km >> (nt * 8 + (e & 1))) & 1ull)) s[nt][e] = -INFINITY;     // beyond Lk or a padded key
           cm[e >> 1] = fmaxf(cm[e >> 1], s[nt][e]);
         }
 #pragma unroll
@@ -648,12 +665,13 @@ __global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParam
       float s[8][4], dp[8][4];
       xyT(s, qa, bK, c0, lane);
       xyT(dp, oa, bV, c0, lane);
+      const unsigned long long km = sKm[c0 >> 6] >> (2 * tq);
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int col = c0 + nt * 8 + 2 * tq + (e & 1);
-          const float pr = col < p.Lk ? ex2f(s[nt][e] * sc - lse[e >> 1]) : 0.f;
+          const float pr = ((km >> (nt * 8 + (e & 1))) & 1ull) ? ex2f(s[nt][e] * sc - lse[e >> 1]) : 0.f;
           float dpe = dp[nt][e];
           if (drop) {
             const uint32_t row = static_cast<uint32_t>(m0 + g + 8 * (e >> 1));
@@ -677,6 +695,8 @@ __global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParam
     for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) { dk[nt][e] = 0.f; dv[nt][e] = 0.f; }
+    // a padded key took no part in the forward: its column of P is zero
+    const float kvalid[2] = {key_is_real(sKm, n0 + g) ? 1.f : 0.f, key_is_real(sKm, n0 + g + 8) ? 1.f : 0.f};
     for (int c0 = 0; c0 < p.Lq_pad; c0 += 64) {
       float st[8][4], dpt[8][4];
       xyT(st, ka, bQ, c0, lane);
@@ -687,7 +707,7 @@ __global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParam
         const float2 dd = *reinterpret_cast<const float2*>(sD + c0 + nt * 8 + 2 * tq);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float pr = ex2f(st[nt][e] * sc - ((e & 1) ? ls.y : ls.x));        // lse = +inf beyond Lq -> 0
+          const float pr = ex2f(st[nt][e] * sc - ((e & 1) ? ls.y : ls.x)) * kvalid[e >> 1];        // lse = +inf beyond Lq -> 0
           float mk = 1.f;
           if (drop) {
             const uint32_t qrow = static_cast<uint32_t>(c0 + nt * 8 + 2 * tq + (e & 1)), key = static_cast<uint32_t>(n0 + g + 8 * (e >> 1));
@@ -703,6 +723,215 @@ __global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParam
     store_tile(p.dk + item * p.dk_is + hoff, p.dk_rs, n0, p.Lk, dk, p.dk_mul, lane);
     store_tile(p.dv + item * p.dv_is + hoff, p.dv_rs, n0, p.Lk, dv, 1.f, lane);
   }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// The same backward for LONG sequences (Lq or Lk in 513 .. 1 280: 800 x 1 024 and 960 x 1 280 images at 1/32), where Q, K, V and dO
+// of a head no longer fit the shared memory of one CTA together.  Two launches:
+//   _q  : CTA = (head, item, 128 queries); K, V of the head resident, its Q / dO / O rows -> log-sum-exp, D, dQ; (lse, D) -> stats
+//   _kv : CTA = (head, item, 64 keys); Q, dO and the (lse, D) of all queries resident, its K / V rows -> dK, dV
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gwd_attention_bwd_mma_q_kernel(AttnBwdParams p) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int head = blockIdx.x, item = blockIdx.y, q0 = blockIdx.z * 128;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  uint32_t* sK = smem;
+  uint32_t* sV = sK + p.Lk_pad * kMW;
+  uint32_t* sQ = sV + p.Lk_pad * kMW;                  // [128]
+  uint32_t* sO = sQ + 128 * kMW;                       // dO [128]
+  float* sD = reinterpret_cast<float*>(sO + 128 * kMW);
+  unsigned long long* sKm = reinterpret_cast<unsigned long long*>(sD + 128);
+  const int64_t hoff = static_cast<int64_t>(head) * kHD;
+  build_key_mask(sKm, p, item);
+  {
+    const bf16* gq = p.q + item * p.q_is + hoff;
+    const bf16* gk = p.k + item * p.k_is + hoff;
+    const bf16* gv = p.v + item * p.v_is + hoff;
+    const bf16* gdo = p.d_o + item * p.do_is + hoff;
+    const bf16* go = p.o + item * p.o_is + hoff;
+    for (int i = threadIdx.x; i < p.Lk_pad * 16; i += 256) {
+      const int r = i >> 4, w = i & 15;
+      const bool in = r < p.Lk;
+      sK[r * kMW + w] = in ? *reinterpret_cast<const uint32_t*>(gk + r * p.k_rs + 2 * w) : 0u;
+      sV[r * kMW + w] = in ? *reinterpret_cast<const uint32_t*>(gv + r * p.v_rs + 2 * w) : 0u;
+    }
+    for (int i = threadIdx.x; i < 128 * 16; i += 256) {
+      const int r = i >> 4, w = i & 15;
+      const int64_t gr = q0 + r;
+      const bool in = gr < p.Lq;
+      const uint32_t dov = in ? *reinterpret_cast<const uint32_t*>(gdo + gr * p.do_rs + 2 * w) : 0u;
+      const uint32_t ov = in ? *reinterpret_cast<const uint32_t*>(go + gr * p.o_rs + 2 * w) : 0u;
+      sQ[r * kMW + w] = in ? *reinterpret_cast<const uint32_t*>(gq + gr * p.q_rs + 2 * w) : 0u;
+      sO[r * kMW + w] = dov;
+      const float2 a = gwd_unpack_bf16x2(dov), b = gwd_unpack_bf16x2(ov);
+      float d = a.x * b.x + a.y * b.y;
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      if (w == 0) sD[r] = d;
+    }
+  }
+  __syncthreads();
+  const uint32_t bQ = smem_u32(sQ), bK = smem_u32(sK), bV = smem_u32(sV), bO = smem_u32(sO);
+  const float sc = p.scale * kLog2eT;
+  const bool drop = p.drop_seed != nullptr;
+  const uint32_t drop_key = drop ? gwd_drop_key(*p.drop_seed, p.drop_site, static_cast<uint32_t>(item * p.heads + head)) : 0u;
+  const int ml = warp * 16, m0 = q0 + ml;              // local / global first query of this warp
+  if (m0 >= p.Lq) return;
+  uint32_t qa[2][4], oa[2][4];
+  load_a_tile(qa, bQ, ml, lane);
+  load_a_tile(oa, bO, ml, lane);
+  float mx[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+  for (int c0 = 0; c0 < p.Lk_pad; c0 += 64) {
+    float s[8][4];
+    xyT(s, qa, bK, c0, lane);
+    float cm[2] = {-INFINITY, -INFINITY};
+    const unsigned long long km = sKm[c0 >> 6] >> (2 * tq);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (!((km >> (nt * 8 + (e & 1))) & 1ull)) s[nt][e] = -INFINITY;
+        cm[e >> 1] = fmaxf(cm[e >> 1], s[nt][e]);
+      }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float mn = fmaxf(mx[h], cm[h]);
+      if (mn > -INFINITY) {
+        float add = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) add += ex2f((s[nt][2 * h] - mn) * sc) + ex2f((s[nt][2 * h + 1] - mn) * sc);
+        l[h] = l[h] * ex2f((mx[h] - mn) * sc) + add;
+        mx[h] = mn;
+      }
+    }
+  }
+  float lse[2], D[2];
+  float* st_out = p.stats + (static_cast<int64_t>(item) * p.heads + head) * p.Lq * 2;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float ma = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+    ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, 2));
+    float lh = l[h] * ex2f((mx[h] - ma) * sc);
+    lh += __shfl_xor_sync(0xffffffffu, lh, 1);
+    lh += __shfl_xor_sync(0xffffffffu, lh, 2);
+    lse[h] = ma * sc + __log2f(lh);
+    const int rl = ml + g + 8 * h;
+    D[h] = sD[rl];
+    if (tq == 0 && q0 + rl < p.Lq) {
+      st_out[(q0 + rl) * 2] = lse[h];
+      st_out[(q0 + rl) * 2 + 1] = D[h];
+    }
+  }
+  float dq[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) { dq[nt][0] = 0.f; dq[nt][1] = 0.f; dq[nt][2] = 0.f; dq[nt][3] = 0.f; }
+  for (int c0 = 0; c0 < p.Lk_pad; c0 += 64) {
+    float s[8][4], dp[8][4];
+    xyT(s, qa, bK, c0, lane);
+    xyT(dp, oa, bV, c0, lane);
+    const unsigned long long km = sKm[c0 >> 6] >> (2 * tq);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int col = c0 + nt * 8 + 2 * tq + (e & 1);
+        const float pr = ((km >> (nt * 8 + (e & 1))) & 1ull) ? ex2f(s[nt][e] * sc - lse[e >> 1]) : 0.f;
+        float dpe = dp[nt][e];
+        if (drop) {
+          const uint32_t row = static_cast<uint32_t>(m0 + g + 8 * (e >> 1));
+          dpe = gwd_drop_keep(drop_key, row * static_cast<uint32_t>(p.Lk) + col, p.drop_thr) ? dpe * p.drop_scale : 0.f;
+        }
+        s[nt][e] = pr * (dpe - D[e >> 1]);
+      }
+    fy(dq, s, bK, c0, lane);
+  }
+  store_tile(p.dq + item * p.dq_is + hoff, p.dq_rs, m0, p.Lq, dq, p.dq_mul, lane);
+}
+
+__global__ void __launch_bounds__(128) gwd_attention_bwd_mma_kv_kernel(AttnBwdParams p) {
+  extern __shared__ __align__(16) uint32_t smem[];
+  const int head = blockIdx.x, item = blockIdx.y, k0 = blockIdx.z * 64;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, tq = lane & 3;
+  uint32_t* sQ = smem;
+  uint32_t* sO = sQ + p.Lq_pad * kMW;                  // dO
+  uint32_t* sK = sO + p.Lq_pad * kMW;                  // [64]
+  uint32_t* sV = sK + 64 * kMW;
+  float* sLse = reinterpret_cast<float*>(sV + 64 * kMW);
+  float* sD = sLse + p.Lq_pad;
+  const int64_t hoff = static_cast<int64_t>(head) * kHD;
+  {
+    const bf16* gq = p.q + item * p.q_is + hoff;
+    const bf16* gk = p.k + item * p.k_is + hoff;
+    const bf16* gv = p.v + item * p.v_is + hoff;
+    const bf16* gdo = p.d_o + item * p.do_is + hoff;
+    const float* st_in = p.stats + (static_cast<int64_t>(item) * p.heads + head) * p.Lq * 2;
+    for (int i = threadIdx.x; i < 64 * 16; i += 128) {
+      const int r = i >> 4, w = i & 15;
+      const int64_t gr = k0 + r;
+      const bool in = gr < p.Lk;
+      sK[r * kMW + w] = in ? *reinterpret_cast<const uint32_t*>(gk + gr * p.k_rs + 2 * w) : 0u;
+      sV[r * kMW + w] = in ? *reinterpret_cast<const uint32_t*>(gv + gr * p.v_rs + 2 * w) : 0u;
+    }
+    for (int i = threadIdx.x; i < p.Lq_pad * 16; i += 128) {
+      const int r = i >> 4, w = i & 15;
+      const bool in = r < p.Lq;
+      sQ[r * kMW + w] = in ? *reinterpret_cast<const uint32_t*>(gq + r * p.q_rs + 2 * w) : 0u;
+      sO[r * kMW + w] = in ? *reinterpret_cast<const uint32_t*>(gdo + r * p.do_rs + 2 * w) : 0u;
+    }
+    for (int r = threadIdx.x; r < p.Lq_pad; r += 128) {
+      sLse[r] = r < p.Lq ? st_in[2 * r] : INFINITY;          // +inf = "no such query": its P is 0
+      sD[r] = r < p.Lq ? st_in[2 * r + 1] : 0.f;
+    }
+  }
+  __syncthreads();
+  const uint32_t bQ = smem_u32(sQ), bK = smem_u32(sK), bV = smem_u32(sV), bO = smem_u32(sO);
+  const float sc = p.scale * kLog2eT;
+  const bool drop = p.drop_seed != nullptr;
+  const uint32_t drop_key = drop ? gwd_drop_key(*p.drop_seed, p.drop_site, static_cast<uint32_t>(item * p.heads + head)) : 0u;
+  const int nl = warp * 16, n0 = k0 + nl;
+  if (n0 >= p.Lk) return;
+  uint32_t ka[2][4], va[2][4];
+  load_a_tile(ka, bK, nl, lane);
+  load_a_tile(va, bV, nl, lane);
+  float dk[4][4], dv[4][4];
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { dk[nt][e] = 0.f; dv[nt][e] = 0.f; }
+  float kvalid[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int key = n0 + g + 8 * h;
+    kvalid[h] = (key < p.Lk && !(p.key_padding != nullptr && p.key_padding[static_cast<int64_t>(item) * p.Lk + key])) ? 1.f : 0.f;
+  }
+  for (int c0 = 0; c0 < p.Lq_pad; c0 += 64) {
+    float st[8][4], dpt[8][4];
+    xyT(st, ka, bQ, c0, lane);
+    xyT(dpt, va, bO, c0, lane);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const float2 ls = *reinterpret_cast<const float2*>(sLse + c0 + nt * 8 + 2 * tq);
+      const float2 dd = *reinterpret_cast<const float2*>(sD + c0 + nt * 8 + 2 * tq);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pr = ex2f(st[nt][e] * sc - ((e & 1) ? ls.y : ls.x)) * kvalid[e >> 1];
+        float mk = 1.f;
+        if (drop) {
+          const uint32_t qrow = static_cast<uint32_t>(c0 + nt * 8 + 2 * tq + (e & 1)), key = static_cast<uint32_t>(n0 + g + 8 * (e >> 1));
+          mk = gwd_drop_keep(drop_key, qrow * static_cast<uint32_t>(p.Lk) + key, p.drop_thr) ? p.drop_scale : 0.f;
+        }
+        st[nt][e] = pr * mk;
+        dpt[nt][e] = pr * (dpt[nt][e] * mk - ((e & 1) ? dd.y : dd.x));
+      }
+    }
+    fy(dv, st, bO, c0, lane);
+    fy(dk, dpt, bQ, c0, lane);
+  }
+  store_tile(p.dk + item * p.dk_is + hoff, p.dk_rs, n0, p.Lk, dk, p.dk_mul, lane);
+  store_tile(p.dv + item * p.dv_is + hoff, p.dv_rs, n0, p.Lk, dv, 1.f, lane);
 }
 
 
@@ -1189,8 +1418,12 @@ extern "C" int gwd_attention_bwd(const gwd_attn_bwd_desc* d, void* stream_) {
   GWD_STREAM;
   GWD_CHECK_ARG(d && d->q && d->k && d->v && d->d_o && d->dq && d->dk && d->dv, "gwd_attention_bwd: null pointer");
   GWD_CHECK_ARG(d->hd == kHD, "gwd_attention_bwd: head dim must be 32 (got %d)", d->hd);
-  GWD_CHECK_ARG(d->items > 0 && d->heads > 0 && d->Lq > 0 && d->Lk > 0 && d->Lk <= 512 && d->Lq <= 512,
-                "gwd_attention_bwd: 1 <= Lq, Lk <= 512");
+  const bool long_seq = d->Lq > 512 || d->Lk > 512;
+  GWD_CHECK_ARG(d->items > 0 && d->heads > 0 && d->Lq > 0 && d->Lk > 0 && d->Lk <= 1280 && d->Lq <= 1280,
+                "gwd_attention_bwd: 1 <= Lq, Lk <= 1280");
+  GWD_CHECK_ARG(!long_seq || (d->o != nullptr && d->stats_ws != nullptr),
+                "gwd_attention_bwd: sequences beyond 512 need the forward output `o` and the stats_ws scratch (items x heads x Lq x 2 floats)");
+  GWD_CHECK_ARG(d->key_padding == nullptr || d->o != nullptr, "gwd_attention_bwd: key_padding needs the forward output `o` (tensor-core kernels)");
   const int64_t strides[14] = {d->q_item_stride, d->q_row_stride, d->k_item_stride, d->k_row_stride, d->v_item_stride,
                                d->v_row_stride, d->do_item_stride, d->do_row_stride, d->dq_item_stride, d->dq_row_stride,
                                d->dk_item_stride, d->dk_row_stride, d->dv_item_stride, d->dv_row_stride};
@@ -1209,6 +1442,7 @@ extern "C" int gwd_attention_bwd(const gwd_attn_bwd_desc* d, void* stream_) {
   p.dq_mul = d->dq_mul != 0.f ? d->dq_mul : d->scale;
   p.dk_mul = d->dk_mul != 0.f ? d->dk_mul : d->scale;
   p.drop_seed = nullptr; p.drop_site = 0; p.drop_thr = 0; p.drop_scale = 1.f; p.heads = d->heads;
+  p.key_padding = d->key_padding; p.stats = d->stats_ws;
   if (d->dropout_seed != nullptr && d->dropout_p > 0.f) {
     GWD_CHECK_ARG(d->o != nullptr, "gwd_attention_bwd: dropout needs the forward output `o` (tensor-core kernel)");
     p.drop_seed = d->dropout_seed; p.drop_site = d->dropout_site;
@@ -1224,12 +1458,25 @@ extern "C" int gwd_attention_bwd(const gwd_attn_bwd_desc* d, void* stream_) {
     p.o = static_cast<const bf16*>(d->o); p.o_is = d->o_item_stride; p.o_rs = d->o_row_stride;
     p.Lq_pad = static_cast<int>(gwd_ceil_div(d->Lq, 64)) * 64;
     p.Lk_pad = static_cast<int>(gwd_ceil_div(d->Lk, 64)) * 64;
-    const size_t sm = static_cast<size_t>(2 * p.Lq_pad + 2 * p.Lk_pad) * kMW * 4 + static_cast<size_t>(2 * p.Lq_pad) * 4;
+    if (long_seq) {
+      const size_t sm_q = static_cast<size_t>(2 * p.Lk_pad + 256) * kMW * 4 + 128 * 4 + static_cast<size_t>(p.Lk_pad / 64) * 8;
+      const size_t sm_kv = static_cast<size_t>(2 * p.Lq_pad + 128) * kMW * 4 + static_cast<size_t>(2 * p.Lq_pad) * 4;
+      GWD_CUDA(cudaFuncSetAttribute(gwd_attention_bwd_mma_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_q)));
+      GWD_CUDA(cudaFuncSetAttribute(gwd_attention_bwd_mma_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm_kv)));
+      gwd_attention_bwd_mma_q_kernel<<<dim3(d->heads, d->items, static_cast<unsigned>(gwd_ceil_div(d->Lq, 128))), 256, sm_q, stream>>>(p);
+      GWD_LAUNCHED();
+      gwd_attention_bwd_mma_kv_kernel<<<dim3(d->heads, d->items, static_cast<unsigned>(gwd_ceil_div(d->Lk, 64))), 128, sm_kv, stream>>>(p);
+      GWD_LAUNCHED();
+      return GWD_OK;
+    }
+    const size_t sm = static_cast<size_t>(2 * p.Lq_pad + 2 * p.Lk_pad) * kMW * 4 + static_cast<size_t>(2 * p.Lq_pad) * 4 +
+                      static_cast<size_t>(p.Lk_pad / 64) * 8;
     GWD_CUDA(cudaFuncSetAttribute(gwd_attention_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)));
     gwd_attention_bwd_mma_kernel<<<grid, 256, sm, stream>>>(p);
     GWD_LAUNCHED();
     return GWD_OK;
   }
+  GWD_CHECK_ARG(!long_seq, "gwd_attention_bwd: sequences beyond 512 need the tensor-core path");
   const size_t smem = static_cast<size_t>(2 * d->Lq + 2 * d->Lk) * kRowW * 4 + static_cast<size_t>(2 * d->Lq) * 4;
   auto launch = [&](auto kern) -> int {
     GWD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

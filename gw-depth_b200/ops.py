@@ -834,8 +834,10 @@ def unpack_conv3x3_grad(dw, n, c):
 
 
 def attention_bwd(q, k, v, d_o, dq, dk, dv, *, items, heads, Lq, Lk, hd, q_strides, k_strides, v_strides, do_strides,
-                  dq_strides, dk_strides, dv_strides, scale=1.0, o=None, o_strides=None, dq_mul=0.0, dk_mul=0.0, dropout=None):
-    """o: the forward output (bf16) -> tensor-core kernel; None -> CUDA-core kernel that recomputes D = rowsum(P dP)"""
+                  dq_strides, dk_strides, dv_strides, scale=1.0, o=None, o_strides=None, dq_mul=0.0, dk_mul=0.0, dropout=None,
+                  key_padding=None):
+    """o: the forward output (bf16) -> tensor-core kernel; None -> CUDA-core kernel that recomputes D = rowsum(P dP).
+    key_padding: uint8 / bool [items, Lk], 1 = padded key.  Lq, Lk <= 1280 (beyond 512: two launches + a scratch, needs o)"""
     d = capi.AttnBwdDesc()
     d.q, d.k, d.v, d.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), d_o.data_ptr()
     d.dq, d.dk, d.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
@@ -853,6 +855,14 @@ def attention_bwd(q, k, v, d_o, dq, dk, dv, *, items, heads, Lq, Lk, hd, q_strid
         d.o_item_stride, d.o_row_stride = o_strides or do_strides
     if dropout is not None:
         d.dropout_seed, d.dropout_site, d.dropout_p = dropout[0].data_ptr(), int(dropout[1]), float(dropout[2])
+    if key_padding is not None:
+        kp = key_padding.to(torch.uint8) if key_padding.dtype != torch.uint8 else key_padding
+        assert kp.is_contiguous() and kp.numel() == items * Lk
+        d.key_padding = kp.data_ptr()
+    ws = None
+    if Lq > 512 or Lk > 512:
+        ws = torch.empty(items * heads * Lq * 2, dtype=torch.float32, device=q.device)
+        d.stats_ws = ws.data_ptr()
     capi.check(_L().gwd_attention_bwd(ctypes.byref(d), _stream()), "gwd_attention_bwd")
 
 

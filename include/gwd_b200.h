@@ -324,7 +324,8 @@ int gwd_conv3x3_wgrad(const void* dy, int64_t dy_cs, const void* x, int64_t x_cs
                       int32_t C, float* dw, float* db, void* stream);
 /* backward of O = softmax(scale Q K^T) V for head_dim 32, Lq, Lk <= 512 (no bias / mask): the soft-max is recomputed
  * from Q, K; dQ, dK, dV are bf16 views addressed like gwd_attn_desc.  With the forward output `o` given the kernel runs
- * on the tensor cores (mma.sync; D_i = dO_i . O_i); with o == NULL a CUDA-core kernel computes D itself. */
+ * on the tensor cores (mma.sync; D_i = dO_i . O_i); with o == NULL a CUDA-core kernel computes D itself (Lq, Lk <= 512, no mask).
+ * Lq, Lk <= 1280. */
 typedef struct gwd_attn_bwd_desc {
   const void* q; const void* k; const void* v; const void* d_o;
   void* dq; void* dk; void* dv;
@@ -340,6 +341,9 @@ typedef struct gwd_attn_bwd_desc {
   const uint32_t* dropout_seed;   /* as in gwd_attn_desc: the forward's mask is regenerated (needs `o`, the forward output) */
   uint32_t dropout_site;
   float dropout_p;
+  const uint8_t* key_padding;     /* [items, Lk], 1 = padded key (nn.MultiheadAttention key_padding_mask), or NULL (needs `o`) */
+  float* stats_ws;                /* Lq or Lk in 513..1280 (two launches: per-query-block, per-key-block): fp32 scratch
+                                     [items * heads * Lq * 2]; may be NULL for shorter sequences */
 } gwd_attn_bwd_desc;
 int gwd_attention_bwd(const gwd_attn_bwd_desc* d, void* stream);
 /* SetCriterion forward + backward for all S decoder stages in one launch (src/models/glassrgbd.py:154-175,231-244,308-358):

@@ -260,6 +260,49 @@ def test_attention_bwd(B, Lq, Lk, fused, use_o):
     assert rel_l2(dv, flat(vh.grad, Lk)) < tol
 
 
+@pytest.mark.parametrize("B,Lq,Lk,pad", [(2, 300, 300, True), (3, 100, 300, True), (1, 850, 850, False), (2, 800, 800, True), (2, 100, 1216, True),
+                                        (1, 1200, 1200, False), (1, 513, 64, False), (1, 1280, 1280, True)])
+def test_attention_bwd_masks_and_long_sequences(B, Lq, Lk, pad):
+    """gwd_attention_bwd with a key-padding mask (padded batches: src_key_padding_mask of nn.MultiheadAttention) and on sequences
+    beyond 512 tokens (two launches: per query block with K, V resident, per key block with Q, dO resident) vs torch.autograd"""
+    ops = _ops()
+    heads, hd = 8, 32
+    E = heads * hd
+    g = _g(Lq * 3 + Lk + int(pad))
+    scale = hd ** -0.5
+    q = torch.randn(B * Lq, E, generator=g).bfloat16().cuda()
+    k = torch.randn(B * Lk, E, generator=g).bfloat16().cuda()
+    v = torch.randn(B * Lk, E, generator=g).bfloat16().cuda()
+    d_o = torch.randn(B * Lq, E, generator=g).bfloat16().cuda()
+    mask = torch.zeros(B, Lk, dtype=torch.bool)
+    if pad:          # ragged tails + a hole, different per image
+        for b in range(B):
+            mask[b, Lk - 17 - 40 * b:] = True
+            mask[b, 5 + b:9 + b] = True
+
+    def heads_of(t, L):
+        return t.float().view(B, L, heads, hd).permute(0, 2, 1, 3).clone().requires_grad_(True)
+    qh, kh, vh = heads_of(q, Lq), heads_of(k, Lk), heads_of(v, Lk)
+    sc = qh @ kh.transpose(-1, -2) * scale
+    sc = sc.masked_fill(mask.cuda()[:, None, None, :], float("-inf"))
+    o = torch.softmax(sc, dim=-1) @ vh
+    o.backward(d_o.float().view(B, Lq, heads, hd).permute(0, 2, 1, 3))
+    flat = lambda t, L: t.permute(0, 2, 1, 3).reshape(B * L, E)
+    dq = torch.empty(B * Lq, E, dtype=torch.bfloat16, device="cuda")
+    dk = torch.full((B * Lk, E), 7.0, dtype=torch.bfloat16, device="cuda")
+    dv = torch.full((B * Lk, E), 7.0, dtype=torch.bfloat16, device="cuda")
+    o_fwd = flat(o.detach(), Lq).bfloat16().contiguous()
+    ops.attention_bwd(q, k, v, d_o, dq, dk, dv, items=B, heads=heads, Lq=Lq, Lk=Lk, hd=hd, q_strides=(Lq * E, E), k_strides=(Lk * E, E),
+                      v_strides=(Lk * E, E), do_strides=(Lq * E, E), dq_strides=(Lq * E, E), dk_strides=(Lk * E, E), dv_strides=(Lk * E, E),
+                      scale=scale, o=o_fwd, o_strides=(Lq * E, E), key_padding=mask.cuda() if pad else None)
+    assert rel_l2(dq, flat(qh.grad, Lq)) < 1e-2
+    assert rel_l2(dk, flat(kh.grad, Lk)) < 1e-2
+    assert rel_l2(dv, flat(vh.grad, Lk)) < 1e-2
+    if pad:          # padded keys get exact zeros
+        m = mask.view(-1).cuda()
+        assert (dk[m] == 0).all() and (dv[m] == 0).all()
+
+
 @pytest.mark.parametrize("max_norm,world", [(0.1, 1), (0.0, 1), (0.1, 2)])
 def test_fused_clip_adamw_matches_torch(max_norm, world):
     ops = _ops()
