@@ -132,6 +132,39 @@ def test_whole_model_gradients_match_oracle_autograd():
     assert not bad, bad
 
 
+def test_training_step_beyond_512_tokens():
+    """a training step on 544 x 1024 images (17 x 32 = 544 tokens at 1/32: the long-sequence attention backward, the key-tiled forward
+    kernel): total loss equals the oracle's, every trained tensor gets a finite, non-zero gradient"""
+    M, Trainer = _mods()
+    B, H, W = 1, 544, 1024
+    images, targets, depth_gt, seg_gt = synth.synth_batch(B, H, W, seed=3)
+    sd = synth_weights()
+    _, crit, _ = M.build_model(M.default_args(device="cuda", dropout=0.0))
+    wd = crit[0].weight_dict
+    trace = {}
+    with torch.no_grad():
+        out = oracle.forward(sd, images, trace=trace)
+        set_l, idx = oracle.set_criterion(out, [t["lines"] for t in targets])
+        total = float(sum(v * wd[k] for k, v in set_l.items()) + sum(oracle.depth_losses(out["pred_depth"], depth_gt)) +
+                      oracle.seg_loss(out["pred_seg"], seg_gt))
+    tr = Trainer(sd)
+    pinned = {"line_ids": trace["line_ids"].cuda(), "sample1": trace["sample1"].cuda(), "sample2": trace["sample2"].cuda()}
+    tg = [{k: v.cuda() for k, v in t.items()} for t in targets]
+    logits, lines, outs = tr.forward(images.cuda(), pinned)
+    g = tr.dense.loss_grads(outs, depth_gt.cuda(), seg_gt.cuda())
+    tr.backward_dense(*g)
+    _, dlogits, dlines = crit[0].cuda().forward_backward_stacked(logits, lines, tg, pinned_pairs=idx[1:] + idx[:1])
+    tr.backward_line(dlogits, dlines)
+    got_total = float(crit[0].last_total + tr.dense.losses().sum())
+    assert abs(got_total - total) < 1e-2 * abs(total), (got_total, total)
+    grads = tr.grads()
+    assert len(grads) == 684
+    for k, v in grads.items():
+        assert torch.isfinite(v).all(), k
+    enc = [v for k, v in grads.items() if k.startswith("transformer.encoder.layers.0.self_attn")]
+    assert enc and all(float(v.abs().max()) > 0 for v in enc)
+
+
 def _loader(B, H, W, steps, NestedTensor):
     for s in range(steps):
         images, targets, depth_gt, seg_gt = synth.synth_batch(B, H, W, seed=s)
