@@ -39,8 +39,10 @@ class NestedTensor(object):
         return str(self.tensors)
 
 
-def nested_tensor_from_tensor_list(tensor_list):
-    """pad a list of [C,H,W] images to a common size; mask is True on padding (src/util/misc.py:291-313)"""
+def nested_tensor_from_tensor_list(tensor_list, size_divisibility=1):
+    """pad a list of [C,H,W] images to a common size; mask is True on padding (src/util/misc.py:291-313).  size_divisibility (an
+    extension; the reference pads to the largest image only): round the common size up to a multiple -- 32 for TRAINING on ragged
+    batches, whose backward kernels want exact x2 pyramids; the extra rows / columns are ordinary padding (zeros, mask True)."""
     if isinstance(tensor_list, torch.Tensor) and tensor_list.dim() == 4:
         tensor_list = list(tensor_list)
     if tensor_list[0].dim() != 3:
@@ -48,6 +50,9 @@ def nested_tensor_from_tensor_list(tensor_list):
     c = tensor_list[0].shape[0]
     hmax = max(t.shape[1] for t in tensor_list)
     wmax = max(t.shape[2] for t in tensor_list)
+    if size_divisibility > 1:
+        hmax = -(-hmax // size_divisibility) * size_divisibility
+        wmax = -(-wmax // size_divisibility) * size_divisibility
     batch = tensor_list[0].new_zeros((len(tensor_list), c, hmax, wmax))
     mask = torch.ones((len(tensor_list), hmax, wmax), dtype=torch.bool, device=batch.device)
     for i, t in enumerate(tensor_list):
@@ -119,10 +124,10 @@ class _TrainStep(torch.autograd.Function):
     the 54 never-used tensors are not inputs, which is what find_unused_parameters=True expects)."""
 
     @staticmethod
-    def forward(ctx, module, images, pinned, *params):
+    def forward(ctx, module, images, pinned, mask, *params):
         tr = module.trainer()
         with torch.no_grad():
-            logits, lines, outs = tr.forward(images, pinned)
+            logits, lines, outs = tr.forward(images, pinned, mask=mask)
         d1, d2, d3, depth = outs["pred_depth"]
         ctx.module, ctx.depth = module, depth
         ctx.shapes = [tuple(t.shape) for t in (logits, lines, d1, d2, d3, depth, outs["pred_seg"])]
@@ -147,7 +152,7 @@ class _TrainStep(torch.autograd.Function):
             tr.backward_line(g_logits, g_lines)
             grads = tr.grads()
             out = tuple(grads[n].clone() for n, _ in module.__dict__["_live"])
-        return (None, None, None) + out
+        return (None, None, None, None) + out
 
 
 class GlassRGBD(_Node):
@@ -279,8 +284,9 @@ class GlassRGBD(_Node):
         padded = getattr(samples, "padded", None)
         if mask is not None and padded is None:
             padded = bool(mask.any())
-        if padded:
-            raise NotImplementedError("training on padded (ragged) batches is not built: collate equal-size images")
+        if padded and (images.shape[-2] % 32 or images.shape[-1] % 32):
+            raise NotImplementedError("training on a ragged batch needs the batch padded to a multiple of 32: collate with "
+                                      "nested_tensor_from_tensor_list(..., size_divisibility=32)")
         tr = self.trainer()
         vers = self._param_versions()
         if vers != self.__dict__["_trainer_versions"]:        # an optimizer (or load_state_dict) changed the nn.Parameters
@@ -289,7 +295,8 @@ class GlassRGBD(_Node):
         tr.exchange_grads = False          # the caller's DistributedDataParallel (or nobody) reduces the .grad tensors
         live = self.__dict__["_live"]
         with torch.cuda.device(images.device):
-            res = _TrainStep.apply(self, images.float().contiguous(), pinned, *[p for _, p in live])
+            res = _TrainStep.apply(self, images.float().contiguous(), pinned, mask.to(images.device) if padded else None,
+                                   *[p for _, p in live])
         logits, lines, d1, d2, d3, depth, seg = res
         out = {"pred_logits": logits[-1], "pred_lines": lines[-1]}
         if self.cfg["aux_loss"]:

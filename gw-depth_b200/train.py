@@ -24,7 +24,7 @@ dC5 so that a backbone backward can be attached.
 import torch
 
 from . import ops, parallel
-from .engine import DEFAULT_CFG, sine_table
+from .engine import DEFAULT_CFG, sine_table, sine_tables_masked
 from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID, RES_AFTER, RES_BEFORE_NORM, RES_NONE, PackedWeight, conv_gemm, round_up
 
 PREFIXES = ("input_proj.", "query_embed.", "transformer.", "class_embed.", "lines_embed.")
@@ -164,11 +164,12 @@ class LineBranch:
     def _drop(self, site):
         return (self.drop_seed, site, self.p_drop) if self.p_drop > 0 else None
 
-    def _attend(self, q, k, v, B, Lq, Lk, q_rs, k_rs, site=0):
+    def _attend(self, q, k, v, B, Lq, Lk, q_rs, k_rs, site=0, kpm=None):
         E, nh = self.cfg["hidden_dim"], self.cfg["nheads"]
         o = torch.empty(B * Lq, E, dtype=torch.bfloat16, device=self.dev)
         ops.attention(q, k, v, o, items=B, heads=nh, Lq=Lq, Lk=Lk, hd=E // nh, q_strides=(Lq * q_rs, q_rs),
-                      k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E), o_strides=(Lq * E, E), dropout=self._drop(site))
+                      k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E), o_strides=(Lq * E, E), dropout=self._drop(site),
+                      key_padding=kpm)
         return o
 
     def _fork_gemm(self, x, lin):
@@ -194,17 +195,23 @@ class LineBranch:
             ops.dropout(hm, self.drop_seed, site, self.p_drop, out=hm)
         return hm
 
-    def forward(self, c5):
-        """c5: bf16 channels-last [B, h, w, 2048] (no gradient flows further back).  Returns fp32 (logits [6,B,Q,2],
-        lines [6,B,Q,6]) and keeps the tape for `backward`."""
+    def forward(self, c5, mask5=None):
+        """c5: bf16 channels-last [B, h, w, 2048] (no gradient flows further back); mask5: None, or the bool [B,h,w] padding mask of a
+        ragged batch at this level (True = padding): per-image position codes and a key-padding mask on the encoder self-attention and
+        the decoder cross-attention (src/models/transformer.py:52-57).  Returns fp32 (logits [6,B,Q,2], lines [6,B,Q,6]) and keeps the
+        tape for `backward`."""
         c = self.cfg
         B, h, w, _ = c5.shape
         E, L, Q = c["hidden_dim"], h * w, c["num_queries"]
-        key = ("pos5", h, w)
-        if key not in self._tables:
-            self._tables[key] = sine_table(h, w, E // 2, True, self.dev).to(torch.bfloat16)
-        pos = self._tables[key]
-        tp = self.tape = {"B": B, "L": L, "enc": [], "dec": []}
+        if mask5 is None:
+            key = ("pos5", h, w)
+            if key not in self._tables:
+                self._tables[key] = sine_table(h, w, E // 2, True, self.dev).to(torch.bfloat16)
+            pos, period, kpm = self._tables[key], L, None
+        else:
+            pos, period = sine_tables_masked(mask5, E // 2, True).view(B * L, E).to(torch.bfloat16), B * L
+            kpm = mask5.reshape(B, L).to(torch.uint8).contiguous()
+        tp = self.tape = {"B": B, "L": L, "enc": [], "dec": [], "kpm": kpm}
         if self.p_drop > 0:
             self.drop_seed.add_(1)          # new masks every step (captured: every graph replay increments it too)
         tp["c5"] = c5.reshape(B * L, c5.shape[-1])
@@ -212,18 +219,18 @@ class LineBranch:
         for li, ly in enumerate(self.enc):
             a = ly["attn"]
             st = 10 * li
-            xp = ops.add_rows(x, pos, L)
+            xp = ops.add_rows(x, pos, period)
             v = self._fork_gemm(x, a["v"])
             qk = conv_gemm(xp, a["qk"].pw, out_scale=self.rs)
             torch.cuda.current_stream().wait_stream(self._side)
-            o = self._attend(qk, qk[:, E:], v, B, L, L, 2 * E, 2 * E, site=st + 1)
+            o = self._attend(qk, qk[:, E:], v, B, L, L, 2 * E, 2 * E, site=st + 1, kpm=kpm)
             x1, z1 = self._ln_gemm(o, a["o"], x, ly["n1"], site=st + 2)
             hm = self._ffn_hidden(x1, ly["l1"], st + 3)
             x2, z2 = self._ln_gemm(hm, ly["l2"], x1, ly["n2"], site=st + 4)
             tp["enc"].append(dict(x=x, xp=xp, qk=qk, v=v, o=o, z1=z1, x1=x1, h=hm, z2=z2))
             x = x2
         memory = x
-        mem_pos = ops.add_rows(memory, pos, L)
+        mem_pos = ops.add_rows(memory, pos, period)
         tp["memory"], tp["mem_pos"] = memory, mem_pos
         tgt = torch.zeros(B * Q, E, dtype=torch.bfloat16, device=self.dev)
         hs = torch.empty(len(self.dec), B * Q, E, dtype=torch.bfloat16, device=self.dev)
@@ -249,7 +256,7 @@ class LineBranch:
             ck, cv = ckv[i]
             if i == 0:
                 torch.cuda.current_stream().wait_stream(self._side2)
-            o2 = self._attend(cq, ck, cv, B, Q, L, E, E, site=st + 3)
+            o2 = self._attend(cq, ck, cv, B, Q, L, E, E, site=st + 3, kpm=kpm)
             x2, z2 = self._ln_gemm(o2, cr["o"], x1, ly["n2"], site=st + 4)
             hm = self._ffn_hidden(x2, ly["l1"], st + 5)
             x3, z3 = self._ln_gemm(hm, ly["l2"], x2, ly["n3"], site=st + 6)
@@ -287,13 +294,14 @@ class LineBranch:
         """gradient of the sub-layer output from the gradient of the pre-LayerNorm sum z = res + dropout(y)"""
         return ops.dropout(dz, self.drop_seed, site, self.p_drop) if self.p_drop > 0 else dz
 
-    def _attend_bwd(self, q, k, v, o, d_o, B, Lq, Lk, q_rs, k_rs, dq, dk, dv, fused=True, site=0):
+    def _attend_bwd(self, q, k, v, o, d_o, B, Lq, Lk, q_rs, k_rs, dq, dk, dv, fused=True, site=0, kpm=None):
         E, nh = self.cfg["hidden_dim"], self.cfg["nheads"]
         ops.attention_bwd(q, k, v, d_o, dq, dk, dv, items=B, heads=nh, Lq=Lq, Lk=Lk, hd=E // nh,
                           q_strides=(Lq * q_rs, q_rs), k_strides=(Lk * k_rs, k_rs), v_strides=(Lk * E, E),
                           do_strides=(Lq * E, E), dq_strides=(Lq * q_rs, q_rs), dk_strides=(Lk * k_rs, k_rs),
                           dv_strides=(Lk * E, E), scale=1.0, o=o, o_strides=(Lq * E, E),
-                          dq_mul=self.rs if fused else self.rs * self.rs, dk_mul=self.rs if fused else 1.0, dropout=self._drop(site))
+                          dq_mul=self.rs if fused else self.rs * self.rs, dk_mul=self.rs if fused else 1.0, dropout=self._drop(site),
+                          key_padding=kpm)
 
     def _ffn_bwd(self, ly, d_out, z, hm, x_in, ln, site_hidden=0, site_out=0):
         dz = self._ln_bwd(d_out, z, ln)
@@ -334,7 +342,7 @@ class LineBranch:
             dz2 = self._ln_bwd(d_x2, s["z2"], ly["n2"])
             d_o = self._lin_bwd(cr["o"], self._sub_grad(dz2, st + 4), s["o2"])
             dq, dk, dv = torch.empty(B * Q, E, **bf), torch.empty(B * L, E, **bf), torch.empty(B * L, E, **bf)
-            self._attend_bwd(s["cq"], s["ck"], s["cv"], s["o2"], d_o, B, Q, L, E, E, dq, dk, dv, fused=False, site=st + 3)
+            self._attend_bwd(s["cq"], s["ck"], s["cv"], s["o2"], d_o, B, Q, L, E, E, dq, dk, dv, fused=False, site=st + 3, kpm=tp["kpm"])
             dtq = self._lin_bwd(cr["q"], dq, s["tq2"])
             gq += dtq.view(B, Q, E).sum(0, dtype=torch.float32)
             d_x1 = self._add(dtq, dz2)
@@ -360,7 +368,8 @@ class LineBranch:
             dz1 = self._ln_bwd(d_x1, s["z1"], ly["n1"])
             d_o = self._lin_bwd(a["o"], self._sub_grad(dz1, st + 2), s["o"])
             dqk, dv = torch.empty(B * L, 2 * E, **bf), torch.empty(B * L, E, **bf)
-            self._attend_bwd(s["qk"], s["qk"][:, E:], s["v"], s["o"], d_o, B, L, L, 2 * E, 2 * E, dqk, dqk[:, E:], dv, site=st + 1)
+            self._attend_bwd(s["qk"], s["qk"][:, E:], s["v"], s["o"], d_o, B, L, L, 2 * E, 2 * E, dqk, dqk[:, E:], dv, site=st + 1,
+                             kpm=tp["kpm"])
             t = self._lin_bwd(a["qk"], dqk, s["xp"], res=dz1)
             d_x = self._lin_bwd(a["v"], dv, s["x"], res=t)
         dc5 = self._lin_bwd(self.input_proj, d_x, tp["c5"])

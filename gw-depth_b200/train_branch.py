@@ -15,7 +15,7 @@ d(C4), d(C3) (the backbone; C2 comes from the frozen layer1 and needs no gradien
 import torch
 
 from . import ops
-from .engine import DEFAULT_CFG, sine_table
+from .engine import DEFAULT_CFG, sine_table, sine_tables_masked
 from .train_entry import DepthHead16, StageEntry
 from .train_flat import FlatModule
 from .train_points import PointPred
@@ -63,7 +63,9 @@ class DenseBranch:
             g.update(m.grads())
         return g
 
-    def _table(self, H, W, C):
+    def _table(self, H, W, C, pad_mask=None):
+        if pad_mask is not None:        # ragged batch: per-image position codes from the padding mask of this level
+            return sine_tables_masked(pad_mask, C // 2, False)
         key = (H, W, C)
         if key not in self._pos:
             self._pos[key] = sine_table(H, W, C // 2, False, self.dev)
@@ -102,7 +104,7 @@ class DenseBranch:
         st["graph"].replay()
         return st["result"]
 
-    def forward(self, x32, depth0, feats, H, W, pinned=None):
+    def forward(self, x32, depth0, feats, H, W, pinned=None, pad_masks=None):
         """x32 bf16 [B,h,w,D] (output of the 1/32 line-window stage); depth0 fp32 [B,h,w] (depth_pred32 of it, only feeds the
         sampling); feats = (C4, C3, C2) bf16 channels-last backbone maps at 1/16, 1/8, 1/4; (H, W): the input size; pinned:
         optional {'sample1', 'sample2'} coordinates overriding the uncertainty sampling.  Returns the outputs dict
@@ -125,7 +127,7 @@ class DenseBranch:
         x2, d2, t2 = s2.forward(x, d, s, B, H2, W2)
         buf2 = torch.cat([x2, d2], dim=1)
         coords1 = coords1.reshape(B, -1, 2).float().contiguous()
-        depth2 = self.point1.forward(buf2, depth1, coords1, self._table(H2, W2, C2), B, H2, W2)
+        depth2 = self.point1.forward(buf2, depth1, coords1, self._table(H2, W2, C2, None if pad_masks is None else pad_masks[1]), B, H2, W2)
         coords2 = pinned["sample2"] if "sample2" in pinned else ops.certain_sample(depth1, depth2, c["interval_sample_num"][1], self.edges)[0]
         # ---- 1/4 + head
         x, d, s = e3.forward(x2.view(B, H2, W2, C2), d2, t2, feats[2])
@@ -134,7 +136,7 @@ class DenseBranch:
         b2d = buf4.view(-1, C3 + 3 * td)
         b2d[:, :C3], b2d[:, C3:C3 + td], b2d[:, C3 + td:C3 + 2 * td] = x3, d3, t3
         coords2 = coords2.reshape(B, -1, 2).float().contiguous()
-        depth3, depth, seg = self.tail.forward(buf4, depth2, coords2, self._table(H3, W3, C3), H, W)
+        depth3, depth, seg = self.tail.forward(buf4, depth2, coords2, self._table(H3, W3, C3, None if pad_masks is None else pad_masks[2]), H, W)
         self._shapes = (B, (H1, W1), (H2, W2), (H3, W3))
         return dict(pred_depth=[depth1, depth2, depth3, depth], pred_seg=seg, sample1=coords1, sample2=coords2)
 

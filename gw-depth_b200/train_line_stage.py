@@ -33,7 +33,7 @@ B200 design
 import torch
 
 from . import ops
-from .engine import shift_mask, sine_table, _compose
+from .engine import shift_mask, sine_table, sine_tables_masked, _compose
 from .ops import ACT_GELU, ACT_SIGMOID, RES_AFTER, PackedWeight, conv_gemm, pack_linear
 from .train_flat import join_wgrads, FlatModule, Linear
 
@@ -118,7 +118,7 @@ class LineStage(FlatModule):
         return self._tables[key]
 
     # ------------------------------------------------------------------ forward
-    def forward(self, c5, ref_xy):
+    def forward(self, c5, ref_xy, pad_mask=None):
         """c5 bf16 [B,h,w,2048] (backbone C5, channels-last); ref_xy fp32 [B,R,2] reference points in [-1,1] (no gradient).
         Returns x32 bf16 [B,h,w,D] and depth0 fp32 [B,h,w] (depth_pred32: feeds the uncertainty sampling only)."""
         B, H, W, _ = c5.shape
@@ -127,7 +127,9 @@ class LineStage(FlatModule):
         Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
         nW = (Hp // ws) * (Wp // ws)
         P = nW * N
-        pos = self._table(("pos", H, W), lambda: sine_table(H, W, D // 2, False, self.dev))
+        # pad_mask: bool [B,H,W] padding mask of a ragged batch at this level -> per-image position codes (multiscale_transformerr.py:1035)
+        pos = (self._table(("pos", H, W), lambda: sine_table(H, W, D // 2, False, self.dev)) if pad_mask is None
+               else sine_tables_masked(pad_mask, D // 2, False))
         mask = self._table(("mask", H, W), lambda: shift_mask(H, W, ws, ws // 2, self.dev))
         c5tok = c5.reshape(B * H * W, c5.shape[-1])
         x = conv_gemm(c5tok, self.dip.pw)

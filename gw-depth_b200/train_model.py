@@ -26,7 +26,7 @@ import torch
 import torch.distributed as dist
 
 from . import ops, parallel
-from .engine import DEFAULT_CFG
+from .engine import level_mask, DEFAULT_CFG
 from .train import LineBranch
 from .train_backbone import BackboneTrain
 from .train_branch import DenseBranch
@@ -122,8 +122,9 @@ class Trainer:
         c = self.cfg
         return ops.select_lines(logits.contiguous(), lines.contiguous(), c["num_ref"], 3 if c["with_dense_center"] else 2)
 
-    def forward(self, images, pinned=None, after_line=None):
-        """images fp32 [B,3,H,W] (equal sizes, H and W multiples of 32).  Returns (logits [S,B,Q,2], lines [S,B,Q,D] fp32 of all
+    def forward(self, images, pinned=None, after_line=None, mask=None):
+        """images fp32 [B,3,H,W] (H and W multiples of 32); mask: None for an equal-size batch, else the bool [B,H,W] padding mask
+        of nested_tensor_from_tensor_list (True = padding; the batch must be padded to a multiple of 32).  Returns (logits [S,B,Q,2], lines [S,B,Q,D] fp32 of all
         decoder stages, final stage LAST; dense outputs dict of DenseBranch.forward).  `after_line(logits, lines)` is called as
         soon as the line branch is enqueued (the fused step starts the matching there)."""
         B, _, H, W = images.shape
@@ -133,7 +134,8 @@ class Trainer:
         bb = self.backbone
         c2 = bb.frozen_front(images.float().contiguous())
         c3, c4, c5 = bb.forward(c2)
-        logits, lines = self.line.forward(c5)
+        masks = None if mask is None else [level_mask(mask, f.shape[1:3]) for f in (c2, c3, c4, c5)]
+        logits, lines = self.line.forward(c5, None if masks is None else masks[3])
         if after_line is not None:
             after_line(logits, lines)
         if "line_ids" in pinned:
@@ -143,8 +145,9 @@ class Trainer:
             ref_xy = (pts if self.cfg["with_dense_center"] else pts[:, :, :2]).reshape(B, -1, 2).contiguous().float()
         else:
             ref_xy, ids = self.reference_points(logits[-1], lines[-1])
-        x32, depth0 = self.stage32.forward(c5, ref_xy)
-        outs = self.dense.forward(x32, depth0, (c4, c3, c2), H, W, {k: v for k, v in pinned.items() if k.startswith("sample")})
+        x32, depth0 = self.stage32.forward(c5, ref_xy, None if masks is None else masks[3])
+        outs = self.dense.forward(x32, depth0, (c4, c3, c2), H, W, {k: v for k, v in pinned.items() if k.startswith("sample")},
+                                  pad_masks=None if masks is None else (masks[2], masks[1], masks[0]))
         outs.update(line_ids=ids, depth0=depth0)
         self._c5_shape = c5.shape
         return logits, lines, outs
@@ -201,14 +204,14 @@ class Trainer:
         return float(self.sumsq.sqrt().item()) / parallel.world_size()
 
     # ------------------------------------------------------------------ one fused training step
-    def train_step(self, images, targets, depth_gt, seg_gt, criterion, pinned=None):
+    def train_step(self, images, targets, depth_gt, seg_gt, criterion, pinned=None, mask=None):
         """images fp32 [B,3,H,W]; targets: list of {'lines' [T,D], 'labels' [T]} on the device; depth_gt fp32 [B,1,H,W] metres;
         seg_gt int64 [B,1,H,W]; criterion: model.SetCriterion.  Returns (total loss tensor [1] on the device, dict of the 17
         un-weighted losses as the engine logs them)."""
-        if self.use_cuda_graph and not pinned:
+        if self.use_cuda_graph and not pinned and mask is None:
             return self._train_step_graphed(images, targets, depth_gt, seg_gt, criterion)
-        pend = {}
-        logits, lines, outs = self.forward(images, pinned,
+        pend = {}       # (a ragged batch -- mask given -- runs kernel by kernel: its shapes change from step to step anyway)
+        logits, lines, outs = self.forward(images, pinned, mask=mask,
                                            after_line=lambda lo, li: pend.update(h=criterion.matcher.stacked_cost(lo, li, targets)))
         g = self.dense.loss_grads(outs, depth_gt, seg_gt)
         self.backward_dense(*g)                                   # enqueued; the GPU works on it while the host solves the LSAPs
