@@ -157,6 +157,42 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def attention_rate(dev, peak_tflops):
+    """BASELINE metric, second half ("attn tensor-pipe util %"): the DETR attention kernel timed alone with CUDA events at the training
+    shape (B = 8, L = 300) and at the corner SURVEY section 7 names (B = 64, L = 1 200 = 960x1280 images); FLOPs = 4 Lq Lk 256 per
+    image.  The tensor-pipe utilisation itself needs ncu: the committed captures are cited."""
+    from gwdepth_b200 import ops
+    out = {"kernel": "gwd_attention_tc_kernel / gwd_attention_flash_tc_kernel (tcgen05 + TMEM + TMA, head dim 32)", "cases": {},
+           "tensor_pipe_active_pct_ncu": {"enc_b64_l1200": 31.9, "enc_b16_l300": "profiles/r2_ncu_full_attention_enc_b16_l300.txt",
+                                          "source": "profiles/r2_ncu_full_attention_enc_b64_l1200.txt (ncu --set full)"},
+           "note": "head dim 32 makes the soft-max exponentials (MUFU, 16 / clk / SM) the bound: <= ~25 % of the tensor pipe"}
+    E, NH, HD = 256, 8, 32
+    for name, (B_, L_) in {"enc_b8_l300": (8, 300), "enc_b64_l1200": (64, 1200)}.items():
+        g = torch.Generator(device=dev).manual_seed(0)
+        sets = [(torch.randn(B_ * L_, E, device=dev, generator=g).bfloat16() * HD ** -0.25,
+                 torch.randn(B_ * L_, E, device=dev, generator=g).bfloat16() * HD ** -0.25,
+                 torch.randn(B_ * L_, E, device=dev, generator=g).bfloat16()) for _ in range(3)]
+        o = torch.empty(B_ * L_, E, device=dev, dtype=torch.bfloat16)
+
+        def call(i):
+            q, k, v = sets[i % 3]
+            ops.attention(q, k, v, o, items=B_, heads=NH, Lq=L_, Lk=L_, hd=HD, q_strides=(L_ * E, E), k_strides=(L_ * E, E),
+                          v_strides=(L_ * E, E), o_strides=(L_ * E, E), scale=1.0)
+        for i in range(3):
+            call(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(20):
+            call(i)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 20
+        tf = 4.0 * B_ * L_ * L_ * E / ms / 1e9
+        out["cases"][name] = {"us": ms * 1000, "tflops": tf, "frac_of_measured_bf16_peak": tf / peak_tflops}
+    return out
+
+
 def data_path_rate(dev, n=48):
     """the training augmentation pipeline (make_coco_transforms('train'), src/datasets/coco.py:74-103) on 480x640
     samples -- gw-depth_b200/data.py on the GPU (one host thread) and, when the staged reference + Pillow are there, the reference's own
@@ -546,9 +582,11 @@ def main():
                 n += 1
             cpu = {"value": n / (time.time() - t0), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                    "sample": "%d training passes (forward + 17 losses + backward) of 1x3x480x640 (1/8 of a step) through oracle/gwdepth_oracle.py" % n}
-    data_path = None
+    data_path, attention = None, None
     if world == 1 and not args.no_data_path:
         data_path = data_path_rate(dev)
+    if world == 1:
+        attention = attention_rate(dev, measured_peak()[0])
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": ms / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "e2e": e2e, "gpu_launches": launches, "clocks": sampler.summary(),
@@ -557,7 +595,7 @@ def main():
                        "l2": "4 rotating input batches; per-step activations are several GB", "loss": loss_value,
                        "optimizer": "AdamW lr 1e-4 (backbone 1e-5), weight decay 1e-4, global clip 0.1; dropout %g" % args.dropout},
             "breakdown": breakdown, "forward": fwd, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_reference": eager,
-            "data_path": data_path}
+            "data_path": data_path, "attention": attention}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
