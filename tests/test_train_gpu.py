@@ -32,7 +32,8 @@ def rel_l2(got, ref):
 
 # ------------------------------------------------------------------------------------------ kernels
 @pytest.mark.parametrize("rows,C,with_add", [(600, 256, False), (4800, 256, True), (77, 512, True), (5, 64, False),
-                                             (4099, 64, True), (1001, 128, False), (3333, 32, True), (2050, 96, False)])
+                                             (4099, 64, True), (1001, 128, False), (3333, 32, True), (2050, 96, False), (5000, 160, True), (4097, 160, False),
+                                             (9001, 144, True), (4100, 168, False), (4098, 136, True), (30000, 152, False)])
 def test_layernorm_bwd(rows, C, with_add):
     ops = _ops()
     g = _g(rows + C)
