@@ -154,7 +154,7 @@ def run_reference(args, rank):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                              "sample": "%d training passes of 1x3x480x640 through oracle/gwdepth_oracle.py under torch.autograd" % args.steps},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def attention_rate(dev, peak_tflops):
@@ -340,8 +340,27 @@ def gpu_eager_reference(dev, n_fwd=5, n_train=3):
     return res
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """the ONE JSON line of the contract on the real stdout (everything else -- NCCL's version banner, library warnings -- was
+    sent to stderr by main())"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse()
+    # fd-level: native libraries (NCCL prints "NCCL version ..." on stdout) must not precede the JSON line
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", 0))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -596,7 +615,7 @@ def main():
                        "optimizer": "AdamW lr 1e-4 (backbone 1e-5), weight decay 1e-4, global clip 0.1; dropout %g" % args.dropout},
             "breakdown": breakdown, "forward": fwd, "roofline": roof, "cpu_baseline": cpu, "gpu_eager_reference": eager,
             "data_path": data_path, "attention": attention}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
