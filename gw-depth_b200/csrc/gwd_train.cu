@@ -292,16 +292,33 @@ gwd_transpose_batch_kernel(const int64_t* __restrict__ table, const int32_t* __r
   }
 }
 
-// vector path of gwd_act_bwd: bf16 dy, bf16 y, no padding, 8 elements per thread
+// vector path of gwd_act_bwd: bf16 dy, bf16 y, no padding, 8 elements per thread, two vectors in flight.  ACT / FROM_INPUT are
+// compile-time: the run-time switch sat inside the per-element loop of a kernel that is bound by instruction issue.
+template <int ACT, int FROM_INPUT>
 __global__ void __launch_bounds__(256)
-gwd_act_bwd_vec_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, int act, bf16* __restrict__ out, int64_t n8,
-                       float y_mul, float scale, int from_input) {
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n8; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+gwd_act_bwd_vec_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, bf16* __restrict__ out, int64_t n8, float y_mul, float scale) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+  for (; i + stride < n8; i += 2 * stride) {
+    float d0[8], v0[8], d1[8], v1[8];
+    ld8(dy + i * 8, d0);
+    ld8(y + i * 8, v0);
+    ld8(dy + (i + stride) * 8, d1);
+    ld8(y + (i + stride) * 8, v1);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      d0[e] = d0[e] * act_factor(v0[e] * y_mul, ACT, FROM_INPUT) * scale;
+      d1[e] = d1[e] * act_factor(v1[e] * y_mul, ACT, FROM_INPUT) * scale;
+    }
+    st8(out + i * 8, d0);
+    st8(out + (i + stride) * 8, d1);
+  }
+  for (; i < n8; i += stride) {
     float d[8], v[8];
     ld8(dy + i * 8, d);
     ld8(y + i * 8, v);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) d[e] = d[e] * act_factor(v[e] * y_mul, act, from_input) * scale;
+    for (int e = 0; e < 8; ++e) d[e] = d[e] * act_factor(v[e] * y_mul, ACT, FROM_INPUT) * scale;
     st8(out + i * 8, d);
   }
 }
@@ -1382,8 +1399,18 @@ extern "C" int gwd_act_bwd(const void* dy, int32_t dy_f32, int64_t dy_rs, const 
       ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
     const int64_t n8 = rows * n / 8;
     const unsigned g = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(n8, 256), 16 * gwd_num_sms()));
-    gwd_act_bwd_vec_kernel<<<g, 256, 0, stream>>>(static_cast<const bf16*>(dy), static_cast<const bf16*>(y), act, o, n8, y_mul, scale,
-                                                  from_input);
+    const bf16* dyp = static_cast<const bf16*>(dy);
+    const bf16* yp = static_cast<const bf16*>(y);
+#define GWD_ACT_VEC(A, F) gwd_act_bwd_vec_kernel<A, F><<<g, 256, 0, stream>>>(dyp, yp, o, n8, y_mul, scale)
+    const int fi = from_input ? 1 : 0;
+    if (act == GWD_ACT_RELU && !fi) GWD_ACT_VEC(GWD_ACT_RELU, 0);
+    else if (act == GWD_ACT_RELU) GWD_ACT_VEC(GWD_ACT_RELU, 1);
+    else if (act == GWD_ACT_ELU && !fi) GWD_ACT_VEC(GWD_ACT_ELU, 0);
+    else if (act == GWD_ACT_ELU) GWD_ACT_VEC(GWD_ACT_ELU, 1);
+    else if (act == GWD_ACT_GELU) GWD_ACT_VEC(GWD_ACT_GELU, 1);          // (GELU from its output is rejected above)
+    else if (act == GWD_ACT_SIGMOID && !fi) GWD_ACT_VEC(GWD_ACT_SIGMOID, 0);
+    else GWD_ACT_VEC(GWD_ACT_SIGMOID, 1);
+#undef GWD_ACT_VEC
     GWD_LAUNCHED();
     return GWD_OK;
   }
