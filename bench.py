@@ -275,7 +275,7 @@ def data_path_rate(dev, n=48):
     return out
 
 
-def gpu_eager_reference(dev, n_fwd=5, n_train=3):
+def gpu_eager_reference(dev, n_fwd=30, n_train=10):
     """the unmodified reference on this GPU, eager fp32, as shipped (no AMP / TF32 override / cudnn.benchmark): forward at batch 16
     (north_star's 10x denominator) and one training step at batch 8 (its own criteria, AdamW, clip)"""
     import ref_shims
@@ -289,7 +289,7 @@ def gpu_eager_reference(dev, n_fwd=5, n_train=3):
         model.to(dev).eval()
         images = synth.synth_batch(FWD_BATCH, H, W, seed=100)[0].to(dev)
         with torch.no_grad():
-            for _ in range(2):
+            for _ in range(10):         # >= 10 warm-up + >= 30 timed iterations for the 10x denominator
                 model(images)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -325,7 +325,8 @@ def gpu_eager_reference(dev, n_fwd=5, n_train=3):
             loss.backward()
             torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
             opt.step()
-        step()
+        for _ in range(3):
+            step()
         torch.cuda.synchronize()
         e0.record()
         for _ in range(n_train):
