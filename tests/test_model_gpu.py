@@ -150,6 +150,32 @@ def test_dense_center_configuration():
     assert rel(base["pred_depth"][3], ref["pred_depth"][3])[0] > 1.3 * m
 
 
+def test_forward_matches_oracle_second_weight_draw():
+    """the same parity on a SECOND random draw of all 970 tensors (more than one weight set), through
+    load_state_dict on the live module (the cached kernel plan must notice the new weights)"""
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import model as M
+    sd = synth_weights(seed=1)
+    net, _, _ = M.build_model(M.default_args(device="cuda"))
+    net.load_state_dict(synth_weights())
+    net.cuda().eval()
+    B, H, W = 2, 224, 320
+    images, _, _, _ = synth.synth_batch(B, H, W, seed=4)
+    with torch.no_grad():
+        first = net(images.cuda())["pred_depth"][3].clone()       # plan built on the first weight set
+    net.load_state_dict(sd)
+    trace = {}
+    ref = oracle.forward(sd, images, trace=trace)
+    with torch.no_grad():
+        out = net(images.cuda(), _pinned=pinned_from(trace))
+    assert float((out["pred_depth"][3] - first).abs().max()) > 1e-3           # the new weights are in use
+    assert rel(out["pred_logits"], ref["pred_logits"])[1] < TOL["logits_max"]
+    assert rel(out["pred_lines"], ref["pred_lines"])[1] < TOL["lines_max"]
+    m, x = rel(out["pred_depth"][3], ref["pred_depth"][3])
+    assert m < TOL["depth_mean"] and x < 0.3, (m, x)
+    assert rel(out["pred_seg"], ref["pred_seg"])[0] < TOL["seg_mean"]
+
+
 def test_unpinned_selections_agree_with_oracle():
     """without pinning, the fp32-kept selection inputs must reproduce most of the oracle's choices"""
     net, _, _ = model()
