@@ -246,7 +246,10 @@ __device__ __forceinline__ void store_row_bf16(bf16* dst, const float (&v)[HD], 
   }
 }
 
-template <int HD>
+// PACK: P and dS of a (query, key) pair live in ONE 32-bit word (bf16 x 2) instead of two fp32 arrays: 73 instead of 93 KB of
+// shared memory per CTA (three CTAs per SM instead of two -- the kernel is latency bound at 8 warps per SM) and one shared-memory
+// access instead of two on both sides of the hand-over to the column pass
+template <int HD, bool PACK>
 __global__ void __launch_bounds__(128) gwd_window_attention_bwd_rows_kernel(const WinBwdParams p) {
   extern __shared__ __align__(16) float smr[];
   constexpr int N = kWN, NN = kWN * kWN;
@@ -255,13 +258,15 @@ __global__ void __launch_bounds__(128) gwd_window_attention_bwd_rows_kernel(cons
   float* slot0 = sMask + NN + 1;              // keep 16-byte alignment: 3 * NN + 1 = 7204 floats
   const int slot = threadIdx.x >> 6, t = threadIdx.x & 63;
   const int h = 2 * blockIdx.x + slot;
-  float* sq = slot0 + slot * (4 * N * HD + 3 * NN + 1);           // + 1: 4 N HD + 3 NN + 1 is a multiple of 4 (16-byte rows)
+  constexpr int kSlot = PACK ? 4 * N * HD + 2 * NN + 2 : 4 * N * HD + 3 * NN + 1;      // multiples of 4 (16-byte rows)
+  float* sq = slot0 + slot * kSlot;
   float* sk = sq + N * HD;
   float* sv = sk + N * HD;
   float* sdo = sv + N * HD;
   float* sP = sdo + N * HD;                   // [N][N]
-  float* sdS = sP + NN;
-  float* sDb = sdS + NN;                      // [N][N] bias-gradient accumulator of this slot's head (row t owned by thread t)
+  float* sdS = sP + NN;                       // (PACK: unused, sP holds the pairs)
+  uint32_t* sPD = reinterpret_cast<uint32_t*>(sP);
+  float* sDb = PACK ? sP + NN : sdS + NN;                      // [N][N] bias-gradient accumulator of this slot's head (row t owned by thread t)
   for (int e = threadIdx.x; e < 2 * NN; e += 128)
     sBias[e] = p.bias ? p.bias[static_cast<int64_t>(2 * blockIdx.x) * NN + e] : 0.f;
   for (int e = t; e < NN; e += 64) sDb[e] = 0.f;
@@ -329,8 +334,8 @@ __global__ void __launch_bounds__(128) gwd_window_attention_bwd_rows_kernel(cons
         if (p.mask) a += sMask[t * N + j];
         const float pr = __expf(a - m) * inv;
         const float ds = pr * (b - dsum);
-        sP[t * N + j] = pr;
-        sdS[t * N + j] = ds;
+        if (PACK) sPD[t * N + j] = gwd_pack_bf16x2(pr, ds);
+        else { sP[t * N + j] = pr; sdS[t * N + j] = ds; }
         sDb[t * N + j] += ds;
 #pragma unroll
         for (int c = 0; c < HD; c += 4) {
@@ -347,7 +352,9 @@ __global__ void __launch_bounds__(128) gwd_window_attention_bwd_rows_kernel(cons
       for (int c = 0; c < HD; ++c) { dk[c] = 0.f; dv[c] = 0.f; }
 #pragma unroll 7
       for (int i = 0; i < N; ++i) {
-        const float ds = sdS[i * N + t], pr = sP[i * N + t];
+        float ds, pr;
+        if (PACK) { const float2 pd = gwd_unpack_bf16x2(sPD[i * N + t]); pr = pd.x; ds = pd.y; }
+        else { ds = sdS[i * N + t]; pr = sP[i * N + t]; }
 #pragma unroll
         for (int c = 0; c < HD; c += 4) {
           const float4 qq = *reinterpret_cast<const float4*>(sq + i * HD + c), gg = *reinterpret_cast<const float4*>(sdo + i * HD + c);
@@ -368,20 +375,29 @@ __global__ void __launch_bounds__(128) gwd_window_attention_bwd_rows_kernel(cons
   }
 }
 
-template <int HD>
-int launch_rows(const WinBwdParams& p, cudaStream_t stream) {
-  const size_t smem = sizeof(float) * (3 * kWN * kWN + 1 + 2 * (4 * kWN * HD + 3 * kWN * kWN + 1));
-  static bool attr_set = false;
-  if (!attr_set) {
-    GWD_CUDA(cudaFuncSetAttribute(gwd_window_attention_bwd_rows_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    attr_set = true;
+template <int HD, bool PACK>
+int launch_rows_impl(const WinBwdParams& p, cudaStream_t stream) {
+  const size_t slot = PACK ? 4 * kWN * HD + 2 * kWN * kWN + 2 : 4 * kWN * HD + 3 * kWN * kWN + 1;
+  const size_t smem = sizeof(float) * (3 * kWN * kWN + 1 + 2 * slot);
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    GWD_CUDA(cudaFuncSetAttribute(gwd_window_attention_bwd_rows_kernel<HD, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+    int nb = 0;
+    GWD_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, gwd_window_attention_bwd_rows_kernel<HD, PACK>, 128, smem));
+    ctas_per_sm = std::max(1, nb);
   }
   const int pairs = p.heads / 2;
-  int per = std::max(1, (gwd_num_sms() * 2) / pairs);
+  int per = std::max(1, (gwd_num_sms() * ctas_per_sm) / pairs);
   per = std::min(per, p.items);
-  gwd_window_attention_bwd_rows_kernel<HD><<<dim3(pairs, per), 128, smem, stream>>>(p);
+  gwd_window_attention_bwd_rows_kernel<HD, PACK><<<dim3(pairs, per), 128, smem, stream>>>(p);
   GWD_LAUNCHED();
   return GWD_OK;
+}
+template <int HD>
+int launch_rows(const WinBwdParams& p, cudaStream_t stream) {
+  static const bool pack = [] { const char* e = getenv("GWD_WINBWD_PACK"); return !(e && e[0] == '0'); }();
+  return pack ? launch_rows_impl<HD, true>(p, stream) : launch_rows_impl<HD, false>(p, stream);
 }
 
 // Warp-per-problem version of the class-token channel attention backward: the CTA-per-(window, head) kernel above spends its
