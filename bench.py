@@ -32,8 +32,23 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
-sys.path.insert(0, os.path.join(ROOT, "oracle"))
+
+
+def _checker_paths():
+    """tests/ and oracle/ on sys.path: ONLY the cpu_baseline leg, the --impl reference arm and the eager-reference leg call this (the
+    product arm imports nothing from there)"""
+    for d in ("tests", "oracle"):
+        p = os.path.join(ROOT, d)
+        if p not in sys.path:
+            sys.path.insert(0, p)
+
+
+def synth_weights(seed=0):
+    """the synthetic state dict of the benchmark: generator in the package, key / shape list from the committed fixture"""
+    from gwdepth_b200 import synth
+    with open(os.path.join(ROOT, "tests", "golden", "state_dict_spec.json")) as f:
+        spec = [tuple(k) for k in json.load(f)["keys"]]
+    return synth.add_structural_buffers(synth.synth_state_dict(spec, seed=seed), spec)
 
 import torch  # noqa: E402
 
@@ -109,6 +124,7 @@ def use_all_host_threads():
 
 def cpu_train_pass(sd_leaves, batch, wd):
     """one forward + backward of the CPU oracle under torch.autograd (the engine's 17 losses) on `batch`"""
+    _checker_paths()
     from helpers import oracle
     images, targets, depth_gt, seg_gt = batch
     for v in sd_leaves.values():
@@ -122,6 +138,7 @@ def cpu_train_pass(sd_leaves, batch, wd):
 
 
 def cpu_setup():
+    _checker_paths()
     from helpers import synth, synth_weights
     use_all_host_threads()
     sd = synth_weights()
@@ -246,6 +263,7 @@ def data_path_rate(dev, n=48):
         out["error"] = repr(e)[:200]
     try:
         from PIL import Image
+        _checker_paths()           # reference leg of the data-path measurement
         import ref_shims
         if ref_shims.reference_available():
             ref_shims.install()
@@ -278,6 +296,7 @@ def data_path_rate(dev, n=48):
 def gpu_eager_reference(dev, n_fwd=30, n_train=10):
     """the unmodified reference on this GPU, eager fp32, as shipped (no AMP / TF32 override / cudnn.benchmark): forward at batch 16
     (north_star's 10x denominator) and one training step at batch 8 (its own criteria, AdamW, clip)"""
+    _checker_paths()
     import ref_shims
     if not ref_shims.reference_available():
         return {"unavailable": "reference tree not staged (run oracle/stage_ref.sh in the build container)"}
@@ -369,9 +388,8 @@ def main():
         run_reference(args, rank)
         return
     import torch.distributed as dist
-    from helpers import synth, synth_weights
     import gwdepth_b200  # noqa: F401
-    from gwdepth_b200 import capi, model as M, ops
+    from gwdepth_b200 import capi, model as M, ops, synth          # (synthetic inputs: generator in the package, not oracle/)
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
