@@ -69,22 +69,15 @@ def vflip(image, target, aux_mats=None):
     return flipped, target, aux_mats
 
 
-def _get_size_with_aspect_ratio(image_size, size, max_size=None):
-    w, h = image_size
-    if max_size is not None:
-        min_original_size = float(min((w, h)))
-        max_original_size = float(max((w, h)))
-        if max_original_size / min_original_size * size > max_size:
-            size = int(round(max_size * min_original_size / max_original_size))
-    if (w <= h and w == size) or (h <= w and h == size):
-        return (h, w)
-    if w < h:
-        ow = size
-        oh = int(size * h / w)
-    else:
-        oh = size
-        ow = int(size * w / h)
-    return (oh, ow)
+def _short_side_target(w, h, size, max_size=None):
+    """output (height, width) of a resize that brings the SHORT side to `size` without letting the long side exceed max_size
+    (the rule of transforms_depth.py:319-339, truncating divisions included)"""
+    short, long_ = (w, h) if w <= h else (h, w)
+    if max_size is not None and float(long_) / float(short) * size > max_size:
+        size = int(round(max_size * float(short) / float(long_)))
+    if short == size:                       # already there: PIL would be asked for the same size
+        return h, w
+    return (int(size * h / w), size) if w < h else (size, int(size * w / h))
 
 
 def resize(image, target, size, max_size=None, aux_mats=None):
@@ -93,7 +86,7 @@ def resize(image, target, size, max_size=None, aux_mats=None):
     if isinstance(size, (list, tuple)):
         oh, ow = size[::-1]
     else:
-        oh, ow = _get_size_with_aspect_ratio((w0, h0), size, max_size)
+        oh, ow = _short_side_target(w0, h0, size, max_size)
     rescaled = ops.resize_bilinear_u8(image, oh, ow)
     if target is None:
         return rescaled, None
@@ -111,111 +104,112 @@ def resize(image, target, size, max_size=None, aux_mats=None):
     return rescaled, target, aux_mats
 
 
-def _centroid(vertexes):
-    xs = [v[0] for v in vertexes]
-    ys = [v[1] for v in vertexes]
-    return (sum(xs) / len(vertexes), sum(ys) / len(vertexes))
+def _mean_point(points):
+    n = len(points)
+    return (sum(pt[0] for pt in points) / n, sum(pt[1] for pt in points) / n)
 
 
-def _intersect_remap(main_coors, poly_coors):
-    """transforms_depth.py:32-43 (shapely, as the reference)"""
+def _polygon_window_overlap(window, polygon):
+    """vertices (closed ring) of the intersection of the crop window with a glass polygon, [] when it is not one polygon
+    (transforms_depth.py:32-43; shapely, imported here only, exactly like the reference)"""
     import numpy as np
     from shapely.geometry import Polygon, mapping
-    inter = Polygon(main_coors).intersection(Polygon(poly_coors))
-    m = mapping(inter)
-    if m["type"] == "Polygon":
-        if np.array(m["coordinates"]).size <= 2:
-            return []
-        return list(inter.exterior.coords)
-    return []
+    common = Polygon(window).intersection(Polygon(polygon))
+    desc = mapping(common)
+    if desc["type"] != "Polygon" or np.array(desc["coordinates"]).size <= 2:
+        return []
+    return list(common.exterior.coords)
+
+
+def _clip_lines(cl, w, h):
+    """pull the end points of the (already shifted) lines [n,4] = (x1, y1, x2, y2) onto the crop window along the line: the eight
+    sequential rules of transforms_depth.py:97-125, applied to all lines at once (same float32 operations in the same order; a rule
+    only changes the rows whose condition holds)"""
+    x1, y1, x2, y2 = (cl[:, k].clone() for k in range(4))
+    slope = (y2 - y1) / (x2 - x1 + 1e-12)
+    zero = torch.zeros_like(x1)
+    # end 1 beyond the left / top, end 2 beyond the right / bottom, then the mirrored four cases
+    c = x1 < 0
+    x1 = torch.where(c, zero, x1)
+    y1 = torch.where(c, y2 + (x1 - x2) * slope, y1)
+    c = y1 < 0
+    y1 = torch.where(c, zero, y1)
+    x1 = torch.where(c, x2 - (y2 - y1) / slope, x1)
+    c = x2 > w
+    x2 = torch.where(c, zero + w, x2)
+    y2 = torch.where(c, y1 + (x2 - x1) * slope, y2)
+    c = y2 > h
+    y2 = torch.where(c, zero + h, y2)
+    x2 = torch.where(c, x1 + (y2 - y1) / slope, x2)
+    c = x2 < 0
+    x2 = torch.where(c, zero, x2)
+    y2 = torch.where(c, y1 + (x2 - x1) * slope, y2)
+    c = y2 < 0
+    y2 = torch.where(c, zero, y2)
+    x2 = torch.where(c, x1 - (y1 - y2) / slope, x2)
+    c = x1 > w
+    x1 = torch.where(c, zero + w, x1)
+    y1 = torch.where(c, y2 + (x1 - x2) * slope, y1)
+    c = y1 > h
+    y1 = torch.where(c, zero + h, y1)
+    x1 = torch.where(c, x2 + (y1 - y2) / slope, x1)
+    out = torch.stack([x1, y1, x2, y2], dim=1)
+    out[:, 0::2].clamp_(min=0, max=w)
+    out[:, 1::2].clamp_(min=0, max=h)
+    return out
 
 
 def crop(image, target, region, aux_mats=None):
-    """transforms_depth.py:59-202: pixels are a view (no copy until the next kernel reads it); the line clipping is the reference's"""
-    i, j, h, w = region
-    cropped = image[i:i + h, j:j + w]
+    """transforms_depth.py:59-202.  Pixels: a view of the device image / maps (no copy until the next kernel reads it).  Targets: lines
+    with both ends beyond the same side of the window are dropped, the others are clipped along themselves; a polygon's centre is
+    recomputed from what is left of it (or from its overlap with the window when three lines or fewer remain)."""
+    top, left, h, w = region
+    cropped = image[top:top + h, left:left + w]
     target = target.copy()
-    x_lt, y_lt = j, i
     target["size"] = torch.tensor([h, w])
-    fields = ["labels", "area", "iscrowd"]
     keep = None
     if "lines" in target:
         lines = target["lines"]
-        cl = lines - torch.as_tensor([j, i, j, i])
-        eps = 1e-12
-        remove_x = torch.logical_or(torch.logical_and(cl[:, 0] < 0, cl[:, 2] < 0), torch.logical_and(cl[:, 0] > w, cl[:, 2] > w))
-        remove_y = torch.logical_or(torch.logical_and(cl[:, 1] < 0, cl[:, 3] < 0), torch.logical_and(cl[:, 1] > h, cl[:, 3] > h))
-        keep = torch.logical_and(~remove_x, ~remove_y)
-        cl = cl[keep]
-        clamped = torch.zeros_like(cl)
-        for n, line in enumerate(cl):
-            x1, y1, x2, y2 = line
-            slope = (y2 - y1) / (x2 - x1 + eps)
-            if x1 < 0:
-                x1 = 0
-                y1 = y2 + (x1 - x2) * slope
-            if y1 < 0:
-                y1 = 0
-                x1 = x2 - (y2 - y1) / slope
-            if x2 > w:
-                x2 = w
-                y2 = y1 + (x2 - x1) * slope
-            if y2 > h:
-                y2 = h
-                x2 = x1 + (y2 - y1) / slope
-            if x2 < 0:
-                x2 = 0
-                y2 = y1 + (x2 - x1) * slope
-            if y2 < 0:
-                y2 = 0
-                x2 = x1 - (y1 - y2) / slope
-            if x1 > w:
-                x1 = w
-                y1 = y2 + (x1 - x2) * slope
-            if y1 > h:
-                y1 = h
-                x1 = x2 + (y1 - y2) / slope
-            clamped[n, :] = torch.tensor([x1, y1, x2, y2])
-        clamped[:, 0::2].clamp_(min=0, max=w)
-        clamped[:, 1::2].clamp_(min=0, max=h)
-        target["lines"] = clamped
-        src_poly_ids = target["poly_ids"]
-        target["poly_ids"] = target["poly_ids"][keep]
+        shifted = lines - torch.as_tensor([left, top, left, top])
+        xs, ys = shifted[:, 0::2], shifted[:, 1::2]
+        gone = ((xs < 0).all(1) | (xs > w).all(1)) | ((ys < 0).all(1) | (ys > h).all(1))
+        keep = ~gone
+        target["lines"] = _clip_lines(shifted[keep], w, h)
+        ids_before = target["poly_ids"]
+        target["poly_ids"] = ids_before[keep]
         if "poly_centers" in target:
-            x_rb, y_rb = x_lt + w - 1, y_lt + h - 1
-            crp_point = [[x_lt, y_lt], [x_lt, y_rb], [x_rb, y_rb], [x_rb, y_lt]]
-            horiz_flipped = bool(lines[0, 0] == lines[1, 2] and lines[0, 1] == lines[1, 3])
-            centers = torch.zeros_like(target["poly_centers"][keep])
-            for py_id in torch.unique(target["poly_ids"]):
-                py_index = target["poly_ids"] == py_id
-                py_lines = target["lines"][py_index]
+            right, bottom = left + w - 1, top + h - 1
+            window = [[left, top], [left, bottom], [right, bottom], [right, top]]
+            # after a horizontal flip every line runs right to left: the polygon's vertex chain is read from the other end
+            mirrored = bool(lines[0, 0] == lines[1, 2] and lines[0, 1] == lines[1, 3])
 
-                def points_of(pl):
-                    if horiz_flipped:
-                        pl = pl.reshape(-1, 2, 2).flip(1).reshape(-1, 4)
-                    return pl[0].reshape(-1, 2).tolist() + pl[1:, 2:].tolist()
-                if len(py_lines) > 3:
-                    centers[py_index, :] = torch.tensor(_centroid(points_of(py_lines)))
+            def vertex_chain(poly_lines):
+                if mirrored:
+                    poly_lines = poly_lines.reshape(-1, 2, 2).flip(1).reshape(-1, 4)
+                return poly_lines[0].reshape(-1, 2).tolist() + poly_lines[1:, 2:].tolist()
+            centers = torch.zeros_like(target["poly_centers"][keep])
+            for pid in torch.unique(target["poly_ids"]):
+                sel = target["poly_ids"] == pid
+                left_over = target["lines"][sel]
+                overlap = [] if len(left_over) > 3 else _polygon_window_overlap(window, vertex_chain(lines[ids_before == pid]))
+                if overlap:
+                    c = torch.tensor(_mean_point(overlap)) - torch.as_tensor([left, top])
+                    c[0].clamp_(min=0, max=w)
+                    c[1].clamp_(min=0, max=h)
                 else:
-                    joint = _intersect_remap(crp_point, points_of(lines[src_poly_ids == py_id]))
-                    if len(joint) > 0:
-                        c = torch.tensor(_centroid(joint)) - torch.as_tensor([x_lt, y_lt])
-                        c[0].clamp_(min=0, max=w)
-                        c[1].clamp_(min=0, max=h)
-                        centers[py_index, :] = c
-                    else:
-                        centers[py_index, :] = torch.tensor(_centroid(points_of(py_lines)))
+                    c = torch.tensor(_mean_point(vertex_chain(left_over)))
+                centers[sel, :] = c
             target["poly_centers"] = centers
     if "reflection_points" in target:
-        pts = target["reflection_points"] - torch.as_tensor([j, i])
-        remove = torch.logical_or(torch.logical_or(pts[:, 0] < 0, pts[:, 0] > w), torch.logical_or(pts[:, 1] < 0, pts[:, 1] > h))
-        target["reflection_points"] = pts[~remove]
+        pts = target["reflection_points"] - torch.as_tensor([left, top])
+        inside = (pts[:, 0] >= 0) & (pts[:, 0] <= w) & (pts[:, 1] >= 0) & (pts[:, 1] <= h)
+        target["reflection_points"] = pts[inside]
     if keep is not None:
-        for field in fields:
+        for field in ("labels", "area", "iscrowd"):
             if field in target:
                 target[field] = target[field][keep]
     if aux_mats is not None:
-        aux_mats = [m[i:i + h, j:j + w] for m in aux_mats]
+        aux_mats = [m[top:top + h, left:left + w] for m in aux_mats]
     return cropped, target, aux_mats
 
 
@@ -233,7 +227,34 @@ def _random_crop_params(image, output_size):
 
 
 # ------------------------------------------------------------------------------------------------ transform classes
-class RandomCrop(object):
+class _Transform(object):
+    """a callable (image, target, aux_mats) -> (image, target, aux_mats); subclasses name the reference's transforms"""
+
+    def __repr__(self):
+        return "%s(%s)" % (type(self).__name__, ", ".join("%s=%r" % kv for kv in sorted(vars(self).items())))
+
+
+class _CoinFlip(_Transform):
+    """applies `self.op` when one draw of random.random() falls below p (the flips of the reference)"""
+    op = None
+
+    def __init__(self, p=0.5):
+        self.p = p
+
+    def __call__(self, img, target, aux_mats=None):
+        hit = random.random() < self.p
+        return type(self).op(img, target, aux_mats=aux_mats) if hit else (img, target, aux_mats)
+
+
+class RandomHorizontalFlip(_CoinFlip):
+    op = staticmethod(hflip)
+
+
+class RandomVerticalFlip(_CoinFlip):
+    op = staticmethod(vflip)
+
+
+class RandomCrop(_Transform):
     def __init__(self, size):
         self.size = size
 
@@ -241,7 +262,10 @@ class RandomCrop(object):
         return crop(img, target, _random_crop_params(img, self.size), aux_mats=aux_mats)
 
 
-class RandomSizeCrop(object):
+class RandomSizeCrop(_Transform):
+    """a window of random size within [min_size, max_size] (and the image) at a random place: width first, then height, then
+    the position draws of RandomCrop -- the reference's order of RNG calls"""
+
     def __init__(self, min_size, max_size):
         self.min_size, self.max_size = min_size, max_size
 
@@ -252,36 +276,17 @@ class RandomSizeCrop(object):
         return crop(img, target, _random_crop_params(img, [h, w]), aux_mats=aux_mats)
 
 
-class RandomHorizontalFlip(object):
-    def __init__(self, p=0.5):
-        self.p = p
-
-    def __call__(self, img, target, aux_mats=None):
-        if random.random() < self.p:
-            return hflip(img, target, aux_mats=aux_mats)
-        return img, target, aux_mats
-
-
-class RandomVerticalFlip(object):
-    def __init__(self, p=0.5):
-        self.p = p
-
-    def __call__(self, img, target, aux_mats=None):
-        if random.random() < self.p:
-            return vflip(img, target, aux_mats=aux_mats)
-        return img, target, aux_mats
-
-
-class RandomResize(object):
+class RandomResize(_Transform):
     def __init__(self, sizes, max_size=None):
-        assert isinstance(sizes, (list, tuple))
+        if not isinstance(sizes, (list, tuple)):
+            raise TypeError("sizes: a list of short-side lengths")
         self.sizes, self.max_size = sizes, max_size
 
     def __call__(self, img, target=None, aux_mats=None):
         return resize(img, target, random.choice(self.sizes), self.max_size, aux_mats=aux_mats)
 
 
-class Resize(object):
+class Resize(_Transform):
     def __init__(self, size):
         self.size = size   # (w, h)
 
@@ -289,31 +294,32 @@ class Resize(object):
         return resize(img, target, self.size, aux_mats=aux_mats)
 
 
-class ColorJitter(object):
+class ColorJitter(_Transform):
     """transforms_depth.py:551-604: the four adjustments in a random order, each with a factor drawn from its range"""
 
     def __init__(self, brightness=0.4, contrast=0.4, saturation=0.4, hue=0.4):
-        self.brightness = self._check_input(brightness, "brightness")
-        self.contrast = self._check_input(contrast, "contrast")
-        self.saturation = self._check_input(saturation, "saturation")
-        self.hue = self._check_input(hue, "hue", center=0, bound=(-0.5, 0.5), clip_first_on_zero=False)
+        inf = float("inf")
+        self.brightness = self._range(brightness, "brightness", 1, 0, inf, True)
+        self.contrast = self._range(contrast, "contrast", 1, 0, inf, True)
+        self.saturation = self._range(saturation, "saturation", 1, 0, inf, True)
+        self.hue = self._range(hue, "hue", 0, -0.5, 0.5, False)
 
     @staticmethod
-    def _check_input(value, name, center=1, bound=(0, float("inf")), clip_first_on_zero=True):
+    def _range(value, name, center, lowest, highest, floor_at_zero):
+        """a number v means [center - v, center + v]; a pair is taken as is; None when the range is the identity"""
         if isinstance(value, (int, float)):
             if value < 0:
-                raise ValueError("If {} is a single number, it must be non negative.".format(name))
-            value = [center - float(value), center + float(value)]
-            if clip_first_on_zero:
-                value[0] = max(value[0], 0.0)
+                raise ValueError("%s must be non negative" % name)
+            lo, hi = center - float(value), center + float(value)
+            if floor_at_zero:
+                lo = max(lo, 0.0)
         elif isinstance(value, (tuple, list)) and len(value) == 2:
-            if not bound[0] <= value[0] <= value[1] <= bound[1]:
-                raise ValueError("{} values should be between {}".format(name, bound))
+            lo, hi = value
+            if not lowest <= lo <= hi <= highest:
+                raise ValueError("%s values should be between %s and %s" % (name, lowest, highest))
         else:
-            raise TypeError("{} should be a single number or a list/tuple with lenght 2.".format(name))
-        if value[0] == value[1] == center:
-            value = None
-        return value
+            raise TypeError("%s should be a number or a pair" % name)
+        return None if lo == hi == center else [lo, hi]
 
     def __call__(self, img, target, aux_mats=None):
         order, factors = [], []
@@ -329,17 +335,18 @@ class ColorJitter(object):
         return img, target
 
 
-class RandomSelect(object):
+class RandomSelect(_Transform):
+    """one draw of random.random(): the first pipeline with probability p, else the second"""
+
     def __init__(self, transforms1, transforms2, p=0.5):
         self.transforms1, self.transforms2, self.p = transforms1, transforms2, p
 
     def __call__(self, img, target, aux_mats=None):
-        if random.random() < self.p:
-            return self.transforms1(img, target, aux_mats=aux_mats)
-        return self.transforms2(img, target, aux_mats=aux_mats)
+        chosen = self.transforms1 if random.random() < self.p else self.transforms2
+        return chosen(img, target, aux_mats=aux_mats)
 
 
-class ToTensor(object):
+class ToTensor(_Transform):
     """uint8 [H,W,3] -> uint8 [3,H,W] view marked for Normalize (the /255 happens there, in one kernel with the normalisation);
     auxiliary maps -> [1,H,W] (transforms_depth.py:618-628)"""
 
@@ -349,7 +356,7 @@ class ToTensor(object):
         return img, target, [m.contiguous()[None] for m in aux_mats]
 
 
-class Normalize(object):
+class Normalize(_Transform):
     """ToTensor's /255 + Normalize of the image (one gwd_images_to_batch launch, bit-identical to torchvision) and the division of
     the targets by the image size (transforms_depth.py:631-659)"""
 
@@ -373,17 +380,18 @@ class Normalize(object):
         return image, target
 
 
-class Compose(object):
+class Compose(_Transform):
     def __init__(self, transforms):
-        self.transforms = transforms
+        self.transforms = list(transforms)
 
     def __call__(self, image, target, aux_mats):
-        for t in self.transforms:
-            image, target, aux_mats = t(image, target, aux_mats=aux_mats)
-        return image, target, aux_mats
+        state = (image, target, aux_mats)
+        for step in self.transforms:
+            state = step(state[0], state[1], aux_mats=state[2])
+        return state
 
     def __repr__(self):
-        return self.__class__.__name__ + "(" + "".join("\n    {0}".format(t) for t in self.transforms) + "\n)"
+        return "Compose(\n    " + "\n    ".join(repr(t) for t in self.transforms) + "\n)"
 
 
 def make_coco_transforms(image_set, args=None, eval_mode=None):
