@@ -33,37 +33,54 @@ def _size(image):
 
 
 # ------------------------------------------------------------------------------------------------ functional forms
+def _map_points(target, scale=None, shift=None, divide=None, swap_ends=False):
+    """apply (x, y) -> (x, y) * scale + shift (or / divide) to everything in the target that lives in pixel coordinates: the line end
+    points [n,4] (optionally exchanging the two ends), the polygon centres and the reflection points [n,2].  The reference only
+    touches the centres when the target has lines (transforms_depth.py:213-224); so does this."""
+    target = target.copy()
+
+    def go(pts, reps):
+        if scale is not None:
+            pts = pts * torch.as_tensor(list(scale) * reps)
+        if shift is not None:
+            pts = pts + torch.as_tensor(list(shift) * reps)
+        if divide is not None:
+            pts = pts / torch.tensor(list(divide) * reps, dtype=torch.float32)
+        return pts
+    has_lines = "lines" in target
+    if has_lines:
+        lines = target["lines"]
+        target["lines"] = go(lines[:, [2, 3, 0, 1]] if swap_ends else lines, 2)
+        if "poly_centers" in target:
+            target["poly_centers"] = go(target["poly_centers"], 1)
+    return target, go, has_lines
+
+
 def hflip(image, target, aux_mats=None):
-    """transforms_depth.py:206-231"""
+    """mirror left-right (transforms_depth.py:206-231): x -> w - x, and the two ends of every line trade places so that the first end
+    stays the left one"""
     w, h = _size(image)
     flipped = ops.resize_bilinear_u8(image, h, w, hflip=True)
-    target = target.copy()
-    if "lines" in target:
-        lines = target["lines"]
-        target["lines"] = lines[:, [2, 3, 0, 1]] * torch.as_tensor([-1, 1, -1, 1]) + torch.as_tensor([w, 0, w, 0])
-        if "poly_centers" in target:
-            target["poly_centers"] = target["poly_centers"] * torch.as_tensor([-1, 1]) + torch.as_tensor([w, 0])
-        if "reflection_points" in target:
-            target["reflection_points"] = target["reflection_points"] * torch.as_tensor([-1, 1]) + torch.as_tensor([w, 0])
+    target, go, has_lines = _map_points(target, scale=(-1, 1), shift=(w, 0), swap_ends=True)
+    if has_lines and "reflection_points" in target:
+        target["reflection_points"] = go(target["reflection_points"], 1)
     if aux_mats is not None:
         aux_mats = [ops.gather2d(m, hflip=True) for m in aux_mats]
     return flipped, target, aux_mats
 
 
 def vflip(image, target, aux_mats=None):
-    """transforms_depth.py:234-263"""
+    """mirror top-bottom (transforms_depth.py:234-263): y -> h - y; a vertical line then has its lower end first, so its ends are
+    exchanged (the data set keeps the upper point first when both x are equal)"""
     w, h = _size(image)
     flipped = ops.resize_bilinear_u8(image, h, w, vflip=True)
-    target = target.copy()
-    if "lines" in target:
-        lines = target["lines"] * torch.as_tensor([1, -1, 1, -1]) + torch.as_tensor([0, h, 0, h])
-        vertical = lines[:, 0] == lines[:, 2]
-        lines[vertical] = torch.index_select(lines[vertical], 1, torch.tensor([2, 3, 0, 1]))
-        target["lines"] = lines
-        if "poly_centers" in target:
-            target["poly_centers"] = target["poly_centers"] * torch.as_tensor([1, -1]) + torch.as_tensor([0, h])
+    target, go, has_lines = _map_points(target, scale=(1, -1), shift=(0, h))
+    if has_lines:
+        lines = target["lines"]
+        upright = lines[:, 0] == lines[:, 2]
+        lines[upright] = lines[upright][:, [2, 3, 0, 1]]
         if "reflection_points" in target:
-            target["reflection_points"] = target["reflection_points"] * torch.as_tensor([1, -1]) + torch.as_tensor([0, h])
+            target["reflection_points"] = go(target["reflection_points"], 1)
     if aux_mats is not None:
         aux_mats = [ops.gather2d(m, vflip=True) for m in aux_mats]
     return flipped, target, aux_mats
@@ -90,14 +107,10 @@ def resize(image, target, size, max_size=None, aux_mats=None):
     rescaled = ops.resize_bilinear_u8(image, oh, ow)
     if target is None:
         return rescaled, None
-    ratio_width, ratio_height = float(ow) / float(w0), float(oh) / float(h0)
-    target = target.copy()
-    if "lines" in target:
-        target["lines"] = target["lines"] * torch.as_tensor([ratio_width, ratio_height, ratio_width, ratio_height])
-        if "poly_centers" in target:
-            target["poly_centers"] = target["poly_centers"] * torch.as_tensor([ratio_width, ratio_height])
+    rx, ry = float(ow) / float(w0), float(oh) / float(h0)
+    target, go, _ = _map_points(target, scale=(rx, ry))
     if "reflection_points" in target:
-        target["reflection_points"] = target["reflection_points"] * torch.as_tensor([ratio_width, ratio_height])
+        target["reflection_points"] = go(target["reflection_points"], 1)
     target["size"] = torch.tensor([oh, ow])
     if aux_mats is not None:
         aux_mats = [ops.gather2d(m, oh, ow) for m in aux_mats]
@@ -368,13 +381,9 @@ class Normalize(_Transform):
         image = ops.images_to_batch([image.contiguous()], mean=self.mean, std=self.std, want_mask=False)[0][0]
         if target is None:
             return image, None
-        target = target.copy()
-        if "lines" in target:
-            target["lines"] = target["lines"] / torch.tensor([w, h, w, h], dtype=torch.float32)
-            if "poly_centers" in target:
-                target["poly_centers"] = target["poly_centers"] / torch.tensor([w, h], dtype=torch.float32)
+        target, go, _ = _map_points(target, divide=(w, h))
         if "reflection_points" in target:
-            target["reflection_points"] = target["reflection_points"] / torch.tensor([w, h], dtype=torch.float32)
+            target["reflection_points"] = go(target["reflection_points"], 1)
         if aux_mats is not None:
             return image, target, aux_mats
         return image, target
