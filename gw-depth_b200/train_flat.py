@@ -224,11 +224,16 @@ class FlatModule:
         return conv_gemm(dY, cv.pwT, bias=False, res=res, res_mode=RES_AFTER if res is not None else RES_NONE)
 
     @staticmethod
-    def lin_bwd(lin, dY, X, need_dx=True, res=None, x_coff=0):
+    def lin_bwd(lin, dY, X, need_dx=True, res=None, x_coff=0, out=None, y_coff=0, accumulate=False):
+        """weight / bias gradient (forked) and the data gradient dX = dY W.  out / y_coff: write dX into a channel slice of a wider
+        buffer; accumulate: add to what `out` already holds (in place: the epilogue reads the old tile and stores the sum)"""
         fork_wgrad(lambda: ops.linear_wgrad(dY, X, lin.gw, lin.gb, x_coff=x_coff), dY, X)
         if not need_dx:
             return None
-        return conv_gemm(dY, lin.pwT, bias=False, res=res, res_mode=RES_AFTER if res is not None else RES_NONE)
+        if accumulate:
+            assert out is not None and res is None
+            return conv_gemm(dY, lin.pwT, bias=False, res=out, res_coff=y_coff, res_mode=RES_AFTER, out=out, y_coff=y_coff)
+        return conv_gemm(dY, lin.pwT, bias=False, res=res, res_mode=RES_AFTER if res is not None else RES_NONE, out=out, y_coff=y_coff)
 
     # ------------------------------------------------------------------ optimizer
     def allreduce_grads(self):

@@ -193,17 +193,20 @@ class ClassStage(FlatModule):
             g_new = [self._mlp_ln_bwd(g, blk[m], blk[n], t["new"][j], t["ln"][j], t["h_raw"][j], t["h"][j])
                      for j, (g, m, n) in enumerate(((g_x, "mlp", "n2"), (g_d, "mlp_d", "nd2"), (g_s, "mlp_s", "ns2")))]
             # adjoint of the window merge: partition the gradient (zero rows in the padding)
-            d_attn = ops.window_gather(g_new[0], B, H, W, ws, shift, C=C)                  # d tx[:, :C] via the residual branch
+            # d tx [rows_w, tC] is assembled in place: the residual-branch gradient of the features lands in its first C columns, the
+            # two token-query data gradients in the token columns, and the gkv data gradient is accumulated over the whole width
+            Hp, Wp = -(-H // ws) * ws, -(-W // ws) * ws
+            d_tx = torch.empty(B * Hp * Wp, tC, dtype=torch.bfloat16, device=self.dev)
+            ops.window_gather(g_new[0], B, H, W, ws, shift, C=C, out=d_tx, y_coff=0)
             d_dpr = ops.window_gather(g_new[1], B, H, W, ws, shift, C=td)
             d_spr = ops.window_gather(g_new[2], B, H, W, ws, shift, C=td)
             d_dout = self.lin_bwd(blk["pdth"], d_dpr, t["dout"])
             d_sout = self.lin_bwd(blk["pdth"], d_spr, t["sout"])
-            g_dq, g_sq, g_gkv = ops.token_attention_bwd(t["dq"], t["sq"], t["gkv"], d_dout, d_sout, items=d_attn.shape[0] // N, N=N,
+            g_dq, g_sq, g_gkv = ops.token_attention_bwd(t["dq"], t["sq"], t["gkv"], d_dout, d_sout, items=d_tx.shape[0] // N, N=N,
                                                         heads=nh, td=td // nh, tc=tC // nh, scale=self.scale)
-            d_tx = self.lin_bwd(blk["gkv"], g_gkv, t["tx"])                                # [rows_w, tC]
-            d_tx[:, :C] += d_attn
-            d_tx[:, C:C + td] += self.lin_bwd(blk["dq"], g_dq, t["tx"], x_coff=C)
-            d_tx[:, C + td:] += self.lin_bwd(blk["sq"], g_sq, t["tx"], x_coff=C + td)
+            self.lin_bwd(blk["dq"], g_dq, t["tx"], x_coff=C, out=d_tx, y_coff=C)
+            self.lin_bwd(blk["sq"], g_sq, t["tx"], x_coff=C + td, out=d_tx, y_coff=C + td)
+            self.lin_bwd(blk["gkv"], g_gkv, t["tx"], out=d_tx, accumulate=True)            # [rows_w, tC]
             d_o = self.lin_bwd(blk["proj"], d_tx, t["o"])                                  # reads the first C columns of d_tx
             blk["dbias"].zero_()
             dqkv = ops.window_attention_bwd(t["qkv"], d_o, items=d_o.shape[0] // N, heads=nh, N=N, hd=hd, scale=self.scale,
