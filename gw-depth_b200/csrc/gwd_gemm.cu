@@ -9,6 +9,10 @@
 // The fp32 accumulator is double-buffered in TMEM so the epilogue of tile i overlaps the main
 // loop of tile i+1.
 //
+// CTA-pair variant (template flag CTA2, clusters of two CTAs): streamed-weight 3x3 convolutions run
+// tcgen05.mma.cta_group::2 -- one M = 256 MMA over both SMs, each CTA holding its 128 rows of A and
+// half of the weight tile -- see the wrappers below and the kernel's header comment.
+//
 // 3x3 convolutions (stride 1, zero pad 1) are tap-GEMMs: for each channel chunk and each dx the
 // producer loads ONE activation box of (TH+2) x TW pixels (TMA out-of-bounds zero fill provides
 // the padding) and the three dy taps are MMAs whose A descriptor start address is shifted by
