@@ -263,6 +263,8 @@ class Trainer:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.dev)
         self._defer = []
+        from . import capi
+        n0 = capi.launch_count()          # library kernels enqueued while capturing = library kernels every replay runs
         st["g1"] = torch.cuda.CUDAGraph()
         with torch.cuda.graph(st["g1"]):
             st["feats"], st["logits"], st["lines"] = self._forward_line(st["images"])
@@ -275,6 +277,7 @@ class Trainer:
         with torch.cuda.graph(st["g3"], pool=st["g1"].pool()):
             self.backward_line(st["dlogits"], st["dlines"])
         st["ex3"], self._defer = self._defer, None
+        st["kernels_per_replay"] = capi.launch_count() - n0
         return st
 
     def _train_step_graphed(self, images, targets, depth_gt, seg_gt, criterion):
@@ -282,6 +285,7 @@ class Trainer:
         st = self._graphs.get(key)
         if st is None:
             st = self._graphs[key] = self._capture(images, depth_gt, seg_gt, criterion, targets)
+        self.replayed_kernels = getattr(self, "replayed_kernels", 0) + st["kernels_per_replay"]
         st["images"].copy_(images, non_blocking=True)
         st["depth_gt"].copy_(depth_gt, non_blocking=True)
         st["seg_gt"].copy_(seg_gt, non_blocking=True)
