@@ -89,3 +89,79 @@ def test_resize_target_size_rule():
         assert min(oh, ow) <= size and (mx is None or max(oh, ow) <= mx + 1)
         if mx is None or max(w, h) / min(w, h) * size <= mx:
             assert min(oh, ow) == size
+
+
+def _reference_transforms():
+    import types
+    import ref_shims
+    if not ref_shims.reference_available():
+        pytest.skip("reference not available")
+    pytest.importorskip("torchvision")
+    ref_shims.install()
+    src = os.path.join(ref_shims.REFERENCE_ROOT, "src")
+    if src not in sys.path:
+        sys.path.insert(0, src)
+    try:
+        import shapely.geometry  # noqa: F401
+    except ImportError:
+        def _no(*a, **k):
+            raise ImportError("shapely is not installed")
+        sh, g = types.ModuleType("shapely"), types.ModuleType("shapely.geometry")
+        g.Polygon, g.mapping, sh.geometry = _no, _no, g
+        sys.modules["shapely"], sys.modules["shapely.geometry"] = sh, g
+    import datasets.transforms_depth as T
+    return T
+
+
+def _targets(seed, h=480, w=640):
+    import torch
+    rng = np.random.default_rng(seed)
+    lines, centers, ids = [], [], []
+    for pid in range(4):
+        cx, cy = rng.uniform(0.1 * w, 0.9 * w), rng.uniform(0.1 * h, 0.9 * h)
+        rx, ry = rng.uniform(20, 0.3 * w), rng.uniform(20, 0.3 * h)
+        pts = [(cx - rx, cy - ry), (cx + rx, cy - ry * 0.8), (cx + rx * 0.9, cy + ry), (cx - rx * 0.7, cy + ry * 0.9), (cx - rx * 1.1, cy)]
+        for k in range(5):
+            (x0, y0), (x1, y1) = pts[k], pts[(k + 1) % 5]
+            if x0 > x1:
+                x0, y0, x1, y1 = x1, y1, x0, y0
+            lines.append([x0, y0, x1, y1])
+            centers.append([cx, cy])
+            ids.append(pid)
+    n = len(lines)
+    return {"lines": torch.tensor(lines, dtype=torch.float32), "poly_centers": torch.tensor(centers, dtype=torch.float32),
+            "poly_ids": torch.tensor(ids), "labels": torch.zeros(n, dtype=torch.int64), "area": torch.ones(n), "iscrowd": torch.zeros(n),
+            "size": torch.as_tensor([h, w])}
+
+
+def test_crop_targets_and_size_rule_equal_the_reference():
+    """the host side of gw-depth_b200/data.py that needs no GPU: the line clipping / polygon-centre logic of crop() (vectorised here,
+    a per-line Python chain in src/datasets/transforms_depth.py:59-202) and the output size of resize (:319-339), against the
+    reference functions on PIL images"""
+    import importlib
+    import torch
+    sys.path.insert(0, ROOT)
+    T = _reference_transforms()
+    data = importlib.import_module("gw-depth_b200.data")
+    rng = np.random.default_rng(0)
+    img = np.zeros((480, 640, 3), np.uint8)
+    checked = 0
+    for seed in range(160):
+        tgt = _targets(seed)
+        w = int(rng.integers(200, 640)); h = int(rng.integers(150, 480))
+        i = int(rng.integers(0, 480 - h + 1)); j = int(rng.integers(0, 640 - w + 1))
+        try:
+            _, ref_t = T.crop(Image.fromarray(img), {k: v.clone() for k, v in tgt.items()}, (i, j, h, w))
+        except ImportError:
+            continue          # the polygon / window intersection branch (shapely)
+        cimg, our_t, _ = data.crop(torch.from_numpy(img), {k: v.clone() for k, v in tgt.items()}, (i, j, h, w))
+        assert tuple(cimg.shape) == (h, w, 3)
+        assert set(our_t) == set(ref_t)
+        for k in ref_t:
+            assert torch.equal(torch.as_tensor(our_t[k]), torch.as_tensor(ref_t[k])), (seed, k)
+        checked += 1
+    assert checked >= 15          # (the other crops hit the shapely branch, which the image does not have)
+    for (w, h, size, mx) in [(640, 480, 800, 1024), (640, 480, 480, 1024), (480, 640, 512, 1024), (1000, 300, 800, 1024), (333, 500, 600, None),
+                             (500, 375, 608, 1024), (1024, 1024, 800, 1024), (641, 480, 480, None)]:
+        ref_img, _ = T.resize(Image.fromarray(np.zeros((h, w, 3), np.uint8)), None, size, mx)
+        assert data._short_side_target(w, h, size, mx) == (ref_img.size[1], ref_img.size[0]) == D.resize_target_size(w, h, size, mx)
