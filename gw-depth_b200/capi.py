@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgwd_b200.so")
 
 ACT_NONE, ACT_RELU, ACT_GELU, ACT_ELU, ACT_SIGMOID = 0, 1, 2, 3, 4
-RES_NONE, RES_BEFORE_NORM, RES_AFTER = 0, 1, 2
+RES_NONE, RES_BEFORE_NORM, RES_AFTER, RES_MUL_ACTGRAD = 0, 1, 2, 3
 
 c_void_p = ctypes.c_void_p
 c_int = ctypes.c_int32
@@ -32,6 +32,7 @@ class GemmDesc(ctypes.Structure):
         ("y_raw", c_void_p), ("yraw_cstride", c_int), ("yraw_coff", c_int),
         ("store_n", c_int), ("w_per_image", c_int), ("upsample2", c_int),
         ("x_wstride", ctypes.c_int64), ("x_hstride", ctypes.c_int64), ("x_bstride", ctypes.c_int64),
+        ("ag_act", c_int), ("ag_from_input", c_int), ("ag_y_mul", c_float), ("ag_scale", c_float),
     ]
 
 

@@ -73,6 +73,27 @@ __device__ __forceinline__ float gwd_gelu_grad(float v) {
   const float du = fmaf(0.1070322243f, v2, 0.7978845608f);
   return fmaf(0.5f * v * fmaf(-t, t, 1.f), du, fmaf(0.5f, t, 0.5f));
 }
+// d act / d (input) as a factor: from the activation's OUTPUT yy (from_input == 0: ReLU, ELU, sigmoid are invertible there) or from
+// its INPUT yy (from_input != 0; GELU needs it).  Shared by gwd_act_bwd, gwd_layernorm_bwd and the activation-gradient epilogue of
+// the data-gradient GEMMs (gwd_conv_gemm, res_mode = GWD_RES_MUL_ACTGRAD).
+__device__ __forceinline__ float gwd_act_grad(float v, int act) {
+  switch (act) {
+    case GWD_ACT_RELU: return v > 0.f ? 1.f : 0.f;
+    case GWD_ACT_GELU: return gwd_gelu_grad(v);
+    case GWD_ACT_ELU: return v > 0.f ? 1.f : __expf(v);
+    case GWD_ACT_SIGMOID: { const float s = 1.f / (1.f + __expf(-v)); return s * (1.f - s); }
+    default: return 1.f;
+  }
+}
+__device__ __forceinline__ float gwd_act_factor(float yy, int act, int from_input) {
+  if (from_input) return gwd_act_grad(yy, act);
+  switch (act) {
+    case GWD_ACT_RELU: return yy > 0.f ? 1.f : 0.f;
+    case GWD_ACT_ELU: return yy > 0.f ? 1.f : yy + 1.f;
+    case GWD_ACT_SIGMOID: return yy * (1.f - yy);
+    default: return 1.f;
+  }
+}
 // erf(x) by Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), kept for callers that need erf itself
 __device__ __forceinline__ float gwd_erf(float x) {
   float ax = fabsf(x);

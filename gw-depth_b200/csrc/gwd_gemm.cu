@@ -69,6 +69,8 @@ struct GemmParams {
   int y_cstride, y_coff, y_f32;
   __nv_bfloat16* y_raw;
   int yraw_cstride, yraw_coff;
+  int ag_act, ag_from_input;      // res_mode == GWD_RES_MUL_ACTGRAD: activation whose derivative (at the saved tensor `res`) scales the result
+  float ag_y_mul, ag_scale;
   int phase_n;      // > 0: fused nearest x2 up-sampling, output channels are 4 phase groups of phase_n channels
   int ln_groups;    // LayerNorm is applied per group of n / ln_groups channels (1 = whole row)
 };
@@ -277,6 +279,14 @@ __device__ __forceinline__ void add_bf16x8(float* v, const uint4& u) {
   v[4] += f2.x; v[5] += f2.y; v[6] += f3.x; v[7] += f3.y;
 }
 
+// v *= act'(saved activation) * scale  (GWD_RES_MUL_ACTGRAD)
+__device__ __forceinline__ void mul_actgrad_bf16x8(float* v, const uint4& u, const GemmParams& p) {
+  const float2 f0 = gwd_unpack_bf16x2(u.x), f1 = gwd_unpack_bf16x2(u.y), f2 = gwd_unpack_bf16x2(u.z), f3 = gwd_unpack_bf16x2(u.w);
+  const float y[8] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, f3.x, f3.y};
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] *= gwd_act_factor(y[i] * p.ag_y_mul, p.ag_act, p.ag_from_input) * p.ag_scale;
+}
+
 // RES_BY_CALLER: the caller adds the (software-pipelined) residual itself
 template <int PRE_ACT, bool RES_BY_CALLER = false>
 __device__ __forceinline__ void load_chunk(const GemmParams& p, uint32_t taddr, int n_base, const RowCtx& rc,
@@ -341,7 +351,10 @@ __device__ __forceinline__ void store_bf16_16(__nv_bfloat16* dst, const float (&
 // sensitive to its instruction footprint).
 // CTA2: the CTA-pair variant (see the cta_group::2 wrappers above).  The pair owns two consecutive M tiles of the same N tile (rank r
 // = M tile 2q + r; an odd tail gives rank 1 a ghost tile: its loads are zero-filled out-of-bounds boxes and its stores are masked).
-template <int PRE_ACT, int POST_ACT, bool HAS_LN, bool TMAEP = false, bool CTA2 = false>
+// ACTGRAD (training, data-gradient GEMMs): the saved activation tensor travels the residual path (software-pipelined loads, or the TMA
+// staging tile) and the result is MULTIPLIED by the activation's derivative there -- the separate gwd_act_bwd pass over the gradient
+// (read dy, read y, write) disappears.  Its own instantiations: the other epilogues do not carry the code.
+template <int PRE_ACT, int POST_ACT, bool HAS_LN, bool TMAEP = false, bool CTA2 = false, bool ACTGRAD = false>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ GemmParams p, const __grid_constant__ CUtensorMap map_res,
@@ -581,7 +594,7 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       const bool res_pf = !TMAEP && p.res_mode != GWD_RES_NONE && rc.valid && (!HAS_LN || p.res_mode == GWD_RES_AFTER);
       const __nv_bfloat16* res_row = p.res + rc.pix * p.res_cstride + p.res_coff + t.n0;
       if (res_pf && c_begin < c_end) {
-        const bool after = p.res_mode == GWD_RES_AFTER;
+        const bool after = p.res_mode != GWD_RES_BEFORE_NORM;
         const int nb = t.n0 + c_begin * 16;
         if (!after || nb + 8 <= p.store_n) rpre0 = __ldg(reinterpret_cast<const uint4*>(res_row + c_begin * 16));
         if (!after || nb + 16 <= p.store_n) rpre1 = __ldg(reinterpret_cast<const uint4*>(res_row + c_begin * 16) + 1);
@@ -652,7 +665,7 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
           load_chunk<PRE_ACT, !HAS_LN>(p, t_row + c * 16, n_base, rc, v);
           const uint4 rcur0 = rpre0, rcur1 = rpre1;
           if (res_pf && c + 1 < my_end) {
-            const bool after = p.res_mode == GWD_RES_AFTER;
+            const bool after = p.res_mode != GWD_RES_BEFORE_NORM;
             rpre0 = rpre1 = make_uint4(0u, 0u, 0u, 0u);
             if (!after || n_base + 24 <= p.store_n) rpre0 = __ldg(reinterpret_cast<const uint4*>(res_row + (c + 1) * 16));
             if (!after || n_base + 32 <= p.store_n) rpre1 = __ldg(reinterpret_cast<const uint4*>(res_row + (c + 1) * 16) + 1);
@@ -703,13 +716,23 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
             for (int i = 0; i < 16; ++i) v[i] *= p.out_scale;
           }
           if (!HAS_LN) {
-            if (res_pf && p.res_mode == GWD_RES_AFTER) {
-              add_bf16x8(v, rcur0);
-              add_bf16x8(v + 8, rcur1);
-            }
-            if (TMAEP && p.res_mode == GWD_RES_AFTER) {
-              add_bf16x8(v, *ep_p0);
-              add_bf16x8(v + 8, *ep_p1);
+            if (ACTGRAD) {
+              if (TMAEP) {
+                mul_actgrad_bf16x8(v, *ep_p0, p);
+                mul_actgrad_bf16x8(v + 8, *ep_p1, p);
+              } else if (res_pf) {
+                mul_actgrad_bf16x8(v, rcur0, p);
+                mul_actgrad_bf16x8(v + 8, rcur1, p);
+              }
+            } else {
+              if (res_pf && p.res_mode == GWD_RES_AFTER) {
+                add_bf16x8(v, rcur0);
+                add_bf16x8(v + 8, rcur1);
+              }
+              if (TMAEP && p.res_mode == GWD_RES_AFTER) {
+                add_bf16x8(v, *ep_p0);
+                add_bf16x8(v + 8, *ep_p1);
+              }
             }
           } else if (res_pf) {   // LayerNorm, residual added after it: the pieces were prefetched (zeros beyond store_n)
             add_bf16x8(v, rcur0);
@@ -827,6 +850,13 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
                   "gwd_conv_gemm: bad residual");
   if (d->y_raw)
     GWD_CHECK_ARG(d->yraw_cstride % 8 == 0 && d->yraw_coff % 8 == 0 && store_n % 8 == 0, "gwd_conv_gemm: bad y_raw");
+  const bool actgrad = d->res_mode == GWD_RES_MUL_ACTGRAD;
+  if (actgrad)
+    GWD_CHECK_ARG(d->ln_g == nullptr && d->pre_act == GWD_ACT_NONE && d->post_act == GWD_ACT_NONE && !d->y_f32 && d->y_raw == nullptr &&
+                      !d->upsample2 && !d->w_per_image && (d->out_scale == 1.f || d->out_scale == 0.f) &&
+                      (d->ag_act == GWD_ACT_RELU || d->ag_act == GWD_ACT_ELU || d->ag_act == GWD_ACT_SIGMOID ||
+                       (d->ag_act == GWD_ACT_GELU && d->ag_from_input)),
+                  "gwd_conv_gemm: GWD_RES_MUL_ACTGRAD needs a plain bf16 epilogue and ReLU / ELU / sigmoid (or GELU from its input)");
 
   GemmParams p;
   memset(&p, 0, sizeof(p));
@@ -1010,6 +1040,9 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
   p.y = d->y; p.y_cstride = d->y_cstride; p.y_coff = d->y_coff; p.y_f32 = d->y_f32;
   p.y_raw = static_cast<__nv_bfloat16*>(d->y_raw);
   p.yraw_cstride = d->yraw_cstride; p.yraw_coff = d->yraw_coff;
+  p.ag_act = d->ag_act; p.ag_from_input = d->ag_from_input;
+  p.ag_y_mul = d->ag_y_mul != 0.f ? d->ag_y_mul : 1.f;
+  p.ag_scale = d->ag_scale != 0.f ? d->ag_scale : 1.f;
   p.phase_n = d->upsample2 ? d->n_pad / 4 : 0;
   p.ln_groups = d->upsample2 ? 4 : 1;
 
@@ -1167,6 +1200,31 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
     launched = true;                                                                                          \
   }
   bool launched = false;
+  if (actgrad) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cta2 ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+#define GWD_GEMM_AG(TM, C2)                                                                                          \
+  {                                                                                                                  \
+    auto kfn = gwd_tapgemm_kernel<GWD_ACT_NONE, GWD_ACT_NONE, false, TM, C2, true>;                                  \
+    static bool attr_set = false;                                                                                    \
+    if (!attr_set) {                                                                                                 \
+      GWD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));                  \
+      attr_set = true;                                                                                               \
+    }                                                                                                                \
+    GWD_CUDA(cudaLaunchKernelEx(&cfg, kfn, map_a, map_b, p, map_res, map_y));                                        \
+  }
+    if (tma_ep) GWD_GEMM_AG(true, false)
+    else if (cta2) GWD_GEMM_AG(false, true)
+    else GWD_GEMM_AG(false, false)
+#undef GWD_GEMM_AG
+    GWD_LAUNCHED();
+    return GWD_OK;
+  }
   GWD_GEMM_CASE_TMAEP(GWD_ACT_NONE)
   else GWD_GEMM_CASE_TMAEP(GWD_ACT_RELU)
   else GWD_GEMM_CASE_TMAEP(GWD_ACT_GELU)

@@ -37,17 +37,6 @@ __device__ __forceinline__ void st8(bf16* p, const float (&f)[8]) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kLnWarps = 8;
 
-// d act(v) / dv from the activation's INPUT v (GELU: gwd_gelu_grad, the derivative of the tanh form the forward evaluates)
-__device__ __forceinline__ float gwd_act_grad(float v, int act) {
-  switch (act) {
-    case GWD_ACT_RELU: return v > 0.f ? 1.f : 0.f;
-    case GWD_ACT_GELU: return gwd_gelu_grad(v);
-    case GWD_ACT_ELU: return v > 0.f ? 1.f : __expf(v);
-    case GWD_ACT_SIGMOID: { const float s = 1.f / (1.f + __expf(-v)); return s * (1.f - s); }
-    default: return 1.f;
-  }
-}
-
 // LPR lanes own one row (32: one row per warp, NV chunks of 256 columns; 16 / 8: two / four rows per warp for C <= 128 / 64,
 // so that narrow rows -- the 64-channel maps of the dense head -- still fill every lane)
 template <int NV, int LPR>
@@ -193,16 +182,7 @@ gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16*
 // activation backward from the OUTPUT value: ReLU: dy * (y > 0); sigmoid: dy * y * (1 - y); none: dy.
 // Converts fp32 / bf16 inputs to a bf16 [rows, out_cols] matrix whose columns n..out_cols are zero.
 // ------------------------------------------------------------------------------------------------
-// derivative factor of `act` from its OUTPUT yy (from_input == 0) or from its INPUT yy (from_input != 0)
-__device__ __forceinline__ float act_factor(float yy, int act, int from_input) {
-  if (from_input) return gwd_act_grad(yy, act);
-  switch (act) {
-    case GWD_ACT_RELU: return yy > 0.f ? 1.f : 0.f;
-    case GWD_ACT_ELU: return yy > 0.f ? 1.f : yy + 1.f;
-    case GWD_ACT_SIGMOID: return yy * (1.f - yy);
-    default: return 1.f;
-  }
-}
+__device__ __forceinline__ float act_factor(float yy, int act, int from_input) { return gwd_act_factor(yy, act, from_input); }
 
 template <typename TD, typename TY>
 __global__ void gwd_act_bwd_kernel(const TD* __restrict__ dy, int64_t dy_rs, const TY* __restrict__ y, int64_t y_rs, int act,

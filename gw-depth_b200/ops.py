@@ -121,7 +121,7 @@ def _as_bhwc(t):
 
 def conv_gemm(x, pw, *, x_coff=0, out=None, y_coff=0, out_channels=None, out_f32=False,
               bias=True, ln=None, ln_eps=1e-5, pre_act=ACT_NONE, post_act=ACT_NONE, out_scale=1.0,
-              res=None, res_coff=0, res_mode=RES_NONE, y_raw=None, w_per_image=False, subsample2=False):
+              res=None, res_coff=0, res_mode=RES_NONE, y_raw=None, w_per_image=False, subsample2=False, act_grad=None):
     """y = epilogue(conv_or_linear(x[..., x_coff:x_coff+cin], pw)).  See include/gwd_b200.h.
 
     x      : bf16 channels-last [B,H,W,Cx] or [rows,Cx] / [B,L,Cx]
@@ -162,6 +162,12 @@ def conv_gemm(x, pw, *, x_coff=0, out=None, y_coff=0, out_channels=None, out_f32
         d.ln_g, d.ln_b = ln[0].data_ptr(), ln[1].data_ptr()
     d.ln_eps = ln_eps
     d.pre_act, d.post_act, d.out_scale = pre_act, post_act, out_scale
+    if act_grad is not None:      # (saved activation, act, from_input, y_mul, scale): result *= act'(saved) * scale  (training)
+        assert res is None and ln is None and pre_act == ACT_NONE and post_act == ACT_NONE and not out_f32
+        ag_y, ag_act, ag_from_input, ag_y_mul, ag_scale = act_grad
+        assert ag_y.dtype == torch.bfloat16 and ag_y.is_contiguous()
+        d.res = ag_y.data_ptr(); d.res_cstride = ag_y.shape[-1]; d.res_coff = 0; d.res_mode = capi.RES_MUL_ACTGRAD
+        d.ag_act, d.ag_from_input, d.ag_y_mul, d.ag_scale = int(ag_act), int(bool(ag_from_input)), float(ag_y_mul), float(ag_scale)
     if res is not None:
         assert res.dtype == torch.bfloat16 and res.is_contiguous() and res_mode != RES_NONE
         d.res = res.data_ptr(); d.res_cstride = res.shape[-1]; d.res_coff = res_coff; d.res_mode = res_mode

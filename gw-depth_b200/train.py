@@ -24,6 +24,7 @@ dC5 so that a backbone backward can be attached.
 import torch
 
 from . import ops, parallel
+from .train_flat import FUSE_ACT_GRAD
 from .engine import DEFAULT_CFG, sine_table, sine_tables_masked
 from .ops import ACT_NONE, ACT_RELU, ACT_SIGMOID, RES_AFTER, RES_BEFORE_NORM, RES_NONE, PackedWeight, conv_gemm, round_up
 
@@ -274,7 +275,7 @@ class LineBranch:
         return logits.view(nl, B, Q, -1), lines.view(nl, B, Q, -1)
 
     # ------------------------------------------------------------------ backward
-    def _lin_bwd(self, lin, dY, X, need_dx=True, res=None):
+    def _lin_bwd(self, lin, dY, X, need_dx=True, res=None, act_grad=None):
         """dY [R, n_pad] bf16, X [R, K] bf16: accumulates dW / db into the flat gradient views; returns dX (+ res) or None.
         The weight gradient is off the critical path (nothing downstream reads it before the optimizer), so it runs on a
         side stream: in the captured graph it becomes a parallel branch next to the dX chain."""
@@ -285,7 +286,7 @@ class LineBranch:
         self._keep.append(dY)                        # the side stream still reads it: no reuse before the join
         if not need_dx:
             return None
-        return conv_gemm(dY, lin.pwT, bias=False, res=res, res_mode=RES_AFTER if res is not None else RES_NONE)
+        return conv_gemm(dY, lin.pwT, bias=False, res=res, res_mode=RES_AFTER if res is not None else RES_NONE, act_grad=act_grad)
 
     def _ln_bwd(self, dy, z, ln, add=None):
         return ops.layernorm_bwd(dy, z, ln[0], ln[2], ln[3], add=add)
@@ -305,9 +306,12 @@ class LineBranch:
 
     def _ffn_bwd(self, ly, d_out, z, hm, x_in, ln, site_hidden=0, site_out=0):
         dz = self._ln_bwd(d_out, z, ln)
-        dh = self._lin_bwd(ly["l2"], self._sub_grad(dz, site_out), hm)
         # hm is the hidden layer AFTER its dropout: hm > 0 <=> active and kept, and kept units carry the factor 1 / (1 - p)
-        dpre = ops.act_bwd(dh, hm, ACT_RELU, scale=1.0 / (1.0 - self.p_drop) if self.p_drop > 0 else 1.0)
+        keep_scale = 1.0 / (1.0 - self.p_drop) if self.p_drop > 0 else 1.0
+        if FUSE_ACT_GRAD:        # relu' (and the dropout factor) in the epilogue of linear2's data-gradient GEMM
+            dpre = self._lin_bwd(ly["l2"], self._sub_grad(dz, site_out), hm, act_grad=(hm, ACT_RELU, False, 1.0, keep_scale))
+        else:
+            dpre = ops.act_bwd(self._lin_bwd(ly["l2"], self._sub_grad(dz, site_out), hm), hm, ACT_RELU, scale=keep_scale)
         return self._lin_bwd(ly["l1"], dpre, x_in, res=dz)
 
     def _add(self, a, b):

@@ -19,7 +19,7 @@ import torch
 
 from . import ops
 from .ops import ACT_RELU, RES_AFTER, RES_BEFORE_NORM, RES_NONE, PackedWeight, conv_gemm, pack_conv3x3, pack_linear
-from .train_flat import join_wgrads, Conv3x3, FlatModule, Linear
+from .train_flat import FUSE_ACT_GRAD, join_wgrads, Conv3x3, FlatModule, Linear
 
 BODY = "backbone.0.body."
 LAYERS = ((1, 3), (2, 4), (3, 6), (4, 3))
@@ -201,13 +201,18 @@ class BackboneTrain(FlatModule):
                 ho, wo = out.shape[1:3]
                 rows_o = B * ho * wo
                 gs = ops.act_bwd(g.reshape(rows_o, -1), out.view(rows_o, -1), ACT_RELU)                    # d(sum) = d out * relu'
-                d_y2 = ops.act_bwd(self.lin_bwd(blk["c3"], gs, y2.view(rows_o, -1)), y2.view(rows_o, -1), ACT_RELU)
+                if FUSE_ACT_GRAD:      # relu' of the conv2 output in the epilogue of conv3's data-gradient GEMM
+                    d_y2 = self.lin_bwd(blk["c3"], gs, y2.view(rows_o, -1), act_grad=(y2.view(rows_o, -1), ACT_RELU, False, 1.0, 1.0))
+                else:
+                    d_y2 = ops.act_bwd(self.lin_bwd(blk["c3"], gs, y2.view(rows_o, -1)), y2.view(rows_o, -1), ACT_RELU)
                 if blk["stride"] == 2:
                     d_col = self.lin_bwd(blk["c2"], d_y2, col.view(rows_o, -1))
                     d_y1 = ops.col2im3x3_s2(d_col.view(B, ho, wo, -1), H, W)
+                    d_y1 = ops.act_bwd(d_y1.view(B * H * W, -1), y1.view(B * H * W, -1), ACT_RELU)
+                elif FUSE_ACT_GRAD:
+                    d_y1 = self.conv_bwd(blk["c2"], d_y2.view(B, ho, wo, -1), y1, act_grad=(y1, ACT_RELU, False, 1.0, 1.0)).view(B * H * W, -1)
                 else:
-                    d_y1 = self.conv_bwd(blk["c2"], d_y2.view(B, ho, wo, -1), y1)
-                d_y1 = ops.act_bwd(d_y1.view(B * H * W, -1), y1.view(B * H * W, -1), ACT_RELU)
+                    d_y1 = ops.act_bwd(self.conv_bwd(blk["c2"], d_y2.view(B, ho, wo, -1), y1).view(B * H * W, -1), y1.view(B * H * W, -1), ACT_RELU)
                 need_dx = blk is not first
                 if blk["stride"] == 2:
                     d_x = self.lin_bwd(blk["c1"], d_y1, x.view(B * H * W, -1), need_dx=need_dx)

@@ -8,6 +8,8 @@ buffer, so the optimizer (reference: AdamW + clip_grad_norm_, src/main_glassrgbd
 is two launches (gwd_sumsq, gwd_adamw_step) and data-parallel training one all-reduce per module.  Padding rows / columns
 have zero gradient and zero value, so they stay zero under AdamW.
 """
+import os
+
 import torch
 
 from . import ops, parallel
@@ -89,6 +91,13 @@ class Linear:
 
     def transposes(self):
         return [(self.wb, self.wT)]
+
+
+# GWD_FUSE_ACT_GRAD=1: the activation backward runs in the epilogue of the data-gradient GEMM that produces its operand
+# (gwd_conv_gemm, res_mode = GWD_RES_MUL_ACTGRAD) instead of as separate gwd_act_bwd launches.  Correct (tests/test_gemm_gpu.py and the
+# whole training suite pass with it), but the step time does not move (33.9 ms either way: the removed passes were overlapped, the
+# epilogues get longer), so the separate launches stay the default.
+FUSE_ACT_GRAD = os.environ.get("GWD_FUSE_ACT_GRAD", "0") == "1"
 
 
 class FlatModule:
@@ -216,15 +225,16 @@ class FlatModule:
             self.view(self.G, short).index_fill_(-1, idx, 0.0)
 
     @staticmethod
-    def conv_bwd(cv, dY, X, need_dx=True, res=None):
-        """dY [B,H,W,n_pad], X [B,H,W,cin_pad] bf16: dW accumulated into the flat gradient view; returns dX (+ res)"""
+    def conv_bwd(cv, dY, X, need_dx=True, res=None, act_grad=None):
+        """dY [B,H,W,n_pad], X [B,H,W,cin_pad] bf16: dW accumulated into the flat gradient view; returns dX (+ res), or dX times the
+        derivative of the activation that produced X (act_grad = (saved, act, from_input, y_mul, scale), fused in the GEMM epilogue)"""
         fork_wgrad(lambda: ops.conv3x3_wgrad(dY, X, cv.gw), dY, X)
         if not need_dx:
             return None
-        return conv_gemm(dY, cv.pwT, bias=False, res=res, res_mode=RES_AFTER if res is not None else RES_NONE)
+        return conv_gemm(dY, cv.pwT, bias=False, res=res, res_mode=RES_AFTER if res is not None else RES_NONE, act_grad=act_grad)
 
     @staticmethod
-    def lin_bwd(lin, dY, X, need_dx=True, res=None, x_coff=0, out=None, y_coff=0, accumulate=False):
+    def lin_bwd(lin, dY, X, need_dx=True, res=None, x_coff=0, out=None, y_coff=0, accumulate=False, act_grad=None):
         """weight / bias gradient (forked) and the data gradient dX = dY W.  out / y_coff: write dX into a channel slice of a wider
         buffer; accumulate: add to what `out` already holds (in place: the epilogue reads the old tile and stores the sum)"""
         fork_wgrad(lambda: ops.linear_wgrad(dY, X, lin.gw, lin.gb, x_coff=x_coff), dY, X)
@@ -233,7 +243,8 @@ class FlatModule:
         if accumulate:
             assert out is not None and res is None
             return conv_gemm(dY, lin.pwT, bias=False, res=out, res_coff=y_coff, res_mode=RES_AFTER, out=out, y_coff=y_coff)
-        return conv_gemm(dY, lin.pwT, bias=False, res=res, res_mode=RES_AFTER if res is not None else RES_NONE, out=out, y_coff=y_coff)
+        return conv_gemm(dY, lin.pwT, bias=False, res=res, res_mode=RES_AFTER if res is not None else RES_NONE, out=out, y_coff=y_coff,
+                         act_grad=act_grad)
 
     # ------------------------------------------------------------------ optimizer
     def allreduce_grads(self):

@@ -35,7 +35,7 @@ import torch
 from . import ops
 from .engine import shift_mask, sine_table, sine_tables_masked, _compose
 from .ops import ACT_GELU, ACT_SIGMOID, RES_AFTER, PackedWeight, conv_gemm, pack_linear
-from .train_flat import join_wgrads, FlatModule, Linear
+from .train_flat import FUSE_ACT_GRAD, join_wgrads, FlatModule, Linear
 
 PREFIX = "dense_encoder.dense_transformer."
 DIP = "dense_input_proj."
@@ -188,8 +188,10 @@ class LineStage(FlatModule):
             shift = t["shift"]
             fc1, fc2 = blk["mlp"]
             # y = x_new + fc2(gelu(fc1(LN2(x_new))))
-            d_h = self.lin_bwd(fc2, g, t["hmid"])
-            d_hraw = ops.act_bwd(d_h, t["h_raw"], ACT_GELU, from_input=True)
+            if FUSE_ACT_GRAD:
+                d_hraw = self.lin_bwd(fc2, g, t["hmid"], act_grad=(t["h_raw"], ACT_GELU, True, 1.0, 1.0))
+            else:
+                d_hraw = ops.act_bwd(self.lin_bwd(fc2, g, t["hmid"]), t["h_raw"], ACT_GELU, from_input=True)
             d_ln = self.lin_bwd(fc1, d_hraw, t["x_ln"])
             g_new = ops.layernorm_bwd(d_ln, t["x_new"], blk["n2"][0], blk["n2"][2], blk["n2"][3], add=g)
             # x_new = x + unwindow(proj(attention))

@@ -26,7 +26,7 @@ import torch
 from . import ops
 from .engine import shift_mask
 from .ops import ACT_GELU, RES_AFTER, PackedWeight, conv_gemm
-from .train_flat import join_wgrads, FlatModule, Linear
+from .train_flat import FUSE_ACT_GRAD, join_wgrads, FlatModule, Linear
 
 _DEAD = ("attn.diff_mu", "attn.diff_logsigma", "attn.border_mu", "attn.border_logsigma", "attn.proj_seg.weight",
          "attn.proj_seg.bias")
@@ -173,8 +173,10 @@ class ClassStage(FlatModule):
     def _mlp_ln_bwd(self, g, mlp, ln, x_new, x_ln, h_raw, hmid):
         """y = x_new + fc2(gelu(fc1(LN(x_new)))): returns d(x_new)"""
         fc1, fc2 = mlp
-        d_h = self.lin_bwd(fc2, g, hmid)
-        d_hraw = ops.act_bwd(d_h, h_raw, ACT_GELU, from_input=True)
+        if FUSE_ACT_GRAD:        # d(fc1 output) = (g W_fc2) * gelu'(h_raw) in the epilogue of the data-gradient GEMM
+            d_hraw = self.lin_bwd(fc2, g, hmid, act_grad=(h_raw, ACT_GELU, True, 1.0, 1.0))
+        else:
+            d_hraw = ops.act_bwd(self.lin_bwd(fc2, g, hmid), h_raw, ACT_GELU, from_input=True)
         d_ln = self.lin_bwd(fc1, d_hraw, x_ln)
         return ops.layernorm_bwd(d_ln, x_new, ln[0], ln[2], ln[3], add=g)
 

@@ -32,7 +32,10 @@ enum gwd_status {
 };
 
 enum gwd_act { GWD_ACT_NONE = 0, GWD_ACT_RELU = 1, GWD_ACT_GELU = 2, GWD_ACT_ELU = 3, GWD_ACT_SIGMOID = 4 };
-enum gwd_res { GWD_RES_NONE = 0, GWD_RES_BEFORE_NORM = 1, GWD_RES_AFTER = 2 };
+enum gwd_res { GWD_RES_NONE = 0, GWD_RES_BEFORE_NORM = 1, GWD_RES_AFTER = 2,
+               GWD_RES_MUL_ACTGRAD = 3 /* training: `res` is a SAVED ACTIVATION (output, or input with ag_from_input); the result is
+                                          multiplied by d act / d input there and by ag_scale: the activation backward fused into
+                                          the data-gradient GEMM that produces its operand.  No LayerNorm / activation / y_f32. */ };
 
 const char* gwd_last_error(void);
 int gwd_version(void);
@@ -95,6 +98,8 @@ typedef struct gwd_gemm_desc {
   int64_t x_wstride, x_hstride, x_bstride;   /* pixel strides of x along W / H / B in PIXELS (0, 0, 0 = dense [B,H,W]); a
                            stride-2 1x1 projection (ResNet downsample, torchvision Bottleneck) is a Linear over the
                            view x[:, ::2, ::2, :]: H, W = the view's extents, strides = (2, 2*W0, H0*W0).  taps == 1 only. */
+  int32_t ag_act, ag_from_input;             /* GWD_RES_MUL_ACTGRAD: the activation and whether `res` holds its input */
+  float ag_y_mul, ag_scale;                  /* factor = act'(res * ag_y_mul) * ag_scale (0 is read as 1) */
 } gwd_gemm_desc;
 
 int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream);

@@ -192,3 +192,49 @@ def test_linear_on_strided_pixels(B, H, W, K, N):
     assert tuple(out.shape) == tuple(ref.shape)
     err = (out.float().cpu() - ref).abs().max().item()
     assert err <= 2e-2 * max(1.0, ref.abs().max().item()), err      # bf16 output rounding
+
+
+@pytest.mark.parametrize("rows,K,N,act,from_input", [(4800, 256, 2048, 1, False), (40000, 256, 64, 2, True), (9000, 2048, 256, 1, False),
+                                                     (70000, 64, 256, 2, True), (777, 128, 96, 3, False), (5000, 512, 128, 4, False)])
+def test_linear_with_activation_gradient_epilogue(rows, K, N, act, from_input):
+    """res_mode = GWD_RES_MUL_ACTGRAD (training): y = (x W^T) * act'(saved) * scale, the activation backward fused into the
+    data-gradient GEMM, on the TMA-epilogue path (N = 128 / 256 / 2048) and the thread-per-row path (N = 64 / 96)"""
+    ops = _ops()
+    g = torch.Generator().manual_seed(rows + N)
+    x = _rand((rows, K), g).bfloat16()
+    w = _rand((N, K), g, K ** -0.5).bfloat16()
+    saved = _rand((rows, N), g).bfloat16()
+    if act == 4 and not from_input:
+        saved = torch.sigmoid(saved.float()).bfloat16()
+    scale = 1.25
+    acc = x.float() @ w.float().t()
+    sv = saved.float()
+    if from_input:
+        v = sv.clone().requires_grad_(True)
+        {1: torch.relu, 2: F.gelu, 3: F.elu, 4: torch.sigmoid}[act](v).sum().backward()
+        fac = v.grad
+    else:
+        fac = {1: (sv > 0).float(), 3: torch.where(sv > 0, torch.ones_like(sv), sv + 1), 4: sv * (1 - sv)}[act]
+    ref = acc * fac * scale
+    pw = ops.pack_linear(w.cuda(), None)
+    y = ops.conv_gemm(x.cuda(), pw, bias=False, act_grad=(saved.cuda(), act, from_input, 1.0, scale))
+    torch.cuda.synchronize()
+    err = (y.float().cpu()[:, :N] - ref).abs().max().item()
+    assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
+
+
+def test_conv3x3_with_activation_gradient_epilogue():
+    """the same epilogue behind a 3x3 data-gradient convolution, single-CTA and CTA-pair tiles"""
+    ops = _ops()
+    for (B, H, W, C, N) in [(2, 30, 40, 64, 32), (4, 120, 160, 160, 160)]:
+        g = torch.Generator().manual_seed(B + C)
+        x = _rand((B, H, W, C), g).bfloat16()
+        w = _rand((N, C, 3, 3), g, (9 * C) ** -0.5).bfloat16()
+        saved = _rand((B, H, W, N), g).bfloat16()
+        acc = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), None, 1, 1).permute(0, 2, 3, 1)
+        sv = saved.float()
+        ref = acc * torch.where(sv > 0, torch.ones_like(sv), sv + 1)          # ELU' from the output
+        y = ops.conv_gemm(x.cuda(), ops.pack_conv3x3(w.cuda(), None), bias=False, act_grad=(saved.cuda(), 3, False, 1.0, 1.0))
+        torch.cuda.synchronize()
+        err = (y.float().cpu() - ref).abs().max().item()
+        assert err < 2e-2 * max(1.0, ref.abs().max().item()), err
