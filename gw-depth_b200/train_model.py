@@ -59,6 +59,8 @@ class Trainer:
         # the fused step replays its three kernel sequences as CUDA graphs (GWD_CUDA_GRAPH=0: launched kernel by kernel)
         self.use_cuda_graph = os.environ.get("GWD_CUDA_GRAPH", "1") != "0"
         self._graphs = {}
+        self.max_graphs = 6          # captured training steps kept (one memory pool each), least recently used first out
+        self._masks = None
         self.last = {}
 
     # ------------------------------------------------------------------ bookkeeping
@@ -208,9 +210,9 @@ class Trainer:
         """images fp32 [B,3,H,W]; targets: list of {'lines' [T,D], 'labels' [T]} on the device; depth_gt fp32 [B,1,H,W] metres;
         seg_gt int64 [B,1,H,W]; criterion: model.SetCriterion.  Returns (total loss tensor [1] on the device, dict of the 17
         un-weighted losses as the engine logs them)."""
-        if self.use_cuda_graph and not pinned and mask is None:
-            return self._train_step_graphed(images, targets, depth_gt, seg_gt, criterion)
-        pend = {}       # (a ragged batch -- mask given -- runs kernel by kernel: its shapes change from step to step anyway)
+        if self.use_cuda_graph and not pinned:
+            return self._train_step_graphed(images, targets, depth_gt, seg_gt, criterion, mask)
+        pend = {}
         logits, lines, outs = self.forward(images, pinned, mask=mask,
                                            after_line=lambda lo, li: pend.update(h=criterion.matcher.stacked_cost(lo, li, targets)))
         g = self.dense.loss_grads(outs, depth_gt, seg_gt)
@@ -229,33 +231,37 @@ class Trainer:
         return total, losses
 
     # ---- the same step as three CUDA-graph replays around the two host-side pieces (matching costs / assignments)
-    def _forward_line(self, images):
+    def _forward_line(self, images, mask=None):
         c2 = self.backbone.frozen_front(images)
         c3, c4, c5 = self.backbone.forward(c2)
-        logits, lines = self.line.forward(c5)
+        # ragged batch: the level masks are built from the (static) batch mask inside the captured region
+        self._masks = None if mask is None else [level_mask(mask, f.shape[1:3]) for f in (c2, c3, c4, c5)]
+        logits, lines = self.line.forward(c5, None if mask is None else self._masks[3])
         self._c5_shape = c5.shape
         return (c2, c3, c4, c5), logits, lines
 
     def _dense_part(self, feats, logits, lines, depth_gt, seg_gt, H, W):
         c2, c3, c4, c5 = feats
+        m = self._masks
         ref_xy, ids = self.reference_points(logits[-1], lines[-1])
-        x32, depth0 = self.stage32.forward(c5, ref_xy)
-        outs = self.dense.forward(x32, depth0, (c4, c3, c2), H, W)
+        x32, depth0 = self.stage32.forward(c5, ref_xy, None if m is None else m[3])
+        outs = self.dense.forward(x32, depth0, (c4, c3, c2), H, W, pad_masks=None if m is None else (m[2], m[1], m[0]))
         outs.update(line_ids=ids, depth0=depth0)
         self.backward_dense(*self.dense.loss_grads(outs, depth_gt, seg_gt))
         return outs
 
-    def _capture(self, images, depth_gt, seg_gt, criterion, targets):
+    def _capture(self, images, depth_gt, seg_gt, criterion, targets, mask=None):
         B, _, H, W = images.shape
         if H % 32 or W % 32:
             raise NotImplementedError("the training path is built for input sizes that are multiples of 32 (exact x2 pyramids)")
-        st = dict(images=images.float().clone(), depth_gt=depth_gt.clone(), seg_gt=seg_gt.clone())
+        st = dict(images=images.float().clone(), depth_gt=depth_gt.clone(), seg_gt=seg_gt.clone(),
+                  mask=None if mask is None else mask.clone())
         # warm-up (eager, on a side stream): lazy kernel attributes, cached tables, transpose tables
         side = torch.cuda.Stream(device=self.dev)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             self._defer = []
-            feats, lo, li = self._forward_line(st["images"])
+            feats, lo, li = self._forward_line(st["images"], st["mask"])
             self._dense_part(feats, lo, li, st["depth_gt"], st["seg_gt"], H, W)
             _, dlo, dli = criterion.forward_backward_stacked(lo, li, targets)
             self.backward_line(dlo, dli)
@@ -267,9 +273,11 @@ class Trainer:
         n0 = capi.launch_count()          # library kernels enqueued while capturing = library kernels every replay runs
         st["g1"] = torch.cuda.CUDAGraph()
         with torch.cuda.graph(st["g1"]):
-            st["feats"], st["logits"], st["lines"] = self._forward_line(st["images"])
+            st["feats"], st["logits"], st["lines"] = self._forward_line(st["images"], st["mask"])
+        st["masks"] = self._masks            # level masks: outputs of graph 1, read by graph 2
         st["g2"] = torch.cuda.CUDAGraph()
         with torch.cuda.graph(st["g2"], pool=st["g1"].pool()):
+            self._masks = st["masks"]
             st["outs"] = self._dense_part(st["feats"], st["logits"], st["lines"], st["depth_gt"], st["seg_gt"], H, W)
         st["ex2"], self._defer = self._defer, []
         st["dlogits"], st["dlines"] = torch.zeros_like(st["logits"]), torch.zeros_like(st["lines"])
@@ -280,11 +288,17 @@ class Trainer:
         st["kernels_per_replay"] = capi.launch_count() - n0
         return st
 
-    def _train_step_graphed(self, images, targets, depth_gt, seg_gt, criterion):
-        key = (tuple(images.shape), tuple(depth_gt.shape), id(criterion))
-        st = self._graphs.get(key)
+    def _train_step_graphed(self, images, targets, depth_gt, seg_gt, criterion, mask=None):
+        key = (tuple(images.shape), tuple(depth_gt.shape), id(criterion), mask is not None)
+        st = self._graphs.pop(key, None)
         if st is None:
-            st = self._graphs[key] = self._capture(images, depth_gt, seg_gt, criterion, targets)
+            # one memory pool per input shape: a ragged data set cycles through a handful of padded sizes; keep the most recent ones
+            while len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
+            st = self._capture(images, depth_gt, seg_gt, criterion, targets, mask)
+        self._graphs[key] = st               # (re-)inserted last = most recently used
+        if mask is not None:
+            st["mask"].copy_(mask, non_blocking=True)
         self.replayed_kernels = getattr(self, "replayed_kernels", 0) + st["kernels_per_replay"]
         st["images"].copy_(images, non_blocking=True)
         st["depth_gt"].copy_(depth_gt, non_blocking=True)
