@@ -337,6 +337,22 @@ def test_drop_in_training_loop_and_fused_step():
     errs = {n: rel_l2(fused[n], eager[n]) for n in fused if not n.endswith("ref_attn_diffusion.bias")}
     worst = sorted(errs.items(), key=lambda kv: -kv[1])[:5]
     assert worst[0][1] < 1e-2, worst
+    # the same for a RAGGED batch (mask as a static graph input), and a second shape gets its own captured step
+    mask = torch.zeros(B, H, W, dtype=torch.bool)
+    mask[-1, H - 32:, :] = True
+    mask[-1, :, W - 32:] = True
+    im_r = images.masked_fill(mask[:, None], 0.0).cuda()
+    tr_g, tr_k = Trainer(sd), Trainer(sd)
+    tr_k.use_cuda_graph = False
+    tot_g, _ = tr_g.train_step(im_r, tg, depth_gt.cuda(), seg_gt.cuda(), criterions2[0].cuda(), mask=mask.cuda())
+    tot_k, _ = tr_k.train_step(im_r, tg, depth_gt.cuda(), seg_gt.cuda(), criterions2[0].cuda(), mask=mask.cuda())
+    assert abs(float(tot_g) - float(tot_k)) < 1e-4 * abs(float(tot_k)), (float(tot_g), float(tot_k))
+    gg, gk = tr_g.grads(), tr_k.grads()
+    worst = sorted(((rel_l2(gg[n], gk[n]), n) for n in gg if not n.endswith("ref_attn_diffusion.bias")), reverse=True)[:3]
+    assert worst[0][0] < 1e-2, worst
+    assert abs(float(tot_g) - float(total)) > 1e-6 * abs(float(total))            # the mask really entered
+    tr_g.train_step(images.cuda(), tg, depth_gt.cuda(), seg_gt.cuda(), criterions2[0].cuda())      # un-masked: another graph key
+    assert len(tr_g._graphs) == 2
     # parameters moved, and the module can be re-synchronised for evaluation / checkpoints
     net2.sync_from_trainer()
     sd_after = tr.state_dict()
