@@ -60,6 +60,20 @@ WORKLOAD = ("GW-Depth stage-1 ResNet-50 line+depth model, whole-model training s
 FLOP_PER_IMAGE_TRAIN, FLOP_PER_IMAGE_FWD = 1049.5e9, 359.0e9          # SURVEY section 6 (FlopCounterMode over the reference)
 
 
+def _tapgemm_dram():
+    """dram__bytes_read.sum + dram__bytes_write.sum per gwd_tapgemm_kernel launch of one training step, from the committed ncu pass
+    (profiles/r2_tapgemm_dram_train.json, written by tools/summarize_dram.py); None when that capture is absent"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_tapgemm_dram_train.json")) as f:
+            d = json.load(f)
+        return d["dram_bytes_per_launch"], "profiles/r2_tapgemm_dram_train.json (%d launches; %s)" % (d["launches"], d["how"])
+    except (OSError, KeyError, ValueError):
+        return None, None
+
+
+TAPGEMM_DRAM_BYTES_PER_LAUNCH, TAPGEMM_DRAM_SOURCE = _tapgemm_dram()
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -507,25 +521,46 @@ def main():
     roof, breakdown = None, None
     if True:      # every rank runs it (the criterion and the optimizer step contain collectives); rank 0 reports
         im, tg, dg, sg = resident[0]
-        ops.PROFILE = []
-        torch.cuda._sleep(int(0.2 * 1.9e9))       # keep the GPU busy while the host enqueues: events bracket kernels, not launch gaps
-        lo, li, outs = tr.forward(im)
-        g = tr.dense.loss_grads(outs, dg, sg)
-        tr.backward_dense(*g)
-        _, dlo, dli = criterion.forward_backward_stacked(lo, li, tg)
-        tr.backward_line(dlo, dli)
+        # the instrumented pass runs the step's kernels ONE AT A TIME (weight gradients not forked onto the side stream), so that
+        # an event pair brackets one tcgen05 GEMM launch alone, like the per-launch times of the ncu launch list under profiles/;
+        # with the forks on, every GEMM shares the SMs with a concurrent weight gradient and its event time is not its own
+        from gwdepth_b200 import train_flat
+        fork0, train_flat.FORK_WGRAD = train_flat.FORK_WGRAD, False
+        try:
+            ops.PROFILE = []
+            torch.cuda._sleep(int(0.2 * 1.9e9))       # keep the GPU busy while the host enqueues: events bracket kernels, not launch gaps
+            lo, li, outs = tr.forward(im)
+            g = tr.dense.loss_grads(outs, dg, sg)
+            tr.backward_dense(*g)
+            _, dlo, dli = criterion.forward_backward_stacked(lo, li, tg)
+            tr.backward_line(dlo, dli)
+            torch.cuda.synchronize()
+            recs, ops.PROFILE = ops.PROFILE, None
+        finally:
+            train_flat.FORK_WGRAD, ops.PROFILE = fork0, None
+        # what an event pair costs on its own (record, record with nothing in between, behind a busy GPU): subtracted per launch
+        torch.cuda._sleep(int(0.02 * 1.9e9))
+        null = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(200)]
+        for a, b in null:
+            a.record()
+            b.record()
         torch.cuda.synchronize()
-        recs, ops.PROFILE = ops.PROFILE, None
-        tot_ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
+        null_ms = sorted(a.elapsed_time(b) for a, b in null)[len(null) // 2]
+        raw_ms = sum(a.elapsed_time(b) for a, b, _, _ in recs)
+        tot_ms = raw_ms - null_ms * len(recs)
         tot_flop = sum(f for _, _, f, _ in recs)
         big = max(recs, key=lambda r: r[2])
         peak, peak_src = measured_peak()
         ach = tot_flop / (tot_ms / 1000.0) / 1e12
         step_ach = value / world * FLOP_PER_IMAGE_TRAIN / 1e12
         roof = {"bound": "tensor", "kernel": "gwd_tapgemm_kernel (tcgen05 implicit GEMM: the %d forward + data-gradient launches of a step)" % len(recs),
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": TAPGEMM_DRAM_BYTES_PER_LAUNCH,
+                "traffic_source": TAPGEMM_DRAM_SOURCE,
                 "algorithmic_flop_per_launch": tot_flop / len(recs), "peak_source": peak_src, "flop_per_step": tot_flop,
-                "kernel_ms_per_step": tot_ms, "kernel_share_of_step": tot_ms / (ms / steps),
+                "kernel_ms_per_step": tot_ms, "kernel_ms_per_step_raw_events": raw_ms, "event_pair_overhead_us": null_ms * 1000.0,
+                "how": "one CUDA-event pair per launch on the launching stream, kernels of the step run one at a time (no forked weight "
+                       "gradients beside them), the median empty event pair subtracted per launch",
+                "kernel_share_of_step": tot_ms / (ms / steps),
                 "largest_launch": {"desc": big[3], "tflops": big[2] / (big[0].elapsed_time(big[1]) / 1000.0) / 1e12},
                 "step": {"achieved": step_ach, "frac": step_ach / peak, "flop_per_image": FLOP_PER_IMAGE_TRAIN,
                          "what": "whole training step per GPU against the reference's fwd+bwd FLOPs (SURVEY section 6)"}}

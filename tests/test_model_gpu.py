@@ -221,6 +221,58 @@ def test_error_is_bf16_roundoff():
     assert e_cuda < 2.0 * e_emu + 5e-3, (e_cuda, e_emu)
 
 
+def _random_init_state_dict(source, seed=0):
+    """random-init weights, as north_star words the parity bar: `package` = build_model()'s own initialisation (xavier / truncated
+    normal, model._init_parameters), `reference` = the UNMODIFIED reference's build_model() under the same seed (staged copy under
+    baseline/_ref or the mounted tree; skipped where neither exists)"""
+    torch.manual_seed(seed)
+    if source == "package":
+        import gwdepth_b200  # noqa: F401
+        from gwdepth_b200 import model as M
+        net = M.build_model(M.default_args(device="cpu", dropout=0.0))[0]
+        return {k: v.detach().clone() for k, v in net.state_dict().items()}, None
+    import ref_shims
+    if not ref_shims.reference_available():
+        pytest.skip("no copy of the reference on this box")
+    ref_model = ref_shims.build_reference()[0].eval()
+    return {k: v.detach().clone() for k, v in ref_model.state_dict().items()}, ref_model
+
+
+# north_star: "outputs must match the reference PyTorch implementation on the same synthetic inputs and random-init weights: depth
+# within 1e-2 relative in bf16".  With RANDOM-INIT weights (either initialiser) the bf16 path meets that bar; the hash-seeded
+# high-gain weights of the other tests (TOL above) are the harder case and do not.  Stated bounds for the rest: every depth value
+# within 6 % of its reference value, end points within 5e-3 absolute (they live in [0, 1]), logits within 8 % of the largest logit.
+NORTH_STAR = {"depth_mean_rel": 1e-2, "depth_pointwise_max_rel": 6e-2, "lines_abs": 5e-3, "logits_max_rel": 8e-2}
+
+
+@pytest.mark.parametrize("source,B,H,W", [("package", 2, 224, 320), ("package", 1, 480, 640), ("reference", 2, 224, 320)])
+def test_random_init_weights_meet_the_north_star_depth_bar(source, B, H, W):
+    import gwdepth_b200  # noqa: F401
+    from gwdepth_b200 import model as M
+    sd, ref_model = _random_init_state_dict(source)
+    images, _, _, _ = synth.synth_batch(B, H, W, seed=0)
+    trace = {}
+    ref = oracle.forward(sd, images, trace=trace)
+    if ref_model is not None:          # the oracle IS the reference on these weights: compare against the reference's own output
+        with torch.no_grad():
+            theirs = ref_model(images)
+        assert rel(ref["pred_depth"][3], theirs["pred_depth"][3])[1] < 1e-5 and rel(ref["pred_logits"], theirs["pred_logits"])[1] < 1e-4
+        ref = {k: theirs[k] for k in ("pred_logits", "pred_lines", "pred_depth", "pred_seg")}
+    net = M.build_model(M.default_args(device="cuda", dropout=0.0))[0]
+    net.load_state_dict(sd)
+    net.cuda().eval()
+    with torch.no_grad():
+        out = net(images.cuda(), _pinned=pinned_from(trace))
+    for i in range(4):
+        a, b = out["pred_depth"][i].float().cpu().reshape(-1), ref["pred_depth"][i].float().reshape(-1)
+        assert torch.isfinite(a).all()
+        mean_rel = float((a - b).abs().mean() / b.abs().mean())
+        point_rel = float(((a - b).abs() / b.abs().clamp_min(1e-3)).max())
+        assert mean_rel < NORTH_STAR["depth_mean_rel"] and point_rel < NORTH_STAR["depth_pointwise_max_rel"], (i, mean_rel, point_rel)
+    assert float((out["pred_lines"].float().cpu() - ref["pred_lines"]).abs().max()) < NORTH_STAR["lines_abs"]
+    assert rel(out["pred_logits"], ref["pred_logits"])[1] < NORTH_STAR["logits_max_rel"]
+
+
 def test_criterion_on_device_outputs():
     """SetCriterion with the CUDA cost-matrix kernel vs the oracle criterion on the SAME predictions"""
     net, criterions, _ = model()
