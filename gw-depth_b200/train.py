@@ -384,15 +384,20 @@ class LineBranch:
         return dc5
 
     # ------------------------------------------------------------------ optimizer
-    def step(self):
-        """gradient all-reduce (one NCCL call on the flat buffer) + global-norm clip + AdamW + bf16 mirror refresh"""
-        world = parallel.allreduce_sum_(self.G)
+    def step(self, sumsq=None, reduced=False):
+        """gradient all-reduce (one NCCL call on the flat buffer) + global-norm clip + AdamW + bf16 mirror refresh.  Same
+        interface as train_flat.FlatModule.step: `sumsq` (fp64 [1] on the device) = the squared norm over ALL modules of the model
+        when the clip is global (the reference clips the whole model, engine_glassrgbd.py:155-159; train_model.Trainer.step does
+        that), None = this branch's own norm; `reduced` = the gradients have already been exchanged."""
+        world = parallel.world_size() if reduced else parallel.allreduce_sum_(self.G)
         self.t += 1
-        self.sumsq.zero_()
-        ops.sumsq(self.G, self.sumsq)
+        if sumsq is None:
+            self.sumsq.zero_()
+            ops.sumsq(self.G, self.sumsq)
+            sumsq = self.sumsq
         ops.adamw_step(self.P, self.G, self.M, self.V, self.Wb, lr=self.lr, betas=self.betas, eps=self.eps,
                        weight_decay=self.weight_decay, step=self.t, max_norm=self.max_norm, grad_scale=1.0 / world,
-                       sumsq_buf=self.sumsq)
+                       sumsq_buf=sumsq)
 
     # ------------------------------------------------------------------ CUDA graphs
     def _captured(self, c5, producer=None):
