@@ -162,6 +162,11 @@ gwd_attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_
   fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   const uint32_t tmem_o = tmem_base + Lk_pad;   // O accumulator after the S columns
+  // launched programmatically (gwd_launch): the prologue above may have overlapped the tail of the kernel in front; global memory
+  // is touched from here on.  The trigger comes after the TMEM allocation: a dependent that took the columns first would wait for
+  // this kernel while holding them
+  gwd_pdl_wait();
+  gwd_pdl_trigger();
 
   if (warp == 4) {
     if (elect_one()) {
@@ -349,6 +354,8 @@ gwd_attention_flash_tc_kernel(const __grid_constant__ CUtensorMap map_q, const _
   fence_after();
   const uint32_t tmem_s = *tmem_ptr;
   const uint32_t tmem_pv = tmem_s + kKT;
+  gwd_pdl_wait();      // launched programmatically (gwd_launch): global memory is touched from here on
+  gwd_pdl_trigger();   // (after the TMEM allocation: a dependent that got the columns first would wait for this kernel while holding them)
 
   if (warp == 4) {
     if (elect_one()) {
@@ -577,7 +584,7 @@ int gwd_attention_tc_try(const gwd_attn_desc* d, cudaStream_t stream) {
       configured_f = true;
     }
     dim3 gridf(static_cast<unsigned>(gwd_ceil_div(d->Lq, kQTile)), d->heads, d->items);
-    gwd_attention_flash_tc_kernel<<<gridf, 160, smem_f, stream>>>(mq, mk, mv, p);
+    GWD_CUDA(gwd_launch(gwd_attention_flash_tc_kernel, gridf, dim3(160), smem_f, stream, 1, mq, mk, mv, p));
     GWD_LAUNCHED();
     return GWD_OK;
   }
@@ -598,7 +605,7 @@ int gwd_attention_tc_try(const gwd_attn_desc* d, cudaStream_t stream) {
     configured = true;
   }
   dim3 grid(static_cast<unsigned>(gwd_ceil_div(d->Lq, kQTile)), d->heads, d->items);
-  gwd_attention_tc_kernel<<<grid, 160, smem, stream>>>(mq, mk, mv, p);
+  GWD_CUDA(gwd_launch(gwd_attention_tc_kernel, grid, dim3(160), smem, stream, 1, mq, mk, mv, p));
   GWD_LAUNCHED();
   return GWD_OK;
 }

@@ -69,6 +69,7 @@ __device__ __forceinline__ void mma_16816_first(float (&d)[4], const uint32_t (&
 // fold into immediates (the run-time-N version of this kernel executed 2.2x the instructions).
 template <int HD, int kD, int N>
 __global__ void __launch_bounds__(kThreads, 2) gwd_window_attention_kernel(const WinParams p) {
+  gwd_pdl_trigger();   // a programmatically launched dependent may start its prologue (gwd_common.cuh, PDL)
   extern __shared__ __align__(16) uint8_t smraw[];
   constexpr int kRowWords = kD / 2 + 4;
   constexpr int KS = (HD + 15) / 16;     // k-steps of Q K^T
@@ -335,6 +336,7 @@ __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
 // NTC = 8-wide key-channel tiles per head (tc padded to 8 * NTC)
 template <int NTC>
 __global__ void __launch_bounds__(256, 2) gwd_token_attention_mma_kernel(const TokMmaParams p) {
+  gwd_pdl_trigger();   // a programmatically launched dependent may start its prologue (gwd_common.cuh, PDL)
   extern __shared__ __align__(16) uint8_t smraw[];
   constexpr int TCP = 8 * NTC;
   const int N = p.N, heads = p.heads, tc = p.tc;

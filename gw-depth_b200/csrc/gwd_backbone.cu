@@ -13,6 +13,7 @@ namespace {
 typedef __nv_bfloat16 bf16;
 
 __global__ void gwd_im2col3x3_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ col, int B, int H, int W, int ho, int wo, int C8) {
+  gwd_pdl_trigger();   // a programmatically launched dependent may start its prologue (gwd_common.cuh, PDL)
   const int64_t total = static_cast<int64_t>(B) * ho * wo * 9 * C8;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
     const int c = i % C8;

@@ -4,8 +4,15 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
 #include <atomic>
+#include <utility>
 #include "../../include/gwd_b200.h"
+
+#ifndef GWD_PDL_DEFAULT
+#define GWD_PDL_DEFAULT 1
+#endif
 
 // ----------------------------------------------------------------------------------------------
 // host side: error reporting + launch accounting
@@ -45,9 +52,52 @@ int gwd_num_sms();
 static inline int64_t gwd_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ----------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL).  The model is ~500 (forward) / ~1 700 (training step) short kernels replayed from CUDA graphs;
+// a tcgen05 GEMM spends 1-2 us before it touches global memory (kernel parameters, barrier initialisation, tensor-map prefetch, TMEM
+// allocation, one CTA-wide barrier).  Launched with cudaLaunchAttributeProgrammaticStreamSerialization that prologue runs while the
+// kernel in front of it on the stream is still finishing: the front kernel executes gwd_pdl_trigger() (griddepcontrol.
+// launch_dependents) once its CTAs are running, the dependent executes gwd_pdl_wait() (griddepcontrol.wait: returns when the front
+// grid has COMPLETED and its memory operations are visible) before its first global-memory access.  Rules kept by every kernel that
+// is launched through gwd_launch(): nothing is read from or written to global memory ahead of gwd_pdl_wait().  Both instructions
+// are no-ops in a kernel that was launched without the attribute / has no programmatic dependent.  GWD_PDL=0 switches the launch
+// attribute off (the instructions stay, as no-ops).
+// ----------------------------------------------------------------------------------------------
+static inline bool gwd_pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("GWD_PDL"); return e ? atoi(e) != 0 : GWD_PDL_DEFAULT != 0; }();
+  return on;
+}
+
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t gwd_launch(void (*kfn)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                                     Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    at[n].id = cudaLaunchAttributeClusterDimension;
+    at[n].val.clusterDim.x = static_cast<unsigned>(cluster_x); at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (gwd_pdl_enabled()) {
+    at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = at; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kfn, std::forward<Args>(args)...);
+}
+#endif
+
+// ----------------------------------------------------------------------------------------------
 // device side: activations, packing, warp reductions
 // ----------------------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void gwd_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void gwd_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // GELU.  The reference uses the erf form (nn.GELU()); here 0.5 x (1 + tanh(sqrt(2/pi) (x + 0.044715 x^3))) on the MUFU
 // tanh unit: 5 FP instructions + 1 MUFU instead of 15 + 2 for an erf polynomial.  |tanh form - erf form| <= 4.8e-4

@@ -149,6 +149,8 @@ template <int NV>
 __global__ void gwd_layernorm_kernel(const bf16* x, int64_t x_rs, const bf16* res, int64_t res_rs, const float* g,
                                      const float* b, float eps, int act, bf16* out, int64_t out_rs, int64_t rows, int C,
                                      int n) {
+  gwd_pdl_wait();      // launched programmatically (gwd_launch): nothing touches global memory before the kernel in front has completed
+  gwd_pdl_trigger();
   RowGroup rg = row_group(C);
   bool live = rg.row < rows;
   int64_t row = live ? rg.row : 0;
@@ -166,6 +168,8 @@ template <int NV>
 __global__ void gwd_layernorm_g8_kernel(const bf16* x, int64_t x_rs, const bf16* res, int64_t res_rs, const float* g,
                                         const float* b, float eps, int act, bf16* out, int64_t out_rs, int64_t rows, int C,
                                         int n) {
+  gwd_pdl_wait();      // launched programmatically (gwd_launch): nothing touches global memory before the kernel in front has completed
+  gwd_pdl_trigger();
   RowGroup rg;
   const int lane = threadIdx.x & 31;
   rg.G = 8;
@@ -185,6 +189,8 @@ __global__ void gwd_layernorm_g8_kernel(const bf16* x, int64_t x_rs, const bf16*
 template <int NV>
 __global__ void gwd_add_rows_kernel(const bf16* x, int64_t x_rs, const bf16* addend, int64_t a_rs, int64_t period,
                                     bf16* out, int64_t out_rs, int64_t rows, int C) {
+  gwd_pdl_wait();      // launched programmatically (gwd_launch): nothing touches global memory before the kernel in front has completed
+  gwd_pdl_trigger();
   RowGroup rg = row_group(C);
   if (rg.row >= rows) return;
   WarpRow<NV> r;
@@ -205,6 +211,8 @@ struct WinGeom {
 template <int NV>
 __global__ void gwd_window_gather_kernel(const bf16* x, int64_t x_rs, const float* g, const float* b, float eps, bf16* out,
                                          int64_t out_rs, WinGeom gm, int C, int n) {
+  gwd_pdl_wait();      // launched programmatically (gwd_launch): nothing touches global memory before the kernel in front has completed
+  gwd_pdl_trigger();
   RowGroup rg = row_group(C);
   const int xs = static_cast<int>(rg.row), ys = blockIdx.y, bb = blockIdx.z;     // position on the shifted, padded map
   const bool live = xs < gm.Wp;
@@ -234,6 +242,8 @@ template <int NV>
 __global__ void gwd_window_merge_kernel(const bf16* win, int64_t win_rs, const bf16* shortcut, int64_t sc_rs, bf16* out,
                                         int64_t out_rs, const float* g, const float* b, float eps, bf16* out_ln,
                                         int64_t ln_rs, WinGeom gm, int C, int n) {
+  gwd_pdl_wait();      // launched programmatically (gwd_launch): nothing touches global memory before the kernel in front has completed
+  gwd_pdl_trigger();
   RowGroup rg = row_group(C);
   const int x = static_cast<int>(rg.row), y = blockIdx.y, bb = blockIdx.z;
   const bool live = x < gm.W;
@@ -262,6 +272,8 @@ __global__ void gwd_window_merge_kernel(const bf16* win, int64_t win_rs, const b
 // nearest (legacy F.interpolate(mode='nearest'): src = floor(dst * in / out)); optional add of a second same-size map
 __global__ void gwd_upsample_nearest_kernel(const bf16* x, int64_t x_rs, int B, int h, int w, bf16* out, int64_t out_rs,
                                             int H, int W, int C, const bf16* add, int64_t add_rs) {
+  gwd_pdl_wait();      // launched programmatically (gwd_launch): nothing touches global memory before the kernel in front has completed
+  gwd_pdl_trigger();
   // grid (vectors of one output row, rows, images): one division per thread (64-bit div / mod chains made these
   // resampling kernels instruction bound)
   const int cv = C / 8;
@@ -286,6 +298,8 @@ __global__ void gwd_upsample_nearest_kernel(const bf16* x, int64_t x_rs, int B, 
 // nn.AvgPool2d(k, stride=k), floor mode
 __global__ void gwd_avgpool_kernel(const bf16* x, int64_t x_rs, int B, int H, int W, int k, bf16* out, int64_t out_rs,
                                    int C) {
+  gwd_pdl_wait();      // launched programmatically (gwd_launch): nothing touches global memory before the kernel in front has completed
+  gwd_pdl_trigger();
   const int cv = C / 8;
   const int oh = H / k, ow = W / k;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -508,6 +522,7 @@ __global__ void gwd_sample_scalar_kernel(const float* x, int B, int H, int W, co
 // win: [B*nW*N, C] (window layout produced by gwd_window_gather), pos: fp32 [H,W,C] (un-shifted), out bf16 [B,R,C]
 __global__ void gwd_line_ref_gather_kernel(const bf16* win, int64_t win_rs, const float* pos, int64_t pos_bs, const float* coords,
                                            int R, bf16* out, int64_t out_rs, WinGeom gm, int C) {
+  gwd_pdl_trigger();   // a programmatically launched dependent may start its prologue (gwd_common.cuh, PDL)
   int64_t wid = (blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (wid >= static_cast<int64_t>(gm.B) * R) return;
@@ -625,10 +640,11 @@ inline int slots_for(int C) {
 #define GWD_ROW_DISPATCH(KERNEL, C, GRID, STREAM, ...)                                   \
   do {                                                                                  \
     int nv__ = slots_for(C);                                                            \
-    if (nv__ <= 1) KERNEL<1><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__);                    \
-    else if (nv__ <= 2) KERNEL<2><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__);               \
-    else if (nv__ <= 4) KERNEL<4><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__);               \
-    else KERNEL<8><<<GRID, 256, 0, STREAM>>>(__VA_ARGS__);                              \
+    /* every kernel dispatched here starts with gwd_pdl_wait(): programmatic launch (gwd_common.cuh) */ \
+    if (nv__ <= 1) GWD_CUDA(gwd_launch(KERNEL<1>, dim3(GRID), dim3(256), 0, STREAM, 1, __VA_ARGS__));      \
+    else if (nv__ <= 2) GWD_CUDA(gwd_launch(KERNEL<2>, dim3(GRID), dim3(256), 0, STREAM, 1, __VA_ARGS__)); \
+    else if (nv__ <= 4) GWD_CUDA(gwd_launch(KERNEL<4>, dim3(GRID), dim3(256), 0, STREAM, 1, __VA_ARGS__)); \
+    else GWD_CUDA(gwd_launch(KERNEL<8>, dim3(GRID), dim3(256), 0, STREAM, 1, __VA_ARGS__));                \
   } while (0)
 
 int grid_for(int64_t total, int threads) {
@@ -686,8 +702,8 @@ extern "C" int gwd_layernorm(const void* x, int64_t x_rs, const void* res, int64
   if (nv64 == 3 || nv64 == 5 || nv64 == 6 || nv64 == 7) {
     const unsigned grid = static_cast<unsigned>(gwd_ceil_div(gwd_ceil_div(rows, 4) * 32, 256));
 #define GWD_LN_G8(NV)                                                                                                  \
-  gwd_layernorm_g8_kernel<NV><<<grid, 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, static_cast<const bf16*>(res), res_rs, \
-                                                        gamma, beta, eps, act, static_cast<bf16*>(out), out_rs, rows, C, n)
+  GWD_CUDA(gwd_launch(gwd_layernorm_g8_kernel<NV>, dim3(grid), dim3(256), 0, stream, 1, static_cast<const bf16*>(x), x_rs,         \
+                      static_cast<const bf16*>(res), res_rs, gamma, beta, eps, act, static_cast<bf16*>(out), out_rs, rows, C, n))
     if (nv64 == 3) GWD_LN_G8(3);
     else if (nv64 == 5) GWD_LN_G8(5);
     else if (nv64 == 6) GWD_LN_G8(6);
@@ -765,9 +781,9 @@ extern "C" int gwd_upsample_nearest(const void* x, int64_t x_rs, int32_t B, int3
                 "gwd_upsample_nearest: bad argument");
   int64_t total = static_cast<int64_t>(B) * H * W * (C / 8);
   GWD_CHECK_ARG(total > 0 && H <= 65535 && B <= 65535, "gwd_upsample_nearest: bad extents");
-  gwd_upsample_nearest_kernel<<<dim3(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(W) * (C / 8), 256)), H, B), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, h, w,
-                                                                        static_cast<bf16*>(out), out_rs, H, W, C,
-                                                                        static_cast<const bf16*>(add), add_rs);
+  GWD_CUDA(gwd_launch(gwd_upsample_nearest_kernel, dim3(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(W) * (C / 8), 256)), H, B),
+                      dim3(256), 0, stream, 1, static_cast<const bf16*>(x), x_rs, B, h, w, static_cast<bf16*>(out), out_rs, H, W, C,
+                      static_cast<const bf16*>(add), add_rs));
   GWD_LAUNCHED();
   return GWD_OK;
 }
@@ -779,8 +795,8 @@ extern "C" int gwd_avgpool(const void* x, int64_t x_rs, int32_t B, int32_t H, in
                 "gwd_avgpool: bad argument");
   int64_t total = static_cast<int64_t>(B) * (H / k) * (W / k) * (C / 8);
   GWD_CHECK_ARG(total > 0 && H / k <= 65535 && B <= 65535, "gwd_avgpool: bad extents");
-  gwd_avgpool_kernel<<<dim3(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(W / k) * (C / 8), 256)), H / k, B), 256, 0, stream>>>(static_cast<const bf16*>(x), x_rs, B, H, W, k,
-                                                               static_cast<bf16*>(out), out_rs, C);
+  GWD_CUDA(gwd_launch(gwd_avgpool_kernel, dim3(static_cast<unsigned>(gwd_ceil_div(static_cast<int64_t>(W / k) * (C / 8), 256)), H / k, B),
+                      dim3(256), 0, stream, 1, static_cast<const bf16*>(x), x_rs, B, H, W, k, static_cast<bf16*>(out), out_rs, C));
   GWD_LAUNCHED();
   return GWD_OK;
 }

@@ -421,6 +421,9 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
+  // everything above ran on kernel parameters, shared memory and TMEM only: with a programmatic launch it overlapped the tail of
+  // the kernel in front.  From here on global memory is touched (gwd_common.cuh, PDL)
+  gwd_pdl_wait();
   if (HAS_LN) {
     const int cnt = p.phase_n > 0 ? p.phase_n : p.Nt;
     for (int i = threadIdx.x; i < cnt; i += blockDim.x) {
@@ -433,6 +436,9 @@ gwd_tapgemm_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_const
   else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // only now may the next kernel's CTAs come aboard: this CTA (pair) holds its TMEM columns.  A dependent that became resident
+  // earlier could take the columns first and then sit in its griddepcontrol.wait for THIS kernel to finish: a deadlock
+  gwd_pdl_trigger();
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -1169,7 +1175,8 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));                \
       attr_set = true;                                                                                        \
     }                                                                                                         \
-    gwd_tapgemm_kernel<GWD_ACT_NONE, POST, false, true><<<grid, threads, smem_bytes, stream>>>(map_a, map_b, p, map_res, map_y); \
+    GWD_CUDA(gwd_launch(gwd_tapgemm_kernel<GWD_ACT_NONE, POST, false, true>, dim3(grid), dim3(threads), smem_bytes, stream, 1, \
+                        map_a, map_b, p, map_res, map_y));                                                    \
     launched = true;                                                                                          \
   }
 #define GWD_GEMM_CASE(PRE, POST, LN)                                                                          \
@@ -1180,14 +1187,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
       GWD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));           \
       attr_set = true;                                                                                        \
     }                                                                                                         \
-    cudaLaunchConfig_t cfg;                                                                                   \
-    memset(&cfg, 0, sizeof(cfg));                                                                             \
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream; \
-    cudaLaunchAttribute at[1];                                                                                \
-    at[0].id = cudaLaunchAttributeClusterDimension;                                                           \
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;                       \
-    cfg.attrs = at; cfg.numAttrs = 1;                                                                         \
-    GWD_CUDA(cudaLaunchKernelEx(&cfg, kfn, map_a, map_b, p, map_res, map_y));                                 \
+    GWD_CUDA(gwd_launch(kfn, dim3(grid), dim3(threads), smem_bytes, stream, 2, map_a, map_b, p, map_res, map_y)); \
     launched = true;                                                                                          \
   } else if (d->pre_act == PRE && d->post_act == POST && has_ln == LN) {                                      \
     static bool attr_set = false;                                                                             \
@@ -1196,18 +1196,12 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
                                     227 * 1024));                                                             \
       attr_set = true;                                                                                        \
     }                                                                                                         \
-    gwd_tapgemm_kernel<PRE, POST, LN><<<grid, threads, smem_bytes, stream>>>(map_a, map_b, p, map_res, map_y); \
+    GWD_CUDA(gwd_launch(gwd_tapgemm_kernel<PRE, POST, LN>, dim3(grid), dim3(threads), smem_bytes, stream, 1,   \
+                        map_a, map_b, p, map_res, map_y));                                                    \
     launched = true;                                                                                          \
   }
   bool launched = false;
   if (actgrad) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem_bytes; cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = cta2 ? 2 : 1; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
 #define GWD_GEMM_AG(TM, C2)                                                                                          \
   {                                                                                                                  \
     auto kfn = gwd_tapgemm_kernel<GWD_ACT_NONE, GWD_ACT_NONE, false, TM, C2, true>;                                  \
@@ -1216,7 +1210,7 @@ extern "C" int gwd_conv_gemm(const gwd_gemm_desc* d, void* stream_) {
       GWD_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));                  \
       attr_set = true;                                                                                               \
     }                                                                                                                \
-    GWD_CUDA(cudaLaunchKernelEx(&cfg, kfn, map_a, map_b, p, map_res, map_y));                                        \
+    GWD_CUDA(gwd_launch(kfn, dim3(grid), dim3(threads), smem_bytes, stream, C2 ? 2 : 1, map_a, map_b, p, map_res, map_y)); \
   }
     if (tma_ep) GWD_GEMM_AG(true, false)
     else if (cta2) GWD_GEMM_AG(false, true)

@@ -46,6 +46,8 @@ gwd_layernorm_bwd_kernel(const bf16* __restrict__ dy, int64_t dy_rs, const bf16*
                          const bf16* __restrict__ add, int64_t add_rs,
                          bf16* __restrict__ dz, int64_t dz_rs, float* __restrict__ dgamma, float* __restrict__ dbeta,
                          int64_t rows, int C, int n) {
+  gwd_pdl_wait();      // launched programmatically (gwd_launch): nothing touches global memory before the kernel in front has completed
+  gwd_pdl_trigger();
   static_assert(LPR == 32 || NV == 1, "row groups narrower than a warp hold one chunk");
   constexpr int RPW = 32 / LPR;                   // rows per warp and iteration
   __shared__ float part[kLnWarps][NV * 256];
@@ -188,6 +190,8 @@ template <typename TD, typename TY>
 __global__ void gwd_act_bwd_kernel(const TD* __restrict__ dy, int64_t dy_rs, const TY* __restrict__ y, int64_t y_rs, int act,
                                    bf16* __restrict__ out, int64_t out_rs, int64_t rows, int n, int out_cols, float y_mul,
                                    float scale, int from_input) {
+  gwd_pdl_wait();      // launched programmatically (gwd_launch): nothing touches global memory before the kernel in front has completed
+  gwd_pdl_trigger();
   const int64_t total = rows * out_cols;
   for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
@@ -277,6 +281,8 @@ gwd_transpose_batch_kernel(const int64_t* __restrict__ table, const int32_t* __r
 template <int ACT, int FROM_INPUT>
 __global__ void __launch_bounds__(256)
 gwd_act_bwd_vec_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ y, bf16* __restrict__ out, int64_t n8, float y_mul, float scale) {
+  gwd_pdl_wait();      // launched programmatically (gwd_launch): nothing touches global memory before the kernel in front has completed
+  gwd_pdl_trigger();
   const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
   int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
   for (; i + stride < n8; i += 2 * stride) {
@@ -565,6 +571,8 @@ __device__ __forceinline__ void build_key_mask(unsigned long long* sKm, const At
 __device__ __forceinline__ bool key_is_real(const unsigned long long* sKm, int key) { return (sKm[key >> 6] >> (key & 63)) & 1ull; }
 
 __global__ void __launch_bounds__(256) gwd_attention_bwd_mma_kernel(AttnBwdParams p) {
+  gwd_pdl_wait();      // launched programmatically (gwd_launch): nothing touches global memory before the kernel in front has completed
+  gwd_pdl_trigger();
   extern __shared__ __align__(16) uint32_t smem[];
   const int head = blockIdx.x, item = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -957,6 +965,8 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
 }
 
 __global__ void __launch_bounds__(256) gwd_wgrad_kernel(WgradParams p) {
+  gwd_pdl_wait();      // launched programmatically (gwd_launch): nothing touches global memory before the kernel in front has completed
+  gwd_pdl_trigger();
   extern __shared__ __align__(16) uint8_t wsm[];
   bf16* sA = reinterpret_cast<bf16*>(wsm);                          // [stages][32][136]  dY tile
   bf16* sB = sA + kWgStages * kWgR * kWgLd;                         // [stages][32][136]  X tile
@@ -1352,15 +1362,14 @@ extern "C" int gwd_layernorm_bwd(const void* dy, int64_t dy_rs, const void* z, i
                 "gwd_layernorm_bwd: C and strides must be multiples of 8, C <= 512");
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(rows, kLnWarps * 2), 4 * gwd_num_sms()));
   auto launch = [&](auto kern) {
-    kern<<<grid, kLnWarps * 32, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, static_cast<const bf16*>(z), z_rs, gamma, beta,
-                                             post_act, eps,
-                                             static_cast<const bf16*>(add), add_rs, static_cast<bf16*>(dz), dz_rs, dgamma,
-                                             dbeta, rows, C, n);
+    return gwd_launch(kern, dim3(grid), dim3(kLnWarps * 32), 0, stream, 1, static_cast<const bf16*>(dy), dy_rs,
+                      static_cast<const bf16*>(z), z_rs, gamma, beta, post_act, eps, static_cast<const bf16*>(add), add_rs,
+                      static_cast<bf16*>(dz), dz_rs, dgamma, dbeta, rows, C, n);
   };
-  if (C <= 64) launch(gwd_layernorm_bwd_kernel<1, 8>);
-  else if (C <= 128) launch(gwd_layernorm_bwd_kernel<1, 16>);
-  else if (C <= 256) launch(gwd_layernorm_bwd_kernel<1, 32>);
-  else launch(gwd_layernorm_bwd_kernel<2, 32>);
+  if (C <= 64) GWD_CUDA(launch(gwd_layernorm_bwd_kernel<1, 8>));
+  else if (C <= 128) GWD_CUDA(launch(gwd_layernorm_bwd_kernel<1, 16>));
+  else if (C <= 256) GWD_CUDA(launch(gwd_layernorm_bwd_kernel<1, 32>));
+  else GWD_CUDA(launch(gwd_layernorm_bwd_kernel<2, 32>));
   GWD_LAUNCHED();
   return GWD_OK;
 }
@@ -1381,7 +1390,7 @@ extern "C" int gwd_act_bwd(const void* dy, int32_t dy_f32, int64_t dy_rs, const 
     const unsigned g = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(n8, 256), 16 * gwd_num_sms()));
     const bf16* dyp = static_cast<const bf16*>(dy);
     const bf16* yp = static_cast<const bf16*>(y);
-#define GWD_ACT_VEC(A, F) gwd_act_bwd_vec_kernel<A, F><<<g, 256, 0, stream>>>(dyp, yp, o, n8, y_mul, scale)
+#define GWD_ACT_VEC(A, F) GWD_CUDA(gwd_launch(gwd_act_bwd_vec_kernel<A, F>, dim3(g), dim3(256), 0, stream, 1, dyp, yp, o, n8, y_mul, scale))
     const int fi = from_input ? 1 : 0;
     if (act == GWD_ACT_RELU && !fi) GWD_ACT_VEC(GWD_ACT_RELU, 0);
     else if (act == GWD_ACT_RELU) GWD_ACT_VEC(GWD_ACT_RELU, 1);
@@ -1396,13 +1405,13 @@ extern "C" int gwd_act_bwd(const void* dy, int32_t dy_f32, int64_t dy_rs, const 
   }
   const unsigned grid = static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(rows * out_cols, 256), 8 * gwd_num_sms()));
   if (dy_f32 && y_f32)
-    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(dy), dy_rs, static_cast<const float*>(y), y_rs, act, o, out_rs, rows, n, out_cols, y_mul, scale, from_input);
+    GWD_CUDA(gwd_launch(gwd_act_bwd_kernel<float, float>, dim3(grid), dim3(256), 0, stream, 1, static_cast<const float*>(dy), dy_rs, static_cast<const float*>(y), y_rs, act, o, out_rs, rows, n, out_cols, y_mul, scale, from_input));
   else if (dy_f32)
-    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const float*>(dy), dy_rs, static_cast<const bf16*>(y), y_rs, act, o, out_rs, rows, n, out_cols, y_mul, scale, from_input);
+    GWD_CUDA(gwd_launch(gwd_act_bwd_kernel<float, bf16>, dim3(grid), dim3(256), 0, stream, 1, static_cast<const float*>(dy), dy_rs, static_cast<const bf16*>(y), y_rs, act, o, out_rs, rows, n, out_cols, y_mul, scale, from_input));
   else if (y_f32)
-    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, static_cast<const float*>(y), y_rs, act, o, out_rs, rows, n, out_cols, y_mul, scale, from_input);
+    GWD_CUDA(gwd_launch(gwd_act_bwd_kernel<bf16, float>, dim3(grid), dim3(256), 0, stream, 1, static_cast<const bf16*>(dy), dy_rs, static_cast<const float*>(y), y_rs, act, o, out_rs, rows, n, out_cols, y_mul, scale, from_input));
   else
-    gwd_act_bwd_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, static_cast<const bf16*>(y), y_rs, act, o, out_rs, rows, n, out_cols, y_mul, scale, from_input);
+    GWD_CUDA(gwd_launch(gwd_act_bwd_kernel<bf16, bf16>, dim3(grid), dim3(256), 0, stream, 1, static_cast<const bf16*>(dy), dy_rs, static_cast<const bf16*>(y), y_rs, act, o, out_rs, rows, n, out_cols, y_mul, scale, from_input));
   GWD_LAUNCHED();
   return GWD_OK;
 }
@@ -1479,7 +1488,7 @@ extern "C" int gwd_attention_bwd(const gwd_attn_bwd_desc* d, void* stream_) {
     const size_t sm = static_cast<size_t>(2 * p.Lq_pad + 2 * p.Lk_pad) * kMW * 4 + static_cast<size_t>(2 * p.Lq_pad) * 4 +
                       static_cast<size_t>(p.Lk_pad / 64) * 8;
     GWD_CUDA(cudaFuncSetAttribute(gwd_attention_bwd_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sm)));
-    gwd_attention_bwd_mma_kernel<<<grid, 256, sm, stream>>>(p);
+    GWD_CUDA(gwd_launch(gwd_attention_bwd_mma_kernel, grid, dim3(256), sm, stream, 1, p));
     GWD_LAUNCHED();
     return GWD_OK;
   }
@@ -1540,6 +1549,8 @@ namespace {
 // by shuffles, the 8 warps in shared memory, one atomic per column and CTA.
 __global__ void __launch_bounds__(256) gwd_colsum_kernel(const bf16* __restrict__ dy, int64_t dy_rs, int64_t rows, int N, int lpr,
                                                          float* __restrict__ db) {
+  gwd_pdl_wait();      // launched programmatically (gwd_launch): nothing touches global memory before the kernel in front has completed
+  gwd_pdl_trigger();
   __shared__ float red[8][32][8];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cv = lane & (lpr - 1), sub = lane / lpr, rpw = 32 / lpr;
@@ -1597,7 +1608,7 @@ extern "C" int gwd_linear_wgrad(const void* dy, int64_t dy_rs, const void* x, in
         while (lpr < 32 && lpr * 8 < N) lpr <<= 1;
         const dim3 grid(static_cast<unsigned>(gwd_ceil_div(N, 256)),
                         static_cast<unsigned>(std::min<int64_t>(gwd_ceil_div(rows, 64 * (32 / lpr)), 2 * gwd_num_sms())));
-        gwd_colsum_kernel<<<grid, 256, 0, stream>>>(static_cast<const bf16*>(dy), dy_rs, rows, N, lpr, db);
+        GWD_CUDA(gwd_launch(gwd_colsum_kernel, grid, dim3(256), 0, stream, 1, static_cast<const bf16*>(dy), dy_rs, rows, N, lpr, db));
         GWD_LAUNCHED();
       }
       return GWD_OK;
@@ -1660,7 +1671,7 @@ static int launch_wgrad(const void* dy, int64_t dy_rs, const void* x, int64_t x_
   const size_t smem = static_cast<size_t>(2) * kWgStages * kWgR * kWgLd * sizeof(bf16);
   GWD_CUDA(cudaFuncSetAttribute(gwd_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(static_cast<unsigned>(gwd_ceil_div(N, kWgT)), static_cast<unsigned>(gwd_ceil_div(K, kWgT)), static_cast<unsigned>(split));
-  gwd_wgrad_kernel<<<grid, 256, smem, stream>>>(p);
+  GWD_CUDA(gwd_launch(gwd_wgrad_kernel, grid, dim3(256), smem, stream, 1, p));
   GWD_LAUNCHED();
   return GWD_OK;
 }

@@ -169,6 +169,11 @@ gwd_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_m, const __grid_cons
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // launched programmatically (gwd_launch): everything above used kernel parameters, shared memory and TMEM only and may have
+  // overlapped the tail of the kernel in front; global memory is touched from here on.  The trigger comes after the TMEM
+  // allocation (a dependent that took the columns first would sit in its wait for this kernel while holding them)
+  gwd_pdl_wait();
+  gwd_pdl_trigger();
 
   if (warp == 4) {
     if (elect_one()) {
@@ -343,7 +348,7 @@ static int launch_tc(WgTcParams& p, const void* dy, int64_t dy_cs, const void* x
     attr_set = true;
   }
   const unsigned grid = static_cast<unsigned>(units * splits);
-  gwd_wgrad_tc_kernel<<<grid, 192, smem, stream>>>(p.m_is_x ? map_x : map_dy, p.m_is_x ? map_dy : map_x, p);
+  GWD_CUDA(gwd_launch(gwd_wgrad_tc_kernel, dim3(grid), dim3(192), smem, stream, 1, p.m_is_x ? map_x : map_dy, p.m_is_x ? map_dy : map_x, p));
   GWD_LAUNCHED();
   return GWD_OK;
 }
