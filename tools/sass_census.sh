@@ -1,13 +1,13 @@
 #!/bin/bash
 # SASS opcode census of libgwd_b200.so: proves which kernels are tcgen05 / TMEM / TMA (UTCHMMA, LDTM, UTMALDG, UTMASTG, UTCBAR)
-# and which run on warp-level MMA (HMMA).  Usage: tools/sass_census.sh > profiles/rNN_sass_census.txt
+# and which run on warp-level MMA (HMMA); ACQBULK / PREEXIT = griddepcontrol.wait / launch_dependents (programmatic dependent launch).  Usage: tools/sass_census.sh > profiles/rNN_sass_census.txt
 set -e
 LIB="$(dirname "$0")/../gw-depth_b200/libgwd_b200.so"
 TMP=$(mktemp)
 cuobjdump -sass "$LIB" > "$TMP"
 echo "# $(basename "$LIB") $(stat -c %s "$LIB") bytes, $(grep -c 'Function :' "$TMP") kernels"
 echo "# whole library"
-for op in UTCHMMA UTCQMMA UTCOMMA LDTM STTM UTMALDG UTMASTG UTMAPF UTCBAR UTCCP SYNCS HMMA; do
+for op in UTCHMMA UTCQMMA UTCOMMA LDTM STTM UTMALDG UTMASTG UTMAPF UTCBAR UTCCP SYNCS HMMA ACQBULK PREEXIT; do
   printf "%-8s %d\n" $op "$(grep -c "^ *\/\*[0-9a-f]*\*\/ *\(@!\?U\?P[0-9T]* \)\?$op" "$TMP" || true)"
 done
 echo "# per kernel (only kernels with tensor-core or TMA instructions)"
