@@ -9,8 +9,9 @@ units) and on the full-resolution depth (weight 1), SegLoss x 2.  The uncertaint
 selection: the sample coordinates carry no gradient; the ANCHOR depths sampled at them do (into the previous scale's depth).
 
 This module only orchestrates the stage modules (train_entry, train_swin, train_points, train_tail); every kernel runs
-through the C ABI.  What it returns for the parts that are not built yet: d(x32) (the line-window stage at 1/32) and
-d(C4), d(C3) (the backbone; C2 comes from the frozen layer1 and needs no gradient).
+through the C ABI.  `backward` returns what the modules in front of it continue with: d(x32) (train_line_stage.LineStage, the
+line-window stage at 1/32) and d(C4), d(C3) (train_backbone.BackboneTrain; C2 comes from the frozen layer1 and needs no gradient);
+train_model.Trainer joins them into the whole-model step.
 """
 import torch
 
