@@ -20,8 +20,10 @@ global clip norm, AdamW.  A step = one such iteration on one batch of 8 syntheti
   forward   : BASELINE configs[1] -- inference forward, batch 16 per GPU (round 1's headline) -- device-resident and end to end
   gpu_eager_reference : the UNMODIFIED reference (staged under baseline/_ref by oracle/stage_ref.sh) as eager fp32 PyTorch on the
               same GPU: forward at batch 16 (the 10x denominator of north_star) and the training step at batch 8
-  cpu_baseline : the CPU oracle (oracle/gwdepth_oracle.py) forward + backward under torch.autograd on the host cores
-The reference arm (--impl reference) times that CPU oracle training pass, 1 image per step (a bounded sample of the 8-image batch).
+  cpu_baseline : the UNMODIFIED reference's own training step on the host cores (all threads, fp32; kind "reference") when its staged
+              copy is present, else the CPU oracle's training pass (oracle/gwdepth_oracle.py under torch.autograd; kind "port");
+              a bounded sample: 1 image of the 8-image batch per step
+The reference arm (--impl reference) times the same thing for --steps steps and prints it as its own line.
 """
 import argparse
 import json
@@ -164,26 +166,51 @@ def cpu_setup():
     return leaves, synth.synth_batch(1, H, W, seed=0), wd
 
 
+def cpu_stepper():
+    """-> (step callable, kind, description): ONE image of the training batch per call on the host cores, all threads, fp32.  With a
+    copy of the reference at hand (baseline/_ref, or the mounted tree in the build container) the UNMODIFIED reference's own training
+    step (`kind` = "reference"); otherwise the oracle port's training pass (`kind` = "port")."""
+    _checker_paths()
+    use_all_host_threads()
+    try:
+        import ref_shims
+        if ref_shims.reference_available():
+            from helpers import synth_weights
+            model, criterions, _, _ = ref_shims.build_reference(["--device", "cpu", "--dropout", "0.0"])
+            model.load_state_dict(synth_weights(), strict=True)
+            step, _opt = reference_train_step(model, criterions, torch.device("cpu"), 1)
+            step()              # (a first, un-timed step inside the guard: whatever goes wrong here falls back to the port)
+            return step, "reference", ("training steps of 1x3x480x640 (1/8 of a step) through the UNMODIFIED reference (baseline/_ref: model, "
+                                       "SetCriterion + Hungarian matcher, SilogLoss x 4, SegLoss, backward, clip_grad_norm_, torch AdamW), "
+                                       "eager fp32 on the host cores")
+    except Exception as e:  # noqa: BLE001  (the CPU figure must always be there: fall back to the port)
+        sys.stderr.write("cpu baseline: the staged reference did not run (%r); timing the oracle port instead\n" % (e,))
+    leaves, batch, wd = cpu_setup()
+    return (lambda: cpu_train_pass(leaves, batch, wd)), "port", ("training passes (forward + 17 losses + backward, no optimizer step) of "
+                                                                 "1x3x480x640 (1/8 of a step) through oracle/gwdepth_oracle.py under torch.autograd")
+
+
 def run_reference(args, rank):
-    """the reference arm: the CPU oracle's training pass (forward + losses + backward, torch.autograd), all host threads, rank 0
-    only; every step is ONE image of the 8-image batch (a bounded sample: the full batch takes ~8x as long)"""
+    """the reference arm, rank 0 only, all host threads, fp32, CPU.  With the staged copy of the reference (baseline/_ref, or the
+    mounted tree in the build container): the UNMODIFIED reference's own training step -- its model, criteria, clip and AdamW -- on
+    the host cores (`kind` = "reference").  Without it: the oracle port's training pass (forward + 17 losses + backward under
+    torch.autograd, `kind` = "port").  Every step is ONE image of the 8-image batch (a bounded sample: the full batch takes ~8x as
+    long), reported as a per-image rate."""
     if rank != 0:
         return
-    leaves, batch, wd = cpu_setup()
+    step, kind, what = cpu_stepper()
     for _ in range(min(args.warmup, 1)):
-        cpu_train_pass(leaves, batch, wd)
+        step()
     t0 = time.time()
     for _ in range(args.steps):
-        cpu_train_pass(leaves, batch, wd)
+        step()
     dt = time.time() - t0
     v = args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "sample": "1 image of the 8-image batch per step, forward + 17 losses + backward on the CPU "
-                       "(no optimizer step); per-image rate"},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                             "sample": "%d training passes of 1x3x480x640 through oracle/gwdepth_oracle.py under torch.autograd" % args.steps},
+            "config": {"workload": WORKLOAD, "sample": "1 image of the 8-image batch per step on the CPU; per-image rate"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind, "sample": "%d %s" % (args.steps, what)},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -307,6 +334,41 @@ def data_path_rate(dev, n=48):
     return out
 
 
+def reference_train_step(model, criterions, dev, batch):
+    """one training step of the UNMODIFIED reference as src/engine_glassrgbd.py:45-166 runs it (its own model, SetCriterion /
+    SilogLoss / SegLoss, clip_grad_norm_ 0.1, torch AdamW with the two learning rates of src/main_glassrgbd.py:53-67) on a synthetic
+    batch of `batch` images resident on `dev`; returns (step callable, optimizer)"""
+    _checker_paths()
+    from helpers import synth
+    import torch.nn.functional as F
+    model.train()
+    crit, crit_d, crit_s = criterions[0].to(dev), criterions[1], criterions[2]
+    crit.train()
+    opt = torch.optim.AdamW([{"params": [p for n, p in model.named_parameters() if "backbone" not in n and p.requires_grad]},
+                             {"params": [p for n, p in model.named_parameters() if "backbone" in n and p.requires_grad], "lr": 1e-5}],
+                            lr=1e-4, weight_decay=1e-4)
+    imgs, targets, depth_gt, seg_gt = synth.synth_batch(batch, H, W, seed=100)
+    imgs, depth_gt, seg_gt = imgs.to(dev), depth_gt.to(dev), seg_gt.to(dev)
+    targets = [{k: v.to(dev) for k, v in t.items()} for t in targets]
+
+    def step():
+        out = model(imgs)
+        ld = crit(out, targets)
+        loss = sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict)
+        mask = (depth_gt >= 0.2) & (depth_gt < 10.0)
+        for i, pd in enumerate(out["pred_depth"]):
+            sz = pd.shape[-2:]
+            loss = loss + crit_d(pd, F.interpolate(depth_gt, size=sz, mode="nearest"),
+                                 F.interpolate(mask.to(torch.uint8), size=sz, mode="nearest").to(torch.bool)) * (0.25, 0.25, 0.25, 1.0)[i]
+        loss = loss + crit_s(out["pred_seg"], seg_gt.squeeze(1)) * 2.0
+        opt.zero_grad()
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
+        opt.step()
+        return loss.detach()          # (no host read here: the GPU leg must not synchronise per step)
+    return step, opt
+
+
 def gpu_eager_reference(dev, n_fwd=30, n_train=10):
     """the unmodified reference on this GPU, eager fp32, as shipped (no AMP / TF32 override / cudnn.benchmark): forward at batch 16
     (north_star's 10x denominator) and one training step at batch 8 (its own criteria, AdamW, clip)"""
@@ -333,31 +395,7 @@ def gpu_eager_reference(dev, n_fwd=30, n_train=10):
             torch.cuda.synchronize()
         res["forward_b16"] = {"value": n_fwd * FWD_BATCH / (e0.elapsed_time(e1) / 1000.0), "unit": UNIT, "ms_per_step": e0.elapsed_time(e1) / n_fwd}
         # training step, batch 8
-        import torch.nn.functional as F
-        model.train()
-        crit, crit_d, crit_s = criterions[0].to(dev), criterions[1], criterions[2]
-        crit.train()
-        opt = torch.optim.AdamW([{"params": [p for n, p in model.named_parameters() if "backbone" not in n and p.requires_grad]},
-                                 {"params": [p for n, p in model.named_parameters() if "backbone" in n and p.requires_grad], "lr": 1e-5}],
-                                lr=1e-4, weight_decay=1e-4)
-        imgs, targets, depth_gt, seg_gt = synth.synth_batch(TRAIN_BATCH, H, W, seed=100)
-        imgs, depth_gt, seg_gt = imgs.to(dev), depth_gt.to(dev), seg_gt.to(dev)
-        targets = [{k: v.to(dev) for k, v in t.items()} for t in targets]
-
-        def step():
-            out = model(imgs)
-            ld = crit(out, targets)
-            loss = sum(ld[k] * crit.weight_dict[k] for k in ld if k in crit.weight_dict)
-            mask = (depth_gt >= 0.2) & (depth_gt < 10.0)
-            for i, pd in enumerate(out["pred_depth"]):
-                sz = pd.shape[-2:]
-                loss = loss + crit_d(pd, F.interpolate(depth_gt, size=sz, mode="nearest"),
-                                     F.interpolate(mask.to(torch.uint8), size=sz, mode="nearest").to(torch.bool)) * (0.25, 0.25, 0.25, 1.0)[i]
-            loss = loss + crit_s(out["pred_seg"], seg_gt.squeeze(1)) * 2.0
-            opt.zero_grad()
-            loss.backward()
-            torch.nn.utils.clip_grad_norm_(model.parameters(), 0.1)
-            opt.step()
+        step, opt = reference_train_step(model, criterions, dev, TRAIN_BATCH)
         for _ in range(3):
             step()
         torch.cuda.synchronize()
@@ -650,14 +688,14 @@ def main():
             if isinstance(eager.get("train_b8"), dict):
                 eager["train_speedup"] = value / eager["train_b8"]["value"]
         if not args.no_cpu_baseline:
-            leaves, batch, wd = cpu_setup()
-            cpu_train_pass(leaves, batch, wd)
+            cpu_step, cpu_kind, cpu_what = cpu_stepper()
+            cpu_step()
             t0, n = time.time(), 0
             while n < 2 or (time.time() - t0 < 20.0 and n < 6):
-                cpu_train_pass(leaves, batch, wd)
+                cpu_step()
                 n += 1
-            cpu = {"value": n / (time.time() - t0), "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                   "sample": "%d training passes (forward + 17 losses + backward) of 1x3x480x640 (1/8 of a step) through oracle/gwdepth_oracle.py" % n}
+            cpu = {"value": n / (time.time() - t0), "unit": UNIT, "cores": torch.get_num_threads(), "kind": cpu_kind,
+                   "sample": "%d %s" % (n, cpu_what)}
     data_path, attention = None, None
     if world == 1 and not args.no_data_path:
         data_path = data_path_rate(dev)
