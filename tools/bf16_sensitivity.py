@@ -8,7 +8,23 @@ from helpers import oracle, synth, synth_weights
 
 B, H, W = 1, int(os.environ.get("H", 224)), int(os.environ.get("W", 320))
 images, _, _, _ = synth.synth_batch(B, H, W, seed=0)
-sd = synth_weights()
+# WEIGHTS=synth (default): the hash-seeded high-gain weights of the test-suite; WEIGHTS=package / reference: RANDOM-INIT weights from
+# this package's build_model() / the unmodified reference's build_model() under torch.manual_seed(0) -- the configuration north_star
+# words its 1e-2 bar on (0.36 % / 0.42 % mean-rel for "weights + activations everywhere")
+WEIGHTS = os.environ.get("WEIGHTS", "synth")
+if WEIGHTS == "synth":
+    sd = synth_weights()
+else:
+    torch.manual_seed(0)
+    if WEIGHTS == "package":
+        import gwdepth_b200  # noqa: F401
+        from gwdepth_b200 import model as M
+        net = M.build_model(M.default_args(device="cpu", dropout=0.0))[0]
+    else:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import ref_shims
+        net = ref_shims.build_reference()[0]
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
 trace = {}
 ref = oracle.forward(sd, images, trace=trace)
 pin = {"line_ids": trace["line_ids"], "sample1": (trace["sample1"], trace["sample1_idx"]), "sample2": (trace["sample2"], trace["sample2_idx"])}
